@@ -1,0 +1,92 @@
+"""Build recipes for the native pieces (in-tree, so the built .so files travel with the snapshot).
+
+* libdabstar_b200.so  -- the product: CUDA kernels + C-ABI (nvcc, sm_100a only)
+* libdab_synth.so     -- bundled synthetic Mode-I transmitter (gcc + OpenMP), a test-signal source
+* oracle/libdab_oracle.so and oracle/_ref/libdabref.so -- test infrastructure (see oracle/)
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_CUDA = os.path.join(PKG_DIR, "libdabstar_b200.so")
+LIB_SYNTH = os.path.join(PKG_DIR, "libdab_synth.so")
+LIB_ORACLE = os.path.join(REPO, "oracle", "libdab_oracle.so")
+LIB_REF = os.path.join(REPO, "oracle", "_ref", "libdabref.so")
+REFERENCE_ROOT = "/root/reference"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--use_fast_math" if False else "-DDABSTAR_NO_FAST_MATH",  # IEEE division/sqrt: parity with the float reference matters
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-shared", "-cudart", "shared",
+]
+
+
+def _newer(target: str, sources: list[str]) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _run(cmd: list[str], cwd: str | None = None) -> None:
+    r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("build failed: " + " ".join(cmd))
+
+
+def cuda_sources() -> list[str]:
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def build_cuda(force: bool = False, verbose_ptxas: bool = False) -> str:
+    srcs = cuda_sources()
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps.append(os.path.join(REPO, "include", "dabstar_b200.h"))
+    if not force and _newer(LIB_CUDA, deps):
+        return LIB_CUDA
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose_ptxas else []) + ["-I", os.path.join(REPO, "include"), "-I", CSRC, "-o", LIB_CUDA] + srcs
+    _run(cmd)
+    return LIB_CUDA
+
+
+def build_synth(force: bool = False) -> str:
+    src = os.path.join(PKG_DIR, "synth", "dab_synth.c")
+    if not force and _newer(LIB_SYNTH, [src]):
+        return LIB_SYNTH
+    _run(["gcc", "-std=gnu11", "-O2", "-fPIC", "-fopenmp", "-shared", "-o", LIB_SYNTH, src, "-lm"])
+    return LIB_SYNTH
+
+
+def build_oracle(force: bool = False) -> str:
+    odir = os.path.join(REPO, "oracle")
+    if force or not _newer(LIB_ORACLE, [os.path.join(odir, "dab_oracle.c"), os.path.join(odir, "dab_oracle.h")]):
+        _run(["make", "-C", odir, "-B" if force else "-s", "libdab_oracle.so"])
+    return LIB_ORACLE
+
+
+def build_ref(force: bool = False) -> str | None:
+    """oracle/_ref from the reference's own sources; only possible where /root/reference exists."""
+    if not os.path.isdir(REFERENCE_ROOT):
+        return LIB_REF if os.path.exists(LIB_REF) else None
+    _run(["make", "-C", os.path.join(REPO, "oracle", "ref_build"), "-j8"] + (["-B"] if force else []))
+    return LIB_REF
+
+
+def build_all(force: bool = False) -> None:
+    build_cuda(force)
+    build_synth(force)
+    build_oracle(force)
+    build_ref(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv)
+    print("built:", LIB_CUDA, LIB_SYNTH, LIB_ORACLE, LIB_REF if os.path.exists(LIB_REF) else "(no oracle/_ref)")

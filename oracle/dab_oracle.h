@@ -1,0 +1,107 @@
+/* dab_oracle — CPU restatement of the reference's DAB Mode-I hot path (TEST INFRASTRUCTURE).
+ *
+ * Plain C, single threaded, written from the reference's behaviour (each function cites the
+ * file:line under /root/reference/src it follows). It exists so the CUDA path can be checked on a
+ * box where /root/reference does not exist. It is pinned against the reference itself
+ * (oracle/_ref/libdabref.so, the unmodified reference sources) by tests/test_oracle_vs_ref.py and
+ * against committed vectors in tests/golden/ that were generated from oracle/_ref.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may load this library.
+ * The product (dabstar_b200/) never does.
+ *
+ * The entry points mirror oracle/ref_build/dabref.h one to one (prefix dabo_ instead of dabref_)
+ * so the same test code can drive either library.
+ */
+#pragma once
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* tables */
+void dabo_freq_interleaver(int16_t out[1536]);
+void dabo_phase_table(float out_re_im[4096]);
+void dabo_fft2048(const float * in, float * out, int sign);
+void dabo_prbs(uint8_t * out, int n);                       /* energy dispersal sequence */
+int  dabo_fic_addresses(int32_t * addr, int cap);           /* FIC depuncture map, returns 2304 */
+
+/* sample formats (raw_reader.cpp:66-70,155-158; xml_reader.cpp:254-372) */
+void dabo_convert_u8(const uint8_t * in, float * out_re_im, int64_t n_samples);
+void dabo_convert_i16(const int16_t * in, float * out_re_im, int64_t n_samples);
+
+/* channel decoding */
+void dabo_viterbi(const int16_t * in, int frame_bits, uint8_t * out);
+void dabo_viterbi_ber(const int16_t * in, const uint8_t * punct, const uint8_t * out_bits, int frame_bits, int * bits, int * errors);
+int  dabo_protection(int short_form, int bit_rate, int prot_level, const int16_t * in, int in_len, uint8_t * out);
+int  dabo_protection_addresses(int short_form, int bit_rate, int prot_level, int32_t * addr, int cap);
+int  dabo_check_crc_bits(const uint8_t * bits, int n);
+uint16_t dabo_calc_crc(const uint8_t * bytes, int n);
+
+void * dabo_fic_new(void);
+void   dabo_fic_free(void * h);
+void   dabo_fic_process_block(void * h, const int16_t * soft3072, int sym_idx);
+void   dabo_fic_get(void * h, uint8_t bits[3072], uint8_t valid[4], int * ratio_percent, int * ber_bits, int * ber_errors);
+
+void * dabo_backend_new(int sub_ch_id, int start_cu, int size_cu, int short_form, int prot_level, int bit_rate);
+void   dabo_backend_free(void * h);
+int    dabo_backend_process(void * h, const int16_t * fragment, uint8_t * out);
+
+/* OFDM */
+void * dabo_ofdm_new(int soft_bit_type);
+void   dabo_ofdm_free(void * h);
+void   dabo_ofdm_reset(void * h);
+void   dabo_ofdm_store_reference_symbol_0(void * h, const float * fft);
+void   dabo_ofdm_store_null_symbol_without_tii(void * h, const float * fft);
+void   dabo_ofdm_decode_symbol(void * h, const float * fft, int sym_idx, float phase_corr, float clock_err, int16_t * out3072);
+void   dabo_ofdm_get_state(void * h, int which, float * out);
+
+void * dabo_phaseref_new(void);
+void   dabo_phaseref_free(void * h);
+int    dabo_phaseref_correlate(void * h, const float * samples2048, float threshold, int strongest_peak);
+int    dabo_phaseref_estimate_offset(void * h, const float * fft2048);
+
+/* whole chain (DabProcessor::run, dab_processor.cpp:110-189) */
+typedef struct
+{
+  int   soft_bit_type;
+  float threshold;
+  int   strongest_peak;
+  int   scan_mode;
+  int   tap_soft_bits;
+  int   tap_fft;
+  int   n_subch;
+  const int32_t * subch;     /* n_subch x 7: subChId,startCU,sizeCU,shortForm,protLevel,bitRate,startFrame */
+  const char * eti_path;     /* ignored by the restatement (ETI framing is out of scope) */
+} dabo_chain_cfg;
+
+typedef struct
+{
+  int64_t sym0_pos;
+  int32_t start_index;
+  float   fbb_sym0;
+  float   fbb_data;
+  float   fbb_null;
+  float   fsync;
+  float   phase_cp;
+  float   clock_err;
+  int32_t fic_ratio_before;
+  int32_t fic_ratio_after;
+  uint8_t fic_valid[4];
+} dabo_frame_info;
+
+void *  dabo_chain_run(const float * iq_re_im, int64_t n_samples, const dabo_chain_cfg * cfg);
+void    dabo_chain_free(void * h);
+int     dabo_chain_n_frames(void * h);
+void    dabo_chain_frame_info(void * h, int frame, dabo_frame_info * out);
+void    dabo_chain_fib_bits(void * h, int frame, uint8_t out[3072]);
+int     dabo_chain_soft_bits(void * h, int frame, int16_t * out);
+int     dabo_chain_fft(void * h, int frame, float * out);
+int     dabo_chain_n_good_fibs(void * h);
+int64_t dabo_chain_msc_size(void * h, int sub_ch_id);
+int64_t dabo_chain_msc_copy(void * h, int sub_ch_id, uint8_t * out, int64_t cap);
+void    dabo_chain_counters(void * h, int64_t out[8]);
+double  dabo_chain_seconds(void * h);
+
+#ifdef __cplusplus
+}
+#endif

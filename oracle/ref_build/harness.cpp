@@ -158,9 +158,12 @@ extern "C" int dabref_backend_process(void * h, const int16_t * fragment, uint8_
 }
 
 // ------------------------------------------------------------------------------------------------ OFDM
+static RingBuffer<cf32> gIqRing{ 2 * 1536 };
+static RingBuffer<f32> gCarrRing{ 2 * 1536 };
+
 extern "C" void * dabref_ofdm_new(int soft_bit_type)
 {
-  auto * d = new OfdmDecoder(&gRadio, nullptr, nullptr);
+  auto * d = new OfdmDecoder(&gRadio, &gIqRing, &gCarrRing);
   d->set_soft_bit_gen_type((ESoftBitType)soft_bit_type);
   return d;
 }
@@ -264,6 +267,8 @@ struct ChainRun : Hooks
   dabref_chain_cfg cfg{};
   std::unique_ptr<MemoryDevice> dev;
   ProcessParams params;
+  RingBuffer<cf32> iqRing{ 2 * 1536 };   // scope outputs of OfdmDecoder::decode_symbol (ofdm_decoder.cpp:320-321) need a sink
+  RingBuffer<f32> carrRing{ 2 * 1536 };
   std::unique_ptr<DabProcessor> proc;
   std::vector<FrameRec> frames;
   std::map<int, std::vector<u8>> msc;
@@ -302,7 +307,7 @@ struct ChainRun : Hooks
 
   void before_fft(fftwf_plan p) override
   {
-    if (p != proc->mFftPlan) return;
+    if (!proc || p != proc->mFftPlan) return;
     if (fftInFrame == 0)
     {
       frames.emplace_back();
@@ -323,7 +328,7 @@ struct ChainRun : Hooks
 
   void after_fft(fftwf_plan p, const float * out) override
   {
-    if (p != proc->mFftPlan) return;
+    if (!proc || p != proc->mFftPlan) return;
     if (cfg.tap_fft && !frames.empty())
     {
       auto & f = frames.back();
@@ -367,6 +372,8 @@ extern "C" void * dabref_chain_run(const float * iq, int64_t n_samples, const da
   }
   c->params.threshold = cfg->threshold;
   c->params.tiiFramesToCount = 5;
+  c->params.iqBuffer = &c->iqRing;
+  c->params.carrBuffer = &c->carrRing;
   c->dev = std::make_unique<MemoryDevice>(reinterpret_cast<const cf32 *>(iq), n_samples);
   ScopedHooks s(c);
   c->proc = std::make_unique<DabProcessor>(&gRadio, c->dev.get(), &c->params);

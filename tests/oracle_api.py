@@ -1,0 +1,240 @@
+"""ctypes front end shared by the two CPU checkers (TEST INFRASTRUCTURE):
+
+* ``Oracle("dabo")``   -> oracle/libdab_oracle.so, the C restatement (travels to the GPU box)
+* ``Oracle("dabref")`` -> oracle/_ref/libdabref.so, the UNMODIFIED reference sources (built here only)
+
+Both export the same entry points (oracle/dab_oracle.h, oracle/ref_build/dabref.h).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from dabstar_b200 import build
+
+c_p = ctypes.c_void_p
+
+
+class ChainCfg(ctypes.Structure):
+    _fields_ = [("soft_bit_type", ctypes.c_int), ("threshold", ctypes.c_float), ("strongest_peak", ctypes.c_int),
+                ("scan_mode", ctypes.c_int), ("tap_soft_bits", ctypes.c_int), ("tap_fft", ctypes.c_int),
+                ("n_subch", ctypes.c_int), ("subch", c_p), ("eti_path", ctypes.c_char_p)]
+
+
+class FrameInfo(ctypes.Structure):
+    _fields_ = [("sym0_pos", ctypes.c_int64), ("start_index", ctypes.c_int32), ("fbb_sym0", ctypes.c_float),
+                ("fbb_data", ctypes.c_float), ("fbb_null", ctypes.c_float), ("fsync", ctypes.c_float),
+                ("phase_cp", ctypes.c_float), ("clock_err", ctypes.c_float), ("fic_ratio_before", ctypes.c_int32),
+                ("fic_ratio_after", ctypes.c_int32), ("fic_valid", ctypes.c_uint8 * 4)]
+
+
+def ref_available() -> bool:
+    return os.path.exists(build.LIB_REF)
+
+
+def _ptr(a: np.ndarray) -> c_p:
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_p)
+
+
+class Oracle:
+    def __init__(self, prefix: str = "dabo"):
+        self.prefix = prefix
+        if prefix == "dabo":
+            path = build.build_oracle()
+        elif prefix == "dabref":
+            path = build.LIB_REF
+            if not os.path.exists(path):
+                raise FileNotFoundError("oracle/_ref/libdabref.so is not built (needs /root/reference)")
+        else:
+            raise ValueError(prefix)
+        self.lib = ctypes.CDLL(path)
+        for name, res in (("fic_new", c_p), ("backend_new", c_p), ("ofdm_new", c_p), ("phaseref_new", c_p), ("chain_run", c_p),
+                          ("calc_crc", ctypes.c_uint16), ("chain_msc_size", ctypes.c_int64), ("chain_msc_copy", ctypes.c_int64),
+                          ("chain_seconds", ctypes.c_double)):
+            self.f(name).restype = res
+
+    def f(self, name: str):
+        return getattr(self.lib, f"{self.prefix}_{name}")
+
+    # ---- tables
+    def freq_interleaver(self) -> np.ndarray:
+        t = np.zeros(1536, np.int16)
+        self.f("freq_interleaver")(_ptr(t))
+        return t
+
+    def phase_table(self) -> np.ndarray:
+        t = np.zeros(2048, np.complex64)
+        self.f("phase_table")(_ptr(t))
+        return t
+
+    def fft2048(self, x: np.ndarray, sign: int = -1) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.complex64)
+        y = np.zeros(2048, np.complex64)
+        self.f("fft2048")(_ptr(x), _ptr(y), ctypes.c_int(sign))
+        return y
+
+    # ---- channel decoding
+    def viterbi(self, soft: np.ndarray, frame_bits: int) -> np.ndarray:
+        soft = np.ascontiguousarray(soft, np.int16)
+        assert soft.size == 4 * (frame_bits + 6)
+        out = np.zeros(frame_bits, np.uint8)
+        self.f("viterbi")(_ptr(soft), ctypes.c_int(frame_bits), _ptr(out))
+        return out
+
+    def viterbi_ber(self, soft: np.ndarray, punct: np.ndarray, bits: np.ndarray) -> tuple[int, int]:
+        b, e = ctypes.c_int(0), ctypes.c_int(0)
+        self.f("viterbi_ber")(_ptr(np.ascontiguousarray(soft, np.int16)), _ptr(np.ascontiguousarray(punct, np.uint8)),
+                              _ptr(np.ascontiguousarray(bits, np.uint8)), ctypes.c_int(bits.size), ctypes.byref(b), ctypes.byref(e))
+        return b.value, e.value
+
+    def protection(self, short_form: int, bit_rate: int, prot_level: int, soft: np.ndarray) -> np.ndarray:
+        soft = np.ascontiguousarray(soft, np.int16)
+        out = np.zeros(24 * bit_rate, np.uint8)
+        self.f("protection")(short_form, bit_rate, prot_level, _ptr(soft), ctypes.c_int(soft.size), _ptr(out))
+        return out
+
+    def protection_addresses(self, short_form: int, bit_rate: int, prot_level: int) -> np.ndarray:
+        cap = 4 * 24 * bit_rate + 24
+        a = np.zeros(cap, np.int32)
+        n = self.f("protection_addresses")(short_form, bit_rate, prot_level, _ptr(a), cap)
+        return a[:n].copy()
+
+    def check_crc_bits(self, bits: np.ndarray) -> bool:
+        bits = np.ascontiguousarray(bits, np.uint8)
+        return bool(self.f("check_crc_bits")(_ptr(bits), ctypes.c_int(bits.size)))
+
+    def calc_crc(self, data: np.ndarray) -> int:
+        data = np.ascontiguousarray(data, np.uint8)
+        return int(self.f("calc_crc")(_ptr(data), ctypes.c_int(data.size)))
+
+    def fic_decode_frames(self, soft: np.ndarray):
+        """soft: int16[n_frames, 3, 3072] (symbols 1..3). Returns bits[n,3072], valid[n,4], ratio[n]."""
+        soft = np.ascontiguousarray(soft, np.int16)
+        n = soft.shape[0]
+        h = c_p(self.f("fic_new")())
+        bits = np.zeros((n, 3072), np.uint8)
+        valid = np.zeros((n, 4), np.uint8)
+        ratio = np.zeros(n, np.int32)
+        ber = np.zeros((n, 2), np.int32)
+        r, bb, be = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        for i in range(n):
+            for s in range(3):
+                self.f("fic_process_block")(h, _ptr(soft[i, s]), ctypes.c_int(s + 1))
+            self.f("fic_get")(h, _ptr(bits[i]), _ptr(valid[i]), ctypes.byref(r), ctypes.byref(bb), ctypes.byref(be))
+            ratio[i] = r.value
+            ber[i] = (bb.value, be.value)
+        self.f("fic_free")(h)
+        return bits, valid, ratio, ber
+
+    def backend_run(self, start_cu: int, size_cu: int, short_form: int, prot_level: int, bit_rate: int, cifs: np.ndarray):
+        """cifs: int16[n, 55296]. Returns (uint8[n_emitted, 24*bitRate], index of first emitting CIF)."""
+        cifs = np.ascontiguousarray(cifs, np.int16)
+        h = c_p(self.f("backend_new")(1, start_cu, size_cu, short_form, prot_level, bit_rate))
+        outs, first = [], None
+        for i in range(cifs.shape[0]):
+            out = np.zeros(24 * bit_rate, np.uint8)
+            frag = np.ascontiguousarray(cifs[i, start_cu * 64:(start_cu + size_cu) * 64])
+            if self.f("backend_process")(h, _ptr(frag), _ptr(out)):
+                outs.append(out)
+                first = i if first is None else first
+        self.f("backend_free")(h)
+        return (np.stack(outs) if outs else np.zeros((0, 24 * bit_rate), np.uint8)), first
+
+    # ---- OFDM
+    def ofdm_new(self, soft_bit_type: int = 0):
+        return c_p(self.f("ofdm_new")(soft_bit_type))
+
+    def ofdm_free(self, h):
+        self.f("ofdm_free")(h)
+
+    def ofdm_reset(self, h):
+        self.f("ofdm_reset")(h)
+
+    def ofdm_store_reference(self, h, fft: np.ndarray):
+        self.f("ofdm_store_reference_symbol_0")(h, _ptr(np.ascontiguousarray(fft, np.complex64)))
+
+    def ofdm_store_null(self, h, fft: np.ndarray):
+        self.f("ofdm_store_null_symbol_without_tii")(h, _ptr(np.ascontiguousarray(fft, np.complex64)))
+
+    def ofdm_decode_symbol(self, h, fft: np.ndarray, sym_idx: int, phase_corr: float = 0.0, clock_err: float = 0.0) -> np.ndarray:
+        out = np.zeros(3072, np.int16)
+        self.f("ofdm_decode_symbol")(h, _ptr(np.ascontiguousarray(fft, np.complex64)), ctypes.c_int(sym_idx),
+                                     ctypes.c_float(phase_corr), ctypes.c_float(clock_err), _ptr(out))
+        return out
+
+    def ofdm_state(self, h, which: int) -> np.ndarray:
+        n = {0: 1536, 1: 1536, 2: 1536, 3: 1536, 4: 2048, 5: 2}[which]
+        out = np.zeros(n, np.float32)
+        self.f("ofdm_get_state")(h, ctypes.c_int(which), _ptr(out))
+        return out
+
+    def phaseref_correlate(self, samples: np.ndarray, threshold: float, strongest: int = 0) -> int:
+        h = c_p(self.f("phaseref_new")())
+        r = self.f("phaseref_correlate")(h, _ptr(np.ascontiguousarray(samples[:2048], np.complex64)), ctypes.c_float(threshold), ctypes.c_int(strongest))
+        self.f("phaseref_free")(h)
+        return int(r)
+
+    def phaseref_estimate_offset(self, fft: np.ndarray) -> int:
+        h = c_p(self.f("phaseref_new")())
+        r = self.f("phaseref_estimate_offset")(h, _ptr(np.ascontiguousarray(fft, np.complex64)))
+        self.f("phaseref_free")(h)
+        return int(r)
+
+    # ---- whole chain
+    def chain_run(self, iq: np.ndarray, subch_table: np.ndarray | None = None, n_subch: int = 0, soft_bit_type: int = 0,
+                  threshold: float = 3.0, strongest_peak: int = 0, scan_mode: int = 0, tap_soft: bool = False, tap_fft: bool = False):
+        iq = np.ascontiguousarray(iq, np.complex64)
+        tab = np.ascontiguousarray(subch_table if subch_table is not None else np.zeros((1, 7)), np.int32)
+        cfg = ChainCfg(soft_bit_type, threshold, strongest_peak, scan_mode, int(tap_soft), int(tap_fft), n_subch, tab.ctypes.data, None)
+        h = c_p(self.f("chain_run")(_ptr(iq), ctypes.c_int64(iq.size), ctypes.byref(cfg)))
+        return ChainResult(self, h, tab[:n_subch].copy())
+
+
+class ChainResult:
+    def __init__(self, o: Oracle, h, tab: np.ndarray):
+        self.o, self.h = o, h
+        f = o.f
+        self.n_frames = int(f("chain_n_frames")(h))
+        self.info = []
+        self.fib_bits = np.zeros((self.n_frames, 3072), np.uint8)
+        for i in range(self.n_frames):
+            fi = FrameInfo()
+            f("chain_frame_info")(h, ctypes.c_int(i), ctypes.byref(fi))
+            self.info.append(fi)
+            f("chain_fib_bits")(h, ctypes.c_int(i), _ptr(self.fib_bits[i]))
+        self.fic_valid = np.array([list(fi.fic_valid) for fi in self.info], np.uint8).reshape(self.n_frames, 4)
+        self.n_good_fibs = int(f("chain_n_good_fibs")(h))
+        self.seconds = float(f("chain_seconds")(h))
+        cnt = np.zeros(8, np.int64)
+        f("chain_counters")(h, _ptr(cnt))
+        self.counters = cnt
+        self.msc = {}
+        for row in tab:
+            sid, br = int(row[0]), int(row[5])
+            n = int(f("chain_msc_size")(h, ctypes.c_int(sid)))
+            buf = np.zeros(n, np.uint8)
+            if n:
+                f("chain_msc_copy")(h, ctypes.c_int(sid), _ptr(buf), ctypes.c_int64(n))
+            self.msc[sid] = buf.reshape(-1, 24 * br)
+
+    def soft_bits(self, frame: int) -> np.ndarray | None:
+        out = np.zeros((75, 3072), np.int16)
+        return out if self.o.f("chain_soft_bits")(self.h, ctypes.c_int(frame), _ptr(out)) else None
+
+    def fft(self, frame: int) -> np.ndarray | None:
+        out = np.zeros((77, 2048), np.complex64)
+        return out if self.o.f("chain_fft")(self.h, ctypes.c_int(frame), _ptr(out)) else None
+
+    def close(self):
+        if self.h is not None:
+            self.o.f("chain_free")(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,336 @@
+"""Host-side mirror of the reference's receive-chain classes over the C ABI (include/dabstar_b200.h).
+
+The class and method names follow the reference (OfdmDecoder, PhaseReference, FreqInterleaver, FicDecoder alias
+FicHandler, Backend, Protection, ViterbiSpiral, DabProcessor) so the parity tests read like calls into it; the
+arguments are batches because the device boundary is batch granular. numpy arrays are host
+memory, torch CUDA tensors are passed by device pointer. Nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import DabstarError, DecoderCfg, FrameInfo, SubCh, c_p
+from .synth import SubChannel
+
+MEM_HOST, MEM_DEVICE = 0, 1
+FMT_CF32, FMT_U8, FMT_I16 = 0, 1, 2
+T_FRAME = 196608
+FRAME_SOFT = 75 * 3072
+
+
+def _np(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _ptr(a: np.ndarray) -> c_p:
+    return a.ctypes.data_as(c_p)
+
+
+class Context:
+    """One CUDA device + stream (dabstar_create). `stream` may be a torch.cuda.Stream or None for a private stream."""
+
+    def __init__(self, device: int = 0, stream=None):
+        self.lib = _lib.load()
+        self.h = c_p()
+        sp = c_p(stream.cuda_stream) if stream is not None else None
+        rc = self.lib.dabstar_create(ctypes.byref(self.h), int(device), sp)
+        if rc != 0:
+            raise DabstarError(f"dabstar_create failed ({rc}): no usable CUDA device {device}; there is no CPU fallback")
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.lib.dabstar_destroy(self.h)
+            self.h = c_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int, what: str) -> int:
+        if rc < 0:
+            raise DabstarError(f"{what} failed ({rc}): {self.lib.dabstar_last_error(self.h).decode()}")
+        return rc
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.dabstar_kernel_launches(self.h))
+
+    # ---- stage taps
+    def fft2048(self, x: np.ndarray, sign: int = -1) -> np.ndarray:
+        """fftwf_execute on the reference's 2048-point plans (dab_processor.cpp:63): x complex64[n, 2048]."""
+        x = _np(x, np.complex64).reshape(-1, 2048)
+        y = np.empty_like(x)
+        self.check(self.lib.dabstar_fft2048(self.h, _ptr(x), _ptr(y), x.shape[0], sign, MEM_HOST), "dabstar_fft2048")
+        return y
+
+
+_default_ctx: Context | None = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+class FreqInterleaver:
+    """ofdm/freq_interleaver.h:50"""
+
+    def __init__(self, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.table = np.zeros(1536, np.int16)
+        self.ctx.check(self.ctx.lib.dabstar_freq_interleaver(self.ctx.h, _ptr(self.table)), "dabstar_freq_interleaver")
+
+    def map_k_to_fft_bin(self, k: int) -> int:
+        return int(self.table[k])
+
+
+class PhaseReference:
+    """ofdm/phasereference.h:53-58"""
+    IDX_NOT_FOUND = 100000
+
+    def __init__(self, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.strongest = 0
+        self.mRefTable = np.zeros(2048, np.complex64)
+        self.ctx.check(self.ctx.lib.dabstar_phase_table(self.ctx.h, _ptr(self.mRefTable)), "dabstar_phase_table")
+
+    def set_sync_on_strongest_peak(self, sync: bool):
+        self.strongest = int(bool(sync))
+
+    def correlate_with_phase_ref_and_find_max_peak(self, samples: np.ndarray, threshold: float) -> np.ndarray:
+        x = _np(samples, np.complex64).reshape(-1, 2048)
+        out = np.zeros(x.shape[0], np.int32)
+        self.ctx.check(self.ctx.lib.dabstar_prs_correlate(self.ctx.h, _ptr(x), x.shape[0], ctypes.c_float(threshold), self.strongest, _ptr(out), MEM_HOST),
+                       "dabstar_prs_correlate")
+        return out
+
+    def estimate_carrier_offset_from_sync_symbol_0(self, fft: np.ndarray) -> np.ndarray:
+        x = _np(fft, np.complex64).reshape(-1, 2048)
+        out = np.zeros(x.shape[0], np.int32)
+        self.ctx.check(self.ctx.lib.dabstar_estimate_carrier_offset(self.ctx.h, _ptr(x), x.shape[0], _ptr(out), MEM_HOST), "dabstar_estimate_carrier_offset")
+        return out
+
+
+class ViterbiSpiral:
+    """support/viterbi_spiral/viterbi_spiral.h:20 — deconvolve() over a batch of equally long code words."""
+
+    def __init__(self, frame_bits: int, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.frame_bits = int(frame_bits)
+
+    def deconvolve(self, soft: np.ndarray) -> np.ndarray:
+        n_in = 4 * (self.frame_bits + 6)
+        soft = _np(soft, np.int16).reshape(-1, n_in)
+        n = soft.shape[0]
+        bits = np.zeros((n, self.frame_bits), np.uint8)
+        soft_off = (np.arange(n, dtype=np.int64) * n_in)
+        bits_off = (np.arange(n, dtype=np.int64) * self.frame_bits)
+        fb = np.full(n, self.frame_bits, np.int32)
+        self.ctx.check(self.ctx.lib.dabstar_viterbi(self.ctx.h, _ptr(soft), _ptr(soft_off), _ptr(fb), n, _ptr(bits), _ptr(bits_off), MEM_HOST), "dabstar_viterbi")
+        return bits
+
+
+def viterbi_ragged(ctx: Context, soft_list: list[np.ndarray], frame_bits: list[int]) -> list[np.ndarray]:
+    """dabstar_viterbi on code words of different lengths in one launch."""
+    soft = np.concatenate([_np(s, np.int16).ravel() for s in soft_list]) if soft_list else np.zeros(0, np.int16)
+    fb = np.asarray(frame_bits, np.int32)
+    soft_off = np.concatenate([[0], np.cumsum(4 * (fb.astype(np.int64) + 6))[:-1]]).astype(np.int64) if len(fb) else np.zeros(0, np.int64)
+    bits_off = np.concatenate([[0], np.cumsum(fb.astype(np.int64))[:-1]]).astype(np.int64) if len(fb) else np.zeros(0, np.int64)
+    bits = np.zeros(int(fb.sum()), np.uint8)
+    ctx.check(ctx.lib.dabstar_viterbi(ctx.h, _ptr(soft), _ptr(soft_off), _ptr(fb), len(fb), _ptr(bits), _ptr(bits_off), MEM_HOST), "dabstar_viterbi")
+    return [bits[o:o + n] for o, n in zip(bits_off, fb)]
+
+
+class Protection:
+    """protection/protection.h:44 (EepProtection / UepProtection): depuncture + Viterbi."""
+
+    def __init__(self, short_form: int, bit_rate: int, prot_level: int, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.short_form, self.bit_rate, self.prot_level = int(short_form), int(bit_rate), int(prot_level)
+
+    def addresses(self) -> np.ndarray:
+        cap = 4 * 24 * self.bit_rate + 24
+        a = np.zeros(cap, np.int32)
+        n = self.ctx.check(self.ctx.lib.dabstar_protection_addresses(self.ctx.h, self.short_form, self.bit_rate, self.prot_level, _ptr(a), cap),
+                           "dabstar_protection_addresses")
+        return a[:n].copy()
+
+    def deconvolve(self, soft: np.ndarray, size_cu: int) -> np.ndarray:
+        soft = _np(soft, np.int16).reshape(-1, size_cu * 64)
+        out = np.zeros((soft.shape[0], 24 * self.bit_rate), np.uint8)
+        self.ctx.check(self.ctx.lib.dabstar_protection_deconvolve(self.ctx.h, self.short_form, self.bit_rate, self.prot_level, size_cu, _ptr(soft),
+                                                                  soft.shape[0], _ptr(out), MEM_HOST), "dabstar_protection_deconvolve")
+        return out
+
+
+class FicDecoder:
+    """decoder/fic_decoder.h:49-58 (the member DabProcessor calls mFicHandler)."""
+
+    def __init__(self, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.ratio = 0
+
+    def process_frames(self, soft: np.ndarray):
+        """soft: int16[n, >=9216] (symbols 1..3 first). Returns fib_bits[n,3072], crc_ok[n,12], ber[n,4,2], ratio_percent[n]."""
+        soft = _np(soft, np.int16)
+        soft = soft.reshape(soft.shape[0], -1)
+        n, stride = soft.shape
+        bits = np.zeros((n, 3072), np.uint8)
+        crc = np.zeros((n, 12), np.uint8)
+        ber = np.zeros((n, 4, 2), np.int32)
+        self.ctx.check(self.ctx.lib.dabstar_fic_decode(self.ctx.h, _ptr(soft), ctypes.c_int64(stride), n, _ptr(bits), _ptr(crc), _ptr(ber), MEM_HOST), "dabstar_fic_decode")
+        ratio = np.zeros(n, np.int32)
+        for i in range(n):  # saturating success counter (fic_decoder.cpp:247-259)
+            for ok in crc[i]:
+                self.ratio = min(10, self.ratio + 1) if ok else max(0, self.ratio - 1)
+            ratio[i] = self.ratio * 10
+        return bits, crc, ber, ratio
+
+    def get_fic_decode_ratio_percent(self) -> int:
+        return self.ratio * 10
+
+
+FicHandler = FicDecoder
+
+
+class Backend:
+    """backend/backend.h:60 for one sub-channel over consecutive CIFs."""
+
+    def __init__(self, desc: SubChannel, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.desc = desc
+
+    def process(self, cifs: np.ndarray) -> np.ndarray:
+        cifs = _np(cifs, np.int16).reshape(-1, 55296)
+        n_out = max(0, cifs.shape[0] - 16)
+        out = np.zeros((n_out, 24 * self.desc.bit_rate), np.uint8)
+        sc = SubCh(*self.desc.as_row())
+        self.ctx.check(self.ctx.lib.dabstar_backend_process(self.ctx.h, ctypes.byref(sc), _ptr(cifs), cifs.shape[0], _ptr(out), MEM_HOST), "dabstar_backend_process")
+        return out
+
+
+class OfdmDecoder:
+    """ofdm/ofdm_decoder.h:63-73 over whole frames."""
+
+    def __init__(self, soft_bit_type: int = 0, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.soft_bit_type = soft_bit_type
+        self.st = c_p()
+        self.ctx.check(self.ctx.lib.dabstar_ofdm_state_create(self.ctx.h, ctypes.byref(self.st)), "dabstar_ofdm_state_create")
+
+    def __del__(self):
+        try:
+            if self.st:
+                self.ctx.lib.dabstar_ofdm_state_destroy(self.ctx.h, self.st)
+        except Exception:
+            pass
+
+    def reset(self):
+        self.ctx.check(self.ctx.lib.dabstar_ofdm_state_reset(self.ctx.h, self.st), "dabstar_ofdm_state_reset")
+
+    def set_soft_bit_gen_type(self, t: int):
+        self.soft_bit_type = int(t)
+
+    def state(self, which: int) -> np.ndarray:
+        out = np.zeros(2 if which == 5 else 1536, np.float32)
+        self.ctx.check(self.ctx.lib.dabstar_ofdm_state_get(self.ctx.h, self.st, which, _ptr(out)), "dabstar_ofdm_state_get")
+        return out
+
+    def decode_frames(self, fft: np.ndarray, clock_err: np.ndarray | None = None, null_is_tii: np.ndarray | None = None) -> np.ndarray:
+        """fft: complex64[n, 77, 2048] (symbol 0, symbols 1..75, null). Returns int16[n, 75, 3072]."""
+        fft = _np(fft, np.complex64).reshape(-1, 77, 2048)
+        n = fft.shape[0]
+        ce = _np(clock_err if clock_err is not None else np.zeros(n), np.float32)
+        tii = _np(null_is_tii if null_is_tii is not None else np.zeros(n), np.uint8)
+        soft = np.zeros((n, 75, 3072), np.int16)
+        self.ctx.check(self.ctx.lib.dabstar_ofdm_decode_frames(self.ctx.h, self.st, _ptr(fft), n, _ptr(ce), _ptr(tii), self.soft_bit_type, _ptr(soft), MEM_HOST),
+                       "dabstar_ofdm_decode_frames")
+        return soft
+
+
+@dataclass
+class RecordingResult:
+    n_frames: int
+    info: list
+    fib_bits: np.ndarray    # uint8[n_frames, 3072]
+    fic_valid: np.ndarray   # uint8[n_frames, 4]
+    msc: dict               # sub_ch_id -> uint8[n_logical_frames, 24*bitRate]
+    counters: np.ndarray    # int64[8]
+
+    @property
+    def n_good_fibs(self) -> int:
+        return int(self.counters[0])
+
+
+class DabProcessor:
+    """main/dab_processor.h:71 for a batch of recordings (one reference DabProcessor per recording, in lock step)."""
+
+    def __init__(self, n_recordings: int = 1, input_format: int = FMT_U8, soft_bit_type: int = 0, sync_threshold: float = 3.0,
+                 strongest_peak: bool = False, scan_mode: bool = False, max_window: int = 0, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.n = int(n_recordings)
+        self.cfg = DecoderCfg(input_format, soft_bit_type, sync_threshold, int(strongest_peak), int(scan_mode), 1, max_window, 0)
+        self.h = c_p()
+        self.ctx.check(self.ctx.lib.dabstar_decoder_create(self.ctx.h, ctypes.byref(self.cfg), self.n, ctypes.byref(self.h)), "dabstar_decoder_create")
+        self.subch: list[list[SubChannel]] = [[] for _ in range(self.n)]
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.ctx.lib.dabstar_decoder_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_audio_channel(self, recording: int, subch: list[SubChannel]):
+        """DabProcessor::set_audio_channel for every entry (start_frame = frame in which the Backend is created)."""
+        arr = (SubCh * max(len(subch), 1))(*[SubCh(*s.as_row()) for s in subch])
+        self.ctx.check(self.ctx.lib.dabstar_decoder_set_subchannels(self.h, recording, arr, len(subch)), "dabstar_decoder_set_subchannels")
+        self.subch[recording] = list(subch)
+
+    def run_ptrs(self, ptrs: list[int], n_samples: list[int], mem: int) -> float:
+        """Decode complete recordings given raw pointers. Returns the device time in ms (CUDA events)."""
+        p = (c_p * self.n)(*[c_p(x) for x in ptrs])
+        ns = (ctypes.c_int64 * self.n)(*n_samples)
+        self.ctx.check(self.ctx.lib.dabstar_decoder_run(self.h, p, ns, mem), "dabstar_decoder_run")
+        return float(self.ctx.lib.dabstar_decoder_last_ms(self.h))
+
+    def run(self, recordings: list[np.ndarray]) -> float:
+        """recordings: host arrays (uint8[n,2] / int16[n,2] / complex64[n]) in the configured input format."""
+        dt = {FMT_U8: np.uint8, FMT_I16: np.int16, FMT_CF32: np.complex64}[self.cfg.input_format]
+        arrs = [_np(r, dt) for r in recordings]
+        self._keep = arrs
+        n = [a.shape[0] for a in arrs]
+        return self.run_ptrs([a.ctypes.data for a in arrs], n, MEM_HOST)
+
+    def result(self, recording: int) -> RecordingResult:
+        lib = self.ctx.lib
+        nf = self.ctx.check(lib.dabstar_decoder_n_frames(self.h, recording), "dabstar_decoder_n_frames")
+        info = (FrameInfo * max(nf, 1))()
+        lib.dabstar_decoder_frame_info(self.h, recording, info, nf)
+        bits = np.zeros((nf, 3072), np.uint8)
+        valid = np.zeros((nf, 4), np.uint8)
+        lib.dabstar_decoder_fib_bits(self.h, recording, _ptr(bits), _ptr(valid))
+        msc = {}
+        for s in self.subch[recording]:
+            n = int(lib.dabstar_decoder_msc_size(self.h, recording, s.sub_ch_id))
+            buf = np.zeros(n, np.uint8)
+            if n:
+                lib.dabstar_decoder_msc_copy(self.h, recording, s.sub_ch_id, _ptr(buf), ctypes.c_int64(n))
+            msc[s.sub_ch_id] = buf.reshape(-1, 24 * s.bit_rate)
+        cnt = np.zeros(8, np.int64)
+        lib.dabstar_decoder_counters(self.h, recording, _ptr(cnt))
+        return RecordingResult(nf, list(info)[:nf], bits, valid, msc, cnt)
+
+    def soft_bits(self, recording: int, frame: int) -> np.ndarray:
+        out = np.zeros((75, 3072), np.int16)
+        self.ctx.check(self.ctx.lib.dabstar_decoder_soft_bits(self.h, recording, frame, _ptr(out)), "dabstar_decoder_soft_bits")
+        return out

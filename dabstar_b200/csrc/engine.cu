@@ -1,0 +1,1270 @@
+// engine.cu — context, stage taps and the whole-path decoder behind include/dabstar_b200.h.
+//
+// The decoder restates DabProcessor's control flow (main/dab_processor.cpp:110-442) as a host-side state machine
+// per recording that drives BATCHED kernels: all recordings advance in lock step, and inside a recording the
+// frame-to-frame dependencies (frame position from the PRS peak, AFC from the cyclic-prefix phase, coarse AFC
+// gated by the FIC success counter) are handled by speculation: a window of frames is laid out assuming the PRS
+// peak stays at T_g and the FIC keeps decoding, every kernel runs over the whole window, and the per-frame PRS
+// peaks / FIB CRCs are verified afterwards. A window that fails verification is replayed from a state snapshot
+// with the length that verified. Acquisition (first frames, or after a sync loss) runs with windows of one frame.
+#include "../../include/dabstar_b200.h"
+#include "kernels.h"
+#include "tables.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace dab;
+
+// ------------------------------------------------------------------------------------------------ helpers
+namespace
+{
+struct DevBuf
+{
+  void * p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t reserve(size_t bytes)
+  {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <typename T> T * as() const { return static_cast<T *>(p); }
+};
+} // namespace
+
+struct dabstar_ctx
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  unsigned long long launches = 0;
+  DeviceTables tab{};
+  std::vector<int16_t> h_bin_signed;
+  std::vector<float2> h_prs;
+  std::vector<VitProfile> profiles; // [0] = FIC
+  std::map<long long, int> profile_index;
+  DevBuf d_profiles;
+  bool profiles_dirty = true;
+  DevBuf scratch[8];
+
+  int fail(int code, const char * fmt, ...)
+  {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+  int cuda_fail(cudaError_t e, const char * what) { return fail(DABSTAR_E_CUDA, "%s: %s", what, cudaGetErrorString(e)); }
+};
+
+#define CK(call)                                                     \
+  do {                                                               \
+    cudaError_t e_ = (call);                                         \
+    if (e_ != cudaSuccess) return ctx->cuda_fail(e_, #call);         \
+  } while (0)
+
+namespace
+{
+int get_profile(dabstar_ctx * ctx, int short_form, int bit_rate, int prot_level)
+{
+  const long long key = ((long long)(short_form ? 1 : 0) << 40) | ((long long)bit_rate << 8) | (long long)(prot_level & 0xff);
+  auto it = ctx->profile_index.find(key);
+  if (it != ctx->profile_index.end()) return it->second;
+  VitProfile p;
+  if (!make_msc_profile(short_form, bit_rate, prot_level, p)) return -1;
+  ctx->profiles.push_back(p);
+  ctx->profiles_dirty = true;
+  const int idx = (int)ctx->profiles.size() - 1;
+  ctx->profile_index[key] = idx;
+  return idx;
+}
+
+int get_identity_profile(dabstar_ctx * ctx, int n_bits)
+{
+  const long long key = (2LL << 40) | (long long)n_bits;
+  auto it = ctx->profile_index.find(key);
+  if (it != ctx->profile_index.end()) return it->second;
+  ctx->profiles.push_back(make_identity_profile(n_bits));
+  ctx->profiles_dirty = true;
+  const int idx = (int)ctx->profiles.size() - 1;
+  ctx->profile_index[key] = idx;
+  return idx;
+}
+
+int sync_profiles(dabstar_ctx * ctx)
+{
+  if (!ctx->profiles_dirty) return 0;
+  CK(ctx->d_profiles.reserve(sizeof(VitProfile) * std::max<size_t>(ctx->profiles.size(), 64)));
+  CK(cudaMemcpyAsync(ctx->d_profiles.p, ctx->profiles.data(), sizeof(VitProfile) * ctx->profiles.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->profiles_dirty = false;
+  return 0;
+}
+
+// Brings `bytes` at `src` (host or device per `mem`) into device memory; returns the device pointer.
+int stage_in(dabstar_ctx * ctx, DevBuf & buf, const void * src, size_t bytes, int mem, const void ** out)
+{
+  if (mem == DABSTAR_MEM_DEVICE) { *out = src; return 0; }
+  CK(buf.reserve(bytes));
+  CK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  *out = buf.p;
+  return 0;
+}
+int stage_out_begin(dabstar_ctx * ctx, DevBuf & buf, void * dst, size_t bytes, int mem, void ** out)
+{
+  if (mem == DABSTAR_MEM_DEVICE) { *out = dst; return 0; }
+  CK(buf.reserve(bytes));
+  *out = buf.p;
+  return 0;
+}
+int stage_out_end(dabstar_ctx * ctx, const void * dev, void * dst, size_t bytes, int mem)
+{
+  if (mem == DABSTAR_MEM_HOST) CK(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+} // namespace
+
+// ------------------------------------------------------------------------------------------------ context
+extern "C" int dabstar_abi_version(void) { return DABSTAR_ABI_VERSION; }
+
+extern "C" int dabstar_create(dabstar_ctx ** out, int device, void * stream)
+{
+  if (!out) return DABSTAR_E_INVALID;
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev) return DABSTAR_E_CUDA; // no CPU fallback
+  std::unique_ptr<dabstar_ctx> ctx(new dabstar_ctx);
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) return DABSTAR_E_CUDA;
+  if (stream) ctx->stream = (cudaStream_t)stream;
+  else
+  {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return DABSTAR_E_CUDA;
+    ctx->own_stream = true;
+  }
+  // tables
+  ctx->h_bin_signed.resize(K_CARR);
+  host_freq_interleaver(ctx->h_bin_signed.data());
+  ctx->h_prs.resize(T_U);
+  host_phase_table(ctx->h_prs.data());
+  std::vector<float2> w(T_U);
+  host_w2048(w.data());
+  std::vector<int16_t> bin_idx(K_CARR), rel(K_CARR);
+  for (int k = 0; k < K_CARR; k++)
+  {
+    const int b = ctx->h_bin_signed[k];
+    bin_idx[k] = (int16_t)(b < 0 ? b + T_U : b);
+    rel[k] = (int16_t)(b < 0 ? b + K_CARR / 2 : b + K_CARR / 2 - 1); // ofdm_decoder.cpp:169-180
+  }
+  std::vector<uint8_t> prbs(9216);
+  host_prbs(prbs.data(), 9216);
+  bool ok = true;
+  ok = ok && cudaMalloc(&ctx->tab.w2048, sizeof(float2) * T_U) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->tab.prs, sizeof(float2) * T_U) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->tab.ref_arg_conj, sizeof(float2) * T_U) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->tab.bin_of_k, sizeof(int16_t) * K_CARR) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->tab.rel_of_k, sizeof(int16_t) * K_CARR) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->tab.prbs, 9216) == cudaSuccess;
+  ok = ok && cudaMemcpy(ctx->tab.w2048, w.data(), sizeof(float2) * T_U, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok = ok && cudaMemcpy(ctx->tab.prs, ctx->h_prs.data(), sizeof(float2) * T_U, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok = ok && cudaMemcpy(ctx->tab.bin_of_k, bin_idx.data(), sizeof(int16_t) * K_CARR, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok = ok && cudaMemcpy(ctx->tab.rel_of_k, rel.data(), sizeof(int16_t) * K_CARR, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok = ok && cudaMemcpy(ctx->tab.prbs, prbs.data(), 9216, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok = ok && launch_init_ref_arg(ctx->stream, ctx->tab, &ctx->launches) == cudaSuccess;
+  ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+  if (!ok) { dabstar_destroy(ctx.release()); return DABSTAR_E_CUDA; }
+  ctx->profiles.push_back(make_fic_profile());
+  *out = ctx.release();
+  return DABSTAR_OK;
+}
+
+extern "C" void dabstar_destroy(dabstar_ctx * ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaFree(ctx->tab.w2048); cudaFree(ctx->tab.prs); cudaFree(ctx->tab.ref_arg_conj);
+  cudaFree(ctx->tab.bin_of_k); cudaFree(ctx->tab.rel_of_k); cudaFree(ctx->tab.prbs);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char * dabstar_last_error(const dabstar_ctx * ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" uint64_t dabstar_kernel_launches(const dabstar_ctx * ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ tables
+extern "C" int dabstar_freq_interleaver(dabstar_ctx * ctx, int16_t out[1536])
+{
+  if (!ctx || !out) return DABSTAR_E_INVALID;
+  memcpy(out, ctx->h_bin_signed.data(), sizeof(int16_t) * K_CARR);
+  return 0;
+}
+extern "C" int dabstar_phase_table(dabstar_ctx * ctx, float out[4096])
+{
+  if (!ctx || !out) return DABSTAR_E_INVALID;
+  memcpy(out, ctx->h_prs.data(), sizeof(float2) * T_U);
+  return 0;
+}
+extern "C" int dabstar_protection_addresses(dabstar_ctx * ctx, int short_form, int bit_rate, int prot_level, int32_t * addr, int cap)
+{
+  if (!ctx || !addr) return DABSTAR_E_INVALID;
+  VitProfile p;
+  if (!make_msc_profile(short_form, bit_rate, prot_level, p)) return ctx->fail(DABSTAR_E_INVALID, "unknown protection profile %d/%d/%d", short_form, bit_rate, prot_level);
+  return profile_addresses(p, addr, cap);
+}
+
+// ------------------------------------------------------------------------------------------------ stage taps
+extern "C" int dabstar_fft2048(dabstar_ctx * ctx, const float * in, float * out, int n, int sign, int mem)
+{
+  if (!ctx || !in || !out || n < 0) return DABSTAR_E_INVALID;
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  const size_t bytes = sizeof(float2) * T_U * (size_t)n;
+  const void * din; void * dout;
+  if (int r = stage_in(ctx, ctx->scratch[0], in, bytes, mem, &din)) return r;
+  if (int r = stage_out_begin(ctx, ctx->scratch[1], out, bytes, mem, &dout)) return r;
+  CK(launch_fft_batch(ctx->stream, ctx->tab, (const float2 *)din, (float2 *)dout, n, sign, &ctx->launches));
+  return stage_out_end(ctx, dout, out, bytes, mem);
+}
+
+static int run_viterbi_jobs(dabstar_ctx * ctx, const std::vector<VitJob> & jobs, int max_steps, const int16_t * d_soft, uint8_t * d_bits,
+                            uint8_t * d_crc, int * d_ber, DevBuf & jobbuf)
+{
+  if (jobs.empty()) return 0;
+  if (int r = sync_profiles(ctx)) return r;
+  CK(jobbuf.reserve(sizeof(VitJob) * jobs.size()));
+  CK(cudaMemcpyAsync(jobbuf.p, jobs.data(), sizeof(VitJob) * jobs.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(launch_viterbi(ctx->stream, jobbuf.as<VitJob>(), (int)jobs.size(), ctx->d_profiles.as<VitProfile>(), max_steps, d_soft, d_bits,
+                    ctx->tab.prbs, d_crc, d_ber, &ctx->launches));
+  return 0;
+}
+
+extern "C" int dabstar_viterbi(dabstar_ctx * ctx, const int16_t * soft, const int64_t * soft_off, const int32_t * frame_bits, int n,
+                               uint8_t * bits, const int64_t * bits_off, int mem)
+{
+  if (!ctx || !soft || !soft_off || !frame_bits || !bits || !bits_off || n < 0) return DABSTAR_E_INVALID;
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  size_t soft_len = 0, bits_len = 0;
+  int max_steps = 0;
+  std::vector<VitJob> jobs((size_t)n);
+  for (int i = 0; i < n; i++)
+  {
+    if (frame_bits[i] <= 0 || frame_bits[i] > 16384) return ctx->fail(DABSTAR_E_INVALID, "frame_bits[%d] = %d", i, frame_bits[i]);
+    VitJob & j = jobs[i];
+    memset(&j, 0, sizeof(j));
+    j.src = soft_off[i];
+    j.out = bits_off[i];
+    j.profile = get_identity_profile(ctx, frame_bits[i]);
+    j.src_mode = VIT_SRC_LINEAR;
+    soft_len = std::max(soft_len, (size_t)soft_off[i] + 4 * (size_t)(frame_bits[i] + 6));
+    bits_len = std::max(bits_len, (size_t)bits_off[i] + (size_t)frame_bits[i]);
+    max_steps = std::max(max_steps, frame_bits[i] + 6);
+  }
+  const void * dsoft; void * dbits;
+  if (int r = stage_in(ctx, ctx->scratch[0], soft, soft_len * sizeof(int16_t), mem, &dsoft)) return r;
+  if (int r = stage_out_begin(ctx, ctx->scratch[1], bits, bits_len, mem, &dbits)) return r;
+  if (int r = run_viterbi_jobs(ctx, jobs, max_steps, (const int16_t *)dsoft, (uint8_t *)dbits, nullptr, nullptr, ctx->scratch[2])) return r;
+  return stage_out_end(ctx, dbits, bits, bits_len, mem);
+}
+
+extern "C" int dabstar_protection_deconvolve(dabstar_ctx * ctx, int short_form, int bit_rate, int prot_level, int size_cu,
+                                             const int16_t * soft, int n, uint8_t * bits, int mem)
+{
+  if (!ctx || !soft || !bits || n < 0 || size_cu <= 0) return DABSTAR_E_INVALID;
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  const int prof = get_profile(ctx, short_form, bit_rate, prot_level);
+  if (prof < 0) return ctx->fail(DABSTAR_E_INVALID, "unknown protection profile %d/%d/%d", short_form, bit_rate, prot_level);
+  const VitProfile & p = ctx->profiles[prof];
+  if (p.n_kept > size_cu * 64) return ctx->fail(DABSTAR_E_INVALID, "size_cu %d too small for profile (%d soft bits)", size_cu, p.n_kept);
+  std::vector<VitJob> jobs((size_t)n);
+  for (int i = 0; i < n; i++)
+  {
+    VitJob & j = jobs[i];
+    memset(&j, 0, sizeof(j));
+    j.src = (long long)i * size_cu * 64;
+    j.out = (long long)i * p.n_bits;
+    j.profile = prof;
+    j.src_mode = VIT_SRC_LINEAR;
+  }
+  const void * dsoft; void * dbits;
+  const size_t in_bytes = sizeof(int16_t) * (size_t)n * size_cu * 64, out_bytes = (size_t)n * p.n_bits;
+  if (int r = stage_in(ctx, ctx->scratch[0], soft, in_bytes, mem, &dsoft)) return r;
+  if (int r = stage_out_begin(ctx, ctx->scratch[1], bits, out_bytes, mem, &dbits)) return r;
+  if (int r = run_viterbi_jobs(ctx, jobs, p.n_bits + 6, (const int16_t *)dsoft, (uint8_t *)dbits, nullptr, nullptr, ctx->scratch[2])) return r;
+  return stage_out_end(ctx, dbits, bits, out_bytes, mem);
+}
+
+static void make_fic_jobs(std::vector<VitJob> & jobs, long long soft_base, long long out_base, int aux_base, int n_fic)
+{
+  for (int b = 0; b < n_fic; b++)
+  {
+    VitJob j;
+    memset(&j, 0, sizeof(j));
+    j.src = soft_base + (long long)b * FIC_IN;
+    j.out = out_base + (long long)b * FIC_OUT;
+    j.profile = 0;
+    j.src_mode = VIT_SRC_LINEAR;
+    j.flags = VIT_FLAG_PRBS | VIT_FLAG_FIC;
+    j.aux = aux_base + b;
+    jobs.push_back(j);
+  }
+}
+
+extern "C" int dabstar_fic_decode(dabstar_ctx * ctx, const int16_t * soft, int64_t frame_stride, int n, uint8_t * fib_bits,
+                                  uint8_t * crc_ok, int32_t * ber, int mem)
+{
+  if (!ctx || !soft || !fib_bits || !crc_ok || !ber || n < 0 || frame_stride < FIC_SOFT) return DABSTAR_E_INVALID;
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  std::vector<VitJob> jobs;
+  jobs.reserve((size_t)4 * n);
+  for (int f = 0; f < n; f++) make_fic_jobs(jobs, (long long)f * frame_stride, (long long)f * 4 * FIC_OUT, 4 * f, 4);
+  const void * dsoft; void * dbits; void * dcrc; void * dber;
+  const size_t in_bytes = sizeof(int16_t) * ((size_t)(n - 1) * frame_stride + FIC_SOFT);
+  if (int r = stage_in(ctx, ctx->scratch[0], soft, in_bytes, mem, &dsoft)) return r;
+  if (int r = stage_out_begin(ctx, ctx->scratch[1], fib_bits, (size_t)n * 3072, mem, &dbits)) return r;
+  if (int r = stage_out_begin(ctx, ctx->scratch[3], crc_ok, (size_t)n * 12, mem, &dcrc)) return r;
+  if (int r = stage_out_begin(ctx, ctx->scratch[4], ber, sizeof(int32_t) * (size_t)n * 8, mem, &dber)) return r;
+  if (int r = run_viterbi_jobs(ctx, jobs, FIC_OUT + 6, (const int16_t *)dsoft, (uint8_t *)dbits, (uint8_t *)dcrc, (int *)dber, ctx->scratch[2])) return r;
+  if (mem == DABSTAR_MEM_HOST)
+  {
+    CK(cudaMemcpyAsync(crc_ok, dcrc, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ber, dber, sizeof(int32_t) * (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  return stage_out_end(ctx, dbits, fib_bits, (size_t)n * 3072, mem);
+}
+
+// Jobs of one Backend over CIFs [g_begin, g_end) of a recording whose frame slot 0 starts at int16 index `rec_base`.
+// g_start = first CIF the Backend saw. Emission starts with its 17th CIF (backend/backend.cpp:146-150).
+static void make_backend_jobs(std::vector<VitJob> & jobs, int prof, const VitProfile & p, long long rec_base, int g_start, int g_begin, int g_end,
+                              int start_cu, long long out_base)
+{
+  long long out = out_base;
+  for (int g = std::max(g_begin, g_start + 16); g < g_end; g++)
+  {
+    VitJob j;
+    memset(&j, 0, sizeof(j));
+    j.src = rec_base;
+    j.out = out;
+    j.profile = prof;
+    j.src_mode = VIT_SRC_TIME_DEINTERLEAVE;
+    j.flags = VIT_FLAG_PRBS;
+    j.cif_first = g - 16;
+    int mask = 0;
+    for (int m = 0; m < 16; m++) if (g - 16 + m >= g_start) mask |= 1 << m;
+    j.row_mask = mask;
+    j.frag_off = start_cu * 64;
+    jobs.push_back(j);
+    out += p.n_bits;
+  }
+}
+
+extern "C" int dabstar_backend_process(dabstar_ctx * ctx, const dabstar_subch * sc, const int16_t * cifs, int n_cifs, uint8_t * bits, int mem)
+{
+  if (!ctx || !sc || !cifs || !bits || n_cifs < 0) return DABSTAR_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  const int prof = get_profile(ctx, sc->short_form, sc->bit_rate, sc->prot_level);
+  if (prof < 0) return ctx->fail(DABSTAR_E_INVALID, "unknown protection profile %d/%d/%d", sc->short_form, sc->bit_rate, sc->prot_level);
+  const VitProfile p = ctx->profiles[prof];
+  if (sc->start_cu < 0 || sc->size_cu <= 0 || sc->start_cu + sc->size_cu > 864 || p.n_kept > sc->size_cu * 64)
+    return ctx->fail(DABSTAR_E_INVALID, "sub-channel geometry %d+%d does not fit", sc->start_cu, sc->size_cu);
+  const int n_out = std::max(0, n_cifs - 16);
+  if (n_out == 0) return 0;
+  // The tap takes plain CIFs; the kernel addresses CIFs inside frame slots, so lay them out as slots (FIC part unused).
+  const int n_slots = (n_cifs + 3) / 4;
+  CK(ctx->scratch[0].reserve(sizeof(int16_t) * (size_t)n_slots * FRAME_SOFT));
+  int16_t * dsoft = ctx->scratch[0].as<int16_t>();
+  for (int g = 0; g < n_cifs; g++)
+    CK(cudaMemcpyAsync(dsoft + cif_offset(g), cifs + (size_t)g * CIF_BITS, sizeof(int16_t) * CIF_BITS,
+                       mem == DABSTAR_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+  std::vector<VitJob> jobs;
+  make_backend_jobs(jobs, prof, p, 0, 0, 0, n_cifs, sc->start_cu, 0);
+  void * dbits;
+  const size_t out_bytes = (size_t)n_out * p.n_bits;
+  if (int r = stage_out_begin(ctx, ctx->scratch[1], bits, out_bytes, mem, &dbits)) return r;
+  if (int r = run_viterbi_jobs(ctx, jobs, p.n_bits + 6, dsoft, (uint8_t *)dbits, nullptr, nullptr, ctx->scratch[2])) return r;
+  if (int r = stage_out_end(ctx, dbits, bits, out_bytes, mem)) return r;
+  return n_out;
+}
+
+struct dabstar_ofdm_state
+{
+  OfdmStateDev * dev = nullptr;
+};
+
+static int ofdm_state_init(dabstar_ctx * ctx, OfdmStateDev * dev, bool full, int count = 1)
+{
+  // full: constructor state (mMeanValue = 1); otherwise reset() which keeps mMeanValue (ofdm_decoder.cpp:90-101)
+  if (full)
+  {
+    static const float ones[2] = { 1.0f, 1.0f };
+    CK(cudaMemsetAsync(dev, 0, sizeof(OfdmStateDev) * (size_t)count, ctx->stream));
+    for (int i = 0; i < count; i++) CK(cudaMemcpyAsync(&dev[i].mean_value, ones, sizeof(ones), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  else
+  {
+    for (int i = 0; i < count; i++) CK(cudaMemsetAsync(&dev[i], 0, offsetof(OfdmStateDev, mean_value), ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int dabstar_ofdm_state_create(dabstar_ctx * ctx, dabstar_ofdm_state ** out)
+{
+  if (!ctx || !out) return DABSTAR_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  std::unique_ptr<dabstar_ofdm_state> st(new dabstar_ofdm_state);
+  CK(cudaMalloc(&st->dev, sizeof(OfdmStateDev)));
+  if (int r = ofdm_state_init(ctx, st->dev, true)) { cudaFree(st->dev); return r; }
+  *out = st.release();
+  return 0;
+}
+extern "C" void dabstar_ofdm_state_destroy(dabstar_ctx * ctx, dabstar_ofdm_state * st)
+{
+  if (!st) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  cudaFree(st->dev);
+  delete st;
+}
+extern "C" int dabstar_ofdm_state_reset(dabstar_ctx * ctx, dabstar_ofdm_state * st)
+{
+  if (!ctx || !st) return DABSTAR_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  return ofdm_state_init(ctx, st->dev, false);
+}
+extern "C" int dabstar_ofdm_state_get(dabstar_ctx * ctx, dabstar_ofdm_state * st, int which, float * out)
+{
+  if (!ctx || !st || !out || which < 0 || which > 5) return DABSTAR_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  OfdmStateDev * d = st->dev;
+  const float * src[6] = { d->integ, d->stddev, d->mean_pow, d->mean_sigma, d->null_pow, &d->mean_value };
+  CK(cudaMemcpy(out, src[which], sizeof(float) * (which == 5 ? 2 : K_CARR), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int dabstar_ofdm_decode_frames(dabstar_ctx * ctx, dabstar_ofdm_state * st, const float * fft, int n_frames, const float * clock_err,
+                                          const uint8_t * null_is_tii, int soft_bit_type, int16_t * soft, int mem)
+{
+  if (!ctx || !st || !fft || !soft || n_frames < 0 || soft_bit_type < 0 || soft_bit_type > 2) return DABSTAR_E_INVALID;
+  if (n_frames == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  const size_t in_bytes = sizeof(float2) * (size_t)n_frames * X_ROWS * T_U, out_bytes = sizeof(int16_t) * (size_t)n_frames * FRAME_SOFT;
+  const void * dfft; void * dsoft;
+  if (int r = stage_in(ctx, ctx->scratch[0], fft, in_bytes, mem, &dfft)) return r;
+  if (int r = stage_out_begin(ctx, ctx->scratch[1], soft, out_bytes, mem, &dsoft)) return r;
+  CK(ctx->scratch[2].reserve(sizeof(float2) * (size_t)n_frames * X_ROWS * K_CARR));
+  CK(launch_reorder_frames(ctx->stream, ctx->tab, (const float2 *)dfft, n_frames, ctx->scratch[2].as<float2>(), &ctx->launches));
+  std::vector<FrameDesc> fd((size_t)n_frames);
+  std::vector<uint8_t> tii((size_t)n_frames, 0);
+  for (int f = 0; f < n_frames; f++)
+  {
+    memset(&fd[f], 0, sizeof(FrameDesc));
+    fd[f].slot = f;
+    fd[f].xslot = f;
+    fd[f].clock_err = clock_err ? clock_err[f] : 0.0f;
+    fd[f].n_syms = 75;
+    if (null_is_tii) tii[f] = null_is_tii[f];
+  }
+  DemapWork wk{ 0, n_frames, 0, 0 };
+  CK(ctx->scratch[3].reserve(sizeof(FrameDesc) * fd.size() + sizeof(DemapWork) + tii.size() + 64));
+  char * aux = ctx->scratch[3].as<char>();
+  FrameDesc * dfd = reinterpret_cast<FrameDesc *>(aux);
+  DemapWork * dwk = reinterpret_cast<DemapWork *>(aux + sizeof(FrameDesc) * fd.size());
+  uint8_t * dtii = reinterpret_cast<uint8_t *>(dwk + 1);
+  CK(cudaMemcpyAsync(dfd, fd.data(), sizeof(FrameDesc) * fd.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dwk, &wk, sizeof(wk), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dtii, tii.data(), tii.size(), cudaMemcpyHostToDevice, ctx->stream));
+  // X rows of slot f live at f*77 rows; soft slot f at f*FRAME_SOFT: both match the tap's layout.
+  CK(launch_demap(ctx->stream, ctx->tab, dwk, 1, dfd, dtii, ctx->scratch[2].as<float2>(), st->dev, soft_bit_type, (int16_t *)dsoft, &ctx->launches));
+  return stage_out_end(ctx, dsoft, soft, out_bytes, mem);
+}
+
+extern "C" int dabstar_prs_correlate(dabstar_ctx * ctx, const float * samples, int n, float threshold, int strongest_peak, int32_t * start_index, int mem)
+{
+  if (!ctx || !samples || !start_index || n < 0) return DABSTAR_E_INVALID;
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  const void * din; void * dout;
+  if (int r = stage_in(ctx, ctx->scratch[0], samples, sizeof(float2) * T_U * (size_t)n, mem, &din)) return r;
+  if (int r = stage_out_begin(ctx, ctx->scratch[1], start_index, sizeof(int32_t) * (size_t)n, mem, &dout)) return r;
+  CK(launch_prs_corr_raw(ctx->stream, ctx->tab, (const float2 *)din, n, threshold, strongest_peak, (int *)dout, &ctx->launches));
+  return stage_out_end(ctx, dout, start_index, sizeof(int32_t) * (size_t)n, mem);
+}
+
+extern "C" int dabstar_estimate_carrier_offset(dabstar_ctx * ctx, const float * fft, int n, int32_t * offset_hz, int mem)
+{
+  if (!ctx || !fft || !offset_hz || n < 0) return DABSTAR_E_INVALID;
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  const void * din; void * dout;
+  if (int r = stage_in(ctx, ctx->scratch[0], fft, sizeof(float2) * T_U * (size_t)n, mem, &din)) return r;
+  if (int r = stage_out_begin(ctx, ctx->scratch[1], offset_hz, sizeof(int32_t) * (size_t)n, mem, &dout)) return r;
+  CK(launch_coarse_afc_raw(ctx->stream, ctx->tab, (const float2 *)din, n, (int *)dout, &ctx->launches));
+  return stage_out_end(ctx, dout, offset_hz, sizeof(int32_t) * (size_t)n, mem);
+}
+
+// ------------------------------------------------------------------------------------------------ whole path
+namespace
+{
+enum class RecState { WAIT_SYNC, EVAL, DONE };
+
+struct MscOut
+{
+  dabstar_subch sc;
+  int profile = -1;
+  std::vector<uint8_t> bits;
+};
+
+struct Recording
+{
+  // input
+  const void * d_iq = nullptr;
+  long long n = 0;
+  // DabProcessor / SampleReader state
+  RecState state = RecState::DONE;
+  long long pos = 0;       // samples consumed
+  int osc_phase = 0;       // SampleReader::currentPhase
+  float f_sync = 0, f_bb = 0, clock_err = 0, phase_cp = 0;
+  bool first_after_sync = true; // syncThreshold = mcThreshold until a frame has been processed (dab_processor.cpp:154,178)
+  int fic_ratio = 0;       // 0..10
+  int known_start = -2;    // PRS peak already measured for the next frame (-2 = not measured)
+  bool spec_ok = false;    // the previous frame's peak was T_g: speculate the next ones
+  int force_window = 0;    // replay length after a failed verification
+  bool ofdm_reset = true;  // OfdmDecoder::reset() pending
+  // bookkeeping
+  long long slot_base = 0; // first frame slot of this recording in the soft-bit / FIB buffers
+  int slot_cap = 0;
+  int n_slots = 0;         // accepted frames (complete ones)
+  int partial_syms = 0;    // data symbols of a trailing cut frame (occupies slot n_slots)
+  std::vector<dabstar_frame_info> frames;
+  std::vector<uint8_t> crc_ok; // 12 per frame
+  std::vector<MscOut> msc;
+  long long cnt_good_fibs = 0, cnt_sync_ok = 0, cnt_sync_fail = 0, cnt_windows = 0, cnt_cut = 0;
+  // window scratch
+  int w_first_desc = 0, w_frames = 0;
+  bool w_careful = false;
+};
+} // namespace
+
+struct dabstar_decoder
+{
+  dabstar_ctx * ctx = nullptr;
+  dabstar_decoder_cfg cfg{};
+  std::vector<Recording> recs;
+  DevBuf d_inputs;      // staged host input
+  DevBuf d_recs;        // RecInput[]
+  DevBuf d_soft;        // [total_slots][75*3072] int16
+  DevBuf d_fib;         // [total_slots][3072]
+  DevBuf d_crc;         // [total_slots][12]
+  DevBuf d_ber;         // [total_slots][8] int
+  DevBuf d_X;           // window: [frames][77][1536] float2
+  DevBuf d_states;      // OfdmStateDev[n_rec]
+  DevBuf d_snap;        // snapshot of d_states
+  DevBuf d_desc, d_work, d_cp, d_start, d_coarse, d_dipw, d_dipr, d_jobs, d_mscbits;
+  std::vector<uint8_t> h_fib;
+  std::vector<int16_t> h_soft_one;
+  long long total_slots = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double last_ms = 0;
+};
+
+static inline int mod_fs_host(long long x)
+{
+  long long r = x % FS;
+  return (int)(r < 0 ? r + FS : r);
+}
+
+extern "C" int dabstar_decoder_create(dabstar_ctx * ctx, const dabstar_decoder_cfg * cfg, int n_recordings, dabstar_decoder ** out)
+{
+  if (!ctx || !cfg || !out || n_recordings <= 0) return DABSTAR_E_INVALID;
+  if (cfg->input_format < 0 || cfg->input_format > 2 || cfg->soft_bit_type < 0 || cfg->soft_bit_type > 2)
+    return ctx->fail(DABSTAR_E_INVALID, "bad decoder configuration");
+  CK(cudaSetDevice(ctx->device));
+  std::unique_ptr<dabstar_decoder> d(new dabstar_decoder);
+  d->ctx = ctx;
+  d->cfg = *cfg;
+  if (d->cfg.max_window <= 0) d->cfg.max_window = 256;
+  if (d->cfg.sync_threshold <= 0.0f) d->cfg.sync_threshold = 3.0f;
+  d->recs.resize((size_t)n_recordings);
+  CK(cudaEventCreate(&d->ev0));
+  CK(cudaEventCreate(&d->ev1));
+  *out = d.release();
+  return 0;
+}
+
+extern "C" void dabstar_decoder_destroy(dabstar_decoder * dec)
+{
+  if (!dec) return;
+  cudaSetDevice(dec->ctx->device);
+  if (dec->ev0) cudaEventDestroy(dec->ev0);
+  if (dec->ev1) cudaEventDestroy(dec->ev1);
+  delete dec;
+}
+
+extern "C" int dabstar_decoder_set_subchannels(dabstar_decoder * dec, int recording, const dabstar_subch * sc, int n)
+{
+  if (!dec || recording < 0 || recording >= (int)dec->recs.size() || n < 0 || (n > 0 && !sc)) return DABSTAR_E_INVALID;
+  dabstar_ctx * ctx = dec->ctx;
+  Recording & r = dec->recs[recording];
+  r.msc.clear();
+  for (int i = 0; i < n; i++)
+  {
+    MscOut m;
+    m.sc = sc[i];
+    m.profile = get_profile(ctx, sc[i].short_form, sc[i].bit_rate, sc[i].prot_level);
+    if (m.profile < 0) return ctx->fail(DABSTAR_E_INVALID, "unknown protection profile %d/%d/%d", sc[i].short_form, sc[i].bit_rate, sc[i].prot_level);
+    const VitProfile & p = ctx->profiles[m.profile];
+    if (sc[i].start_cu < 0 || sc[i].size_cu <= 0 || sc[i].start_cu + sc[i].size_cu > 864 || p.n_kept > sc[i].size_cu * 64 || sc[i].start_frame < 0)
+      return ctx->fail(DABSTAR_E_INVALID, "sub-channel %d geometry does not fit", sc[i].sub_ch_id);
+    r.msc.push_back(m);
+  }
+  return 0;
+}
+
+namespace
+{
+// Host restatement of the per-frame control bookkeeping (dab_processor.cpp:191-265, 389-414).
+struct FrameCtl
+{
+  FrameDesc desc;
+  dabstar_frame_info info;
+};
+
+void ctl_begin_frame(Recording & r, int start_index, int n_syms, FrameCtl & fc)
+{
+  memset(&fc, 0, sizeof(fc));
+  fc.desc.eval = r.pos;
+  fc.desc.f_sym0 = (int)roundf(r.f_bb);
+  fc.desc.ph_eval = r.osc_phase;
+  fc.desc.sym0 = r.pos + start_index;
+  fc.desc.n_syms = n_syms;
+  fc.info.sym0_pos = fc.desc.sym0;
+  fc.info.start_index = start_index;
+  fc.info.fbb_sym0 = r.f_bb;
+  fc.info.fic_ratio_before = r.fic_ratio * 10;
+  r.osc_phase = mod_fs_host((long long)r.osc_phase - (long long)fc.desc.f_sym0 * (T_U + start_index));
+  r.pos += T_U + start_index;
+}
+
+// correction: result of the coarse AFC (only when the FIC ratio was below 30 %), or 0 with ran_coarse = false
+void ctl_after_coarse(Recording & r, bool ran_coarse, int correction, FrameCtl & fc)
+{
+  if (ran_coarse)
+  {
+    if (correction != 100000)
+    {
+      r.f_sync += (float)correction;
+      if (fabsf(r.f_sync) > 35000.0f) r.f_sync = 0.0f;
+    }
+    if (correction != 0) r.clock_err = 0.0f;
+    r.f_bb = r.f_sync;
+  }
+  fc.desc.f_data = (int)roundf(r.f_bb);
+  fc.desc.ph_data = r.osc_phase;
+  fc.desc.clock_err = r.clock_err;
+  fc.info.fbb_data = r.f_bb;
+  fc.info.clock_err = r.clock_err;
+}
+
+void ctl_finish_frame(Recording & r, float2 cp_raw, bool ran_coarse, int correction, FrameCtl & fc)
+{
+  const int n_syms = fc.desc.n_syms;
+  r.osc_phase = mod_fs_host((long long)r.osc_phase - (long long)fc.desc.f_data * ((long long)n_syms * T_S));
+  r.pos += (long long)n_syms * T_S;
+  if (n_syms < 75) return; // recording ends inside this frame
+  // the reference sums the derotated samples: raw sum times e^{-j 2 pi f / 1000}
+  const double ang = -2.0 * M_PI * (double)fc.desc.f_data / 1000.0;
+  const double cr = cos(ang), sr = sin(ang);
+  const float re = (float)((double)cp_raw.x * cr - (double)cp_raw.y * sr), im = (float)((double)cp_raw.x * sr + (double)cp_raw.y * cr);
+  float ph = atan2f(im, re);
+  const float lim = 20.0f * RAD_PER_DEG_F;
+  ph = ph > lim ? lim : (ph < -lim ? -lim : ph);
+  r.phase_cp = ph;
+  r.f_sync += ph / TWO_PI_F * 1000.0f;
+  r.f_bb = r.f_sync;
+  fc.desc.f_null = (int)roundf(r.f_bb);
+  fc.desc.ph_null = r.osc_phase;
+  r.osc_phase = mod_fs_host((long long)r.osc_phase - (long long)fc.desc.f_null * T_N);
+  r.pos += T_N;
+  fc.info.fbb_null = r.f_bb;
+  fc.info.fsync = r.f_sync;
+  fc.info.phase_cp = ph;
+  if (!ran_coarse || correction == 0)
+  {
+    const int sample_count = fc.info.start_index + T_U + 75 * T_S + T_N;
+    float ce = (float)FS * ((float)sample_count / (float)T_F - 1.0f);
+    ce = ce > 307.2f ? 307.2f : (ce < -307.2f ? -307.2f : ce);
+    r.clock_err += 0.1f * (ce - r.clock_err);
+  }
+}
+
+struct CtlSnapshot
+{
+  long long pos; int osc_phase; float f_sync, f_bb, clock_err, phase_cp; int fic_ratio;
+};
+CtlSnapshot take(const Recording & r) { return { r.pos, r.osc_phase, r.f_sync, r.f_bb, r.clock_err, r.phase_cp, r.fic_ratio }; }
+void restore(Recording & r, const CtlSnapshot & s)
+{
+  r.pos = s.pos; r.osc_phase = s.osc_phase; r.f_sync = s.f_sync; r.f_bb = s.f_bb; r.clock_err = s.clock_err; r.phase_cp = s.phase_cp; r.fic_ratio = s.fic_ratio;
+}
+} // namespace
+
+extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * iq, const int64_t * n_samples, int mem)
+{
+  if (!dec || !iq || !n_samples) return DABSTAR_E_INVALID;
+  dabstar_ctx * ctx = dec->ctx;
+  CK(cudaSetDevice(ctx->device));
+  const int n_rec = (int)dec->recs.size();
+  const int fmt = dec->cfg.input_format;
+  const size_t bps = fmt == FMT_U8 ? 2 : (fmt == FMT_I16 ? 4 : 8);
+  cudaStream_t st = ctx->stream;
+  CK(cudaEventRecord(dec->ev0, st));
+
+  // ---- inputs
+  std::vector<RecInput> rin((size_t)n_rec);
+  if (mem == DABSTAR_MEM_HOST)
+  {
+    size_t total = 0;
+    for (int r = 0; r < n_rec; r++) total += ((size_t)n_samples[r] * bps + 255) & ~(size_t)255;
+    CK(dec->d_inputs.reserve(total));
+    size_t off = 0;
+    for (int r = 0; r < n_rec; r++)
+    {
+      char * p = dec->d_inputs.as<char>() + off;
+      CK(cudaMemcpyAsync(p, iq[r], (size_t)n_samples[r] * bps, cudaMemcpyHostToDevice, st));
+      rin[r] = { p, (long long)n_samples[r] };
+      off += ((size_t)n_samples[r] * bps + 255) & ~(size_t)255;
+    }
+  }
+  else for (int r = 0; r < n_rec; r++) rin[r] = { iq[r], (long long)n_samples[r] };
+  CK(dec->d_recs.reserve(sizeof(RecInput) * (size_t)n_rec));
+  CK(cudaMemcpyAsync(dec->d_recs.p, rin.data(), sizeof(RecInput) * (size_t)n_rec, cudaMemcpyHostToDevice, st));
+  const RecInput * d_rin = dec->d_recs.as<RecInput>();
+
+  // ---- per-recording reset (DabProcessor::run prologue, dab_processor.cpp:110-142)
+  dec->total_slots = 0;
+  for (int r = 0; r < n_rec; r++)
+  {
+    Recording & R = dec->recs[r];
+    std::vector<MscOut> keep = std::move(R.msc);
+    R = Recording();
+    R.msc = std::move(keep);
+    for (auto & m : R.msc) m.bits.clear();
+    R.d_iq = rin[r].iq;
+    R.n = rin[r].n;
+    R.slot_base = dec->total_slots;
+    R.slot_cap = (int)(R.n / T_F) + 2;
+    dec->total_slots += R.slot_cap;
+    R.pos = 20LL * T_U; // 20 reads of T_u samples for the level estimate, no mixing (f = 0)
+    R.state = R.pos <= R.n ? RecState::WAIT_SYNC : RecState::DONE;
+    R.ofdm_reset = true;
+  }
+  CK(dec->d_soft.reserve(sizeof(int16_t) * (size_t)dec->total_slots * FRAME_SOFT));
+  CK(dec->d_fib.reserve((size_t)dec->total_slots * 3072));
+  CK(dec->d_crc.reserve((size_t)dec->total_slots * 12));
+  CK(dec->d_ber.reserve(sizeof(int) * (size_t)dec->total_slots * 8));
+  CK(dec->d_states.reserve(sizeof(OfdmStateDev) * (size_t)n_rec));
+  CK(dec->d_snap.reserve(sizeof(OfdmStateDev) * (size_t)n_rec));
+  if (int e = ofdm_state_init(ctx, dec->d_states.as<OfdmStateDev>(), true, n_rec)) return e;
+  CK(cudaMemsetAsync(dec->d_crc.p, 0, (size_t)dec->total_slots * 12, st));
+
+  const float thr0 = dec->cfg.sync_threshold;
+  // X budget: bound the frames of one round so the window spectrum buffer stays below ~12 GB
+  const long long x_frame_bytes = (long long)sizeof(float2) * X_ROWS * K_CARR;
+  const long long max_round_frames = std::max<long long>(n_rec, (12LL << 30) / x_frame_bytes);
+
+  std::vector<FrameCtl> ctl;
+  std::vector<CtlSnapshot> snaps((size_t)n_rec);
+  std::vector<int> win_recs;
+
+  while (true)
+  {
+    // ================= time sync for recordings without frame lock
+    {
+      std::vector<DipWork> dw;
+      std::vector<int> who;
+      for (int r = 0; r < n_rec; r++)
+      {
+        Recording & R = dec->recs[r];
+        if (R.state != RecState::WAIT_SYNC) continue;
+        R.ofdm_reset = true;       // dab_processor.cpp:149
+        R.first_after_sync = true; // syncThreshold = mcThreshold
+        R.known_start = -2;
+        R.spec_ok = false;
+        dw.push_back({ r, R.pos });
+        who.push_back(r);
+      }
+      if (!dw.empty())
+      {
+        CK(dec->d_dipw.reserve(sizeof(DipWork) * dw.size()));
+        CK(dec->d_dipr.reserve(sizeof(DipResult) * dw.size()));
+        CK(cudaMemcpyAsync(dec->d_dipw.p, dw.data(), sizeof(DipWork) * dw.size(), cudaMemcpyHostToDevice, st));
+        CK(launch_dip_search(st, dec->d_dipw.as<DipWork>(), (int)dw.size(), d_rin, fmt, dec->d_dipr.as<DipResult>(), &ctx->launches));
+        std::vector<DipResult> dr(dw.size());
+        CK(cudaMemcpyAsync(dr.data(), dec->d_dipr.p, sizeof(DipResult) * dw.size(), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < who.size(); i++)
+        {
+          Recording & R = dec->recs[who[i]];
+          R.pos = dr[i].pos;
+          R.clock_err = 0.0f; // dab_processor.cpp:158
+          if (dr[i].status == 0) { R.state = RecState::EVAL; R.cnt_sync_ok++; }
+          else if (dr[i].status == 3) R.state = RecState::DONE;
+          else R.cnt_sync_fail++;
+        }
+      }
+    }
+
+    // ================= lay out this round's windows
+    ctl.clear();
+    win_recs.clear();
+    long long budget = max_round_frames;
+    bool any_wait = false;
+    for (int r = 0; r < n_rec; r++)
+    {
+      Recording & R = dec->recs[r];
+      if (R.state == RecState::WAIT_SYNC) { any_wait = true; continue; }
+      if (R.state != RecState::EVAL) continue;
+      if (R.pos + T_U > R.n) { R.state = RecState::DONE; continue; } // the eval read hits the end of the data
+      R.w_careful = (R.fic_ratio * 10 < 30) || (R.known_start == -2 && !R.spec_ok);
+      R.w_first_desc = (int)ctl.size();
+      R.w_frames = 0;
+      snaps[r] = take(R);
+      win_recs.push_back(r);
+    }
+    if (win_recs.empty()) { if (any_wait) continue; break; }
+
+    // ---- step A: measure the PRS peak of the first frame where it is not known and not speculated
+    {
+      std::vector<FrameDesc> fd;
+      std::vector<uint8_t> first;
+      std::vector<int> who;
+      for (int r : win_recs)
+      {
+        Recording & R = dec->recs[r];
+        if (!(R.w_careful && R.known_start == -2)) continue;
+        FrameDesc d;
+        memset(&d, 0, sizeof(d));
+        d.rec = r; d.eval = R.pos; d.f_sym0 = (int)roundf(R.f_bb); d.ph_eval = R.osc_phase;
+        fd.push_back(d);
+        first.push_back(R.first_after_sync ? 1 : 0);
+        who.push_back(r);
+      }
+      if (!fd.empty())
+      {
+        CK(dec->d_desc.reserve(sizeof(FrameDesc) * fd.size() + fd.size() + 64));
+        CK(dec->d_start.reserve(sizeof(int) * fd.size()));
+        uint8_t * dfirst = dec->d_desc.as<uint8_t>() + sizeof(FrameDesc) * fd.size();
+        CK(cudaMemcpyAsync(dec->d_desc.p, fd.data(), sizeof(FrameDesc) * fd.size(), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dfirst, first.data(), first.size(), cudaMemcpyHostToDevice, st));
+        CK(launch_prs_corr(st, ctx->tab, dec->d_desc.as<FrameDesc>(), (int)fd.size(), d_rin, fmt, thr0, 2.0f * thr0, dfirst,
+                           dec->cfg.strongest_peak, dec->d_start.as<int>(), &ctx->launches));
+        std::vector<int> si(fd.size());
+        CK(cudaMemcpyAsync(si.data(), dec->d_start.p, sizeof(int) * fd.size(), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < who.size(); i++)
+        {
+          Recording & R = dec->recs[who[i]];
+          if (si[i] < 0)
+          {
+            // no peak: the 2048 samples are consumed and the time sync starts over (dab_processor.cpp:397-401)
+            R.osc_phase = mod_fs_host((long long)R.osc_phase - (long long)roundf(R.f_bb) * T_U);
+            R.pos += T_U;
+            R.state = RecState::WAIT_SYNC;
+          }
+          else R.known_start = si[i];
+        }
+        win_recs.erase(std::remove_if(win_recs.begin(), win_recs.end(), [&](int r) { return dec->recs[r].state != RecState::EVAL; }), win_recs.end());
+        if (win_recs.empty()) continue;
+      }
+    }
+
+    // ---- frame layout (positions only; AFC values are filled in after the CP correlation)
+    struct Plan { int rec, n_frames, n_syms_last; };
+    std::vector<Plan> plans;
+    for (int r : win_recs)
+    {
+      Recording & R = dec->recs[r];
+      const int s0 = R.known_start >= 0 ? R.known_start : T_G;
+      long long p = R.pos;
+      int want = R.w_careful ? 1 : (R.force_window > 0 ? R.force_window : dec->cfg.max_window);
+      want = (int)std::min<long long>(want, std::max<long long>(1, budget / std::max<size_t>(1, win_recs.size())));
+      want = std::min(want, R.slot_cap - R.n_slots);
+      int nf = 0, last_syms = 75;
+      for (int j = 0; j < want; j++)
+      {
+        const int s = j == 0 ? s0 : T_G;
+        if (p + T_U + s > R.n) break;                          // eval window + rest of symbol 0 not available
+        const long long after_sym0 = p + T_U + s;
+        const long long avail = R.n - after_sym0;
+        if (avail >= 75LL * T_S + T_N) { nf++; p = after_sym0 + 75LL * T_S + T_N; continue; }
+        // the recording ends inside this frame: the reference still decodes the symbols it could read
+        last_syms = (int)std::min<long long>(75, avail / T_S);
+        nf++;
+        break;
+      }
+      if (nf == 0) { R.state = RecState::DONE; continue; }
+      plans.push_back({ r, nf, last_syms });
+      budget -= nf;
+    }
+    if (plans.empty()) continue;
+
+    // descriptors with positions; AFC fields provisional
+    ctl.clear();
+    for (auto & pl : plans)
+    {
+      Recording & R = dec->recs[pl.rec];
+      R.w_first_desc = (int)ctl.size();
+      R.w_frames = pl.n_frames;
+      long long p = R.pos;
+      const int s0 = R.known_start >= 0 ? R.known_start : T_G;
+      for (int j = 0; j < pl.n_frames; j++)
+      {
+        FrameCtl fc;
+        memset(&fc, 0, sizeof(fc));
+        const int s = j == 0 ? s0 : T_G;
+        fc.desc.rec = pl.rec;
+        fc.desc.eval = p;
+        fc.desc.sym0 = p + s;
+        fc.desc.n_syms = (j == pl.n_frames - 1) ? pl.n_syms_last : 75;
+        fc.desc.slot = (int)(R.slot_base + R.n_slots + j);
+        fc.desc.xslot = (int)ctl.size();
+        ctl.push_back(fc);
+        p += T_U + s + 75LL * T_S + T_N;
+      }
+    }
+    const int n_desc = (int)ctl.size();
+    std::vector<FrameDesc> fdv((size_t)n_desc);
+    for (int i = 0; i < n_desc; i++) fdv[i] = ctl[i].desc;
+    CK(dec->d_desc.reserve(sizeof(FrameDesc) * (size_t)n_desc + (size_t)n_desc + 64));
+    CK(cudaMemcpyAsync(dec->d_desc.p, fdv.data(), sizeof(FrameDesc) * (size_t)n_desc, cudaMemcpyHostToDevice, st));
+    FrameDesc * d_fd = dec->d_desc.as<FrameDesc>();
+
+    // ---- CP correlation on raw samples (all frames) and coarse AFC (careful frames), then the scalar recurrences
+    CK(dec->d_cp.reserve(sizeof(float2) * (size_t)n_desc));
+    CK(launch_cp_corr(st, d_fd, n_desc, d_rin, fmt, dec->d_cp.as<float2>(), &ctx->launches));
+    std::vector<float2> cp((size_t)n_desc);
+    CK(cudaMemcpyAsync(cp.data(), dec->d_cp.p, sizeof(float2) * (size_t)n_desc, cudaMemcpyDeviceToHost, st));
+    std::vector<int> coarse((size_t)n_desc, 0);
+    {
+      // coarse AFC needs symbol 0 derotated with the CURRENT f_bb / phase, which are known for the first frame of a window
+      std::vector<FrameDesc> cf;
+      std::vector<int> idx;
+      for (auto & pl : plans)
+      {
+        Recording & R = dec->recs[pl.rec];
+        if (!(R.fic_ratio * 10 < 30)) continue;
+        FrameDesc d = ctl[R.w_first_desc].desc;
+        d.f_sym0 = (int)roundf(R.f_bb);
+        d.ph_eval = R.osc_phase;
+        cf.push_back(d);
+        idx.push_back(R.w_first_desc);
+      }
+      if (!cf.empty())
+      {
+        CK(dec->d_work.reserve(sizeof(FrameDesc) * cf.size()));
+        CK(dec->d_coarse.reserve(sizeof(int) * cf.size()));
+        CK(cudaMemcpyAsync(dec->d_work.p, cf.data(), sizeof(FrameDesc) * cf.size(), cudaMemcpyHostToDevice, st));
+        CK(launch_coarse_afc(st, ctx->tab, dec->d_work.as<FrameDesc>(), (int)cf.size(), d_rin, fmt, dec->d_coarse.as<int>(), &ctx->launches));
+        std::vector<int> res(cf.size());
+        CK(cudaMemcpyAsync(res.data(), dec->d_coarse.p, sizeof(int) * cf.size(), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < idx.size(); i++) coarse[idx[i]] = res[i];
+      }
+    }
+    CK(cudaStreamSynchronize(st));
+
+    for (auto & pl : plans)
+    {
+      Recording & R = dec->recs[pl.rec];
+      const int s0 = R.known_start >= 0 ? R.known_start : T_G;
+      for (int j = 0; j < pl.n_frames; j++)
+      {
+        const int i = R.w_first_desc + j;
+        const int slot = ctl[i].desc.slot, n_syms = ctl[i].desc.n_syms;
+        FrameCtl fc;
+        ctl_begin_frame(R, j == 0 ? s0 : T_G, n_syms, fc);
+        const bool ran_coarse = (j == 0) && (R.fic_ratio * 10 < 30);
+        ctl_after_coarse(R, ran_coarse, coarse[i], fc);
+        ctl_finish_frame(R, cp[i], ran_coarse, coarse[i], fc);
+        fc.desc.rec = pl.rec;
+        fc.desc.slot = slot;
+        fc.desc.xslot = i;
+        ctl[i] = fc;
+      }
+    }
+    for (int i = 0; i < n_desc; i++) fdv[i] = ctl[i].desc;
+    CK(cudaMemcpyAsync(dec->d_desc.p, fdv.data(), sizeof(FrameDesc) * (size_t)n_desc, cudaMemcpyHostToDevice, st));
+
+    // ---- verification input: PRS peak of every frame whose start index was speculated
+    std::vector<uint8_t> first_flags((size_t)n_desc, 0);
+    for (auto & pl : plans) if (dec->recs[pl.rec].first_after_sync) first_flags[dec->recs[pl.rec].w_first_desc] = 1;
+    uint8_t * d_first = dec->d_desc.as<uint8_t>() + sizeof(FrameDesc) * (size_t)n_desc;
+    CK(cudaMemcpyAsync(d_first, first_flags.data(), (size_t)n_desc, cudaMemcpyHostToDevice, st));
+    CK(dec->d_start.reserve(sizeof(int) * (size_t)n_desc));
+    CK(launch_prs_corr(st, ctx->tab, d_fd, n_desc, d_rin, fmt, thr0, 2.0f * thr0, d_first, dec->cfg.strongest_peak, dec->d_start.as<int>(), &ctx->launches));
+
+    // ---- heavy pass: FFT (+ingest, derotation, de-interleave) -> demap -> FIC
+    CK(dec->d_work.reserve(sizeof(DemapWork) * plans.size() + 64));
+    CK(dec->d_X.reserve((size_t)x_frame_bytes * (size_t)n_desc));
+    CK(launch_fft_frames(st, ctx->tab, d_fd, n_desc, d_rin, fmt, dec->d_X.as<float2>(), &ctx->launches));
+    CK(cudaMemcpyAsync(dec->d_snap.p, dec->d_states.p, sizeof(OfdmStateDev) * (size_t)n_rec, cudaMemcpyDeviceToDevice, st));
+    {
+      std::vector<DemapWork> wk;
+      for (auto & pl : plans)
+      {
+        Recording & R = dec->recs[pl.rec];
+        wk.push_back({ R.w_first_desc, pl.n_frames, pl.rec, R.ofdm_reset ? 1 : 0 });
+      }
+      DemapWork * d_wk = dec->d_work.as<DemapWork>();
+      CK(cudaMemcpyAsync(d_wk, wk.data(), sizeof(DemapWork) * wk.size(), cudaMemcpyHostToDevice, st));
+      CK(launch_demap(st, ctx->tab, d_wk, (int)wk.size(), d_fd, nullptr, dec->d_X.as<float2>(), dec->d_states.as<OfdmStateDev>(), dec->cfg.soft_bit_type,
+                      dec->d_soft.as<int16_t>(), &ctx->launches));
+    }
+    {
+      std::vector<VitJob> jobs;
+      jobs.reserve((size_t)4 * n_desc);
+      for (int i = 0; i < n_desc; i++)
+      {
+        const int n_fic = std::min(4, ctl[i].desc.n_syms * SYM_BITS / FIC_IN);
+        make_fic_jobs(jobs, (long long)ctl[i].desc.slot * FRAME_SOFT, (long long)ctl[i].desc.slot * 3072, 4 * ctl[i].desc.slot, n_fic);
+      }
+      if (int e = run_viterbi_jobs(ctx, jobs, FIC_OUT + 6, dec->d_soft.as<int16_t>(), dec->d_fib.as<uint8_t>(), dec->d_crc.as<uint8_t>(), dec->d_ber.as<int>(), dec->d_jobs)) return e;
+    }
+
+    // ---- read back the verification data
+    std::vector<int> start((size_t)n_desc);
+    CK(cudaMemcpyAsync(start.data(), dec->d_start.p, sizeof(int) * (size_t)n_desc, cudaMemcpyDeviceToHost, st));
+    std::vector<uint8_t> crc((size_t)n_desc * 12);
+    for (auto & pl : plans)
+    {
+      Recording & R = dec->recs[pl.rec];
+      CK(cudaMemcpyAsync(crc.data() + (size_t)R.w_first_desc * 12, dec->d_crc.as<uint8_t>() + (size_t)ctl[R.w_first_desc].desc.slot * 12,
+                         (size_t)pl.n_frames * 12, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+
+    // ---- verify and accept
+    bool need_restore = false;
+    std::vector<int> restore_recs;
+    for (auto & pl : plans)
+    {
+      Recording & R = dec->recs[pl.rec];
+      R.cnt_windows++;
+      const int base = R.w_first_desc;
+      const int s0 = R.known_start >= 0 ? R.known_start : T_G;
+      int ratio = snaps[pl.rec].fic_ratio;
+      int valid = 0;
+      int next_start = -2;
+      bool lost = false;
+      std::vector<int> ratio_after((size_t)pl.n_frames);
+      for (int j = 0; j < pl.n_frames; j++)
+      {
+        const int i = base + j;
+        const int expect = j == 0 ? s0 : T_G;
+        if (!(j == 0 && R.known_start >= 0) && start[i] != expect)
+        {
+          // frame j does not start where the layout assumed
+          if (start[i] < 0) lost = true; else next_start = start[i];
+          break;
+        }
+        if (j > 0 && ratio * 10 < 30) break; // this frame needed the coarse AFC: replay it as the first frame of a careful window
+        const int n_fic = std::min(4, ctl[i].desc.n_syms * SYM_BITS / FIC_IN);
+        for (int b = 0; b < n_fic; b++)
+          for (int q = 0; q < 3; q++)
+          {
+            if (crc[(size_t)i * 12 + 3 * b + q]) { if (ratio < 10) ratio++; }
+            else if (ratio > 0) ratio--;
+          }
+        ratio_after[j] = ratio;
+        valid++;
+      }
+      if (valid == pl.n_frames)
+      {
+        // whole window verified: commit
+        for (int j = 0; j < pl.n_frames; j++)
+        {
+          const int i = base + j;
+          const bool complete = ctl[i].desc.n_syms == 75;
+          ctl[i].info.fic_ratio_after = ratio_after[j] * 10;
+          const int n_fic = std::min(4, ctl[i].desc.n_syms * SYM_BITS / FIC_IN);
+          for (int b = 0; b < 4; b++)
+          {
+            bool ok = b < n_fic;
+            for (int q = 0; q < 3 && ok; q++) ok = crc[(size_t)i * 12 + 3 * b + q] != 0;
+            ctl[i].info.fic_valid[b] = ok ? 1 : 0;
+            for (int q = 0; q < 3; q++) if (b < n_fic && crc[(size_t)i * 12 + 3 * b + q]) R.cnt_good_fibs++;
+          }
+          if (complete)
+          {
+            R.frames.push_back(ctl[i].info);
+            R.crc_ok.insert(R.crc_ok.end(), crc.begin() + (size_t)i * 12, crc.begin() + (size_t)i * 12 + 12);
+            R.n_slots++;
+          }
+          else { R.partial_syms = ctl[i].desc.n_syms; R.state = RecState::DONE; }
+        }
+        R.fic_ratio = ratio;
+        R.ofdm_reset = false;
+        R.force_window = 0;
+        R.known_start = -2;
+        R.spec_ok = true;
+        R.first_after_sync = false;
+      }
+      else
+      {
+        // roll back this recording and replay the verified prefix (or handle the event at frame 0)
+        R.cnt_cut++;
+        restore(R, snaps[pl.rec]);
+        restore_recs.push_back(pl.rec);
+        need_restore = true;
+        if (valid > 0) { R.force_window = valid; }
+        else
+        {
+          R.force_window = 0;
+          if (lost)
+          {
+            R.osc_phase = mod_fs_host((long long)R.osc_phase - (long long)roundf(R.f_bb) * T_U);
+            R.pos += T_U;
+            R.state = RecState::WAIT_SYNC;
+          }
+          else if (next_start >= 0) { R.known_start = next_start; R.spec_ok = false; }
+          else { R.spec_ok = false; } // FIC ratio dropped below 30 % at the first frame: careful mode follows from the ratio
+        }
+      }
+    }
+    if (need_restore)
+    {
+      for (int r : restore_recs)
+        CK(cudaMemcpyAsync(dec->d_states.as<OfdmStateDev>() + r, dec->d_snap.as<OfdmStateDev>() + r, sizeof(OfdmStateDev), cudaMemcpyDeviceToDevice, st));
+    }
+  }
+
+  // ================= MSC: all logical frames of all sub-channels in one batch per profile size
+  if (!dec->cfg.scan_mode)
+  {
+    std::map<int, std::vector<VitJob>> by_steps; // group launches by code-word length (shared-memory footprint)
+    long long out_total = 0;
+    struct OutRef { int rec, ch; long long off, len; };
+    std::vector<OutRef> outs;
+    for (int r = 0; r < n_rec; r++)
+    {
+      Recording & R = dec->recs[r];
+      const int n_cifs = 4 * R.n_slots + std::max(0, (R.partial_syms - 3) / 18);
+      for (size_t c = 0; c < R.msc.size(); c++)
+      {
+        MscOut & m = R.msc[c];
+        const VitProfile & p = ctx->profiles[m.profile];
+        const int g_start = 4 * m.sc.start_frame;
+        const int n_out = std::max(0, n_cifs - (g_start + 16));
+        m.bits.assign((size_t)n_out * p.n_bits, 0);
+        if (n_out == 0) continue;
+        make_backend_jobs(by_steps[p.n_bits + 6], m.profile, p, R.slot_base * FRAME_SOFT, g_start, 0, n_cifs, m.sc.start_cu, out_total);
+        outs.push_back({ r, (int)c, out_total, (long long)n_out * p.n_bits });
+        out_total += (long long)n_out * p.n_bits;
+      }
+    }
+    if (out_total > 0)
+    {
+      CK(dec->d_mscbits.reserve((size_t)out_total));
+      for (auto & kv : by_steps)
+        if (int e = run_viterbi_jobs(ctx, kv.second, kv.first, dec->d_soft.as<int16_t>(), dec->d_mscbits.as<uint8_t>(), nullptr, nullptr, dec->d_jobs))
+          return e;
+        else CK(cudaStreamSynchronize(st)); // d_jobs is reused by the next group
+      for (auto & o : outs)
+        CK(cudaMemcpyAsync(dec->recs[o.rec].msc[o.ch].bits.data(), dec->d_mscbits.as<uint8_t>() + o.off, (size_t)o.len, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  // FIB bits of all accepted frames
+  dec->h_fib.assign((size_t)dec->total_slots * 3072, 0);
+  for (int r = 0; r < n_rec; r++)
+  {
+    Recording & R = dec->recs[r];
+    if (R.n_slots > 0)
+      CK(cudaMemcpyAsync(dec->h_fib.data() + (size_t)R.slot_base * 3072, dec->d_fib.as<uint8_t>() + (size_t)R.slot_base * 3072, (size_t)R.n_slots * 3072, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaEventRecord(dec->ev1, st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, dec->ev0, dec->ev1));
+  dec->last_ms = ms;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ results
+extern "C" int dabstar_decoder_n_frames(const dabstar_decoder * dec, int recording)
+{
+  if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  return dec->recs[recording].n_slots;
+}
+extern "C" int dabstar_decoder_frame_info(const dabstar_decoder * dec, int recording, dabstar_frame_info * out, int cap)
+{
+  if (!dec || !out || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  const Recording & R = dec->recs[recording];
+  const int n = std::min<int>(cap, (int)R.frames.size());
+  for (int i = 0; i < n; i++) out[i] = R.frames[i];
+  return n;
+}
+extern "C" int dabstar_decoder_fib_bits(const dabstar_decoder * dec, int recording, uint8_t * bits, uint8_t * valid)
+{
+  if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  const Recording & R = dec->recs[recording];
+  if (bits && R.n_slots > 0) memcpy(bits, dec->h_fib.data() + (size_t)R.slot_base * 3072, (size_t)R.n_slots * 3072);
+  if (valid) for (int i = 0; i < R.n_slots; i++) memcpy(valid + 4 * i, R.frames[i].fic_valid, 4);
+  return R.n_slots;
+}
+extern "C" int dabstar_decoder_soft_bits(const dabstar_decoder * dec, int recording, int frame, int16_t * out)
+{
+  if (!dec || !out || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  const Recording & R = dec->recs[recording];
+  if (frame < 0 || frame >= R.n_slots) return DABSTAR_E_INVALID;
+  if (cudaSetDevice(dec->ctx->device) != cudaSuccess) return DABSTAR_E_CUDA;
+  if (cudaMemcpy(out, dec->d_soft.as<int16_t>() + (size_t)(R.slot_base + frame) * FRAME_SOFT, sizeof(int16_t) * FRAME_SOFT, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return DABSTAR_E_CUDA;
+  return 0;
+}
+static const MscOut * find_msc(const dabstar_decoder * dec, int recording, int sub_ch_id)
+{
+  if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return nullptr;
+  for (const auto & m : dec->recs[recording].msc) if (m.sc.sub_ch_id == sub_ch_id) return &m;
+  return nullptr;
+}
+extern "C" int64_t dabstar_decoder_msc_size(const dabstar_decoder * dec, int recording, int sub_ch_id)
+{
+  const MscOut * m = find_msc(dec, recording, sub_ch_id);
+  return m ? (int64_t)m->bits.size() : 0;
+}
+extern "C" int64_t dabstar_decoder_msc_copy(const dabstar_decoder * dec, int recording, int sub_ch_id, uint8_t * out, int64_t cap)
+{
+  const MscOut * m = find_msc(dec, recording, sub_ch_id);
+  if (!m || !out) return 0;
+  const int64_t n = std::min<int64_t>(cap, (int64_t)m->bits.size());
+  memcpy(out, m->bits.data(), (size_t)n);
+  return n;
+}
+extern "C" int dabstar_decoder_counters(const dabstar_decoder * dec, int recording, int64_t out[8])
+{
+  if (!dec || !out || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  const Recording & R = dec->recs[recording];
+  out[0] = R.cnt_good_fibs; out[1] = R.cnt_sync_ok; out[2] = R.cnt_sync_fail; out[3] = R.pos;
+  out[4] = R.cnt_windows; out[5] = R.cnt_cut; out[6] = R.n_slots; out[7] = R.partial_syms;
+  return 0;
+}
+extern "C" double dabstar_decoder_last_ms(const dabstar_decoder * dec) { return dec ? dec->last_ms : 0.0; }

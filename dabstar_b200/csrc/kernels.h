@@ -1,0 +1,72 @@
+// kernels.h — host-callable launchers of the sm_100a kernels (one translation unit per kernel family).
+#pragma once
+#include "common.cuh"
+#include "viterbi.cuh"
+
+namespace dab
+{
+// Device-resident constant tables, built once per context (tables.cu).
+struct DeviceTables
+{
+  float2 * w2048;        // e^{-j 2 pi m / 2048}
+  float2 * prs;          // phase reference symbol, fft order
+  float2 * ref_arg_conj; // coarse-AFC reference (phasereference.cpp:58-66), filled by init_ref_arg
+  int16_t * bin_of_k;    // frequency interleaver: nominal carrier k -> fft index 0..2047
+  int16_t * rel_of_k;    // realCarrRelIdx of carrier k (ofdm_decoder.cpp:169-180)
+  uint8_t * prbs;        // energy dispersal sequence, 9216 bits
+};
+
+// Per-recording OFDM decoder state in HBM (ofdm_decoder.h:89-103), nominal carrier order.
+struct OfdmStateDev
+{
+  float integ[K_CARR], stddev[K_CARR], mean_pow[K_CARR], mean_sigma[K_CARR], null_pow[K_CARR];
+  float mean_value;
+  float mean_pow_all;
+  float pad[2];
+};
+
+struct DemapWork
+{
+  int desc_first;  // first FrameDesc of this recording in the window
+  int n_frames;
+  int state;       // index into the OfdmStateDev array
+  int reset;       // OfdmDecoder::reset() before the first frame (after a time-sync loss)
+};
+
+struct DipWork
+{
+  int rec;
+  long long pos;   // stream position where TimeSyncer::read_samples_until_end_of_level_drop starts
+};
+struct DipResult
+{
+  long long pos;   // stream position after the call
+  int status;      // 0 established, 1 no dip, 2 no end of dip, 3 end of data
+  float s_level;
+};
+
+// viterbi_kernels.cu
+int viterbi_smem_bytes(int max_steps, int warps);
+cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, int n_jobs, const VitProfile * profiles, int max_steps,
+                           const int16_t * soft, uint8_t * out_bits, const uint8_t * prbs, uint8_t * crc_ok, int * ber,
+                           unsigned long long * launch_counter);
+
+// ofdm_kernels.cu
+cudaError_t launch_init_ref_arg(cudaStream_t s, const DeviceTables & t, unsigned long long * lc);
+cudaError_t launch_fft_batch(cudaStream_t s, const DeviceTables & t, const float2 * in, float2 * out, int n, int sign, unsigned long long * lc);
+cudaError_t launch_fft_frames(cudaStream_t s, const DeviceTables & t, const FrameDesc * frames, int n_frames, const RecInput * recs, int fmt,
+                              float2 * X, unsigned long long * lc);
+cudaError_t launch_reorder_frames(cudaStream_t s, const DeviceTables & t, const float2 * fft_nat, int n_frames, float2 * X, unsigned long long * lc);
+cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork * work, int n_work, const FrameDesc * frames,
+                         const uint8_t * null_is_tii, const float2 * X, OfdmStateDev * states, int soft_bit_type, int16_t * soft,
+                         unsigned long long * lc);
+cudaError_t launch_cp_corr(cudaStream_t s, const FrameDesc * frames, int n_frames, const RecInput * recs, int fmt, float2 * cp, unsigned long long * lc);
+cudaError_t launch_prs_corr(cudaStream_t s, const DeviceTables & t, const FrameDesc * frames, int n_frames, const RecInput * recs, int fmt,
+                            float threshold_first, float threshold_rest, const uint8_t * first_flags, int strongest, int * start_index, unsigned long long * lc);
+cudaError_t launch_prs_corr_raw(cudaStream_t s, const DeviceTables & t, const float2 * samples, int n, float threshold, int strongest,
+                                int * start_index, unsigned long long * lc);
+cudaError_t launch_coarse_afc(cudaStream_t s, const DeviceTables & t, const FrameDesc * frames, int n_frames, const RecInput * recs, int fmt,
+                              int * offset_hz, unsigned long long * lc);
+cudaError_t launch_coarse_afc_raw(cudaStream_t s, const DeviceTables & t, const float2 * fft_nat, int n, int * offset_hz, unsigned long long * lc);
+cudaError_t launch_dip_search(cudaStream_t s, const DipWork * work, int n, const RecInput * recs, int fmt, DipResult * out, unsigned long long * lc);
+} // namespace dab

@@ -1,0 +1,187 @@
+/* dabstar_b200.h — C ABI of the B200-native DAB Mode-I baseband decode path.
+ *
+ * The reference (tomneda/DABstar) has no plugin/FFI layer; its boundary for this path is the public C++
+ * surface of the classes that DabProcessor drives. Each entry point below names the
+ * reference interface it replaces (file:line under /root/reference/src). The reference calls those
+ * interfaces once per OFDM symbol; a device boundary has to be batch granular, so every call here takes
+ * a batch (frames, symbols or code words) and the C++ facades in dabstar_b200/host/ restore the
+ * reference's class names and per-call signatures on top of it.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `mem` says whether data pointers are host (DABSTAR_MEM_HOST) or
+ *     CUDA device pointers on the context's device (DABSTAR_MEM_DEVICE). Small descriptor arrays
+ *     (offsets, sub-channel tables) are always host pointers.
+ *   - every function returns 0 or a negative DABSTAR_E_* code; nothing throws across the ABI.
+ *     dabstar_last_error() gives the text for the last failure on that context.
+ *   - a context is single threaded; different contexts are independent; no global mutable state
+ *     (unlike viterbi_spiral.cpp:40-41 / eti_generator.cpp:9-24 in the reference).
+ *   - calls are synchronous unless stated: results are complete when the function returns.
+ *   - there is no CPU fallback: without a CUDA device dabstar_create() fails.
+ */
+#ifndef DABSTAR_B200_H
+#define DABSTAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DABSTAR_ABI_VERSION 1
+
+enum { DABSTAR_MEM_HOST = 0, DABSTAR_MEM_DEVICE = 1 };
+enum { DABSTAR_FMT_CF32 = 0, DABSTAR_FMT_U8 = 1, DABSTAR_FMT_I16 = 2 };
+enum
+{
+  DABSTAR_OK = 0,
+  DABSTAR_E_INVALID = -1,   /* bad argument */
+  DABSTAR_E_CUDA = -2,      /* CUDA runtime error, see dabstar_last_error */
+  DABSTAR_E_NOMEM = -3,
+  DABSTAR_E_UNSUPPORTED = -4
+};
+
+/* Mode-I constants (common/glob_defs.h:40-55) */
+enum
+{
+  DABSTAR_L = 76, DABSTAR_K = 1536, DABSTAR_TU = 2048, DABSTAR_TG = 504, DABSTAR_TS = 2552, DABSTAR_TN = 2656,
+  DABSTAR_TF = 196608, DABSTAR_SYM_BITS = 3072, DABSTAR_CIF_BITS = 55296, DABSTAR_FIC_BITS = 768,
+  DABSTAR_FRAME_SOFT = 75 * 3072
+};
+
+typedef struct dabstar_ctx dabstar_ctx;
+
+/* ------------------------------------------------------------------------------------------------ context */
+/* stream: a cudaStream_t to run on (e.g. torch's current stream), or NULL to create a private one. */
+int  dabstar_create(dabstar_ctx ** out, int device, void * stream);
+void dabstar_destroy(dabstar_ctx * ctx);
+const char * dabstar_last_error(const dabstar_ctx * ctx);
+int  dabstar_abi_version(void);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t dabstar_kernel_launches(const dabstar_ctx * ctx);
+
+/* ------------------------------------------------------------------------------------------------ tables (init-only rows D0, S4, M3) */
+/* FreqInterleaver::map_k_to_fft_bin for k = 0..1535 (ofdm/freq_interleaver.h:50). */
+int dabstar_freq_interleaver(dabstar_ctx * ctx, int16_t out[1536]);
+/* PhaseTable::mRefTable, 2048 complex floats (ofdm/phasetable.h:51). */
+int dabstar_phase_table(dabstar_ctx * ctx, float out_re_im[4096]);
+/* EepProtection / UepProtection viterbiBlockAddresses (protection/eep_protection.cpp:43-151,
+ * uep_protection.cpp:155-196): destination index of every kept soft bit. Returns the count or <0. */
+int dabstar_protection_addresses(dabstar_ctx * ctx, int short_form, int bit_rate, int prot_level, int32_t * addr, int cap);
+
+/* ------------------------------------------------------------------------------------------------ stage taps */
+/* fftwf_execute on a 2048-point plan (main/dab_processor.cpp:63,201,276,338): n transforms,
+ * unnormalised, sign -1 forward / +1 backward, natural order, complex float interleaved. */
+int dabstar_fft2048(dabstar_ctx * ctx, const float * in, float * out, int n, int sign, int mem);
+
+/* ViterbiSpiral::deconvolve (support/viterbi_spiral/viterbi_spiral.h:20) for n code words.
+ * soft: concatenated int16 inputs, code word i starts at soft_off[i] and holds 4*(frame_bits[i]+6) values;
+ * bits: one decoded bit per byte, code word i at bits_off[i], frame_bits[i] bytes. */
+int dabstar_viterbi(dabstar_ctx * ctx, const int16_t * soft, const int64_t * soft_off, const int32_t * frame_bits,
+                    int n, uint8_t * bits, const int64_t * bits_off, int mem);
+
+/* Protection::deconvolve (protection/protection.h:44) for n logical frames of ONE sub-channel profile:
+ * depuncture + Viterbi, no time de-interleaving, no energy dispersal.
+ * soft: n fragments of size_cu*64 int16 each (stride = size_cu*64); bits: n x 24*bit_rate bytes. */
+int dabstar_protection_deconvolve(dabstar_ctx * ctx, int short_form, int bit_rate, int prot_level, int size_cu,
+                                  const int16_t * soft, int n, uint8_t * bits, int mem);
+
+/* FicDecoder::process_block x3 + get_fib_bits (decoder/fic_decoder.h:49-58) for n frames.
+ * soft: n x 9216 int16 (symbols 1..3 of each frame, frame stride `frame_stride` int16);
+ * fib_bits: n x 3072 bytes (4 FICs x 768, dispersal removed); crc_ok: n x 12 (one per FIB);
+ * ber: n x 4 x 2 int32 {compared bits, sign errors} per FIC (ViterbiSpiral::calculate_BER). */
+int dabstar_fic_decode(dabstar_ctx * ctx, const int16_t * soft, int64_t frame_stride, int n, uint8_t * fib_bits,
+                       uint8_t * crc_ok, int32_t * ber, int mem);
+
+typedef struct
+{
+  int32_t sub_ch_id;
+  int32_t start_cu;
+  int32_t size_cu;
+  int32_t short_form;  /* 1: UEP, prot_level 1..5; 0: EEP, prot_level 0..3 = 1-A..4-A, 4..7 = 1-B..4-B */
+  int32_t prot_level;
+  int32_t bit_rate;    /* kbit/s */
+  int32_t start_frame; /* frame in which the Backend is created (MscHandler::set_channel) */
+} dabstar_subch;
+
+/* Backend::process (backend/backend.h:60) for n_cifs consecutive CIFs and one sub-channel: 16-CIF time
+ * de-interleave, depuncture, Viterbi, energy dispersal. cifs: n_cifs x 55296 int16. The Backend is new
+ * (zero history) at CIF 0, so CIF r >= 16 emits logical frame r-16: bits holds (n_cifs-16) x 24*bit_rate
+ * bytes. Returns the number of logical frames written or <0. */
+int dabstar_backend_process(dabstar_ctx * ctx, const dabstar_subch * sc, const int16_t * cifs, int n_cifs,
+                            uint8_t * bits, int mem);
+
+/* OfdmDecoder (ofdm/ofdm_decoder.h:63-73) over whole frames for ONE recording.
+ * state: opaque per-recording decoder state (the reference's per-carrier IIR vectors, phase reference,
+ * mMeanValue), created zeroed as OfdmDecoder() does. */
+typedef struct dabstar_ofdm_state dabstar_ofdm_state;
+int  dabstar_ofdm_state_create(dabstar_ctx * ctx, dabstar_ofdm_state ** out);
+void dabstar_ofdm_state_destroy(dabstar_ctx * ctx, dabstar_ofdm_state * st);
+int  dabstar_ofdm_state_reset(dabstar_ctx * ctx, dabstar_ofdm_state * st);                 /* OfdmDecoder::reset */
+/* which: 0 integAbsPhase 1 stdDevSq 2 meanPower 3 meanSigmaSq (1536 each, nominal carrier order)
+ *        4 nullPower (1536, nominal carrier order k -> bin map_k_to_fft_bin(k)) 5 {meanValue, 0} */
+int  dabstar_ofdm_state_get(dabstar_ctx * ctx, dabstar_ofdm_state * st, int which, float * out);
+/* fft: n_frames x 77 x 2048 complex float, rows = symbol 0 (store_reference_symbol_0), symbols 1..75
+ * (decode_symbol), null symbol (store_null_symbol_without_tii when null_is_tii[f]==0);
+ * clock_err: n_frames floats (iClockErr); soft: n_frames x 75 x 3072 int16. */
+int  dabstar_ofdm_decode_frames(dabstar_ctx * ctx, dabstar_ofdm_state * st, const float * fft, int n_frames,
+                                const float * clock_err, const uint8_t * null_is_tii, int soft_bit_type,
+                                int16_t * soft, int mem);
+
+/* PhaseReference::correlate_with_phase_ref_and_find_max_peak (ofdm/phasereference.h:53) for n windows of
+ * 2048 complex samples; start_index[i] = peak index or -1. */
+int dabstar_prs_correlate(dabstar_ctx * ctx, const float * samples, int n, float threshold, int strongest_peak,
+                          int32_t * start_index, int mem);
+/* PhaseReference::estimate_carrier_offset_from_sync_symbol_0 (ofdm/phasereference.h:54) for n FFT'd
+ * symbols 0; offset_hz[i] = Hz or 100000 (IDX_NOT_FOUND). */
+int dabstar_estimate_carrier_offset(dabstar_ctx * ctx, const float * fft, int n, int32_t * offset_hz, int mem);
+
+/* ------------------------------------------------------------------------------------------------ whole path */
+typedef struct
+{
+  int32_t input_format;    /* DABSTAR_FMT_* (raw_reader.cpp:66-70, xml_reader.cpp:254-372) */
+  int32_t soft_bit_type;   /* ESoftBitType: 0 SOFTDEC1 (default), 1 SOFTDEC2, 2 SOFTDEC3 */
+  float   sync_threshold;  /* 3.0 (dabradio.cpp:92) */
+  int32_t strongest_peak;  /* PhaseReference::set_sync_on_strongest_peak */
+  int32_t scan_mode;       /* DabProcessor::set_scan_mode: FIC only */
+  int32_t keep_soft_bits;  /* keep 75x3072 int16 per frame for dabstar_decoder_soft_bits */
+  int32_t max_window;      /* frames speculated per recording per round (0 = default 256) */
+  int32_t reserved;
+} dabstar_decoder_cfg;
+
+typedef struct
+{
+  int64_t sym0_pos;        /* stream index of the first useful sample of symbol 0 */
+  int32_t start_index;     /* PRS correlation peak */
+  float   fbb_sym0, fbb_data, fbb_null, fsync, phase_cp, clock_err;
+  int32_t fic_ratio_before, fic_ratio_after;
+  uint8_t fic_valid[4];
+} dabstar_frame_info;
+
+typedef struct dabstar_decoder dabstar_decoder;
+
+/* One decoder = one DabProcessor per recording (main/dab_processor.h:71), n_recordings of them in lock step. */
+int  dabstar_decoder_create(dabstar_ctx * ctx, const dabstar_decoder_cfg * cfg, int n_recordings, dabstar_decoder ** out);
+void dabstar_decoder_destroy(dabstar_decoder * dec);
+/* DabProcessor::set_audio_channel / MscHandler::set_channel (backend/msc_handler.h:43) */
+int  dabstar_decoder_set_subchannels(dabstar_decoder * dec, int recording, const dabstar_subch * sc, int n);
+/* DabProcessor::run() over complete recordings. iq[r]: n_samples[r] IQ pairs in cfg.input_format. */
+int  dabstar_decoder_run(dabstar_decoder * dec, const void * const * iq, const int64_t * n_samples, int mem);
+
+int     dabstar_decoder_n_frames(const dabstar_decoder * dec, int recording);
+int     dabstar_decoder_frame_info(const dabstar_decoder * dec, int recording, dabstar_frame_info * out, int cap);
+/* FicDecoder::get_fib_bits per frame: n_frames x 3072 bytes, valid: n_frames x 4 */
+int     dabstar_decoder_fib_bits(const dabstar_decoder * dec, int recording, uint8_t * bits, uint8_t * valid);
+int     dabstar_decoder_soft_bits(const dabstar_decoder * dec, int recording, int frame, int16_t * out);
+int64_t dabstar_decoder_msc_size(const dabstar_decoder * dec, int recording, int sub_ch_id);
+/* FrameProcessor::add_to_frame payloads (backend/frame_processor.h:43), concatenated, one bit per byte */
+int64_t dabstar_decoder_msc_copy(const dabstar_decoder * dec, int recording, int sub_ch_id, uint8_t * out, int64_t cap);
+/* out[0] good FIBs, [1] time-sync established count, [2] time-sync failures, [3] samples consumed,
+ * [4] speculation windows run, [5] windows cut short by verification, [6] frames decoded, [7] reserved */
+int     dabstar_decoder_counters(const dabstar_decoder * dec, int recording, int64_t out[8]);
+/* Device time of the last dabstar_decoder_run in milliseconds (CUDA events on the context's stream). */
+double  dabstar_decoder_last_ms(const dabstar_decoder * dec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

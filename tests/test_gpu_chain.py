@@ -1,0 +1,109 @@
+"""-m gpu: whole-path parity (IQ -> FIB / MSC bits) of the CUDA decoder against the CPU oracle chain."""
+import numpy as np
+import pytest
+
+from dabstar_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+SC_3A = synth.SubChannel(3, 100, 54, 0, 2, 72)
+
+
+def _run_both(oracle, ctx, rec, subch, fmt, **kw):
+    iq_f = rec.iq if fmt == synth.FMT_CF32 else None
+    if fmt == synth.FMT_U8:
+        iq_f = np.zeros(rec.iq.shape[0], np.complex64)
+        oracle.f("convert_u8")(rec.iq.ctypes.data_as(api.c_p), iq_f.ctypes.data_as(api.c_p), api.ctypes.c_int64(rec.iq.shape[0]))
+    elif fmt == synth.FMT_I16:
+        iq_f = np.zeros(rec.iq.shape[0], np.complex64)
+        oracle.f("convert_i16")(rec.iq.ctypes.data_as(api.c_p), iq_f.ctypes.data_as(api.c_p), api.ctypes.c_int64(rec.iq.shape[0]))
+    want = oracle.chain_run(iq_f, synth.subch_table(subch), len(subch), tap_soft=True, scan_mode=kw.get("scan_mode", 0))
+    dp = api.DabProcessor(1, input_format=fmt, ctx=ctx, **kw)
+    dp.set_audio_channel(0, subch)
+    dp.run([rec.iq])
+    return want, dp, dp.result(0)
+
+
+def _compare(want, dp, got, subch, soft_frames=3):
+    assert got.n_frames == want.n_frames
+    for a, b in zip(got.info, want.info):
+        assert (a.sym0_pos, a.start_index) == (b.sym0_pos, b.start_index)
+        assert round(a.fbb_data) == round(b.fbb_data) and round(a.fbb_null) == round(b.fbb_null)
+        assert abs(a.fsync - b.fsync) < 0.05 and abs(a.clock_err - b.clock_err) < 1e-3
+        assert (a.fic_ratio_before, a.fic_ratio_after) == (b.fic_ratio_before, b.fic_ratio_after)
+    assert np.array_equal(got.fic_valid, want.fic_valid)
+    ok = want.fic_valid.astype(bool).repeat(768, axis=1)
+    assert np.array_equal(got.fib_bits[ok], want.fib_bits[ok])  # CRC-good FIC blocks are what the reference hands on
+    assert got.n_good_fibs == want.n_good_fibs
+    for s in subch:
+        assert np.array_equal(got.msc[s.sub_ch_id], want.msc[s.sub_ch_id]), s
+    for f in range(min(soft_frames, got.n_frames)):
+        d = np.abs(dp.soft_bits(0, f).astype(np.int32) - want.soft_bits(f).astype(np.int32))
+        assert (d > 1).mean() <= 1e-4, (f, d.max(), (d > 1).mean())
+
+
+@pytest.mark.parametrize("fmt", [synth.FMT_U8, synth.FMT_I16, synth.FMT_CF32])
+def test_config1_one_dabplus_subchannel(ctx, oracle, fmt):
+    rec = synth.generate(22, seed=1, snr_db=20.0, subch=[SC_3A], fmt=fmt)
+    want, dp, got = _run_both(oracle, ctx, rec, [SC_3A], fmt)
+    assert want.n_frames == 22 and want.fic_valid.all()
+    _compare(want, dp, got, [SC_3A])
+    # payload is what was transmitted
+    assert np.array_equal(got.fib_bits, rec.fib_truth[:got.n_frames])
+    assert np.array_equal(got.msc[3], rec.msc_truth[0][:got.msc[3].shape[0]])
+
+
+@pytest.mark.parametrize("cfo", [700.0, -4300.0, 31000.0])
+def test_carrier_offset_acquisition(ctx, oracle, cfo):
+    rec = synth.generate(12, seed=5, snr_db=15.0, cfo_hz=cfo, subch=[SC_3A], fmt=synth.FMT_U8, lead_samples=77777)
+    want, dp, got = _run_both(oracle, ctx, rec, [SC_3A], synth.FMT_U8)
+    assert want.n_frames >= 11
+    _compare(want, dp, got, [SC_3A], soft_frames=2)
+
+
+def test_mixed_eep_uep_ensemble(ctx, oracle):
+    subch = [synth.SubChannel(1, 0, 108, 0, 0, 72), synth.SubChannel(2, 108, 42, 0, 5, 64), synth.SubChannel(4, 150, 96, 1, 3, 128),
+             synth.SubChannel(9, 246, 64, 1, 5, 128, start_frame=2), synth.SubChannel(11, 310, 36, 0, 3, 72), synth.SubChannel(12, 346, 140, 1, 1, 128)]
+    rec = synth.generate(9, seed=7, snr_db=14.0, subch=subch, fmt=synth.FMT_U8)
+    want, dp, got = _run_both(oracle, ctx, rec, subch, synth.FMT_U8)
+    _compare(want, dp, got, subch, soft_frames=1)
+    assert got.msc[9].shape[0] == got.msc[1].shape[0] - 8  # Backend created two frames later emits 8 logical frames fewer
+
+
+def test_low_snr_same_crc_counts(ctx, oracle):
+    rec = synth.generate(10, seed=11, snr_db=6.0, subch=[SC_3A], fmt=synth.FMT_U8)
+    want, dp, got = _run_both(oracle, ctx, rec, [SC_3A], synth.FMT_U8)
+    assert got.n_frames == want.n_frames
+    assert [i.sym0_pos for i in got.info] == [i.sym0_pos for i in want.info]
+    # below the 10 dB parity bar: report, require the CRC pass counts to be close
+    assert abs(got.n_good_fibs - want.n_good_fibs) <= max(2, want.n_good_fibs // 50)
+
+
+def test_scan_mode_and_small_windows(ctx, oracle):
+    rec = synth.generate(14, seed=13, snr_db=18.0, fmt=synth.FMT_U8)
+    want, dp, got = _run_both(oracle, ctx, rec, [], synth.FMT_U8, scan_mode=True, max_window=3)
+    _compare(want, dp, got, [])
+    assert got.counters[4] >= 5  # several speculation windows were needed
+
+
+def test_batch_of_recordings_matches_single(ctx, oracle):
+    recs = [synth.generate(6 + i, seed=20 + i, snr_db=12.0 + 3 * i, cfo_hz=(-1) ** i * 900.0 * i, subch=[SC_3A], fmt=synth.FMT_U8, lead_samples=50000 + 7919 * i)
+            for i in range(5)]
+    dp = api.DabProcessor(len(recs), input_format=synth.FMT_U8, ctx=ctx)
+    for i in range(len(recs)):
+        dp.set_audio_channel(i, [SC_3A])
+    dp.run([r.iq for r in recs])
+    for i, rec in enumerate(recs):
+        iq_f = np.zeros(rec.iq.shape[0], np.complex64)
+        oracle.f("convert_u8")(rec.iq.ctypes.data_as(api.c_p), iq_f.ctypes.data_as(api.c_p), api.ctypes.c_int64(rec.iq.shape[0]))
+        want = oracle.chain_run(iq_f, synth.subch_table([SC_3A]), 1)
+        got = dp.result(i)
+        assert got.n_frames == want.n_frames, i
+        assert np.array_equal(got.fic_valid, want.fic_valid)
+        assert np.array_equal(got.msc[3], want.msc[3]), i
+
+
+def test_empty_and_short_inputs(ctx):
+    dp = api.DabProcessor(2, input_format=synth.FMT_U8, ctx=ctx)
+    dp.run([np.zeros((0, 2), np.uint8), np.full((50000, 2), 127, np.uint8)])
+    assert dp.result(0).n_frames == 0 and dp.result(1).n_frames == 0

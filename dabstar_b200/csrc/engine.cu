@@ -1075,7 +1075,7 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
       int valid = 0;
       int next_start = -2;
       bool lost = false;
-      std::vector<int> ratio_after((size_t)pl.n_frames);
+      std::vector<int> ratio_after((size_t)pl.n_frames), ratio_before((size_t)pl.n_frames);
       for (int j = 0; j < pl.n_frames; j++)
       {
         const int i = base + j;
@@ -1087,6 +1087,7 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
           break;
         }
         if (j > 0 && ratio * 10 < 30) break; // this frame needed the coarse AFC: replay it as the first frame of a careful window
+        ratio_before[j] = ratio;
         const int n_fic = std::min(4, ctl[i].desc.n_syms * SYM_BITS / FIC_IN);
         for (int b = 0; b < n_fic; b++)
           for (int q = 0; q < 3; q++)
@@ -1104,6 +1105,7 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
         {
           const int i = base + j;
           const bool complete = ctl[i].desc.n_syms == 75;
+          ctl[i].info.fic_ratio_before = ratio_before[j] * 10;
           ctl[i].info.fic_ratio_after = ratio_after[j] * 10;
           const int n_fic = std::min(4, ctl[i].desc.n_syms * SYM_BITS / FIC_IN);
           for (int b = 0; b < 4; b++)

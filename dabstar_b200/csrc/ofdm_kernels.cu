@@ -455,9 +455,13 @@ __device__ __forceinline__ float first_quadrant(float ph)
   return ph;
 }
 
+// (i16)(float) as the reference's x86-64 build evaluates it (ofdm_decoder.cpp:254-255): cvttss2si to 32 bits
+// (0x80000000 when out of range or NaN), then the low 16 bits. Out-of-range values only occur in the start-up
+// transient of the SOFTDEC2 weighting; the Viterbi clamps to +-127 afterwards anyway.
 __device__ __forceinline__ short to_i16(float v)
 {
-  return (short)max(-32768, min(32767, __float2int_rz(v)));
+  const int r = (fabsf(v) < 2147483648.0f) ? __float2int_rz(v) : (int)0x80000000;
+  return (short)(r & 0xffff);
 }
 
 struct CarrierState

@@ -8,10 +8,12 @@ namespace dab
 namespace
 {
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int VIT_SMEM_PER_STEP = 14; // bytes of shared memory per trellis step and warp
 
 __device__ __forceinline__ unsigned clamp_sym(int v)
 {
-  v += 127; // viterbi_scalar.h:34-40
+  // viterbi_scalar.h:34-40: `i16 tmp = in; tmp += 127;` wraps in 16 bits before the clamp (inputs above 32640 become 0)
+  v = (int)(short)(v + 127);
   return (unsigned)min(max(v, 0), 255);
 }
 
@@ -20,7 +22,7 @@ __device__ __forceinline__ unsigned parity8(unsigned x)
   return __popc(x) & 1u;
 }
 
-// shared memory per warp: survivors u64[cap] | symbols u32[cap] | decoded bits u8[cap]
+// shared memory per warp: survivors u64[cap] | symbols u32[cap] | decoded bits u8[cap] | input signs, 1 bit per position (cap/2 bytes)
 __global__ void __launch_bounds__(256) k_viterbi(const VitJob * __restrict__ jobs, int n_jobs, const VitProfile * __restrict__ profiles,
                                                  const int16_t * __restrict__ soft, uint8_t * __restrict__ out_bits,
                                                  const uint8_t * __restrict__ prbs, uint8_t * __restrict__ crc_ok,
@@ -28,11 +30,12 @@ __global__ void __launch_bounds__(256) k_viterbi(const VitJob * __restrict__ job
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  unsigned char * base = smem_raw + (size_t)warp * (size_t)cap * 13;
+  unsigned char * base = smem_raw + (size_t)warp * (size_t)cap * VIT_SMEM_PER_STEP;
   unsigned long long * surv = reinterpret_cast<unsigned long long *>(base);
   unsigned * syms = reinterpret_cast<unsigned *>(base + (size_t)cap * 8);
   unsigned char * syms8 = reinterpret_cast<unsigned char *>(syms);
   unsigned char * dbits = base + (size_t)cap * 12;
+  unsigned * sgn = reinterpret_cast<unsigned *>(base + (size_t)cap * 13);
 
   const unsigned xmask = vit_branch_mask(lane);
   const unsigned sel = (lane & 1) ? 0x3244u : 0x1044u; // PRMT: chosen 16-bit half -> upper half, zeros below
@@ -45,20 +48,26 @@ __global__ void __launch_bounds__(256) k_viterbi(const VitJob * __restrict__ job
     const int n_bits = pr.n_bits, steps = n_bits + 6;
 
     // ---- gather: depuncture (+ time de-interleave) and clamp to u8
-    for (int p = lane; p < 4 * steps; p += 32)
+    for (int p0 = 0; p0 < 4 * steps; p0 += 32)
     {
-      const int idx = vit_src_index(pr, p);
+      const int p = p0 + lane;
       int v = 0;
-      if (idx >= 0)
+      if (p < 4 * steps)
       {
-        if (job.src_mode == VIT_SRC_LINEAR) v = soft[job.src + idx];
-        else
+        const int idx = vit_src_index(pr, p);
+        if (idx >= 0)
         {
-          const int m = time_map(idx);
-          if ((job.row_mask >> m) & 1) v = soft[job.src + cif_offset(job.cif_first + m) + job.frag_off + idx];
+          if (job.src_mode == VIT_SRC_LINEAR) v = soft[job.src + idx];
+          else
+          {
+            const int m = time_map(idx);
+            if ((job.row_mask >> m) & 1) v = soft[job.src + cif_offset(job.cif_first + m) + job.frag_off + idx];
+          }
         }
+        syms8[p] = (unsigned char)clamp_sym(v);
       }
-      syms8[p] = (unsigned char)clamp_sym(v);
+      const unsigned pos = __ballot_sync(FULL, v > 0); // sign of the raw input, for calculate_BER
+      if (lane == 0) sgn[p0 >> 5] = pos;
     }
     __syncwarp();
 
@@ -116,13 +125,12 @@ __global__ void __launch_bounds__(256) k_viterbi(const VitJob * __restrict__ job
           const int ii = i - q;
           if (ii >= 0 && ii < n_bits) sr |= (unsigned)dbits[ii] << q;
         }
-        const unsigned sw = syms[i];
         const int poly[4] = { 109, 79, 83, 109 };
 #pragma unroll
         for (int g = 0; g < 4; g++)
         {
           if (vit_src_index(pr, 4 * i + g) < 0) continue;
-          const unsigned hard = ((sw >> (8 * g)) & 0xffu) > 127u;
+          const unsigned hard = (sgn[(4 * i + g) >> 5] >> ((4 * i + g) & 31)) & 1u;
           errors += hard != parity8(sr & (unsigned)poly[g]);
         }
       }
@@ -152,7 +160,7 @@ __global__ void __launch_bounds__(256) k_viterbi(const VitJob * __restrict__ job
 int viterbi_smem_bytes(int max_steps, int warps)
 {
   const int cap = (max_steps + 15) & ~15;
-  return cap * 13 * warps;
+  return cap * VIT_SMEM_PER_STEP * warps;
 }
 
 // Picks warps per CTA so the shared-memory footprint allows several CTAs per SM, launches the jobs.
@@ -162,7 +170,7 @@ cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, int n_jobs,
 {
   if (n_jobs <= 0) return cudaSuccess;
   const int cap = (max_steps + 15) & ~15;
-  const int per_warp = cap * 13;
+  const int per_warp = cap * VIT_SMEM_PER_STEP;
   int warps = 8;
   while (warps > 1 && per_warp * warps > 56 * 1024) warps >>= 1; // <= 56 KB per CTA -> 4 CTAs/SM when possible
   const int smem = per_warp * warps;

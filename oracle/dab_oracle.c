@@ -319,7 +319,7 @@ void dabo_viterbi(const int16_t * in, int frame_bits, uint8_t * out)
     int sym[4];
     for (int j = 0; j < 4; j++)
     {
-      int v = in[4 * t + j] + 127;
+      int v = (int16_t)(in[4 * t + j] + 127); /* `i16 tmp; tmp += 127;` wraps in 16 bits (viterbi_scalar.h:34-40) */
       sym[j] = v < 0 ? 0 : (v > 255 ? 255 : v);
     }
     uint64_t d = 0;

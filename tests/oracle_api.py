@@ -76,6 +76,26 @@ class Oracle:
         self.f("fft2048")(_ptr(x), _ptr(y), ctypes.c_int(sign))
         return y
 
+    def prbs(self, n: int) -> np.ndarray:
+        out = np.zeros(n, np.uint8)
+        self.f("prbs")(_ptr(out), ctypes.c_int(n))
+        return out
+
+    def fic_addresses(self) -> np.ndarray:
+        a = np.zeros(2304, np.int32)
+        n = self.f("fic_addresses")(_ptr(a), ctypes.c_int(2304))
+        assert n == 2304
+        return a
+
+    def to_cf32(self, iq: np.ndarray) -> np.ndarray:
+        """File sample formats -> complex float exactly as the reference's readers do (raw_reader.cpp:66-70)."""
+        if iq.dtype == np.complex64:
+            return iq
+        out = np.zeros(iq.shape[0], np.complex64)
+        name = "convert_u8" if iq.dtype == np.uint8 else "convert_i16"
+        self.f(name)(_ptr(np.ascontiguousarray(iq)), _ptr(out), ctypes.c_int64(iq.shape[0]))
+        return out
+
     # ---- channel decoding
     def viterbi(self, soft: np.ndarray, frame_bits: int) -> np.ndarray:
         soft = np.ascontiguousarray(soft, np.int16)

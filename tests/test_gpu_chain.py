@@ -10,13 +10,7 @@ SC_3A = synth.SubChannel(3, 100, 54, 0, 2, 72)
 
 
 def _run_both(oracle, ctx, rec, subch, fmt, **kw):
-    iq_f = rec.iq if fmt == synth.FMT_CF32 else None
-    if fmt == synth.FMT_U8:
-        iq_f = np.zeros(rec.iq.shape[0], np.complex64)
-        oracle.f("convert_u8")(rec.iq.ctypes.data_as(api.c_p), iq_f.ctypes.data_as(api.c_p), api.ctypes.c_int64(rec.iq.shape[0]))
-    elif fmt == synth.FMT_I16:
-        iq_f = np.zeros(rec.iq.shape[0], np.complex64)
-        oracle.f("convert_i16")(rec.iq.ctypes.data_as(api.c_p), iq_f.ctypes.data_as(api.c_p), api.ctypes.c_int64(rec.iq.shape[0]))
+    iq_f = oracle.to_cf32(rec.iq)
     want = oracle.chain_run(iq_f, synth.subch_table(subch), len(subch), tap_soft=True, scan_mode=kw.get("scan_mode", 0))
     dp = api.DabProcessor(1, input_format=fmt, ctx=ctx, **kw)
     dp.set_audio_channel(0, subch)
@@ -94,9 +88,7 @@ def test_batch_of_recordings_matches_single(ctx, oracle):
         dp.set_audio_channel(i, [SC_3A])
     dp.run([r.iq for r in recs])
     for i, rec in enumerate(recs):
-        iq_f = np.zeros(rec.iq.shape[0], np.complex64)
-        oracle.f("convert_u8")(rec.iq.ctypes.data_as(api.c_p), iq_f.ctypes.data_as(api.c_p), api.ctypes.c_int64(rec.iq.shape[0]))
-        want = oracle.chain_run(iq_f, synth.subch_table([SC_3A]), 1)
+        want = oracle.chain_run(oracle.to_cf32(rec.iq), synth.subch_table([SC_3A]), 1)
         got = dp.result(i)
         assert got.n_frames == want.n_frames, i
         assert np.array_equal(got.fic_valid, want.fic_valid)

@@ -73,10 +73,8 @@ def test_protection_deconvolve(ctx, oracle, sf, lvl, br, size_cu):
 def test_fic_decode(ctx, oracle):
     rng = np.random.default_rng(9)
     n = 12
-    fic_addr = np.zeros(2304, np.int32)
-    oracle.f("fic_addresses")(fic_addr.ctypes.data_as(api.c_p), 2304)
-    prbs = np.zeros(768, np.uint8)
-    oracle.f("prbs")(prbs.ctypes.data_as(api.c_p), 768)
+    fic_addr = oracle.fic_addresses()
+    prbs = oracle.prbs(768)
     soft = np.zeros((n, 3, 3072), np.int16)
     for f in range(n):
         flat = soft[f].reshape(-1)

@@ -330,6 +330,15 @@ class DabProcessor:
         lib.dabstar_decoder_counters(self.h, recording, _ptr(cnt))
         return RecordingResult(nf, list(info)[:nf], bits, valid, msc, cnt)
 
+    STAGES = ("time_sync", "prs_corr", "cp_corr", "coarse_afc", "ingest_fft", "demap", "fic_viterbi", "msc_viterbi")
+
+    def stage_ms(self) -> dict:
+        """Device milliseconds and launch counts per kernel family of the last run()."""
+        ms = (ctypes.c_double * 8)()
+        ln = (ctypes.c_int64 * 8)()
+        self.ctx.check(self.ctx.lib.dabstar_decoder_stage_ms(self.h, ms, ln), "dabstar_decoder_stage_ms")
+        return {n: (ms[i], int(ln[i])) for i, n in enumerate(self.STAGES)}
+
     def soft_bits(self, recording: int, frame: int) -> np.ndarray:
         out = np.zeros((75, 3072), np.int16)
         self.ctx.check(self.ctx.lib.dabstar_decoder_soft_bits(self.h, recording, frame, _ptr(out)), "dabstar_decoder_soft_bits")

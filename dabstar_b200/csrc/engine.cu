@@ -584,7 +584,22 @@ struct dabstar_decoder
   long long total_slots = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0;
+  // per-stage device time of the last run: CUDA events around every kernel launch on the context's stream
+  struct Span { int stage; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  double stage_ms[8] = { 0 };
+  long long stage_launches[8] = { 0 };
+  cudaEvent_t ev_get()
+  {
+    if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
+    return ev_pool[ev_used++];
+  }
+  void span_begin(int stage) { Span sp{ stage, ev_get(), ev_get() }; cudaEventRecord(sp.a, ctx->stream); spans.push_back(sp); }
+  void span_end() { cudaEventRecord(spans.back().b, ctx->stream); stage_launches[spans.back().stage]++; }
 };
+enum { ST_DIP = 0, ST_PRS = 1, ST_CP = 2, ST_COARSE = 3, ST_FFT = 4, ST_DEMAP = 5, ST_FIC = 6, ST_MSC = 7 };
 
 static inline int mod_fs_host(long long x)
 {
@@ -616,6 +631,7 @@ extern "C" void dabstar_decoder_destroy(dabstar_decoder * dec)
   cudaSetDevice(dec->ctx->device);
   if (dec->ev0) cudaEventDestroy(dec->ev0);
   if (dec->ev1) cudaEventDestroy(dec->ev1);
+  for (cudaEvent_t e : dec->ev_pool) cudaEventDestroy(e);
   delete dec;
 }
 
@@ -736,6 +752,9 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
   const int fmt = dec->cfg.input_format;
   const size_t bps = fmt == FMT_U8 ? 2 : (fmt == FMT_I16 ? 4 : 8);
   cudaStream_t st = ctx->stream;
+  dec->spans.clear();
+  dec->ev_used = 0;
+  for (int i = 0; i < 8; i++) { dec->stage_ms[i] = 0; dec->stage_launches[i] = 0; }
   CK(cudaEventRecord(dec->ev0, st));
 
   // ---- inputs
@@ -817,7 +836,9 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
         CK(dec->d_dipw.reserve(sizeof(DipWork) * dw.size()));
         CK(dec->d_dipr.reserve(sizeof(DipResult) * dw.size()));
         CK(cudaMemcpyAsync(dec->d_dipw.p, dw.data(), sizeof(DipWork) * dw.size(), cudaMemcpyHostToDevice, st));
+        dec->span_begin(ST_DIP);
         CK(launch_dip_search(st, dec->d_dipw.as<DipWork>(), (int)dw.size(), d_rin, fmt, dec->d_dipr.as<DipResult>(), &ctx->launches));
+        dec->span_end();
         std::vector<DipResult> dr(dw.size());
         CK(cudaMemcpyAsync(dr.data(), dec->d_dipr.p, sizeof(DipResult) * dw.size(), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -875,8 +896,10 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
         uint8_t * dfirst = dec->d_desc.as<uint8_t>() + sizeof(FrameDesc) * fd.size();
         CK(cudaMemcpyAsync(dec->d_desc.p, fd.data(), sizeof(FrameDesc) * fd.size(), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(dfirst, first.data(), first.size(), cudaMemcpyHostToDevice, st));
+        dec->span_begin(ST_PRS);
         CK(launch_prs_corr(st, ctx->tab, dec->d_desc.as<FrameDesc>(), (int)fd.size(), d_rin, fmt, thr0, 2.0f * thr0, dfirst,
                            dec->cfg.strongest_peak, dec->d_start.as<int>(), &ctx->launches));
+        dec->span_end();
         std::vector<int> si(fd.size());
         CK(cudaMemcpyAsync(si.data(), dec->d_start.p, sizeof(int) * fd.size(), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -960,7 +983,9 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
 
     // ---- CP correlation on raw samples (all frames) and coarse AFC (careful frames), then the scalar recurrences
     CK(dec->d_cp.reserve(sizeof(float2) * (size_t)n_desc));
+    dec->span_begin(ST_CP);
     CK(launch_cp_corr(st, d_fd, n_desc, d_rin, fmt, dec->d_cp.as<float2>(), &ctx->launches));
+    dec->span_end();
     std::vector<float2> cp((size_t)n_desc);
     CK(cudaMemcpyAsync(cp.data(), dec->d_cp.p, sizeof(float2) * (size_t)n_desc, cudaMemcpyDeviceToHost, st));
     std::vector<int> coarse((size_t)n_desc, 0);
@@ -983,7 +1008,9 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
         CK(dec->d_work.reserve(sizeof(FrameDesc) * cf.size()));
         CK(dec->d_coarse.reserve(sizeof(int) * cf.size()));
         CK(cudaMemcpyAsync(dec->d_work.p, cf.data(), sizeof(FrameDesc) * cf.size(), cudaMemcpyHostToDevice, st));
+        dec->span_begin(ST_COARSE);
         CK(launch_coarse_afc(st, ctx->tab, dec->d_work.as<FrameDesc>(), (int)cf.size(), d_rin, fmt, dec->d_coarse.as<int>(), &ctx->launches));
+        dec->span_end();
         std::vector<int> res(cf.size());
         CK(cudaMemcpyAsync(res.data(), dec->d_coarse.p, sizeof(int) * cf.size(), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -1020,12 +1047,16 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
     uint8_t * d_first = dec->d_desc.as<uint8_t>() + sizeof(FrameDesc) * (size_t)n_desc;
     CK(cudaMemcpyAsync(d_first, first_flags.data(), (size_t)n_desc, cudaMemcpyHostToDevice, st));
     CK(dec->d_start.reserve(sizeof(int) * (size_t)n_desc));
+    dec->span_begin(ST_PRS);
     CK(launch_prs_corr(st, ctx->tab, d_fd, n_desc, d_rin, fmt, thr0, 2.0f * thr0, d_first, dec->cfg.strongest_peak, dec->d_start.as<int>(), &ctx->launches));
+    dec->span_end();
 
     // ---- heavy pass: FFT (+ingest, derotation, de-interleave) -> demap -> FIC
     CK(dec->d_work.reserve(sizeof(DemapWork) * plans.size() + 64));
     CK(dec->d_X.reserve((size_t)x_frame_bytes * (size_t)n_desc));
+    dec->span_begin(ST_FFT);
     CK(launch_fft_frames(st, ctx->tab, d_fd, n_desc, d_rin, fmt, dec->d_X.as<float2>(), &ctx->launches));
+    dec->span_end();
     CK(cudaMemcpyAsync(dec->d_snap.p, dec->d_states.p, sizeof(OfdmStateDev) * (size_t)n_rec, cudaMemcpyDeviceToDevice, st));
     {
       std::vector<DemapWork> wk;
@@ -1036,8 +1067,10 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
       }
       DemapWork * d_wk = dec->d_work.as<DemapWork>();
       CK(cudaMemcpyAsync(d_wk, wk.data(), sizeof(DemapWork) * wk.size(), cudaMemcpyHostToDevice, st));
+      dec->span_begin(ST_DEMAP);
       CK(launch_demap(st, ctx->tab, d_wk, (int)wk.size(), d_fd, nullptr, dec->d_X.as<float2>(), dec->d_states.as<OfdmStateDev>(), dec->cfg.soft_bit_type,
                       dec->d_soft.as<int16_t>(), &ctx->launches));
+      dec->span_end();
     }
     {
       std::vector<VitJob> jobs;
@@ -1047,7 +1080,9 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
         const int n_fic = std::min(4, ctl[i].desc.n_syms * SYM_BITS / FIC_IN);
         make_fic_jobs(jobs, (long long)ctl[i].desc.slot * FRAME_SOFT, (long long)ctl[i].desc.slot * 3072, 4 * ctl[i].desc.slot, n_fic);
       }
+      dec->span_begin(ST_FIC);
       if (int e = run_viterbi_jobs(ctx, jobs, FIC_OUT + 6, dec->d_soft.as<int16_t>(), dec->d_fib.as<uint8_t>(), dec->d_crc.as<uint8_t>(), dec->d_ber.as<int>(), dec->d_jobs)) return e;
+      dec->span_end();
     }
 
     // ---- read back the verification data
@@ -1187,9 +1222,12 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
     {
       CK(dec->d_mscbits.reserve((size_t)out_total));
       for (auto & kv : by_steps)
-        if (int e = run_viterbi_jobs(ctx, kv.second, kv.first, dec->d_soft.as<int16_t>(), dec->d_mscbits.as<uint8_t>(), nullptr, nullptr, dec->d_jobs))
-          return e;
-        else CK(cudaStreamSynchronize(st)); // d_jobs is reused by the next group
+      {
+        dec->span_begin(ST_MSC);
+        if (int e = run_viterbi_jobs(ctx, kv.second, kv.first, dec->d_soft.as<int16_t>(), dec->d_mscbits.as<uint8_t>(), nullptr, nullptr, dec->d_jobs)) return e;
+        dec->span_end();
+        CK(cudaStreamSynchronize(st)); // d_jobs is reused by the next group
+      }
       for (auto & o : outs)
         CK(cudaMemcpyAsync(dec->recs[o.rec].msc[o.ch].bits.data(), dec->d_mscbits.as<uint8_t>() + o.off, (size_t)o.len, cudaMemcpyDeviceToHost, st));
     }
@@ -1207,6 +1245,11 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, dec->ev0, dec->ev1));
   dec->last_ms = ms;
+  for (auto & sp : dec->spans)
+  {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) dec->stage_ms[sp.stage] += t;
+  }
   return 0;
 }
 
@@ -1270,3 +1313,9 @@ extern "C" int dabstar_decoder_counters(const dabstar_decoder * dec, int recordi
   return 0;
 }
 extern "C" double dabstar_decoder_last_ms(const dabstar_decoder * dec) { return dec ? dec->last_ms : 0.0; }
+extern "C" int dabstar_decoder_stage_ms(const dabstar_decoder * dec, double ms[8], int64_t launches[8])
+{
+  if (!dec || !ms || !launches) return DABSTAR_E_INVALID;
+  for (int i = 0; i < 8; i++) { ms[i] = dec->stage_ms[i]; launches[i] = dec->stage_launches[i]; }
+  return 0;
+}

@@ -180,6 +180,9 @@ int64_t dabstar_decoder_msc_copy(const dabstar_decoder * dec, int recording, int
 int     dabstar_decoder_counters(const dabstar_decoder * dec, int recording, int64_t out[8]);
 /* Device time of the last dabstar_decoder_run in milliseconds (CUDA events on the context's stream). */
 double  dabstar_decoder_last_ms(const dabstar_decoder * dec);
+/* Device time and launch count per kernel family of the last run (CUDA events around every launch):
+ * [0] time sync [1] PRS correlation [2] CP correlation [3] coarse AFC [4] ingest+FFT [5] demap [6] FIC Viterbi [7] MSC Viterbi */
+int     dabstar_decoder_stage_ms(const dabstar_decoder * dec, double ms[8], int64_t launches[8]);
 
 #ifdef __cplusplus
 }

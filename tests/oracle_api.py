@@ -88,13 +88,15 @@ class Oracle:
         return a
 
     def to_cf32(self, iq: np.ndarray) -> np.ndarray:
-        """File sample formats -> complex float exactly as the reference's readers do (raw_reader.cpp:66-70)."""
+        """File sample formats -> complex float exactly as the reference's readers do: u8 (v - 127.38f) / 128
+        (raw_reader.cpp:66-70), i16 v / 32768 (xml_reader.cpp:254-372). IEEE float32 arithmetic, same as dabo_convert_*."""
         if iq.dtype == np.complex64:
-            return iq
-        out = np.zeros(iq.shape[0], np.complex64)
-        name = "convert_u8" if iq.dtype == np.uint8 else "convert_i16"
-        self.f(name)(_ptr(np.ascontiguousarray(iq)), _ptr(out), ctypes.c_int64(iq.shape[0]))
-        return out
+            return np.ascontiguousarray(iq)
+        if iq.dtype == np.uint8:
+            f = (iq.astype(np.float32) - np.float32(127.38)) / np.float32(128.0)
+        else:
+            f = iq.astype(np.float32) / np.float32(32768.0)
+        return np.ascontiguousarray(f).view(np.complex64).reshape(-1)
 
     # ---- channel decoding
     def viterbi(self, soft: np.ndarray, frame_bits: int) -> np.ndarray:

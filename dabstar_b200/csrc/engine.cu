@@ -44,6 +44,23 @@ struct DevBuf
 };
 } // namespace
 
+// pinned host memory for result read-back (pageable memory makes cudaMemcpyAsync synchronous and ~3x slower)
+struct HostBuf
+{
+  void * p = nullptr;
+  size_t cap = 0;
+  ~HostBuf() { if (p) cudaFreeHost(p); }
+  cudaError_t reserve(size_t bytes)
+  {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+    cudaError_t e = cudaHostAlloc(&p, bytes + bytes / 8 + 256, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = bytes + bytes / 8 + 256;
+    return e;
+  }
+  template <typename T> T * as() const { return static_cast<T *>(p); }
+};
+
 struct dabstar_ctx
 {
   int device = 0;
@@ -579,7 +596,7 @@ struct dabstar_decoder
   DevBuf d_states;      // OfdmStateDev[n_rec]
   DevBuf d_snap;        // snapshot of d_states
   DevBuf d_desc, d_work, d_cp, d_start, d_coarse, d_dipw, d_dipr, d_jobs, d_mscbits;
-  std::vector<uint8_t> h_fib;
+  HostBuf h_fib;
   std::vector<int16_t> h_soft_one;
   long long total_slots = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1233,12 +1250,12 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
     }
   }
   // FIB bits of all accepted frames
-  dec->h_fib.assign((size_t)dec->total_slots * 3072, 0);
+  CK(dec->h_fib.reserve((size_t)dec->total_slots * 3072));
   for (int r = 0; r < n_rec; r++)
   {
     Recording & R = dec->recs[r];
     if (R.n_slots > 0)
-      CK(cudaMemcpyAsync(dec->h_fib.data() + (size_t)R.slot_base * 3072, dec->d_fib.as<uint8_t>() + (size_t)R.slot_base * 3072, (size_t)R.n_slots * 3072, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(dec->h_fib.as<uint8_t>() + (size_t)R.slot_base * 3072, dec->d_fib.as<uint8_t>() + (size_t)R.slot_base * 3072, (size_t)R.n_slots * 3072, cudaMemcpyDeviceToHost, st));
   }
   CK(cudaEventRecord(dec->ev1, st));
   CK(cudaStreamSynchronize(st));
@@ -1271,7 +1288,7 @@ extern "C" int dabstar_decoder_fib_bits(const dabstar_decoder * dec, int recordi
 {
   if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
   const Recording & R = dec->recs[recording];
-  if (bits && R.n_slots > 0) memcpy(bits, dec->h_fib.data() + (size_t)R.slot_base * 3072, (size_t)R.n_slots * 3072);
+  if (bits && R.n_slots > 0) memcpy(bits, dec->h_fib.as<uint8_t>() + (size_t)R.slot_base * 3072, (size_t)R.n_slots * 3072);
   if (valid) for (int i = 0; i < R.n_slots; i++) memcpy(valid + 4 * i, R.frames[i].fic_valid, 4);
   return R.n_slots;
 }

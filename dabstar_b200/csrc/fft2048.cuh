@@ -26,22 +26,28 @@ constexpr int FFT_SB_STRIDE = 152;  // float2 per k1 row (16 j1 x 9 + 8): same p
 constexpr int FFT_SB_J1 = 9;        // 8 m2 + 1 pad: stage-3 LDS.64 of consecutive pairs hit distinct banks
 constexpr int FFT_SMEM_F2 = 16 * FFT_SB_STRIDE; // 2432 float2 = 19 456 B (>= 2048 for the natural-order staging)
 
+constexpr int FFT_TW2_F2 = 16 * 8;  // second-stage twiddle table W128^(m2*j1), [j1][m2], shared by the CTA
+
 struct FftTwiddles
 {
-  float2 w1[16]; // W2048^(t*k1), t = tid
-  float2 w2[16]; // W128^(m2*j1) = W2048^(16*m2*j1), m2 = tid & 7
+  float2 w1[16];      // W2048^(t*k1), t = tid: per thread, in registers
+  const float2 * w2;  // shared-memory table [j1][m2] = W128^(m2*j1) = W2048^(16*m2*j1)
 };
 
-// w2048[m] = e^{-j 2 pi m / 2048}, computed on the host in double (tables.cu)
-__host__ __device__ inline void fft_load_twiddles(FftTwiddles & tw, const float2 * w2048, int tid)
+// w2048[m] = e^{-j 2 pi m / 2048}, computed on the host in double (tables.cu). tw2 must hold FFT_TW2_F2 entries;
+// every thread of the CTA calls this (the caller synchronises before the first transform).
+__host__ __device__ inline void fft_load_twiddles(FftTwiddles & tw, const float2 * w2048, float2 * tw2, int tid)
 {
 #pragma unroll
-  for (int i = 0; i < 16; i++)
-  {
-    tw.w1[i] = w2048[(tid * i) & 2047];
-    tw.w2[i] = w2048[(16 * (tid & 7) * i) & 2047];
-  }
+  for (int i = 0; i < 16; i++) tw.w1[i] = w2048[(tid * i) & 2047];
+  tw2[tid] = w2048[(16 * (tid & 7) * (tid >> 3)) & 2047]; // tid = 8*j1 + m2
+  tw.w2 = tw2;
 }
+
+// Natural-order staging index: one pad element per 16 so that the stage-3 scatter (stride 16) and the strided
+// gathers of the callers spread over the banks.
+__host__ __device__ inline int fft_nat(int n) { return n + (n >> 4); }
+constexpr int FFT_NAT_F2 = 2048 + 128;
 
 __host__ __device__ inline void dft4(float2 & a, float2 & b, float2 & c, float2 & d)
 {
@@ -130,7 +136,7 @@ __host__ __device__ inline void fft_stage2(float2 (&v)[16], const FftTwiddles & 
 #pragma unroll
   for (int j1 = 0; j1 < 16; j1++)
   {
-    const float2 b = j1 == 0 ? v[0] : cmul(v[j1], tw.w2[j1]);
+    const float2 b = j1 == 0 ? v[0] : cmul(v[j1], tw.w2[8 * j1 + m2]);
     smem[k1 * FFT_SB_STRIDE + j1 * FFT_SB_J1 + m2] = b;
   }
 }
@@ -156,7 +162,7 @@ __host__ __device__ inline int fft_out_index(int tid, int h, int j2)
 
 #ifdef __CUDACC__
 // Whole transform for a CTA of FFT_THREADS threads. v[n1] = x[128 n1 + tid] on entry; on return the
-// natural-order spectrum is in smem[0..2047] (all threads synchronised).
+// natural-order spectrum is in smem[fft_nat(0..2047)] (all threads synchronised).
 __device__ inline void fft2048_to_smem(float2 (&v)[16], const FftTwiddles & tw, float2 * smem, int tid)
 {
   fft_stage1(v, tw, smem, tid);
@@ -170,7 +176,7 @@ __device__ inline void fft2048_to_smem(float2 (&v)[16], const FftTwiddles & tw, 
 #pragma unroll
   for (int h = 0; h < 2; h++)
 #pragma unroll
-    for (int j2 = 0; j2 < 8; j2++) smem[fft_out_index(tid, h, j2)] = v[8 * h + j2];
+    for (int j2 = 0; j2 < 8; j2++) smem[fft_nat(fft_out_index(tid, h, j2))] = v[8 * h + j2];
   __syncthreads();
 }
 #endif

@@ -8,6 +8,7 @@
 #include "fft2048.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace dab
@@ -15,20 +16,19 @@ namespace dab
 namespace
 {
 // ------------------------------------------------------------------------------------------------ ingest
-// One IQ pair -> complex float. u8: (v - 127.38)/128 (raw_reader.cpp:66-70); i16: v/32768 (xml_reader.cpp:254-372).
+// Raw IQ pair as stored in the recording. u8: (v - 127.38)/128 (raw_reader.cpp:66-70); i16: v/32768 (xml_reader.cpp:254-372).
+template <int FMT> struct Raw;
+template <> struct Raw<FMT_U8> { typedef uchar2 type; };
+template <> struct Raw<FMT_I16> { typedef short2 type; };
+template <> struct Raw<FMT_CF32> { typedef float2 type; };
+
+__device__ __forceinline__ float2 to_cf(uchar2 v) { return make_float2(((float)v.x - 127.38f) * (1.0f / 128.0f), ((float)v.y - 127.38f) * (1.0f / 128.0f)); }
+__device__ __forceinline__ float2 to_cf(short2 v) { return make_float2((float)v.x * (1.0f / 32768.0f), (float)v.y * (1.0f / 32768.0f)); }
+__device__ __forceinline__ float2 to_cf(float2 v) { return v; }
+
 template <int FMT> __device__ __forceinline__ float2 load_sample(const void * __restrict__ iq, long long i)
 {
-  if (FMT == FMT_U8)
-  {
-    const uchar2 v = reinterpret_cast<const uchar2 *>(iq)[i];
-    return make_float2(((float)v.x - 127.38f) * (1.0f / 128.0f), ((float)v.y - 127.38f) * (1.0f / 128.0f));
-  }
-  else if (FMT == FMT_I16)
-  {
-    const short2 v = reinterpret_cast<const short2 *>(iq)[i];
-    return make_float2((float)v.x * (1.0f / 32768.0f), (float)v.y * (1.0f / 32768.0f));
-  }
-  else return reinterpret_cast<const float2 *>(iq)[i];
+  return to_cf(reinterpret_cast<const typename Raw<FMT>::type *>(iq)[i]);
 }
 
 __device__ __forceinline__ int mod_fs(long long x)
@@ -37,26 +37,58 @@ __device__ __forceinline__ int mod_fs(long long x)
   return r < 0 ? r + FS : r;
 }
 
-// e^{j 2 pi idx / FS}: the reference's oscillator table entry (sample_reader.cpp:44-50), evaluated in double.
+// e^{j 2 pi idx / FS}, the reference's oscillator table entry (sample_reader.cpp:44-50), without the 16 MB table:
+// exact integer reduction to a quadrant, float sincos of an angle in [0, pi/2) (|phase error| < 2e-7 rad), exact
+// quadrant rotation.
 __device__ __forceinline__ float2 osc(int idx)
 {
-  double s, c;
-  sincospi(2.0 * (double)idx / (double)FS, &s, &c);
-  return make_float2((float)c, (float)s);
+  const int q = idx / (FS / 4), rem = idx - q * (FS / 4);
+  float s, c;
+  sincosf((float)rem * (PI_2_F / (float)(FS / 4)), &s, &c);
+  switch (q)
+  {
+  case 0: return make_float2(c, s);
+  case 1: return make_float2(-s, c);
+  case 2: return make_float2(-c, -s);
+  default: return make_float2(s, -c);
+  }
 }
 
-// Loads the 2048 samples starting at `start` in the FFT's register layout (v[n1] = x[128 n1 + tid]) and mixes them
-// with the integer-Hz oscillator. `ph` is the oscillator phase BEFORE sample `start`. step[] is a 16-entry
-// shared scratch (phasor of -f*128*n1).
+// Fetches the 2048 raw samples starting at `start` in the FFT's register layout (r[n1] = x[128 n1 + tid]).
 template <int FMT>
-__device__ __forceinline__ void load_symbol(float2 (&v)[16], const void * __restrict__ iq, long long n_total, long long start, int f, int ph,
-                                            float2 * step, int tid)
+__device__ __forceinline__ void fetch_symbol(typename Raw<FMT>::type (&r)[16], const void * __restrict__ iq, long long n_total, long long start, int tid)
 {
+  typedef typename Raw<FMT>::type T;
+  const T * p = reinterpret_cast<const T *>(iq) + start + tid;
+  if (start >= 0 && start + T_U <= n_total)
+  {
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) r[n1] = p[128 * n1];
+  }
+  else
+  {
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++)
+    {
+      const long long i = start + 128 * n1 + tid;
+      if (i >= 0 && i < n_total) r[n1] = p[128 * n1];
+      else r[n1] = T(); // outside the recording; mix_symbol replaces it by a zero amplitude
+    }
+  }
+}
+
+// Converts the fetched samples and mixes them with the integer-Hz oscillator. `ph` is the oscillator phase BEFORE
+// sample `start`. step[] is a 16-entry shared scratch (phasor of -f*128*n1). Samples outside the recording are zero.
+template <int FMT>
+__device__ __forceinline__ void mix_symbol(float2 (&v)[16], const typename Raw<FMT>::type (&r)[16], long long n_total, long long start, int f, int ph,
+                                           float2 * step, int tid)
+{
+  const bool inside = start >= 0 && start + T_U <= n_total;
 #pragma unroll
   for (int n1 = 0; n1 < 16; n1++)
   {
-    const long long i = start + 128 * n1 + tid;
-    v[n1] = (i >= 0 && i < n_total) ? load_sample<FMT>(iq, i) : make_float2(0.0f, 0.0f);
+    v[n1] = to_cf(r[n1]);
+    if (!inside) { const long long i = start + 128 * n1 + tid; if (i < 0 || i >= n_total) v[n1] = make_float2(0.0f, 0.0f); }
   }
   if (f == 0 && ph == 0) return; // osc[0] = 1: the reference multiplies by exactly (1, 0)
   if (tid < 16) step[tid] = osc(mod_fs(-(long long)f * 128 * tid));
@@ -67,52 +99,104 @@ __device__ __forceinline__ void load_symbol(float2 (&v)[16], const void * __rest
   __syncthreads();
 }
 
+template <int FMT>
+__device__ __forceinline__ void load_symbol(float2 (&v)[16], const void * __restrict__ iq, long long n_total, long long start, int f, int ph,
+                                            float2 * step, int tid)
+{
+  typename Raw<FMT>::type r[16];
+  fetch_symbol<FMT>(r, iq, n_total, start, tid);
+  mix_symbol<FMT>(v, r, n_total, start, f, ph, step, tid);
+}
+
 // ------------------------------------------------------------------------------------------------ FFT of whole frames
 // Work item = (frame, row): row 0 = symbol 0, rows 1..75 data symbols, row 76 the null symbol.
-// Output: X[slot][row][k] = spectrum at the bin of nominal carrier k (frequency de-interleaving fused into the store).
+// Output: X[xslot][row][k] = spectrum at the bin of nominal carrier k (frequency de-interleaving fused into the store).
+struct SymbolItem
+{
+  const void * iq;
+  long long n_total, start;
+  int f, ph;
+  long long out; // float2 index of X row, -1: nothing to do
+};
+
+__device__ __forceinline__ SymbolItem symbol_item(const FrameDesc * __restrict__ frames, const RecInput * __restrict__ recs, int item)
+{
+  SymbolItem it;
+  const int fi = item / X_ROWS, row = item - fi * X_ROWS;
+  const FrameDesc fd = frames[fi];
+  const RecInput rin = recs[fd.rec];
+  it.iq = rin.iq;
+  it.n_total = rin.n;
+  it.out = ((long long)fd.xslot * X_ROWS + row) * K_CARR;
+  if (row == 0) { it.start = fd.sym0; it.f = fd.f_sym0; it.ph = mod_fs((long long)fd.ph_eval - (long long)it.f * (fd.sym0 - fd.eval)); }
+  else if (row <= 75)
+  {
+    it.start = fd.sym0 + T_U + (long long)(row - 1) * T_S + T_G;
+    it.f = fd.f_data;
+    it.ph = mod_fs((long long)fd.ph_data - (long long)it.f * ((long long)(row - 1) * T_S + T_G));
+    if (row > fd.n_syms) it.out = -1;
+  }
+  else
+  {
+    it.start = fd.sym0 + T_U + 75LL * T_S + T_G;
+    it.f = fd.f_null;
+    it.ph = mod_fs((long long)fd.ph_null - (long long)it.f * T_G);
+    if (fd.n_syms < 75) it.out = -1;
+  }
+  return it;
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(FFT_THREADS, 4) k_fft_frames(const FrameDesc * __restrict__ frames, int n_items, const RecInput * __restrict__ recs,
                                                                const float2 * __restrict__ w2048, const int16_t * __restrict__ bin_of_k,
                                                                float2 * __restrict__ X)
 {
   __shared__ float2 smem[FFT_SMEM_F2];
+  __shared__ float2 tw2s[FFT_TW2_F2];
   __shared__ float2 step[16];
-  __shared__ int16_t bins[K_CARR];
+  __shared__ int16_t bins[K_CARR]; // padded natural-order slot of nominal carrier k
   const int tid = threadIdx.x;
   FftTwiddles tw;
-  fft_load_twiddles(tw, w2048, tid);
-  for (int k = tid; k < K_CARR; k += FFT_THREADS) bins[k] = bin_of_k[k];
+  fft_load_twiddles(tw, w2048, tw2s, tid);
+  for (int k = tid; k < K_CARR; k += FFT_THREADS) bins[k] = (int16_t)fft_nat(bin_of_k[k]);
   __syncthreads();
 
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x)
+  // software pipeline: the raw samples of the next symbol are in flight while the current one is transformed
+  typename Raw<FMT>::type raw[16];
+  int item = blockIdx.x;
+  SymbolItem cur;
+  if (item < n_items)
   {
-    const int fi = item / X_ROWS, row = item - fi * X_ROWS;
-    const FrameDesc fd = frames[fi];
-    if (row >= 1 && row <= 75 && row > fd.n_syms) continue;
-    if (row == 76 && fd.n_syms < 75) continue;
-    const RecInput rin = recs[fd.rec];
-    long long start;
-    int f, ph;
-    if (row == 0) { start = fd.sym0; f = fd.f_sym0; ph = mod_fs((long long)fd.ph_eval - (long long)f * (fd.sym0 - fd.eval)); }
-    else if (row <= 75)
-    {
-      start = fd.sym0 + T_U + (long long)(row - 1) * T_S + T_G;
-      f = fd.f_data;
-      ph = mod_fs((long long)fd.ph_data - (long long)f * ((long long)(row - 1) * T_S + T_G));
-    }
-    else { start = fd.sym0 + T_U + 75LL * T_S + T_G; f = fd.f_null; ph = mod_fs((long long)fd.ph_null - (long long)f * T_G); }
-
+    cur = symbol_item(frames, recs, item);
+    if (cur.out >= 0) fetch_symbol<FMT>(raw, cur.iq, cur.n_total, cur.start, tid);
+  }
+  while (item < n_items)
+  {
     float2 v[16];
-    load_symbol<FMT>(v, rin.iq, rin.n, start, f, ph, step, tid);
-    fft2048_to_smem(v, tw, smem, tid);
-    float2 * out = X + ((size_t)fd.xslot * X_ROWS + row) * K_CARR;
-#pragma unroll
-    for (int i = 0; i < K_CARR / FFT_THREADS; i++)
+    const bool active = cur.out >= 0;
+    if (active) mix_symbol<FMT>(v, raw, cur.n_total, cur.start, cur.f, cur.ph, step, tid);
+    const int next = item + gridDim.x;
+    SymbolItem nxt;
+    nxt.out = -1;
+    if (next < n_items)
     {
-      const int k = tid + FFT_THREADS * i;
-      out[k] = smem[bins[k]];
+      nxt = symbol_item(frames, recs, next);
+      if (nxt.out >= 0) fetch_symbol<FMT>(raw, nxt.iq, nxt.n_total, nxt.start, tid);
     }
-    __syncthreads();
+    if (active)
+    {
+      fft2048_to_smem(v, tw, smem, tid);
+      float2 * out = X + cur.out;
+#pragma unroll
+      for (int i = 0; i < K_CARR / FFT_THREADS; i++)
+      {
+        const int k = tid + FFT_THREADS * i;
+        out[k] = smem[bins[k]];
+      }
+      __syncthreads();
+    }
+    cur = nxt;
+    item = next;
   }
 }
 
@@ -121,9 +205,11 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) k_fft_batch(const float2 * __r
                                                               const float2 * __restrict__ w2048)
 {
   __shared__ float2 smem[FFT_SMEM_F2];
+  __shared__ float2 tw2s[FFT_TW2_F2];
   const int tid = threadIdx.x;
   FftTwiddles tw;
-  fft_load_twiddles(tw, w2048, tid);
+  fft_load_twiddles(tw, w2048, tw2s, tid);
+  __syncthreads();
   for (int item = blockIdx.x; item < n; item += gridDim.x)
   {
     float2 v[16];
@@ -136,7 +222,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) k_fft_batch(const float2 * __r
     fft2048_to_smem(v, tw, smem, tid);
     for (int i = tid; i < T_U; i += FFT_THREADS)
     {
-      float2 r = smem[i];
+      float2 r = smem[fft_nat(i)];
       if (sign > 0) r.y = -r.y;
       out[(size_t)item * T_U + i] = r;
     }
@@ -171,7 +257,7 @@ __device__ void prs_correlate_cta(float2 (&v)[16], const FftTwiddles & tw, const
   for (int n1 = 0; n1 < 16; n1++)
   {
     const int i = 128 * n1 + tid;
-    const float2 x = smem[i], p = prs[i];
+    const float2 x = smem[fft_nat(i)], p = prs[i];
     v[n1] = make_float2(x.x * p.x + x.y * p.y, x.x * p.y - x.y * p.x); // conj(x) * p
   }
   __syncthreads();
@@ -182,7 +268,7 @@ __device__ void prs_correlate_cta(float2 (&v)[16], const FftTwiddles & tw, const
 #pragma unroll
   for (int n1 = 0; n1 < 16; n1++)
   {
-    const float2 c = smem[128 * n1 + tid];
+    const float2 c = smem[fft_nat(128 * n1 + tid)];
     m[n1] = sqrtf(c.x * c.x + c.y * c.y);
     part += m[n1];
   }
@@ -242,8 +328,10 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) k_prs_corr(const FrameDesc * _
   __shared__ float red[4];
   __shared__ int result;
   const int tid = threadIdx.x;
+  __shared__ float2 tw2s[FFT_TW2_F2];
   FftTwiddles tw;
-  fft_load_twiddles(tw, w2048, tid);
+  fft_load_twiddles(tw, w2048, tw2s, tid);
+  __syncthreads();
   for (int fi = blockIdx.x; fi < n_frames; fi += gridDim.x)
   {
     const FrameDesc fd = frames[fi];
@@ -265,8 +353,10 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) k_prs_corr_raw(const float2 * 
   __shared__ float red[4];
   __shared__ int result;
   const int tid = threadIdx.x;
+  __shared__ float2 tw2s[FFT_TW2_F2];
   FftTwiddles tw;
-  fft_load_twiddles(tw, w2048, tid);
+  fft_load_twiddles(tw, w2048, tw2s, tid);
+  __syncthreads();
   for (int it = blockIdx.x; it < n; it += gridDim.x)
   {
     float2 v[16];
@@ -290,7 +380,7 @@ __device__ void coarse_afc_cta(const FftTwiddles & tw, const float2 * __restrict
     const int i = 128 * n1 + tid;
     if (i < T_U - 1)
     {
-      const float2 a = smem[i], b = smem[i + 1];
+      const float2 a = smem[fft_nat(i)], b = smem[fft_nat(i + 1)];
       const float2 d = make_float2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
       v[n1] = make_float2(d.x, -d.y);
     }
@@ -302,15 +392,15 @@ __device__ void coarse_afc_cta(const FftTwiddles & tw, const float2 * __restrict
   for (int n1 = 0; n1 < 16; n1++)
   {
     const int i = 128 * n1 + tid;
-    const float2 c = make_float2(smem[i].x, -smem[i].y);
-    v[n1] = cmul(c, ref_arg_conj[i]);
+    const float2 sv = smem[fft_nat(i)];
+    v[n1] = cmul(make_float2(sv.x, -sv.y), ref_arg_conj[i]);
   }
   __syncthreads();
   fft2048_to_smem(v, tw, smem, tid);
   // peak over bins -70..70 (phasereference.cpp:248-279)
   for (int i = tid; i < 143; i += FFT_THREADS)
   {
-    const float2 c = smem[(T_U + i - 71) & (T_U - 1)];
+    const float2 c = smem[fft_nat((T_U + i - 71) & (T_U - 1))];
     magw[i] = sqrtf(c.x * c.x + c.y * c.y); // magw[i] = |bin i-71|, i = 0..142 (one guard bin each side)
   }
   __syncthreads();
@@ -346,8 +436,10 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) k_coarse_afc(const FrameDesc *
   __shared__ float magw[144];
   __shared__ int result;
   const int tid = threadIdx.x;
+  __shared__ float2 tw2s[FFT_TW2_F2];
   FftTwiddles tw;
-  fft_load_twiddles(tw, w2048, tid);
+  fft_load_twiddles(tw, w2048, tw2s, tid);
+  __syncthreads();
   for (int fi = blockIdx.x; fi < n_frames; fi += gridDim.x)
   {
     const FrameDesc fd = frames[fi];
@@ -362,18 +454,20 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) k_coarse_afc(const FrameDesc *
   }
 }
 
-__global__ void __launch_bounds__(FFT_THREADS, 4) k_coarse_afc_raw(const float2 * __restrict__ fft_nat, int n, const float2 * __restrict__ w2048,
+__global__ void __launch_bounds__(FFT_THREADS, 4) k_coarse_afc_raw(const float2 * __restrict__ fft_nat_in, int n, const float2 * __restrict__ w2048,
                                                                    const float2 * __restrict__ ref_arg_conj, int * __restrict__ offset_hz)
 {
   __shared__ float2 smem[FFT_SMEM_F2];
   __shared__ float magw[144];
   __shared__ int result;
   const int tid = threadIdx.x;
+  __shared__ float2 tw2s[FFT_TW2_F2];
   FftTwiddles tw;
-  fft_load_twiddles(tw, w2048, tid);
+  fft_load_twiddles(tw, w2048, tw2s, tid);
+  __syncthreads();
   for (int it = blockIdx.x; it < n; it += gridDim.x)
   {
-    for (int i = tid; i < T_U; i += FFT_THREADS) smem[i] = fft_nat[(size_t)it * T_U + i];
+    for (int i = tid; i < T_U; i += FFT_THREADS) smem[fft_nat(i)] = fft_nat_in[(size_t)it * T_U + i];
     __syncthreads();
     coarse_afc_cta(tw, ref_arg_conj, smem, magw, &result, tid);
     if (tid == 0) offset_hz[it] = result;
@@ -386,8 +480,10 @@ __global__ void __launch_bounds__(FFT_THREADS) k_init_ref_arg(const float2 * __r
 {
   __shared__ float2 smem[FFT_SMEM_F2];
   const int tid = threadIdx.x;
+  __shared__ float2 tw2s[FFT_TW2_F2];
   FftTwiddles tw;
-  fft_load_twiddles(tw, w2048, tid);
+  fft_load_twiddles(tw, w2048, tw2s, tid);
+  __syncthreads();
   float2 v[16];
 #pragma unroll
   for (int n1 = 0; n1 < 16; n1++)
@@ -402,7 +498,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_init_ref_arg(const float2 * __r
   }
   fft2048_to_smem(v, tw, smem, tid);
   // IFFT(d) = conj(smem); ref_arg_conj = conj(IFFT(d)) = smem
-  for (int i = tid; i < T_U; i += FFT_THREADS) ref_arg_conj[i] = smem[i];
+  for (int i = tid; i < T_U; i += FFT_THREADS) ref_arg_conj[i] = smem[fft_nat(i)];
 }
 
 // ------------------------------------------------------------------------------------------------ CP correlation (F2)
@@ -591,6 +687,218 @@ __global__ void __launch_bounds__(DEMAP_THREADS, 1) k_demap(const DemapWork * __
   if (tid == 0) sd.mean_value = mean_value;
 }
 
+// ------------------------------------------------------------------------------------------------ DQPSK demapper, cluster version
+// The same arithmetic as k_demap, laid out for throughput: a cluster of 4 CTAs x 384 threads decodes one recording, one
+// nominal carrier per thread, so 96 recordings fill the 148 SMs with ~36 resident warps each. The only coupling between
+// carriers is mMeanValue (the sum of |r| over the 1536 carriers of the PREVIOUS symbol, ofdm_decoder.cpp:256,294).
+// It is exchanged through distributed shared memory without any block or cluster barrier in the loop:
+//   * every warp reduces its 32 |r| values (fixed shuffle tree) and stores {sum, tag} as ONE 64-bit word into slot
+//     [symbol mod 4][warp] of the ring in each of the 4 CTAs (st.shared::cluster.b64, single-copy atomic);
+//   * warp 0 of each CTA polls the 48 words of that symbol, adds them in a fixed order and publishes {total, tag};
+//   * a warp polls {total, tag} of symbol g-1 only when it needs the scale for symbol g's output, i.e. one symbol of
+//     work later, so the poll normally falls through.
+// The ring depth of 4 is safe because a warp can run at most one symbol ahead of the slowest warp of the cluster.
+// Division, square root and atan2 use the SFU approximations (<= 2 ulp each); the +-1 LSB soft-bit bar is unaffected
+// (tests/test_gpu_stages.py::test_ofdm_decoder_soft_bits).
+constexpr int DM2_CLUSTER = 4;
+constexpr int DM2_THREADS = K_CARR / DM2_CLUSTER;      // 384
+constexpr int DM2_WARPS = DM2_THREADS / 32;            // 12
+constexpr int DM2_ALL_WARPS = DM2_WARPS * DM2_CLUSTER; // 48
+constexpr int DM2_RING = 4;
+
+__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float fast_sqrt(float a)
+{
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+
+// turn_phase_to_first_quadrant(arg(z)) (glob_defs.h:173-182) without atan2/fmod: rotate z by a multiple of 90 degrees
+// into the first quadrant, then atan of a ratio <= 1 (Cephes-style reduction, |error| < 2e-7 rad).
+__device__ __forceinline__ float first_quadrant_phase(float x, float y)
+{
+  float u, v;
+  if (y >= 0.0f) { if (x > 0.0f) { u = x; v = y; } else { u = y; v = -x; } }
+  else { if (x < 0.0f) { u = -x; v = -y; } else { u = -y; v = x; } }
+  const bool swap = v > u;
+  const float num = swap ? u : v, den = swap ? v : u;
+  float t = den > 0.0f ? fast_div(num, den) : 0.0f;       // t in [0, 1]
+  const bool hi = t > 0.4142135623730950f;                // tan(pi/8)
+  if (hi) t = fast_div(t - 1.0f, t + 1.0f);
+  const float z = t * t;
+  float p = ((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f;
+  float a = p * z * t + t;
+  if (hi) a += PI_4_F;
+  return swap ? PI_2_F - a : a;
+}
+
+template <int SOFT>
+__device__ __forceinline__ float2 demap_carrier_fast(CarrierState & st, float2 x, float2 ref, float clock_term)
+{
+  constexpr float ALPHA = 0.005f;
+  const float ref_abs = fast_sqrt(ref.x * ref.x + ref.y * ref.y);
+  const float inv_ref = fast_div(1.0f, ref_abs);
+  float2 raw = cmul_conj(x, ref);
+  raw.x *= inv_ref;
+  raw.y *= inv_ref;
+  const float a = -(clock_term + st.integ), a2 = a * a;
+  const float2 rot = make_float2(0.9994032382965087890625f + a2 * (a2 * 3.679168224334716796875e-2f + -0.495580852031707763671875f),
+                                 a * (a2 * -0.16034401953220367431640625f + 0.99903142452239990234375f));
+  const float2 z = cmul(raw, rot);
+  const float ph = first_quadrant_phase(z.x, z.y);
+  st.integ += 0.2f * ALPHA * (ph - PI_4_F);
+  st.integ = fminf(fmaxf(st.integ, -20.0f * RAD_PER_DEG_F), 20.0f * RAD_PER_DEG_F);
+  const float dv = ph - PI_4_F;
+  st.stddev += ALPHA * (dv * dv - st.stddev);
+  const float pw = z.x * z.x + z.y * z.y;
+  st.mean_pow += ALPHA * (pw - st.mean_pow);
+  const float lvl = fast_sqrt(st.mean_pow);
+  const float axis = lvl * 0.70710678118654752440f;
+  const float dr = fabsf(z.x) - axis, di = fabsf(z.y) - axis;
+  st.mean_sigma += ALPHA * (dr * dr + di * di - st.mean_sigma);
+  float sig = st.mean_pow - st.null_pow;
+  if (sig <= 0.0f) sig = 0.1f;
+  float w1;
+  if (SOFT == 2) w1 = ref_abs;
+  else if (SOFT == 1) w1 = fast_div(ref_abs, st.mean_sigma * (fast_div(st.null_pow, sig) + 0.7f));
+  else
+  {
+    const float zabs = fast_sqrt(pw);
+    // sqrt(zabs*ref_abs) * lvl / (nullPow/sig + 0.7) / (meanSigma * zabs)
+    w1 = fast_div(fast_sqrt(zabs * ref_abs) * lvl, (fast_div(st.null_pow, sig) + 0.7f) * (st.mean_sigma * zabs));
+  }
+  return make_float2(z.x * w1, z.y * w1);
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void * p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_cluster_b64(unsigned local_addr, unsigned rank, unsigned long long v)
+{
+  unsigned remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(remote), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_volatile_b64(unsigned addr)
+{
+  unsigned long long v;
+  asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_rank()
+{
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+template <int SOFT>
+__global__ void __cluster_dims__(DM2_CLUSTER, 1, 1) __launch_bounds__(DM2_THREADS, 3)
+k_demap2(const DemapWork * __restrict__ work, const FrameDesc * __restrict__ frames, const uint8_t * __restrict__ null_is_tii,
+         const float2 * __restrict__ X, const int16_t * __restrict__ rel_of_k, OfdmStateDev * __restrict__ states, int16_t * __restrict__ soft)
+{
+  __shared__ __align__(8) unsigned long long ring[DM2_RING][DM2_ALL_WARPS]; // {tag << 32 | float bits} per warp of the cluster
+  __shared__ __align__(8) unsigned long long total[DM2_RING];
+  const DemapWork wk = work[blockIdx.x / DM2_CLUSTER];
+  const unsigned rank = cluster_rank();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = (int)rank * DM2_THREADS + tid;
+  const int cwarp = (int)rank * DM2_WARPS + warp;
+  for (int i = tid; i < DM2_RING * DM2_ALL_WARPS; i += DM2_THREADS) (&ring[0][0])[i] = 0ull;
+  if (tid < DM2_RING) total[tid] = 0ull;
+  cluster_sync_all(); // rings are zero before any remote store can arrive
+
+  OfdmStateDev & sd = states[wk.state];
+  CarrierState s = wk.reset ? CarrierState{ 0.0f, 0.0f, 0.0f, 0.0f, 0.0f }
+                            : CarrierState{ sd.integ[k], sd.stddev[k], sd.mean_pow[k], sd.mean_sigma[k], sd.null_pow[k] };
+  float mean_value = sd.mean_value;
+  const float gk = (float)(K_CARR / 2 - rel_of_k[k]) / (float)(K_CARR / 2);
+  constexpr float W2 = SOFT == 0 ? -100.0f : -140.0f;
+  const unsigned ring_base = smem_u32(&ring[0][0]), total_base = smem_u32(&total[0]);
+  int g = 0; // symbols decoded so far in this launch; tag of symbol g is g + 1
+
+  for (int fi = 0; fi < wk.n_frames; fi++)
+  {
+    const FrameDesc fd = frames[wk.desc_first + fi];
+    const float2 * row = X + (size_t)fd.xslot * X_ROWS * K_CARR + k;
+    int16_t * out = soft + (size_t)fd.slot * FRAME_SOFT + k;
+    const float cterm = fd.clock_err / 1024.0f * PI_F * gk;
+    float2 ref = row[0];
+    float2 cur = fd.n_syms >= 1 ? row[K_CARR] : ref;
+    float2 nxt = fd.n_syms >= 1 ? row[2 * K_CARR] : ref;
+    for (int sym = 1; sym <= fd.n_syms; sym++, g++)
+    {
+      const float2 nn = sym + 2 <= 76 ? row[(size_t)(sym + 2) * K_CARR] : nxt; // prefetch two rows ahead (row 76 = null symbol)
+      const float2 r = demap_carrier_fast<SOFT>(s, cur, ref, cterm);
+      // publish this warp's share of sum |r| for symbol g
+      float part = fast_sqrt(r.x * r.x + r.y * r.y);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      const unsigned long long word = ((unsigned long long)(unsigned)(g + 1) << 32) | (unsigned long long)__float_as_uint(part);
+      if (lane < DM2_CLUSTER) st_cluster_b64(ring_base + 8u * (unsigned)((g & (DM2_RING - 1)) * DM2_ALL_WARPS + cwarp), (unsigned)lane, word);
+      // scale of symbol g = mean |r| of symbol g-1
+      if (g > 0)
+      {
+        const unsigned addr = total_base + 8u * (unsigned)((g - 1) & (DM2_RING - 1));
+        unsigned long long t = ld_volatile_b64(addr);
+        while ((unsigned)(t >> 32) != (unsigned)g) t = ld_volatile_b64(addr);
+        mean_value = __uint_as_float((unsigned)t) / (float)K_CARR;
+      }
+      const float w2 = fast_div(W2, mean_value);
+      out[(size_t)(sym - 1) * SYM_BITS] = to_i16(r.x * w2);
+      out[(size_t)(sym - 1) * SYM_BITS + K_CARR] = to_i16(r.y * w2);
+      // warp 0 gathers the 48 partial sums of symbol g and publishes the total
+      if (warp == 0)
+      {
+        const unsigned slot = ring_base + 8u * (unsigned)((g & (DM2_RING - 1)) * DM2_ALL_WARPS);
+        float acc = 0.0f;
+        if (lane < DM2_ALL_WARPS - 32)
+        {
+          unsigned long long e = ld_volatile_b64(slot + 8u * (unsigned)(lane + 32));
+          while ((unsigned)(e >> 32) != (unsigned)(g + 1)) e = ld_volatile_b64(slot + 8u * (unsigned)(lane + 32));
+          acc = __uint_as_float((unsigned)e);
+        }
+        unsigned long long e = ld_volatile_b64(slot + 8u * (unsigned)lane);
+        while ((unsigned)(e >> 32) != (unsigned)(g + 1)) e = ld_volatile_b64(slot + 8u * (unsigned)lane);
+        acc += __uint_as_float((unsigned)e);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0)
+        {
+          const unsigned long long tw = ((unsigned long long)(unsigned)(g + 1) << 32) | (unsigned long long)__float_as_uint(acc);
+          asm volatile("st.volatile.shared.b64 [%0], %1;" ::"r"(total_base + 8u * (unsigned)(g & (DM2_RING - 1))), "l"(tw) : "memory");
+        }
+      }
+      ref = cur;
+      cur = nxt;
+      nxt = nn;
+    }
+    if (fd.n_syms == 75 && !(null_is_tii != nullptr && null_is_tii[wk.desc_first + fi]))
+    {
+      constexpr float MIN_POW = (1.0f / 32767.0f) * (1.0f / 32767.0f);
+      s.null_pow += 0.05f * (cur.x * cur.x + cur.y * cur.y + MIN_POW - s.null_pow); // `cur` is row 76 here
+    }
+  }
+  // mMeanValue after the last symbol
+  if (g > 0)
+  {
+    const unsigned addr = total_base + 8u * (unsigned)((g - 1) & (DM2_RING - 1));
+    unsigned long long t = ld_volatile_b64(addr);
+    while ((unsigned)(t >> 32) != (unsigned)g) t = ld_volatile_b64(addr);
+    mean_value = __uint_as_float((unsigned)t) / (float)K_CARR;
+  }
+  sd.integ[k] = s.integ;
+  sd.stddev[k] = s.stddev;
+  sd.mean_pow[k] = s.mean_pow;
+  sd.mean_sigma[k] = s.mean_sigma;
+  sd.null_pow[k] = s.null_pow;
+  cluster_sync_all(); // nobody leaves while a peer may still store into its ring; all reads of sd.mean_value are done
+  if (rank == 0 && tid == 0) sd.mean_value = mean_value;
+}
+
 // ------------------------------------------------------------------------------------------------ time sync (S1)
 // TimeSyncer::read_samples_until_end_of_level_drop (timesyncer.cpp:40-90) on top of SampleReader's level IIR
 // (sample_reader.cpp:236, alpha = 1e-5). One CTA per recording; the stream is scanned in blocks of 1024 samples.
@@ -773,13 +1081,25 @@ cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork
                          unsigned long long * lc)
 {
   if (n_work <= 0) return cudaSuccess;
+  if (soft_bit_type < 0 || soft_bit_type > 2) return cudaErrorInvalidValue;
   if (lc) (*lc)++;
+  static const bool use_v1 = getenv("DABSTAR_DEMAP_V1") != nullptr; // one CTA per recording, IEEE div/sqrt/atan2 (debug aid)
+  if (use_v1)
+  {
+    switch (soft_bit_type)
+    {
+    case 0: k_demap<0><<<n_work, DEMAP_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
+    case 1: k_demap<1><<<n_work, DEMAP_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
+    default: k_demap<2><<<n_work, DEMAP_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
+    }
+    return cudaGetLastError();
+  }
+  const int grid = n_work * DM2_CLUSTER;
   switch (soft_bit_type)
   {
-  case 0: k_demap<0><<<n_work, DEMAP_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
-  case 1: k_demap<1><<<n_work, DEMAP_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
-  case 2: k_demap<2><<<n_work, DEMAP_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
-  default: return cudaErrorInvalidValue;
+  case 0: k_demap2<0><<<grid, DM2_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
+  case 1: k_demap2<1><<<grid, DM2_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
+  default: k_demap2<2><<<grid, DM2_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
   }
   return cudaGetLastError();
 }

@@ -1,0 +1,88 @@
+// dab_file_decode — headless file-input harness: raw interleaved IQ file(s) -> decoded FIC / MSC bits on the GPU.
+//
+//   dab_file_decode [-f u8|i16|cf32] [-s subChId,startCU,sizeCU,shortForm,protLevel,bitRate]... [-o prefix] file.iq [file2.iq ...]
+//
+// The reference can only play files through its GUI, paced to real time (raw_reader.cpp:153-165); this harness feeds
+// whole files to dabstar::DabProcessor (one reference DabProcessor per file, all files in lock step) and writes
+//   <prefix><n>.fic      CRC-good FIBs packed to 32 bytes, the reference's FIC dump format (fic_decoder.cpp:291-308)
+//   <prefix><n>.sub<id>  the sub-channel's logical frames packed 8 bits per byte (as eti_generator.cpp:403-411 packs them)
+// Build: g++ -std=c++17 -O2 dab_file_decode.cpp -I../../include -L.. -ldabstar_b200 -o dab_file_decode
+#include "dabstar_facade.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+static std::vector<unsigned char> read_file(const char * path)
+{
+  FILE * f = fopen(path, "rb");
+  if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<unsigned char> v((size_t)n);
+  if (n > 0 && fread(v.data(), 1, (size_t)n, f) != (size_t)n) { fclose(f); throw std::runtime_error("short read"); }
+  fclose(f);
+  return v;
+}
+
+int main(int argc, char ** argv)
+{
+  int fmt = DABSTAR_FMT_U8;
+  std::string prefix = "dab_out_";
+  std::vector<dabstar_subch> subch;
+  std::vector<const char *> files;
+  for (int i = 1; i < argc; i++)
+  {
+    const std::string a = argv[i];
+    if (a == "-f" && i + 1 < argc) { const std::string v = argv[++i]; fmt = v == "i16" ? DABSTAR_FMT_I16 : (v == "cf32" ? DABSTAR_FMT_CF32 : DABSTAR_FMT_U8); }
+    else if (a == "-o" && i + 1 < argc) prefix = argv[++i];
+    else if (a == "-s" && i + 1 < argc)
+    {
+      dabstar_subch s{};
+      if (sscanf(argv[++i], "%d,%d,%d,%d,%d,%d", &s.sub_ch_id, &s.start_cu, &s.size_cu, &s.short_form, &s.prot_level, &s.bit_rate) != 6) { fprintf(stderr, "bad -s\n"); return 2; }
+      subch.push_back(s);
+    }
+    else files.push_back(argv[i]);
+  }
+  if (files.empty()) { fprintf(stderr, "usage: dab_file_decode [-f u8|i16|cf32] [-s id,startCU,sizeCU,shortForm,protLevel,bitRate]... [-o prefix] file.iq ...\n"); return 2; }
+  try
+  {
+    dabstar::Context ctx(0);
+    const size_t bps = fmt == DABSTAR_FMT_U8 ? 2 : (fmt == DABSTAR_FMT_I16 ? 4 : 8);
+    std::vector<std::vector<unsigned char>> data;
+    std::vector<const void *> ptrs;
+    std::vector<int64_t> ns;
+    for (const char * f : files) { data.push_back(read_file(f)); }
+    for (auto & d : data) { ptrs.push_back(d.data()); ns.push_back((int64_t)(d.size() / bps)); }
+    dabstar::DabProcessor proc(ctx, (int)files.size(), fmt, subch.empty());
+    for (size_t r = 0; r < files.size(); r++) proc.set_audio_channel((int)r, subch);
+    proc.run(ptrs, ns);
+    for (size_t r = 0; r < files.size(); r++)
+    {
+      long fibs = 0;
+      FILE * fic = fopen((prefix + std::to_string(r) + ".fic").c_str(), "wb");
+      std::vector<FILE *> outs;
+      for (auto & s : subch) outs.push_back(fopen((prefix + std::to_string(r) + ".sub" + std::to_string(s.sub_ch_id)).c_str(), "wb"));
+      proc.deliver((int)r,
+        [&](const std::array<dabstar::u8, 256> & fib, dabstar::u16) {
+          unsigned char b[32];
+          for (int j = 0; j < 32; j++) { b[j] = 0; for (int k = 0; k < 8; k++) b[j] = (unsigned char)((b[j] << 1) | (fib[8 * j + k] & 1)); }
+          if (fic) fwrite(b, 1, 32, fic);
+          fibs++;
+        },
+        [&](int id, const std::vector<dabstar::u8> & bits) {
+          for (size_t c = 0; c < subch.size(); c++)
+          {
+            if (subch[c].sub_ch_id != id || !outs[c]) continue;
+            for (size_t j = 0; j + 8 <= bits.size(); j += 8) { unsigned char b = 0; for (int k = 0; k < 8; k++) b = (unsigned char)((b << 1) | (bits[j + k] & 1)); fputc(b, outs[c]); }
+          }
+        }, subch);
+      if (fic) fclose(fic);
+      for (FILE * o : outs) if (o) fclose(o);
+      printf("%s: %d frames, %ld good FIBs, %.2f ms device time\n", files[r], proc.n_frames((int)r), fibs, proc.last_ms());
+    }
+  }
+  catch (const std::exception & e) { fprintf(stderr, "error: %s\n", e.what()); return 1; }
+  return 0;
+}

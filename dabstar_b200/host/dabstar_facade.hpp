@@ -1,0 +1,308 @@
+// dabstar_facade.hpp — C++ host facades over the C ABI (include/dabstar_b200.h) that keep the reference's class
+// names and call shapes, so DABstar's headless callers can switch the GPU path in for the CPU one.
+//
+//   reference class (file:line under /root/reference/src)            facade here
+//   FreqInterleaver::map_k_to_fft_bin   ofdm/freq_interleaver.h:50    dabstar::FreqInterleaver
+//   PhaseReference                       ofdm/phasereference.h:53-58   dabstar::PhaseReference
+//   ViterbiSpiral::deconvolve            viterbi_spiral.h:20           dabstar::ViterbiSpiral      (same signature)
+//   Protection::deconvolve               protection/protection.h:44    dabstar::Protection         (same signature)
+//   FicDecoder (mFicHandler)             decoder/fic_decoder.h:49-58   dabstar::FicDecoder         (same signature)
+//   Backend::process                     backend/backend.h:60          dabstar::Backend            (same signature)
+//   OfdmDecoder                          ofdm/ofdm_decoder.h:63-73     dabstar::OfdmDecoder        (frame granular)
+//   DabProcessor                         main/dab_processor.h:71       dabstar::DabProcessor       (whole recordings)
+//
+// The per-call facades (ViterbiSpiral, Protection, FicDecoder, Backend) launch a batch of one: they exist for drop-in
+// compatibility and for tests; throughput comes from the batch entry points (DabProcessor, *_batch methods).
+// Errors: the ABI's negative codes are turned into std::runtime_error carrying dabstar_last_error().
+#pragma once
+#include "../../include/dabstar_b200.h"
+
+#include <array>
+#include <complex>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace dabstar
+{
+using i16 = int16_t;
+using i32 = int32_t;
+using u8 = uint8_t;
+using u16 = uint16_t;
+using f32 = float;
+using cf32 = std::complex<float>;
+
+class Context
+{
+public:
+  explicit Context(int device = 0, void * cudaStream = nullptr)
+  {
+    if (dabstar_create(&mCtx, device, cudaStream) != DABSTAR_OK) throw std::runtime_error("dabstar_create: no usable CUDA device (no CPU fallback)");
+  }
+  ~Context() { dabstar_destroy(mCtx); }
+  Context(const Context &) = delete;
+  Context & operator=(const Context &) = delete;
+  dabstar_ctx * get() const { return mCtx; }
+  int check(int rc, const char * what) const
+  {
+    if (rc < 0) throw std::runtime_error(std::string(what) + ": " + dabstar_last_error(mCtx));
+    return rc;
+  }
+
+private:
+  dabstar_ctx * mCtx = nullptr;
+};
+
+class FreqInterleaver
+{
+public:
+  explicit FreqInterleaver(Context & c) { c.check(dabstar_freq_interleaver(c.get(), mTable.data()), "dabstar_freq_interleaver"); }
+  i16 map_k_to_fft_bin(const i16 k) const { return mTable[k]; }
+
+private:
+  std::array<i16, DABSTAR_K> mTable{};
+};
+
+class PhaseReference
+{
+public:
+  static constexpr i32 IDX_NOT_FOUND = 100000;
+  explicit PhaseReference(Context & c) : mC(c) { c.check(dabstar_phase_table(c.get(), reinterpret_cast<float *>(mRefTable.data())), "dabstar_phase_table"); }
+  void set_sync_on_strongest_peak(bool s) { mStrongest = s; }
+  // iV: at least 2048 samples (TArrayTn in the reference)
+  i32 correlate_with_phase_ref_and_find_max_peak(const cf32 * iV, const f32 iThreshold)
+  {
+    i32 r = -1;
+    mC.check(dabstar_prs_correlate(mC.get(), reinterpret_cast<const float *>(iV), 1, iThreshold, mStrongest ? 1 : 0, &r, DABSTAR_MEM_HOST), "dabstar_prs_correlate");
+    return r;
+  }
+  i32 estimate_carrier_offset_from_sync_symbol_0(const cf32 * iFft)
+  {
+    i32 r = IDX_NOT_FOUND;
+    mC.check(dabstar_estimate_carrier_offset(mC.get(), reinterpret_cast<const float *>(iFft), 1, &r, DABSTAR_MEM_HOST), "dabstar_estimate_carrier_offset");
+    return r;
+  }
+  std::array<cf32, DABSTAR_TU> mRefTable{};
+
+private:
+  Context & mC;
+  bool mStrongest = false;
+};
+
+class ViterbiSpiral
+{
+public:
+  ViterbiSpiral(Context & c, const i16 iWordlength) : mC(c), mFrameBits(iWordlength) {}
+  // input: 4 * (wordlength + 6) soft bits, output: wordlength bits, one per byte
+  void deconvolve(const i16 * input, u8 * output)
+  {
+    const int64_t zero = 0;
+    const int32_t n = mFrameBits;
+    mC.check(dabstar_viterbi(mC.get(), input, &zero, &n, 1, output, &zero, DABSTAR_MEM_HOST), "dabstar_viterbi");
+  }
+
+private:
+  Context & mC;
+  const i16 mFrameBits;
+};
+
+// EepProtection / UepProtection: shortForm selects the table as BackendDeconvolver does (backend_deconvolver.cpp:32-42)
+class Protection
+{
+public:
+  Protection(Context & c, bool iShortForm, i16 iBitRate, i16 iProtLevel, i16 iCuSize) : mC(c), mShort(iShortForm), mBitRate(iBitRate), mLevel(iProtLevel), mCuSize(iCuSize) {}
+  bool deconvolve(const i16 * iV, i32 /*iSize*/, u8 * oOut)
+  {
+    mC.check(dabstar_protection_deconvolve(mC.get(), mShort ? 1 : 0, mBitRate, mLevel, mCuSize, iV, 1, oOut, DABSTAR_MEM_HOST), "dabstar_protection_deconvolve");
+    return true;
+  }
+
+private:
+  Context & mC;
+  bool mShort;
+  i16 mBitRate, mLevel, mCuSize;
+};
+
+// Consumer of CRC-good FIBs: IFibDecoder::process_FIB (decoder/fib_decoder_if.h:81)
+using FibSink = std::function<void(const std::array<u8, 256> &, u16 ficIdx)>;
+
+class FicDecoder
+{
+public:
+  explicit FicDecoder(Context & c, FibSink sink = nullptr) : mC(c), mSink(std::move(sink)) { mSoft.resize(3 * DABSTAR_SYM_BITS); }
+  void restart() { mRatio = 0; mRunning = true; }
+  void stop() { mRunning = false; }
+  // symbols 1..3 of a frame; the four FICs are decoded when the third symbol has arrived
+  void process_block(const std::vector<i16> & iOfdmSoftBits, const i32 iOfdmSymbIdx)
+  {
+    if (iOfdmSymbIdx < 1 || iOfdmSymbIdx > 3 || iOfdmSoftBits.size() != DABSTAR_SYM_BITS) throw std::invalid_argument("FicDecoder::process_block");
+    memcpy(&mSoft[(size_t)(iOfdmSymbIdx - 1) * DABSTAR_SYM_BITS], iOfdmSoftBits.data(), sizeof(i16) * DABSTAR_SYM_BITS);
+    if (iOfdmSymbIdx != 3 || !mRunning) return;
+    u8 crc[12];
+    i32 ber[8];
+    mC.check(dabstar_fic_decode(mC.get(), mSoft.data(), 3 * DABSTAR_SYM_BITS, 1, mFibBits.data(), crc, ber, DABSTAR_MEM_HOST), "dabstar_fic_decode");
+    for (int fic = 0; fic < 4; fic++)
+    {
+      mFicValid[fic] = true;
+      for (int fib = 0; fib < 3; fib++)
+      {
+        if (crc[3 * fic + fib])
+        {
+          if (mSink)
+          {
+            std::array<u8, 256> one;
+            memcpy(one.data(), &mFibBits[fic * 768 + fib * 256], 256);
+            mSink(one, (u16)fic);
+          }
+          if (mRatio < 10) mRatio++;
+        }
+        else
+        {
+          mFicValid[fic] = false;
+          if (mRatio > 0) mRatio--;
+        }
+      }
+    }
+  }
+  void get_fib_bits(u8 * v, bool * b) const
+  {
+    memcpy(v, mFibBits.data(), mFibBits.size());
+    for (int i = 0; i < 4; i++) b[i] = mFicValid[i];
+  }
+  i32 get_fic_decode_ratio_percent() const { return mRatio * 10; }
+
+private:
+  Context & mC;
+  FibSink mSink;
+  std::vector<i16> mSoft;
+  std::array<u8, 4 * 768> mFibBits{};
+  std::array<bool, 4> mFicValid{};
+  i32 mRatio = 0;
+  bool mRunning = true;
+};
+
+// FrameProcessor::add_to_frame (backend/frame_processor.h:43)
+using FrameSink = std::function<void(const std::vector<u8> &)>;
+
+class Backend
+{
+public:
+  Backend(Context & c, const dabstar_subch & d, FrameSink sink) : mC(c), mD(d), mSink(std::move(sink)), mOut((size_t)24 * d.bit_rate) {}
+  // one CIF fragment (CuSize * 64 soft bits). Keeps the last 17 fragments on the host and runs them as one batch
+  // per emitted logical frame; use DabProcessor for throughput.
+  i32 process(const i16 * iV, const i32 cnt)
+  {
+    if (cnt != mD.size_cu * 64) throw std::invalid_argument("Backend::process");
+    mHist.emplace_back(iV, iV + cnt);
+    if (mHist.size() > 17) mHist.erase(mHist.begin());
+    mSeen++;
+    if (mSeen < 17) return 1;
+    std::vector<i16> cifs((size_t)17 * DABSTAR_CIF_BITS, 0);
+    for (size_t g = 0; g < 17; g++) memcpy(&cifs[g * DABSTAR_CIF_BITS + (size_t)mD.start_cu * 64], mHist[g].data(), sizeof(i16) * (size_t)cnt);
+    mC.check(dabstar_backend_process(mC.get(), &mD, cifs.data(), 17, mOut.data(), DABSTAR_MEM_HOST), "dabstar_backend_process");
+    if (mSink) mSink(mOut);
+    return 1;
+  }
+
+private:
+  Context & mC;
+  dabstar_subch mD;
+  FrameSink mSink;
+  std::vector<u8> mOut;
+  std::vector<std::vector<i16>> mHist;
+  long mSeen = 0;
+};
+
+enum class ESoftBitType { SOFTDEC1 = 0, SOFTDEC2 = 1, SOFTDEC3 = 2 };
+
+// Frame granular: one call = store_reference_symbol_0 + 75 x decode_symbol + store_null_symbol_without_tii.
+class OfdmDecoder
+{
+public:
+  explicit OfdmDecoder(Context & c) : mC(c) { c.check(dabstar_ofdm_state_create(c.get(), &mSt), "dabstar_ofdm_state_create"); }
+  ~OfdmDecoder() { dabstar_ofdm_state_destroy(mC.get(), mSt); }
+  void reset() { mC.check(dabstar_ofdm_state_reset(mC.get(), mSt), "dabstar_ofdm_state_reset"); }
+  void set_soft_bit_gen_type(ESoftBitType t) { mType = t; }
+  // iFft: nFrames x 77 x 2048 spectra; oBits: nFrames x 75 x 3072
+  void decode_frames(const cf32 * iFft, int nFrames, const f32 * iClockErr, const u8 * iNullIsTii, i16 * oBits)
+  {
+    mC.check(dabstar_ofdm_decode_frames(mC.get(), mSt, reinterpret_cast<const float *>(iFft), nFrames, iClockErr, iNullIsTii, (int)mType, oBits, DABSTAR_MEM_HOST),
+             "dabstar_ofdm_decode_frames");
+  }
+
+private:
+  Context & mC;
+  dabstar_ofdm_state * mSt = nullptr;
+  ESoftBitType mType = ESoftBitType::SOFTDEC1;
+};
+
+// Whole recordings: DabProcessor::run() for n recordings in lock step.
+class DabProcessor
+{
+public:
+  DabProcessor(Context & c, int nRecordings, int inputFormat = DABSTAR_FMT_U8, bool scanMode = false, ESoftBitType t = ESoftBitType::SOFTDEC1)
+    : mC(c), mN(nRecordings)
+  {
+    dabstar_decoder_cfg cfg{};
+    cfg.input_format = inputFormat;
+    cfg.soft_bit_type = (int)t;
+    cfg.sync_threshold = 3.0f; // dabradio.cpp:92
+    cfg.scan_mode = scanMode ? 1 : 0;
+    c.check(dabstar_decoder_create(c.get(), &cfg, nRecordings, &mDec), "dabstar_decoder_create");
+  }
+  ~DabProcessor() { dabstar_decoder_destroy(mDec); }
+  void set_audio_channel(int recording, const std::vector<dabstar_subch> & sc)
+  {
+    mC.check(dabstar_decoder_set_subchannels(mDec, recording, sc.data(), (int)sc.size()), "dabstar_decoder_set_subchannels");
+  }
+  // iq[r]: nSamples[r] interleaved IQ pairs in the configured format, host memory
+  void run(const std::vector<const void *> & iq, const std::vector<int64_t> & nSamples)
+  {
+    mC.check(dabstar_decoder_run(mDec, iq.data(), nSamples.data(), DABSTAR_MEM_HOST), "dabstar_decoder_run");
+  }
+  int n_frames(int recording) const { return dabstar_decoder_n_frames(mDec, recording); }
+  std::vector<dabstar_frame_info> frame_info(int recording) const
+  {
+    std::vector<dabstar_frame_info> v((size_t)std::max(0, n_frames(recording)));
+    if (!v.empty()) dabstar_decoder_frame_info(mDec, recording, v.data(), (int)v.size());
+    return v;
+  }
+  // Delivers the decoded FIBs (CRC-good only, as FicDecoder does) and MSC logical frames in stream order.
+  void deliver(int recording, const FibSink & fibSink, const std::function<void(int subChId, const std::vector<u8> &)> & mscSink,
+               const std::vector<dabstar_subch> & sc) const
+  {
+    const int nf = n_frames(recording);
+    std::vector<u8> bits((size_t)nf * 3072), valid((size_t)nf * 4);
+    dabstar_decoder_fib_bits(mDec, recording, bits.data(), valid.data());
+    if (fibSink)
+      for (int f = 0; f < nf; f++)
+        for (int fic = 0; fic < 4; fic++)
+          if (valid[(size_t)4 * f + fic])
+            for (int fib = 0; fib < 3; fib++)
+            {
+              std::array<u8, 256> one;
+              memcpy(one.data(), &bits[(size_t)f * 3072 + fic * 768 + fib * 256], 256);
+              fibSink(one, (u16)fic);
+            }
+    if (mscSink)
+      for (const auto & s : sc)
+      {
+        const int64_t n = dabstar_decoder_msc_size(mDec, recording, s.sub_ch_id);
+        std::vector<u8> all((size_t)n);
+        dabstar_decoder_msc_copy(mDec, recording, s.sub_ch_id, all.data(), n);
+        const size_t fb = (size_t)24 * s.bit_rate;
+        for (size_t o = 0; o + fb <= all.size(); o += fb) mscSink(s.sub_ch_id, std::vector<u8>(all.begin() + o, all.begin() + o + fb));
+      }
+  }
+  double last_ms() const { return dabstar_decoder_last_ms(mDec); }
+  dabstar_decoder * get() const { return mDec; }
+
+private:
+  Context & mC;
+  int mN;
+  dabstar_decoder * mDec = nullptr;
+};
+} // namespace dabstar

@@ -16,10 +16,10 @@ int main()
   for (auto & s : x) s = make_float2(rand() / (float)RAND_MAX - 0.5f, rand() / (float)RAND_MAX - 0.5f);
   static float2 regs[FFT_THREADS][16];
   static FftTwiddles tw[FFT_THREADS];
-  std::vector<float2> smem(FFT_SMEM_F2), out(2048);
+  std::vector<float2> smem(FFT_SMEM_F2), out(2048), tw2(FFT_TW2_F2);
   for (int t = 0; t < FFT_THREADS; t++)
   {
-    fft_load_twiddles(tw[t], w.data(), t);
+    fft_load_twiddles(tw[t], w.data(), tw2.data(), t);
     for (int n1 = 0; n1 < 16; n1++) regs[t][n1] = x[128 * n1 + t];
   }
   for (int t = 0; t < FFT_THREADS; t++) fft_stage1(regs[t], tw[t], smem.data(), t);
@@ -30,6 +30,8 @@ int main()
   for (int t = 0; t < FFT_THREADS; t++)
     for (int h = 0; h < 2; h++)
       for (int j2 = 0; j2 < 8; j2++) { out[fft_out_index(t, h, j2)] = regs[t][8 * h + j2]; hit[fft_out_index(t, h, j2)]++; }
+  std::vector<int> slot(FFT_NAT_F2, 0);
+  for (int k = 0; k < 2048; k++) { if (fft_nat(k) >= FFT_NAT_F2 || slot[fft_nat(k)]++) { printf("FAIL: padded index collision at %d\n", k); return 1; } }
   for (int k = 0; k < 2048; k++) if (hit[k] != 1) { printf("FAIL: output index %d written %d times\n", k, hit[k]); return 1; }
   double max_err = 0, max_mag = 0;
   for (int k = 0; k < 2048; k++)

@@ -198,7 +198,8 @@ def native_arm(args, rank, local_rank, world):
         for _ in range(args.warmup):
             dp.run_ptrs(d_ptrs, ns, api.MEM_DEVICE)
         frames_per_step = frames_done()
-        good_fibs = sum(int(dp.result(r).counters[0]) for r in range(R))
+        cnt = np.sum([dp.result(r).counters for r in range(R)], axis=0)
+        good_fibs = int(cnt[0])
         # ---- timed: inputs resident in HBM
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         clocks = ClockSampler(local_rank)
@@ -286,7 +287,8 @@ def native_arm(args, rank, local_rank, world):
         "config": {"workload": "configs[1] FIC-only decode of a 10k-frame batch", "recordings_per_gpu": R, "frames_per_recording": F,
                    "frames_per_step_all_gpus": total_frames, "input": "u8 IQ 2.048 MS/s", "input_bytes_per_gpu": int(R * n_samples * 2),
                    "l2": "inputs (3.9 GB) and intermediates far exceed the 126 MB L2", "window": args.window,
-                   "fib_crc_pass": good_fibs / max(1.0, 12.0 * frames_per_step), "x_real_time": value / world / (2048000 / T_F)},
+                   "fib_crc_pass": good_fibs / max(1.0, 12.0 * frames_per_step),
+                   "windows_per_recording": float(cnt[4]) / R, "frames_through_heavy_pass": int(cnt[7]), "x_real_time": value / world / (2048000 / T_F)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(R * n_samples * 2), "d2h_bytes_per_step": int(frames_per_step * 3072),
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "stages": stages, "cpu_baseline": cpu,

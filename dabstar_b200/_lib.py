@@ -21,7 +21,7 @@ class SubCh(ctypes.Structure):
 class DecoderCfg(ctypes.Structure):
     _fields_ = [("input_format", ctypes.c_int32), ("soft_bit_type", ctypes.c_int32), ("sync_threshold", ctypes.c_float),
                 ("strongest_peak", ctypes.c_int32), ("scan_mode", ctypes.c_int32), ("keep_soft_bits", ctypes.c_int32),
-                ("max_window", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("max_window", ctypes.c_int32), ("upload_chunk_frames", ctypes.c_int32)]
 
 
 class FrameInfo(ctypes.Structure):

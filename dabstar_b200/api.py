@@ -275,10 +275,11 @@ class DabProcessor:
     """main/dab_processor.h:71 for a batch of recordings (one reference DabProcessor per recording, in lock step)."""
 
     def __init__(self, n_recordings: int = 1, input_format: int = FMT_U8, soft_bit_type: int = 0, sync_threshold: float = 3.0,
-                 strongest_peak: bool = False, scan_mode: bool = False, max_window: int = 0, ctx: Context | None = None):
+                 strongest_peak: bool = False, scan_mode: bool = False, max_window: int = 0, upload_chunk_frames: int = 0,
+                 ctx: Context | None = None):
         self.ctx = ctx or default_context()
         self.n = int(n_recordings)
-        self.cfg = DecoderCfg(input_format, soft_bit_type, sync_threshold, int(strongest_peak), int(scan_mode), 1, max_window, 0)
+        self.cfg = DecoderCfg(input_format, soft_bit_type, sync_threshold, int(strongest_peak), int(scan_mode), 1, max_window, upload_chunk_frames)
         self.h = c_p()
         self.ctx.check(self.ctx.lib.dabstar_decoder_create(self.ctx.h, ctypes.byref(self.cfg), self.n, ctypes.byref(self.h)), "dabstar_decoder_create")
         self.subch: list[list[SubChannel]] = [[] for _ in range(self.n)]

@@ -12,6 +12,7 @@
 #include "tables.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -54,12 +55,40 @@ struct HostBuf
   {
     if (bytes <= cap) return cudaSuccess;
     if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
-    cudaError_t e = cudaHostAlloc(&p, bytes + bytes / 8 + 256, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(&p, bytes + bytes / 8 + 256, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e == cudaSuccess) cap = bytes + bytes / 8 + 256;
     return e;
   }
   template <typename T> T * as() const { return static_cast<T *>(p); }
 };
+
+// Small host->device transfers (descriptors, job lists) go through a pinned, device-mapped arena and a copy KERNEL
+// instead of cudaMemcpyAsync: the H2D copy engine is a FIFO shared by all streams, and while a recording upload is
+// queued on it (dabstar_decoder_run with host input) a 6 KB descriptor copy would wait behind hundreds of megabytes.
+__global__ void k_upload(unsigned char * __restrict__ dst, const unsigned char * __restrict__ src, size_t bytes)
+{
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  if ((((size_t)dst | (size_t)src) & 15) == 0)
+  {
+    const size_t n16 = bytes >> 4;
+    for (size_t i = i0; i < n16; i += stride) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+    for (size_t i = (n16 << 4) + i0; i < bytes; i += stride) dst[i] = src[i];
+  }
+  else for (size_t i = i0; i < bytes; i += stride) dst[i] = src[i];
+}
+
+__global__ void k_ofdm_state_init(OfdmStateDev * __restrict__ st, int count, int full)
+{
+  // full: constructor state (mMeanValue = 1); otherwise reset(), which keeps mMeanValue (ofdm_decoder.cpp:90-101)
+  const int per = (int)(sizeof(OfdmStateDev) / sizeof(float));
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)count * per; i += (size_t)gridDim.x * blockDim.x)
+  {
+    float * f = reinterpret_cast<float *>(st) + i;
+    const bool is_mean_value = (i % per) == offsetof(OfdmStateDev, mean_value) / sizeof(float);
+    if (is_mean_value) { if (full) *f = 1.0f; }
+    else *f = 0.0f;
+  }
+}
 
 struct dabstar_ctx
 {
@@ -76,6 +105,9 @@ struct dabstar_ctx
   DevBuf d_profiles;
   bool profiles_dirty = true;
   DevBuf scratch[8];
+  DevBuf demap_ring;    // exchange ring of the sliced demapper
+  HostBuf arena;        // pinned staging of small uploads; reused after every stream synchronisation
+  size_t arena_off = 0;
 
   int fail(int code, const char * fmt, ...)
   {
@@ -98,6 +130,36 @@ struct dabstar_ctx
 
 namespace
 {
+// cudaStreamSynchronize of the context's stream; every staged upload has been consumed afterwards
+int sync_stream(dabstar_ctx * ctx)
+{
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->arena_off = 0;
+  return 0;
+}
+
+// Asynchronous small host->device copy on the context's stream (see k_upload). `src` may be reused on return.
+int upload(dabstar_ctx * ctx, void * dst, const void * src, size_t bytes)
+{
+  if (bytes == 0) return 0;
+  const size_t need = (bytes + 255) & ~(size_t)255;
+  if (ctx->arena.cap < need || ctx->arena_off + need > ctx->arena.cap)
+  {
+    if (int r = sync_stream(ctx)) return r;
+    if (ctx->arena.cap < need) CK(ctx->arena.reserve(std::max<size_t>(need, (size_t)8 << 20)));
+  }
+  unsigned char * stage = ctx->arena.as<unsigned char>() + ctx->arena_off;
+  memcpy(stage, src, bytes);
+  ctx->arena_off += need;
+  const int grid = (int)std::min<size_t>(64, (bytes / 16 + 255) / 256 + 1);
+  k_upload<<<grid, 256, 0, ctx->stream>>>(static_cast<unsigned char *>(dst), stage, bytes);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+#define UP(dst, src, bytes) do { if (int r_ = upload(ctx, (dst), (src), (bytes))) return r_; } while (0)
+#define SYNC() do { if (int r_ = sync_stream(ctx)) return r_; } while (0)
+
 int get_profile(dabstar_ctx * ctx, int short_form, int bit_rate, int prot_level)
 {
   const long long key = ((long long)(short_form ? 1 : 0) << 40) | ((long long)bit_rate << 8) | (long long)(prot_level & 0xff);
@@ -129,7 +191,7 @@ int sync_profiles(dabstar_ctx * ctx)
   if (!ctx->profiles_dirty) return 0;
   CK(ctx->d_profiles.reserve(sizeof(VitProfile) * std::max<size_t>(ctx->profiles.size(), 64)));
   CK(cudaMemcpyAsync(ctx->d_profiles.p, ctx->profiles.data(), sizeof(VitProfile) * ctx->profiles.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  SYNC();
   ctx->profiles_dirty = false;
   return 0;
 }
@@ -266,7 +328,7 @@ static int run_viterbi_jobs(dabstar_ctx * ctx, const std::vector<VitJob> & jobs,
   if (jobs.empty()) return 0;
   if (int r = sync_profiles(ctx)) return r;
   CK(jobbuf.reserve(sizeof(VitJob) * jobs.size()));
-  CK(cudaMemcpyAsync(jobbuf.p, jobs.data(), sizeof(VitJob) * jobs.size(), cudaMemcpyHostToDevice, ctx->stream));
+  UP(jobbuf.p, jobs.data(), sizeof(VitJob) * jobs.size());
   CK(launch_viterbi(ctx->stream, jobbuf.as<VitJob>(), (int)jobs.size(), ctx->d_profiles.as<VitProfile>(), max_steps, d_soft, d_bits,
                     ctx->tab.prbs, d_crc, d_ber, &ctx->launches));
   return 0;
@@ -429,18 +491,9 @@ struct dabstar_ofdm_state
 
 static int ofdm_state_init(dabstar_ctx * ctx, OfdmStateDev * dev, bool full, int count = 1)
 {
-  // full: constructor state (mMeanValue = 1); otherwise reset() which keeps mMeanValue (ofdm_decoder.cpp:90-101)
-  if (full)
-  {
-    static const float ones[2] = { 1.0f, 1.0f };
-    CK(cudaMemsetAsync(dev, 0, sizeof(OfdmStateDev) * (size_t)count, ctx->stream));
-    for (int i = 0; i < count; i++) CK(cudaMemcpyAsync(&dev[i].mean_value, ones, sizeof(ones), cudaMemcpyHostToDevice, ctx->stream));
-  }
-  else
-  {
-    for (int i = 0; i < count; i++) CK(cudaMemsetAsync(&dev[i], 0, offsetof(OfdmStateDev, mean_value), ctx->stream));
-  }
-  CK(cudaStreamSynchronize(ctx->stream));
+  k_ofdm_state_init<<<std::min(count * 8, 1024), 256, 0, ctx->stream>>>(dev, count, full ? 1 : 0);
+  ctx->launches++;
+  CK(cudaGetLastError());
   return 0;
 }
 
@@ -506,11 +559,13 @@ extern "C" int dabstar_ofdm_decode_frames(dabstar_ctx * ctx, dabstar_ofdm_state 
   FrameDesc * dfd = reinterpret_cast<FrameDesc *>(aux);
   DemapWork * dwk = reinterpret_cast<DemapWork *>(aux + sizeof(FrameDesc) * fd.size());
   uint8_t * dtii = reinterpret_cast<uint8_t *>(dwk + 1);
-  CK(cudaMemcpyAsync(dfd, fd.data(), sizeof(FrameDesc) * fd.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(dwk, &wk, sizeof(wk), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(dtii, tii.data(), tii.size(), cudaMemcpyHostToDevice, ctx->stream));
+  UP(dfd, fd.data(), sizeof(FrameDesc) * fd.size());
+  UP(dwk, &wk, sizeof(wk));
+  UP(dtii, tii.data(), tii.size());
   // X rows of slot f live at f*77 rows; soft slot f at f*FRAME_SOFT: both match the tap's layout.
-  CK(launch_demap(ctx->stream, ctx->tab, dwk, 1, dfd, dtii, ctx->scratch[2].as<float2>(), st->dev, soft_bit_type, (int16_t *)dsoft, &ctx->launches));
+  CK(ctx->demap_ring.reserve(demap_ring_bytes(1)));
+  CK(launch_demap(ctx->stream, ctx->tab, dwk, 1, dfd, dtii, ctx->scratch[2].as<float2>(), st->dev, soft_bit_type, (int16_t *)dsoft,
+                  ctx->demap_ring.as<unsigned long long>(), &ctx->launches));
   return stage_out_end(ctx, dsoft, soft, out_bytes, mem);
 }
 
@@ -574,7 +629,7 @@ struct Recording
   std::vector<dabstar_frame_info> frames;
   std::vector<uint8_t> crc_ok; // 12 per frame
   std::vector<MscOut> msc;
-  long long cnt_good_fibs = 0, cnt_sync_ok = 0, cnt_sync_fail = 0, cnt_windows = 0, cnt_cut = 0;
+  long long cnt_good_fibs = 0, cnt_sync_ok = 0, cnt_sync_fail = 0, cnt_windows = 0, cnt_cut = 0, cnt_heavy = 0;
   // window scratch
   int w_first_desc = 0, w_frames = 0;
   bool w_careful = false;
@@ -601,6 +656,13 @@ struct dabstar_decoder
   long long total_slots = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0;
+  // host-input pipeline: the recordings are uploaded in time-ordered chunks on a second stream while earlier
+  // chunks are being decoded; chunk_ev[c] fires when chunk c of every recording is resident
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_ev;
+  long long chunk_samples = 0;
+  int n_chunks = 0, chunks_done = 0, chunks_waited = -1;
+  long long cnt_rounds = 0;
   // per-stage device time of the last run: CUDA events around every kernel launch on the context's stream
   struct Span { int stage; cudaEvent_t a, b; };
   std::vector<Span> spans;
@@ -638,6 +700,7 @@ extern "C" int dabstar_decoder_create(dabstar_ctx * ctx, const dabstar_decoder_c
   d->recs.resize((size_t)n_recordings);
   CK(cudaEventCreate(&d->ev0));
   CK(cudaEventCreate(&d->ev1));
+  CK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
   *out = d.release();
   return 0;
 }
@@ -649,6 +712,8 @@ extern "C" void dabstar_decoder_destroy(dabstar_decoder * dec)
   if (dec->ev0) cudaEventDestroy(dec->ev0);
   if (dec->ev1) cudaEventDestroy(dec->ev1);
   for (cudaEvent_t e : dec->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : dec->chunk_ev) cudaEventDestroy(e);
+  if (dec->copy_stream) cudaStreamDestroy(dec->copy_stream);
   delete dec;
 }
 
@@ -774,25 +839,83 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
   for (int i = 0; i < 8; i++) { dec->stage_ms[i] = 0; dec->stage_launches[i] = 0; }
   CK(cudaEventRecord(dec->ev0, st));
 
+  static const bool trace = getenv("DABSTAR_TRACE") != nullptr; // per-round progress on stderr (debug aid)
+  const auto t_run0 = std::chrono::steady_clock::now();
+  auto tr = [&](const char * what) {
+    if (trace) fprintf(stderr, "[dabstar]   %-28s t=%.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_run0).count());
+  };
   // ---- inputs
+  // Host input is uploaded in time-ordered chunks on the copy stream; the decode stream waits for the chunk a kernel
+  // reads (need_upto), and windows are sized to what has arrived, so the PCIe transfer overlaps the decode.
   std::vector<RecInput> rin((size_t)n_rec);
-  if (mem == DABSTAR_MEM_HOST)
+  const bool host_in = mem == DABSTAR_MEM_HOST;
+  dec->n_chunks = 0;
+  dec->chunks_done = 0;
+  dec->chunks_waited = -1;
+  dec->cnt_rounds = 0;
+  if (host_in)
   {
-    size_t total = 0;
-    for (int r = 0; r < n_rec; r++) total += ((size_t)n_samples[r] * bps + 255) & ~(size_t)255;
-    CK(dec->d_inputs.reserve(total));
-    size_t off = 0;
-    for (int r = 0; r < n_rec; r++)
+    long long max_n = 0;
+    for (int r = 0; r < n_rec; r++) max_n = std::max<long long>(max_n, n_samples[r]);
+    const size_t dstride = ((size_t)max_n * bps + 255) & ~(size_t)255; // uniform device stride: a chunk of all recordings is one 2D copy
+    CK(dec->d_inputs.reserve(dstride * (size_t)n_rec));
+    for (int r = 0; r < n_rec; r++) rin[r] = { dec->d_inputs.as<char>() + dstride * (size_t)r, (long long)n_samples[r] };
+    // recordings at a constant host stride (rows of one array) and of equal length go as one cudaMemcpy2DAsync per chunk
+    bool uniform = n_rec > 1;
+    const ptrdiff_t hstride = n_rec > 1 ? (const char *)iq[1] - (const char *)iq[0] : 0;
+    for (int r = 0; r < n_rec && uniform; r++)
+      uniform = n_samples[r] == n_samples[0] && (const char *)iq[r] - (const char *)iq[0] == hstride * (ptrdiff_t)r && hstride >= (ptrdiff_t)((size_t)n_samples[0] * bps);
+    long long chunk_frames = (long long)((128LL << 20) / ((long long)n_rec * (long long)bps * T_F));
+    chunk_frames = std::min<long long>(64, std::max<long long>(4, chunk_frames));
+    if (dec->cfg.upload_chunk_frames > 0) chunk_frames = dec->cfg.upload_chunk_frames;
+    dec->chunk_samples = chunk_frames * T_F;
+    dec->n_chunks = (int)std::max<long long>(1, (max_n + dec->chunk_samples - 1) / dec->chunk_samples);
+    while ((int)dec->chunk_ev.size() < dec->n_chunks)
     {
-      char * p = dec->d_inputs.as<char>() + off;
-      CK(cudaMemcpyAsync(p, iq[r], (size_t)n_samples[r] * bps, cudaMemcpyHostToDevice, st));
-      rin[r] = { p, (long long)n_samples[r] };
-      off += ((size_t)n_samples[r] * bps + 255) & ~(size_t)255;
+      cudaEvent_t e;
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      dec->chunk_ev.push_back(e);
+    }
+    CK(cudaStreamWaitEvent(dec->copy_stream, dec->ev0, 0)); // earlier work on the decode stream may still read d_inputs
+    for (int c = 0; c < dec->n_chunks; c++)
+    {
+      const long long lo = (long long)c * dec->chunk_samples;
+      if (uniform)
+      {
+        const long long hi = std::min<long long>(n_samples[0], lo + dec->chunk_samples);
+        if (lo < hi)
+          CK(cudaMemcpy2DAsync((char *)rin[0].iq + (size_t)lo * bps, dstride, (const char *)iq[0] + (size_t)lo * bps, (size_t)hstride, (size_t)(hi - lo) * bps, (size_t)n_rec,
+                               cudaMemcpyHostToDevice, dec->copy_stream));
+      }
+      else
+        for (int r = 0; r < n_rec; r++)
+        {
+          const long long hi = std::min<long long>(n_samples[r], lo + dec->chunk_samples);
+          if (lo < hi)
+            CK(cudaMemcpyAsync((char *)rin[r].iq + (size_t)lo * bps, (const char *)iq[r] + (size_t)lo * bps, (size_t)(hi - lo) * bps, cudaMemcpyHostToDevice, dec->copy_stream));
+        }
+      CK(cudaEventRecord(dec->chunk_ev[c], dec->copy_stream));
     }
   }
   else for (int r = 0; r < n_rec; r++) rin[r] = { iq[r], (long long)n_samples[r] };
+  // the decode stream must not read samples at or beyond `upto` before their chunk has landed
+  auto need_upto = [&](long long upto) -> cudaError_t {
+    if (!host_in) return cudaSuccess;
+    int c = (int)std::min<long long>(dec->n_chunks - 1, std::max<long long>(0, (upto - 1) / dec->chunk_samples));
+    if (c <= dec->chunks_waited) return cudaSuccess;
+    dec->chunks_waited = c;
+    return cudaStreamWaitEvent(st, dec->chunk_ev[c], 0);
+  };
+  // samples known to be resident (polled, never blocks)
+  auto resident_upto = [&]() -> long long {
+    if (!host_in) return (long long)1 << 62;
+    while (dec->chunks_done < dec->n_chunks && cudaEventQuery(dec->chunk_ev[dec->chunks_done]) == cudaSuccess) dec->chunks_done++;
+    (void)cudaGetLastError(); // cudaErrorNotReady from the poll is not an error
+    if (dec->chunks_done >= dec->n_chunks) return (long long)1 << 62;
+    return (long long)dec->chunks_done * dec->chunk_samples;
+  };
   CK(dec->d_recs.reserve(sizeof(RecInput) * (size_t)n_rec));
-  CK(cudaMemcpyAsync(dec->d_recs.p, rin.data(), sizeof(RecInput) * (size_t)n_rec, cudaMemcpyHostToDevice, st));
+  UP(dec->d_recs.p, rin.data(), sizeof(RecInput) * (size_t)n_rec);
   const RecInput * d_rin = dec->d_recs.as<RecInput>();
 
   // ---- per-recording reset (DabProcessor::run prologue, dab_processor.cpp:110-142)
@@ -822,6 +945,7 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
   if (int e = ofdm_state_init(ctx, dec->d_states.as<OfdmStateDev>(), true, n_rec)) return e;
   CK(cudaMemsetAsync(dec->d_crc.p, 0, (size_t)dec->total_slots * 12, st));
 
+  tr("setup done");
   const float thr0 = dec->cfg.sync_threshold;
   // X budget: bound the frames of one round so the window spectrum buffer stays below ~12 GB
   const long long x_frame_bytes = (long long)sizeof(float2) * X_ROWS * K_CARR;
@@ -852,13 +976,19 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
       {
         CK(dec->d_dipw.reserve(sizeof(DipWork) * dw.size()));
         CK(dec->d_dipr.reserve(sizeof(DipResult) * dw.size()));
-        CK(cudaMemcpyAsync(dec->d_dipw.p, dw.data(), sizeof(DipWork) * dw.size(), cudaMemcpyHostToDevice, st));
+        UP(dec->d_dipw.p, dw.data(), sizeof(DipWork) * dw.size());
+        {
+          long long upto = 0; // the search reads at most T_F + T_N + 70 samples (timesyncer.cpp:66-85) plus one scan block
+          for (auto & w : dw) upto = std::max(upto, w.pos + T_F + T_N + 70 + 4096);
+          CK(need_upto(upto));
+        }
         dec->span_begin(ST_DIP);
         CK(launch_dip_search(st, dec->d_dipw.as<DipWork>(), (int)dw.size(), d_rin, fmt, dec->d_dipr.as<DipResult>(), &ctx->launches));
         dec->span_end();
         std::vector<DipResult> dr(dw.size());
         CK(cudaMemcpyAsync(dr.data(), dec->d_dipr.p, sizeof(DipResult) * dw.size(), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        SYNC();
+        tr("time sync done");
         for (size_t i = 0; i < who.size(); i++)
         {
           Recording & R = dec->recs[who[i]];
@@ -911,15 +1041,20 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
         CK(dec->d_desc.reserve(sizeof(FrameDesc) * fd.size() + fd.size() + 64));
         CK(dec->d_start.reserve(sizeof(int) * fd.size()));
         uint8_t * dfirst = dec->d_desc.as<uint8_t>() + sizeof(FrameDesc) * fd.size();
-        CK(cudaMemcpyAsync(dec->d_desc.p, fd.data(), sizeof(FrameDesc) * fd.size(), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(dfirst, first.data(), first.size(), cudaMemcpyHostToDevice, st));
+        UP(dec->d_desc.p, fd.data(), sizeof(FrameDesc) * fd.size());
+        UP(dfirst, first.data(), first.size());
+        {
+          long long upto = 0;
+          for (auto & d : fd) upto = std::max(upto, (long long)d.eval + T_U);
+          CK(need_upto(upto));
+        }
         dec->span_begin(ST_PRS);
         CK(launch_prs_corr(st, ctx->tab, dec->d_desc.as<FrameDesc>(), (int)fd.size(), d_rin, fmt, thr0, 2.0f * thr0, dfirst,
                            dec->cfg.strongest_peak, dec->d_start.as<int>(), &ctx->launches));
         dec->span_end();
         std::vector<int> si(fd.size());
         CK(cudaMemcpyAsync(si.data(), dec->d_start.p, sizeof(int) * fd.size(), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        SYNC();
         for (size_t i = 0; i < who.size(); i++)
         {
           Recording & R = dec->recs[who[i]];
@@ -937,136 +1072,235 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
       }
     }
 
-    // ---- frame layout (positions only; AFC values are filled in after the CP correlation)
-    struct Plan { int rec, n_frames, n_syms_last; };
+    // ---- frame layout. A window is grown in passes: lay out the frames that follow the verified ones assuming the PRS
+    //      peak stays at T_g, run the cheap kernels on them (CP correlation, PRS correlation; coarse AFC for a careful
+    //      frame), resolve the scalar AFC / clock recurrences on the host, and keep the frames up to the first one whose
+    //      measured peak differs from the layout. That frame's peak is now known, so the next pass continues from it.
+    //      The expensive kernels run once per round, over verified frames only.
+    struct Plan
+    {
+      int rec, want;
+      std::vector<FrameCtl> fr; // verified frames of this window
+      bool open;
+      int next_start;           // measured PRS peak of the frame after fr (-2: not measured)
+      int event;                // 1: the frame after the window has no PRS peak (time sync lost)
+      int t_first, t_frames;    // this pass: descriptors of the tail being laid out
+    };
     std::vector<Plan> plans;
     for (int r : win_recs)
     {
       Recording & R = dec->recs[r];
-      const int s0 = R.known_start >= 0 ? R.known_start : T_G;
-      long long p = R.pos;
       int want = R.w_careful ? 1 : (R.force_window > 0 ? R.force_window : dec->cfg.max_window);
       want = (int)std::min<long long>(want, std::max<long long>(1, budget / std::max<size_t>(1, win_recs.size())));
       want = std::min(want, R.slot_cap - R.n_slots);
-      int nf = 0, last_syms = 75;
-      for (int j = 0; j < want; j++)
-      {
-        const int s = j == 0 ? s0 : T_G;
-        if (p + T_U + s > R.n) break;                          // eval window + rest of symbol 0 not available
-        const long long after_sym0 = p + T_U + s;
-        const long long avail = R.n - after_sym0;
-        if (avail >= 75LL * T_S + T_N) { nf++; p = after_sym0 + 75LL * T_S + T_N; continue; }
-        // the recording ends inside this frame: the reference still decodes the symbols it could read
-        last_syms = (int)std::min<long long>(75, avail / T_S);
-        nf++;
-        break;
-      }
-      if (nf == 0) { R.state = RecState::DONE; continue; }
-      plans.push_back({ r, nf, last_syms });
-      budget -= nf;
+      plans.push_back({ r, want, {}, true, R.known_start, 0, 0, 0 });
     }
-    if (plans.empty()) continue;
+    const long long resident = resident_upto();
+    bool first_pass = true;
+    while (true)
+    {
+      // tail layout of the open plans
+      ctl.clear();
+      long long window_end = 0;
+      for (auto & pl : plans)
+      {
+        if (!pl.open) continue;
+        Recording & R = dec->recs[pl.rec];
+        const int s0 = pl.next_start >= 0 ? pl.next_start : T_G;
+        long long p = R.pos;
+        // host input still in flight: stay within what has arrived, but always reach into the chunk being copied
+        const long long lim = host_in ? std::max(resident, (snaps[pl.rec].pos / dec->chunk_samples + 1) * dec->chunk_samples) : ((long long)1 << 62);
+        pl.t_first = (int)ctl.size();
+        pl.t_frames = 0;
+        const int room = pl.want - (int)pl.fr.size();
+        for (int j = 0; j < room; j++)
+        {
+          const int s = j == 0 ? s0 : T_G;
+          if (p + T_U + s > R.n) break;                          // eval window + rest of symbol 0 not available
+          const long long after_sym0 = p + T_U + s;
+          const long long avail = R.n - after_sym0;
+          if (!(pl.fr.empty() && j == 0) && std::min<long long>(R.n, after_sym0 + 75LL * T_S + T_N) > lim) break;
+          FrameCtl fc;
+          memset(&fc, 0, sizeof(fc));
+          fc.desc.rec = pl.rec;
+          fc.desc.eval = p;
+          fc.desc.sym0 = p + s;
+          fc.desc.n_syms = 75;
+          fc.desc.slot = (int)(R.slot_base + R.n_slots + (int)pl.fr.size() + j);
+          fc.desc.xslot = (int)ctl.size();
+          pl.t_frames++;
+          if (avail >= 75LL * T_S + T_N) { ctl.push_back(fc); p = after_sym0 + 75LL * T_S + T_N; continue; }
+          // the recording ends inside this frame: the reference still decodes the symbols it could read
+          fc.desc.n_syms = (int)std::min<long long>(75, avail / T_S);
+          ctl.push_back(fc);
+          p = after_sym0 + (long long)fc.desc.n_syms * T_S;
+          break;
+        }
+        if (pl.t_frames == 0) { pl.open = false; continue; }
+        window_end = std::max(window_end, p);
+      }
+      const int n_tail = (int)ctl.size();
+      if (n_tail == 0) break;
+      CK(need_upto(window_end));
+      std::vector<FrameDesc> fdv((size_t)n_tail);
+      for (int i = 0; i < n_tail; i++) fdv[i] = ctl[i].desc;
+      CK(dec->d_desc.reserve(sizeof(FrameDesc) * (size_t)n_tail + (size_t)n_tail + 64));
+      UP(dec->d_desc.p, fdv.data(), sizeof(FrameDesc) * (size_t)n_tail);
+      FrameDesc * d_fd = dec->d_desc.as<FrameDesc>();
 
-    // descriptors with positions; AFC fields provisional
+      // CP correlation on raw samples (all tail frames) and coarse AFC (first frame of a careful window)
+      CK(dec->d_cp.reserve(sizeof(float2) * (size_t)n_tail));
+      dec->span_begin(ST_CP);
+      CK(launch_cp_corr(st, d_fd, n_tail, d_rin, fmt, dec->d_cp.as<float2>(), &ctx->launches));
+      dec->span_end();
+      std::vector<float2> cp((size_t)n_tail);
+      CK(cudaMemcpyAsync(cp.data(), dec->d_cp.p, sizeof(float2) * (size_t)n_tail, cudaMemcpyDeviceToHost, st));
+      std::vector<int> coarse((size_t)n_tail, 0);
+      if (first_pass)
+      {
+        // coarse AFC needs symbol 0 derotated with the CURRENT f_bb / phase, which are known for the first frame of a window
+        std::vector<FrameDesc> cf;
+        std::vector<int> idx;
+        for (auto & pl : plans)
+        {
+          Recording & R = dec->recs[pl.rec];
+          if (!pl.open || !(R.fic_ratio * 10 < 30)) continue;
+          FrameDesc d = ctl[pl.t_first].desc;
+          d.f_sym0 = (int)roundf(R.f_bb);
+          d.ph_eval = R.osc_phase;
+          cf.push_back(d);
+          idx.push_back(pl.t_first);
+        }
+        if (!cf.empty())
+        {
+          CK(dec->d_work.reserve(sizeof(FrameDesc) * cf.size()));
+          CK(dec->d_coarse.reserve(sizeof(int) * cf.size()));
+          UP(dec->d_work.p, cf.data(), sizeof(FrameDesc) * cf.size());
+          dec->span_begin(ST_COARSE);
+          CK(launch_coarse_afc(st, ctx->tab, dec->d_work.as<FrameDesc>(), (int)cf.size(), d_rin, fmt, dec->d_coarse.as<int>(), &ctx->launches));
+          dec->span_end();
+          std::vector<int> res(cf.size());
+          CK(cudaMemcpyAsync(res.data(), dec->d_coarse.p, sizeof(int) * cf.size(), cudaMemcpyDeviceToHost, st));
+          SYNC();
+          for (size_t i = 0; i < idx.size(); i++) coarse[idx[i]] = res[i];
+        }
+      }
+      SYNC();
+
+      // scalar recurrences (dab_processor.cpp:205-251), with the control state after every frame
+      std::vector<CtlSnapshot> after((size_t)n_tail), before_tail(plans.size());
+      std::vector<uint8_t> first_flags((size_t)n_tail, 0);
+      for (size_t pi = 0; pi < plans.size(); pi++)
+      {
+        Plan & pl = plans[pi];
+        if (!pl.open) continue;
+        Recording & R = dec->recs[pl.rec];
+        before_tail[pi] = take(R);
+        const int s0 = pl.next_start >= 0 ? pl.next_start : T_G;
+        if (pl.fr.empty() && R.first_after_sync) first_flags[pl.t_first] = 1;
+        for (int j = 0; j < pl.t_frames; j++)
+        {
+          const int i = pl.t_first + j;
+          const int slot = ctl[i].desc.slot, n_syms = ctl[i].desc.n_syms;
+          FrameCtl fc;
+          ctl_begin_frame(R, j == 0 ? s0 : T_G, n_syms, fc);
+          const bool ran_coarse = pl.fr.empty() && (j == 0) && (R.fic_ratio * 10 < 30);
+          ctl_after_coarse(R, ran_coarse, coarse[i], fc);
+          ctl_finish_frame(R, cp[i], ran_coarse, coarse[i], fc);
+          fc.desc.rec = pl.rec;
+          fc.desc.slot = slot;
+          fc.desc.xslot = i;
+          ctl[i] = fc;
+          after[i] = take(R);
+        }
+      }
+      for (int i = 0; i < n_tail; i++) fdv[i] = ctl[i].desc;
+      UP(dec->d_desc.p, fdv.data(), sizeof(FrameDesc) * (size_t)n_tail);
+
+      // PRS peak of every tail frame
+      uint8_t * d_first = dec->d_desc.as<uint8_t>() + sizeof(FrameDesc) * (size_t)n_tail;
+      UP(d_first, first_flags.data(), (size_t)n_tail);
+      CK(dec->d_start.reserve(sizeof(int) * (size_t)n_tail));
+      dec->span_begin(ST_PRS);
+      CK(launch_prs_corr(st, ctx->tab, d_fd, n_tail, d_rin, fmt, thr0, 2.0f * thr0, d_first, dec->cfg.strongest_peak, dec->d_start.as<int>(), &ctx->launches));
+      dec->span_end();
+      std::vector<int> start((size_t)n_tail);
+      CK(cudaMemcpyAsync(start.data(), dec->d_start.p, sizeof(int) * (size_t)n_tail, cudaMemcpyDeviceToHost, st));
+      SYNC();
+
+      bool any_open = false;
+      for (size_t pi = 0; pi < plans.size(); pi++)
+      {
+        Plan & pl = plans[pi];
+        if (!pl.open) continue;
+        Recording & R = dec->recs[pl.rec];
+        int valid = 0;
+        for (int j = 0; j < pl.t_frames; j++)
+        {
+          const int expect = j == 0 ? (pl.next_start >= 0 ? pl.next_start : T_G) : T_G;
+          if (!(j == 0 && pl.next_start >= 0) && start[pl.t_first + j] != expect) break;
+          valid++;
+        }
+        for (int j = 0; j < valid; j++) pl.fr.push_back(ctl[pl.t_first + j]);
+        if (valid > 0) pl.next_start = -2;
+        if (valid == pl.t_frames)
+        {
+          // a partial frame ends the recording; otherwise the window may still grow (data that has arrived meanwhile is left to the next round)
+          pl.open = false;
+          continue;
+        }
+        restore(R, valid > 0 ? after[pl.t_first + valid - 1] : before_tail[pi]);
+        const int sj = start[pl.t_first + valid];
+        if (sj < 0) { pl.event = 1; pl.open = false; }
+        else { pl.next_start = sj; any_open = true; R.cnt_cut++; }
+      }
+      first_pass = false;
+      tr("layout pass done");
+      if (!any_open) break;
+    }
+
+    // ---- this round's verified frames
     ctl.clear();
-    for (auto & pl : plans)
     {
-      Recording & R = dec->recs[pl.rec];
-      R.w_first_desc = (int)ctl.size();
-      R.w_frames = pl.n_frames;
-      long long p = R.pos;
-      const int s0 = R.known_start >= 0 ? R.known_start : T_G;
-      for (int j = 0; j < pl.n_frames; j++)
-      {
-        FrameCtl fc;
-        memset(&fc, 0, sizeof(fc));
-        const int s = j == 0 ? s0 : T_G;
-        fc.desc.rec = pl.rec;
-        fc.desc.eval = p;
-        fc.desc.sym0 = p + s;
-        fc.desc.n_syms = (j == pl.n_frames - 1) ? pl.n_syms_last : 75;
-        fc.desc.slot = (int)(R.slot_base + R.n_slots + j);
-        fc.desc.xslot = (int)ctl.size();
-        ctl.push_back(fc);
-        p += T_U + s + 75LL * T_S + T_N;
-      }
-    }
-    const int n_desc = (int)ctl.size();
-    std::vector<FrameDesc> fdv((size_t)n_desc);
-    for (int i = 0; i < n_desc; i++) fdv[i] = ctl[i].desc;
-    CK(dec->d_desc.reserve(sizeof(FrameDesc) * (size_t)n_desc + (size_t)n_desc + 64));
-    CK(cudaMemcpyAsync(dec->d_desc.p, fdv.data(), sizeof(FrameDesc) * (size_t)n_desc, cudaMemcpyHostToDevice, st));
-    FrameDesc * d_fd = dec->d_desc.as<FrameDesc>();
-
-    // ---- CP correlation on raw samples (all frames) and coarse AFC (careful frames), then the scalar recurrences
-    CK(dec->d_cp.reserve(sizeof(float2) * (size_t)n_desc));
-    dec->span_begin(ST_CP);
-    CK(launch_cp_corr(st, d_fd, n_desc, d_rin, fmt, dec->d_cp.as<float2>(), &ctx->launches));
-    dec->span_end();
-    std::vector<float2> cp((size_t)n_desc);
-    CK(cudaMemcpyAsync(cp.data(), dec->d_cp.p, sizeof(float2) * (size_t)n_desc, cudaMemcpyDeviceToHost, st));
-    std::vector<int> coarse((size_t)n_desc, 0);
-    {
-      // coarse AFC needs symbol 0 derotated with the CURRENT f_bb / phase, which are known for the first frame of a window
-      std::vector<FrameDesc> cf;
-      std::vector<int> idx;
+      std::vector<Plan> kept;
       for (auto & pl : plans)
       {
         Recording & R = dec->recs[pl.rec];
-        if (!(R.fic_ratio * 10 < 30)) continue;
-        FrameDesc d = ctl[R.w_first_desc].desc;
-        d.f_sym0 = (int)roundf(R.f_bb);
-        d.ph_eval = R.osc_phase;
-        cf.push_back(d);
-        idx.push_back(R.w_first_desc);
+        if (pl.fr.empty())
+        {
+          if (pl.event == 1)
+          {
+            // no peak: the 2048 samples are consumed and the time sync starts over (dab_processor.cpp:397-401)
+            R.cnt_windows++;
+            R.osc_phase = mod_fs_host((long long)R.osc_phase - (long long)roundf(R.f_bb) * T_U);
+            R.pos += T_U;
+            R.state = RecState::WAIT_SYNC;
+          }
+          else R.state = RecState::DONE; // nothing left to read
+          continue;
+        }
+        R.w_first_desc = (int)ctl.size();
+        R.w_frames = (int)pl.fr.size();
+        for (auto & fc : pl.fr) { fc.desc.xslot = (int)ctl.size(); ctl.push_back(fc); }
+        budget -= (long long)pl.fr.size();
+        kept.push_back(std::move(pl));
       }
-      if (!cf.empty())
-      {
-        CK(dec->d_work.reserve(sizeof(FrameDesc) * cf.size()));
-        CK(dec->d_coarse.reserve(sizeof(int) * cf.size()));
-        CK(cudaMemcpyAsync(dec->d_work.p, cf.data(), sizeof(FrameDesc) * cf.size(), cudaMemcpyHostToDevice, st));
-        dec->span_begin(ST_COARSE);
-        CK(launch_coarse_afc(st, ctx->tab, dec->d_work.as<FrameDesc>(), (int)cf.size(), d_rin, fmt, dec->d_coarse.as<int>(), &ctx->launches));
-        dec->span_end();
-        std::vector<int> res(cf.size());
-        CK(cudaMemcpyAsync(res.data(), dec->d_coarse.p, sizeof(int) * cf.size(), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        for (size_t i = 0; i < idx.size(); i++) coarse[idx[i]] = res[i];
-      }
+      plans.swap(kept);
     }
-    CK(cudaStreamSynchronize(st));
-
-    for (auto & pl : plans)
+    if (plans.empty()) continue;
+    dec->cnt_rounds++;
+    const int n_desc = (int)ctl.size();
+    if (trace)
+      fprintf(stderr, "[dabstar] round %lld t=%.3f ms: %zu recordings, %d frames, chunks resident %d/%d waited %d\n", dec->cnt_rounds,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_run0).count(), plans.size(), n_desc, dec->chunks_done, dec->n_chunks,
+              dec->chunks_waited);
     {
-      Recording & R = dec->recs[pl.rec];
-      const int s0 = R.known_start >= 0 ? R.known_start : T_G;
-      for (int j = 0; j < pl.n_frames; j++)
-      {
-        const int i = R.w_first_desc + j;
-        const int slot = ctl[i].desc.slot, n_syms = ctl[i].desc.n_syms;
-        FrameCtl fc;
-        ctl_begin_frame(R, j == 0 ? s0 : T_G, n_syms, fc);
-        const bool ran_coarse = (j == 0) && (R.fic_ratio * 10 < 30);
-        ctl_after_coarse(R, ran_coarse, coarse[i], fc);
-        ctl_finish_frame(R, cp[i], ran_coarse, coarse[i], fc);
-        fc.desc.rec = pl.rec;
-        fc.desc.slot = slot;
-        fc.desc.xslot = i;
-        ctl[i] = fc;
-      }
+      std::vector<FrameDesc> fdv((size_t)n_desc);
+      for (int i = 0; i < n_desc; i++) fdv[i] = ctl[i].desc;
+      CK(dec->d_desc.reserve(sizeof(FrameDesc) * (size_t)n_desc + 64));
+      UP(dec->d_desc.p, fdv.data(), sizeof(FrameDesc) * (size_t)n_desc);
     }
-    for (int i = 0; i < n_desc; i++) fdv[i] = ctl[i].desc;
-    CK(cudaMemcpyAsync(dec->d_desc.p, fdv.data(), sizeof(FrameDesc) * (size_t)n_desc, cudaMemcpyHostToDevice, st));
-
-    // ---- verification input: PRS peak of every frame whose start index was speculated
-    std::vector<uint8_t> first_flags((size_t)n_desc, 0);
-    for (auto & pl : plans) if (dec->recs[pl.rec].first_after_sync) first_flags[dec->recs[pl.rec].w_first_desc] = 1;
-    uint8_t * d_first = dec->d_desc.as<uint8_t>() + sizeof(FrameDesc) * (size_t)n_desc;
-    CK(cudaMemcpyAsync(d_first, first_flags.data(), (size_t)n_desc, cudaMemcpyHostToDevice, st));
-    CK(dec->d_start.reserve(sizeof(int) * (size_t)n_desc));
-    dec->span_begin(ST_PRS);
-    CK(launch_prs_corr(st, ctx->tab, d_fd, n_desc, d_rin, fmt, thr0, 2.0f * thr0, d_first, dec->cfg.strongest_peak, dec->d_start.as<int>(), &ctx->launches));
-    dec->span_end();
+    FrameDesc * d_fd = dec->d_desc.as<FrameDesc>();
 
     // ---- heavy pass: FFT (+ingest, derotation, de-interleave) -> demap -> FIC
     CK(dec->d_work.reserve(sizeof(DemapWork) * plans.size() + 64));
@@ -1074,19 +1308,23 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
     dec->span_begin(ST_FFT);
     CK(launch_fft_frames(st, ctx->tab, d_fd, n_desc, d_rin, fmt, dec->d_X.as<float2>(), &ctx->launches));
     dec->span_end();
-    CK(cudaMemcpyAsync(dec->d_snap.p, dec->d_states.p, sizeof(OfdmStateDev) * (size_t)n_rec, cudaMemcpyDeviceToDevice, st));
+    // snapshot of the decoder states (copy kernel: a D2D cudaMemcpyAsync may queue behind the recording upload on a copy engine)
+    k_upload<<<64, 256, 0, st>>>(dec->d_snap.as<unsigned char>(), dec->d_states.as<unsigned char>(), sizeof(OfdmStateDev) * (size_t)n_rec);
+    ctx->launches++;
+    CK(cudaGetLastError());
     {
       std::vector<DemapWork> wk;
       for (auto & pl : plans)
       {
         Recording & R = dec->recs[pl.rec];
-        wk.push_back({ R.w_first_desc, pl.n_frames, pl.rec, R.ofdm_reset ? 1 : 0 });
+        wk.push_back({ R.w_first_desc, (int)pl.fr.size(), pl.rec, R.ofdm_reset ? 1 : 0 });
       }
       DemapWork * d_wk = dec->d_work.as<DemapWork>();
-      CK(cudaMemcpyAsync(d_wk, wk.data(), sizeof(DemapWork) * wk.size(), cudaMemcpyHostToDevice, st));
+      UP(d_wk, wk.data(), sizeof(DemapWork) * wk.size());
       dec->span_begin(ST_DEMAP);
+      CK(ctx->demap_ring.reserve(demap_ring_bytes((int)wk.size())));
       CK(launch_demap(st, ctx->tab, d_wk, (int)wk.size(), d_fd, nullptr, dec->d_X.as<float2>(), dec->d_states.as<OfdmStateDev>(), dec->cfg.soft_bit_type,
-                      dec->d_soft.as<int16_t>(), &ctx->launches));
+                      dec->d_soft.as<int16_t>(), ctx->demap_ring.as<unsigned long long>(), &ctx->launches));
       dec->span_end();
     }
     {
@@ -1102,42 +1340,33 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
       dec->span_end();
     }
 
-    // ---- read back the verification data
-    std::vector<int> start((size_t)n_desc);
-    CK(cudaMemcpyAsync(start.data(), dec->d_start.p, sizeof(int) * (size_t)n_desc, cudaMemcpyDeviceToHost, st));
+    tr("heavy pass enqueued");
+    // ---- read back the FIB CRC flags
     std::vector<uint8_t> crc((size_t)n_desc * 12);
     for (auto & pl : plans)
     {
       Recording & R = dec->recs[pl.rec];
       CK(cudaMemcpyAsync(crc.data() + (size_t)R.w_first_desc * 12, dec->d_crc.as<uint8_t>() + (size_t)ctl[R.w_first_desc].desc.slot * 12,
-                         (size_t)pl.n_frames * 12, cudaMemcpyDeviceToHost, st));
+                         (size_t)(int)pl.fr.size() * 12, cudaMemcpyDeviceToHost, st));
     }
-    CK(cudaStreamSynchronize(st));
+    SYNC();
 
-    // ---- verify and accept
+    tr("heavy pass done");
+    // ---- accept: the FIC success ratio must not have fallen below 30 % at a frame start (that frame needs the coarse AFC)
     bool need_restore = false;
     std::vector<int> restore_recs;
     for (auto & pl : plans)
     {
       Recording & R = dec->recs[pl.rec];
       R.cnt_windows++;
+      R.cnt_heavy += (int)pl.fr.size();
       const int base = R.w_first_desc;
-      const int s0 = R.known_start >= 0 ? R.known_start : T_G;
       int ratio = snaps[pl.rec].fic_ratio;
       int valid = 0;
-      int next_start = -2;
-      bool lost = false;
-      std::vector<int> ratio_after((size_t)pl.n_frames), ratio_before((size_t)pl.n_frames);
-      for (int j = 0; j < pl.n_frames; j++)
+      std::vector<int> ratio_after((size_t)(int)pl.fr.size()), ratio_before((size_t)(int)pl.fr.size());
+      for (int j = 0; j < (int)pl.fr.size(); j++)
       {
         const int i = base + j;
-        const int expect = j == 0 ? s0 : T_G;
-        if (!(j == 0 && R.known_start >= 0) && start[i] != expect)
-        {
-          // frame j does not start where the layout assumed
-          if (start[i] < 0) lost = true; else next_start = start[i];
-          break;
-        }
         if (j > 0 && ratio * 10 < 30) break; // this frame needed the coarse AFC: replay it as the first frame of a careful window
         ratio_before[j] = ratio;
         const int n_fic = std::min(4, ctl[i].desc.n_syms * SYM_BITS / FIC_IN);
@@ -1150,10 +1379,10 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
         ratio_after[j] = ratio;
         valid++;
       }
-      if (valid == pl.n_frames)
+      if (valid == (int)pl.fr.size())
       {
         // whole window verified: commit
-        for (int j = 0; j < pl.n_frames; j++)
+        for (int j = 0; j < (int)pl.fr.size(); j++)
         {
           const int i = base + j;
           const bool complete = ctl[i].desc.n_syms == 75;
@@ -1181,33 +1410,35 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
         R.known_start = -2;
         R.spec_ok = true;
         R.first_after_sync = false;
+        if (pl.event == 1 && R.state == RecState::EVAL)
+        {
+          // the frame after this window has no PRS peak (dab_processor.cpp:397-401)
+          R.osc_phase = mod_fs_host((long long)R.osc_phase - (long long)roundf(R.f_bb) * T_U);
+          R.pos += T_U;
+          R.state = RecState::WAIT_SYNC;
+        }
+        else if (pl.next_start >= 0) { R.known_start = pl.next_start; R.spec_ok = false; } // already measured for the next window
       }
       else
       {
-        // roll back this recording and replay the verified prefix (or handle the event at frame 0)
+        // the FIC ratio fell below 30 % inside the window: roll back and replay the prefix that needs no coarse AFC
         R.cnt_cut++;
         restore(R, snaps[pl.rec]);
         restore_recs.push_back(pl.rec);
         need_restore = true;
-        if (valid > 0) { R.force_window = valid; }
-        else
-        {
-          R.force_window = 0;
-          if (lost)
-          {
-            R.osc_phase = mod_fs_host((long long)R.osc_phase - (long long)roundf(R.f_bb) * T_U);
-            R.pos += T_U;
-            R.state = RecState::WAIT_SYNC;
-          }
-          else if (next_start >= 0) { R.known_start = next_start; R.spec_ok = false; }
-          else { R.spec_ok = false; } // FIC ratio dropped below 30 % at the first frame: careful mode follows from the ratio
-        }
+        if (valid > 0) R.force_window = valid;
+        else { R.force_window = 0; R.spec_ok = false; } // careful mode follows from the ratio
       }
     }
     if (need_restore)
     {
       for (int r : restore_recs)
-        CK(cudaMemcpyAsync(dec->d_states.as<OfdmStateDev>() + r, dec->d_snap.as<OfdmStateDev>() + r, sizeof(OfdmStateDev), cudaMemcpyDeviceToDevice, st));
+      {
+        k_upload<<<8, 256, 0, st>>>(reinterpret_cast<unsigned char *>(dec->d_states.as<OfdmStateDev>() + r), reinterpret_cast<unsigned char *>(dec->d_snap.as<OfdmStateDev>() + r),
+                                    sizeof(OfdmStateDev));
+        ctx->launches++;
+        CK(cudaGetLastError());
+      }
     }
   }
 
@@ -1243,12 +1474,13 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
         dec->span_begin(ST_MSC);
         if (int e = run_viterbi_jobs(ctx, kv.second, kv.first, dec->d_soft.as<int16_t>(), dec->d_mscbits.as<uint8_t>(), nullptr, nullptr, dec->d_jobs)) return e;
         dec->span_end();
-        CK(cudaStreamSynchronize(st)); // d_jobs is reused by the next group
+        SYNC(); // d_jobs is reused by the next group
       }
       for (auto & o : outs)
         CK(cudaMemcpyAsync(dec->recs[o.rec].msc[o.ch].bits.data(), dec->d_mscbits.as<uint8_t>() + o.off, (size_t)o.len, cudaMemcpyDeviceToHost, st));
     }
   }
+  tr("rounds done");
   // FIB bits of all accepted frames
   CK(dec->h_fib.reserve((size_t)dec->total_slots * 3072));
   for (int r = 0; r < n_rec; r++)
@@ -1258,7 +1490,8 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
       CK(cudaMemcpyAsync(dec->h_fib.as<uint8_t>() + (size_t)R.slot_base * 3072, dec->d_fib.as<uint8_t>() + (size_t)R.slot_base * 3072, (size_t)R.n_slots * 3072, cudaMemcpyDeviceToHost, st));
   }
   CK(cudaEventRecord(dec->ev1, st));
-  CK(cudaStreamSynchronize(st));
+  SYNC();
+  if (trace) fprintf(stderr, "[dabstar] run done t=%.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_run0).count());
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, dec->ev0, dec->ev1));
   dec->last_ms = ms;
@@ -1326,7 +1559,7 @@ extern "C" int dabstar_decoder_counters(const dabstar_decoder * dec, int recordi
   if (!dec || !out || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
   const Recording & R = dec->recs[recording];
   out[0] = R.cnt_good_fibs; out[1] = R.cnt_sync_ok; out[2] = R.cnt_sync_fail; out[3] = R.pos;
-  out[4] = R.cnt_windows; out[5] = R.cnt_cut; out[6] = R.n_slots; out[7] = R.partial_syms;
+  out[4] = R.cnt_windows; out[5] = R.cnt_cut; out[6] = R.n_slots; out[7] = R.cnt_heavy;
   return 0;
 }
 extern "C" double dabstar_decoder_last_ms(const dabstar_decoder * dec) { return dec ? dec->last_ms : 0.0; }

@@ -57,9 +57,12 @@ cudaError_t launch_fft_batch(cudaStream_t s, const DeviceTables & t, const float
 cudaError_t launch_fft_frames(cudaStream_t s, const DeviceTables & t, const FrameDesc * frames, int n_frames, const RecInput * recs, int fmt,
                               float2 * X, unsigned long long * lc);
 cudaError_t launch_reorder_frames(cudaStream_t s, const DeviceTables & t, const float2 * fft_nat, int n_frames, float2 * X, unsigned long long * lc);
+// ring: device scratch of demap_ring_bytes(n_work) bytes (exchange of the per-symbol sums between the CTAs of a recording).
+// The frames of one DemapWork must occupy consecutive row blocks (xslot) of X.
+size_t demap_ring_bytes(int n_work);
 cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork * work, int n_work, const FrameDesc * frames,
                          const uint8_t * null_is_tii, const float2 * X, OfdmStateDev * states, int soft_bit_type, int16_t * soft,
-                         unsigned long long * lc);
+                         unsigned long long * ring, unsigned long long * lc);
 cudaError_t launch_cp_corr(cudaStream_t s, const FrameDesc * frames, int n_frames, const RecInput * recs, int fmt, float2 * cp, unsigned long long * lc);
 cudaError_t launch_prs_corr(cudaStream_t s, const DeviceTables & t, const FrameDesc * frames, int n_frames, const RecInput * recs, int fmt,
                             float threshold_first, float threshold_rest, const uint8_t * first_flags, int strongest, int * start_index, unsigned long long * lc);

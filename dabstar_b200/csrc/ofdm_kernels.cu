@@ -8,6 +8,7 @@
 #include "fft2048.cuh"
 #include "kernels.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
@@ -899,6 +900,255 @@ k_demap2(const DemapWork * __restrict__ work, const FrameDesc * __restrict__ fra
   if (rank == 0 && tid == 0) sd.mean_value = mean_value;
 }
 
+// ------------------------------------------------------------------------------------------------ DQPSK demapper, sliced version
+// Same arithmetic again, laid out so that nothing in the symbol loop waits:
+//   * a recording's 1536 carriers are split into `slices` CTAs (2 adjacent carriers per thread: one 16-byte load per
+//     spectrum row, one 4-byte store per soft-bit plane), the slice count chosen by the launcher so that the CTAs of
+//     all recordings fill the 148 SMs evenly; the launch is cooperative, so every CTA is resident;
+//   * the only coupling between carriers, mMeanValue (sum of |r| over the PREVIOUS symbol, ofdm_decoder.cpp:256,294),
+//     scales the OUTPUT only. Each warp publishes its partial sum of symbol g as one 64-bit word {g+1, sum} in a ring
+//     in global memory (L2), keeps its unscaled r in a small shared-memory stash, and writes the soft bits of symbol
+//     g - DM3_LAG, whose scale (24 partial sums of symbol g - DM3_LAG - 1, added in a fixed order by every warp for
+//     itself) was published several symbols ago and has been prefetched one iteration earlier: the tag check almost
+//     never spins, and there is no barrier, cluster or designated reducer;
+//   * spectrum rows are prefetched three rows ahead across frame boundaries (a recording's frames occupy consecutive
+//     row blocks of X);
+//   * 6 MUFU per carrier and symbol: rsqrt|X|^2 (shared by two symbols), rcp for the arctangent, sqrt(meanPow),
+//     rsqrt|z|^2, sqrt(|P|/|z|) and one reciprocal of the combined denominator.
+constexpr int DM3_LAG = 3;
+constexpr int DM3_STASH = DM3_LAG + 1;   // stash depth (power of two)
+static_assert((DM3_STASH & (DM3_STASH - 1)) == 0, "stash depth must be a power of two");
+constexpr int DM3_RING = 16;           // > 2 * DM3_LAG + 2: a slot is never overwritten while a slower warp may still read it
+constexpr int DM3_WARPS = K_CARR / 64; // warps per recording
+constexpr int DM3_ROW4 = K_CARR / 2;   // float4 per spectrum row
+
+__device__ __forceinline__ float rcp_ftz(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ float rsqrt_ftz(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ float sqrt_ftz(float a) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+
+// turn_phase_to_first_quadrant(arg(z)) (glob_defs.h:173-182) = arg(z) mod pi/2: the angle of (|x|, |y|), mirrored when
+// x and y have different signs. One reciprocal and an odd minimax polynomial of degree 13 on [0, 1] (|error| < 3.1e-7 rad).
+__device__ __forceinline__ float folded_phase(float x, float y)
+{
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mn = fminf(ax, ay), mx = fmaxf(ax, ay);
+  const float t = mn * rcp_ftz(mx);
+  const float z = t * t;
+  float p = 0.00681177107617259f;
+  p = p * z + -0.033604156225919724f;
+  p = p * z + 0.07962360233068466f;
+  p = p * z + -0.13233338296413422f;
+  p = p * z + 0.19807815551757812f;
+  p = p * z + -0.3331736922264099f;
+  p = p * z + 0.9999961256980896f;
+  const float a = p * t;
+  const bool mirror = (ay > ax) != ((__float_as_int(x) ^ __float_as_int(y)) < 0);
+  return mirror ? PI_2_F - a : a;
+}
+
+template <int SOFT>
+__device__ __forceinline__ float2 dm3_carrier(CarrierState & st, float2 x, float2 ref, float ref_abs, float ref_inv, float clock_term, float & r_abs)
+{
+  constexpr float ALPHA = 0.005f;
+  float2 raw = cmul_conj(x, ref);
+  raw.x *= ref_inv;
+  raw.y *= ref_inv;
+  const float a = -(clock_term + st.integ), a2 = a * a;
+  const float2 rot = make_float2(0.9994032382965087890625f + a2 * (a2 * 3.679168224334716796875e-2f + -0.495580852031707763671875f),
+                                 a * (a2 * -0.16034401953220367431640625f + 0.99903142452239990234375f));
+  const float2 z = cmul(raw, rot);
+  const float dv = folded_phase(z.x, z.y) - PI_4_F;
+  st.integ = fminf(fmaxf(st.integ + 0.2f * ALPHA * dv, -20.0f * RAD_PER_DEG_F), 20.0f * RAD_PER_DEG_F);
+  st.stddev += ALPHA * (dv * dv - st.stddev);
+  const float pw = z.x * z.x + z.y * z.y;
+  st.mean_pow += ALPHA * (pw - st.mean_pow);
+  const float lvl = sqrt_ftz(st.mean_pow);
+  const float axis = lvl * 0.70710678118654752440f;
+  const float dr = fabsf(z.x) - axis, di = fabsf(z.y) - axis;
+  st.mean_sigma += ALPHA * (dr * dr + di * di - st.mean_sigma);
+  float sig = st.mean_pow - st.null_pow;
+  if (sig <= 0.0f) sig = 0.1f;
+  const float inv_z = rsqrt_ftz(pw);
+  float w1;
+  if (SOFT == 2) w1 = ref_abs;
+  else
+  {
+    // 1 / ((nullPow / sig + 0.7) * meanSigma) = sig / ((nullPow + 0.7 sig) * meanSigma)
+    const float g = sig * rcp_ftz((st.null_pow + 0.7f * sig) * st.mean_sigma);
+    if (SOFT == 1) w1 = ref_abs * g;
+    else w1 = sqrt_ftz(ref_abs * inv_z) * lvl * g; // sqrt(|z| |P|) / |z| = sqrt(|P| / |z|)
+  }
+  r_abs = pw * inv_z * w1; // |z| w1, w1 >= 0
+  return make_float2(z.x * w1, z.y * w1);
+}
+
+// low 16 bits of the x86 cvttss2si result (see to_i16): the saturated positive case must read 0, not 0xffff
+__device__ __forceinline__ unsigned i16_bits(float v)
+{
+  const int r = __float2int_rz(v);
+  return r == 0x7fffffff ? 0u : (unsigned)r & 0xffffu;
+}
+
+__device__ __forceinline__ unsigned long long ld_volatile_global_b64(const unsigned long long * p)
+{
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_global_b64(unsigned long long * p, unsigned long long v)
+{
+  asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Sum of |r| over the 1536 carriers of the symbol with tag `tag`: lane l < 24 holds the word of warp l (possibly stale).
+__device__ __forceinline__ float dm3_total(const unsigned long long * slot, unsigned long long w, unsigned tag, int lane)
+{
+  while (__any_sync(0xffffffffu, lane < DM3_WARPS && (unsigned)(w >> 32) != tag)) w = ld_volatile_global_b64(slot + (lane < DM3_WARPS ? lane : 0));
+  float v = lane < DM3_WARPS ? __uint_as_float((unsigned)w) : 0.0f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int SOFT>
+__global__ void __launch_bounds__(DM3_ROW4) k_demap3(const DemapWork * __restrict__ work, const FrameDesc * __restrict__ frames,
+                                                     const uint8_t * __restrict__ null_is_tii, const float2 * __restrict__ X,
+                                                     const int16_t * __restrict__ rel_of_k, OfdmStateDev * __restrict__ states,
+                                                     int16_t * __restrict__ soft, unsigned long long * __restrict__ ring, int slices)
+{
+  extern __shared__ float4 dm3_stash[]; // [DM3_STASH][blockDim.x]: unscaled (r0.x, r0.y, r1.x, r1.y) of the last symbols
+  const int w = blockIdx.x / slices, slice = blockIdx.x - w * slices;
+  const DemapWork wk = work[w];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int t_rec = slice * (int)blockDim.x + tid; // thread index within the recording: carriers 2 t_rec, 2 t_rec + 1
+  const int gw = t_rec >> 5;                       // warp index within the recording
+  const int k0 = 2 * t_rec;
+  unsigned long long * my_ring = ring + (size_t)w * DM3_RING * DM3_WARPS;
+
+  OfdmStateDev & sd = states[wk.state];
+  CarrierState s0, s1;
+  if (wk.reset) { s0 = CarrierState{ 0.0f, 0.0f, 0.0f, 0.0f, 0.0f }; s1 = s0; }
+  else
+  {
+    s0 = CarrierState{ sd.integ[k0], sd.stddev[k0], sd.mean_pow[k0], sd.mean_sigma[k0], sd.null_pow[k0] };
+    s1 = CarrierState{ sd.integ[k0 + 1], sd.stddev[k0 + 1], sd.mean_pow[k0 + 1], sd.mean_sigma[k0 + 1], sd.null_pow[k0 + 1] };
+  }
+  const float mean_value0 = sd.mean_value; // not touched by reset() (ofdm_decoder.cpp:90-101)
+  const float g0 = (float)(K_CARR / 2 - rel_of_k[k0]) / (float)(K_CARR / 2);
+  const float g1 = (float)(K_CARR / 2 - rel_of_k[k0 + 1]) / (float)(K_CARR / 2);
+  constexpr float W2 = SOFT == 0 ? -100.0f : -140.0f;
+
+  const int total_rows = wk.n_frames * X_ROWS;
+  const float4 * rows = reinterpret_cast<const float4 *>(X + (size_t)(total_rows > 0 ? frames[wk.desc_first].xslot : 0) * X_ROWS * K_CARR) + t_rec;
+  float4 cur = total_rows > 0 ? rows[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 n1 = total_rows > 1 ? rows[(size_t)DM3_ROW4] : cur;
+  float4 n2 = total_rows > 2 ? rows[(size_t)2 * DM3_ROW4] : cur;
+
+  float4 ref = cur;
+  float ref_abs0 = 0.f, ref_inv0 = 0.f, ref_abs1 = 0.f, ref_inv1 = 0.f;
+  float c0 = 0.f, c1 = 0.f;
+  int n_syms = 0, row = 0, fi = 0;
+  int out_row0 = 0;
+  bool tii = false;
+  int g = 0;               // symbols decoded so far; tag of symbol g is g + 1
+  int orow[DM3_LAG];       // output rows (slot * 75 + symbol - 1) of the last DM3_LAG symbols, newest first
+#pragma unroll
+  for (int i = 0; i < DM3_LAG; i++) orow[i] = 0;
+  unsigned long long pre = 0; // prefetched ring word of the symbol whose total is needed next
+
+  // soft bits of symbol d (its unscaled values are in the stash, its scale is the total of symbol d - 1)
+  auto emit = [&](int d, int o_row, unsigned long long word) {
+    float w2;
+    if (d == 0) w2 = rcp_ftz(mean_value0) * W2;
+    else w2 = rcp_ftz(dm3_total(my_ring + (size_t)((d - 1) & (DM3_RING - 1)) * DM3_WARPS, word, (unsigned)d, lane)) * (W2 * (float)K_CARR);
+    const float4 r = dm3_stash[(d & (DM3_STASH - 1)) * blockDim.x + tid];
+    unsigned * o = reinterpret_cast<unsigned *>(soft + (size_t)o_row * SYM_BITS);
+    o[t_rec] = i16_bits(r.x * w2) | (i16_bits(r.z * w2) << 16);
+    o[K_CARR / 2 + t_rec] = i16_bits(r.y * w2) | (i16_bits(r.w * w2) << 16);
+  };
+
+  for (int q = 0; q < total_rows; q++)
+  {
+    const float4 nn = q + 3 < total_rows ? rows[(size_t)(q + 3) * DM3_ROW4] : n2;
+    if (row == 0)
+    {
+      const FrameDesc fd = frames[wk.desc_first + fi];
+      const float ce = fd.clock_err / 1024.0f * PI_F;
+      c0 = ce * g0;
+      c1 = ce * g1;
+      n_syms = fd.n_syms;
+      out_row0 = fd.slot * 75;
+      tii = null_is_tii != nullptr && null_is_tii[wk.desc_first + fi];
+    }
+    if (row == 0 || row <= n_syms)
+    {
+      if (row > 0)
+      {
+        const int d = g - DM3_LAG; // symbol whose soft bits are written in this iteration
+        float a0, a1;
+        const float2 r0 = dm3_carrier<SOFT>(s0, make_float2(cur.x, cur.y), make_float2(ref.x, ref.y), ref_abs0, ref_inv0, c0, a0);
+        const float2 r1 = dm3_carrier<SOFT>(s1, make_float2(cur.z, cur.w), make_float2(ref.z, ref.w), ref_abs1, ref_inv1, c1, a1);
+        float part = a0 + a1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0)
+          st_volatile_global_b64(my_ring + (size_t)(g & (DM3_RING - 1)) * DM3_WARPS + gw,
+                                 ((unsigned long long)(unsigned)(g + 1) << 32) | (unsigned long long)__float_as_uint(part));
+        dm3_stash[(g & (DM3_STASH - 1)) * blockDim.x + tid] = make_float4(r0.x, r0.y, r1.x, r1.y);
+        if (d >= 0) emit(d, orow[DM3_LAG - 1], pre);
+        // ring word for the next iteration's output (symbol d + 1 is scaled by the total of symbol d): a whole iteration to land
+        if (d >= 0 && lane < DM3_WARPS) pre = ld_volatile_global_b64(my_ring + (size_t)(d & (DM3_RING - 1)) * DM3_WARPS + lane);
+#pragma unroll
+        for (int i = DM3_LAG - 1; i > 0; i--) orow[i] = orow[i - 1];
+        orow[0] = out_row0 + (row - 1);
+        g++;
+      }
+      // this row is the phase reference of the next symbol
+      ref = cur;
+      const float p0 = cur.x * cur.x + cur.y * cur.y, p1 = cur.z * cur.z + cur.w * cur.w;
+      ref_inv0 = rsqrt_ftz(p0);
+      ref_inv1 = rsqrt_ftz(p1);
+      ref_abs0 = p0 * ref_inv0;
+      ref_abs1 = p1 * ref_inv1;
+    }
+    else if (row == X_ROWS - 1 && n_syms == 75 && !tii)
+    {
+      // store_null_symbol_without_tii (ofdm_decoder.cpp:114-130)
+      constexpr float MIN_POW = (1.0f / 32767.0f) * (1.0f / 32767.0f);
+      s0.null_pow += 0.05f * (cur.x * cur.x + cur.y * cur.y + MIN_POW - s0.null_pow);
+      s1.null_pow += 0.05f * (cur.z * cur.z + cur.w * cur.w + MIN_POW - s1.null_pow);
+    }
+    cur = n1;
+    n1 = n2;
+    n2 = nn;
+    if (++row == X_ROWS) { row = 0; fi++; }
+  }
+  // drain: the last DM3_LAG symbols
+#pragma unroll
+  for (int i = DM3_LAG - 1; i >= 0; i--)
+  {
+    const int d = g - 1 - i;
+    if (d < 0) continue;
+    unsigned long long word = 0;
+    if (d >= 1 && lane < DM3_WARPS) word = ld_volatile_global_b64(my_ring + (size_t)((d - 1) & (DM3_RING - 1)) * DM3_WARPS + lane);
+    emit(d, orow[i], word);
+  }
+  sd.integ[k0] = s0.integ; sd.integ[k0 + 1] = s1.integ;
+  sd.stddev[k0] = s0.stddev; sd.stddev[k0 + 1] = s1.stddev;
+  sd.mean_pow[k0] = s0.mean_pow; sd.mean_pow[k0 + 1] = s1.mean_pow;
+  sd.mean_sigma[k0] = s0.mean_sigma; sd.mean_sigma[k0 + 1] = s1.mean_sigma;
+  sd.null_pow[k0] = s0.null_pow; sd.null_pow[k0 + 1] = s1.null_pow;
+  // mMeanValue after the last symbol (every other thread has read sd.mean_value before it published anything)
+  if (gw == 0 && g > 0)
+  {
+    unsigned long long word = 0;
+    const unsigned long long * slot = my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM3_WARPS;
+    if (lane < DM3_WARPS) word = ld_volatile_global_b64(slot + lane);
+    const float tot = dm3_total(slot, word, (unsigned)g, lane);
+    if (lane == 0) sd.mean_value = tot / (float)K_CARR;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ time sync (S1)
 // TimeSyncer::read_samples_until_end_of_level_drop (timesyncer.cpp:40-90) on top of SampleReader's level IIR
 // (sample_reader.cpp:236, alpha = 1e-5). One CTA per recording; the stream is scanned in blocks of 1024 samples.
@@ -1076,9 +1326,12 @@ cudaError_t launch_reorder_frames(cudaStream_t s, const DeviceTables & t, const 
   return cudaGetLastError();
 }
 
+size_t demap_ring_bytes(int n_work) { return sizeof(unsigned long long) * (size_t)std::max(n_work, 1) * DM3_RING * DM3_WARPS; }
+static size_t demap3_smem_bytes(int threads) { return sizeof(float4) * (size_t)DM3_STASH * (size_t)threads; }
+
 cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork * work, int n_work, const FrameDesc * frames,
                          const uint8_t * null_is_tii, const float2 * X, OfdmStateDev * states, int soft_bit_type, int16_t * soft,
-                         unsigned long long * lc)
+                         unsigned long long * ring, unsigned long long * lc)
 {
   if (n_work <= 0) return cudaSuccess;
   if (soft_bit_type < 0 || soft_bit_type > 2) return cudaErrorInvalidValue;
@@ -1094,14 +1347,58 @@ cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork
     }
     return cudaGetLastError();
   }
-  const int grid = n_work * DM2_CLUSTER;
-  switch (soft_bit_type)
+  static const bool use_v2 = getenv("DABSTAR_DEMAP_V2") != nullptr; // cluster of 4 CTAs per recording, DSMEM exchange (kept for comparison)
+  if (use_v2)
   {
-  case 0: k_demap2<0><<<grid, DM2_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
-  case 1: k_demap2<1><<<grid, DM2_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
-  default: k_demap2<2><<<grid, DM2_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
+    const int grid = n_work * DM2_CLUSTER;
+    switch (soft_bit_type)
+    {
+    case 0: k_demap2<0><<<grid, DM2_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
+    case 1: k_demap2<1><<<grid, DM2_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
+    default: k_demap2<2><<<grid, DM2_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
+    }
+    return cudaGetLastError();
   }
-  return cudaGetLastError();
+  if (ring == nullptr) return cudaErrorInvalidValue;
+  const void * fn = soft_bit_type == 0 ? (const void *)k_demap3<0> : (soft_bit_type == 1 ? (const void *)k_demap3<1> : (const void *)k_demap3<2>);
+  // slices per recording: fill the SMs as evenly as the co-residency limit allows
+  static int n_sm = 0;
+  if (n_sm == 0)
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = N_SM;
+  }
+  const int cand[7] = { 1, 2, 3, 4, 6, 8, 12 };
+  int best_s = 0, best_cap = 0;
+  double best_eff = -1.0;
+  for (int ci = 0; ci < 7; ci++)
+  {
+    const int sl = cand[ci], threads = DM3_ROW4 / sl;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, demap3_smem_bytes(threads)) != cudaSuccess || occ <= 0) continue;
+    const int cap = occ * n_sm;                       // CTAs that can be resident at once
+    const int recs = std::min(n_work, cap / sl);      // recordings per launch
+    if (recs <= 0) continue;
+    const int ctas = recs * sl, per_sm = (ctas + n_sm - 1) / n_sm;
+    const double eff = (double)ctas / ((double)per_sm * n_sm) * (recs == n_work ? 1.0 : 0.999);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_s = sl; best_cap = cap; }
+  }
+  if (best_s == 0) return cudaErrorLaunchOutOfResources;
+  const int threads = DM3_ROW4 / best_s, per_launch = std::max(1, best_cap / best_s);
+  cudaError_t e = cudaMemsetAsync(ring, 0, demap_ring_bytes(n_work), s);
+  for (int first = 0; first < n_work && e == cudaSuccess; first += per_launch)
+  {
+    const int n = std::min(per_launch, n_work - first);
+    const DemapWork * wk = work + first;
+    unsigned long long * rg = ring + (size_t)first * DM3_RING * DM3_WARPS;
+    const int16_t * rel = t.rel_of_k;
+    int sl = best_s;
+    void * args[] = { (void *)&wk, (void *)&frames, (void *)&null_is_tii, (void *)&X, (void *)&rel, (void *)&states, (void *)&soft, (void *)&rg, (void *)&sl };
+    e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)(n * best_s)), dim3((unsigned)threads), args, demap3_smem_bytes(threads), s);
+    if (lc && first > 0) (*lc)++;
+  }
+  return e;
 }
 
 cudaError_t launch_cp_corr(cudaStream_t s, const FrameDesc * frames, int n_frames, const RecInput * recs, int fmt, float2 * cp, unsigned long long * lc)

@@ -145,7 +145,7 @@ typedef struct
   int32_t scan_mode;       /* DabProcessor::set_scan_mode: FIC only */
   int32_t keep_soft_bits;  /* keep 75x3072 int16 per frame for dabstar_decoder_soft_bits */
   int32_t max_window;      /* frames speculated per recording per round (0 = default 256) */
-  int32_t reserved;
+  int32_t upload_chunk_frames; /* host input is uploaded in chunks of this many frames per recording, overlapped with the decode (0 = auto) */
 } dabstar_decoder_cfg;
 
 typedef struct
@@ -176,7 +176,8 @@ int64_t dabstar_decoder_msc_size(const dabstar_decoder * dec, int recording, int
 /* FrameProcessor::add_to_frame payloads (backend/frame_processor.h:43), concatenated, one bit per byte */
 int64_t dabstar_decoder_msc_copy(const dabstar_decoder * dec, int recording, int sub_ch_id, uint8_t * out, int64_t cap);
 /* out[0] good FIBs, [1] time-sync established count, [2] time-sync failures, [3] samples consumed,
- * [4] speculation windows run, [5] windows cut short by verification, [6] frames decoded, [7] reserved */
+ * [4] speculation windows run, [5] windows cut short by verification, [6] frames decoded,
+ * [7] frames sent through the FFT/demap/FIC pass (exceeds [6] by replayed and partial frames) */
 int     dabstar_decoder_counters(const dabstar_decoder * dec, int recording, int64_t out[8]);
 /* Device time of the last dabstar_decoder_run in milliseconds (CUDA events on the context's stream). */
 double  dabstar_decoder_last_ms(const dabstar_decoder * dec);

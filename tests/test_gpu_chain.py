@@ -99,3 +99,52 @@ def test_empty_and_short_inputs(ctx):
     dp = api.DabProcessor(2, input_format=synth.FMT_U8, ctx=ctx)
     dp.run([np.zeros((0, 2), np.uint8), np.full((50000, 2), 127, np.uint8)])
     assert dp.result(0).n_frames == 0 and dp.result(1).n_frames == 0
+
+
+def test_no_replay_on_a_clean_recording(ctx):
+    """A window ends before the first frame whose PRS peak is not where the layout assumed (here: the noise after the last
+    frame), instead of being decoded and replayed: every complete frame goes through the FFT/demap/FIC pass exactly once."""
+    rec = synth.generate(14, seed=13, snr_db=18.0, fmt=synth.FMT_U8)
+    dp = api.DabProcessor(1, input_format=synth.FMT_U8, scan_mode=True, ctx=ctx)
+    dp.run([rec.iq])
+    got = dp.result(0)
+    assert got.n_frames == 14 and got.fic_valid.all()
+    assert got.counters[7] <= got.n_frames + 1, got.counters  # + at most one trailing partial frame
+
+
+def _same_result(a, b):
+    assert a.n_frames == b.n_frames
+    for x, y in zip(a.info, b.info):
+        for f in ("sym0_pos", "start_index", "fbb_sym0", "fbb_data", "fbb_null", "fsync", "phase_cp", "clock_err", "fic_ratio_before", "fic_ratio_after"):
+            assert getattr(x, f) == getattr(y, f), f
+    assert np.array_equal(a.fic_valid, b.fic_valid) and np.array_equal(a.fib_bits, b.fib_bits)
+    assert a.counters[0] == b.counters[0]
+    for k in a.msc:
+        assert np.array_equal(a.msc[k], b.msc[k])
+
+
+def test_chunked_host_upload_matches_device_resident(ctx):
+    """MEM_HOST input is uploaded in chunks on a second stream and decoded as it arrives (windows sized to what is
+    resident); the result must not depend on the chunking or on where the input lives."""
+    import torch
+    recs = [synth.generate(9 + 2 * i, seed=40 + i, snr_db=14.0 + i, cfo_hz=350.0 * i, subch=[SC_3A], fmt=synth.FMT_U8, lead_samples=30000 + 4111 * i)
+            for i in range(4)]
+    results = []
+    for chunk in (0, 2, 5):
+        dp = api.DabProcessor(len(recs), input_format=synth.FMT_U8, upload_chunk_frames=chunk, ctx=ctx)
+        for i in range(len(recs)):
+            dp.set_audio_channel(i, [SC_3A])
+        pinned = [torch.from_numpy(np.ascontiguousarray(r.iq)).pin_memory() for r in recs]
+        dp.run_ptrs([t.data_ptr() for t in pinned], [t.shape[0] for t in pinned], api.MEM_HOST)
+        results.append([dp.result(i) for i in range(len(recs))])
+    dp = api.DabProcessor(len(recs), input_format=synth.FMT_U8, ctx=ctx)
+    for i in range(len(recs)):
+        dp.set_audio_channel(i, [SC_3A])
+    dev = [torch.from_numpy(np.ascontiguousarray(r.iq)).cuda() for r in recs]
+    torch.cuda.synchronize()
+    dp.run_ptrs([t.data_ptr() for t in dev], [t.shape[0] for t in dev], api.MEM_DEVICE)
+    want = [dp.result(i) for i in range(len(recs))]
+    for res in results:
+        for a, b in zip(res, want):
+            _same_result(a, b)
+    assert all(w.n_frames >= 8 for w in want)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarises an ncu report's SASS source page: instruction mix, top stall sites, shared-memory conflict sites.
-Usage: python tools/ncu_hot.py report.ncu-rep [top_n]"""
+Usage: python tools/ncu_hot.py report.ncu-rep [top_n] [kernel_index]   (kernel_index: which kernel of a multi-kernel report)"""
 import collections
 import csv
 import subprocess
@@ -10,8 +10,12 @@ rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 lines = out.splitlines()
-start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
-rows = list(csv.DictReader(lines[start:]))
+kidx = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+starts = [i for i, l in enumerate(lines) if l.startswith('"Address"')]
+start = starts[kidx]
+end = starts[kidx + 1] - 1 if kidx + 1 < len(starts) else len(lines)
+print(lines[start - 1][:160])
+rows = list(csv.DictReader(lines[start:end]))
 tot_inst = sum(int(r["Instructions Executed"]) for r in rows)
 tot_samp = sum(int(r["# Samples"]) for r in rows)
 mix = collections.Counter()

@@ -329,7 +329,7 @@ static int run_viterbi_jobs(dabstar_ctx * ctx, const std::vector<VitJob> & jobs,
   if (int r = sync_profiles(ctx)) return r;
   CK(jobbuf.reserve(sizeof(VitJob) * jobs.size()));
   UP(jobbuf.p, jobs.data(), sizeof(VitJob) * jobs.size());
-  CK(launch_viterbi(ctx->stream, jobbuf.as<VitJob>(), (int)jobs.size(), ctx->d_profiles.as<VitProfile>(), max_steps, d_soft, d_bits,
+  CK(launch_viterbi(ctx->stream, jobbuf.as<VitJob>(), nullptr, (int)jobs.size(), ctx->d_profiles.as<VitProfile>(), max_steps, d_soft, d_bits,
                     ctx->tab.prbs, d_crc, d_ber, &ctx->launches));
   return 0;
 }
@@ -620,6 +620,8 @@ struct Recording
   int known_start = -2;    // PRS peak already measured for the next frame (-2 = not measured)
   bool spec_ok = false;    // the previous frame's peak was T_g: speculate the next ones
   int force_window = 0;    // replay length after a failed verification
+  bool careful_spec = true;// a window that starts with a coarse-AFC frame may speculate that its FIC decodes (reset when that failed)
+  int last_start = -1;     // PRS peak index of the last verified frame (-1: none since the time sync)
   bool ofdm_reset = true;  // OfdmDecoder::reset() pending
   // bookkeeping
   long long slot_base = 0; // first frame slot of this recording in the soft-bit / FIB buffers
@@ -969,6 +971,7 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
         R.first_after_sync = true; // syncThreshold = mcThreshold
         R.known_start = -2;
         R.spec_ok = false;
+        R.last_start = -1;
         dw.push_back({ r, R.pos });
         who.push_back(r);
       }
@@ -1090,7 +1093,7 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
     for (int r : win_recs)
     {
       Recording & R = dec->recs[r];
-      int want = R.w_careful ? 1 : (R.force_window > 0 ? R.force_window : dec->cfg.max_window);
+      int want = R.force_window > 0 ? R.force_window : ((R.w_careful && !R.careful_spec) ? 1 : dec->cfg.max_window);
       want = (int)std::min<long long>(want, std::max<long long>(1, budget / std::max<size_t>(1, win_recs.size())));
       want = std::min(want, R.slot_cap - R.n_slots);
       plans.push_back({ r, want, {}, true, R.known_start, 0, 0, 0 });
@@ -1112,7 +1115,13 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
         const long long lim = host_in ? std::max(resident, (snaps[pl.rec].pos / dec->chunk_samples + 1) * dec->chunk_samples) : ((long long)1 << 62);
         pl.t_first = (int)ctl.size();
         pl.t_frames = 0;
-        const int room = pl.want - (int)pl.fr.size();
+        int room = pl.want - (int)pl.fr.size();
+        {
+          // while the frame timing is still settling (the last peak was not at T_g) only one frame is probed per pass
+          const int prev = pl.fr.empty() ? R.last_start : pl.fr.back().info.start_index;
+          const int cur0 = pl.next_start >= 0 ? pl.next_start : (prev == T_G ? T_G : -1);
+          if (cur0 != T_G) room = std::min(room, 1);
+        }
         for (int j = 0; j < room; j++)
         {
           const int s = j == 0 ? s0 : T_G;
@@ -1245,8 +1254,10 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
         if (valid > 0) pl.next_start = -2;
         if (valid == pl.t_frames)
         {
-          // a partial frame ends the recording; otherwise the window may still grow (data that has arrived meanwhile is left to the next round)
-          pl.open = false;
+          // everything laid out in this pass verified; the next pass closes the plan when there is no room or no data left
+          // (a pass may have been limited to one probe frame)
+          if ((int)pl.fr.size() >= pl.want || pl.fr.back().desc.n_syms < 75) pl.open = false;
+          else any_open = true;
           continue;
         }
         restore(R, valid > 0 ? after[pl.t_first + valid - 1] : before_tail[pi]);
@@ -1328,15 +1339,11 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
       dec->span_end();
     }
     {
-      std::vector<VitJob> jobs;
-      jobs.reserve((size_t)4 * n_desc);
-      for (int i = 0; i < n_desc; i++)
-      {
-        const int n_fic = std::min(4, ctl[i].desc.n_syms * SYM_BITS / FIC_IN);
-        make_fic_jobs(jobs, (long long)ctl[i].desc.slot * FRAME_SOFT, (long long)ctl[i].desc.slot * 3072, 4 * ctl[i].desc.slot, n_fic);
-      }
+      // the 4 FIC blocks of every frame, straight from the descriptors (no job list)
+      if (int e = sync_profiles(ctx)) return e;
       dec->span_begin(ST_FIC);
-      if (int e = run_viterbi_jobs(ctx, jobs, FIC_OUT + 6, dec->d_soft.as<int16_t>(), dec->d_fib.as<uint8_t>(), dec->d_crc.as<uint8_t>(), dec->d_ber.as<int>(), dec->d_jobs)) return e;
+      CK(launch_viterbi(st, nullptr, d_fd, 4 * n_desc, ctx->d_profiles.as<VitProfile>(), FIC_OUT + 6, dec->d_soft.as<int16_t>(), dec->d_fib.as<uint8_t>(),
+                        ctx->tab.prbs, dec->d_crc.as<uint8_t>(), dec->d_ber.as<int>(), &ctx->launches));
       dec->span_end();
     }
 
@@ -1405,6 +1412,8 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
           else { R.partial_syms = ctl[i].desc.n_syms; R.state = RecState::DONE; }
         }
         R.fic_ratio = ratio;
+        R.last_start = pl.fr.back().info.start_index;
+        if (ratio * 10 >= 30) R.careful_spec = true;
         R.ofdm_reset = false;
         R.force_window = 0;
         R.known_start = -2;
@@ -1426,6 +1435,7 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
         restore(R, snaps[pl.rec]);
         restore_recs.push_back(pl.rec);
         need_restore = true;
+        R.careful_spec = false;
         if (valid > 0) R.force_window = valid;
         else { R.force_window = 0; R.spec_ok = false; } // careful mode follows from the ratio
       }

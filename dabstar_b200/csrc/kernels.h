@@ -47,7 +47,8 @@ struct DipResult
 
 // viterbi_kernels.cu
 int viterbi_smem_bytes(int max_steps, int warps);
-cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, int n_jobs, const VitProfile * profiles, int max_steps,
+// fic_frames != nullptr: the jobs are the 4 FIC blocks of each of the n_jobs / 4 frame descriptors (jobs is ignored)
+cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, const FrameDesc * fic_frames, int n_jobs, const VitProfile * profiles, int max_steps,
                            const int16_t * soft, uint8_t * out_bits, const uint8_t * prbs, uint8_t * crc_ok, int * ber,
                            unsigned long long * launch_counter);
 

@@ -23,7 +23,8 @@ __device__ __forceinline__ unsigned parity8(unsigned x)
 }
 
 // shared memory per warp: survivors u64[cap] | symbols u32[cap] | decoded bits u8[cap] | input signs, 1 bit per position (cap/2 bytes)
-__global__ void __launch_bounds__(256) k_viterbi(const VitJob * __restrict__ jobs, int n_jobs, const VitProfile * __restrict__ profiles,
+// fic_frames != nullptr: job j is FIC block (j & 3) of frame descriptor j >> 2 (no job list needed)
+__global__ void __launch_bounds__(256) k_viterbi(const VitJob * __restrict__ jobs, const FrameDesc * __restrict__ fic_frames, int n_jobs, const VitProfile * __restrict__ profiles,
                                                  const int16_t * __restrict__ soft, uint8_t * __restrict__ out_bits,
                                                  const uint8_t * __restrict__ prbs, uint8_t * __restrict__ crc_ok,
                                                  int * __restrict__ ber, int cap)
@@ -43,7 +44,21 @@ __global__ void __launch_bounds__(256) k_viterbi(const VitJob * __restrict__ job
 
   for (int j = blockIdx.x * warps + warp; j < n_jobs; j += gridDim.x * warps)
   {
-    const VitJob job = jobs[j];
+    VitJob job;
+    if (fic_frames != nullptr)
+    {
+      const FrameDesc & fd = fic_frames[j >> 2];
+      const int b = j & 3, n_fic = min(4, fd.n_syms * SYM_BITS / FIC_IN);
+      if (b >= n_fic) continue;
+      job.src = (long long)fd.slot * FRAME_SOFT + (long long)b * FIC_IN;
+      job.out = (long long)fd.slot * (4 * FIC_OUT) + (long long)b * FIC_OUT;
+      job.profile = 0;
+      job.src_mode = VIT_SRC_LINEAR;
+      job.flags = VIT_FLAG_PRBS | VIT_FLAG_FIC;
+      job.cif_first = job.row_mask = job.frag_off = 0;
+      job.aux = 4 * fd.slot + b;
+    }
+    else job = jobs[j];
     const VitProfile pr = profiles[job.profile];
     const int n_bits = pr.n_bits, steps = n_bits + 6;
 
@@ -164,7 +179,7 @@ int viterbi_smem_bytes(int max_steps, int warps)
 }
 
 // Picks warps per CTA so the shared-memory footprint allows several CTAs per SM, launches the jobs.
-cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, int n_jobs, const VitProfile * profiles, int max_steps,
+cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, const FrameDesc * fic_frames, int n_jobs, const VitProfile * profiles, int max_steps,
                            const int16_t * soft, uint8_t * out_bits, const uint8_t * prbs, uint8_t * crc_ok, int * ber,
                            unsigned long long * launch_counter)
 {
@@ -185,7 +200,7 @@ cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, int n_jobs,
   const int ctas_needed = (n_jobs + warps - 1) / warps;
   const int per_sm = max(1, min(16, (227 * 1024) / max(smem, 1)));
   const int grid = min(ctas_needed, N_SM * per_sm);
-  k_viterbi<<<grid, warps * 32, smem, stream>>>(jobs, n_jobs, profiles, soft, out_bits, prbs, crc_ok, ber, cap);
+  k_viterbi<<<grid, warps * 32, smem, stream>>>(jobs, fic_frames, n_jobs, profiles, soft, out_bits, prbs, crc_ok, ber, cap);
   if (launch_counter) (*launch_counter)++;
   return cudaGetLastError();
 }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarises an ncu report's SASS source page: instruction mix, top stall sites, shared-memory conflict sites.
-Usage: python tools/ncu_hot.py report.ncu-rep [top_n] [kernel_index]   (kernel_index: which kernel of a multi-kernel report)"""
+Usage: python tools/ncu_hot.py report.ncu-rep [top_n] [kernel_index]   (kernel_index: section number, or a kernel-name substring)"""
 import collections
 import csv
 import subprocess
@@ -10,8 +10,12 @@ rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 lines = out.splitlines()
-kidx = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 starts = [i for i, l in enumerate(lines) if l.startswith('"Address"')]
+karg = sys.argv[3] if len(sys.argv) > 3 else "0"
+if karg.lstrip("-").isdigit():
+    kidx = int(karg)
+else:  # kernel-name substring: first section whose header names it
+    kidx = next(i for i, st in enumerate(starts) if karg in lines[st - 1])
 start = starts[kidx]
 end = starts[kidx + 1] - 1 if kidx + 1 < len(starts) else len(lines)
 print(lines[start - 1][:160])

@@ -270,6 +270,18 @@ def native_arm(args, rank, local_rank, world):
     roofline = {"kernel": {"ingest_fft": "k_fft_frames", "demap": "k_demap", "cp_corr": "k_cp_corr", "prs_corr": "k_prs_corr"}[dom], "bound": "hbm",
                 "achieved": hbm_stages[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm_stages[dom]["frac_hbm"], "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_frame": BYTES_PER_FRAME[dom]}
+    # achieved / traffic are per launch: algorithmic bytes of one launch over its average CUDA-event duration
+    n_launch = max(1.0, hbm_stages[dom]["launches_per_step"])
+    roofline["algorithmic_bytes_per_launch"] = BYTES_PER_FRAME[dom] * frames_per_step / n_launch
+    roofline["ms_per_launch"] = hbm_stages[dom]["ms_per_step"] / n_launch
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        k = tr["kernels"].get(roofline["kernel"])
+        if k and n_launch == 1.0 and int(tr["frames_per_launch"]) == int(frames_per_step):
+            roofline["traffic"] = k["dram_read_bytes"] + k["dram_write_bytes"]
+            roofline["traffic_source"] = tr["source"] + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, same workload)"
+    except Exception:
+        pass
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -103,9 +103,12 @@ struct dabstar_ctx
   std::vector<VitProfile> profiles; // [0] = FIC
   std::map<long long, int> profile_index;
   DevBuf d_profiles;
+  std::vector<uint32_t> step_tab;   // vit_step_entry of every profile, back to back (VitProfile::tab_off)
+  DevBuf d_step_tab;
   bool profiles_dirty = true;
   DevBuf scratch[8];
   DevBuf demap_ring;    // exchange ring of the sliced demapper
+  DevBuf vit_ws;        // symbols + decision words of the thread-per-code-word Viterbi
   HostBuf arena;        // pinned staging of small uploads; reused after every stream synchronisation
   size_t arena_off = 0;
 
@@ -160,6 +163,24 @@ int upload(dabstar_ctx * ctx, void * dst, const void * src, size_t bytes)
 #define UP(dst, src, bytes) do { if (int r_ = upload(ctx, (dst), (src), (bytes))) return r_; } while (0)
 #define SYNC() do { if (int r_ = sync_stream(ctx)) return r_; } while (0)
 
+// Registers a profile: appends its step table (viterbi.cuh: vit_step_entry_make) and returns its index.
+int push_profile(dabstar_ctx * ctx, VitProfile p)
+{
+  p.tab_off = (int)ctx->step_tab.size();
+  const int steps = p.n_bits + 6;
+  int kept = 0;
+  for (int t = 0; t < steps; t++)
+  {
+    unsigned mask = 0;
+    for (int g = 0; g < 4; g++) if (vit_src_index(p, 4 * t + g) >= 0) mask |= 1u << g;
+    ctx->step_tab.push_back(vit_step_entry_make(kept, mask));
+    kept += __builtin_popcount(mask);
+  }
+  ctx->profiles.push_back(p);
+  ctx->profiles_dirty = true;
+  return (int)ctx->profiles.size() - 1;
+}
+
 int get_profile(dabstar_ctx * ctx, int short_form, int bit_rate, int prot_level)
 {
   const long long key = ((long long)(short_form ? 1 : 0) << 40) | ((long long)bit_rate << 8) | (long long)(prot_level & 0xff);
@@ -167,9 +188,7 @@ int get_profile(dabstar_ctx * ctx, int short_form, int bit_rate, int prot_level)
   if (it != ctx->profile_index.end()) return it->second;
   VitProfile p;
   if (!make_msc_profile(short_form, bit_rate, prot_level, p)) return -1;
-  ctx->profiles.push_back(p);
-  ctx->profiles_dirty = true;
-  const int idx = (int)ctx->profiles.size() - 1;
+  const int idx = push_profile(ctx, p);
   ctx->profile_index[key] = idx;
   return idx;
 }
@@ -179,9 +198,7 @@ int get_identity_profile(dabstar_ctx * ctx, int n_bits)
   const long long key = (2LL << 40) | (long long)n_bits;
   auto it = ctx->profile_index.find(key);
   if (it != ctx->profile_index.end()) return it->second;
-  ctx->profiles.push_back(make_identity_profile(n_bits));
-  ctx->profiles_dirty = true;
-  const int idx = (int)ctx->profiles.size() - 1;
+  const int idx = push_profile(ctx, make_identity_profile(n_bits));
   ctx->profile_index[key] = idx;
   return idx;
 }
@@ -191,6 +208,8 @@ int sync_profiles(dabstar_ctx * ctx)
   if (!ctx->profiles_dirty) return 0;
   CK(ctx->d_profiles.reserve(sizeof(VitProfile) * std::max<size_t>(ctx->profiles.size(), 64)));
   CK(cudaMemcpyAsync(ctx->d_profiles.p, ctx->profiles.data(), sizeof(VitProfile) * ctx->profiles.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx->d_step_tab.reserve(sizeof(uint32_t) * std::max<size_t>(ctx->step_tab.size(), 4096)));
+  CK(cudaMemcpyAsync(ctx->d_step_tab.p, ctx->step_tab.data(), sizeof(uint32_t) * ctx->step_tab.size(), cudaMemcpyHostToDevice, ctx->stream));
   SYNC();
   ctx->profiles_dirty = false;
   return 0;
@@ -269,7 +288,7 @@ extern "C" int dabstar_create(dabstar_ctx ** out, int device, void * stream)
   ok = ok && launch_init_ref_arg(ctx->stream, ctx->tab, &ctx->launches) == cudaSuccess;
   ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
   if (!ok) { dabstar_destroy(ctx.release()); return DABSTAR_E_CUDA; }
-  ctx->profiles.push_back(make_fic_profile());
+  push_profile(ctx.get(), make_fic_profile());
   *out = ctx.release();
   return DABSTAR_OK;
 }
@@ -322,6 +341,14 @@ extern "C" int dabstar_fft2048(dabstar_ctx * ctx, const float * in, float * out,
   return stage_out_end(ctx, dout, out, bytes, mem);
 }
 
+// Workspace of the thread-per-code-word Viterbi: what one launch needs, capped (the launcher then works in chunks).
+static int reserve_viterbi_ws(dabstar_ctx * ctx, int n_jobs, int max_steps)
+{
+  const size_t cap = (size_t)3 << 29; // 1.5 GiB
+  CK(ctx->vit_ws.reserve(std::min(viterbi_ws_bytes(n_jobs, max_steps), cap)));
+  return 0;
+}
+
 static int run_viterbi_jobs(dabstar_ctx * ctx, const std::vector<VitJob> & jobs, int max_steps, const int16_t * d_soft, uint8_t * d_bits,
                             uint8_t * d_crc, int * d_ber, DevBuf & jobbuf)
 {
@@ -329,8 +356,9 @@ static int run_viterbi_jobs(dabstar_ctx * ctx, const std::vector<VitJob> & jobs,
   if (int r = sync_profiles(ctx)) return r;
   CK(jobbuf.reserve(sizeof(VitJob) * jobs.size()));
   UP(jobbuf.p, jobs.data(), sizeof(VitJob) * jobs.size());
+  if (int r = reserve_viterbi_ws(ctx, (int)jobs.size(), max_steps)) return r;
   CK(launch_viterbi(ctx->stream, jobbuf.as<VitJob>(), nullptr, (int)jobs.size(), ctx->d_profiles.as<VitProfile>(), max_steps, d_soft, d_bits,
-                    ctx->tab.prbs, d_crc, d_ber, &ctx->launches));
+                    ctx->tab.prbs, d_crc, d_ber, ctx->d_step_tab.as<unsigned>(), ctx->vit_ws.p, ctx->vit_ws.cap, &ctx->launches));
   return 0;
 }
 
@@ -1341,9 +1369,10 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
     {
       // the 4 FIC blocks of every frame, straight from the descriptors (no job list)
       if (int e = sync_profiles(ctx)) return e;
+      if (int e = reserve_viterbi_ws(ctx, 4 * n_desc, FIC_OUT + 6)) return e;
       dec->span_begin(ST_FIC);
       CK(launch_viterbi(st, nullptr, d_fd, 4 * n_desc, ctx->d_profiles.as<VitProfile>(), FIC_OUT + 6, dec->d_soft.as<int16_t>(), dec->d_fib.as<uint8_t>(),
-                        ctx->tab.prbs, dec->d_crc.as<uint8_t>(), dec->d_ber.as<int>(), &ctx->launches));
+                        ctx->tab.prbs, dec->d_crc.as<uint8_t>(), dec->d_ber.as<int>(), ctx->d_step_tab.as<unsigned>(), ctx->vit_ws.p, ctx->vit_ws.cap, &ctx->launches));
       dec->span_end();
     }
 

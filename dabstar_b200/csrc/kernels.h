@@ -47,10 +47,13 @@ struct DipResult
 
 // viterbi_kernels.cu
 int viterbi_smem_bytes(int max_steps, int warps);
-// fic_frames != nullptr: the jobs are the 4 FIC blocks of each of the n_jobs / 4 frame descriptors (jobs is ignored)
+// fic_frames != nullptr: the jobs are the 4 FIC blocks of each of the n_jobs / 4 frame descriptors (jobs is ignored).
+// step_tab: device copy of the profiles' step tables (VitProfile::tab_off). ws / ws_bytes: device workspace of the thread-per-code-word path (viterbi_ws_bytes() for one launch; a smaller
+// workspace makes the launcher work in chunks, none selects the warp-per-code-word kernel).
+size_t viterbi_ws_bytes(int n_jobs, int max_steps);
 cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, const FrameDesc * fic_frames, int n_jobs, const VitProfile * profiles, int max_steps,
                            const int16_t * soft, uint8_t * out_bits, const uint8_t * prbs, uint8_t * crc_ok, int * ber,
-                           unsigned long long * launch_counter);
+                           const unsigned * step_tab, void * ws, size_t ws_bytes, unsigned long long * launch_counter);
 
 // ofdm_kernels.cu
 cudaError_t launch_init_ref_arg(cudaStream_t s, const DeviceTables & t, unsigned long long * lc);

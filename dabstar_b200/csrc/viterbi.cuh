@@ -32,7 +32,13 @@ struct VitProfile
   int seg_kept[VIT_MAX_SEG];   // kept soft bits before segment s
   unsigned seg_mask[VIT_MAX_SEG]; // puncturing vector of the segment, bit j = position j mod 32 kept
   int n_kept;                  // total kept soft bits
+  int tab_off;                 // first entry of this profile in the step table (vit_step_entry), one entry per trellis step
 };
+
+// Step-table entry of trellis step t: kept soft bits before Viterbi-input position 4t (bits 0..27) and which of the
+// positions 4t..4t+3 are kept (bits 28..31). Built on the host when a profile is registered; the batched kernels read
+// it instead of searching the puncturing segments per position.
+__host__ __device__ inline unsigned vit_step_entry_make(int kept_before, unsigned mask4) { return (unsigned)kept_before | (mask4 << 28); }
 
 enum { VIT_SRC_LINEAR = 0, VIT_SRC_TIME_DEINTERLEAVE = 1 };
 enum { VIT_FLAG_PRBS = 1, VIT_FLAG_FIC = 2 };

@@ -1,7 +1,10 @@
 // viterbi_kernels.cu — warp-per-code-word Viterbi with fused depuncture / time de-interleave gather,
 // energy dispersal, FIB CRC and BER re-encode. See viterbi.cuh for the algorithm and reference citations.
 #include "viterbi.cuh"
+#include "viterbi_tpc.cuh"
 #include "kernels.h"
+
+#include <cstdlib>
 
 namespace dab
 {
@@ -20,6 +23,46 @@ __device__ __forceinline__ unsigned clamp_sym(int v)
 __device__ __forceinline__ unsigned parity8(unsigned x)
 {
   return __popc(x) & 1u;
+}
+
+// Job j of a launch: either an entry of the job list, or (fic_frames != nullptr) FIC block (j & 3) of frame descriptor
+// j >> 2. Returns false when the frame ends before that FIC block.
+__device__ __forceinline__ bool load_job(const VitJob * __restrict__ jobs, const FrameDesc * __restrict__ fic_frames, int j, VitJob & job)
+{
+  if (fic_frames != nullptr)
+  {
+    const FrameDesc & fd = fic_frames[j >> 2];
+    const int b = j & 3, n_fic = min(4, fd.n_syms * SYM_BITS / FIC_IN);
+    if (b >= n_fic) return false;
+    job.src = (long long)fd.slot * FRAME_SOFT + (long long)b * FIC_IN;
+    job.out = (long long)fd.slot * (4 * FIC_OUT) + (long long)b * FIC_OUT;
+    job.profile = 0;
+    job.src_mode = VIT_SRC_LINEAR;
+    job.flags = VIT_FLAG_PRBS | VIT_FLAG_FIC;
+    job.cif_first = job.row_mask = job.frag_off = 0;
+    job.aux = 4 * fd.slot + b;
+    job.pad = 0;
+  }
+  else job = jobs[j];
+  return true;
+}
+
+// Raw soft input of kept bit idx of a job (0 where the time de-interleaver memory is still empty).
+__device__ __forceinline__ int job_soft(const VitJob & job, const int16_t * __restrict__ soft, int idx)
+{
+  if (job.src_mode == VIT_SRC_LINEAR) return soft[job.src + idx];
+  const int m = time_map(idx);
+  if (!((job.row_mask >> m) & 1)) return 0;
+  return soft[job.src + cif_offset(job.cif_first + m) + job.frag_off + idx];
+}
+
+// Eight consecutive energy-dispersal bits as a byte, first bit most significant: bit 7 - j = prbs[i + j] (i a multiple of 8)
+__device__ __forceinline__ unsigned prbs_byte_msb(const uint8_t * __restrict__ prbs, int i)
+{
+  const uint2 w = *reinterpret_cast<const uint2 *>(prbs + i); // one 0/1 byte per bit
+  // bytes b0..b3 of a word times 0x08040201: the top byte of the product is 8 b0 + 4 b1 + 2 b2 + b3 (no carries reach it)
+  const unsigned n0 = ((w.x * 0x08040201u) >> 24) & 0x0fu, n1 = ((w.y * 0x08040201u) >> 24) & 0x0fu;
+  return (n0 << 4) | n1;
 }
 
 // shared memory per warp: survivors u64[cap] | symbols u32[cap] | decoded bits u8[cap] | input signs, 1 bit per position (cap/2 bytes)
@@ -45,20 +88,7 @@ __global__ void __launch_bounds__(256) k_viterbi(const VitJob * __restrict__ job
   for (int j = blockIdx.x * warps + warp; j < n_jobs; j += gridDim.x * warps)
   {
     VitJob job;
-    if (fic_frames != nullptr)
-    {
-      const FrameDesc & fd = fic_frames[j >> 2];
-      const int b = j & 3, n_fic = min(4, fd.n_syms * SYM_BITS / FIC_IN);
-      if (b >= n_fic) continue;
-      job.src = (long long)fd.slot * FRAME_SOFT + (long long)b * FIC_IN;
-      job.out = (long long)fd.slot * (4 * FIC_OUT) + (long long)b * FIC_OUT;
-      job.profile = 0;
-      job.src_mode = VIT_SRC_LINEAR;
-      job.flags = VIT_FLAG_PRBS | VIT_FLAG_FIC;
-      job.cif_first = job.row_mask = job.frag_off = 0;
-      job.aux = 4 * fd.slot + b;
-    }
-    else job = jobs[j];
+    if (!load_job(jobs, fic_frames, j, job)) continue;
     const VitProfile pr = profiles[job.profile];
     const int n_bits = pr.n_bits, steps = n_bits + 6;
 
@@ -72,12 +102,7 @@ __global__ void __launch_bounds__(256) k_viterbi(const VitJob * __restrict__ job
         const int idx = vit_src_index(pr, p);
         if (idx >= 0)
         {
-          if (job.src_mode == VIT_SRC_LINEAR) v = soft[job.src + idx];
-          else
-          {
-            const int m = time_map(idx);
-            if ((job.row_mask >> m) & 1) v = soft[job.src + cif_offset(job.cif_first + m) + job.frag_off + idx];
-          }
+          v = job_soft(job, soft, idx);
         }
         syms8[p] = (unsigned char)clamp_sym(v);
       }
@@ -170,6 +195,235 @@ __global__ void __launch_bounds__(256) k_viterbi(const VitJob * __restrict__ job
     __syncwarp();
   }
 }
+
+// ================================================================================================ thread per code word
+// Three kernels (algorithm and reference citations: viterbi_tpc.cuh):
+//   k_vit_gather : depuncture (+ 16-CIF time de-interleave) + clamp; writes the 4 symbols of every trellis step as one
+//                  32-bit word, [step][code word], through a shared-memory transpose (coalesced on both sides)
+//   k_vit_tpc    : forward pass (decision words to [step][code word]) and chain back, energy dispersal fused into the
+//                  packed byte store
+//   k_fic_post   : FIB CRC and BER re-encode of FIC blocks (warp per block)
+constexpr int GATHER_STEPS = 64; // trellis steps per CTA tile
+
+__global__ void __launch_bounds__(256) k_vit_gather(const VitJob * __restrict__ jobs, const FrameDesc * __restrict__ fic_frames, int job_first, int n_jobs,
+                                                    const VitProfile * __restrict__ profiles, const unsigned * __restrict__ step_tab,
+                                                    const int16_t * __restrict__ soft, unsigned * __restrict__ sym, int stride, int rows)
+{
+  __shared__ unsigned tile[32][GATHER_STEPS + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int jb = blockIdx.x * 32, t0 = blockIdx.y * GATHER_STEPS;
+#pragma unroll 1
+  for (int c = 0; c < 4; c++)
+  {
+    const int jl = jb + 4 * warp + c;
+    VitJob job;
+    const bool valid = jl < n_jobs && load_job(jobs, fic_frames, job_first + jl, job);
+    int steps = 0;
+    const unsigned * tab = nullptr;
+    if (valid) { const VitProfile * pr = profiles + job.profile; steps = pr->n_bits + 6; tab = step_tab + pr->tab_off; }
+#pragma unroll
+    for (int h = 0; h < GATHER_STEPS / 32; h++)
+    {
+      const int t = t0 + lane + 32 * h;
+      unsigned word = 0x7f7f7f7fu; // erasures
+      if (t < steps)
+      {
+        const unsigned e = tab[t];
+        int k = (int)(e & 0x0fffffffu), v[4];
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+        {
+          const bool keep = (e >> (28 + g)) & 1u;
+          v[g] = keep ? job_soft(job, soft, k) : 0;
+          k += keep;
+        }
+        word = tpc_pack_syms(v);
+      }
+      tile[4 * warp + c][lane + 32 * h] = word;
+    }
+  }
+  __syncthreads();
+  for (int r = warp; r < GATHER_STEPS; r += 8)
+  {
+    const int t = t0 + r;
+    if (t < rows) sym[(size_t)t * stride + jb + lane] = tile[lane][r];
+  }
+}
+
+__global__ void __launch_bounds__(32) k_vit_tpc(const VitJob * __restrict__ jobs, const FrameDesc * __restrict__ fic_frames, int job_first, int n_jobs,
+                                                const VitProfile * __restrict__ profiles, const unsigned * __restrict__ sym,
+                                                unsigned long long * __restrict__ surv, int stride, uint8_t * __restrict__ out_bits,
+                                                const uint8_t * __restrict__ prbs)
+{
+  __shared__ unsigned char pos_lut[5][64]; // bit of the decision word that holds the decision of state y, per step type
+  for (int i = threadIdx.x; i < 5 * 64; i += 32) pos_lut[i >> 6][i & 63] = (unsigned char)tpc_decision_bit(i >> 6, i & 63);
+  __syncwarp();
+  const int jl = blockIdx.x * 32 + threadIdx.x;
+  if (jl >= n_jobs) return;
+  VitJob job;
+  if (!load_job(jobs, fic_frames, job_first + jl, job)) return;
+  const int n_bits = profiles[job.profile].n_bits, steps = n_bits + 6;
+  const unsigned * sp = sym + jl;
+  unsigned long long * vp = surv + jl;
+
+  // ---- forward pass, five steps per iteration; the symbols of the next TWO iterations are in flight meanwhile
+  // (rows are padded to a multiple of 5, loads beyond the code word are clamped to its last block of rows)
+  unsigned S[32];
+  tpc_init(S);
+  const int last0 = (steps - 1) / 5 * 5;
+  unsigned cur[5], nx1[5];
+#pragma unroll
+  for (int i = 0; i < 5; i++) { cur[i] = sp[(size_t)i * stride]; nx1[i] = sp[(size_t)(min(5, last0) + i) * stride]; }
+#pragma unroll 1
+  for (int t0 = 0; t0 < steps; t0 += 5)
+  {
+    unsigned nx2[5];
+    const int tn = min(t0 + 10, last0);
+#pragma unroll
+    for (int i = 0; i < 5; i++) nx2[i] = sp[(size_t)(tn + i) * stride];
+    unsigned long long dec[5];
+    tpc_five_steps(S, cur, dec, (t0 + 5) % TPC_RENORM == 0);
+#pragma unroll
+    for (int i = 0; i < 5; i++)
+    {
+      if (t0 + i < steps) vp[(size_t)(t0 + i) * stride] = dec[i];
+      cur[i] = nx1[i];
+      nx1[i] = nx2[i];
+    }
+  }
+
+  // ---- chain back from state 0; decoded bit i is the decision read at step i + 6 (viterbi_scalar.h:84-93).
+  // The decision words of the next 8 steps are loaded while the current 8 are walked (the addresses do not depend on
+  // the state, only the walk itself is serial).
+  unsigned y = 0;
+  const bool scramble = (job.flags & VIT_FLAG_PRBS) != 0;
+  uint8_t * out = out_bits + job.out;
+  if ((((unsigned long long)(uintptr_t)out | (unsigned long long)n_bits) & 7) == 0 && n_bits >= 8)
+  {
+    unsigned long long w[8], wn[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) w[q] = vp[(size_t)(n_bits - 8 + 6 + q) * stride];
+    int ty7 = (n_bits + 5) % 5; // type of step i + 13 for i = n_bits - 8
+#pragma unroll 1
+    for (int i = n_bits - 8; i >= 0; i -= 8)
+    {
+      const int ip = i >= 8 ? i - 8 : 0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) wn[q] = vp[(size_t)(ip + 6 + q) * stride];
+      unsigned lo = 0, hi = 0;
+      int ty = ty7;
+#pragma unroll
+      for (int q = 7; q >= 0; q--)
+      {
+        const unsigned k = tpc_traceback_step(w[q], pos_lut[ty][y], y);
+        if (q >= 4) hi |= k << (8 * (q - 4)); else lo |= k << (8 * q);
+        ty = ty == 0 ? 4 : ty - 1;
+      }
+      ty7 = ty;
+      if (scramble) { const uint2 pw = *reinterpret_cast<const uint2 *>(prbs + i); lo ^= pw.x; hi ^= pw.y; }
+      *reinterpret_cast<uint2 *>(out + i) = make_uint2(lo, hi);
+#pragma unroll
+      for (int q = 0; q < 8; q++) w[q] = wn[q];
+    }
+  }
+  else
+  {
+    for (int i = n_bits - 1; i >= 0; i--)
+    {
+      const unsigned k = tpc_traceback_step(vp[(size_t)(i + 6) * stride], pos_lut[(i + 6) % 5][y], y);
+      out[i] = (uint8_t)(k ^ (scramble ? prbs[i] : 0));
+    }
+  }
+}
+
+// FIB CRC (backend/crc.cpp:98-132) and BER re-encode (viterbi_spiral.cpp:128-164) of decoded FIC blocks. One warp per
+// block: the decoded bits are packed into 32-bit words with ballots; every lane then re-encodes the trellis steps
+// lane, lane + 32, ... from an 8-bit window of that vector (the generators bit-reversed, so no reversal of the window)
+// and compares with the sign of the kept soft inputs; the three FIB CRCs run byte-wise from a table in shared memory.
+constexpr int POST_WARPS = 8;
+constexpr int POST_WORDS = 40; // >= 1 (zero word in front) + ceil((max FIC-like n_bits + 6) / 32) + 1
+
+__global__ void __launch_bounds__(POST_WARPS * 32) k_fic_post(const VitJob * __restrict__ jobs, const FrameDesc * __restrict__ fic_frames, int job_first, int n_jobs,
+                                                              const VitProfile * __restrict__ profiles, const unsigned * __restrict__ step_tab,
+                                                              const int16_t * __restrict__ soft, const uint8_t * __restrict__ out_bits,
+                                                              const uint8_t * __restrict__ prbs, uint8_t * __restrict__ crc_ok, int * __restrict__ ber)
+{
+  __shared__ unsigned short crc_tab[256];
+  __shared__ unsigned vec[POST_WARPS][POST_WORDS];
+  {
+    // CRC-16/CCITT table, polynomial 0x1021, most significant bit first
+    unsigned r = threadIdx.x << 8;
+#pragma unroll
+    for (int b = 0; b < 8; b++) r = (r & 0x8000u) ? ((r << 1) ^ 0x1021u) : (r << 1);
+    crc_tab[threadIdx.x] = (unsigned short)r;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int jl = blockIdx.x * POST_WARPS + warp;
+  if (jl >= n_jobs) return;
+  VitJob job;
+  if (!load_job(jobs, fic_frames, job_first + jl, job)) return;
+  if (!(job.flags & VIT_FLAG_FIC)) return;
+  const VitProfile & pr = profiles[job.profile];
+  const int n_bits = pr.n_bits, steps = n_bits + 6;
+  if (steps + 64 > 32 * POST_WORDS) return; // not a FIC-sized block
+  const uint8_t * ob = out_bits + job.out;
+  const bool scr = (job.flags & VIT_FLAG_PRBS) != 0;
+  unsigned * v = vec[warp];
+  // v[1 + c] bit b = decoded bit 32 c + b before energy dispersal; zero outside [0, n_bits)
+  const int n_words = (steps + 31) / 32 + 2;
+  for (int c = 0; c + 1 < n_words; c++)
+  {
+    const int i = 32 * c + lane;
+    const unsigned bit = i < n_bits ? (unsigned)(ob[i] ^ (scr ? prbs[i] : 0)) : 0u;
+    const unsigned wv = __ballot_sync(FULL, bit & 1u);
+    if (lane == 0) v[1 + c] = wv;
+  }
+  if (lane == 0) v[0] = 0;
+  __syncwarp();
+  if (ber != nullptr)
+  {
+    // window bit j = decoded bit i - 7 + j; the encoder register has bit q = decoded bit i - q, so generator g sees
+    // parity(window & reverse8(g)): reverse8 of {109, 79, 83, 109} = {0xB6, 0xF2, 0xCA, 0xB6}
+    const unsigned * tab = step_tab + pr.tab_off;
+    int errors = 0;
+    for (int i = lane; i < steps; i += 32)
+    {
+      const int p = i - 7 + 32; // bit position of the window start in v[]
+      const unsigned long long two = (unsigned long long)v[p >> 5] | ((unsigned long long)v[(p >> 5) + 1] << 32);
+      const unsigned win = (unsigned)(two >> (p & 31)) & 0xffu;
+      const unsigned e = tab[i];
+      int k = (int)(e & 0x0fffffffu);
+      const unsigned rp[4] = { 0xB6u, 0xF2u, 0xCAu, 0xB6u };
+#pragma unroll
+      for (int g = 0; g < 4; g++)
+      {
+        if (!((e >> (28 + g)) & 1u)) continue;
+        const unsigned hard = job_soft(job, soft, k) > 0;
+        k++;
+        errors += hard != (__popc(win & rp[g]) & 1u);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) errors += __shfl_xor_sync(FULL, errors, o);
+    if (lane == 0) { ber[2 * job.aux] = pr.n_kept; ber[2 * job.aux + 1] = errors; }
+  }
+  if (crc_ok != nullptr && lane < 3 && 256 * (lane + 1) <= n_bits)
+  {
+    // FIB `lane`: 32 bytes, first bit = most significant; all-ones start, the last two bytes inverted, pass <=> 0
+    unsigned reg = 0xffffu;
+    for (int b = 0; b < 32; b++)
+    {
+      const int i = 256 * lane + 8 * b; // multiple of 8: the byte does not straddle words
+      unsigned byte = (v[1 + (i >> 5)] >> (i & 31)) & 0xffu;
+      byte = __brev(byte) >> 24;                                   // decoded bit i -> bit 7
+      byte ^= prbs_byte_msb(prbs, i);                              // the CRC runs on the descrambled bits
+      if (b >= 30) byte ^= 0xffu;
+      reg = ((reg << 8) & 0xffffu) ^ crc_tab[((reg >> 8) ^ byte) & 0xffu];
+    }
+    crc_ok[3 * job.aux + lane] = reg == 0;
+  }
+}
 } // namespace
 
 int viterbi_smem_bytes(int max_steps, int warps)
@@ -178,12 +432,19 @@ int viterbi_smem_bytes(int max_steps, int warps)
   return cap * VIT_SMEM_PER_STEP * warps;
 }
 
-// Picks warps per CTA so the shared-memory footprint allows several CTAs per SM, launches the jobs.
-cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, const FrameDesc * fic_frames, int n_jobs, const VitProfile * profiles, int max_steps,
-                           const int16_t * soft, uint8_t * out_bits, const uint8_t * prbs, uint8_t * crc_ok, int * ber,
-                           unsigned long long * launch_counter)
+// Workspace of the thread-per-code-word path for one launch of n_jobs code words of at most max_steps trellis steps:
+// symbols u32[rows][stride] + decision words u64[rows][stride], rows = max_steps rounded up to 5, stride = jobs rounded up to 32.
+static inline int tpc_rows(int max_steps) { return (max_steps + 4) / 5 * 5; }
+size_t viterbi_ws_bytes(int n_jobs, int max_steps)
 {
-  if (n_jobs <= 0) return cudaSuccess;
+  const size_t stride = ((size_t)n_jobs + 31) & ~(size_t)31;
+  return (size_t)tpc_rows(max_steps) * stride * 12 + 256;
+}
+
+static cudaError_t launch_viterbi_warp(cudaStream_t stream, const VitJob * jobs, const FrameDesc * fic_frames, int n_jobs, const VitProfile * profiles, int max_steps,
+                                       const int16_t * soft, uint8_t * out_bits, const uint8_t * prbs, uint8_t * crc_ok, int * ber,
+                                       unsigned long long * launch_counter)
+{
   const int cap = (max_steps + 15) & ~15;
   const int per_warp = cap * VIT_SMEM_PER_STEP;
   int warps = 8;
@@ -203,5 +464,46 @@ cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, const Frame
   k_viterbi<<<grid, warps * 32, smem, stream>>>(jobs, fic_frames, n_jobs, profiles, soft, out_bits, prbs, crc_ok, ber, cap);
   if (launch_counter) (*launch_counter)++;
   return cudaGetLastError();
+}
+
+// Batches of at least VIT_TPC_MIN_JOBS code words take the thread-per-code-word path (in chunks that fit the workspace);
+// small batches (single frames while a recording acquires lock, stage taps on a handful of code words) keep one warp
+// per code word, which has the shorter latency. Both produce the reference's bits exactly.
+constexpr int VIT_TPC_MIN_JOBS = 2048;
+
+cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, const FrameDesc * fic_frames, int n_jobs, const VitProfile * profiles, int max_steps,
+                           const int16_t * soft, uint8_t * out_bits, const uint8_t * prbs, uint8_t * crc_ok, int * ber,
+                           const unsigned * step_tab, void * ws, size_t ws_bytes, unsigned long long * launch_counter)
+{
+  if (n_jobs <= 0) return cudaSuccess;
+  const int rows = tpc_rows(max_steps);
+  const size_t per_job = (size_t)rows * 12;
+  size_t fit = ws != nullptr && ws_bytes > 256 ? (ws_bytes - 256) / per_job : 0;
+  fit &= ~(size_t)31;
+  // DABSTAR_VITERBI_TPC_MIN overrides the batch size from which the thread-per-code-word path is taken (read per launch
+  // so the parity tests can run every case through both kernels)
+  int min_jobs = VIT_TPC_MIN_JOBS;
+  if (const char * ev = getenv("DABSTAR_VITERBI_TPC_MIN")) min_jobs = atoi(ev);
+  if (n_jobs < min_jobs || fit < 32 || step_tab == nullptr)
+    return launch_viterbi_warp(stream, jobs, fic_frames, n_jobs, profiles, max_steps, soft, out_bits, prbs, crc_ok, ber, launch_counter);
+  const int chunk = (int)min((size_t)((n_jobs + 31) & ~31), fit);
+  unsigned * sym = static_cast<unsigned *>(ws);
+  unsigned long long * surv = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(ws) + (((size_t)rows * chunk * 4 + 255) & ~(size_t)255));
+  for (int first = 0; first < n_jobs; first += chunk)
+  {
+    const int n = min(chunk, n_jobs - first);
+    const int groups = (n + 31) / 32;
+    k_vit_gather<<<dim3((unsigned)groups, (unsigned)((rows + GATHER_STEPS - 1) / GATHER_STEPS)), 256, 0, stream>>>(jobs, fic_frames, first, n, profiles, step_tab, soft, sym, chunk, rows);
+    k_vit_tpc<<<groups, 32, 0, stream>>>(jobs, fic_frames, first, n, profiles, sym, surv, chunk, out_bits, prbs);
+    if (launch_counter) (*launch_counter) += 2;
+    if (crc_ok != nullptr || ber != nullptr)
+    {
+      k_fic_post<<<(n + POST_WARPS - 1) / POST_WARPS, POST_WARPS * 32, 0, stream>>>(jobs, fic_frames, first, n, profiles, step_tab, soft, out_bits, prbs, crc_ok, ber);
+      if (launch_counter) (*launch_counter)++;
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 } // namespace dab

@@ -29,3 +29,16 @@ def refo():
 def ctx():
     from dabstar_b200 import api
     return api.default_context()
+
+
+@pytest.fixture(params=["warp_per_codeword", "thread_per_codeword"])
+def viterbi_path(request):
+    """Runs a test through both Viterbi kernels: the launcher picks the thread-per-code-word path from
+    DABSTAR_VITERBI_TPC_MIN code words per launch on (default 2048; read per launch, viterbi_kernels.cu)."""
+    old = os.environ.get("DABSTAR_VITERBI_TPC_MIN")
+    os.environ["DABSTAR_VITERBI_TPC_MIN"] = "1" if request.param == "thread_per_codeword" else "1000000000"
+    yield request.param
+    if old is None:
+        del os.environ["DABSTAR_VITERBI_TPC_MIN"]
+    else:
+        os.environ["DABSTAR_VITERBI_TPC_MIN"] = old

@@ -4,6 +4,7 @@
 //   VIT <frame_bits> <seed> <fnv1a of decoded bits>      for inputs read from stdin (binary int16)
 #include "tables.h"
 #include "viterbi.cuh"
+#include "viterbi_tpc.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -57,6 +58,32 @@ static void viterbi_emulated(const VitProfile & pr, const int16_t * soft, uint8_
   for (int e = steps - 1; e >= 6; e--) out[e - 6] = (uint8_t)vit_traceback_step(surv[e], r);
 }
 
+// The thread-per-code-word kernel (viterbi_tpc.cuh): the same host/device functions, one "thread".
+static void viterbi_tpc_emulated(const VitProfile & pr, const int16_t * soft, uint8_t * out)
+{
+  const int steps = pr.n_bits + 6, rows = (steps + 4) / 5 * 5;
+  std::vector<unsigned> syms(rows, 0);
+  for (int t = 0; t < steps; t++)
+  {
+    int v[4];
+    for (int g = 0; g < 4; g++) { const int idx = vit_src_index(pr, 4 * t + g); v[g] = idx >= 0 ? soft[idx] : 0; }
+    syms[t] = tpc_pack_syms(v);
+  }
+  std::vector<unsigned long long> surv(rows);
+  unsigned S[32];
+  tpc_init(S);
+  for (int t0 = 0; t0 < steps; t0 += 5)
+  {
+    const unsigned sy[5] = { syms[t0], syms[t0 + 1], syms[t0 + 2], syms[t0 + 3], syms[t0 + 4] };
+    unsigned long long dec[5];
+    tpc_five_steps(S, sy, dec, (t0 + 5) % TPC_RENORM == 0);
+    for (int i = 0; i < 5; i++) surv[t0 + i] = dec[i];
+    for (int i = 0; i < 32; i++) if ((S[i] & 0xffffu) > 60000u || (S[i] >> 16) > 60000u) { fprintf(stderr, "metric overflow\n"); exit(3); }
+  }
+  unsigned y = 0;
+  for (int e = steps - 1; e >= 6; e--) out[e - 6] = (uint8_t)tpc_traceback_step(surv[e], (unsigned)tpc_decision_bit(e % 5, (int)y), y);
+}
+
 int main(int argc, char ** argv)
 {
   if (argc >= 2 && !strcmp(argv[1], "addr"))
@@ -84,8 +111,9 @@ int main(int argc, char ** argv)
     printf("ADDR 9 0 0 %d %u\n", n, fnv(addr.data(), sizeof(int32_t) * n));
     return 0;
   }
-  if (argc >= 4 && !strcmp(argv[1], "vit"))
+  if (argc >= 4 && (!strcmp(argv[1], "vit") || !strcmp(argv[1], "vit2")))
   {
+    const bool tpc = !strcmp(argv[1], "vit2");
     const int n_bits = atoi(argv[2]), count = atoi(argv[3]);
     const VitProfile pr = make_identity_profile(n_bits);
     std::vector<int16_t> soft(4 * (n_bits + 6));
@@ -93,7 +121,8 @@ int main(int argc, char ** argv)
     for (int c = 0; c < count; c++)
     {
       if (fread(soft.data(), sizeof(int16_t), soft.size(), stdin) != soft.size()) return 2;
-      viterbi_emulated(pr, soft.data(), bits.data());
+      if (tpc) viterbi_tpc_emulated(pr, soft.data(), bits.data());
+      else viterbi_emulated(pr, soft.data(), bits.data());
       printf("VIT %d %d %u\n", n_bits, c, fnv(bits.data(), bits.size()));
     }
     return 0;

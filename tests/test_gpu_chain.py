@@ -37,7 +37,7 @@ def _compare(want, dp, got, subch, soft_frames=3):
 
 
 @pytest.mark.parametrize("fmt", [synth.FMT_U8, synth.FMT_I16, synth.FMT_CF32])
-def test_config1_one_dabplus_subchannel(ctx, oracle, fmt):
+def test_config1_one_dabplus_subchannel(ctx, oracle, fmt, viterbi_path):
     rec = synth.generate(22, seed=1, snr_db=20.0, subch=[SC_3A], fmt=fmt)
     want, dp, got = _run_both(oracle, ctx, rec, [SC_3A], fmt)
     assert want.n_frames == 22 and want.fic_valid.all()
@@ -55,7 +55,7 @@ def test_carrier_offset_acquisition(ctx, oracle, cfo):
     _compare(want, dp, got, [SC_3A], soft_frames=2)
 
 
-def test_mixed_eep_uep_ensemble(ctx, oracle):
+def test_mixed_eep_uep_ensemble(ctx, oracle, viterbi_path):
     subch = [synth.SubChannel(1, 0, 108, 0, 0, 72), synth.SubChannel(2, 108, 42, 0, 5, 64), synth.SubChannel(4, 150, 96, 1, 3, 128),
              synth.SubChannel(9, 246, 64, 1, 5, 128, start_frame=2), synth.SubChannel(11, 310, 36, 0, 3, 72), synth.SubChannel(12, 346, 140, 1, 1, 128)]
     rec = synth.generate(9, seed=7, snr_db=14.0, subch=subch, fmt=synth.FMT_U8)

@@ -31,7 +31,7 @@ def test_fft_bins(ctx, oracle):
 
 
 @pytest.mark.parametrize("frame_bits,sigma", [(768, 0.0), (768, 60.0), (768, 120.0), (768, 200.0), (1728, 150.0), (192, 100.0), (3072, 180.0), (9216, 150.0)])
-def test_viterbi_bit_exact(ctx, oracle, frame_bits, sigma):
+def test_viterbi_bit_exact(ctx, oracle, frame_bits, sigma, viterbi_path):
     n = 24 if frame_bits < 4000 else 3
     _, soft = helpers.random_codewords(n, frame_bits, sigma, seed=frame_bits + int(sigma))
     got = api.ViterbiSpiral(frame_bits, ctx).deconvolve(soft)
@@ -39,7 +39,7 @@ def test_viterbi_bit_exact(ctx, oracle, frame_bits, sigma):
     assert np.array_equal(got, want), f"{(got != want).sum()} differing bits"
 
 
-def test_viterbi_saturating_inputs_and_ties(ctx, oracle):
+def test_viterbi_saturating_inputs_and_ties(ctx, oracle, viterbi_path):
     # clamp to [0,255] after +127 (viterbi_scalar.h:34-40); all-zero input = all erasures = every comparison ties
     rng = np.random.default_rng(5)
     soft = rng.integers(-32768, 32767, (6, 4 * (768 + 6))).astype(np.int16)
@@ -51,8 +51,8 @@ def test_viterbi_saturating_inputs_and_ties(ctx, oracle):
     assert np.array_equal(got, want)
 
 
-def test_viterbi_ragged_batch(ctx, oracle):
-    sizes = [192, 768, 1536, 768, 2304, 192]
+def test_viterbi_ragged_batch(ctx, oracle, viterbi_path):
+    sizes = [192, 768, 1536, 768, 2304, 192, 190, 331, 5]  # incl. lengths that are not a multiple of 4 (byte-wise output path)
     softs = [helpers.random_codewords(1, n, 140.0, seed=100 + i)[1][0] for i, n in enumerate(sizes)]
     got = api.viterbi_ragged(ctx, softs, sizes)
     for g, s, n in zip(got, softs, sizes):
@@ -61,7 +61,7 @@ def test_viterbi_ragged_batch(ctx, oracle):
 
 
 @pytest.mark.parametrize("sf,lvl,br,size_cu", helpers.ALL_PROFILES)
-def test_protection_deconvolve(ctx, oracle, sf, lvl, br, size_cu):
+def test_protection_deconvolve(ctx, oracle, sf, lvl, br, size_cu, viterbi_path):
     rng = np.random.default_rng(br + lvl)
     n = 6
     soft = rng.integers(-200, 200, (n, size_cu * 64)).astype(np.int16)
@@ -70,7 +70,7 @@ def test_protection_deconvolve(ctx, oracle, sf, lvl, br, size_cu):
     assert np.array_equal(got, want)
 
 
-def test_fic_decode(ctx, oracle):
+def test_fic_decode(ctx, oracle, viterbi_path):
     rng = np.random.default_rng(9)
     n = 12
     fic_addr = oracle.fic_addresses()
@@ -104,7 +104,7 @@ def test_fic_decode(ctx, oracle):
 
 
 @pytest.mark.parametrize("sf,lvl,br,size_cu", [helpers.EEP_A_72[2], helpers.EEP_B_64[1], helpers.UEP_128[2]])
-def test_backend_time_deinterleave(ctx, oracle, sf, lvl, br, size_cu):
+def test_backend_time_deinterleave(ctx, oracle, sf, lvl, br, size_cu, viterbi_path):
     rng = np.random.default_rng(br)
     n_cifs = 22
     cifs = rng.integers(-150, 150, (n_cifs, 55296)).astype(np.int16)
@@ -114,6 +114,25 @@ def test_backend_time_deinterleave(ctx, oracle, sf, lvl, br, size_cu):
     assert first == 16 and got.shape == want.shape
     assert np.array_equal(got, want)
     assert api.Backend(synth.SubChannel(1, start_cu, size_cu, sf, lvl, br), ctx).process(cifs[:10]).shape[0] == 0  # fewer than 17 CIFs: nothing
+
+
+def test_viterbi_large_batch(ctx, oracle):
+    """Default dispatch: >= 2048 code words per launch take the thread-per-code-word kernels (gather, decode)."""
+    n = 2304
+    sig = np.array([0.0, 80.0, 150.0, 220.0, 400.0])
+    rng = np.random.default_rng(77)
+    bits = rng.integers(0, 2, (n, 768), dtype=np.uint8)
+    coded = np.stack([helpers.conv_encode(b) for b in bits[:64]])
+    coded = coded[rng.integers(0, 64, n)]  # 64 distinct code words, independent noise per row
+    soft = np.clip(np.trunc((2.0 * coded - 1.0) * 127.0 + rng.normal(size=coded.shape) * sig[np.arange(n) % 5, None]), -32768, 32767).astype(np.int16)
+    soft[7] = 0
+    soft[8] = 32767
+    soft[9] = -32768
+    launches = ctx.kernel_launches
+    got = api.ViterbiSpiral(768, ctx).deconvolve(soft)
+    assert ctx.kernel_launches - launches >= 2  # gather + decode (one warp-per-code-word launch would count 1)
+    want = np.stack([oracle.viterbi(s, 768) for s in soft])
+    assert np.array_equal(got, want), f"{(got != want).sum()} differing bits"
 
 
 def _frames_fft(oracle, n_frames, snr_db, seed, cfo=0.0):

@@ -61,12 +61,13 @@ def test_puncturing_tables_match_oracle(host_logic, oracle):
     assert seen >= 64 + 48
 
 
-@pytest.mark.parametrize("frame_bits,sigma", [(768, 0.0), (768, 150.0), (768, 400.0), (192, 200.0), (1728, 170.0)])
-def test_warp_viterbi_algorithm_emulated(host_logic, oracle, frame_bits, sigma):
+@pytest.mark.parametrize("mode", ["vit", "vit2"])  # warp per code word (viterbi.cuh), thread per code word (viterbi_tpc.cuh)
+@pytest.mark.parametrize("frame_bits,sigma", [(768, 0.0), (768, 150.0), (768, 400.0), (192, 200.0), (1728, 170.0), (9216, 300.0)])
+def test_warp_viterbi_algorithm_emulated(host_logic, oracle, frame_bits, sigma, mode):
     n = 6
     _, soft = helpers.random_codewords(n, frame_bits, sigma, seed=frame_bits + int(sigma))
     soft[-1] = 0  # all erasures: every comparison ties, path 0 must win
-    out = subprocess.run([host_logic, "vit", str(frame_bits), str(n)], input=soft.tobytes(), capture_output=True, check=True).stdout.decode()
+    out = subprocess.run([host_logic, mode, str(frame_bits), str(n)], input=soft.tobytes(), capture_output=True, check=True).stdout.decode()
     lines = out.splitlines()
     assert len(lines) == n
     for i, line in enumerate(lines):

@@ -31,11 +31,16 @@ class FrameInfo(ctypes.Structure):
                 ("fic_ratio_after", ctypes.c_int32), ("fic_valid", ctypes.c_uint8 * 4)]
 
 
+class SampleFormatC(ctypes.Structure):
+    _fields_ = [("container", ctypes.c_int32), ("bits_per_channel", ctypes.c_int32), ("msb_first", ctypes.c_int32), ("iq_order", ctypes.c_int32)]
+
+
 # every symbol include/dabstar_b200.h declares: (name, restype)
 EXPORTS = [
     ("dabstar_create", ctypes.c_int), ("dabstar_destroy", None), ("dabstar_last_error", ctypes.c_char_p),
     ("dabstar_abi_version", ctypes.c_int), ("dabstar_kernel_launches", ctypes.c_uint64),
     ("dabstar_freq_interleaver", ctypes.c_int), ("dabstar_phase_table", ctypes.c_int), ("dabstar_protection_addresses", ctypes.c_int),
+    ("dabstar_ingest_convert", ctypes.c_int), ("dabstar_sample_format_bytes", ctypes.c_int),
     ("dabstar_fft2048", ctypes.c_int), ("dabstar_viterbi", ctypes.c_int), ("dabstar_protection_deconvolve", ctypes.c_int),
     ("dabstar_fic_decode", ctypes.c_int), ("dabstar_backend_process", ctypes.c_int),
     ("dabstar_ofdm_state_create", ctypes.c_int), ("dabstar_ofdm_state_destroy", None), ("dabstar_ofdm_state_reset", ctypes.c_int),

@@ -30,6 +30,34 @@ def _ptr(a: np.ndarray) -> c_p:
     return a.ctypes.data_as(c_p)
 
 
+CONTAINERS = {"int8": 0, "uint8": 1, "int16": 2, "int24": 3, "int32": 4, "float32": 5}
+IQ_ORDERS = {"IQ": 0, "QI": 1, "I_Only": 2, "Q_Only": 3}
+
+
+@dataclass
+class SampleFormat:
+    """Sample description of an XML/UFF, raw or WAV recording (xml-descriptor fields Container / bitsperChannel / Ordering / iqOrder)."""
+    container: str = "uint8"
+    bits_per_channel: int = 0   # 0: the container's width
+    byte_order: str = "LSB"
+    iq_order: str = "IQ"
+
+    def c_struct(self) -> _lib.SampleFormatC:
+        return _lib.SampleFormatC(CONTAINERS.get(self.container, -1), int(self.bits_per_channel), 1 if self.byte_order == "MSB" else 0, IQ_ORDERS.get(self.iq_order, -1))
+
+    def native(self) -> int | None:
+        """The decoder input format that reads this layout directly (converted inside the FFT kernel), if any."""
+        if self.iq_order != "IQ":
+            return None
+        if self.container == "uint8":
+            return FMT_U8
+        if self.container == "int16" and self.byte_order == "LSB" and self.bits_per_channel in (0, 16):
+            return FMT_I16
+        if self.container == "float32" and self.byte_order == "LSB":
+            return FMT_CF32
+        return None
+
+
 class Context:
     """One CUDA device + stream (dabstar_create). `stream` may be a torch.cuda.Stream or None for a private stream."""
 
@@ -61,6 +89,20 @@ class Context:
     @property
     def kernel_launches(self) -> int:
         return int(self.lib.dabstar_kernel_launches(self.h))
+
+    # ---- ingest (row I1)
+    def ingest_convert(self, raw: np.ndarray, fmt: "SampleFormat", n_samples: int | None = None) -> np.ndarray:
+        """File samples -> complex64 as the reference's file readers convert them (xml_reader.cpp:254-800,
+        raw_reader.cpp:66-70, wav_reader.cpp:164). raw: the bytes of the file's data section."""
+        raw = np.ascontiguousarray(raw).view(np.uint8).reshape(-1)
+        c = fmt.c_struct()
+        elem = int(self.lib.dabstar_sample_format_bytes(ctypes.byref(c)))
+        if elem == 0:
+            raise DabstarError(f"unknown sample format {fmt}")
+        n = raw.size // elem if n_samples is None else int(n_samples)
+        out = np.empty(n, np.complex64)
+        self.check(self.lib.dabstar_ingest_convert(self.h, _ptr(raw), ctypes.byref(c), ctypes.c_int64(n), _ptr(out), MEM_HOST), "dabstar_ingest_convert")
+        return out
 
     # ---- stage taps
     def fft2048(self, x: np.ndarray, sign: int = -1) -> np.ndarray:
@@ -311,6 +353,18 @@ class DabProcessor:
         self._keep = arrs
         n = [a.shape[0] for a in arrs]
         return self.run_ptrs([a.ctypes.data for a in arrs], n, MEM_HOST)
+
+    def run_files(self, raws: list[np.ndarray], fmt: SampleFormat) -> float:
+        """Recordings in any file sample format: layouts the FFT kernel does not read natively are first converted to
+        complex float on the device (dabstar_ingest_convert); the decoder must have been created with FMT_CF32 then."""
+        nat = fmt.native()
+        if nat is not None and nat == self.cfg.input_format:
+            dt = {FMT_U8: np.uint8, FMT_I16: np.int16, FMT_CF32: np.complex64}[nat]
+            flat = [np.ascontiguousarray(r).view(np.uint8).reshape(-1).view(dt) for r in raws]
+            return self.run([f if nat == FMT_CF32 else f.reshape(-1, 2) for f in flat])
+        if self.cfg.input_format != FMT_CF32:
+            raise DabstarError("run_files with a converted sample format needs a decoder created with input_format=FMT_CF32")
+        return self.run([self.ctx.ingest_convert(r, fmt) for r in raws])
 
     def result(self, recording: int) -> RecordingResult:
         lib = self.ctx.lib

@@ -31,10 +31,45 @@ constexpr float RAD_PER_DEG_F = 0.01745329251994329577f;
 
 enum { FMT_CF32 = 0, FMT_U8 = 1, FMT_I16 = 2 };
 
+// Complex arithmetic. On the device these are the packed FP32 instructions of sm_100 (FADD2 / FMUL2 / FFMA2 work on an
+// aligned register pair = one complex number; an operand may be a broadcast scalar or have its halves swapped for free),
+// so a complex add is ONE instruction and a complex multiply three (two with a prepared constant). The host versions
+// (index-arithmetic tests) are the plain formulas; results differ by rounding only (FMA contraction).
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+  const float2 t = __fmul2_rn(a, make_float2(b.x, b.x));                           // (a.x b.x, a.y b.x)
+  const float2 u = __fmul2_rn(make_float2(a.y, a.x), make_float2(b.y, b.y));       // (a.y b.y, a.x b.y)
+  return __ffma2_rn(u, make_float2(-1.0f, 1.0f), t);
+}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) // a * conj(b)
+{
+  const float2 t = __fmul2_rn(a, make_float2(b.x, b.x));                           // (a.x b.x, a.y b.x)
+  const float2 u = __fmul2_rn(make_float2(a.y, a.x), make_float2(b.y, b.y));       // (a.y b.y, a.x b.y)
+  return __ffma2_rn(u, make_float2(1.0f, -1.0f), t);
+}
+// a * (c + j s) for a compile-time constant: (a.x c - a.y s, a.y c + a.x s) = a * c + swap(a) * (-s, s)
+__device__ __forceinline__ float2 cmul_const(float2 a, float c, float s)
+{
+  return __ffma2_rn(make_float2(a.y, a.x), make_float2(-s, s), __fmul2_rn(a, make_float2(c, c)));
+}
+// -j a
+__device__ __forceinline__ float2 cmul_mj(float2 a) { return __fmul2_rn(make_float2(a.y, a.x), make_float2(1.0f, -1.0f)); }
+// a - j b and a + j b
+__device__ __forceinline__ float2 csub_j(float2 a, float2 b) { return __ffma2_rn(make_float2(b.y, b.x), make_float2(1.0f, -1.0f), a); }
+__device__ __forceinline__ float2 cadd_j(float2 a, float2 b) { return __ffma2_rn(make_float2(b.y, b.x), make_float2(-1.0f, 1.0f), a); }
+#else
 __host__ __device__ inline float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __host__ __device__ inline float2 cmul_conj(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); } // a * conj(b)
 __host__ __device__ inline float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __host__ __device__ inline float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__host__ __device__ inline float2 cmul_const(float2 a, float c, float s) { return cmul(a, make_float2(c, s)); }
+__host__ __device__ inline float2 cmul_mj(float2 a) { return make_float2(a.y, -a.x); }
+__host__ __device__ inline float2 csub_j(float2 a, float2 b) { return make_float2(a.x + b.y, a.y - b.x); }
+__host__ __device__ inline float2 cadd_j(float2 a, float2 b) { return make_float2(a.x - b.y, a.y + b.x); }
+#endif
 
 // One frame of one recording as the kernels see it. Built on the host by the control loop (engine.cu),
 // which restates DabProcessor's AFC/clock bookkeeping (main/dab_processor.cpp:191-265).

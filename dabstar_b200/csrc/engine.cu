@@ -327,6 +327,58 @@ extern "C" int dabstar_protection_addresses(dabstar_ctx * ctx, int short_form, i
   return profile_addresses(p, addr, cap);
 }
 
+// ------------------------------------------------------------------------------------------------ ingest (I1)
+extern "C" int dabstar_sample_format_bytes(const dabstar_sample_format * fmt)
+{
+  if (!fmt || fmt->iq_order < 0 || fmt->iq_order > 3) return 0;
+  int b;
+  switch (fmt->container)
+  {
+  case DABSTAR_CONTAINER_INT8: case DABSTAR_CONTAINER_UINT8: b = 1; break;
+  case DABSTAR_CONTAINER_INT16: b = 2; break;
+  case DABSTAR_CONTAINER_INT24: b = 3; break;
+  case DABSTAR_CONTAINER_INT32: case DABSTAR_CONTAINER_FLOAT32: b = 4; break;
+  default: return 0;
+  }
+  return fmt->iq_order <= DABSTAR_ORDER_QI ? 2 * b : b;
+}
+
+extern "C" int dabstar_ingest_convert(dabstar_ctx * ctx, const void * src, const dabstar_sample_format * fmt, int64_t n_samples, float * dst, int mem)
+{
+  if (!ctx || !src || !fmt || !dst || n_samples < 0) return DABSTAR_E_INVALID;
+  const int elem = dabstar_sample_format_bytes(fmt);
+  if (elem == 0) return ctx->fail(DABSTAR_E_INVALID, "unknown sample format %d / order %d", fmt->container, fmt->iq_order);
+  if (n_samples == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  const int width = fmt->container == DABSTAR_CONTAINER_INT16 ? 16 : (fmt->container == DABSTAR_CONTAINER_INT24 ? 24 : 32);
+  const int bits = fmt->bits_per_channel > 0 ? fmt->bits_per_channel : width;
+  if (bits < 1 || bits > 32) return ctx->fail(DABSTAR_E_INVALID, "bits_per_channel %d", fmt->bits_per_channel);
+  // f32 scaler = f32(shift(nrBits)), shift(a) = 2^(a-1) in i32 (xml_reader.cpp:43-51): 32 bits wrap to -2^31, so int32
+  // files come out negated exactly as the reference reads them; x / (+-2^k) == x * (+-2^-k) exactly
+  const float inv_scaler = 1.0f / (float)(int32_t)(1u << (bits - 1));
+  const float * d_lut = nullptr;
+  if (fmt->container <= DABSTAR_CONTAINER_UINT8)
+  {
+    float lut[256];
+    for (int i = 0; i < 256; i++)
+    {
+      if (fmt->container == DABSTAR_CONTAINER_UINT8) lut[i] = ((float)i - 127.38f) / 128.0f;                 // mapTable, xml_reader.cpp:93-96
+      else if (fmt->iq_order == DABSTAR_ORDER_IQ) lut[i] = (float)(int8_t)i / 127.0f;                        // xml_reader.cpp:266
+      else lut[i] = (float)((double)(int8_t)i / 127.0);                                                      // xml_reader.cpp:411,560,690: double division
+    }
+    CK(ctx->scratch[5].reserve(sizeof(lut)));
+    UP(ctx->scratch[5].p, lut, sizeof(lut));
+    d_lut = ctx->scratch[5].as<float>();
+  }
+  const void * dsrc; void * ddst;
+  if (int r = stage_in(ctx, ctx->scratch[0], src, (size_t)n_samples * elem, mem, &dsrc)) return r;
+  if (int r = stage_out_begin(ctx, ctx->scratch[1], dst, sizeof(float2) * (size_t)n_samples, mem, &ddst)) return r;
+  CK(launch_ingest_convert(ctx->stream, dsrc, fmt->container, fmt->msb_first ? 1 : 0, fmt->iq_order, inv_scaler, d_lut, n_samples, (float2 *)ddst, &ctx->launches));
+  if (int r = stage_out_end(ctx, ddst, dst, sizeof(float2) * (size_t)n_samples, mem)) return r;
+  ctx->arena_off = 0; // the stream is idle: staged uploads have been consumed
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ stage taps
 extern "C" int dabstar_fft2048(dabstar_ctx * ctx, const float * in, float * out, int n, int sign, int mem)
 {

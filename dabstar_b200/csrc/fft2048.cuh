@@ -54,8 +54,8 @@ __host__ __device__ inline void dft4(float2 & a, float2 & b, float2 & c, float2 
   const float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = csub(b, d);
   a = cadd(t0, t2);
   c = csub(t0, t2);
-  b = make_float2(t1.x + t3.y, t1.y - t3.x); // t1 - j t3
-  d = make_float2(t1.x - t3.y, t1.y + t3.x); // t1 + j t3
+  b = csub_j(t1, t3); // t1 - j t3
+  d = cadd_j(t1, t3); // t1 + j t3
 }
 
 // In-place 16-point forward DFT, natural order in and out.
@@ -66,15 +66,15 @@ __host__ __device__ inline void dft16(float2 (&v)[16])
 #pragma unroll
   for (int b = 0; b < 4; b++) dft4(v[b], v[4 + b], v[8 + b], v[12 + b]);
   // twiddles W16^(b c)
-  v[4 + 1] = cmul(v[4 + 1], make_float2(C1, -S1));   // b=1,c=1 : m=1
-  v[8 + 1] = cmul(v[8 + 1], make_float2(R, -R));     // b=1,c=2 : m=2
-  v[12 + 1] = cmul(v[12 + 1], make_float2(S1, -C1)); // b=1,c=3 : m=3
-  v[4 + 2] = cmul(v[4 + 2], make_float2(R, -R));     // b=2,c=1 : m=2
-  v[8 + 2] = make_float2(v[8 + 2].y, -v[8 + 2].x);   // b=2,c=2 : m=4 -> -j
-  v[12 + 2] = cmul(v[12 + 2], make_float2(-R, -R));  // b=2,c=3 : m=6
-  v[4 + 3] = cmul(v[4 + 3], make_float2(S1, -C1));   // b=3,c=1 : m=3
-  v[8 + 3] = cmul(v[8 + 3], make_float2(-R, -R));    // b=3,c=2 : m=6
-  v[12 + 3] = cmul(v[12 + 3], make_float2(-C1, S1)); // b=3,c=3 : m=9
+  v[4 + 1] = cmul_const(v[4 + 1], C1, -S1);   // b=1,c=1 : m=1
+  v[8 + 1] = cmul_const(v[8 + 1], R, -R);     // b=1,c=2 : m=2
+  v[12 + 1] = cmul_const(v[12 + 1], S1, -C1); // b=1,c=3 : m=3
+  v[4 + 2] = cmul_const(v[4 + 2], R, -R);     // b=2,c=1 : m=2
+  v[8 + 2] = cmul_mj(v[8 + 2]);               // b=2,c=2 : m=4 -> -j
+  v[12 + 2] = cmul_const(v[12 + 2], -R, -R);  // b=2,c=3 : m=6
+  v[4 + 3] = cmul_const(v[4 + 3], S1, -C1);   // b=3,c=1 : m=3
+  v[8 + 3] = cmul_const(v[8 + 3], -R, -R);    // b=3,c=2 : m=6
+  v[12 + 3] = cmul_const(v[12 + 3], -C1, S1); // b=3,c=3 : m=9
   // DFT over b for each c -> X[c + 4d] in slot v[4c + d]
 #pragma unroll
   for (int c = 0; c < 4; c++) dft4(v[4 * c + 0], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
@@ -99,12 +99,11 @@ __host__ __device__ inline void dft8(float2 * v)
   float2 o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
   dft4(e0, e1, e2, e3);
   dft4(o0, o1, o2, o3);
-  o1 = cmul(o1, make_float2(R, -R));
-  o2 = make_float2(o2.y, -o2.x);
-  o3 = cmul(o3, make_float2(-R, -R));
+  o1 = cmul_const(o1, R, -R);
+  o3 = cmul_const(o3, -R, -R);
   v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
   v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
-  v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+  v[2] = csub_j(e2, o2); v[6] = cadd_j(e2, o2); // o2 * (-j) folded into the add
   v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
 }
 

@@ -75,5 +75,8 @@ cudaError_t launch_prs_corr_raw(cudaStream_t s, const DeviceTables & t, const fl
 cudaError_t launch_coarse_afc(cudaStream_t s, const DeviceTables & t, const FrameDesc * frames, int n_frames, const RecInput * recs, int fmt,
                               int * offset_hz, unsigned long long * lc);
 cudaError_t launch_coarse_afc_raw(cudaStream_t s, const DeviceTables & t, const float2 * fft_nat, int n, int * offset_hz, unsigned long long * lc);
+// src: packed file samples (see dabstar_sample_format in the C header); lut: 256 floats for the 8-bit containers (device), else nullptr
+cudaError_t launch_ingest_convert(cudaStream_t s, const void * src, int container, int msb_first, int iq_order, float inv_scaler, const float * lut,
+                                  long long n_samples, float2 * dst, unsigned long long * lc);
 cudaError_t launch_dip_search(cudaStream_t s, const DipWork * work, int n, const RecInput * recs, int fmt, DipResult * out, unsigned long long * lc);
 } // namespace dab

@@ -18,19 +18,33 @@ namespace
 {
 // ------------------------------------------------------------------------------------------------ ingest
 // Raw IQ pair as stored in the recording. u8: (v - 127.38)/128 (raw_reader.cpp:66-70); i16: v/32768 (xml_reader.cpp:254-372).
+// A u8 pair stays ONE 16-bit register value until it is converted (a uchar2 would be split into two byte registers
+// right after the load); conversion = two I2F with byte / half-word selectors + one packed FFMA2:
+// (v - 127.38) / 128 = fma(v, 2^-7, -127.38 * 2^-7) bit for bit (scaling by a power of two commutes with the rounding).
 template <int FMT> struct Raw;
-template <> struct Raw<FMT_U8> { typedef uchar2 type; };
-template <> struct Raw<FMT_I16> { typedef short2 type; };
-template <> struct Raw<FMT_CF32> { typedef float2 type; };
+template <> struct Raw<FMT_U8> { typedef unsigned short type; typedef unsigned reg; };  // reg: how a loaded sample is held in registers
+template <> struct Raw<FMT_I16> { typedef short2 type; typedef short2 reg; };
+template <> struct Raw<FMT_CF32> { typedef float2 type; typedef float2 reg; };
 
-__device__ __forceinline__ float2 to_cf(uchar2 v) { return make_float2(((float)v.x - 127.38f) * (1.0f / 128.0f), ((float)v.y - 127.38f) * (1.0f / 128.0f)); }
-__device__ __forceinline__ float2 to_cf(short2 v) { return make_float2((float)v.x * (1.0f / 32768.0f), (float)v.y * (1.0f / 32768.0f)); }
+__device__ __forceinline__ float2 to_cf(unsigned v)
+{
+  // byte -> float without the quarter-rate I2F: 0x4B0000bb is 2^23 + b exactly; subtracting 2^23 is exact
+  const float2 m = make_float2(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540)), __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7541)));
+  const float2 f = __fadd2_rn(m, make_float2(-8388608.0f, -8388608.0f));
+  return __ffma2_rn(f, make_float2(1.0f / 128.0f, 1.0f / 128.0f), make_float2(-127.38f / 128.0f, -127.38f / 128.0f));
+}
+__device__ __forceinline__ float2 to_cf(short2 v) { return __fmul2_rn(make_float2((float)v.x, (float)v.y), make_float2(1.0f / 32768.0f, 1.0f / 32768.0f)); }
 __device__ __forceinline__ float2 to_cf(float2 v) { return v; }
 
 template <int FMT> __device__ __forceinline__ float2 load_sample(const void * __restrict__ iq, long long i)
 {
-  return to_cf(reinterpret_cast<const typename Raw<FMT>::type *>(iq)[i]);
+  return to_cf((typename Raw<FMT>::reg)reinterpret_cast<const typename Raw<FMT>::type *>(iq)[i]);
 }
+
+__device__ __forceinline__ unsigned smem_addr_u32(const void * p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(unsigned dst, const void * src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ int mod_fs(long long x)
 {
@@ -57,7 +71,7 @@ __device__ __forceinline__ float2 osc(int idx)
 
 // Fetches the 2048 raw samples starting at `start` in the FFT's register layout (r[n1] = x[128 n1 + tid]).
 template <int FMT>
-__device__ __forceinline__ void fetch_symbol(typename Raw<FMT>::type (&r)[16], const void * __restrict__ iq, long long n_total, long long start, int tid)
+__device__ __forceinline__ void fetch_symbol(typename Raw<FMT>::reg (&r)[16], const void * __restrict__ iq, long long n_total, long long start, int tid)
 {
   typedef typename Raw<FMT>::type T;
   const T * p = reinterpret_cast<const T *>(iq) + start + tid;
@@ -73,7 +87,7 @@ __device__ __forceinline__ void fetch_symbol(typename Raw<FMT>::type (&r)[16], c
     {
       const long long i = start + 128 * n1 + tid;
       if (i >= 0 && i < n_total) r[n1] = p[128 * n1];
-      else r[n1] = T(); // outside the recording; mix_symbol replaces it by a zero amplitude
+      else r[n1] = typename Raw<FMT>::reg(); // outside the recording; mix_symbol replaces it by a zero amplitude
     }
   }
 }
@@ -81,7 +95,7 @@ __device__ __forceinline__ void fetch_symbol(typename Raw<FMT>::type (&r)[16], c
 // Converts the fetched samples and mixes them with the integer-Hz oscillator. `ph` is the oscillator phase BEFORE
 // sample `start`. step[] is a 16-entry shared scratch (phasor of -f*128*n1). Samples outside the recording are zero.
 template <int FMT>
-__device__ __forceinline__ void mix_symbol(float2 (&v)[16], const typename Raw<FMT>::type (&r)[16], long long n_total, long long start, int f, int ph,
+__device__ __forceinline__ void mix_symbol(float2 (&v)[16], const typename Raw<FMT>::reg (&r)[16], long long n_total, long long start, int f, int ph,
                                            float2 * step, int tid)
 {
   const bool inside = start >= 0 && start + T_U <= n_total;
@@ -104,7 +118,7 @@ template <int FMT>
 __device__ __forceinline__ void load_symbol(float2 (&v)[16], const void * __restrict__ iq, long long n_total, long long start, int f, int ph,
                                             float2 * step, int tid)
 {
-  typename Raw<FMT>::type r[16];
+  typename Raw<FMT>::reg r[16];
   fetch_symbol<FMT>(r, iq, n_total, start, tid);
   mix_symbol<FMT>(v, r, n_total, start, f, ph, step, tid);
 }
@@ -120,12 +134,9 @@ struct SymbolItem
   long long out; // float2 index of X row, -1: nothing to do
 };
 
-__device__ __forceinline__ SymbolItem symbol_item(const FrameDesc * __restrict__ frames, const RecInput * __restrict__ recs, int item)
+__device__ __forceinline__ SymbolItem symbol_item(const FrameDesc & fd, const RecInput & rin, int row)
 {
   SymbolItem it;
-  const int fi = item / X_ROWS, row = item - fi * X_ROWS;
-  const FrameDesc fd = frames[fi];
-  const RecInput rin = recs[fd.rec];
   it.iq = rin.iq;
   it.n_total = rin.n;
   it.out = ((long long)fd.xslot * X_ROWS + row) * K_CARR;
@@ -147,11 +158,33 @@ __device__ __forceinline__ SymbolItem symbol_item(const FrameDesc * __restrict__
   return it;
 }
 
+// Raw samples reach the CTA through a double-buffered cp.async stage in shared memory: the 16-byte chunks that cover
+// the next symbol are requested before the current symbol is transformed, no register holds them meanwhile and no
+// instruction waits for them until the next iteration (register prefetch made the compiler sink the loads and the
+// first use stalled on HBM latency). Symbols within 8 samples of either end of a recording (where the 16-byte aligned
+// superset could leave the buffer) take the bounds-checked path.
+template <int FMT> __host__ __device__ constexpr int fft_stage_bytes() { return T_U * (int)sizeof(typename Raw<FMT>::type) + 16; }
+
 template <int FMT>
-__global__ void __launch_bounds__(FFT_THREADS, 4) k_fft_frames(const FrameDesc * __restrict__ frames, int n_items, const RecInput * __restrict__ recs,
+__device__ __forceinline__ bool item_async(const SymbolItem & it) { return it.out >= 0 && it.start >= 8 && it.start + T_U + 8 <= it.n_total; }
+
+template <int FMT>
+__device__ __forceinline__ void stage_symbol(const SymbolItem & it, unsigned stage_addr, int tid)
+{
+  typedef typename Raw<FMT>::type T;
+  const unsigned long long a = (unsigned long long)(reinterpret_cast<const T *>(it.iq) + it.start);
+  const unsigned long long a0 = a & ~15ull;
+  const int chunks = (int)((a - a0) + T_U * sizeof(T) + 15) >> 4;
+  for (int c = tid; c < chunks; c += FFT_THREADS) cp_async16(stage_addr + 16u * (unsigned)c, reinterpret_cast<const void *>(a0 + 16ull * (unsigned)c));
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(FFT_THREADS, 5) k_fft_frames(const FrameDesc * __restrict__ frames, int n_items, const RecInput * __restrict__ recs,
                                                                const float2 * __restrict__ w2048, const int16_t * __restrict__ bin_of_k,
                                                                float2 * __restrict__ X)
 {
+  typedef typename Raw<FMT>::type T;
+  extern __shared__ __align__(16) unsigned char fft_stage[]; // 2 x fft_stage_bytes<FMT>()
   __shared__ float2 smem[FFT_SMEM_F2];
   __shared__ float2 tw2s[FFT_TW2_F2];
   __shared__ float2 step[16];
@@ -160,32 +193,61 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) k_fft_frames(const FrameDesc *
   FftTwiddles tw;
   fft_load_twiddles(tw, w2048, tw2s, tid);
   for (int k = tid; k < K_CARR; k += FFT_THREADS) bins[k] = (int16_t)fft_nat(bin_of_k[k]);
-  __syncthreads();
+  const unsigned stage0 = smem_addr_u32(fft_stage);
+  constexpr int SB = fft_stage_bytes<FMT>();
 
-  // software pipeline: the raw samples of the next symbol are in flight while the current one is transformed
-  typename Raw<FMT>::type raw[16];
-  int item = blockIdx.x;
+  // A CTA walks a contiguous range of (frame, row) items, so the frame descriptor is fetched once per 77 symbols
+  // instead of in front of every symbol (where its latency sat on the critical path of the cp.async issue).
+  const int per = n_items / (int)gridDim.x, rem = n_items - per * (int)gridDim.x;
+  int item = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
+  const int item_end = item + per + ((int)blockIdx.x < rem ? 1 : 0);
+  int buf = 0, fi = item / X_ROWS, row = item - fi * X_ROWS;
+  FrameDesc fd;
+  RecInput rin;
   SymbolItem cur;
-  if (item < n_items)
+  cur.out = -1;
+  if (item < item_end)
   {
-    cur = symbol_item(frames, recs, item);
-    if (cur.out >= 0) fetch_symbol<FMT>(raw, cur.iq, cur.n_total, cur.start, tid);
+    fd = frames[fi];
+    rin = recs[fd.rec];
+    cur = symbol_item(fd, rin, row);
+    if (item_async<FMT>(cur)) stage_symbol<FMT>(cur, stage0, tid);
   }
-  while (item < n_items)
+  cp_async_commit();
+  __syncthreads();
+  while (item < item_end)
   {
-    float2 v[16];
-    const bool active = cur.out >= 0;
-    if (active) mix_symbol<FMT>(v, raw, cur.n_total, cur.start, cur.f, cur.ph, step, tid);
-    const int next = item + gridDim.x;
+    const int next = item + 1;
     SymbolItem nxt;
     nxt.out = -1;
-    if (next < n_items)
+    if (next < item_end)
     {
-      nxt = symbol_item(frames, recs, next);
-      if (nxt.out >= 0) fetch_symbol<FMT>(raw, nxt.iq, nxt.n_total, nxt.start, tid);
+      if (++row == X_ROWS)
+      {
+        row = 0;
+        fi++;
+        fd = frames[fi];
+        rin = recs[fd.rec];
+      }
+      nxt = symbol_item(fd, rin, row);
+      if (item_async<FMT>(nxt)) stage_symbol<FMT>(nxt, stage0 + (unsigned)((buf ^ 1) * SB), tid);
     }
-    if (active)
+    cp_async_commit();
+    if (cur.out >= 0)
     {
+      float2 v[16];
+      if (item_async<FMT>(cur))
+      {
+        cp_async_wait<1>();  // this thread's chunks of the current symbol have landed ...
+        __syncthreads();     // ... and so have everybody else's
+        const unsigned off = (unsigned)((unsigned long long)(reinterpret_cast<const T *>(cur.iq) + cur.start) & 15ull);
+        const T * sp = reinterpret_cast<const T *>(fft_stage + buf * SB + off) + tid;
+        typename Raw<FMT>::reg r[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) r[n1] = sp[128 * n1];
+        mix_symbol<FMT>(v, r, cur.n_total, cur.start, cur.f, cur.ph, step, tid);
+      }
+      else load_symbol<FMT>(v, cur.iq, cur.n_total, cur.start, cur.f, cur.ph, step, tid);
       fft2048_to_smem(v, tw, smem, tid);
       float2 * out = X + cur.out;
 #pragma unroll
@@ -194,11 +256,13 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) k_fft_frames(const FrameDesc *
         const int k = tid + FFT_THREADS * i;
         out[k] = smem[bins[k]];
       }
-      __syncthreads();
     }
+    __syncthreads(); // smem and the stage buffer of this symbol are free again
     cur = nxt;
     item = next;
+    buf ^= 1;
   }
+  cp_async_wait<0>();
 }
 
 // Natural-order batch transform (stage tap dabstar_fft2048). sign > 0: conj in, conj out.
@@ -1149,6 +1213,281 @@ __global__ void __launch_bounds__(DM3_ROW4) k_demap3(const DemapWork * __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------ DQPSK demapper, packed version
+// k_demap3's scheme (sliced cooperative launch, lagged scale exchange through L2) with the arithmetic and the data path
+// redone for sm_100:
+//   * the two carriers of a thread run in the two halves of the packed FP32 instructions (FADD2 / FMUL2 / FFMA2): every
+//     multiply-add of the per-carrier recurrences is issued once for both carriers; only MUFU, min/max and the selects
+//     stay scalar;
+//   * spectrum rows arrive through a per-thread cp.async ring in shared memory, DM4_PF rows deep: the load of row q + 8
+//     is issued when row q is consumed and nothing reads a destination register in between. k_demap3 rotates its
+//     prefetch registers with MOVs, and the first MOV waits for the load (an effective distance of ONE row); a register
+//     ring rotated by unrolling the row loop was measured too and is worse (9.7 ms against 7.6 ms: the loads in flight
+//     share the six scoreboards, and a wait on a shared scoreboard waits for the newest load);
+//   * x86 (i16)(float) semantics of the output conversion are checked once per thread and row (rare path) instead of
+//     once per value.
+constexpr int DM4_PF = 8; // rows in flight per thread (power of two)
+
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+struct CarrierPair
+{
+  float2 integ, stddev, mean_pow, mean_sigma, null_pow; // .x = carrier 2t, .y = carrier 2t + 1
+};
+
+// arg(z) mod pi/2 for both carriers (see folded_phase)
+__device__ __forceinline__ float2 folded_phase2(float2 re, float2 im)
+{
+  const float ax0 = fabsf(re.x), ay0 = fabsf(im.x), ax1 = fabsf(re.y), ay1 = fabsf(im.y);
+  const float2 mn = make_float2(fminf(ax0, ay0), fminf(ax1, ay1));
+  const float2 t = mul2(mn, make_float2(rcp_ftz(fmaxf(ax0, ay0)), rcp_ftz(fmaxf(ax1, ay1))));
+  const float2 z = mul2(t, t);
+  float2 p = f2(0.00681177107617259f);
+  p = fma2(p, z, f2(-0.033604156225919724f));
+  p = fma2(p, z, f2(0.07962360233068466f));
+  p = fma2(p, z, f2(-0.13233338296413422f));
+  p = fma2(p, z, f2(0.19807815551757812f));
+  p = fma2(p, z, f2(-0.3331736922264099f));
+  p = fma2(p, z, f2(0.9999961256980896f));
+  const float2 a = mul2(p, t);
+  const bool m0 = (ay0 > ax0) != ((__float_as_int(re.x) ^ __float_as_int(im.x)) < 0);
+  const bool m1 = (ay1 > ax1) != ((__float_as_int(re.y) ^ __float_as_int(im.y)) < 0);
+  return make_float2(m0 ? PI_2_F - a.x : a.x, m1 ? PI_2_F - a.y : a.y);
+}
+
+// decode_symbol (ofdm_decoder.cpp:166-294) for the two carriers of a thread. xr/xi, rr/ri: real and imaginary parts of the
+// symbol and of the phase reference; returns the unscaled soft values in o_re/o_im and |r| of both carriers in r_abs.
+template <int SOFT>
+__device__ __forceinline__ void dm4_pair(CarrierPair & st, float2 xr, float2 xi, float2 rr, float2 ri, float2 ref_abs, float2 ref_inv, float2 cterm,
+                                         float2 & o_re, float2 & o_im, float2 & r_abs)
+{
+  constexpr float ALPHA = 0.005f;
+  // raw = x conj(ref) / |ref|
+  const float2 re = mul2(fma2(xi, ri, mul2(xr, rr)), ref_inv);
+  const float2 im = mul2(fma2(neg2(xr), ri, mul2(xi, rr)), ref_inv);
+  // rotation by -(clock term + integrator), minimax polynomial of ofdm_decoder.cpp:70-88
+  const float2 t = add2(cterm, st.integ), a2 = mul2(t, t);
+  const float2 rx = fma2(a2, fma2(a2, f2(3.679168224334716796875e-2f), f2(-0.495580852031707763671875f)), f2(0.9994032382965087890625f));
+  const float2 ry = mul2(neg2(t), fma2(a2, f2(-0.16034401953220367431640625f), f2(0.99903142452239990234375f)));
+  const float2 zr = fma2(neg2(im), ry, mul2(re, rx));
+  const float2 zi = fma2(im, rx, mul2(re, ry));
+  const float2 dv = add2(folded_phase2(zr, zi), f2(-PI_4_F));
+  const float2 in = fma2(dv, f2(0.2f * ALPHA), st.integ);
+  st.integ = make_float2(fminf(fmaxf(in.x, -20.0f * RAD_PER_DEG_F), 20.0f * RAD_PER_DEG_F), fminf(fmaxf(in.y, -20.0f * RAD_PER_DEG_F), 20.0f * RAD_PER_DEG_F));
+  st.stddev = fma2(fma2(dv, dv, neg2(st.stddev)), f2(ALPHA), st.stddev);
+  const float2 pw = fma2(zr, zr, mul2(zi, zi));
+  st.mean_pow = fma2(add2(pw, neg2(st.mean_pow)), f2(ALPHA), st.mean_pow);
+  const float2 lvl = make_float2(sqrt_ftz(st.mean_pow.x), sqrt_ftz(st.mean_pow.y));
+  const float2 dr = fma2(lvl, f2(-0.70710678118654752440f), make_float2(fabsf(zr.x), fabsf(zr.y)));
+  const float2 di = fma2(lvl, f2(-0.70710678118654752440f), make_float2(fabsf(zi.x), fabsf(zi.y)));
+  st.mean_sigma = fma2(add2(fma2(dr, dr, mul2(di, di)), neg2(st.mean_sigma)), f2(ALPHA), st.mean_sigma);
+  float2 sig = add2(st.mean_pow, neg2(st.null_pow));
+  if (sig.x <= 0.0f) sig.x = 0.1f;
+  if (sig.y <= 0.0f) sig.y = 0.1f;
+  const float2 inv_z = make_float2(rsqrt_ftz(pw.x), rsqrt_ftz(pw.y));
+  float2 w1;
+  if (SOFT == 2) w1 = ref_abs;
+  else
+  {
+    // 1 / ((nullPow / sig + 0.7) * meanSigma) = sig / ((nullPow + 0.7 sig) * meanSigma)
+    const float2 den = mul2(fma2(sig, f2(0.7f), st.null_pow), st.mean_sigma);
+    const float2 g = mul2(sig, make_float2(rcp_ftz(den.x), rcp_ftz(den.y)));
+    if (SOFT == 1) w1 = mul2(ref_abs, g);
+    else
+    {
+      const float2 q = mul2(ref_abs, inv_z); // sqrt(|z| |P|) / |z| = sqrt(|P| / |z|)
+      w1 = mul2(mul2(make_float2(sqrt_ftz(q.x), sqrt_ftz(q.y)), lvl), g);
+    }
+  }
+  r_abs = mul2(mul2(pw, inv_z), w1); // |z| w1, w1 >= 0
+  o_re = mul2(zr, w1);
+  o_im = mul2(zi, w1);
+}
+
+constexpr int DM4_MAX_THREADS = 384; // at least two slices per recording: leaves 170 registers per thread
+
+template <int SOFT>
+__global__ void __launch_bounds__(DM4_MAX_THREADS) k_demap4(const DemapWork * __restrict__ work, const FrameDesc * __restrict__ frames,
+                                                     const uint8_t * __restrict__ null_is_tii, const float2 * __restrict__ X,
+                                                     const int16_t * __restrict__ rel_of_k, OfdmStateDev * __restrict__ states,
+                                                     int16_t * __restrict__ soft, unsigned long long * __restrict__ ring, int slices)
+{
+  extern __shared__ float4 dm4_smem[]; // [DM3_STASH][T] unscaled soft values of the last symbols | [DM4_PF][T] spectrum rows in flight
+  const int T = (int)blockDim.x;
+  float4 * stash = dm4_smem;
+  float4 * rowbuf = dm4_smem + DM3_STASH * T;
+  const int w = blockIdx.x / slices, slice = blockIdx.x - w * slices;
+  const DemapWork wk = work[w];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int t_rec = slice * T + tid; // thread index within the recording: carriers 2 t_rec, 2 t_rec + 1
+  const int gw = t_rec >> 5;         // warp index within the recording
+  const int k0 = 2 * t_rec;
+  unsigned long long * my_ring = ring + (size_t)w * DM3_RING * DM3_WARPS;
+
+  OfdmStateDev & sd = states[wk.state];
+  CarrierPair st;
+  if (wk.reset) st = CarrierPair{ f2(0.f), f2(0.f), f2(0.f), f2(0.f), f2(0.f) };
+  else
+    st = CarrierPair{ make_float2(sd.integ[k0], sd.integ[k0 + 1]), make_float2(sd.stddev[k0], sd.stddev[k0 + 1]), make_float2(sd.mean_pow[k0], sd.mean_pow[k0 + 1]),
+                      make_float2(sd.mean_sigma[k0], sd.mean_sigma[k0 + 1]), make_float2(sd.null_pow[k0], sd.null_pow[k0 + 1]) };
+  const float mean_value0 = sd.mean_value; // not touched by reset() (ofdm_decoder.cpp:90-101)
+  const float2 gk = make_float2((float)(K_CARR / 2 - rel_of_k[k0]) / (float)(K_CARR / 2), (float)(K_CARR / 2 - rel_of_k[k0 + 1]) / (float)(K_CARR / 2));
+  constexpr float W2 = SOFT == 0 ? -100.0f : -140.0f;
+
+  const int total_rows = wk.n_frames * X_ROWS;
+  const float4 * rows = reinterpret_cast<const float4 *>(X + (size_t)(total_rows > 0 ? frames[wk.desc_first].xslot : 0) * X_ROWS * K_CARR) + t_rec;
+  const unsigned rowbuf_addr = smem_addr_u32(rowbuf + tid);
+#pragma unroll
+  for (int i = 0; i < DM4_PF; i++)
+  {
+    if (i < total_rows) cp_async16(rowbuf_addr + (unsigned)(i * T) * 16u, rows + (size_t)i * DM3_ROW4);
+    cp_async_commit();
+  }
+
+  float2 rr = f2(0.f), ri = f2(0.f), ref_abs = f2(0.f), ref_inv = f2(0.f), cterm = f2(0.f);
+  int n_syms = 0, row = 0, fi = 0;
+  int out_row0 = 0;
+  bool tii = false;
+  int g = 0;               // symbols decoded so far; tag of symbol g is g + 1
+  int orow[DM3_LAG];       // output rows (slot * 75 + symbol - 1) of the last DM3_LAG symbols, newest first
+#pragma unroll
+  for (int i = 0; i < DM3_LAG; i++) orow[i] = 0;
+  unsigned long long pre = 0; // prefetched ring word of the symbol whose total is needed next
+
+  // soft bits of symbol d (its unscaled values are in the stash); total = sum |r| of symbol d - 1 (unused for d = 0)
+  auto emit = [&](int d, int o_row, float total) {
+    const float w2 = d == 0 ? rcp_ftz(mean_value0) * W2 : rcp_ftz(total) * (W2 * (float)K_CARR);
+    const float4 r = stash[(d & (DM3_STASH - 1)) * T + tid]; // (re0, re1, im0, im1)
+    const float2 vre = mul2(make_float2(r.x, r.y), f2(w2)), vim = mul2(make_float2(r.z, r.w), f2(w2));
+    int a = __float2int_rz(vre.x), b = __float2int_rz(vre.y), c = __float2int_rz(vim.x), e = __float2int_rz(vim.y);
+    if (max(max(a, b), max(c, e)) == 0x7fffffff)
+    {
+      // x86 cvttss2si returns 0x80000000 out of range (to_i16): the saturated positive case must read 0, not 0xffff
+      a = a == 0x7fffffff ? 0 : a; b = b == 0x7fffffff ? 0 : b; c = c == 0x7fffffff ? 0 : c; e = e == 0x7fffffff ? 0 : e;
+    }
+    unsigned * o = reinterpret_cast<unsigned *>(soft + (size_t)o_row * SYM_BITS);
+    o[t_rec] = __byte_perm((unsigned)a, (unsigned)b, 0x5410);
+    o[K_CARR / 2 + t_rec] = __byte_perm((unsigned)c, (unsigned)e, 0x5410);
+  };
+  // warp sum in a fixed order
+  auto wsum = [](float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+  float part_prev = 0.0f; // this thread's |r| sum of symbol g - 1, published (reduced over the warp) one symbol late
+
+  for (int q = 0; q < total_rows; q++)
+  {
+    cp_async_wait<DM4_PF - 1>();
+    const unsigned slot = (unsigned)((q & (DM4_PF - 1)) * T);
+    const float4 cur = rowbuf[slot + tid];
+    if (q + DM4_PF < total_rows) cp_async16(rowbuf_addr + slot * 16u, rows + (size_t)(q + DM4_PF) * DM3_ROW4);
+    cp_async_commit();
+    const float2 xr = make_float2(cur.x, cur.z), xi = make_float2(cur.y, cur.w);
+    if (row == 0)
+    {
+      const FrameDesc fd = frames[wk.desc_first + fi];
+      cterm = mul2(f2(fd.clock_err / 1024.0f * PI_F), gk);
+      n_syms = fd.n_syms;
+      out_row0 = fd.slot * 75;
+      tii = null_is_tii != nullptr && null_is_tii[wk.desc_first + fi];
+    }
+    if (row == 0 || row <= n_syms)
+    {
+      if (row > 0)
+      {
+        const int d = g - DM3_LAG; // symbol whose soft bits are written in this iteration
+        // Two shuffle chains that do not depend on this symbol's arithmetic, so the scheduler overlaps them with it:
+        // (1) the warp's share of sum |r| of the PREVIOUS symbol, published under tag g;
+        if (g > 0)
+        {
+          const float part = wsum(part_prev);
+          if (lane == 0)
+            st_volatile_global_b64(my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM3_WARPS + gw,
+                                   ((unsigned long long)(unsigned)g << 32) | (unsigned long long)__float_as_uint(part));
+        }
+        // (2) the total of symbol d - 1 from the ring words fetched one iteration ago (valid if every tag reads d).
+        const float tot_fast = wsum(lane < DM3_WARPS ? __uint_as_float((unsigned)pre) : 0.0f);
+        const bool tags_ok = __all_sync(0xffffffffu, lane >= DM3_WARPS || (unsigned)(pre >> 32) == (unsigned)d);
+        float2 o_re, o_im, r_abs;
+        dm4_pair<SOFT>(st, xr, xi, rr, ri, ref_abs, ref_inv, cterm, o_re, o_im, r_abs);
+        part_prev = r_abs.x + r_abs.y;
+        stash[(g & (DM3_STASH - 1)) * T + tid] = make_float4(o_re.x, o_re.y, o_im.x, o_im.y);
+        if (d >= 0)
+        {
+          float tot = tot_fast;
+          if (d > 0 && !tags_ok) tot = dm3_total(my_ring + (size_t)((d - 1) & (DM3_RING - 1)) * DM3_WARPS, pre, (unsigned)d, lane);
+          emit(d, orow[DM3_LAG - 1], tot);
+        }
+        // ring words for the next iteration's output (symbol d + 1 is scaled by the total of symbol d, published at iteration d + 1)
+        if (d >= 0 && lane < DM3_WARPS) pre = ld_volatile_global_b64(my_ring + (size_t)(d & (DM3_RING - 1)) * DM3_WARPS + lane);
+#pragma unroll
+        for (int i = DM3_LAG - 1; i > 0; i--) orow[i] = orow[i - 1];
+        orow[0] = out_row0 + (row - 1);
+        g++;
+      }
+      // this row is the phase reference of the next symbol
+      rr = xr;
+      ri = xi;
+      const float2 p = fma2(xr, xr, mul2(xi, xi));
+      ref_inv = make_float2(rsqrt_ftz(p.x), rsqrt_ftz(p.y));
+      ref_abs = mul2(p, ref_inv);
+    }
+    else if (row == X_ROWS - 1 && n_syms == 75 && !tii)
+    {
+      // store_null_symbol_without_tii (ofdm_decoder.cpp:114-130)
+      constexpr float MIN_POW = (1.0f / 32767.0f) * (1.0f / 32767.0f);
+      const float2 p = add2(fma2(xr, xr, mul2(xi, xi)), f2(MIN_POW));
+      st.null_pow = fma2(add2(p, neg2(st.null_pow)), f2(0.05f), st.null_pow);
+    }
+    if (++row == X_ROWS) { row = 0; fi++; }
+  }
+  cp_async_wait<0>();
+  // the last symbol's share has not been published yet
+  if (g > 0)
+  {
+    const float part = wsum(part_prev);
+    if (lane == 0)
+      st_volatile_global_b64(my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM3_WARPS + gw,
+                             ((unsigned long long)(unsigned)g << 32) | (unsigned long long)__float_as_uint(part));
+  }
+  // drain: the last DM3_LAG symbols
+#pragma unroll
+  for (int i = DM3_LAG - 1; i >= 0; i--)
+  {
+    const int d = g - 1 - i;
+    if (d < 0) continue;
+    float tot = 0.0f;
+    if (d >= 1)
+    {
+      const unsigned long long * slot = my_ring + (size_t)((d - 1) & (DM3_RING - 1)) * DM3_WARPS;
+      unsigned long long word = 0;
+      if (lane < DM3_WARPS) word = ld_volatile_global_b64(slot + lane);
+      tot = dm3_total(slot, word, (unsigned)d, lane);
+    }
+    emit(d, orow[i], tot);
+  }
+  sd.integ[k0] = st.integ.x; sd.integ[k0 + 1] = st.integ.y;
+  sd.stddev[k0] = st.stddev.x; sd.stddev[k0 + 1] = st.stddev.y;
+  sd.mean_pow[k0] = st.mean_pow.x; sd.mean_pow[k0 + 1] = st.mean_pow.y;
+  sd.mean_sigma[k0] = st.mean_sigma.x; sd.mean_sigma[k0 + 1] = st.mean_sigma.y;
+  sd.null_pow[k0] = st.null_pow.x; sd.null_pow[k0 + 1] = st.null_pow.y;
+  // mMeanValue after the last symbol (every other thread has read sd.mean_value before it published anything)
+  if (gw == 0 && g > 0)
+  {
+    unsigned long long word = 0;
+    const unsigned long long * slot = my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM3_WARPS;
+    if (lane < DM3_WARPS) word = ld_volatile_global_b64(slot + lane);
+    const float tot = dm3_total(slot, word, (unsigned)g, lane);
+    if (lane == 0) sd.mean_value = tot / (float)K_CARR;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ time sync (S1)
 // TimeSyncer::read_samples_until_end_of_level_drop (timesyncer.cpp:40-90) on top of SampleReader's level IIR
 // (sample_reader.cpp:236, alpha = 1e-5). One CTA per recording; the stream is scanned in blocks of 1024 samples.
@@ -1278,6 +1617,62 @@ __global__ void __launch_bounds__(DIP_THREADS) k_dip_search(const DipWork * __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------ file sample formats (I1)
+// XmlReader::readElements_* (xml_filereader/xml_reader.cpp:254-800) for the formats the FFT kernel does not read natively.
+// One thread per complex sample; the 8-bit containers go through a 256-entry table computed on the host with the
+// reference's own expressions, the wider ones are assembled byte by byte (either byte order) and divided by 2^(bits-1)
+// (an exact multiplication by the reciprocal).
+__device__ __forceinline__ float ingest_value(const unsigned char * p, int container, int msb_first, float inv_scaler, const float * __restrict__ lut)
+{
+  switch (container)
+  {
+  case 0: case 1: return lut[p[0]];
+  case 2:
+  {
+    const int v = msb_first ? ((p[0] << 8) | p[1]) : ((p[1] << 8) | p[0]);
+    return (float)(short)v * inv_scaler;
+  }
+  case 3:
+  {
+    int v = msb_first ? ((p[0] << 16) | (p[1] << 8) | p[2]) : ((p[2] << 16) | (p[1] << 8) | p[0]);
+    if (v & 0x800000) v |= (int)0xFF000000;
+    return (float)v * inv_scaler;
+  }
+  case 4:
+  {
+    const unsigned v = msb_first ? (((unsigned)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]) : (((unsigned)p[3] << 24) | (p[2] << 16) | (p[1] << 8) | p[0]);
+    return (float)(int)v * inv_scaler;
+  }
+  default:
+  {
+    const unsigned v = msb_first ? (((unsigned)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]) : (((unsigned)p[3] << 24) | (p[2] << 16) | (p[1] << 8) | p[0]);
+    return __uint_as_float(v);
+  }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ingest_convert(const unsigned char * __restrict__ src, int container, int msb_first, int iq_order, float inv_scaler,
+                                                        const float * __restrict__ lut, long long n, float2 * __restrict__ dst)
+{
+  const int bytes = container <= 1 ? 1 : (container == 2 ? 2 : (container == 3 ? 3 : 4));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  {
+    float2 o;
+    if (iq_order <= 1)
+    {
+      const float a = ingest_value(src + (2 * i) * bytes, container, msb_first, inv_scaler, lut);
+      const float b = ingest_value(src + (2 * i + 1) * bytes, container, msb_first, inv_scaler, lut);
+      o = iq_order == 0 ? make_float2(a, b) : make_float2(b, a);
+    }
+    else
+    {
+      const float a = ingest_value(src + i * bytes, container, msb_first, inv_scaler, lut);
+      o = iq_order == 2 ? make_float2(a, 0.0f) : make_float2(0.0f, a);
+    }
+    dst[i] = o;
+  }
+}
+
 template <typename F> cudaError_t dispatch_fmt(int fmt, F && f)
 {
   switch (fmt)
@@ -1315,7 +1710,15 @@ cudaError_t launch_fft_frames(cudaStream_t s, const DeviceTables & t, const Fram
   if (n_frames <= 0) return cudaSuccess;
   const int n_items = n_frames * X_ROWS;
   if (lc) (*lc)++;
-  return dispatch_fmt(fmt, [&](auto F) { k_fft_frames<decltype(F)::value><<<fft_grid(n_items), FFT_THREADS, 0, s>>>(frames, n_items, recs, t.w2048, t.bin_of_k, X); });
+  return dispatch_fmt(fmt, [&](auto F) {
+    constexpr int FMT = decltype(F)::value;
+    constexpr int stage = 2 * fft_stage_bytes<FMT>();
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_fft_frames<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage); attr_set = true; }
+    static int per_sm = 0; // resident CTAs per SM (registers and shared memory of this instantiation)
+    if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fft_frames<FMT>, FFT_THREADS, stage) != cudaSuccess || per_sm <= 0)) per_sm = 4;
+    k_fft_frames<FMT><<<std::min(n_items, N_SM * per_sm), FFT_THREADS, stage, s>>>(frames, n_items, recs, t.w2048, t.bin_of_k, X);
+  });
 }
 
 cudaError_t launch_reorder_frames(cudaStream_t s, const DeviceTables & t, const float2 * fft_nat, int n_frames, float2 * X, unsigned long long * lc)
@@ -1328,6 +1731,7 @@ cudaError_t launch_reorder_frames(cudaStream_t s, const DeviceTables & t, const 
 
 size_t demap_ring_bytes(int n_work) { return sizeof(unsigned long long) * (size_t)std::max(n_work, 1) * DM3_RING * DM3_WARPS; }
 static size_t demap3_smem_bytes(int threads) { return sizeof(float4) * (size_t)DM3_STASH * (size_t)threads; }
+static size_t demap4_smem_bytes(int threads) { return sizeof(float4) * (size_t)(DM3_STASH + DM4_PF) * (size_t)threads; }
 
 cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork * work, int n_work, const FrameDesc * frames,
                          const uint8_t * null_is_tii, const float2 * X, OfdmStateDev * states, int soft_bit_type, int16_t * soft,
@@ -1360,7 +1764,10 @@ cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork
     return cudaGetLastError();
   }
   if (ring == nullptr) return cudaErrorInvalidValue;
-  const void * fn = soft_bit_type == 0 ? (const void *)k_demap3<0> : (soft_bit_type == 1 ? (const void *)k_demap3<1> : (const void *)k_demap3<2>);
+  static const bool use_v3 = getenv("DABSTAR_DEMAP_V3") != nullptr; // scalar arithmetic, register prefetch (kept for comparison)
+  const void * fn = use_v3 ? (soft_bit_type == 0 ? (const void *)k_demap3<0> : (soft_bit_type == 1 ? (const void *)k_demap3<1> : (const void *)k_demap3<2>))
+                           : (soft_bit_type == 0 ? (const void *)k_demap4<0> : (soft_bit_type == 1 ? (const void *)k_demap4<1> : (const void *)k_demap4<2>));
+  auto smem_bytes = [&](int threads) { return use_v3 ? demap3_smem_bytes(threads) : demap4_smem_bytes(threads); };
   // slices per recording: fill the SMs as evenly as the co-residency limit allows
   static int n_sm = 0;
   if (n_sm == 0)
@@ -1375,8 +1782,9 @@ cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork
   for (int ci = 0; ci < 7; ci++)
   {
     const int sl = cand[ci], threads = DM3_ROW4 / sl;
+    if (!use_v3 && threads > DM4_MAX_THREADS) continue;
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, demap3_smem_bytes(threads)) != cudaSuccess || occ <= 0) continue;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem_bytes(threads)) != cudaSuccess || occ <= 0) continue;
     const int cap = occ * n_sm;                       // CTAs that can be resident at once
     const int recs = std::min(n_work, cap / sl);      // recordings per launch
     if (recs <= 0) continue;
@@ -1395,7 +1803,7 @@ cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork
     const int16_t * rel = t.rel_of_k;
     int sl = best_s;
     void * args[] = { (void *)&wk, (void *)&frames, (void *)&null_is_tii, (void *)&X, (void *)&rel, (void *)&states, (void *)&soft, (void *)&rg, (void *)&sl };
-    e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)(n * best_s)), dim3((unsigned)threads), args, demap3_smem_bytes(threads), s);
+    e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)(n * best_s)), dim3((unsigned)threads), args, smem_bytes(threads), s);
     if (lc && first > 0) (*lc)++;
   }
   return e;
@@ -1442,6 +1850,17 @@ cudaError_t launch_coarse_afc_raw(cudaStream_t s, const DeviceTables & t, const 
 {
   if (n <= 0) return cudaSuccess;
   k_coarse_afc_raw<<<fft_grid(n), FFT_THREADS, 0, s>>>(fft_nat, n, t.w2048, t.ref_arg_conj, offset_hz);
+  if (lc) (*lc)++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ingest_convert(cudaStream_t s, const void * src, int container, int msb_first, int iq_order, float inv_scaler, const float * lut,
+                                  long long n_samples, float2 * dst, unsigned long long * lc)
+{
+  if (n_samples <= 0) return cudaSuccess;
+  const long long blocks = (n_samples + 255) / 256;
+  k_ingest_convert<<<(unsigned)std::min<long long>(blocks, N_SM * 16), 256, 0, s>>>(static_cast<const unsigned char *>(src), container, msb_first, iq_order, inv_scaler, lut,
+                                                                                    n_samples, dst);
   if (lc) (*lc)++;
   return cudaGetLastError();
 }

@@ -68,6 +68,34 @@ int dabstar_phase_table(dabstar_ctx * ctx, float out_re_im[4096]);
  * uep_protection.cpp:155-196): destination index of every kept soft bit. Returns the count or <0. */
 int dabstar_protection_addresses(dabstar_ctx * ctx, int short_form, int bit_rate, int prot_level, int32_t * addr, int cap);
 
+/* ------------------------------------------------------------------------------------------------ ingest (row I1) */
+/* File-reader sample conversion to complex float, as XmlReader::readElements_IQ / _QI / _I / _Q do it
+ * (devices/filereaders/xml_filereader/xml_reader.cpp:254-372, 400-545, 547-676, 678-800; scaler = 2^(bits-1),
+ * xml_reader.cpp:43-51,256-257), RawReader (raw_files/raw_reader.cpp:66-70: u8, (v - 127.38) / 128) and WavReader
+ * (wav_files/wav_reader.cpp:164: libsndfile float read of 16-bit PCM = int16 / 32768).
+ *   int8: v / 127 (IQ order in float, the other orders through double as the reference writes them);
+ *   uint8: (v - 127.38) / 128; int16 / int24 / int32: v / 2^(bits_per_channel - 1), the scaler held in an i32 as the
+ *   reference does, so 32 bits per channel divide by -2^31; float32: as is.
+ * The decoder's native input formats (DABSTAR_FMT_U8 / I16 / CF32) are converted inside the FFT kernel; every
+ * other combination goes through this call first and is then decoded as DABSTAR_FMT_CF32.
+ * Reference reader bugs that are NOT reproduced (they read the wrong byte or a constant): uint8 with QI order
+ * indexes the table with the loop counter (xml_reader.cpp:421), int8 with Q_Only sets the real part to 127
+ * (:690), MSB int24 takes one byte from offset 4*i+4 (:309). */
+enum { DABSTAR_CONTAINER_INT8 = 0, DABSTAR_CONTAINER_UINT8 = 1, DABSTAR_CONTAINER_INT16 = 2, DABSTAR_CONTAINER_INT24 = 3,
+       DABSTAR_CONTAINER_INT32 = 4, DABSTAR_CONTAINER_FLOAT32 = 5 };
+enum { DABSTAR_ORDER_IQ = 0, DABSTAR_ORDER_QI = 1, DABSTAR_ORDER_I_ONLY = 2, DABSTAR_ORDER_Q_ONLY = 3 };
+typedef struct
+{
+  int32_t container;        /* DABSTAR_CONTAINER_* */
+  int32_t bits_per_channel; /* significant bits (scaler 2^(bits-1)); 0 = the container's width */
+  int32_t msb_first;        /* byte order of multi-byte containers: 0 LSB first, 1 MSB first */
+  int32_t iq_order;         /* DABSTAR_ORDER_* */
+} dabstar_sample_format;
+/* src: n_samples elements (pairs, or single values for the *_ONLY orders); dst: n_samples complex floats. */
+int dabstar_ingest_convert(dabstar_ctx * ctx, const void * src, const dabstar_sample_format * fmt, int64_t n_samples, float * dst, int mem);
+/* Bytes per element of `src` for a format (0 if the format is invalid). */
+int dabstar_sample_format_bytes(const dabstar_sample_format * fmt);
+
 /* ------------------------------------------------------------------------------------------------ stage taps */
 /* fftwf_execute on a 2048-point plan (main/dab_processor.cpp:63,201,276,338): n transforms,
  * unnormalised, sign -1 forward / +1 backward, natural order, complex float interleaved. */

@@ -152,6 +152,72 @@ void dabo_convert_i16(const int16_t * in, float * out, int64_t n_samples)
   for (int64_t i = 0; i < 2 * n_samples; i++) out[i] = (float)in[i] / 32768.0f;
 }
 
+/* xml_reader.cpp:43-51: scaler = 2^(bits-1) computed in i32, so 32 bits per channel give -2^31 (the x86 build wraps):
+ * int32 files come out negated, which the differential demodulation does not notice */
+static float xml_scaler(int bits)
+{
+  uint32_t r = 1;
+  while (--bits > 0) r <<= 1;
+  return (float)(int32_t)r;
+}
+
+/* one value of an XML/UFF file, xml_reader.cpp:254-372 (the same expressions repeat in the QI / I / Q readers) */
+static float xml_value(const uint8_t * p, int container, int msb, float scaler, int order)
+{
+  switch (container)
+  {
+  case 0: return order == 0 ? (float)((int8_t)p[0]) / 127.0f : (float)((int8_t)p[0] / 127.0); /* :266 float, :411,:560 double */
+  case 1: return ((float)p[0] - 127.38f) / 128.0f;                                             /* mapTable, :93-96 */
+  case 2:
+  {
+    const int16_t v = msb ? (int16_t)((p[0] << 8) | p[1]) : (int16_t)((p[1] << 8) | p[0]);     /* :286-301 */
+    return (float)v / scaler;
+  }
+  case 3:
+  {
+    int32_t v = msb ? ((p[0] << 16) | (p[1] << 8) | p[2]) : ((p[2] << 16) | (p[1] << 8) | p[0]); /* :308-341 */
+    if (v & 0x800000) v |= (int32_t)0xFF000000;
+    return (float)v / scaler;
+  }
+  case 4:
+  {
+    const uint32_t u = msb ? (((uint32_t)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]) : (((uint32_t)p[3] << 24) | (p[2] << 16) | (p[1] << 8) | p[0]);
+    return (float)(int32_t)u / scaler;                                                          /* :346-366 */
+  }
+  default:
+  {
+    union { uint32_t u; float f; } c;                                                           /* UCnv, :376-397 */
+    c.u = msb ? (((uint32_t)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]) : (((uint32_t)p[3] << 24) | (p[2] << 16) | (p[1] << 8) | p[0]);
+    return c.f;
+  }
+  }
+}
+
+int dabo_convert_samples(const uint8_t * in, int container, int bits, int msb_first, int order, int64_t n_samples, float * out)
+{
+  static const int width[6] = { 1, 1, 2, 3, 4, 4 };
+  if (container < 0 || container > 5 || order < 0 || order > 3) return -1;
+  const int b = width[container];
+  const float scaler = xml_scaler(bits > 0 ? bits : 8 * b);
+  for (int64_t i = 0; i < n_samples; i++)
+  {
+    if (order <= 1)
+    {
+      const float x = xml_value(in + (2 * i) * b, container, msb_first, scaler, order);
+      const float y = xml_value(in + (2 * i + 1) * b, container, msb_first, scaler, order);
+      out[2 * i] = order == 0 ? x : y;
+      out[2 * i + 1] = order == 0 ? y : x;
+    }
+    else
+    {
+      const float x = xml_value(in + i * b, container, msb_first, scaler, order);
+      out[2 * i] = order == 2 ? x : 0.0f;
+      out[2 * i + 1] = order == 2 ? 0.0f : x;
+    }
+  }
+  return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Energy dispersal PRBS x^9 + x^5 + 1, all-ones start (decoder/fic_decoder.cpp:59-73,
  * backend/backend.cpp:72-84).

@@ -28,6 +28,11 @@ int  dabo_fic_addresses(int32_t * addr, int cap);           /* FIC depuncture ma
 /* sample formats (raw_reader.cpp:66-70,155-158; xml_reader.cpp:254-372) */
 void dabo_convert_u8(const uint8_t * in, float * out_re_im, int64_t n_samples);
 void dabo_convert_i16(const int16_t * in, float * out_re_im, int64_t n_samples);
+/* XmlReader::readElements_IQ / _QI / _I / _Q (xml_filereader/xml_reader.cpp:254-800) for every container, byte order and
+ * IQ order. container: 0 int8, 1 uint8, 2 int16, 3 int24, 4 int32, 5 float32; order: 0 IQ, 1 QI, 2 I_Only, 3 Q_Only;
+ * bits = bitsperChannel (scaler 2^(bits-1)). The reader's wrong-byte bugs (:309, :421, :690) are not restated. Returns 0, or
+ * -1 for an unknown format. */
+int dabo_convert_samples(const uint8_t * in, int container, int bits, int msb_first, int order, int64_t n_samples, float * out_re_im);
 
 /* channel decoding */
 void dabo_viterbi(const int16_t * in, int frame_bits, uint8_t * out);

@@ -98,6 +98,17 @@ class Oracle:
             f = iq.astype(np.float32) / np.float32(32768.0)
         return np.ascontiguousarray(f).view(np.complex64).reshape(-1)
 
+    def convert_samples(self, raw: np.ndarray, container: int, bits: int, msb_first: int, order: int, n_samples: int) -> np.ndarray:
+        """XmlReader::readElements_* (xml_reader.cpp:254-800); only in the C restatement (the reader needs Qt)."""
+        raw = np.ascontiguousarray(raw, np.uint8)
+        out = np.zeros(n_samples, np.complex64)
+        fn = self.f("convert_samples")
+        fn.restype = ctypes.c_int
+        r = fn(raw.ctypes.data_as(ctypes.c_void_p), int(container), int(bits), int(msb_first), int(order), ctypes.c_int64(n_samples),
+               out.ctypes.data_as(ctypes.c_void_p))
+        assert r == 0
+        return out
+
     # ---- channel decoding
     def viterbi(self, soft: np.ndarray, frame_bits: int) -> np.ndarray:
         soft = np.ascontiguousarray(soft, np.int16)

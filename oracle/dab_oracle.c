@@ -847,6 +847,7 @@ typedef struct
   msc_ch * ch;
   int n_ch;
   int16_t cif[CIF_BITS];
+  void * eti;                 /* eti_t when cfg.eti_path is set */
 
   frame_rec * frames;
   int n_frames, cap_frames;
@@ -920,6 +921,143 @@ static frame_rec * new_frame(chain_t * c)
   return f;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * ETI-NI generator (eti_handler/eti_generator.cpp:63-204 process_block, :207-308 _init_eti, :330-412 _process_cif /
+ * _process_sub_channel). Whole-CIF time de-interleaver with the same map as Backend, but emission starts one CIF
+ * earlier and the start-up bookkeeping (`amount`, `Minor`, `index_Out`) drops the 16th CIF from the history; the CIF
+ * counter comes from the FIB decoder (cif_hi / cif_lo of the configuration, the harness' stub returns 0, 0).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct
+{
+  int running, index_out, amount, minor, cif_hi, cif_lo;
+  int16_t cif_in[CIF_BITS];
+  int16_t (*cif_vec)[CIF_BITS];   /* 16 CIFs, zero at start (file-scope statics in the reference, eti_generator.cpp:9-24) */
+  int16_t * temp;
+  uint8_t fib_vec[16][96];
+  protection_t * prot[64];
+  uint8_t * desc[64];
+  uint8_t * out;
+  int64_t n, cap;
+} eti_t;
+
+static eti_t * eti_new(void)
+{
+  eti_t * e = (eti_t *)calloc(1, sizeof(*e));
+  e->cif_vec = (int16_t (*)[CIF_BITS])calloc(16, sizeof(int16_t) * CIF_BITS);
+  e->temp = (int16_t *)calloc(CIF_BITS, sizeof(int16_t));
+  e->cif_hi = e->cif_lo = e->minor = -1;
+  return e;
+}
+
+static void eti_free(eti_t * e)
+{
+  if (!e) return;
+  for (int i = 0; i < 64; i++) { if (e->prot[i]) protection_free(e->prot[i]); free(e->desc[i]); }
+  free(e->cif_vec); free(e->temp); free(e->out); free(e);
+}
+
+/* eti_generator.cpp:207-308 */
+static int eti_init_frame(uint8_t * eti, int cif_hi, int cif_lo, int minor, const int32_t * subch, int n_subch)
+{
+  int fill = 0;
+  cif_lo += minor;
+  if (cif_lo >= 250) { cif_lo %= 250; cif_hi++; }
+  if (cif_hi >= 20) cif_hi = 20;
+  eti[fill++] = 0xFF;                                         /* ERR: error level 0 */
+  if (cif_lo & 1) { eti[fill++] = 0xf8; eti[fill++] = 0xc5; eti[fill++] = 0x49; }
+  else { eti[fill++] = 0x07; eti[fill++] = 0x3a; eti[fill++] = 0xb6; }
+  eti[fill++] = (uint8_t)cif_lo;                              /* FCT */
+  int nst = 0, fl = 0;
+  for (int i = 0; i < n_subch; i++) { nst++; fl += (subch[7 * i + 5] * 3) / 4; }
+  fl += nst + 1 + 24;                                         /* STC + EOH + FIC (mode I), in words */
+  eti[fill++] = (uint8_t)((1 << 7) | nst);                    /* FICF | NST */
+  const int fp = ((cif_hi * 250) + cif_lo) % 8;
+  eti[fill++] = (uint8_t)((fp << 5) | (0x01 << 3) | ((fl & 0x700) >> 8));
+  eti[fill++] = (uint8_t)(fl & 0xff);
+  for (int i = 0; i < n_subch; i++)
+  {
+    const int32_t * sc = subch + 7 * i;
+    const int scid = sc[0], sad = sc[1];
+    const int tpl = sc[3] ? (0x10 | (sc[4] - 1)) : (0x20 | sc[4]);
+    const int stl = sc[5] * 3 / 8;
+    eti[fill++] = (uint8_t)((scid << 2) | ((sad & 0x300) >> 8));
+    eti[fill++] = (uint8_t)(sad & 0xFF);
+    eti[fill++] = (uint8_t)((tpl << 2) | ((stl & 0x300) >> 8));
+    eti[fill++] = (uint8_t)(stl & 0xFF);
+  }
+  eti[fill++] = 0xFF; eti[fill++] = 0xFF;                     /* MNSC */
+  const uint16_t hcrc = dabo_calc_crc(&eti[4], fill - 4);
+  eti[fill++] = (uint8_t)(hcrc >> 8);
+  eti[fill++] = (uint8_t)(hcrc & 0xff);
+  return fill;
+}
+
+/* one OFDM symbol of soft bits, eti_generator.cpp:90-204 */
+static void eti_block(eti_t * e, const dabo_chain_cfg * cfg, const uint8_t * fib_bits, const int16_t * soft, int sym)
+{
+  if (!e->running && sym == 1) e->running = 1;
+  if (!e->running || sym < 4) return;
+  if (sym == 4)
+  {
+    for (int i = 0; i < 4; i++)
+      for (int j = 0; j < 96; j++)
+      {
+        unsigned v = 0;
+        for (int k = 0; k < 8; k++) v = (v << 1) | (fib_bits[i * 768 + 8 * j + k] & 1u);
+        e->fib_vec[(e->index_out + i) & 15][j] = (uint8_t)v;
+      }
+    e->minor = 0;
+    e->cif_hi = cfg->eti_cif_hi;
+    e->cif_lo = cfg->eti_cif_lo;
+  }
+  const int blk = (sym - 4) % 18;
+  memcpy(&e->cif_in[blk * BITS_PER_SYM], soft, sizeof(int16_t) * BITS_PER_SYM);
+  if (blk != 17) return;
+  for (int i = 0; i < CIF_BITS; i++)
+  {
+    e->temp[i] = e->cif_vec[(e->index_out + TIME_MAP[i & 15]) & 15][i];
+    e->cif_vec[e->index_out & 15][i] = e->cif_in[i];
+  }
+  if (e->amount < 15) { e->amount++; e->index_out = (e->index_out + 1) & 15; e->minor = -1; return; }
+  if (e->cif_hi < 0 || e->cif_lo < 0) { e->minor = -1; return; }
+  if (e->minor < 0) return;
+  uint8_t v[6144];
+  int off = eti_init_frame(v, e->cif_hi, e->cif_lo, e->minor, cfg->subch, cfg->n_subch);
+  const int base = off;
+  memcpy(&v[off], e->fib_vec[e->index_out], 96);
+  off += 96;
+  for (int i = 0; i < cfg->n_subch; i++)
+  {
+    const int32_t * sc = cfg->subch + 7 * i;
+    const int id = sc[0] & 63, nb = 24 * sc[5];
+    if (!e->prot[id])
+    {
+      e->prot[id] = protection_new(sc[3], sc[5], sc[4]);
+      e->desc[id] = (uint8_t *)malloc((size_t)nb);
+      dabo_prbs(e->desc[id], nb);
+    }
+    uint8_t * bits = (uint8_t *)calloc((size_t)nb, 1);
+    protection_run(e->prot[id], &e->temp[sc[1] * 64], bits);
+    for (int j = 0; j < nb / 8; j++)
+    {
+      unsigned t = 0;
+      for (int k = 0; k < 8; k++) t = (t << 1) | ((bits[8 * j + k] ^ e->desc[id][8 * j + k]) & 1u);
+      v[off++] = (uint8_t)t;
+    }
+    free(bits);
+  }
+  const uint16_t crc = dabo_calc_crc(&v[base], off - base);
+  v[off++] = (uint8_t)(crc >> 8); v[off++] = (uint8_t)(crc & 0xff);
+  v[off++] = 0xFF; v[off++] = 0xFF;                           /* RFU */
+  v[off++] = 0xFF; v[off++] = 0xFF; v[off++] = 0xFF; v[off++] = 0xFF; /* TIST unused */
+  memset(&v[off], 0x55, (size_t)(6144 - off));
+  if (e->n + 6144 > e->cap) { e->cap = e->cap ? 2 * e->cap : 6144 * 64; e->out = (uint8_t *)realloc(e->out, (size_t)e->cap); }
+  memcpy(e->out + e->n, v, 6144);
+  e->n += 6144;
+  e->index_out = (e->index_out + 1) & 15;
+  e->minor++;
+}
+
 static void msc_block(chain_t * c, const int16_t * soft, int sym, int frames_done)
 {
   const int blk = (sym - 4) % 18;
@@ -956,6 +1094,7 @@ void * dabo_chain_run(const float * iq, int64_t n_samples, const dabo_chain_cfg 
   }
   c->ofdm = (ofdm_t *)dabo_ofdm_new(cfg->soft_bit_type);
   c->fic = (fic_t *)dabo_fic_new();
+  if (cfg->eti_path != NULL) c->eti = eti_new();
   c->pref = (phaseref_t *)dabo_phaseref_new();
   c->n_ch = cfg->scan_mode ? 0 : cfg->n_subch;
   c->ch = (msc_ch *)calloc((size_t)(c->n_ch > 0 ? c->n_ch : 1), sizeof(msc_ch));
@@ -1035,6 +1174,7 @@ void * dabo_chain_run(const float * iq, int64_t n_samples, const dabo_chain_cfg 
         if (f->soft) memcpy(&f->soft[(size_t)(sym - 1) * BITS_PER_SYM], bits, sizeof(bits));
         if (sym <= 3) dabo_fic_process_block(c->fic, bits, sym);
         else if (!cfg->scan_mode) msc_block(c, bits, sym, frames_done);
+        if (c->eti) eti_block((eti_t *)c->eti, cfg, c->fic->bits, bits, sym); /* dab_processor.cpp:352-355 */
       }
       if (cut) { c->n_frames--; break; }
       phase_cp = clampf_sym(atan2f(corr.im, corr.re), 20.0f * RAD_PER_DEG_F);
@@ -1065,6 +1205,11 @@ void * dabo_chain_run(const float * iq, int64_t n_samples, const dabo_chain_cfg 
   }
   clock_gettime(CLOCK_MONOTONIC, &t1);
   c->seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  if (c->eti && cfg->eti_path[0] != 0)
+  {
+    FILE * f = fopen(cfg->eti_path, "wb");
+    if (f) { fwrite(((eti_t *)c->eti)->out, 1, (size_t)((eti_t *)c->eti)->n, f); fclose(f); }
+  }
   return c;
 }
 
@@ -1075,7 +1220,17 @@ void dabo_chain_free(void * h)
   for (int i = 0; i < c->n_ch; i++) { if (c->ch[i].be) dabo_backend_free(c->ch[i].be); free(c->ch[i].out); }
   free(c->frames); free(c->ch); free(c->osc);
   dabo_ofdm_free(c->ofdm); dabo_fic_free(c->fic); dabo_phaseref_free(c->pref);
+  eti_free((eti_t *)c->eti);
   free(c);
+}
+int64_t dabo_chain_eti_size(void * h) { chain_t * c = (chain_t *)h; return c->eti ? ((eti_t *)c->eti)->n : 0; }
+int64_t dabo_chain_eti_copy(void * h, uint8_t * out, int64_t cap)
+{
+  chain_t * c = (chain_t *)h;
+  if (!c->eti) return 0;
+  const int64_t n = ((eti_t *)c->eti)->n < cap ? ((eti_t *)c->eti)->n : cap;
+  memcpy(out, ((eti_t *)c->eti)->out, (size_t)n);
+  return n;
 }
 int dabo_chain_n_frames(void * h) { return ((chain_t *)h)->n_frames; }
 void dabo_chain_frame_info(void * h, int frame, dabo_frame_info * out) { *out = ((chain_t *)h)->frames[frame].info; }

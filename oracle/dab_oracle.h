@@ -76,7 +76,8 @@ typedef struct
   int   tap_fft;
   int   n_subch;
   const int32_t * subch;     /* n_subch x 7: subChId,startCU,sizeCU,shortForm,protLevel,bitRate,startFrame */
-  const char * eti_path;     /* ignored by the restatement (ETI framing is out of scope) */
+  const char * eti_path;     /* NULL = ETI generator off; else the ETI-NI stream is also written to this file (as dabref does) */
+  int   eti_cif_hi, eti_cif_lo; /* IFibDecoder::get_cif_count(hi, lo) as sampled at symbol 4 of every frame (the dabref stub: 0, 0) */
 } dabo_chain_cfg;
 
 typedef struct
@@ -104,6 +105,9 @@ int     dabo_chain_fft(void * h, int frame, float * out);
 int     dabo_chain_n_good_fibs(void * h);
 int64_t dabo_chain_msc_size(void * h, int sub_ch_id);
 int64_t dabo_chain_msc_copy(void * h, int sub_ch_id, uint8_t * out, int64_t cap);
+/* ETI-NI frames (6144 bytes each) produced by the run (eti_generator.cpp:90-204); only in the restatement, dabref writes the file */
+int64_t dabo_chain_eti_size(void * h);
+int64_t dabo_chain_eti_copy(void * h, uint8_t * out, int64_t cap);
 void    dabo_chain_counters(void * h, int64_t out[8]);
 double  dabo_chain_seconds(void * h);
 

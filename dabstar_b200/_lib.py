@@ -50,6 +50,7 @@ EXPORTS = [
     ("dabstar_decoder_run", ctypes.c_int), ("dabstar_decoder_n_frames", ctypes.c_int), ("dabstar_decoder_frame_info", ctypes.c_int),
     ("dabstar_decoder_fib_bits", ctypes.c_int), ("dabstar_decoder_soft_bits", ctypes.c_int),
     ("dabstar_decoder_msc_size", ctypes.c_int64), ("dabstar_decoder_msc_copy", ctypes.c_int64),
+    ("dabstar_decoder_enable_eti", ctypes.c_int), ("dabstar_decoder_eti_size", ctypes.c_int64), ("dabstar_decoder_eti_copy", ctypes.c_int64),
     ("dabstar_decoder_counters", ctypes.c_int), ("dabstar_decoder_last_ms", ctypes.c_double),
     ("dabstar_decoder_stage_ms", ctypes.c_int),
 ]

@@ -339,6 +339,22 @@ class DabProcessor:
         self.ctx.check(self.ctx.lib.dabstar_decoder_set_subchannels(self.h, recording, arr, len(subch)), "dabstar_decoder_set_subchannels")
         self.subch[recording] = list(subch)
 
+    def start_eti_generator(self, recording: int, cif_count_hi: int = 0, cif_count_lo: int = 0):
+        """DabProcessor::start_eti_generator (dab_processor.cpp:529-546): the next run also produces the ETI(NI) stream of
+        this recording with every sub-channel set through set_audio_channel; see eti()."""
+        self.ctx.check(self.ctx.lib.dabstar_decoder_enable_eti(self.h, recording, 1, cif_count_hi, cif_count_lo), "dabstar_decoder_enable_eti")
+
+    def stop_eti_generator(self, recording: int):
+        self.ctx.check(self.ctx.lib.dabstar_decoder_enable_eti(self.h, recording, 0, 0, 0), "dabstar_decoder_enable_eti")
+
+    def eti(self, recording: int) -> np.ndarray:
+        """ETI(NI) frames of the last run, uint8[n_frames, 6144] (what EtiGenerator writes to its file)."""
+        n = int(self.ctx.check(self.ctx.lib.dabstar_decoder_eti_size(self.h, recording), "dabstar_decoder_eti_size"))
+        buf = np.zeros(n, np.uint8)
+        if n:
+            self.ctx.lib.dabstar_decoder_eti_copy(self.h, recording, _ptr(buf), ctypes.c_int64(n))
+        return buf.reshape(-1, 6144)
+
     def run_ptrs(self, ptrs: list[int], n_samples: list[int], mem: int) -> float:
         """Decode complete recordings given raw pointers. Returns the device time in ms (CUDA events)."""
         p = (c_p * self.n)(*[c_p(x) for x in ptrs])

@@ -711,6 +711,9 @@ struct Recording
   std::vector<dabstar_frame_info> frames;
   std::vector<uint8_t> crc_ok; // 12 per frame
   std::vector<MscOut> msc;
+  bool eti_on = false;       // EtiGenerator running from the first frame of the run (DabProcessor::start_eti_generator)
+  int eti_cif_hi = 0, eti_cif_lo = 0; // IFibDecoder::get_cif_count(hi, lo) as the generator samples it at symbol 4
+  std::vector<uint8_t> eti;  // ETI-NI frames of the last run, 6144 bytes each
   long long cnt_good_fibs = 0, cnt_sync_ok = 0, cnt_sync_fail = 0, cnt_windows = 0, cnt_cut = 0, cnt_heavy = 0;
   // window scratch
   int w_first_desc = 0, w_frames = 0;
@@ -732,7 +735,7 @@ struct dabstar_decoder
   DevBuf d_X;           // window: [frames][77][1536] float2
   DevBuf d_states;      // OfdmStateDev[n_rec]
   DevBuf d_snap;        // snapshot of d_states
-  DevBuf d_desc, d_work, d_cp, d_start, d_coarse, d_dipw, d_dipr, d_jobs, d_mscbits;
+  DevBuf d_desc, d_work, d_cp, d_start, d_coarse, d_dipw, d_dipr, d_jobs, d_mscbits, d_etibits, d_etipacked;
   HostBuf h_fib;
   std::vector<int16_t> h_soft_one;
   long long total_slots = 0;
@@ -819,8 +822,80 @@ extern "C" int dabstar_decoder_set_subchannels(dabstar_decoder * dec, int record
   return 0;
 }
 
+extern "C" int dabstar_decoder_enable_eti(dabstar_decoder * dec, int recording, int enable, int cif_count_hi, int cif_count_lo)
+{
+  if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  if (enable && (cif_count_hi < 0 || cif_count_lo < 0)) return dec->ctx->fail(DABSTAR_E_INVALID, "negative CIF count"); // the generator waits for a valid count (eti_generator.cpp:158-162)
+  Recording & r = dec->recs[recording];
+  r.eti_on = enable != 0;
+  r.eti_cif_hi = cif_count_hi;
+  r.eti_cif_lo = cif_count_lo;
+  return 0;
+}
+extern "C" int64_t dabstar_decoder_eti_size(const dabstar_decoder * dec, int recording)
+{
+  if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  return (int64_t)dec->recs[recording].eti.size();
+}
+extern "C" int64_t dabstar_decoder_eti_copy(const dabstar_decoder * dec, int recording, uint8_t * out, int64_t cap)
+{
+  if (!dec || !out || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  const std::vector<uint8_t> & e = dec->recs[recording].eti;
+  const int64_t n = std::min<int64_t>(cap, (int64_t)e.size());
+  if (n > 0) memcpy(out, e.data(), (size_t)n);
+  return n;
+}
+
 namespace
 {
+// ---- ETI-NI framing (eti_handler/eti_generator.cpp:169-199 frame tail, :207-308 _init_eti)
+// CRC of ETS 300 799: x^16 + x^12 + x^5 + 1, register preset to all ones, remainder complemented (backend/crc.cpp:75-96)
+uint16_t eti_crc(const uint8_t * p, int n)
+{
+  unsigned reg = 0xffffu;
+  for (int i = 0; i < n; i++)
+  {
+    reg ^= (unsigned)p[i] << 8;
+    for (int b = 0; b < 8; b++) reg = (reg & 0x8000u) ? ((reg << 1) ^ 0x1021u) : (reg << 1);
+    reg &= 0xffffu;
+  }
+  return (uint16_t)(~reg & 0xffffu);
+}
+
+// Header of one ETI(NI) frame: SYNC, FC, one STC per stream, EOH. Returns the offset of the MST field.
+int eti_header(uint8_t * f, int cif_hi, int cif_lo, int minor, const std::vector<MscOut> & streams)
+{
+  int o = 0;
+  cif_lo += minor;
+  if (cif_lo >= 250) { cif_lo %= 250; cif_hi++; }
+  if (cif_hi >= 20) cif_hi = 20;
+  f[o++] = 0xFF;                                                       // ERR
+  static const uint8_t fsync[2][3] = { { 0x07, 0x3a, 0xb6 }, { 0xf8, 0xc5, 0x49 } };
+  for (int i = 0; i < 3; i++) f[o++] = fsync[cif_lo & 1][i];
+  f[o++] = (uint8_t)cif_lo;                                            // FCT
+  const int nst = (int)streams.size();
+  int fl = nst + 1 + 24;                                               // STC + EOH + FIC in 32-bit words (mode I)
+  for (const MscOut & m : streams) fl += (m.sc.bit_rate * 3) / 4;
+  f[o++] = (uint8_t)(0x80 | nst);                                      // FICF, NST
+  const int fp = (cif_hi * 250 + cif_lo) % 8;
+  f[o++] = (uint8_t)((fp << 5) | (0x01 << 3) | ((fl & 0x700) >> 8));   // FP, MID = mode I, FL
+  f[o++] = (uint8_t)(fl & 0xff);
+  for (const MscOut & m : streams)
+  {
+    const int tpl = m.sc.short_form ? (0x10 | (m.sc.prot_level - 1)) : (0x20 | m.sc.prot_level);
+    const int stl = m.sc.bit_rate * 3 / 8;
+    f[o++] = (uint8_t)((m.sc.sub_ch_id << 2) | ((m.sc.start_cu & 0x300) >> 8));
+    f[o++] = (uint8_t)(m.sc.start_cu & 0xff);
+    f[o++] = (uint8_t)((tpl << 2) | ((stl & 0x300) >> 8));
+    f[o++] = (uint8_t)(stl & 0xff);
+  }
+  f[o++] = 0xFF; f[o++] = 0xFF;                                        // MNSC
+  const uint16_t hcrc = eti_crc(f + 4, o - 4);
+  f[o++] = (uint8_t)(hcrc >> 8);
+  f[o++] = (uint8_t)(hcrc & 0xff);
+  return o;
+}
+
 // Host restatement of the per-frame control bookkeeping (dab_processor.cpp:191-265, 389-414).
 struct FrameCtl
 {
@@ -1006,8 +1081,13 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
   {
     Recording & R = dec->recs[r];
     std::vector<MscOut> keep = std::move(R.msc);
+    const bool eti_on = R.eti_on;
+    const int eti_hi = R.eti_cif_hi, eti_lo = R.eti_cif_lo;
     R = Recording();
     R.msc = std::move(keep);
+    R.eti_on = eti_on;
+    R.eti_cif_hi = eti_hi;
+    R.eti_cif_lo = eti_lo;
     for (auto & m : R.msc) m.bits.clear();
     R.d_iq = rin[r].iq;
     R.n = rin[r].n;
@@ -1571,18 +1651,113 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
         CK(cudaMemcpyAsync(dec->recs[o.rec].msc[o.ch].bits.data(), dec->d_mscbits.as<uint8_t>() + o.off, (size_t)o.len, cudaMemcpyDeviceToHost, st));
     }
   }
+  // ================= ETI: every sub-channel of every CIF through EtiGenerator's own de-interleaver (eti_generator.cpp:90-204)
+  // The generator's ring holds 16 whole CIFs and, unlike Backend, emits with its 17th CIF but loses the 16th from the
+  // history while `Minor` is still -1 (the CIF is stored, index_Out does not advance, the next CIF overwrites it). Seen
+  // from ETI frame n (n = 0 is CIF 16 of the run) de-interleaver row m therefore reads entry n - 1 + m of the CIF sequence
+  // 0..14, 16, 17, ...; entry -1 (row 0 of frame 0) is the slot about to be overwritten, which still holds CIF 15.
+  struct EtiRef { int rec; long long bit_off; int n_out; };
+  std::vector<EtiRef> eti_refs;
+  {
+    std::map<int, std::vector<VitJob>> by_steps;
+    long long bits_total = 0;
+    for (int r = 0; r < n_rec; r++)
+    {
+      Recording & R = dec->recs[r];
+      R.eti.clear();
+      if (!R.eti_on || R.msc.empty()) continue;
+      const int n_cifs = 4 * R.n_slots + std::max(0, (R.partial_syms - 3) / 18);
+      const int n_out = std::max(0, n_cifs - 16);
+      if (n_out == 0) continue;
+      eti_refs.push_back({ r, bits_total, n_out });
+      for (int n = 0; n < n_out; n++)
+        for (MscOut & m : R.msc)
+        {
+          const VitProfile & p = ctx->profiles[m.profile];
+          VitJob j;
+          memset(&j, 0, sizeof(j));
+          j.src = R.slot_base * FRAME_SOFT;
+          j.out = bits_total;
+          j.profile = m.profile;
+          j.src_mode = VIT_SRC_TIME_DEINTERLEAVE;
+          j.flags = VIT_FLAG_PRBS;
+          j.cif_first = n - 1;
+          j.row_mask = 0xffff;
+          j.frag_off = m.sc.start_cu * 64;
+          j.skip_plus1 = 15 + 1;
+          by_steps[p.n_bits + 6].push_back(j);
+          bits_total += p.n_bits;
+        }
+    }
+    if (bits_total > 0)
+    {
+      CK(dec->d_etibits.reserve((size_t)bits_total));
+      CK(dec->d_etipacked.reserve((size_t)(bits_total / 8)));
+      for (auto & kv : by_steps)
+      {
+        dec->span_begin(ST_MSC);
+        if (int e = run_viterbi_jobs(ctx, kv.second, kv.first, dec->d_soft.as<int16_t>(), dec->d_etibits.as<uint8_t>(), nullptr, nullptr, dec->d_jobs)) return e;
+        dec->span_end();
+        SYNC(); // d_jobs is reused by the next group
+      }
+      dec->span_begin(ST_MSC);
+      CK(launch_pack_bits(st, dec->d_etibits.as<uint8_t>(), dec->d_etipacked.as<uint8_t>(), bits_total / 8, &ctx->launches));
+      dec->span_end();
+    }
+  }
   tr("rounds done");
   // FIB bits of all accepted frames
   CK(dec->h_fib.reserve((size_t)dec->total_slots * 3072));
   for (int r = 0; r < n_rec; r++)
   {
     Recording & R = dec->recs[r];
-    if (R.n_slots > 0)
-      CK(cudaMemcpyAsync(dec->h_fib.as<uint8_t>() + (size_t)R.slot_base * 3072, dec->d_fib.as<uint8_t>() + (size_t)R.slot_base * 3072, (size_t)R.n_slots * 3072, cudaMemcpyDeviceToHost, st));
+    const int fib_slots = std::min(R.slot_cap, R.n_slots + ((R.eti_on && R.partial_syms > 3) ? 1 : 0)); // the generator also frames the CIFs of a cut last frame
+    if (fib_slots > 0)
+      CK(cudaMemcpyAsync(dec->h_fib.as<uint8_t>() + (size_t)R.slot_base * 3072, dec->d_fib.as<uint8_t>() + (size_t)R.slot_base * 3072, (size_t)fib_slots * 3072, cudaMemcpyDeviceToHost, st));
+  }
+  std::vector<uint8_t> eti_packed;
+  if (!eti_refs.empty())
+  {
+    const EtiRef & last = eti_refs.back();
+    long long bits_total = last.bit_off;
+    for (const MscOut & m : dec->recs[last.rec].msc) bits_total += (long long)last.n_out * 24 * m.sc.bit_rate;
+    eti_packed.resize((size_t)(bits_total / 8));
+    CK(cudaMemcpyAsync(eti_packed.data(), dec->d_etipacked.p, eti_packed.size(), cudaMemcpyDeviceToHost, st));
   }
   CK(cudaEventRecord(dec->ev1, st));
   SYNC();
   if (trace) fprintf(stderr, "[dabstar] run done t=%.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_run0).count());
+  // ETI(NI) frames: header, FIC of the frame the CIF belongs to, the streams, EOF and TIST, padding (eti_generator.cpp:163-199)
+  for (const EtiRef & er : eti_refs)
+  {
+    Recording & R = dec->recs[er.rec];
+    R.eti.assign((size_t)er.n_out * 6144, 0x55);
+    const uint8_t * src = eti_packed.data() + er.bit_off / 8;
+    for (int n = 0; n < er.n_out; n++)
+    {
+      uint8_t * f = R.eti.data() + (size_t)n * 6144;
+      int o = eti_header(f, R.eti_cif_hi, R.eti_cif_lo, n & 3, R.msc);
+      const int base = o;
+      // fibVector: the four FICs of the frame as the FIC decoder left them at symbol 4, whether their CRCs passed or not
+      const uint8_t * fib = dec->h_fib.as<uint8_t>() + ((size_t)R.slot_base + 4 + (size_t)(n >> 2)) * 3072 + (size_t)(n & 3) * 768;
+      for (int j = 0; j < 96; j++)
+      {
+        unsigned v = 0;
+        for (int k = 0; k < 8; k++) v = (v << 1) | (fib[8 * j + k] & 1u);
+        f[o++] = (uint8_t)v;
+      }
+      for (const MscOut & m : R.msc)
+      {
+        const int nb = 3 * m.sc.bit_rate;
+        memcpy(f + o, src, (size_t)nb);
+        src += nb;
+        o += nb;
+      }
+      const uint16_t crc = eti_crc(f + base, o - base);
+      f[o++] = (uint8_t)(crc >> 8); f[o++] = (uint8_t)(crc & 0xff);
+      for (int i = 0; i < 6; i++) f[o++] = 0xFF;                       // RFU, TIST (time stamp not used)
+    }
+  }
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, dec->ev0, dec->ev1));
   dec->last_ms = ms;

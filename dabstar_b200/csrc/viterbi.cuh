@@ -54,8 +54,21 @@ struct VitJob
   int row_mask;        // bit m set: the CIF of row m exists (otherwise the de-interleaver memory is still zero)
   int frag_off;        // startCU * 64
   int aux;             // FIC: index of the FIC block (crc_ok[3*aux..], ber[2*aux..])
-  int pad;
+  int skip_plus1;      // TIME_DEINTERLEAVE, EtiGenerator only: CIF (skip_plus1 - 1) is missing from the de-interleaver history
+                       // (rows at or after it read one CIF later, row index -1 reads the dropped CIF itself); 0 = Backend
 };
+
+// CIF read by de-interleaver row m of a job (see VitJob::skip_plus1 and engine.cu, ETI section)
+__host__ __device__ inline int vit_row_cif(int cif_first, int skip_plus1, int m)
+{
+  int cif = cif_first + m;
+  if (skip_plus1 > 0)
+  {
+    const int skip = skip_plus1 - 1;
+    cif = cif < 0 ? skip : (cif >= skip ? cif + 1 : cif);
+  }
+  return cif;
+}
 
 // Time de-interleaver row of fragment bit i (backend/backend.cpp:129): out_r[i] = in_{r-16+map[i&15]}[i]
 __host__ __device__ inline int time_map(int i)

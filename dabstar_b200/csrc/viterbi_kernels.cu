@@ -41,7 +41,7 @@ __device__ __forceinline__ bool load_job(const VitJob * __restrict__ jobs, const
     job.flags = VIT_FLAG_PRBS | VIT_FLAG_FIC;
     job.cif_first = job.row_mask = job.frag_off = 0;
     job.aux = 4 * fd.slot + b;
-    job.pad = 0;
+    job.skip_plus1 = 0;
   }
   else job = jobs[j];
   return true;
@@ -53,7 +53,7 @@ __device__ __forceinline__ int job_soft(const VitJob & job, const int16_t * __re
   if (job.src_mode == VIT_SRC_LINEAR) return soft[job.src + idx];
   const int m = time_map(idx);
   if (!((job.row_mask >> m) & 1)) return 0;
-  return soft[job.src + cif_offset(job.cif_first + m) + job.frag_off + idx];
+  return soft[job.src + cif_offset(vit_row_cif(job.cif_first, job.skip_plus1, m)) + job.frag_off + idx];
 }
 
 // Eight consecutive energy-dispersal bits as a byte, first bit most significant: bit 7 - j = prbs[i + j] (i a multiple of 8)
@@ -424,7 +424,26 @@ __global__ void __launch_bounds__(POST_WARPS * 32) k_fic_post(const VitJob * __r
     crc_ok[3 * job.aux + lane] = reg == 0;
   }
 }
+// EtiGenerator::_process_sub_channel storage loop (eti_generator.cpp:403-411): 8 decoded bits (one per byte) -> one byte, first bit most significant
+__global__ void __launch_bounds__(256) k_pack_bits(const uint8_t * __restrict__ bits, uint8_t * __restrict__ out, long long n_bytes)
+{
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_bytes; i += (long long)gridDim.x * blockDim.x)
+  {
+    const uint2 w = *reinterpret_cast<const uint2 *>(bits + 8 * i);
+    // bytes b0..b3 of a word times 0x08040201: the top byte of the product is 8 b0 + 4 b1 + 2 b2 + b3
+    out[i] = (uint8_t)(((((w.x & 0x01010101u) * 0x08040201u) >> 24) << 4) | (((w.y & 0x01010101u) * 0x08040201u) >> 24));
+  }
+}
 } // namespace
+
+cudaError_t launch_pack_bits(cudaStream_t stream, const uint8_t * bits, uint8_t * out, long long n_bytes, unsigned long long * launch_counter)
+{
+  if (n_bytes <= 0) return cudaSuccess;
+  const long long blocks = (n_bytes + 255) / 256;
+  k_pack_bits<<<(unsigned)(blocks < N_SM * 16 ? blocks : N_SM * 16), 256, 0, stream>>>(bits, out, n_bytes);
+  if (launch_counter) (*launch_counter)++;
+  return cudaGetLastError();
+}
 
 int viterbi_smem_bytes(int max_steps, int warps)
 {

@@ -203,6 +203,14 @@ int     dabstar_decoder_soft_bits(const dabstar_decoder * dec, int recording, in
 int64_t dabstar_decoder_msc_size(const dabstar_decoder * dec, int recording, int sub_ch_id);
 /* FrameProcessor::add_to_frame payloads (backend/frame_processor.h:43), concatenated, one bit per byte */
 int64_t dabstar_decoder_msc_copy(const dabstar_decoder * dec, int recording, int sub_ch_id, uint8_t * out, int64_t cap);
+/* EtiGenerator (eti_handler/eti_generator.h:56-66: start_eti_generator before run / process_block per symbol): every
+ * sub-channel set with dabstar_decoder_set_subchannels is decoded for every CIF through the generator's own whole-CIF
+ * de-interleaver (first frame with its 17th CIF; its start-up bookkeeping, which loses the 16th CIF, is reproduced) and
+ * framed as ETI(NI), 6144 bytes per CIF (eti_generator.cpp:163-199, 207-308). cif_count_hi / cif_count_lo are what
+ * IFibDecoder::get_cif_count(hi, lo) returns (FIG 0/0); they are constant over the run here. Independent of scan_mode. */
+int     dabstar_decoder_enable_eti(dabstar_decoder * dec, int recording, int enable, int cif_count_hi, int cif_count_lo);
+int64_t dabstar_decoder_eti_size(const dabstar_decoder * dec, int recording);
+int64_t dabstar_decoder_eti_copy(const dabstar_decoder * dec, int recording, uint8_t * out, int64_t cap);
 /* out[0] good FIBs, [1] time-sync established count, [2] time-sync failures, [3] samples consumed,
  * [4] speculation windows run, [5] windows cut short by verification, [6] frames decoded,
  * [7] frames sent through the FFT/demap/FIC pass (exceeds [6] by replayed and partial frames) */

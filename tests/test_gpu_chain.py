@@ -148,3 +148,31 @@ def test_chunked_host_upload_matches_device_resident(ctx):
         for a, b in zip(res, want):
             _same_result(a, b)
     assert all(w.n_frames >= 8 for w in want)
+
+
+def test_eti_generator_stream(ctx, oracle, viterbi_path):
+    """Row E: the ETI(NI) stream (every sub-channel of every CIF through EtiGenerator's de-interleaver, ETS 300 799 framing)
+    is byte for byte what the reference's generator writes, incl. its start-up and a recording that ends inside a frame."""
+    sc = [synth.SubChannel(3, 100, 54, 0, 2, 72), synth.SubChannel(5, 300, 84, 1, 4, 128), synth.SubChannel(9, 400, 30, 0, 7, 64)]
+    rec = synth.generate(10, seed=31, snr_db=13.0, subch=sc, fmt=synth.FMT_U8)
+    iq = rec.iq[:rec.iq.shape[0] - 120000]  # the last frame is cut after its second CIF
+    want = oracle.chain_run(oracle.to_cf32(iq), synth.subch_table(sc), 3, eti=True)
+    dp = api.DabProcessor(1, input_format=api.FMT_U8, ctx=ctx)
+    dp.set_audio_channel(0, sc)
+    dp.start_eti_generator(0)
+    dp.run([iq])
+    got = dp.eti(0)
+    assert want.eti.size > 0 and got.shape == (want.eti.size // 6144, 6144)
+    assert np.array_equal(got, want.eti.reshape(-1, 6144))
+    # the Backend outputs of the same run are unaffected
+    for s in sc:
+        assert np.array_equal(dp.result(0).msc[s.sub_ch_id], want.msc[s.sub_ch_id])
+    # scan mode: no Backend output, the ETI stream is the same (dab_processor.cpp:352-360)
+    dp2 = api.DabProcessor(1, input_format=api.FMT_U8, scan_mode=True, ctx=ctx)
+    dp2.set_audio_channel(0, sc)
+    dp2.start_eti_generator(0)
+    dp2.run([iq])
+    assert np.array_equal(dp2.eti(0), got)
+    dp2.stop_eti_generator(0)
+    dp2.run([iq])
+    assert dp2.eti(0).shape[0] == 0

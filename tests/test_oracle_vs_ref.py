@@ -69,3 +69,15 @@ def test_whole_chain(oracle, refo, cfo, snr):
         d = np.abs(a.soft_bits(f).astype(np.int32) - b.soft_bits(f).astype(np.int32))
         assert (d > 1).mean() <= 1e-4
     assert np.array_equal(a.counters[:4], b.counters[:4])
+
+
+def test_eti_generator(oracle, refo):
+    """EtiGenerator restatement against the reference's own generator (its output file), incl. a recording that ends inside a frame."""
+    sc = [synth.SubChannel(3, 100, 54, 0, 2, 72), synth.SubChannel(5, 300, 84, 1, 4, 128), synth.SubChannel(9, 400, 30, 0, 7, 64)]
+    rec = synth.generate(8, seed=31, snr_db=13.0, subch=sc, fmt=synth.FMT_CF32)
+    iq = rec.iq[:rec.iq.size - 120000]  # cut the last frame after its second CIF
+    a = oracle.chain_run(iq, synth.subch_table(sc), 3, eti=True)
+    b = refo.chain_run(iq, synth.subch_table(sc), 3, eti=True)
+    assert a.n_frames == b.n_frames
+    assert b.eti.size > 0 and b.eti.size % 6144 == 0
+    assert np.array_equal(a.eti, b.eti)

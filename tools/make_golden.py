@@ -97,6 +97,15 @@ def main():
         chain[f"{name}_fft_f1"] = r.fft(1)[[0, 1, 76]]
         r.close()
     np.savez_compressed(os.path.join(OUT, "chain.npz"), **chain)
+
+    # ---- ETI-NI stream of the reference's own EtiGenerator (eti_generator.cpp) for the mixed ensemble, 9 frames
+    kw = dict(n_frames=9, seed=7, snr_db=14.0, cfo_hz=0.0,
+              subch=[synth.SubChannel(1, 0, 108, 0, 0, 72), synth.SubChannel(2, 108, 42, 0, 5, 64), synth.SubChannel(4, 150, 96, 1, 3, 128)])
+    rec = synth.generate(fmt=synth.FMT_U8, **kw)
+    iq_f = ((rec.iq.astype(np.float32) - np.float32(127.38)) / np.float32(128.0)).view(np.complex64).reshape(-1)
+    r = ref.chain_run(iq_f, synth.subch_table(kw["subch"]), len(kw["subch"]), eti=True)
+    np.savez_compressed(os.path.join(OUT, "eti.npz"), iq_sha256=np.array(sha(rec.iq)), n_frames=np.int32(r.n_frames), eti=r.eti.reshape(-1, 6144))
+    r.close()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 # usage: bash tools/run_gpu.sh <tag> [ncu kernel regex] [extra bench args]   -- tests, bench, optional ncu full capture
-TAG=${1:-x}; KREGEX=${2:-}; shift 2 || true
+TAG=${1:-x}; KREGEX=${2:-}; shift; shift || true
 set -x
 cd $GRAFT_REPO_ROOT
 O=gpurun_out/${TAG}

@@ -35,12 +35,22 @@ class SampleFormatC(ctypes.Structure):
     _fields_ = [("container", ctypes.c_int32), ("bits_per_channel", ctypes.c_int32), ("msb_first", ctypes.c_int32), ("iq_order", ctypes.c_int32)]
 
 
+class EnsembleInfoC(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("eid", "change_flags", "alarm", "cif_count_hi", "cif_count_lo", "n_subch", "n_components", "restarts")]
+
+
+class ServiceCompC(ctypes.Structure):
+    _fields_ = [("sid", ctypes.c_uint32)] + [(n, ctypes.c_int32) for n in ("comp_index", "tmid", "type", "sub_ch_id", "primary", "ca_flag")]
+
+
 # every symbol include/dabstar_b200.h declares: (name, restype)
 EXPORTS = [
     ("dabstar_create", ctypes.c_int), ("dabstar_destroy", None), ("dabstar_last_error", ctypes.c_char_p),
     ("dabstar_abi_version", ctypes.c_int), ("dabstar_kernel_launches", ctypes.c_uint64),
     ("dabstar_freq_interleaver", ctypes.c_int), ("dabstar_phase_table", ctypes.c_int), ("dabstar_protection_addresses", ctypes.c_int),
     ("dabstar_ingest_convert", ctypes.c_int), ("dabstar_sample_format_bytes", ctypes.c_int),
+    ("dabstar_fib_parser_create", ctypes.c_int), ("dabstar_fib_parser_destroy", None), ("dabstar_fib_parser_push", ctypes.c_int),
+    ("dabstar_fib_parser_ensemble", ctypes.c_int), ("dabstar_fib_parser_subchannels", ctypes.c_int), ("dabstar_fib_parser_components", ctypes.c_int),
     ("dabstar_fft2048", ctypes.c_int), ("dabstar_viterbi", ctypes.c_int), ("dabstar_protection_deconvolve", ctypes.c_int),
     ("dabstar_fic_decode", ctypes.c_int), ("dabstar_backend_process", ctypes.c_int),
     ("dabstar_ofdm_state_create", ctypes.c_int), ("dabstar_ofdm_state_destroy", None), ("dabstar_ofdm_state_reset", ctypes.c_int),
@@ -50,6 +60,7 @@ EXPORTS = [
     ("dabstar_decoder_run", ctypes.c_int), ("dabstar_decoder_n_frames", ctypes.c_int), ("dabstar_decoder_frame_info", ctypes.c_int),
     ("dabstar_decoder_fib_bits", ctypes.c_int), ("dabstar_decoder_soft_bits", ctypes.c_int),
     ("dabstar_decoder_msc_size", ctypes.c_int64), ("dabstar_decoder_msc_copy", ctypes.c_int64),
+    ("dabstar_decoder_set_auto_config", ctypes.c_int), ("dabstar_decoder_subchannels", ctypes.c_int), ("dabstar_decoder_ensemble", ctypes.c_int),
     ("dabstar_decoder_enable_eti", ctypes.c_int), ("dabstar_decoder_eti_size", ctypes.c_int64), ("dabstar_decoder_eti_copy", ctypes.c_int64),
     ("dabstar_decoder_counters", ctypes.c_int), ("dabstar_decoder_last_ms", ctypes.c_double),
     ("dabstar_decoder_stage_ms", ctypes.c_int),

@@ -58,6 +58,63 @@ class SampleFormat:
         return None
 
 
+@dataclass
+class ServiceComponent:
+    sid: int
+    comp_index: int
+    tmid: int
+    type: int
+    sub_ch_id: int
+    primary: int
+    ca_flag: int
+
+
+class FibParser:
+    """FibDecoder::process_FIB for FIG 0/0, 0/1, 0/2 (fib_decoder.cpp:59-106, fib_decoder_fig0.cpp:89-290): host code, no device."""
+
+    def __init__(self):
+        self.lib = _lib.load()
+        self.h = c_p()
+        if self.lib.dabstar_fib_parser_create(ctypes.byref(self.h)) != 0:
+            raise DabstarError("dabstar_fib_parser_create failed")
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.dabstar_fib_parser_destroy(self.h)
+                self.h = c_p()
+        except Exception:
+            pass
+
+    def process_FIB(self, fib_bits: np.ndarray):
+        """fib_bits: uint8[n, 256] (or [256]), one bit per byte; the caller has checked the CRCs."""
+        b = _np(fib_bits, np.uint8).reshape(-1, 256)
+        if self.lib.dabstar_fib_parser_push(self.h, _ptr(b), b.shape[0]) != 0:
+            raise DabstarError("dabstar_fib_parser_push failed")
+
+    def ensemble(self) -> _lib.EnsembleInfoC | None:
+        e = _lib.EnsembleInfoC()
+        seen = self.lib.dabstar_fib_parser_ensemble(self.h, ctypes.byref(e))
+        return e if seen == 1 else None
+
+    def get_cif_count(self) -> tuple[int, int]:
+        e = _lib.EnsembleInfoC()
+        seen = self.lib.dabstar_fib_parser_ensemble(self.h, ctypes.byref(e))
+        return (e.cif_count_hi, e.cif_count_lo) if seen == 1 else (-1, -1)
+
+    def sub_channels(self) -> list[SubChannel]:
+        n = self.lib.dabstar_fib_parser_subchannels(self.h, None, 0)
+        arr = (SubCh * max(n, 1))()
+        self.lib.dabstar_fib_parser_subchannels(self.h, arr, n)
+        return [SubChannel(a.sub_ch_id, a.start_cu, a.size_cu, a.short_form, a.prot_level, a.bit_rate, a.start_frame) for a in arr[:n]]
+
+    def components(self) -> list[ServiceComponent]:
+        n = self.lib.dabstar_fib_parser_components(self.h, None, 0)
+        arr = (_lib.ServiceCompC * max(n, 1))()
+        self.lib.dabstar_fib_parser_components(self.h, arr, n)
+        return [ServiceComponent(a.sid, a.comp_index, a.tmid, a.type, a.sub_ch_id, a.primary, a.ca_flag) for a in arr[:n]]
+
+
 class Context:
     """One CUDA device + stream (dabstar_create). `stream` may be a torch.cuda.Stream or None for a private stream."""
 
@@ -325,6 +382,7 @@ class DabProcessor:
         self.h = c_p()
         self.ctx.check(self.ctx.lib.dabstar_decoder_create(self.ctx.h, ctypes.byref(self.cfg), self.n, ctypes.byref(self.h)), "dabstar_decoder_create")
         self.subch: list[list[SubChannel]] = [[] for _ in range(self.n)]
+        self.auto: dict[int, bool] = {}
 
     def __del__(self):
         try:
@@ -338,6 +396,22 @@ class DabProcessor:
         arr = (SubCh * max(len(subch), 1))(*[SubCh(*s.as_row()) for s in subch])
         self.ctx.check(self.ctx.lib.dabstar_decoder_set_subchannels(self.h, recording, arr, len(subch)), "dabstar_decoder_set_subchannels")
         self.subch[recording] = list(subch)
+
+    def set_auto_config(self, recording: int, enable: bool = True):
+        """Take the recording's sub-channels and CIF counter from its own FIC (FIG 0/0, 0/1) instead of set_audio_channel."""
+        self.ctx.check(self.ctx.lib.dabstar_decoder_set_auto_config(self.h, recording, 1 if enable else 0), "dabstar_decoder_set_auto_config")
+        self.auto[recording] = bool(enable)
+
+    def sub_channels(self, recording: int) -> list[SubChannel]:
+        n = self.ctx.check(self.ctx.lib.dabstar_decoder_subchannels(self.h, recording, None, 0), "dabstar_decoder_subchannels")
+        arr = (SubCh * max(n, 1))()
+        self.ctx.lib.dabstar_decoder_subchannels(self.h, recording, arr, n)
+        return [SubChannel(a.sub_ch_id, a.start_cu, a.size_cu, a.short_form, a.prot_level, a.bit_rate, a.start_frame) for a in arr[:n]]
+
+    def ensemble(self, recording: int) -> _lib.EnsembleInfoC:
+        e = _lib.EnsembleInfoC()
+        self.ctx.check(self.ctx.lib.dabstar_decoder_ensemble(self.h, recording, ctypes.byref(e)), "dabstar_decoder_ensemble")
+        return e
 
     def start_eti_generator(self, recording: int, cif_count_hi: int = 0, cif_count_lo: int = 0):
         """DabProcessor::start_eti_generator (dab_processor.cpp:529-546): the next run also produces the ETI(NI) stream of
@@ -391,7 +465,7 @@ class DabProcessor:
         valid = np.zeros((nf, 4), np.uint8)
         lib.dabstar_decoder_fib_bits(self.h, recording, _ptr(bits), _ptr(valid))
         msc = {}
-        for s in self.subch[recording]:
+        for s in (self.sub_channels(recording) if self.auto.get(recording) else self.subch[recording]):
             n = int(lib.dabstar_decoder_msc_size(self.h, recording, s.sub_ch_id))
             buf = np.zeros(n, np.uint8)
             if n:

@@ -682,6 +682,7 @@ struct MscOut
 {
   dabstar_subch sc;
   int profile = -1;
+  int first_seen = 0;   // frame whose FIC first described the sub-channel (self-configuration; 0 when set by the caller)
   std::vector<uint8_t> bits;
 };
 
@@ -714,6 +715,9 @@ struct Recording
   bool eti_on = false;       // EtiGenerator running from the first frame of the run (DabProcessor::start_eti_generator)
   int eti_cif_hi = 0, eti_cif_lo = 0; // IFibDecoder::get_cif_count(hi, lo) as the generator samples it at symbol 4
   std::vector<uint8_t> eti;  // ETI-NI frames of the last run, 6144 bytes each
+  bool auto_cfg = false;     // sub-channels and CIF counter from the recording's own FIG 0/0 and 0/1
+  std::vector<int> cif_hi_f, cif_lo_f; // auto_cfg: CIF counter as the FIB decoder holds it after each frame's FIC (-1: none yet)
+  dabstar_ensemble_info ens{};
   long long cnt_good_fibs = 0, cnt_sync_ok = 0, cnt_sync_fail = 0, cnt_windows = 0, cnt_cut = 0, cnt_heavy = 0;
   // window scratch
   int w_first_desc = 0, w_frames = 0;
@@ -822,6 +826,25 @@ extern "C" int dabstar_decoder_set_subchannels(dabstar_decoder * dec, int record
   return 0;
 }
 
+extern "C" int dabstar_decoder_set_auto_config(dabstar_decoder * dec, int recording, int enable)
+{
+  if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  dec->recs[recording].auto_cfg = enable != 0;
+  return 0;
+}
+extern "C" int dabstar_decoder_subchannels(const dabstar_decoder * dec, int recording, dabstar_subch * out, int cap)
+{
+  if (!dec || recording < 0 || recording >= (int)dec->recs.size() || (!out && cap > 0)) return DABSTAR_E_INVALID;
+  const std::vector<MscOut> & m = dec->recs[recording].msc;
+  for (int i = 0; i < (int)m.size() && i < cap; i++) out[i] = m[i].sc;
+  return (int)m.size();
+}
+extern "C" int dabstar_decoder_ensemble(const dabstar_decoder * dec, int recording, dabstar_ensemble_info * out)
+{
+  if (!dec || !out || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  *out = dec->recs[recording].ens;
+  return 0;
+}
 extern "C" int dabstar_decoder_enable_eti(dabstar_decoder * dec, int recording, int enable, int cif_count_hi, int cif_count_lo)
 {
   if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
@@ -1081,9 +1104,11 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
   {
     Recording & R = dec->recs[r];
     std::vector<MscOut> keep = std::move(R.msc);
-    const bool eti_on = R.eti_on;
+    const bool eti_on = R.eti_on, auto_cfg = R.auto_cfg;
     const int eti_hi = R.eti_cif_hi, eti_lo = R.eti_cif_lo;
     R = Recording();
+    R.auto_cfg = auto_cfg;
+    if (auto_cfg) keep.clear(); // rediscovered from this run's FIC
     R.msc = std::move(keep);
     R.eti_on = eti_on;
     R.eti_cif_hi = eti_hi;
@@ -1613,6 +1638,65 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
     }
   }
 
+  // ================= self-configuration: sub-channels and CIF counter from the recording's own FIC (FIG 0/0, 0/1)
+  // FibDecoder::process_FIB sees the CRC-good FIBs in stream order; a Backend is taken to exist from the frame after the one
+  // whose FIC first described its sub-channel (in the reference that moment is a GUI action), EtiGenerator samples the
+  // sub-channel list and the CIF counter at symbol 4 of every frame, i.e. after that frame's own FIC.
+  {
+    bool any = false;
+    for (int r = 0; r < n_rec; r++) any = any || (dec->recs[r].auto_cfg && dec->recs[r].n_slots > 0);
+    if (any)
+    {
+      CK(dec->h_fib.reserve((size_t)dec->total_slots * 3072));
+      for (int r = 0; r < n_rec; r++)
+      {
+        Recording & R = dec->recs[r];
+        const int fs = std::min(R.slot_cap, R.n_slots + (R.partial_syms > 3 ? 1 : 0));
+        if (R.auto_cfg && fs > 0)
+          CK(cudaMemcpyAsync(dec->h_fib.as<uint8_t>() + (size_t)R.slot_base * 3072, dec->d_fib.as<uint8_t>() + (size_t)R.slot_base * 3072, (size_t)fs * 3072, cudaMemcpyDeviceToHost, st));
+      }
+      SYNC();
+      for (int r = 0; r < n_rec; r++)
+      {
+        Recording & R = dec->recs[r];
+        if (!R.auto_cfg || R.n_slots == 0) continue;
+        dabstar_fib_parser * fp = nullptr;
+        if (dabstar_fib_parser_create(&fp) != 0) return ctx->fail(DABSTAR_E_NOMEM, "fib parser");
+        R.msc.clear();
+        R.cif_hi_f.assign((size_t)R.n_slots + 1, -1);
+        R.cif_lo_f.assign((size_t)R.n_slots + 1, -1);
+        int known = 0;
+        const int n_f = (int)(R.crc_ok.size() / 12);
+        for (int f = 0; f < n_f && f <= R.n_slots; f++)
+        {
+          const uint8_t * fb = dec->h_fib.as<uint8_t>() + ((size_t)R.slot_base + f) * 3072;
+          for (int k = 0; k < 12; k++)
+            if (R.crc_ok[(size_t)12 * f + k]) dabstar_fib_parser_push(fp, fb + (size_t)(k / 3) * 768 + (size_t)(k % 3) * 256, 1);
+          dabstar_ensemble_info e;
+          if (dabstar_fib_parser_ensemble(fp, &e) == 1) { R.cif_hi_f[f] = e.cif_count_hi; R.cif_lo_f[f] = e.cif_count_lo; }
+          if (e.restarts > 0 && e.n_subch < known) { R.msc.clear(); known = 0; } // the parser dropped its database
+          std::vector<dabstar_subch> all((size_t)std::max(1, e.n_subch));
+          dabstar_fib_parser_subchannels(fp, all.data(), (int)all.size());
+          for (int i = known; i < e.n_subch; i++)
+          {
+            MscOut m;
+            m.sc = all[i];
+            m.sc.start_frame = f + 1;
+            m.first_seen = f;
+            m.profile = get_profile(ctx, m.sc.short_form, m.sc.bit_rate, m.sc.prot_level);
+            if (m.profile < 0 || ctx->profiles[m.profile].n_kept > m.sc.size_cu * 64) continue; // described but not decodable (unknown profile)
+            R.msc.push_back(m);
+          }
+          known = e.n_subch;
+          R.ens = e;
+        }
+        for (int f = n_f; f <= R.n_slots; f++) { R.cif_hi_f[f] = f > 0 ? R.cif_hi_f[f - 1] : -1; R.cif_lo_f[f] = f > 0 ? R.cif_lo_f[f - 1] : -1; }
+        dabstar_fib_parser_destroy(fp);
+      }
+      if (int e = sync_profiles(ctx)) return e;
+    }
+  }
+
   // ================= MSC: all logical frames of all sub-channels in one batch per profile size
   if (!dec->cfg.scan_mode)
   {
@@ -1673,6 +1757,7 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
       for (int n = 0; n < n_out; n++)
         for (MscOut & m : R.msc)
         {
+          if (m.first_seen > 4 + (n >> 2)) continue; // not yet in the FIB decoder's list when the generator sampled it
           const VitProfile & p = ctx->profiles[m.profile];
           VitJob j;
           memset(&j, 0, sizeof(j));
@@ -1720,7 +1805,8 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
   {
     const EtiRef & last = eti_refs.back();
     long long bits_total = last.bit_off;
-    for (const MscOut & m : dec->recs[last.rec].msc) bits_total += (long long)last.n_out * 24 * m.sc.bit_rate;
+    for (int n = 0; n < last.n_out; n++)
+      for (const MscOut & m : dec->recs[last.rec].msc) if (m.first_seen <= 4 + (n >> 2)) bits_total += 24LL * m.sc.bit_rate;
     eti_packed.resize((size_t)(bits_total / 8));
     CK(cudaMemcpyAsync(eti_packed.data(), dec->d_etipacked.p, eti_packed.size(), cudaMemcpyDeviceToHost, st));
   }
@@ -1736,7 +1822,11 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
     for (int n = 0; n < er.n_out; n++)
     {
       uint8_t * f = R.eti.data() + (size_t)n * 6144;
-      int o = eti_header(f, R.eti_cif_hi, R.eti_cif_lo, n & 3, R.msc);
+      const int fr = 4 + (n >> 2);
+      std::vector<MscOut> streams; // the sub-channel list as sampled at symbol 4 of the CIF's frame
+      for (const MscOut & m : R.msc) if (m.first_seen <= fr) { streams.push_back(MscOut()); streams.back().sc = m.sc; }
+      const bool own = R.auto_cfg && fr < (int)R.cif_hi_f.size() && R.cif_hi_f[fr] >= 0;
+      int o = eti_header(f, own ? R.cif_hi_f[fr] : R.eti_cif_hi, own ? R.cif_lo_f[fr] : R.eti_cif_lo, n & 3, streams);
       const int base = o;
       // fibVector: the four FICs of the frame as the FIC decoder left them at symbol 4, whether their CRCs passed or not
       const uint8_t * fib = dec->h_fib.as<uint8_t>() + ((size_t)R.slot_base + 4 + (size_t)(n >> 2)) * 3072 + (size_t)(n & 3) * 768;
@@ -1746,7 +1836,7 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
         for (int k = 0; k < 8; k++) v = (v << 1) | (fib[8 * j + k] & 1u);
         f[o++] = (uint8_t)v;
       }
-      for (const MscOut & m : R.msc)
+      for (const MscOut & m : streams)
       {
         const int nb = 3 * m.sc.bit_rate;
         memcpy(f + o, src, (size_t)nb);

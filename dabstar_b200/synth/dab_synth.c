@@ -34,6 +34,9 @@ typedef struct
   int32_t  tail_samples;  /* filler after the last frame (lets the receiver finish the last frame) */
   int32_t  n_subch;
   const int32_t * subch;  /* n_subch x 7: subChId,startCU,sizeCU,shortForm,protLevel,bitRate,(unused) */
+  int32_t  fig_mode;      /* 0: random FIB payloads; 1: MCI of the configured ensemble (FIG 0/0 with a running CIF counter,
+                             FIG 0/1 per sub-channel, FIG 0/2 one audio service per sub-channel), EN 300 401 clauses 6.2-6.4 */
+  int32_t  eid;           /* ensemble identifier for fig_mode 1 */
 } dabsynth_cfg;
 
 /* ---------------------------------------------------------------------------------------------- rng */
@@ -253,6 +256,125 @@ int64_t dabsynth_num_samples(const dabsynth_cfg * c)
   return (int64_t)c->lead_samples + (int64_t)c->n_frames * TF + (int64_t)c->tail_samples;
 }
 
+/* ---- FIC content for fig_mode 1 (EN 300 401 clause 5.2.2 FIG structure, 6.4.1 FIG 0/0, 6.2.1 FIG 0/1, 6.3.1 FIG 0/2) ---- */
+/* index into EN 300 401 table 8 (bit rate, protection level) -> short-form table index, -1 if the pair is not in the table */
+static const int16_t T8_RATE[14] = { 32, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384 };
+static int table8_index(int bit_rate, int level)
+{
+  int idx = 0;
+  for (int r = 0; r < 14; r++)
+    for (int l = 5; l >= 1; l--)
+    {
+      /* pairs the table leaves out: 56/1, 112/1, 320/3, 320/1, 384/4, 384/2 */
+      const int rate = T8_RATE[r];
+      if ((rate == 56 && l == 1) || (rate == 112 && l == 1) || (rate == 320 && (l == 3 || l == 1)) || (rate == 384 && (l == 4 || l == 2))) continue;
+      if (rate == bit_rate && l == level) return idx;
+      idx++;
+    }
+  return -1;
+}
+
+typedef struct { uint8_t b[12][30]; int fib, used; } fic_writer;
+
+static void ficw_init(fic_writer * w) { memset(w->b, 0, sizeof(w->b)); w->fib = 0; w->used = 0; }
+/* room for a FIG of `bytes` bytes in the current FIB, else close it (end marker) and move on; NULL when the FIC is full */
+static uint8_t * ficw_reserve(fic_writer * w, int bytes)
+{
+  if (w->used + bytes > 30)
+  {
+    if (w->used < 30) w->b[w->fib][w->used] = 0xFF;
+    w->fib++;
+    w->used = 0;
+  }
+  if (w->fib >= 12) return NULL;
+  uint8_t * p = &w->b[w->fib][w->used];
+  w->used += bytes;
+  return p;
+}
+static void ficw_finish(fic_writer * w)
+{
+  if (w->fib < 12 && w->used < 30) w->b[w->fib][w->used] = 0xFF;
+  for (int f = w->fib + 1; f < 12; f++) w->b[f][0] = 0xFF;
+}
+
+/* The 12 FIBs (30 bytes each, CRC not included) of frame f */
+static int build_mci(const dabsynth_cfg * c, int f, fic_writer * w)
+{
+  ficw_init(w);
+  const int cif = (4 * f) % 5000;
+  uint8_t * p = ficw_reserve(w, 6);
+  p[0] = (0 << 5) | 5;                                  /* FIG type 0, length 5 */
+  p[1] = 0;                                             /* C/N 0, OE 0, P/D 0, extension 0 */
+  p[2] = (uint8_t)(c->eid >> 8); p[3] = (uint8_t)c->eid;
+  p[4] = (uint8_t)((0 << 6) | (0 << 5) | ((cif / 250) & 31)); /* change flags 0, alarm 0, CIF count high */
+  p[5] = (uint8_t)(cif % 250);
+  /* FIG 0/1: as many sub-channels per FIG as fit into the FIB */
+  int i = 0;
+  while (i < c->n_subch)
+  {
+    int room = 30 - w->used;
+    if (room < 2 + 4) room = 30;
+    int n = 0, bytes = 2;
+    while (i + n < c->n_subch)
+    {
+      const int add = c->subch[7 * (i + n) + 3] ? 3 : 4;
+      if (bytes + add > room) break;
+      bytes += add; n++;
+    }
+    p = ficw_reserve(w, bytes);
+    if (!p || n == 0) return -1;
+    p[0] = (uint8_t)((0 << 5) | (bytes - 1));
+    p[1] = 1;
+    uint8_t * q = p + 2;
+    for (int k = 0; k < n; k++, i++)
+    {
+      const int32_t * s = c->subch + 7 * i;
+      q[0] = (uint8_t)((s[0] << 2) | ((s[1] >> 8) & 3));
+      q[1] = (uint8_t)(s[1] & 0xff);
+      if (s[3])
+      {
+        const int ti = table8_index(s[5], s[4]);
+        if (ti < 0) return -1;
+        q[2] = (uint8_t)((0 << 7) | (0 << 6) | ti);     /* short form, table switch 0 */
+        q += 3;
+      }
+      else
+      {
+        const int option = (s[4] & 4) ? 1 : 0, level = s[4] & 3;
+        q[2] = (uint8_t)((1 << 7) | (option << 4) | (level << 2) | ((s[2] >> 8) & 3));
+        q[3] = (uint8_t)(s[2] & 0xff);
+        q += 4;
+      }
+    }
+  }
+  /* FIG 0/2: one programme service with one stream-audio component per sub-channel */
+  i = 0;
+  while (i < c->n_subch)
+  {
+    int room = 30 - w->used;
+    if (room < 2 + 5) room = 30;
+    int n = (room - 2) / 5;
+    if (n > c->n_subch - i) n = c->n_subch - i;
+    p = ficw_reserve(w, 2 + 5 * n);
+    if (!p || n == 0) return -1;
+    p[0] = (uint8_t)((0 << 5) | (1 + 5 * n));
+    p[1] = 2;
+    uint8_t * q = p + 2;
+    for (int k = 0; k < n; k++, i++, q += 5)
+    {
+      const int32_t * s = c->subch + 7 * i;
+      const int sid = 0xD000 + s[0];
+      q[0] = (uint8_t)(sid >> 8); q[1] = (uint8_t)sid;
+      q[2] = 1;                                         /* local flag 0, CAId 0, one component */
+      const int ascty = s[3] ? 0 : 63;                  /* UEP: MPEG layer II, EEP: DAB+ */
+      q[3] = (uint8_t)((0 << 6) | ascty);               /* TMId 0 (stream audio) */
+      q[4] = (uint8_t)((s[0] << 2) | (1 << 1) | 0);     /* SubChId, primary, no CA */
+    }
+  }
+  ficw_finish(w);
+  return 0;
+}
+
 /* fib_truth: n_frames*3072 bytes (one bit per byte, FIBs incl. CRC, as the receiver delivers them).
  * msc_truth[s]: n_frames*4*24*bitRate bytes for sub-channel s (logical frames in transmit order); may be NULL. */
 int dabsynth_generate(const dabsynth_cfg * c, void * out_iq, uint8_t * fib_truth, uint8_t ** msc_truth)
@@ -323,11 +445,15 @@ int dabsynth_generate(const dabsynth_cfg * c, void * out_iq, uint8_t * fib_truth
       {
         /* FIC: 4 blocks of 3 FIBs */
         rng_t r = rng_make(c->seed, 0x10, (uint64_t)f);
+        fic_writer mci;
+        if (c->fig_mode == 1) build_mci(c, f, &mci);
         for (int blk = 0; blk < 4; blk++)
         {
           for (int fib = 0; fib < 3; fib++)
           {
             uint8_t * p = &fic[fib * 256];
+            if (c->fig_mode == 1) { for (int i = 0; i < 240; i++) p[i] = (uint8_t)((mci.b[3 * blk + fib][i >> 3] >> (7 - (i & 7))) & 1u); }
+            else
             for (int i = 0; i < 240; i += 60) { uint64_t w = rng_next(&r); for (int b = 0; b < 60; b++) p[i + b] = (uint8_t)((w >> b) & 1u); }
             const uint16_t crc = crc16(p, 240);
             for (int b = 0; b < 16; b++) p[240 + b] = (uint8_t)((crc >> (15 - b)) & 1u);

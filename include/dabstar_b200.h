@@ -163,6 +163,38 @@ int dabstar_prs_correlate(dabstar_ctx * ctx, const float * samples, int n, float
  * symbols 0; offset_hz[i] = Hz or 100000 (IDX_NOT_FOUND). */
 int dabstar_estimate_carrier_offset(dabstar_ctx * ctx, const float * fft, int n, int32_t * offset_hz, int mem);
 
+/* ------------------------------------------------------------------------------------------------ multiplex configuration (FIG 0/0, 0/1, 0/2) */
+/* The part of FibDecoder the decode path depends on (decoder/fib_decoder.cpp:59-106 process_FIB,
+ * fib_decoder_fig0.cpp:89-113 FIG 0/0, :142-227 FIG 0/1, :229-290 FIG 0/2, fib_table.h:51 short-form table): which
+ * sub-channels exist (MscHandler::set_channel), the CIF counter and the sub-channel list EtiGenerator frames. Host
+ * code; current configuration (C/N = 0) only. A sub-channel that leaves the CIF or overlaps a known one makes the
+ * parser drop what it collected, as FibDecoder::_restart_fib_decoding does. */
+typedef struct
+{
+  int32_t eid, change_flags, alarm;
+  int32_t cif_count_hi, cif_count_lo;   /* IFibDecoder::get_cif_count(hi, lo) */
+  int32_t n_subch, n_components, restarts;
+} dabstar_ensemble_info;
+typedef struct
+{
+  uint32_t sid;
+  int32_t comp_index;  /* position inside the service's FIG 0/2 entry */
+  int32_t tmid;        /* 0 stream audio, 1 stream data, 3 packet data */
+  int32_t type;        /* ASCTy (0 MPEG layer II, 63 DAB+) / DSCTy / SCId */
+  int32_t sub_ch_id;   /* -1 for packet mode */
+  int32_t primary, ca_flag;
+} dabstar_service_comp;
+typedef struct dabstar_fib_parser dabstar_fib_parser;
+int  dabstar_fib_parser_create(dabstar_fib_parser ** out);
+void dabstar_fib_parser_destroy(dabstar_fib_parser * p);
+/* IFibDecoder::process_FIB (fib_decoder_if.h:81) for n_fibs CRC-good FIBs: 256 bytes each, one bit per byte. */
+int  dabstar_fib_parser_push(dabstar_fib_parser * p, const uint8_t * fib_bits, int n_fibs);
+/* returns 1 once a FIG 0/0 has been seen, else 0 */
+int  dabstar_fib_parser_ensemble(const dabstar_fib_parser * p, dabstar_ensemble_info * out);
+/* sub-channels in order of first appearance (start_frame = 0); returns the total count */
+int  dabstar_fib_parser_subchannels(const dabstar_fib_parser * p, dabstar_subch * out, int cap);
+int  dabstar_fib_parser_components(const dabstar_fib_parser * p, dabstar_service_comp * out, int cap);
+
 /* ------------------------------------------------------------------------------------------------ whole path */
 typedef struct
 {
@@ -203,6 +235,14 @@ int     dabstar_decoder_soft_bits(const dabstar_decoder * dec, int recording, in
 int64_t dabstar_decoder_msc_size(const dabstar_decoder * dec, int recording, int sub_ch_id);
 /* FrameProcessor::add_to_frame payloads (backend/frame_processor.h:43), concatenated, one bit per byte */
 int64_t dabstar_decoder_msc_copy(const dabstar_decoder * dec, int recording, int sub_ch_id, uint8_t * out, int64_t cap);
+/* Self-configuration: the recording's sub-channels and CIF counter are taken from its own FIC (dabstar_fib_parser on the
+ * CRC-good FIBs in stream order) instead of dabstar_decoder_set_subchannels. Every sub-channel FIG 0/1 describes gets a
+ * Backend from the frame after its first description (in the reference that moment is a GUI action); with ETI enabled the
+ * generator frames the sub-channel list and FIG 0/0's CIF counter as it would sample them at symbol 4 of each frame. */
+int     dabstar_decoder_set_auto_config(dabstar_decoder * dec, int recording, int enable);
+/* sub-channels of the last run (as set, or as discovered); returns the count */
+int     dabstar_decoder_subchannels(const dabstar_decoder * dec, int recording, dabstar_subch * out, int cap);
+int     dabstar_decoder_ensemble(const dabstar_decoder * dec, int recording, dabstar_ensemble_info * out);
 /* EtiGenerator (eti_handler/eti_generator.h:56-66: start_eti_generator before run / process_block per symbol): every
  * sub-channel set with dabstar_decoder_set_subchannels is decoded for every CIF through the generator's own whole-CIF
  * de-interleaver (first frame with its 17th CIF; its start-up bookkeeping, which loses the 16th CIF, is reproduced) and

@@ -1008,8 +1008,34 @@ static void eti_block(eti_t * e, const dabo_chain_cfg * cfg, const uint8_t * fib
         e->fib_vec[(e->index_out + i) & 15][j] = (uint8_t)v;
       }
     e->minor = 0;
-    e->cif_hi = cfg->eti_cif_hi;
-    e->cif_lo = cfg->eti_cif_lo;
+    if (cfg->eti_cif_hi >= 0) { e->cif_hi = cfg->eti_cif_hi; e->cif_lo = cfg->eti_cif_lo; }
+    else
+    {
+      /* a real FIB decoder behind get_cif_count(): the CIF counter of the last FIG 0/0 among the CRC-good FIBs so far
+       * (fib_decoder.cpp:59-106 FIG walk, fib_decoder_fig0.cpp:89-113) */
+      for (int k = 0; k < 12; k++)
+      {
+        const uint8_t * fib = fib_bits + (k / 3) * 768 + (k % 3) * 256;
+        if (!dabo_check_crc_bits(fib, 256)) continue;
+        int done = 0;
+        while (done < 30)
+        {
+          const uint8_t * d = fib + 8 * done;
+          unsigned type = 0, len = 0, ext = 0, hi = 0, lo = 0;
+          for (int b = 0; b < 3; b++) type = (type << 1) | d[b];
+          for (int b = 3; b < 8; b++) len = (len << 1) | d[b];
+          if ((type == 7 && len == 31) || done + (int)len + 1 > 30) break;
+          for (int b = 11; b < 16; b++) ext = (ext << 1) | d[b];
+          if (type == 0 && ext == 0 && len >= 5)
+          {
+            for (int b = 35; b < 40; b++) hi = (hi << 1) | d[b];
+            for (int b = 40; b < 48; b++) lo = (lo << 1) | d[b];
+            e->cif_hi = (int)hi; e->cif_lo = (int)lo;
+          }
+          done += (int)len + 1;
+        }
+      }
+    }
   }
   const int blk = (sym - 4) % 18;
   memcpy(&e->cif_in[blk * BITS_PER_SYM], soft, sizeof(int16_t) * BITS_PER_SYM);

@@ -77,7 +77,8 @@ typedef struct
   int   n_subch;
   const int32_t * subch;     /* n_subch x 7: subChId,startCU,sizeCU,shortForm,protLevel,bitRate,startFrame */
   const char * eti_path;     /* NULL = ETI generator off; else the ETI-NI stream is also written to this file (as dabref does) */
-  int   eti_cif_hi, eti_cif_lo; /* IFibDecoder::get_cif_count(hi, lo) as sampled at symbol 4 of every frame (the dabref stub: 0, 0) */
+  int   eti_cif_hi, eti_cif_lo; /* IFibDecoder::get_cif_count(hi, lo) as sampled at symbol 4 of every frame (the dabref stub: 0, 0);
+                                   eti_cif_hi < 0: the counter of the last FIG 0/0 received, as a real FIB decoder reports it */
 } dabo_chain_cfg;
 
 typedef struct

@@ -221,7 +221,7 @@ class Oracle:
     # ---- whole chain
     def chain_run(self, iq: np.ndarray, subch_table: np.ndarray | None = None, n_subch: int = 0, soft_bit_type: int = 0,
                   threshold: float = 3.0, strongest_peak: int = 0, scan_mode: int = 0, tap_soft: bool = False, tap_fft: bool = False,
-                  eti: bool = False):
+                  eti: bool = False, eti_cif: tuple[int, int] = (0, 0)):
         """eti: also run the reference's EtiGenerator (start_eti_generator before run); the ETI-NI stream is in result.eti."""
         iq = np.ascontiguousarray(iq, np.complex64)
         tab = np.ascontiguousarray(subch_table if subch_table is not None else np.zeros((1, 7)), np.int32)
@@ -230,7 +230,7 @@ class Oracle:
             fd, eti_path = tempfile.mkstemp(suffix=".eti")
             os.close(fd)
         cfg = ChainCfg(soft_bit_type, threshold, strongest_peak, scan_mode, int(tap_soft), int(tap_fft), n_subch, tab.ctypes.data,
-                       eti_path.encode() if eti_path else None, 0, 0)
+                       eti_path.encode() if eti_path else None, int(eti_cif[0]), int(eti_cif[1]))
         h = c_p(self.f("chain_run")(_ptr(iq), ctypes.c_int64(iq.size), ctypes.byref(cfg)))
         res = ChainResult(self, h, tab[:n_subch].copy())
         if eti_path:

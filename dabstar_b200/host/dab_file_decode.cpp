@@ -1,6 +1,10 @@
 // dab_file_decode — headless file-input harness: raw interleaved IQ file(s) -> decoded FIC / MSC bits on the GPU.
 //
-//   dab_file_decode [-f u8|i16|cf32] [-s subChId,startCU,sizeCU,shortForm,protLevel,bitRate]... [-o prefix] file.iq [file2.iq ...]
+//   dab_file_decode [-f u8|i16|cf32] [-x container,bits,LSB|MSB,IQ|QI|I_Only|Q_Only] [-a] [-e]
+//                   [-s subChId,startCU,sizeCU,shortForm,protLevel,bitRate]... [-o prefix] file.iq [file2.iq ...]
+//     -x  XML/UFF sample description (container int8|uint8|int16|int24|int32|float32) for layouts other than the three native ones
+//     -a  self-configuration: sub-channels from the recording's FIG 0/1 (no -s needed)
+//     -e  also write the ETI(NI) stream, <prefix><n>.eti (what DABstar's ETI generator writes)
 //
 // The reference can only play files through its GUI, paced to real time (raw_reader.cpp:153-165); this harness feeds
 // whole files to dabstar::DabProcessor (one reference DabProcessor per file, all files in lock step) and writes
@@ -29,6 +33,8 @@ static std::vector<unsigned char> read_file(const char * path)
 int main(int argc, char ** argv)
 {
   int fmt = DABSTAR_FMT_U8;
+  bool autoCfg = false, eti = false, xml = false;
+  dabstar_sample_format sf{};
   std::string prefix = "dab_out_";
   std::vector<dabstar_subch> subch;
   std::vector<const char *> files;
@@ -37,6 +43,23 @@ int main(int argc, char ** argv)
     const std::string a = argv[i];
     if (a == "-f" && i + 1 < argc) { const std::string v = argv[++i]; fmt = v == "i16" ? DABSTAR_FMT_I16 : (v == "cf32" ? DABSTAR_FMT_CF32 : DABSTAR_FMT_U8); }
     else if (a == "-o" && i + 1 < argc) prefix = argv[++i];
+    else if (a == "-a") autoCfg = true;
+    else if (a == "-e") eti = true;
+    else if (a == "-x" && i + 1 < argc)
+    {
+      char cont[16] = { 0 }, order[8] = { 0 }, iq[16] = { 0 };
+      int bitsPer = 0;
+      if (sscanf(argv[++i], "%15[^,],%d,%7[^,],%15s", cont, &bitsPer, order, iq) != 4) { fprintf(stderr, "bad -x\n"); return 2; }
+      static const char * const conts[6] = { "int8", "uint8", "int16", "int24", "int32", "float32" };
+      static const char * const orders[4] = { "IQ", "QI", "I_Only", "Q_Only" };
+      sf.container = -1; sf.iq_order = -1;
+      for (int k = 0; k < 6; k++) if (std::string(cont) == conts[k]) sf.container = k;
+      for (int k = 0; k < 4; k++) if (std::string(iq) == orders[k]) sf.iq_order = k;
+      sf.bits_per_channel = bitsPer;
+      sf.msb_first = std::string(order) == "MSB";
+      xml = true;
+      fmt = DABSTAR_FMT_CF32;
+    }
     else if (a == "-s" && i + 1 < argc)
     {
       dabstar_subch s{};
@@ -49,17 +72,37 @@ int main(int argc, char ** argv)
   try
   {
     dabstar::Context ctx(0);
-    const size_t bps = fmt == DABSTAR_FMT_U8 ? 2 : (fmt == DABSTAR_FMT_I16 ? 4 : 8);
+    const int elem = xml ? dabstar_sample_format_bytes(&sf) : 0;
+    if (xml && elem == 0) { fprintf(stderr, "unknown sample format in -x\n"); return 2; }
+    const size_t bps = xml ? (size_t)elem : (fmt == DABSTAR_FMT_U8 ? 2 : (fmt == DABSTAR_FMT_I16 ? 4 : 8));
     std::vector<std::vector<unsigned char>> data;
     std::vector<const void *> ptrs;
     std::vector<int64_t> ns;
     for (const char * f : files) { data.push_back(read_file(f)); }
     for (auto & d : data) { ptrs.push_back(d.data()); ns.push_back((int64_t)(d.size() / bps)); }
-    dabstar::DabProcessor proc(ctx, (int)files.size(), fmt, subch.empty());
-    for (size_t r = 0; r < files.size(); r++) proc.set_audio_channel((int)r, subch);
-    proc.run(ptrs, ns);
+    dabstar::DabProcessor proc(ctx, (int)files.size(), fmt, subch.empty() && !autoCfg);
     for (size_t r = 0; r < files.size(); r++)
     {
+      if (autoCfg) proc.set_auto_config((int)r);
+      else proc.set_audio_channel((int)r, subch);
+      if (eti) proc.start_eti_generator((int)r);
+    }
+    if (xml) proc.run_files(ptrs, ns, sf);
+    else proc.run(ptrs, ns);
+    for (size_t r = 0; r < files.size(); r++)
+    {
+      if (autoCfg)
+      {
+        subch = proc.sub_channels((int)r);
+        for (auto & s : subch) printf("%s: sub-channel %d: CU %d+%d, %s level %d, %d kbit/s\n", files[r], s.sub_ch_id, s.start_cu, s.size_cu, s.short_form ? "UEP" : "EEP", s.prot_level, s.bit_rate);
+      }
+      if (eti)
+      {
+        const std::vector<dabstar::u8> e = proc.eti((int)r);
+        FILE * ef = fopen((prefix + std::to_string(r) + ".eti").c_str(), "wb");
+        if (ef) { fwrite(e.data(), 1, e.size(), ef); fclose(ef); }
+        printf("%s: %zu ETI(NI) frames\n", files[r], e.size() / 6144);
+      }
       long fibs = 0;
       FILE * fic = fopen((prefix + std::to_string(r) + ".fic").c_str(), "wb");
       std::vector<FILE *> outs;

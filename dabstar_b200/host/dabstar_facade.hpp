@@ -263,6 +263,40 @@ public:
   {
     mC.check(dabstar_decoder_run(mDec, iq.data(), nSamples.data(), DABSTAR_MEM_HOST), "dabstar_decoder_run");
   }
+  // Recordings in any file sample format (XmlReader::readElements_*, xml_reader.cpp:254-800): layouts the FFT kernel does not read
+  // natively are converted to complex float on the device first; the processor must have been created with DABSTAR_FMT_CF32.
+  void run_files(const std::vector<const void *> & raw, const std::vector<int64_t> & nSamples, const dabstar_sample_format & fmt)
+  {
+    std::vector<std::vector<float>> conv(raw.size());
+    std::vector<const void *> ptrs(raw.size());
+    for (size_t r = 0; r < raw.size(); r++)
+    {
+      conv[r].resize((size_t)2 * (size_t)nSamples[r]);
+      mC.check(dabstar_ingest_convert(mC.get(), raw[r], &fmt, nSamples[r], conv[r].data(), DABSTAR_MEM_HOST), "dabstar_ingest_convert");
+      ptrs[r] = conv[r].data();
+    }
+    run(ptrs, nSamples);
+  }
+  // Sub-channels and CIF counter from the recording's own FIG 0/0 and 0/1 instead of set_audio_channel.
+  void set_auto_config(int recording, bool on = true) { mC.check(dabstar_decoder_set_auto_config(mDec, recording, on ? 1 : 0), "dabstar_decoder_set_auto_config"); }
+  std::vector<dabstar_subch> sub_channels(int recording) const
+  {
+    std::vector<dabstar_subch> v((size_t)std::max(0, dabstar_decoder_subchannels(mDec, recording, nullptr, 0)));
+    if (!v.empty()) dabstar_decoder_subchannels(mDec, recording, v.data(), (int)v.size());
+    return v;
+  }
+  // DabProcessor::start_eti_generator / stop_eti_generator (dab_processor.cpp:529-558): the next run also frames ETI(NI)
+  void start_eti_generator(int recording, int cifCountHi = 0, int cifCountLo = 0)
+  {
+    mC.check(dabstar_decoder_enable_eti(mDec, recording, 1, cifCountHi, cifCountLo), "dabstar_decoder_enable_eti");
+  }
+  void stop_eti_generator(int recording) { mC.check(dabstar_decoder_enable_eti(mDec, recording, 0, 0, 0), "dabstar_decoder_enable_eti"); }
+  std::vector<u8> eti(int recording) const
+  {
+    std::vector<u8> v((size_t)std::max<int64_t>(0, dabstar_decoder_eti_size(mDec, recording)));
+    if (!v.empty()) dabstar_decoder_eti_copy(mDec, recording, v.data(), (int64_t)v.size());
+    return v;
+  }
   int n_frames(int recording) const { return dabstar_decoder_n_frames(mDec, recording); }
   std::vector<dabstar_frame_info> frame_info(int recording) const
   {

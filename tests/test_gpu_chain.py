@@ -176,3 +176,34 @@ def test_eti_generator_stream(ctx, oracle, viterbi_path):
     dp2.stop_eti_generator(0)
     dp2.run([iq])
     assert dp2.eti(0).shape[0] == 0
+
+
+def test_cpp_harness_end_to_end(ctx, tmp_path):
+    """The C++ facades + headless harness (dabstar_b200/host/): self-configured decode of a big-endian QI int16 file, FIC dump,
+    sub-channel files and ETI stream equal what the Python mirror of the same ABI produces."""
+    import os, shutil, subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "dab_file_decode")
+    subprocess.run(["g++", "-std=c++17", "-O2", os.path.join(root, "dabstar_b200", "host", "dab_file_decode.cpp"), "-I", os.path.join(root, "include"),
+                    "-L", os.path.join(root, "dabstar_b200"), "-ldabstar_b200", "-Wl,-rpath," + os.path.join(root, "dabstar_b200"), "-o", exe], check=True)
+    sc = [synth.SubChannel(3, 100, 54, 0, 2, 72), synth.SubChannel(5, 300, 84, 1, 4, 128)]
+    rec = synth.generate(8, seed=44, snr_db=17.0, subch=sc, fmt=synth.FMT_I16, fig_mode=1)
+    raw = np.ascontiguousarray(rec.iq[:, ::-1]).astype(">i2")  # Ordering MSB, iqOrder QI
+    path = str(tmp_path / "rec.iq")
+    raw.tofile(path)
+    prefix = str(tmp_path / "out_")
+    r = subprocess.run([exe, "-x", "int16,16,MSB,QI", "-a", "-e", "-o", prefix, path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "sub-channel 3: CU 100+54, EEP level 2, 72 kbit/s" in r.stdout and "sub-channel 5: CU 300+84, UEP level 4, 128 kbit/s" in r.stdout
+    dp = api.DabProcessor(1, input_format=api.FMT_CF32, ctx=ctx)
+    dp.set_auto_config(0)
+    dp.start_eti_generator(0)
+    dp.run_files([raw.view(np.uint8)], api.SampleFormat("int16", 16, "MSB", "QI"))
+    got = dp.result(0)
+    assert got.n_frames == 8 and got.fic_valid.all()
+    assert np.array_equal(np.fromfile(prefix + "0.eti", np.uint8).reshape(-1, 6144), dp.eti(0))
+    assert np.fromfile(prefix + "0.fic", np.uint8).size == 32 * got.n_good_fibs
+    for s in sc:
+        assert np.array_equal(np.fromfile(prefix + f"0.sub{s.sub_ch_id}", np.uint8), np.packbits(got.msc[s.sub_ch_id].reshape(-1)))

@@ -58,6 +58,31 @@ class SampleFormat:
         return None
 
 
+class Mp4Processor:
+    """backend/audio/mp4processor.h for a run of logical frames: super-frame sync, RS(120,110), Fire code, AU borders and CRCs on the GPU."""
+
+    def __init__(self, bit_rate: int, ctx: "Context | None" = None):
+        self.ctx = ctx or default_context()
+        self.bit_rate = int(bit_rate)
+
+    def add_frames(self, frame_bits: np.ndarray):
+        """frame_bits: uint8[n_frames, 24*bit_rate] (FrameProcessor::add_to_frame payloads). Returns (records, payload[n, 110*bit_rate/8])."""
+        b = _np(frame_bits, np.uint8).reshape(-1, 24 * self.bit_rate)
+        n = b.shape[0]
+        cap = max(n, 1)
+        rec = (_lib.SuperFrameC * cap)()
+        pay = np.zeros((cap, 110 * (self.bit_rate // 8)), np.uint8)
+        m = self.ctx.check(self.ctx.lib.dabstar_dabplus_decode(self.ctx.h, _ptr(b), self.bit_rate, n, rec, cap, _ptr(pay), MEM_HOST), "dabstar_dabplus_decode")
+        return list(rec[:m]), pay[:m]
+
+    @staticmethod
+    def access_units(rec, payload_row: np.ndarray) -> list[bytes]:
+        """The CRC-good access units of an accepted super-frame, as handed to the AAC decoder (mp4processor.cpp:333-372)."""
+        if not rec.ok:
+            return []
+        return [payload_row[rec.au_start[u]:rec.au_start[u + 1] - 2].tobytes() for u in range(rec.num_aus) if rec.au_state[u] == 1]
+
+
 @dataclass
 class ServiceComponent:
     sid: int

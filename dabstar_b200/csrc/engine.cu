@@ -109,6 +109,7 @@ struct dabstar_ctx
   DevBuf scratch[8];
   DevBuf demap_ring;    // exchange ring of the sliced demapper
   DevBuf vit_ws;        // symbols + decision words of the thread-per-code-word Viterbi
+  DevBuf d_gf, d_fc_syn; // DAB+ outer code: GF(2^8) / Fire code tables (built on first use)
   HostBuf arena;        // pinned staging of small uploads; reused after every stream synchronisation
   size_t arena_off = 0;
 
@@ -377,6 +378,73 @@ extern "C" int dabstar_ingest_convert(dabstar_ctx * ctx, const void * src, const
   if (int r = stage_out_end(ctx, ddst, dst, sizeof(float2) * (size_t)n_samples, mem)) return r;
   ctx->arena_off = 0; // the stream is idle: staged uploads have been consumed
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ DAB+ outer code (next row f2)
+extern "C" int dabstar_dabplus_decode(dabstar_ctx * ctx, const uint8_t * frame_bits, int bit_rate, int n_frames, dabstar_superframe * out, int cap,
+                                      uint8_t * payload, int mem)
+{
+  if (!ctx || (!frame_bits && n_frames > 0) || n_frames < 0 || cap < 0 || (cap > 0 && !out)) return DABSTAR_E_INVALID;
+  if (bit_rate < 8 || bit_rate > 192 || bit_rate % 8) return ctx->fail(DABSTAR_E_INVALID, "DAB+ bit rate %d", bit_rate);
+  const int n_windows = n_frames - 4;
+  if (n_windows <= 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->d_gf.p)
+  {
+    std::vector<uint8_t> gf;
+    std::vector<uint16_t> syn;
+    dabplus_host_tables(gf, syn);
+    CK(ctx->d_gf.reserve(gf.size()));
+    CK(ctx->d_fc_syn.reserve(sizeof(uint16_t) * syn.size()));
+    CK(cudaMemcpyAsync(ctx->d_gf.p, gf.data(), gf.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_fc_syn.p, syn.data(), sizeof(uint16_t) * syn.size(), cudaMemcpyHostToDevice, ctx->stream));
+    SYNC();
+  }
+  const int rs_dims = bit_rate / 8, sf_bytes = 110 * rs_dims;
+  const size_t n_bits = (size_t)n_frames * 24 * bit_rate;
+  const void * dbits;
+  if (int r = stage_in(ctx, ctx->scratch[0], frame_bits, n_bits, mem, &dbits)) return r;
+  CK(ctx->scratch[1].reserve(n_bits / 8));                                   // packed frames
+  CK(ctx->scratch[2].reserve((size_t)n_windows * sf_bytes));                 // decoded super-frame of every window
+  CK(ctx->scratch[3].reserve((size_t)n_windows * rs_dims));                  // Reed-Solomon return codes
+  CK(ctx->scratch[4].reserve(sizeof(SuperFrameRec) * (size_t)n_windows));
+  CK(launch_pack_bits(ctx->stream, (const uint8_t *)dbits, ctx->scratch[1].as<uint8_t>(), (long long)(n_bits / 8), &ctx->launches));
+  CK(launch_dabplus(ctx->stream, ctx->scratch[1].as<uint8_t>(), bit_rate, n_frames, ctx->d_gf.p, ctx->d_fc_syn.as<uint16_t>(), ctx->scratch[2].as<uint8_t>(),
+                    ctx->scratch[3].as<int8_t>(), ctx->scratch[4].as<SuperFrameRec>(), &ctx->launches));
+  std::vector<SuperFrameRec> rec((size_t)n_windows);
+  CK(cudaMemcpyAsync(rec.data(), ctx->scratch[4].p, sizeof(SuperFrameRec) * rec.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  SYNC();
+  // Mp4Processor::add_to_frame (mp4processor.cpp:95-180): which windows the processor attempts, given every window's outcome
+  int in_buf = 0, sync = 0, n_out = 0;
+  for (int f = 0; f < n_frames; f++)
+  {
+    if (++in_buf < 5) continue;
+    const int w = f - 4;
+    if (sync == 0)
+    {
+      if (rec[w].pre_ok) sync = 4;
+      else { in_buf = 4; continue; }
+    }
+    in_buf = 0;
+    if (rec[w].ok) sync = 4;
+    else if (--sync == 0) in_buf = 4;
+    if (n_out < cap)
+    {
+      const SuperFrameRec & r = rec[w];
+      dabstar_superframe & o = out[n_out];
+      o.first_frame = r.first_frame; o.ok = r.ok; o.rs_errors = r.rs_errors; o.rs_corrections = r.rs_corrections; o.fc_corrected = r.fc_corrected;
+      o.dac_rate = r.dac_rate; o.sbr_flag = r.sbr_flag; o.aac_channel_mode = r.aac_channel_mode; o.ps_flag = r.ps_flag; o.mpeg_surround = r.mpeg_surround;
+      o.num_aus = r.num_aus;
+      for (int i = 0; i < 7; i++) o.au_start[i] = r.au_start[i];
+      for (int i = 0; i < 6; i++) o.au_state[i] = r.au_state[i];
+      if (payload)
+        CK(cudaMemcpyAsync(payload + (size_t)n_out * sf_bytes, ctx->scratch[2].as<uint8_t>() + (size_t)w * sf_bytes, (size_t)sf_bytes,
+                           mem == DABSTAR_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    n_out++;
+  }
+  SYNC();
+  return n_out;
 }
 
 // ------------------------------------------------------------------------------------------------ stage taps

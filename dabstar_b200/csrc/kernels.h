@@ -3,6 +3,8 @@
 #include "common.cuh"
 #include "viterbi.cuh"
 
+#include <vector>
+
 namespace dab
 {
 // Device-resident constant tables, built once per context (tables.cu).
@@ -57,6 +59,18 @@ cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, const Frame
 
 // bits: one decoded bit per byte (8-byte aligned, n_bytes * 8 of them) -> out: n_bytes bytes, first bit most significant
 cudaError_t launch_pack_bits(cudaStream_t stream, const uint8_t * bits, uint8_t * out, long long n_bytes, unsigned long long * launch_counter);
+
+// dabplus_kernels.cu: one record per five-frame window of a DAB+ sub-channel
+struct SuperFrameRec
+{
+  int first_frame, pre_ok, ok, rs_errors, rs_corrections, fc_corrected;
+  int dac_rate, sbr_flag, aac_channel_mode, ps_flag, mpeg_surround;
+  int num_aus, au_start[7], au_state[6];
+};
+void dabplus_host_tables(std::vector<uint8_t> & gf_blob, std::vector<uint16_t> & fc_syn);
+// frames: n_frames x 3*bit_rate packed bytes; payload: (n_frames-4) x 110*(bit_rate/8); ler: (n_frames-4) x bit_rate/8; rec: n_frames-4
+cudaError_t launch_dabplus(cudaStream_t s, const uint8_t * frames, int bit_rate, int n_frames, const void * gf_tables, const uint16_t * fc_syn,
+                           uint8_t * payload, int8_t * ler, SuperFrameRec * rec, unsigned long long * lc);
 
 // ofdm_kernels.cu
 cudaError_t launch_init_ref_arg(cudaStream_t s, const DeviceTables & t, unsigned long long * lc);

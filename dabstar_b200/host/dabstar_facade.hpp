@@ -216,6 +216,35 @@ private:
   long mSeen = 0;
 };
 
+// backend/audio/mp4processor.h: the DAB+ outer code of one sub-channel (super-frame sync, RS(120,110), Fire code, AU CRCs).
+// Batch granular: add_frames takes a run of FrameProcessor::add_to_frame payloads; the AAC decoder stays a CPU consumer.
+class Mp4Processor
+{
+public:
+  using AuSink = std::function<void(const u8 * au, int len, const dabstar_superframe & sf)>;
+  Mp4Processor(Context & c, int bitRate, AuSink sink = nullptr) : mC(c), mBitRate(bitRate), mSink(std::move(sink)) {}
+  // iBits: nFrames x 24*bitRate bytes (one bit each). Returns the super-frames the processor attempted.
+  std::vector<dabstar_superframe> add_frames(const u8 * iBits, int nFrames)
+  {
+    std::vector<dabstar_superframe> rec((size_t)std::max(nFrames, 1));
+    const size_t sf = (size_t)110 * (mBitRate / 8);
+    std::vector<u8> pay(rec.size() * sf);
+    const int n = mC.check(dabstar_dabplus_decode(mC.get(), iBits, mBitRate, nFrames, rec.data(), (int)rec.size(), pay.data(), DABSTAR_MEM_HOST), "dabstar_dabplus_decode");
+    rec.resize((size_t)n);
+    if (mSink)
+      for (int i = 0; i < n; i++)
+        if (rec[i].ok)
+          for (int u = 0; u < rec[i].num_aus; u++)
+            if (rec[i].au_state[u] == 1) mSink(&pay[(size_t)i * sf + rec[i].au_start[u]], rec[i].au_start[u + 1] - rec[i].au_start[u] - 2, rec[i]);
+    return rec;
+  }
+
+private:
+  Context & mC;
+  int mBitRate;
+  AuSink mSink;
+};
+
 enum class ESoftBitType { SOFTDEC1 = 0, SOFTDEC2 = 1, SOFTDEC3 = 2 };
 
 // Frame granular: one call = store_reference_symbol_0 + 75 x decode_symbol + store_null_symbol_without_tii.

@@ -163,6 +163,29 @@ int dabstar_prs_correlate(dabstar_ctx * ctx, const float * samples, int n, float
  * symbols 0; offset_hz[i] = Hz or 100000 (IDX_NOT_FOUND). */
 int dabstar_estimate_carrier_offset(dabstar_ctx * ctx, const float * fft, int n, int32_t * offset_hz, int mem);
 
+/* ------------------------------------------------------------------------------------------------ DAB+ outer code */
+/* Mp4Processor::add_to_frame for a run of logical frames of one DAB+ sub-channel (backend/audio/mp4processor.cpp:95-334):
+ * super-frame synchronisation by Fire code (backend/firecode_checker.cpp), RS(120,110) over the bit_rate/8 interleaved code
+ * words (ReedSolomon(8, 0435, 0, 1, 10), backend/reed_solomon.cpp:140-260), Fire-code check with 6-bit burst correction of
+ * the decoded header, header fields, access-unit borders and CRCs (backend/crc.cpp:75-96). The AAC decoder stays a CPU
+ * consumer of the access units.
+ * frame_bits: n_frames x 24*bit_rate bytes, one bit each, exactly what Backend hands to FrameProcessor::add_to_frame
+ * (dabstar_decoder_msc_copy). out: one record per super-frame the processor ATTEMPTS, in stream order (at most cap are
+ * written); payload: 110*(bit_rate/8) bytes per record, the decoded super-frame (mOutVec) whatever the outcome.
+ * Returns the number of attempts or <0. */
+typedef struct
+{
+  int32_t first_frame;      /* index of the super-frame's first logical frame */
+  int32_t ok;               /* _process_reed_solomon_frame succeeded: the access units below are handed on */
+  int32_t rs_errors, rs_corrections, fc_corrected;
+  int32_t dac_rate, sbr_flag, aac_channel_mode, ps_flag, mpeg_surround;
+  int32_t num_aus;
+  int32_t au_start[7];      /* access unit u occupies payload[au_start[u] .. au_start[u+1]-3], followed by its 2-byte CRC */
+  int32_t au_state[6];      /* 0: length check failed (mp4processor.cpp:326), 1: CRC good, 2: CRC error */
+} dabstar_superframe;
+int dabstar_dabplus_decode(dabstar_ctx * ctx, const uint8_t * frame_bits, int bit_rate, int n_frames, dabstar_superframe * out, int cap,
+                           uint8_t * payload, int mem);
+
 /* ------------------------------------------------------------------------------------------------ multiplex configuration (FIG 0/0, 0/1, 0/2) */
 /* The part of FibDecoder the decode path depends on (decoder/fib_decoder.cpp:59-106 process_FIB,
  * fib_decoder_fig0.cpp:89-113 FIG 0/0, :142-227 FIG 0/1, :229-290 FIG 0/2, fib_table.h:51 short-form table): which

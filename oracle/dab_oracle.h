@@ -51,6 +51,26 @@ void * dabo_backend_new(int sub_ch_id, int start_cu, int size_cu, int short_form
 void   dabo_backend_free(void * h);
 int    dabo_backend_process(void * h, const int16_t * fragment, uint8_t * out);
 
+/* DAB+ outer code (dab_outer.c): ReedSolomon(8, 0435, 0, 1, 10).dec(in, out, 135) (backend/reed_solomon.cpp:140-260), FirecodeChecker
+ * (backend/firecode_checker.cpp), check_crc_bytes (backend/crc.cpp:89-96), Mp4Processor's super-frame handling (mp4processor.cpp:95-334) */
+int  dabo_rs_decode(const uint8_t * in120, uint8_t * out110);            /* returns corrections, 0, or -1 */
+void dabo_rs_encode(const uint8_t * in110, uint8_t * out120);            /* test-vector encoder */
+int  dabo_firecode_check(const uint8_t * x11);
+int  dabo_firecode_check_and_correct(uint8_t * x11);
+void dabo_firecode_syndrome_table(uint16_t * out65536);
+int  dabo_check_crc_bytes(const uint8_t * msg, int len);
+typedef struct
+{
+  int32_t first_frame;      /* logical frame (CIF) index of the super-frame's first block */
+  int32_t ok;               /* Reed-Solomon + Fire code accepted (Mp4Processor::_process_reed_solomon_frame) */
+  int32_t rs_errors, rs_corrections, fc_corrected;
+  int32_t dac_rate, sbr_flag, aac_channel_mode, ps_flag, mpeg_surround;
+  int32_t num_aus;
+  int32_t au_start[7];
+  int32_t au_state[6];      /* 0 bad length, 1 CRC good, 2 CRC error */
+} dabo_superframe;
+int  dabo_dabplus_run(const uint8_t * frame_bits, int bit_rate, int n_frames, dabo_superframe * out, int cap, uint8_t * payload);
+
 /* OFDM */
 void * dabo_ofdm_new(int soft_bit_type);
 void   dabo_ofdm_free(void * h);

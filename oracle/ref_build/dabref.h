@@ -16,6 +16,12 @@ void dabref_phase_table(float out_re_im[4096]);                  /* PhaseTable::
 void dabref_fft2048(const float * in, float * out, int sign);    /* the FFTW shim itself */
 
 /* channel decoding */
+/* DAB+ outer code: the reference's ReedSolomon(8, 0435, 0, 1, 10), FirecodeChecker and check_crc_bytes objects */
+int  dabref_rs_decode(const uint8_t * in120, uint8_t * out110);
+void dabref_rs_encode(const uint8_t * in110, uint8_t * out120);
+int  dabref_firecode_check(const uint8_t * x11);
+int  dabref_firecode_check_and_correct(uint8_t * x11);
+int  dabref_check_crc_bytes(const uint8_t * msg, int len);
 void dabref_viterbi(const int16_t * in, int frame_bits, uint8_t * out);                 /* ViterbiSpiral::deconvolve */
 void dabref_viterbi_ber(const int16_t * in, const uint8_t * punct, const uint8_t * out_bits, int frame_bits, int * bits, int * errors);
 int  dabref_protection(int short_form, int bit_rate, int prot_level, const int16_t * in, int in_len, uint8_t * out);

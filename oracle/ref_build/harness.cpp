@@ -2,6 +2,9 @@
 // Nothing here is product code; the CUDA path never links or loads this.
 #include "harness_internal.h"
 #include "dabref.h"
+#include "reed_solomon.h"
+#include "firecode_checker.h"
+#include "crc.h"
 
 #include <chrono>
 #include <cstring>
@@ -46,6 +49,30 @@ extern "C" void dabref_fft2048(const float * in, float * out, int sign)
   memcpy(out, bo.data(), sizeof(cf32) * cTu);
   fftwf_destroy_plan(p);
 }
+
+// ------------------------------------------------------------------------------------------------ DAB+ outer code
+// The reference's own ReedSolomon(8, 0435, 0, 1, 10) and FirecodeChecker as Mp4Processor uses them (mp4processor.cpp:52,184-241).
+extern "C" int dabref_rs_decode(const uint8_t * in120, uint8_t * out110)
+{
+  static ReedSolomon rs(8, 0435, 0, 1, 10);
+  return rs.dec(in120, out110, 135);
+}
+extern "C" void dabref_rs_encode(const uint8_t * in110, uint8_t * out120)
+{
+  static ReedSolomon rs(8, 0435, 0, 1, 10);
+  rs.enc(in110, out120, 135);
+}
+extern "C" int dabref_firecode_check(const uint8_t * x11)
+{
+  static FirecodeChecker fc;
+  return fc.check(x11) ? 1 : 0;
+}
+extern "C" int dabref_firecode_check_and_correct(uint8_t * x11)
+{
+  static FirecodeChecker fc;
+  return fc.check_and_correct_6bits(x11) ? 1 : 0;
+}
+extern "C" int dabref_check_crc_bytes(const uint8_t * msg, int len) { return check_crc_bytes(msg, len) ? 1 : 0; }
 
 // ------------------------------------------------------------------------------------------------ channel decoding
 extern "C" void dabref_viterbi(const int16_t * in, int frame_bits, uint8_t * out)

@@ -32,6 +32,15 @@ class FrameInfo(ctypes.Structure):
                 ("fic_ratio_after", ctypes.c_int32), ("fic_valid", ctypes.c_uint8 * 4)]
 
 
+class SuperFrame(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("first_frame", "ok", "rs_errors", "rs_corrections", "fc_corrected", "dac_rate", "sbr_flag",
+                                              "aac_channel_mode", "ps_flag", "mpeg_surround", "num_aus")] + [("au_start", ctypes.c_int32 * 7), ("au_state", ctypes.c_int32 * 6)]
+
+    def key(self):
+        return (self.first_frame, self.ok, self.rs_errors, self.rs_corrections, self.fc_corrected, self.dac_rate, self.sbr_flag, self.aac_channel_mode,
+                self.ps_flag, self.mpeg_surround, self.num_aus, tuple(self.au_start), tuple(self.au_state))
+
+
 def ref_available() -> bool:
     return os.path.exists(build.LIB_REF)
 
@@ -110,6 +119,34 @@ class Oracle:
                out.ctypes.data_as(ctypes.c_void_p))
         assert r == 0
         return out
+
+    # ---- DAB+ outer code
+    def rs_decode(self, cw: np.ndarray):
+        cw = np.ascontiguousarray(cw, np.uint8)
+        out = np.zeros(110, np.uint8)
+        return int(self.f("rs_decode")(_ptr(cw), _ptr(out))), out
+
+    def rs_encode(self, data: np.ndarray) -> np.ndarray:
+        data = np.ascontiguousarray(data, np.uint8)
+        out = np.zeros(120, np.uint8)
+        self.f("rs_encode")(_ptr(data), _ptr(out))
+        return out
+
+    def firecode_check(self, x: np.ndarray) -> bool:
+        return bool(self.f("firecode_check")(_ptr(np.ascontiguousarray(x, np.uint8))))
+
+    def firecode_check_and_correct(self, x: np.ndarray):
+        y = np.ascontiguousarray(x, np.uint8).copy()
+        return bool(self.f("firecode_check_and_correct")(_ptr(y))), y
+
+    def dabplus_run(self, frame_bits: np.ndarray, bit_rate: int):
+        """Mp4Processor over a run of logical frames (restatement only): list of SuperFrame records and the decoded super-frames."""
+        b = np.ascontiguousarray(frame_bits, np.uint8).reshape(-1, 24 * bit_rate)
+        cap = max(b.shape[0], 1)
+        rec = (SuperFrame * cap)()
+        pay = np.zeros((cap, 110 * (bit_rate // 8)), np.uint8)
+        n = int(self.f("dabplus_run")(_ptr(b), int(bit_rate), int(b.shape[0]), rec, cap, _ptr(pay)))
+        return list(rec[:n]), pay[:n]
 
     # ---- channel decoding
     def viterbi(self, soft: np.ndarray, frame_bits: int) -> np.ndarray:

@@ -982,7 +982,7 @@ k_demap2(const DemapWork * __restrict__ work, const FrameDesc * __restrict__ fra
 constexpr int DM3_LAG = 3;
 constexpr int DM3_STASH = DM3_LAG + 1;   // stash depth (power of two)
 static_assert((DM3_STASH & (DM3_STASH - 1)) == 0, "stash depth must be a power of two");
-constexpr int DM3_RING = 16;           // > 2 * DM3_LAG + 2: a slot is never overwritten while a slower warp may still read it
+constexpr int DM3_RING = 64;           // > 2 * lag + 2 (k_demap3: DM3_LAG, k_demap4: its LAG): a slot is never overwritten while a slower warp may still read it
 constexpr int DM3_WARPS = K_CARR / 64; // warps per recording
 constexpr int DM3_ROW4 = K_CARR / 2;   // float4 per spectrum row
 
@@ -1310,16 +1310,23 @@ __device__ __forceinline__ void dm4_pair(CarrierPair & st, float2 xr, float2 xi,
 
 constexpr int DM4_MAX_THREADS = 384; // at least two slices per recording: leaves 170 registers per thread
 
-template <int SOFT>
+// LAG: symbols between the arithmetic of a symbol and the write of its soft bits (the scale of symbol d is the total of
+// symbol d - 1, which the other warps of the recording publish at their own pace). A longer lag averages the pace of
+// the 24 warps over more symbols before anybody has to wait.
+template <int SOFT, int LAG>
 __global__ void __launch_bounds__(DM4_MAX_THREADS) k_demap4(const DemapWork * __restrict__ work, const FrameDesc * __restrict__ frames,
                                                      const uint8_t * __restrict__ null_is_tii, const float2 * __restrict__ X,
                                                      const int16_t * __restrict__ rel_of_k, OfdmStateDev * __restrict__ states,
                                                      int16_t * __restrict__ soft, unsigned long long * __restrict__ ring, int slices)
 {
-  extern __shared__ float4 dm4_smem[]; // [DM3_STASH][T] unscaled soft values of the last symbols | [DM4_PF][T] spectrum rows in flight
+  constexpr int STASH = LAG + 1; // stash depth (power of two)
+  static_assert((STASH & (STASH - 1)) == 0, "stash depth must be a power of two");
+  static_assert(DM3_RING > 2 * LAG + 2, "a ring slot must not be overwritten while a slower warp may still read it");
+  extern __shared__ float4 dm4_smem[]; // [STASH][T] unscaled soft values of the last symbols | [DM4_PF][T] spectrum rows in flight | [STASH][T / 32] output rows
   const int T = (int)blockDim.x;
   float4 * stash = dm4_smem;
-  float4 * rowbuf = dm4_smem + DM3_STASH * T;
+  float4 * rowbuf = dm4_smem + STASH * T;
+  int * orow_ring = reinterpret_cast<int *>(rowbuf + DM4_PF * T) + (threadIdx.x >> 5); // this warp's column: output row (slot * 75 + symbol - 1) of the last STASH symbols
   const int w = blockIdx.x / slices, slice = blockIdx.x - w * slices;
   const DemapWork wk = work[w];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -1353,15 +1360,12 @@ __global__ void __launch_bounds__(DM4_MAX_THREADS) k_demap4(const DemapWork * __
   int out_row0 = 0;
   bool tii = false;
   int g = 0;               // symbols decoded so far; tag of symbol g is g + 1
-  int orow[DM3_LAG];       // output rows (slot * 75 + symbol - 1) of the last DM3_LAG symbols, newest first
-#pragma unroll
-  for (int i = 0; i < DM3_LAG; i++) orow[i] = 0;
-  unsigned long long pre = 0; // prefetched ring word of the symbol whose total is needed next
+  unsigned long long pre = 0; // ring words (lane l < 24: warp l) of the symbol whose total scales this iteration's output
 
   // soft bits of symbol d (its unscaled values are in the stash); total = sum |r| of symbol d - 1 (unused for d = 0)
   auto emit = [&](int d, int o_row, float total) {
     const float w2 = d == 0 ? rcp_ftz(mean_value0) * W2 : rcp_ftz(total) * (W2 * (float)K_CARR);
-    const float4 r = stash[(d & (DM3_STASH - 1)) * T + tid]; // (re0, re1, im0, im1)
+    const float4 r = stash[(d & (STASH - 1)) * T + tid]; // (re0, re1, im0, im1)
     const float2 vre = mul2(make_float2(r.x, r.y), f2(w2)), vim = mul2(make_float2(r.z, r.w), f2(w2));
     int a = __float2int_rz(vre.x), b = __float2int_rz(vre.y), c = __float2int_rz(vim.x), e = __float2int_rz(vim.y);
     if (max(max(a, b), max(c, e)) == 0x7fffffff)
@@ -1380,6 +1384,7 @@ __global__ void __launch_bounds__(DM4_MAX_THREADS) k_demap4(const DemapWork * __
     return v;
   };
   float part_prev = 0.0f; // this thread's |r| sum of symbol g - 1, published (reduced over the warp) one symbol late
+  const bool upper = (lane & 16) != 0;
 
   for (int q = 0; q < total_rows; q++)
   {
@@ -1401,34 +1406,38 @@ __global__ void __launch_bounds__(DM4_MAX_THREADS) k_demap4(const DemapWork * __
     {
       if (row > 0)
       {
-        const int d = g - DM3_LAG; // symbol whose soft bits are written in this iteration
-        // Two shuffle chains that do not depend on this symbol's arithmetic, so the scheduler overlaps them with it:
-        // (1) the warp's share of sum |r| of the PREVIOUS symbol, published under tag g;
-        if (g > 0)
-        {
-          const float part = wsum(part_prev);
-          if (lane == 0)
-            st_volatile_global_b64(my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM3_WARPS + gw,
-                                   ((unsigned long long)(unsigned)g << 32) | (unsigned long long)__float_as_uint(part));
-        }
-        // (2) the total of symbol d - 1 from the ring words fetched one iteration ago (valid if every tag reads d).
-        const float tot_fast = wsum(lane < DM3_WARPS ? __uint_as_float((unsigned)pre) : 0.0f);
+        const int d = g - LAG; // symbol whose soft bits are written in this iteration
+        // ONE shuffle chain, independent of this symbol's arithmetic (the scheduler overlaps the two), reduces two values:
+        // a: this warp's share of sum |r| of the PREVIOUS symbol, published under tag g (lower half warp);
+        // b: the total of symbol d - 1 from the ring words fetched one iteration ago (upper half warp; valid if every tag reads d).
+        // After the first exchange the lower lanes hold a[l] + a[l + 16], the upper ones b[l] + b[l - 16]; the remaining
+        // four steps stay inside a half, so both sums come out exactly as two separate butterflies would give them.
+        const float b_in = lane < DM3_WARPS ? __uint_as_float((unsigned)pre) : 0.0f;
         const bool tags_ok = __all_sync(0xffffffffu, lane >= DM3_WARPS || (unsigned)(pre >> 32) == (unsigned)d);
+        const unsigned long long pre_used = pre;
+        // ring words for the NEXT iteration's output (symbol d + 1 is scaled by the total of symbol d, published at
+        // iteration d + 1 of every warp): requested now, a whole iteration before they are looked at
+        if (d >= 0 && lane < DM3_WARPS) pre = ld_volatile_global_b64(my_ring + (size_t)(d & (DM3_RING - 1)) * DM3_WARPS + lane);
+        float v = (upper ? b_in : part_prev) + __shfl_xor_sync(0xffffffffu, upper ? part_prev : b_in, 16);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const float tot_fast = __shfl_sync(0xffffffffu, v, 16);
         float2 o_re, o_im, r_abs;
         dm4_pair<SOFT>(st, xr, xi, rr, ri, ref_abs, ref_inv, cterm, o_re, o_im, r_abs);
         part_prev = r_abs.x + r_abs.y;
-        stash[(g & (DM3_STASH - 1)) * T + tid] = make_float4(o_re.x, o_re.y, o_im.x, o_im.y);
+        stash[(g & (STASH - 1)) * T + tid] = make_float4(o_re.x, o_re.y, o_im.x, o_im.y);
+        if (lane == 0) orow_ring[(g & (STASH - 1)) * (T >> 5)] = out_row0 + (row - 1);
+        __syncwarp();
+        // (the store sits behind the arithmetic so that the chain above shares a basic block with it)
+        if (lane == 0 && g > 0)
+          st_volatile_global_b64(my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM3_WARPS + gw,
+                                 ((unsigned long long)(unsigned)g << 32) | (unsigned long long)__float_as_uint(v));
         if (d >= 0)
         {
           float tot = tot_fast;
-          if (d > 0 && !tags_ok) tot = dm3_total(my_ring + (size_t)((d - 1) & (DM3_RING - 1)) * DM3_WARPS, pre, (unsigned)d, lane);
-          emit(d, orow[DM3_LAG - 1], tot);
+          if (d > 0 && !tags_ok) tot = dm3_total(my_ring + (size_t)((d - 1) & (DM3_RING - 1)) * DM3_WARPS, pre_used, (unsigned)d, lane);
+          emit(d, orow_ring[(d & (STASH - 1)) * (T >> 5)], tot);
         }
-        // ring words for the next iteration's output (symbol d + 1 is scaled by the total of symbol d, published at iteration d + 1)
-        if (d >= 0 && lane < DM3_WARPS) pre = ld_volatile_global_b64(my_ring + (size_t)(d & (DM3_RING - 1)) * DM3_WARPS + lane);
-#pragma unroll
-        for (int i = DM3_LAG - 1; i > 0; i--) orow[i] = orow[i - 1];
-        orow[0] = out_row0 + (row - 1);
         g++;
       }
       // this row is the phase reference of the next symbol
@@ -1456,9 +1465,9 @@ __global__ void __launch_bounds__(DM4_MAX_THREADS) k_demap4(const DemapWork * __
       st_volatile_global_b64(my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM3_WARPS + gw,
                              ((unsigned long long)(unsigned)g << 32) | (unsigned long long)__float_as_uint(part));
   }
-  // drain: the last DM3_LAG symbols
+  // drain: the last LAG symbols
 #pragma unroll
-  for (int i = DM3_LAG - 1; i >= 0; i--)
+  for (int i = LAG - 1; i >= 0; i--)
   {
     const int d = g - 1 - i;
     if (d < 0) continue;
@@ -1470,7 +1479,7 @@ __global__ void __launch_bounds__(DM4_MAX_THREADS) k_demap4(const DemapWork * __
       if (lane < DM3_WARPS) word = ld_volatile_global_b64(slot + lane);
       tot = dm3_total(slot, word, (unsigned)d, lane);
     }
-    emit(d, orow[i], tot);
+    emit(d, orow_ring[(d & (STASH - 1)) * (T >> 5)], tot);
   }
   sd.integ[k0] = st.integ.x; sd.integ[k0 + 1] = st.integ.y;
   sd.stddev[k0] = st.stddev.x; sd.stddev[k0 + 1] = st.stddev.y;
@@ -1731,7 +1740,11 @@ cudaError_t launch_reorder_frames(cudaStream_t s, const DeviceTables & t, const 
 
 size_t demap_ring_bytes(int n_work) { return sizeof(unsigned long long) * (size_t)std::max(n_work, 1) * DM3_RING * DM3_WARPS; }
 static size_t demap3_smem_bytes(int threads) { return sizeof(float4) * (size_t)DM3_STASH * (size_t)threads; }
-static size_t demap4_smem_bytes(int threads) { return sizeof(float4) * (size_t)(DM3_STASH + DM4_PF) * (size_t)threads; }
+static size_t demap4_smem_bytes(int threads, int lag) { return sizeof(float4) * (size_t)(lag + 1 + DM4_PF) * (size_t)threads + sizeof(int) * (size_t)(lag + 1) * (size_t)(threads / 32); }
+template <int LAG> static const void * demap4_fn(int soft_bit_type)
+{
+  return soft_bit_type == 0 ? (const void *)k_demap4<0, LAG> : (soft_bit_type == 1 ? (const void *)k_demap4<1, LAG> : (const void *)k_demap4<2, LAG>);
+}
 
 cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork * work, int n_work, const FrameDesc * frames,
                          const uint8_t * null_is_tii, const float2 * X, OfdmStateDev * states, int soft_bit_type, int16_t * soft,
@@ -1765,9 +1778,20 @@ cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork
   }
   if (ring == nullptr) return cudaErrorInvalidValue;
   static const bool use_v3 = getenv("DABSTAR_DEMAP_V3") != nullptr; // scalar arithmetic, register prefetch (kept for comparison)
+  static const int lag = getenv("DABSTAR_DEMAP_LAG") ? atoi(getenv("DABSTAR_DEMAP_LAG")) : 7; // 3 or 7 symbols between arithmetic and output
   const void * fn = use_v3 ? (soft_bit_type == 0 ? (const void *)k_demap3<0> : (soft_bit_type == 1 ? (const void *)k_demap3<1> : (const void *)k_demap3<2>))
-                           : (soft_bit_type == 0 ? (const void *)k_demap4<0> : (soft_bit_type == 1 ? (const void *)k_demap4<1> : (const void *)k_demap4<2>));
-  auto smem_bytes = [&](int threads) { return use_v3 ? demap3_smem_bytes(threads) : demap4_smem_bytes(threads); };
+                           : (lag == 3 ? demap4_fn<3>(soft_bit_type) : (lag == 15 ? demap4_fn<15>(soft_bit_type) : demap4_fn<7>(soft_bit_type)));
+  auto smem_bytes = [&](int threads) { return use_v3 ? demap3_smem_bytes(threads) : demap4_smem_bytes(threads, lag == 3 ? 3 : (lag == 15 ? 15 : 7)); };
+  if (!use_v3)
+  {
+    static bool attr_set[3] = { false, false, false }; // (per soft-bit type; the lag is fixed for the process)
+    if (!attr_set[soft_bit_type])
+    {
+      cudaError_t ea = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(DM4_MAX_THREADS));
+      if (ea != cudaSuccess) return ea;
+      attr_set[soft_bit_type] = true;
+    }
+  }
   // slices per recording: fill the SMs as evenly as the co-residency limit allows
   static int n_sm = 0;
   if (n_sm == 0)

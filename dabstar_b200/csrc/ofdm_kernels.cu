@@ -1802,7 +1802,7 @@ cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork
   }
   const int cand[7] = { 1, 2, 3, 4, 6, 8, 12 };
   int best_s = 0, best_cap = 0;
-  double best_eff = -1.0;
+  long long best_cost = -1;
   for (int ci = 0; ci < 7; ci++)
   {
     const int sl = cand[ci], threads = DM3_ROW4 / sl;
@@ -1810,11 +1810,13 @@ cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem_bytes(threads)) != cudaSuccess || occ <= 0) continue;
     const int cap = occ * n_sm;                       // CTAs that can be resident at once
-    const int recs = std::min(n_work, cap / sl);      // recordings per launch
-    if (recs <= 0) continue;
-    const int ctas = recs * sl, per_sm = (ctas + n_sm - 1) / n_sm;
-    const double eff = (double)ctas / ((double)per_sm * n_sm) * (recs == n_work ? 1.0 : 0.999);
-    if (eff > best_eff + 1e-9) { best_eff = eff; best_s = sl; best_cap = cap; }
+    const int per_launch = cap / sl;                  // recordings per launch
+    if (per_launch <= 0) continue;
+    // cost: every launch lasts as long as its busiest SM has threads to run (threads per SM summed over the launches)
+    long long cost = 0;
+    for (int first = 0; first < n_work; first += per_launch)
+      cost += (long long)((std::min(per_launch, n_work - first) * sl + n_sm - 1) / n_sm) * threads;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = sl; best_cap = cap; }
   }
   if (best_s == 0) return cudaErrorLaunchOutOfResources;
   const int threads = DM3_ROW4 / best_s, per_launch = std::max(1, best_cap / best_s);

@@ -369,6 +369,14 @@ class OfdmDecoder:
         self.ctx.check(self.ctx.lib.dabstar_ofdm_state_get(self.ctx.h, self.st, which, _ptr(out)), "dabstar_ofdm_state_get")
         return out
 
+    QUALITY = ("mer_db", "snr_db", "mean_value", "mean_power_overall", "noise_power", "sigma_freq_corr")
+
+    def quality(self) -> dict:
+        """SLcdData figures (ofdm_decoder.h:53-61) from the current state."""
+        out = np.zeros(6, np.float32)
+        self.ctx.check(self.ctx.lib.dabstar_ofdm_state_quality(self.ctx.h, self.st, _ptr(out)), "dabstar_ofdm_state_quality")
+        return dict(zip(self.QUALITY, (float(v) for v in out)))
+
     def decode_frames(self, fft: np.ndarray, clock_err: np.ndarray | None = None, null_is_tii: np.ndarray | None = None) -> np.ndarray:
         """fft: complex64[n, 77, 2048] (symbol 0, symbols 1..75, null). Returns int16[n, 75, 3072]."""
         fft = _np(fft, np.complex64).reshape(-1, 77, 2048)
@@ -499,6 +507,12 @@ class DabProcessor:
         cnt = np.zeros(8, np.int64)
         lib.dabstar_decoder_counters(self.h, recording, _ptr(cnt))
         return RecordingResult(nf, list(info)[:nf], bits, valid, msc, cnt)
+
+    def quality(self, recording: int) -> dict:
+        """SLcdData figures (MER, SNR, ...) of a recording's OFDM decoder at the end of the last run()."""
+        out = np.zeros(6, np.float32)
+        self.ctx.check(self.ctx.lib.dabstar_decoder_quality(self.h, recording, _ptr(out)), "dabstar_decoder_quality")
+        return dict(zip(OfdmDecoder.QUALITY, (float(v) for v in out)))
 
     STAGES = ("time_sync", "prs_corr", "cp_corr", "coarse_afc", "ingest_fft", "demap", "fic_viterbi", "msc_viterbi")
 

@@ -85,8 +85,9 @@ __global__ void k_ofdm_state_init(OfdmStateDev * __restrict__ st, int count, int
   {
     float * f = reinterpret_cast<float *>(st) + i;
     const bool is_mean_value = (i % per) == offsetof(OfdmStateDev, mean_value) / sizeof(float);
+    const bool is_pow_carry = (i % per) == offsetof(OfdmStateDev, pow_carry) / sizeof(float);
     if (is_mean_value) { if (full) *f = 1.0f; }
-    else *f = 0.0f;
+    else *f = is_pow_carry ? 1.0f : 0.0f; // mMeanPowerOvrAll = 1 (ofdm_decoder.h:99, ofdm_decoder.cpp:98)
   }
 }
 
@@ -668,14 +669,55 @@ extern "C" int dabstar_ofdm_state_reset(dabstar_ctx * ctx, dabstar_ofdm_state * 
   CK(cudaSetDevice(ctx->device));
   return ofdm_state_init(ctx, st->dev, false);
 }
+// The figures OfdmDecoder hands to signal_show_lcd_data (ofdm_decoder.cpp:326-345, _compute_noise_Power :357-371) from a
+// recording's state: out = { MER dB, SNR dB, mMeanValue, mMeanPowerOvrAll, noise power, sqrt(mMeanSigmaSqFreqCorr) }.
+static int quality_from_state(dabstar_ctx * ctx, const OfdmStateDev * dev, float sigma_sq_freq_corr, float out[6])
+{
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::unique_ptr<OfdmStateDev> h(new OfdmStateDev);
+  CK(cudaMemcpy(h.get(), dev, sizeof(OfdmStateDev), cudaMemcpyDeviceToHost));
+  // mMeanPowerOvrAll = A^G y0 + b sum_k (1-b)^(1535-k) c_k (kernels.h, OfdmStateDev)
+  double acc = 0.0, w = 1.0;
+  for (int k = K_CARR - 1; k >= 0; k--) { acc += w * (double)h->pow_acc[k]; w *= 1.0 - POW_ALL_BETA; }
+  const float mean_pow_all = (float)((double)h->pow_carry + POW_ALL_BETA * acc);
+  float sum_noise = 0.0f, sd = 0.0f;
+  for (int k = 0; k < K_CARR; k++) { sum_noise += h->null_pow[k]; sd += h->stddev[k]; }
+  if (sum_noise == 0.0f) sum_noise = (1.0f / 32767.0f) * (1.0f / 32767.0f) * (float)K_CARR;
+  const float noise = sum_noise / (float)K_CARR;
+  float snr = (mean_pow_all - noise) / noise;
+  if (snr <= 0.0f) snr = 0.1f;
+  sd /= (float)K_CARR;
+  const float pi_4 = 0.78539816339744830962f;
+  out[0] = 10.0f * log10f(pi_4 * pi_4 / sd);
+  out[1] = 10.0f * log10f(snr);
+  out[2] = h->mean_value;
+  out[3] = mean_pow_all;
+  out[4] = noise;
+  out[5] = sqrtf(sigma_sq_freq_corr);
+  return 0;
+}
+
 extern "C" int dabstar_ofdm_state_get(dabstar_ctx * ctx, dabstar_ofdm_state * st, int which, float * out)
 {
   if (!ctx || !st || !out || which < 0 || which > 5) return DABSTAR_E_INVALID;
   CK(cudaSetDevice(ctx->device));
   OfdmStateDev * d = st->dev;
-  const float * src[6] = { d->integ, d->stddev, d->mean_pow, d->mean_sigma, d->null_pow, &d->mean_value };
-  CK(cudaMemcpy(out, src[which], sizeof(float) * (which == 5 ? 2 : K_CARR), cudaMemcpyDeviceToHost));
+  if (which == 5)
+  {
+    float q[6];
+    if (int r = quality_from_state(ctx, d, 0.0f, q)) return r;
+    out[0] = q[2]; out[1] = q[3];
+    return 0;
+  }
+  const float * src[5] = { d->integ, d->stddev, d->mean_pow, d->mean_sigma, d->null_pow };
+  CK(cudaMemcpy(out, src[which], sizeof(float) * K_CARR, cudaMemcpyDeviceToHost));
   return 0;
+}
+extern "C" int dabstar_ofdm_state_quality(dabstar_ctx * ctx, dabstar_ofdm_state * st, float out[6])
+{
+  if (!ctx || !st || !out) return DABSTAR_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  return quality_from_state(ctx, st->dev, 0.0f, out);
 }
 
 extern "C" int dabstar_ofdm_decode_frames(dabstar_ctx * ctx, dabstar_ofdm_state * st, const float * fft, int n_frames, const float * clock_err,
@@ -1985,6 +2027,24 @@ extern "C" int dabstar_decoder_counters(const dabstar_decoder * dec, int recordi
   out[0] = R.cnt_good_fibs; out[1] = R.cnt_sync_ok; out[2] = R.cnt_sync_fail; out[3] = R.pos;
   out[4] = R.cnt_windows; out[5] = R.cnt_cut; out[6] = R.n_slots; out[7] = R.cnt_heavy;
   return 0;
+}
+extern "C" int dabstar_decoder_quality(const dabstar_decoder * dec, int recording, float out[6])
+{
+  if (!dec || !out || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  if (dec->d_states.cap < sizeof(OfdmStateDev) * dec->recs.size()) return DABSTAR_E_INVALID; // no run yet
+  dabstar_ctx * ctx = dec->ctx;
+  CK(cudaSetDevice(ctx->device));
+  // mMeanSigmaSqFreqCorr (ofdm_decoder.cpp:296-300): at symbol 1 of every frame, from the cyclic-prefix phase the
+  // previous frame left behind (dab_processor.cpp:236-240,342); not touched by OfdmDecoder::reset()
+  const Recording & R = dec->recs[recording];
+  float sigma = 0.0f, phase = 0.0f;
+  for (const auto & fi : R.frames)
+  {
+    const float fc = phase / TWO_PI_F * 1000.0f;
+    sigma += 0.2f * (fc * fc - sigma);
+    phase = fi.phase_cp;
+  }
+  return quality_from_state(ctx, dec->d_states.as<OfdmStateDev>() + recording, sigma, out);
 }
 extern "C" double dabstar_decoder_last_ms(const dabstar_decoder * dec) { return dec ? dec->last_ms : 0.0; }
 extern "C" int dabstar_decoder_stage_ms(const dabstar_decoder * dec, double ms[8], int64_t launches[8])

@@ -23,9 +23,18 @@ struct OfdmStateDev
 {
   float integ[K_CARR], stddev[K_CARR], mean_pow[K_CARR], mean_sigma[K_CARR], null_pow[K_CARR];
   float mean_value;
-  float mean_pow_all;
-  float pad[2];
+  float mean_pow_all; // unused on the device (see pow_acc)
+  // mMeanPowerOvrAll (ofdm_decoder.cpp:214) is ONE IIR that walks the 1536 carriers of every symbol in turn:
+  //   y <- y + b (p_k - y), b = 0.005 / 1536.
+  // Over G symbols that is  y = A^G y0 + b sum_k w_k c_k  with A = (1-b)^1536, w_k = (1-b)^(1535-k) and the per-carrier
+  // recurrence c_k <- A c_k + p_k, which the demapper keeps in pow_acc (one packed FMA per symbol); pow_carry = A^G y0
+  // (y0 = 1 at reset()). The weighted sum is formed on the host when the figure is asked for.
+  float pow_carry;
+  float pad[1];
+  float pow_acc[K_CARR];
 };
+constexpr double POW_ALL_BETA = 3.255208184782532e-06;   // (float)(0.005f / 1536.0f)
+constexpr float POW_ALL_DECAY = 0.9950124713222692f;     // (1 - beta)^1536
 
 struct DemapWork
 {

@@ -1263,7 +1263,7 @@ __device__ __forceinline__ float2 folded_phase2(float2 re, float2 im)
 // symbol and of the phase reference; returns the unscaled soft values in o_re/o_im and |r| of both carriers in r_abs.
 template <int SOFT>
 __device__ __forceinline__ void dm4_pair(CarrierPair & st, float2 xr, float2 xi, float2 rr, float2 ri, float2 ref_abs, float2 ref_inv, float2 cterm,
-                                         float2 & o_re, float2 & o_im, float2 & r_abs)
+                                         float2 & o_re, float2 & o_im, float2 & r_abs, float2 & pow_acc)
 {
   constexpr float ALPHA = 0.005f;
   // raw = x conj(ref) / |ref|
@@ -1281,6 +1281,7 @@ __device__ __forceinline__ void dm4_pair(CarrierPair & st, float2 xr, float2 xi,
   st.stddev = fma2(fma2(dv, dv, neg2(st.stddev)), f2(ALPHA), st.stddev);
   const float2 pw = fma2(zr, zr, mul2(zi, zi));
   st.mean_pow = fma2(add2(pw, neg2(st.mean_pow)), f2(ALPHA), st.mean_pow);
+  pow_acc = fma2(pow_acc, f2(POW_ALL_DECAY), pw); // this carrier's share of mMeanPowerOvrAll (kernels.h, OfdmStateDev)
   const float2 lvl = make_float2(sqrt_ftz(st.mean_pow.x), sqrt_ftz(st.mean_pow.y));
   const float2 dr = fma2(lvl, f2(-0.70710678118654752440f), make_float2(fabsf(zr.x), fabsf(zr.y)));
   const float2 di = fma2(lvl, f2(-0.70710678118654752440f), make_float2(fabsf(zi.x), fabsf(zi.y)));
@@ -1342,6 +1343,8 @@ __global__ void __launch_bounds__(DM4_MAX_THREADS) k_demap4(const DemapWork * __
     st = CarrierPair{ make_float2(sd.integ[k0], sd.integ[k0 + 1]), make_float2(sd.stddev[k0], sd.stddev[k0 + 1]), make_float2(sd.mean_pow[k0], sd.mean_pow[k0 + 1]),
                       make_float2(sd.mean_sigma[k0], sd.mean_sigma[k0 + 1]), make_float2(sd.null_pow[k0], sd.null_pow[k0 + 1]) };
   const float mean_value0 = sd.mean_value; // not touched by reset() (ofdm_decoder.cpp:90-101)
+  float2 pow_acc = wk.reset ? f2(0.f) : make_float2(sd.pow_acc[k0], sd.pow_acc[k0 + 1]);
+  const float pow_carry0 = wk.reset ? 1.0f : sd.pow_carry; // mMeanPowerOvrAll = 1 at reset() (ofdm_decoder.cpp:98)
   const float2 gk = make_float2((float)(K_CARR / 2 - rel_of_k[k0]) / (float)(K_CARR / 2), (float)(K_CARR / 2 - rel_of_k[k0 + 1]) / (float)(K_CARR / 2));
   constexpr float W2 = SOFT == 0 ? -100.0f : -140.0f;
 
@@ -1423,7 +1426,7 @@ __global__ void __launch_bounds__(DM4_MAX_THREADS) k_demap4(const DemapWork * __
         for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         const float tot_fast = __shfl_sync(0xffffffffu, v, 16);
         float2 o_re, o_im, r_abs;
-        dm4_pair<SOFT>(st, xr, xi, rr, ri, ref_abs, ref_inv, cterm, o_re, o_im, r_abs);
+        dm4_pair<SOFT>(st, xr, xi, rr, ri, ref_abs, ref_inv, cterm, o_re, o_im, r_abs, pow_acc);
         part_prev = r_abs.x + r_abs.y;
         stash[(g & (STASH - 1)) * T + tid] = make_float4(o_re.x, o_re.y, o_im.x, o_im.y);
         if (lane == 0) orow_ring[(g & (STASH - 1)) * (T >> 5)] = out_row0 + (row - 1);
@@ -1486,6 +1489,7 @@ __global__ void __launch_bounds__(DM4_MAX_THREADS) k_demap4(const DemapWork * __
   sd.mean_pow[k0] = st.mean_pow.x; sd.mean_pow[k0 + 1] = st.mean_pow.y;
   sd.mean_sigma[k0] = st.mean_sigma.x; sd.mean_sigma[k0 + 1] = st.mean_sigma.y;
   sd.null_pow[k0] = st.null_pow.x; sd.null_pow[k0 + 1] = st.null_pow.y;
+  sd.pow_acc[k0] = pow_acc.x; sd.pow_acc[k0 + 1] = pow_acc.y;
   // mMeanValue after the last symbol (every other thread has read sd.mean_value before it published anything)
   if (gw == 0 && g > 0)
   {
@@ -1495,6 +1499,7 @@ __global__ void __launch_bounds__(DM4_MAX_THREADS) k_demap4(const DemapWork * __
     const float tot = dm3_total(slot, word, (unsigned)g, lane);
     if (lane == 0) sd.mean_value = tot / (float)K_CARR;
   }
+  if (t_rec == 0) sd.pow_carry = pow_carry0 * powf(POW_ALL_DECAY, (float)g); // (only this thread reads or writes pow_carry)
 }
 
 // ------------------------------------------------------------------------------------------------ time sync (S1)

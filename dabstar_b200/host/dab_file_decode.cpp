@@ -124,6 +124,11 @@ int main(int argc, char ** argv)
       if (fic) fclose(fic);
       for (FILE * o : outs) if (o) fclose(o);
       printf("%s: %d frames, %ld good FIBs, %.2f ms device time\n", files[r], proc.n_frames((int)r), fibs, proc.last_ms());
+      if (proc.n_frames((int)r) > 0)
+      {
+        const dabstar::SLcdData q = proc.lcd_data((int)r);
+        printf("%s: MER %.1f dB, SNR %.1f dB\n", files[r], q.MER, q.SNR);
+      }
     }
   }
   catch (const std::exception & e) { fprintf(stderr, "error: %s\n", e.what()); return 1; }

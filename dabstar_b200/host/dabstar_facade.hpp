@@ -247,6 +247,12 @@ private:
 
 enum class ESoftBitType { SOFTDEC1 = 0, SOFTDEC2 = 1, SOFTDEC3 = 2 };
 
+// OfdmDecoder::SLcdData (ofdm/ofdm_decoder.h:53-61) plus the two state scalars it is computed from
+struct SLcdData
+{
+  f32 MER, SNR, MeanValue, MeanPowerOvrAll, NoisePower, MeanSigmaSqFreqCorr;
+};
+
 // Frame granular: one call = store_reference_symbol_0 + 75 x decode_symbol + store_null_symbol_without_tii.
 class OfdmDecoder
 {
@@ -260,6 +266,12 @@ public:
   {
     mC.check(dabstar_ofdm_decode_frames(mC.get(), mSt, reinterpret_cast<const float *>(iFft), nFrames, iClockErr, iNullIsTii, (int)mType, oBits, DABSTAR_MEM_HOST),
              "dabstar_ofdm_decode_frames");
+  }
+  SLcdData lcd_data() const // what signal_show_lcd_data would carry now
+  {
+    float q[6];
+    mC.check(dabstar_ofdm_state_quality(mC.get(), mSt, q), "dabstar_ofdm_state_quality");
+    return SLcdData{ q[0], q[1], q[2], q[3], q[4], q[5] };
   }
 
 private:
@@ -327,6 +339,12 @@ public:
     return v;
   }
   int n_frames(int recording) const { return dabstar_decoder_n_frames(mDec, recording); }
+  SLcdData lcd_data(int recording) const // the recording's OfdmDecoder figures at the end of the run
+  {
+    float q[6];
+    mC.check(dabstar_decoder_quality(mDec, recording, q), "dabstar_decoder_quality");
+    return SLcdData{ q[0], q[1], q[2], q[3], q[4], q[5] };
+  }
   std::vector<dabstar_frame_info> frame_info(int recording) const
   {
     std::vector<dabstar_frame_info> v((size_t)std::max(0, n_frames(recording)));

@@ -148,6 +148,12 @@ int  dabstar_ofdm_state_reset(dabstar_ctx * ctx, dabstar_ofdm_state * st);      
 /* which: 0 integAbsPhase 1 stdDevSq 2 meanPower 3 meanSigmaSq (1536 each, nominal carrier order)
  *        4 nullPower (1536, nominal carrier order k -> bin map_k_to_fft_bin(k)) 5 {meanValue, 0} */
 int  dabstar_ofdm_state_get(dabstar_ctx * ctx, dabstar_ofdm_state * st, int which, float * out);
+/* What OfdmDecoder reports through signal_show_lcd_data (SLcdData, ofdm/ofdm_decoder.h:53-61; ofdm_decoder.cpp:326-345,
+ * _compute_noise_Power :357-371), from the current state:
+ * out = { MER dB, SNR dB, mMeanValue, mMeanPowerOvrAll, noise power, sqrt(mMeanSigmaSqFreqCorr) (0 for a bare state) }.
+ * mMeanPowerOvrAll is a serial IIR over the carriers of every symbol; the demapper keeps an algebraically equal
+ * per-carrier form (csrc/kernels.h), so the figure agrees with the reference to float rounding (1e-4 relative). */
+int  dabstar_ofdm_state_quality(dabstar_ctx * ctx, dabstar_ofdm_state * st, float out[6]);
 /* fft: n_frames x 77 x 2048 complex float, rows = symbol 0 (store_reference_symbol_0), symbols 1..75
  * (decode_symbol), null symbol (store_null_symbol_without_tii when null_is_tii[f]==0);
  * clock_err: n_frames floats (iClockErr); soft: n_frames x 75 x 3072 int16. */
@@ -277,6 +283,9 @@ int64_t dabstar_decoder_eti_copy(const dabstar_decoder * dec, int recording, uin
 /* out[0] good FIBs, [1] time-sync established count, [2] time-sync failures, [3] samples consumed,
  * [4] speculation windows run, [5] windows cut short by verification, [6] frames decoded,
  * [7] frames sent through the FFT/demap/FIC pass (exceeds [6] by replayed and partial frames) */
+/* dabstar_ofdm_state_quality for a recording's decoder at the end of the last run (the reference shows these figures
+ * every 5 frames; mMeanSigmaSqFreqCorr is replayed from the per-frame cyclic-prefix phases). */
+int     dabstar_decoder_quality(const dabstar_decoder * dec, int recording, float out[6]);
 int     dabstar_decoder_counters(const dabstar_decoder * dec, int recording, int64_t out[8]);
 /* Device time of the last dabstar_decoder_run in milliseconds (CUDA events on the context's stream). */
 double  dabstar_decoder_last_ms(const dabstar_decoder * dec);

@@ -612,6 +612,10 @@ typedef struct
   cf32 ref[T_U];
   float integ[K_CARR], stddev[K_CARR], mean_pow[K_CARR], mean_sigma[K_CARR], null_pow[T_U];
   float mean_value, mean_pow_all;
+  /* LCD statistics (ofdm_decoder.cpp:154-158,296-300,326-352; members ofdm_decoder.h:86-88,103) */
+  int show_cnt, next_shown, n_lcd;
+  float sigma_sq_freq_corr;
+  float lcd[6]; /* last SLcdData: CurOfdmSymbolNo, MeanSigmaSqFreqCorr, SNR, MER, TestData1, TestData2 */
 } ofdm_t;
 
 void dabo_ofdm_reset(void * h)
@@ -627,6 +631,7 @@ void * dabo_ofdm_new(int soft_bit_type)
   ofdm_t * d = (ofdm_t *)calloc(1, sizeof(*d));
   d->soft_type = soft_bit_type;
   d->mean_value = 1.0f;
+  d->next_shown = 1;
   dabo_freq_interleaver(d->bin);
   dabo_ofdm_reset(d);
   return d;
@@ -647,6 +652,28 @@ void dabo_ofdm_store_null_symbol_without_tii(void * h, const float * fft)
   }
 }
 
+/* The figures signal_show_lcd_data carries, from the CURRENT state (ofdm_decoder.cpp:326-345, _compute_noise_Power :357-371):
+ * out = { MER dB, SNR dB, mMeanValue, mMeanPowerOvrAll, noise power, sqrt(mMeanSigmaSqFreqCorr) } */
+void dabo_ofdm_quality(void * h, float out[6])
+{
+  const ofdm_t * d = (const ofdm_t *)h;
+  float sum_noise = 0.0f;
+  for (int idx = -K_CARR / 2; idx < K_CARR / 2; idx++) sum_noise += d->null_pow[idx < 0 ? idx + T_U : idx + 1];
+  if (sum_noise == 0.0f) sum_noise = (1.0f / 32767.0f) * (1.0f / 32767.0f) * (float)K_CARR;
+  const float noise = sum_noise / (float)K_CARR;
+  float snr = (d->mean_pow_all - noise) / noise;
+  if (snr <= 0.0f) snr = 0.1f;
+  float sd = 0.0f;
+  for (int k = 0; k < K_CARR; k++) sd += d->stddev[k];
+  sd /= (float)K_CARR;
+  out[0] = 10.0f * log10f(PI_4_F * PI_4_F / sd);
+  out[1] = 10.0f * log10f(snr);
+  out[2] = d->mean_value;
+  out[3] = d->mean_pow_all;
+  out[4] = noise;
+  out[5] = sqrtf(d->sigma_sq_freq_corr);
+}
+
 /* arg folded into [0, pi/2) (common/glob_defs.h:173-182) */
 static float first_quadrant(float ph)
 {
@@ -660,7 +687,8 @@ void dabo_ofdm_decode_symbol(void * h, const float * fft, int sym_idx, float pha
   const cf32 * x = (const cf32 *)fft;
   const float alpha = 0.005f;
   float sum = 0.0f;
-  (void)sym_idx; (void)phase_corr;
+  d->show_cnt++;
+  const int show_stat = d->show_cnt > 5 * 76 && sym_idx == d->next_shown; /* ofdm_decoder.cpp:157 */
   for (int k = 0; k < K_CARR; k++)
   {
     int b = d->bin[k], rel = b;
@@ -714,7 +742,31 @@ void dabo_ofdm_decode_symbol(void * h, const float * fft, int sym_idx, float pha
     sum += cabs32(r);
   }
   d->mean_value = sum / (float)K_CARR;
+  if (sym_idx == 1)
+  {
+    const float fc = phase_corr / (2.0f * PI_F) * 1000.0f; /* cCarrDiff = 1000 Hz */
+    d->sigma_sq_freq_corr += 0.2f * (fc * fc - d->sigma_sq_freq_corr);
+  }
+  if (show_stat)
+  {
+    float q[6];
+    dabo_ofdm_quality(d, q);
+    d->lcd[0] = (float)(sym_idx + 1); d->lcd[1] = q[5]; d->lcd[2] = q[1]; d->lcd[3] = q[0];
+    d->lcd[4] = d->mean_value; d->lcd[5] = phase_corr / (2.0f * PI_F) * 1000.0f;
+    d->n_lcd++;
+    d->show_cnt = 0;
+    d->next_shown = (d->next_shown + 1) % 76;
+    if (d->next_shown == 0) d->next_shown = 1;
+  }
   memcpy(d->ref, x, sizeof(cf32) * T_U);
+}
+
+/* last emitted SLcdData; returns the number of emissions so far */
+int dabo_ofdm_lcd(void * h, float out[6])
+{
+  ofdm_t * d = (ofdm_t *)h;
+  memcpy(out, d->lcd, sizeof(d->lcd));
+  return d->n_lcd;
 }
 
 void dabo_ofdm_get_state(void * h, int which, float * out)
@@ -1298,3 +1350,5 @@ void dabo_chain_counters(void * h, int64_t out[8])
   out[0] = c->dip_found; out[1] = c->no_dip; out[2] = c->single_reads; out[3] = c->pos;
 }
 double dabo_chain_seconds(void * h) { return ((chain_t *)h)->seconds; }
+void dabo_chain_quality(void * h, float out[6]) { dabo_ofdm_quality(((chain_t *)h)->ofdm, out); }
+int dabo_chain_lcd(void * h, float out[6]) { return dabo_ofdm_lcd(((chain_t *)h)->ofdm, out); }

@@ -79,6 +79,10 @@ void   dabo_ofdm_store_reference_symbol_0(void * h, const float * fft);
 void   dabo_ofdm_store_null_symbol_without_tii(void * h, const float * fft);
 void   dabo_ofdm_decode_symbol(void * h, const float * fft, int sym_idx, float phase_corr, float clock_err, int16_t * out3072);
 void   dabo_ofdm_get_state(void * h, int which, float * out);
+/* SLcdData figures from the current state: { MER dB, SNR dB, mMeanValue, mMeanPowerOvrAll, noise power, sqrt(mMeanSigmaSqFreqCorr) } */
+void   dabo_ofdm_quality(void * h, float out[6]);
+/* last SLcdData emitted at the reference's cadence { CurOfdmSymbolNo, MeanSigmaSqFreqCorr, SNR, MER, TestData1, TestData2 }; returns the emission count */
+int    dabo_ofdm_lcd(void * h, float out[6]);
 
 void * dabo_phaseref_new(void);
 void   dabo_phaseref_free(void * h);
@@ -130,6 +134,8 @@ int64_t dabo_chain_msc_copy(void * h, int sub_ch_id, uint8_t * out, int64_t cap)
 int64_t dabo_chain_eti_size(void * h);
 int64_t dabo_chain_eti_copy(void * h, uint8_t * out, int64_t cap);
 void    dabo_chain_counters(void * h, int64_t out[8]);
+void    dabo_chain_quality(void * h, float out[6]); /* dabo_ofdm_quality of the chain's decoder at the end of the run */
+int     dabo_chain_lcd(void * h, float out[6]);     /* dabo_ofdm_lcd of the chain's decoder */
 double  dabo_chain_seconds(void * h);
 
 #ifdef __cplusplus

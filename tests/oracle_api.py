@@ -243,6 +243,14 @@ class Oracle:
         self.f("ofdm_get_state")(h, ctypes.c_int(which), _ptr(out))
         return out
 
+    QUALITY = ("mer_db", "snr_db", "mean_value", "mean_power_overall", "noise_power", "sigma_freq_corr")
+
+    def ofdm_quality(self, h) -> dict:
+        """SLcdData figures from the current state (restatement only: the reference keeps them private)."""
+        out = np.zeros(6, np.float32)
+        self.f("ofdm_quality")(h, _ptr(out))
+        return dict(zip(self.QUALITY, (float(v) for v in out)))
+
     def phaseref_correlate(self, samples: np.ndarray, threshold: float, strongest: int = 0) -> int:
         h = c_p(self.f("phaseref_new")())
         r = self.f("phaseref_correlate")(h, _ptr(np.ascontiguousarray(samples[:2048], np.complex64)), ctypes.c_float(threshold), ctypes.c_int(strongest))
@@ -294,6 +302,14 @@ class ChainResult:
         cnt = np.zeros(8, np.int64)
         f("chain_counters")(h, _ptr(cnt))
         self.counters = cnt
+        self.quality, self.lcd, self.n_lcd = None, None, 0
+        if o.prefix == "dabo":
+            q = np.zeros(6, np.float32)
+            f("chain_quality")(h, _ptr(q))
+            self.quality = dict(zip(Oracle.QUALITY, (float(v) for v in q)))
+            lcd = np.zeros(6, np.float32)
+            self.n_lcd = int(f("chain_lcd")(h, _ptr(lcd)))
+            self.lcd = dict(zip(("symbol_no", "sigma_freq_corr", "snr_db", "mer_db", "test1", "test2"), (float(v) for v in lcd)))
         self.msc = {}
         for row in tab:
             sid, br = int(row[0]), int(row[5])

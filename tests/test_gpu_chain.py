@@ -34,6 +34,13 @@ def _compare(want, dp, got, subch, soft_frames=3):
     for f in range(min(soft_frames, got.n_frames)):
         d = np.abs(dp.soft_bits(0, f).astype(np.int32) - want.soft_bits(f).astype(np.int32))
         assert (d > 1).mean() <= 1e-4, (f, d.max(), (d > 1).mean())
+    # signal-quality figures at the end of the run (MER, SNR, mMeanValue, mMeanPowerOvrAll, noise, frequency-correction sigma)
+    if want.quality is not None and got.n_frames > 0:
+        q = dp.quality(0)
+        for k, tol in (("mer_db", 0.01), ("snr_db", 0.01), ("sigma_freq_corr", 0.05)):
+            assert abs(q[k] - want.quality[k]) < tol, (k, q, want.quality)
+        for k in ("mean_value", "mean_power_overall", "noise_power"):
+            assert np.isclose(q[k], want.quality[k], rtol=2e-4), (k, q, want.quality)
 
 
 @pytest.mark.parametrize("fmt", [synth.FMT_U8, synth.FMT_I16, synth.FMT_CF32])

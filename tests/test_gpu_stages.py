@@ -169,6 +169,11 @@ def test_ofdm_decoder_soft_bits(ctx, oracle, soft_type):
         assert np.allclose(a, b, rtol=tol, atol=1e-6), which
     assert np.allclose(dec.state(4), oracle.ofdm_state(h, 4)[idx], rtol=1e-4, atol=1e-12)
     assert np.isclose(dec.state(5)[0], oracle.ofdm_state(h, 5)[0], rtol=1e-4)
+    # mMeanPowerOvrAll (a serial IIR over carriers in the reference, a per-carrier form on the device) and the LCD figures
+    assert np.isclose(dec.state(5)[1], oracle.ofdm_state(h, 5)[1], rtol=1e-4)
+    q, qo = dec.quality(), oracle.ofdm_quality(h)
+    assert abs(q["mer_db"] - qo["mer_db"]) < 0.01 and abs(q["snr_db"] - qo["snr_db"]) < 0.01, (q, qo)
+    assert np.isclose(q["noise_power"], qo["noise_power"], rtol=1e-4) and np.isclose(q["mean_power_overall"], qo["mean_power_overall"], rtol=1e-4)
     oracle.ofdm_free(h)
 
 

@@ -69,6 +69,9 @@ def test_whole_chain(oracle, refo, cfo, snr):
         d = np.abs(a.soft_bits(f).astype(np.int32) - b.soft_bits(f).astype(np.int32))
         assert (d > 1).mean() <= 1e-4
     assert np.array_equal(a.counters[:4], b.counters[:4])
+    # SLcdData as the reference emitted it last (signal_show_lcd_data; the harness keeps SNR and MER x 1000, truncated)
+    assert a.n_lcd >= 1
+    assert abs(a.lcd["snr_db"] - b.counters[4] / 1000.0) < 3e-3 and abs(a.lcd["mer_db"] - b.counters[5] / 1000.0) < 3e-3
 
 
 def test_eti_generator(oracle, refo):

@@ -30,7 +30,9 @@ def _ptr(a: np.ndarray) -> c_p:
     return a.ctypes.data_as(c_p)
 
 
-CONTAINERS = {"int8": 0, "uint8": 1, "int16": 2, "int24": 3, "int32": 4, "float32": 5}
+CONTAINERS = {"int8": 0, "uint8": 1, "int16": 2, "int24": 3, "int32": 4, "float32": 5, "uint8_pcm": 6, "int32_pcm": 7}
+FILE_KINDS = ("raw", "xml", "wav")
+READER_XML, READER_WAV = 0, 1
 IQ_ORDERS = {"IQ": 0, "QI": 1, "I_Only": 2, "Q_Only": 3}
 
 
@@ -186,6 +188,32 @@ class Context:
         self.check(self.lib.dabstar_ingest_convert(self.h, _ptr(raw), ctypes.byref(c), ctypes.c_int64(n), _ptr(out), MEM_HOST), "dabstar_ingest_convert")
         return out
 
+    def resample_linear(self, x: np.ndarray, sample_rate: int, reader: int = READER_XML) -> np.ndarray:
+        """The file readers' conversion to 2.048 MS/s (linear interpolation per 1 ms block; xml_reader.cpp:212-231,
+        wav_reader.cpp:196-211). x: complex64 at sample_rate."""
+        x = _np(x, np.complex64).reshape(-1)
+        n = int(self.lib.dabstar_resample_count(ctypes.c_int64(x.size), int(sample_rate), int(reader)))
+        if n < 0:
+            raise DabstarError(f"resample: unsupported rate {sample_rate} / reader {reader}")
+        out = np.empty(n, np.complex64)
+        got = int(self.lib.dabstar_resample_linear(self.h, _ptr(x), ctypes.c_int64(x.size), int(sample_rate), int(reader), _ptr(out), ctypes.c_int64(n), MEM_HOST))
+        self.check(min(got, 0), "dabstar_resample_linear")
+        return out[:got]
+
+    def read_file(self, data: np.ndarray | bytes | str) -> tuple[np.ndarray, "FileInfo"]:
+        """A recording file (path, bytes or uint8 array: raw u8 IQ, XML/UFF, RIFF/WAVE) -> complex64 at 2.048 MS/s, the
+        sample stream the reference's file reader would hand to DabProcessor, plus what the header said."""
+        if isinstance(data, str):
+            data = np.fromfile(data, np.uint8)
+        raw = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+        info = file_probe(raw)
+        elem = int(self.lib.dabstar_sample_format_bytes(ctypes.byref(info.fmt.c_struct())))
+        body = raw[info.data_offset:info.data_offset + info.n_samples * elem]
+        x = self.ingest_convert(body, info.fmt, info.n_samples)
+        if info.sample_rate != 2048000:
+            x = self.resample_linear(x, info.sample_rate, info.reader)
+        return x, info
+
     # ---- stage taps
     def fft2048(self, x: np.ndarray, sign: int = -1) -> np.ndarray:
         """fftwf_execute on the reference's 2048-point plans (dab_processor.cpp:63): x complex64[n, 2048]."""
@@ -193,6 +221,33 @@ class Context:
         y = np.empty_like(x)
         self.check(self.lib.dabstar_fft2048(self.h, _ptr(x), _ptr(y), x.shape[0], sign, MEM_HOST), "dabstar_fft2048")
         return y
+
+
+@dataclass
+class FileInfo:
+    kind: str            # "raw" | "xml" | "wav"
+    reader: int          # READER_XML / READER_WAV
+    sample_rate: int
+    n_channels: int
+    fmt: SampleFormat
+    data_offset: int
+    n_samples: int
+    frequency_hz: int
+
+
+def file_probe(head: np.ndarray | bytes, file_bytes: int | None = None) -> FileInfo:
+    """XmlDescriptor / WavFileHandler / RawReader header inspection (host code, no GPU): see dabstar_file_probe."""
+    lib = _lib.load()
+    raw = np.frombuffer(head, np.uint8) if isinstance(head, (bytes, bytearray)) else np.ascontiguousarray(head).view(np.uint8).reshape(-1)
+    fi = _lib.FileInfoC()
+    n = int(raw.size)
+    rc = lib.dabstar_file_probe(_ptr(raw), ctypes.c_int64(n), ctypes.c_int64(n if file_bytes is None else file_bytes), ctypes.byref(fi))
+    if rc < 0:
+        raise DabstarError("dabstar_file_probe: not a playable recording (unsupported header)")
+    inv_c = {v: k for k, v in CONTAINERS.items()}
+    inv_o = {v: k for k, v in IQ_ORDERS.items()}
+    fmt = SampleFormat(inv_c[fi.fmt.container], fi.fmt.bits_per_channel, "MSB" if fi.fmt.msb_first else "LSB", inv_o[fi.fmt.iq_order])
+    return FileInfo(FILE_KINDS[fi.kind], fi.reader, fi.sample_rate, fi.n_channels, fmt, int(fi.data_offset), int(fi.n_samples), fi.frequency_hz)
 
 
 _default_ctx: Context | None = None

@@ -336,10 +336,10 @@ extern "C" int dabstar_sample_format_bytes(const dabstar_sample_format * fmt)
   int b;
   switch (fmt->container)
   {
-  case DABSTAR_CONTAINER_INT8: case DABSTAR_CONTAINER_UINT8: b = 1; break;
+  case DABSTAR_CONTAINER_INT8: case DABSTAR_CONTAINER_UINT8: case DABSTAR_CONTAINER_UINT8_PCM: b = 1; break;
   case DABSTAR_CONTAINER_INT16: b = 2; break;
   case DABSTAR_CONTAINER_INT24: b = 3; break;
-  case DABSTAR_CONTAINER_INT32: case DABSTAR_CONTAINER_FLOAT32: b = 4; break;
+  case DABSTAR_CONTAINER_INT32: case DABSTAR_CONTAINER_FLOAT32: case DABSTAR_CONTAINER_INT32_PCM: b = 4; break;
   default: return 0;
   }
   return fmt->iq_order <= DABSTAR_ORDER_QI ? 2 * b : b;
@@ -359,12 +359,13 @@ extern "C" int dabstar_ingest_convert(dabstar_ctx * ctx, const void * src, const
   // files come out negated exactly as the reference reads them; x / (+-2^k) == x * (+-2^-k) exactly
   const float inv_scaler = 1.0f / (float)(int32_t)(1u << (bits - 1));
   const float * d_lut = nullptr;
-  if (fmt->container <= DABSTAR_CONTAINER_UINT8)
+  if (fmt->container <= DABSTAR_CONTAINER_UINT8 || fmt->container == DABSTAR_CONTAINER_UINT8_PCM)
   {
     float lut[256];
     for (int i = 0; i < 256; i++)
     {
-      if (fmt->container == DABSTAR_CONTAINER_UINT8) lut[i] = ((float)i - 127.38f) / 128.0f;                 // mapTable, xml_reader.cpp:93-96
+      if (fmt->container == DABSTAR_CONTAINER_UINT8_PCM) lut[i] = (float)(i - 128) / 128.0f;                 // libsndfile pcm.c uc2f: (v - 128) / 128
+      else if (fmt->container == DABSTAR_CONTAINER_UINT8) lut[i] = ((float)i - 127.38f) / 128.0f;            // mapTable, xml_reader.cpp:93-96
       else if (fmt->iq_order == DABSTAR_ORDER_IQ) lut[i] = (float)(int8_t)i / 127.0f;                        // xml_reader.cpp:266
       else lut[i] = (float)((double)(int8_t)i / 127.0);                                                      // xml_reader.cpp:411,560,690: double division
     }
@@ -379,6 +380,76 @@ extern "C" int dabstar_ingest_convert(dabstar_ctx * ctx, const void * src, const
   if (int r = stage_out_end(ctx, ddst, dst, sizeof(float2) * (size_t)n_samples, mem)) return r;
   ctx->arena_off = 0; // the stream is idle: staged uploads have been consumed
   return 0;
+}
+
+// ---- sample-rate conversion of the file readers (xml_reader.cpp:70-76,212-231; wav_reader.cpp:66-83,196-211)
+static void resample_tables(int sample_rate, int reader, short base[2048], float frac[2048], int * block_in, int * shift)
+{
+  if (reader == DABSTAR_READER_WAV)
+  {
+    // mConvBufferSize = rate / 1000; tables in float (wav_reader.cpp:66-79)
+    *block_in = (int)(int16_t)(sample_rate / 1000);
+    *shift = 0;
+    const float in_val = (float)sample_rate / 1000.0f;
+    for (int i = 0; i < 2048; i++)
+    {
+      base[i] = (short)floorf((float)i * (in_val / 2048.0f));
+      frac[i] = (float)i * (in_val / 2048.0f) - (float)base[i];
+    }
+  }
+  else
+  {
+    // convBufferSize = rate / 1000; integer part in double, fraction in float (xml_reader.cpp:70-76)
+    *block_in = sample_rate / 1000;
+    *shift = 1;
+    const float in_val = (float)(sample_rate / 1000);
+    for (int i = 0; i < 2048; i++)
+    {
+      base[i] = (short)floor(i * (in_val / 2048.0));
+      frac[i] = i * (in_val / 2048.0f) - base[i];
+    }
+  }
+}
+
+extern "C" int64_t dabstar_resample_count(int64_t n_in, int sample_rate, int reader)
+{
+  if (n_in < 0 || sample_rate < 1000 || sample_rate > 32000000 || (reader != DABSTAR_READER_XML && reader != DABSTAR_READER_WAV)) return DABSTAR_E_INVALID;
+  if (sample_rate == FS) return n_in;
+  const int64_t n = sample_rate / 1000;
+  // whole 1 ms blocks only: the WAV reader needs N + 1 samples for its first block and N for every further one
+  const int64_t blocks = reader == DABSTAR_READER_WAV ? (n_in >= 1 ? (n_in - 1) / n : 0) : n_in / n;
+  return blocks * 2048;
+}
+
+extern "C" int64_t dabstar_resample_linear(dabstar_ctx * ctx, const float * in, int64_t n_in, int sample_rate, int reader, float * out, int64_t out_cap, int mem)
+{
+  if (!ctx || !in || !out) return DABSTAR_E_INVALID;
+  const int64_t n_out = dabstar_resample_count(n_in, sample_rate, reader);
+  if (n_out < 0) return ctx->fail(DABSTAR_E_INVALID, "resample: rate %d / reader %d", sample_rate, reader);
+  if (n_out > out_cap) return ctx->fail(DABSTAR_E_INVALID, "resample: %lld output samples, room for %lld", (long long)n_out, (long long)out_cap);
+  if (n_out == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  if (sample_rate == FS)
+  {
+    CK(cudaMemcpyAsync(out, in, sizeof(float2) * (size_t)n_in, mem == DABSTAR_MEM_HOST ? cudaMemcpyHostToHost : cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return n_out;
+  }
+  short base[2048];
+  float frac[2048];
+  int block_in = 0, shift = 0;
+  resample_tables(sample_rate, reader, base, frac, &block_in, &shift);
+  CK(ctx->scratch[5].reserve(sizeof(base) + sizeof(frac)));
+  float * d_frac = ctx->scratch[5].as<float>();
+  short * d_base = reinterpret_cast<short *>(d_frac + 2048);
+  CK(cudaMemcpyAsync(d_frac, frac, sizeof(frac), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_base, base, sizeof(base), cudaMemcpyHostToDevice, ctx->stream));
+  const void * din; void * dout;
+  if (int r = stage_in(ctx, ctx->scratch[0], in, sizeof(float2) * (size_t)n_in, mem, &din)) return r;
+  if (int r = stage_out_begin(ctx, ctx->scratch[1], out, sizeof(float2) * (size_t)n_out, mem, &dout)) return r;
+  CK(launch_resample_linear(ctx->stream, (const float2 *)din, n_in, block_in, shift, d_base, d_frac, n_out, (float2 *)dout, &ctx->launches));
+  if (int r = stage_out_end(ctx, dout, out, sizeof(float2) * (size_t)n_out, mem)) return r; // (synchronises: base / frac are consumed)
+  return n_out;
 }
 
 // ------------------------------------------------------------------------------------------------ DAB+ outer code (next row f2)

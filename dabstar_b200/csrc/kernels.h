@@ -102,6 +102,9 @@ cudaError_t launch_coarse_afc(cudaStream_t s, const DeviceTables & t, const Fram
                               int * offset_hz, unsigned long long * lc);
 cudaError_t launch_coarse_afc_raw(cudaStream_t s, const DeviceTables & t, const float2 * fft_nat, int n, int * offset_hz, unsigned long long * lc);
 // src: packed file samples (see dabstar_sample_format in the C header); lut: 256 floats for the 8-bit containers (device), else nullptr
+// File readers' sample-rate conversion (linear interpolation per 1 ms block); base / frac: 2048-entry device tables.
+cudaError_t launch_resample_linear(cudaStream_t s, const float2 * in, long long n_in, int block_in, int shift, const short * base, const float * frac,
+                                   long long n_out, float2 * out, unsigned long long * lc);
 cudaError_t launch_ingest_convert(cudaStream_t s, const void * src, int container, int msb_first, int iq_order, float inv_scaler, const float * lut,
                                   long long n_samples, float2 * dst, unsigned long long * lc);
 cudaError_t launch_dip_search(cudaStream_t s, const DipWork * work, int n, const RecInput * recs, int fmt, DipResult * out, unsigned long long * lc);

@@ -1640,7 +1640,12 @@ __device__ __forceinline__ float ingest_value(const unsigned char * p, int conta
 {
   switch (container)
   {
-  case 0: case 1: return lut[p[0]];
+  case 0: case 1: case 6: return lut[p[0]];
+  case 7: // libsndfile PCM_32 -> float: v / 2^31 (positive scaler, unlike the XML reader's wrapped one)
+  {
+    const unsigned v = ((unsigned)p[3] << 24) | (p[2] << 16) | (p[1] << 8) | p[0];
+    return (float)(int)v * 4.656612873077393e-10f;
+  }
   case 2:
   {
     const int v = msb_first ? ((p[0] << 8) | p[1]) : ((p[1] << 8) | p[0]);
@@ -1668,7 +1673,7 @@ __device__ __forceinline__ float ingest_value(const unsigned char * p, int conta
 __global__ void __launch_bounds__(256) k_ingest_convert(const unsigned char * __restrict__ src, int container, int msb_first, int iq_order, float inv_scaler,
                                                         const float * __restrict__ lut, long long n, float2 * __restrict__ dst)
 {
-  const int bytes = container <= 1 ? 1 : (container == 2 ? 2 : (container == 3 ? 3 : 4));
+  const int bytes = (container <= 1 || container == 6) ? 1 : (container == 2 ? 2 : (container == 3 ? 3 : 4));
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
   {
     float2 o;
@@ -1684,6 +1689,27 @@ __global__ void __launch_bounds__(256) k_ingest_convert(const unsigned char * __
       o = iq_order == 2 ? make_float2(a, 0.0f) : make_float2(0.0f, a);
     }
     dst[i] = o;
+  }
+}
+
+// Sample-rate conversion of the file readers without liquid-dsp (xml_reader.cpp:70-76,215-224; wav_reader.cpp:66-83,
+// 196-206): every block of N = rate / 1000 input samples becomes 2048 output samples by linear interpolation,
+//   out[2048 b + j] = x[b N + base_j + 1 - shift] * frac_j + x[b N + base_j - shift] * (1 - frac_j)
+// (shift = 1 for the XML reader, whose buffer starts with the previous block's last sample and with 0 before the first
+// block; 0 for the WAV reader). Two roundings per product and one per sum, as the scalar x86 code does it (no FMA).
+__global__ void __launch_bounds__(256) k_resample_linear(const float2 * __restrict__ in, long long n_in, int block_in, int shift,
+                                                         const short * __restrict__ base, const float * __restrict__ frac,
+                                                         long long n_out, float2 * __restrict__ out)
+{
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < n_out; o += (long long)gridDim.x * blockDim.x)
+  {
+    const long long b = o >> 11;
+    const int j = (int)(o & 2047);
+    const long long lo = b * block_in + base[j] - shift;
+    const float r = frac[j], r1 = __fsub_rn(1.0f, r);
+    const float2 hi_v = lo + 1 < n_in ? in[lo + 1] : make_float2(0.f, 0.f);
+    const float2 lo_v = lo >= 0 ? in[lo] : make_float2(0.f, 0.f);
+    out[o] = make_float2(__fadd_rn(__fmul_rn(hi_v.x, r), __fmul_rn(lo_v.x, r1)), __fadd_rn(__fmul_rn(hi_v.y, r), __fmul_rn(lo_v.y, r1)));
   }
 }
 
@@ -1892,6 +1918,16 @@ cudaError_t launch_ingest_convert(cudaStream_t s, const void * src, int containe
   const long long blocks = (n_samples + 255) / 256;
   k_ingest_convert<<<(unsigned)std::min<long long>(blocks, N_SM * 16), 256, 0, s>>>(static_cast<const unsigned char *>(src), container, msb_first, iq_order, inv_scaler, lut,
                                                                                     n_samples, dst);
+  if (lc) (*lc)++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_resample_linear(cudaStream_t s, const float2 * in, long long n_in, int block_in, int shift, const short * base, const float * frac,
+                                   long long n_out, float2 * out, unsigned long long * lc)
+{
+  if (n_out <= 0) return cudaSuccess;
+  const long long blocks = (n_out + 255) / 256;
+  k_resample_linear<<<(unsigned)std::min<long long>(blocks, N_SM * 16), 256, 0, s>>>(in, n_in, block_in, shift, base, frac, n_out, out);
   if (lc) (*lc)++;
   return cudaGetLastError();
 }

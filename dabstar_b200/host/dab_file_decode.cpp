@@ -3,6 +3,8 @@
 //   dab_file_decode [-f u8|i16|cf32] [-x container,bits,LSB|MSB,IQ|QI|I_Only|Q_Only] [-a] [-e]
 //                   [-s subChId,startCU,sizeCU,shortForm,protLevel,bitRate]... [-o prefix] file.iq [file2.iq ...]
 //     -x  XML/UFF sample description (container int8|uint8|int16|int24|int32|float32) for layouts other than the three native ones
+//     -c  containers: every file's header is inspected (RIFF/WAVE .wav / .sdr, XML .uff, else raw u8); samples are converted and
+//         resampled to 2.048 MS/s as the reference's file readers do
 //     -a  self-configuration: sub-channels from the recording's FIG 0/1 (no -s needed)
 //     -e  also write the ETI(NI) stream, <prefix><n>.eti (what DABstar's ETI generator writes)
 //
@@ -33,7 +35,7 @@ static std::vector<unsigned char> read_file(const char * path)
 int main(int argc, char ** argv)
 {
   int fmt = DABSTAR_FMT_U8;
-  bool autoCfg = false, eti = false, xml = false;
+  bool autoCfg = false, eti = false, xml = false, containers = false;
   dabstar_sample_format sf{};
   std::string prefix = "dab_out_";
   std::vector<dabstar_subch> subch;
@@ -44,6 +46,7 @@ int main(int argc, char ** argv)
     if (a == "-f" && i + 1 < argc) { const std::string v = argv[++i]; fmt = v == "i16" ? DABSTAR_FMT_I16 : (v == "cf32" ? DABSTAR_FMT_CF32 : DABSTAR_FMT_U8); }
     else if (a == "-o" && i + 1 < argc) prefix = argv[++i];
     else if (a == "-a") autoCfg = true;
+    else if (a == "-c") { containers = true; fmt = DABSTAR_FMT_CF32; }
     else if (a == "-e") eti = true;
     else if (a == "-x" && i + 1 < argc)
     {
@@ -78,8 +81,21 @@ int main(int argc, char ** argv)
     std::vector<std::vector<unsigned char>> data;
     std::vector<const void *> ptrs;
     std::vector<int64_t> ns;
+    std::vector<std::vector<float>> conv;
     for (const char * f : files) { data.push_back(read_file(f)); }
-    for (auto & d : data) { ptrs.push_back(d.data()); ns.push_back((int64_t)(d.size() / bps)); }
+    if (containers)
+    {
+      for (size_t r = 0; r < data.size(); r++)
+      {
+        dabstar_file_info fi{};
+        conv.push_back(dabstar::read_recording(ctx, data[r].data(), data[r].size(), &fi));
+        static const char * const kinds[3] = { "raw", "xml", "wav" };
+        printf("%s: %s container, %d S/s, %lld samples from byte %lld\n", files[r], kinds[fi.kind], fi.sample_rate, (long long)fi.n_samples, (long long)fi.data_offset);
+      }
+      for (auto & v : conv) { ptrs.push_back(v.data()); ns.push_back((int64_t)(v.size() / 2)); }
+    }
+    else
+      for (auto & d : data) { ptrs.push_back(d.data()); ns.push_back((int64_t)(d.size() / bps)); }
     dabstar::DabProcessor proc(ctx, (int)files.size(), fmt, subch.empty() && !autoCfg);
     for (size_t r = 0; r < files.size(); r++)
     {
@@ -87,7 +103,7 @@ int main(int argc, char ** argv)
       else proc.set_audio_channel((int)r, subch);
       if (eti) proc.start_eti_generator((int)r);
     }
-    if (xml) proc.run_files(ptrs, ns, sf);
+    if (xml && !containers) proc.run_files(ptrs, ns, sf);
     else proc.run(ptrs, ns);
     for (size_t r = 0; r < files.size(); r++)
     {

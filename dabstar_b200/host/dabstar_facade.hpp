@@ -247,6 +247,27 @@ private:
 
 enum class ESoftBitType { SOFTDEC1 = 0, SOFTDEC2 = 1, SOFTDEC3 = 2 };
 
+// What XmlFileReader / WavFileHandler / RawFileHandler + their reader threads produce from a recording file: the header
+// is inspected on the host (dabstar_file_probe), the samples are converted and brought to 2.048 MS/s on the GPU.
+// Returns interleaved re / im floats.
+inline std::vector<float> read_recording(Context & c, const u8 * file, size_t fileBytes, dabstar_file_info * oInfo = nullptr)
+{
+  dabstar_file_info fi{};
+  if (dabstar_file_probe(file, (int64_t)fileBytes, (int64_t)fileBytes, &fi) != DABSTAR_OK) throw std::runtime_error("dabstar_file_probe: unsupported recording header");
+  if (oInfo) *oInfo = fi;
+  std::vector<float> x((size_t)std::max<int64_t>(fi.n_samples, 1) * 2);
+  c.check(dabstar_ingest_convert(c.get(), file + fi.data_offset, &fi.fmt, fi.n_samples, x.data(), DABSTAR_MEM_HOST), "dabstar_ingest_convert");
+  x.resize((size_t)fi.n_samples * 2);
+  if (fi.sample_rate == 2048000) return x;
+  const int64_t n = dabstar_resample_count(fi.n_samples, fi.sample_rate, fi.reader);
+  if (n < 0) throw std::runtime_error("dabstar_resample_count: unsupported sample rate");
+  std::vector<float> y((size_t)std::max<int64_t>(n, 1) * 2);
+  const int64_t got = dabstar_resample_linear(c.get(), x.data(), fi.n_samples, fi.sample_rate, fi.reader, y.data(), n, DABSTAR_MEM_HOST);
+  c.check((int)std::min<int64_t>(got, 0), "dabstar_resample_linear");
+  y.resize((size_t)got * 2);
+  return y;
+}
+
 // OfdmDecoder::SLcdData (ofdm/ofdm_decoder.h:53-61) plus the two state scalars it is computed from
 struct SLcdData
 {

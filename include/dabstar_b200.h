@@ -82,7 +82,10 @@ int dabstar_protection_addresses(dabstar_ctx * ctx, int short_form, int bit_rate
  * indexes the table with the loop counter (xml_reader.cpp:421), int8 with Q_Only sets the real part to 127
  * (:690), MSB int24 takes one byte from offset 4*i+4 (:309). */
 enum { DABSTAR_CONTAINER_INT8 = 0, DABSTAR_CONTAINER_UINT8 = 1, DABSTAR_CONTAINER_INT16 = 2, DABSTAR_CONTAINER_INT24 = 3,
-       DABSTAR_CONTAINER_INT32 = 4, DABSTAR_CONTAINER_FLOAT32 = 5 };
+       DABSTAR_CONTAINER_INT32 = 4, DABSTAR_CONTAINER_FLOAT32 = 5,
+       /* RIFF/WAVE files go through libsndfile's float read in the reference (wav_reader.cpp:164): 16 / 24-bit PCM and
+        * float equal the XML containers above; 8-bit PCM is (v - 128) / 128 and 32-bit PCM v / 2^31 (little endian) */
+       DABSTAR_CONTAINER_UINT8_PCM = 6, DABSTAR_CONTAINER_INT32_PCM = 7 };
 enum { DABSTAR_ORDER_IQ = 0, DABSTAR_ORDER_QI = 1, DABSTAR_ORDER_I_ONLY = 2, DABSTAR_ORDER_Q_ONLY = 3 };
 typedef struct
 {
@@ -95,6 +98,37 @@ typedef struct
 int dabstar_ingest_convert(dabstar_ctx * ctx, const void * src, const dabstar_sample_format * fmt, int64_t n_samples, float * dst, int mem);
 /* Bytes per element of `src` for a format (0 if the format is invalid). */
 int dabstar_sample_format_bytes(const dabstar_sample_format * fmt);
+
+/* ------------------------------------------------------------------------------------------------ input containers (next row f4) */
+/* What the file readers learn before the first sample (host code, csrc/file_probe.cu):
+ *   XML / UFF: XmlDescriptor (xml_filereader/xml_descriptor.cpp:100-242) + XmlFileReader's start offset and sample count
+ *              (xml_filereader.cpp:103-126,313-335);
+ *   WAV / SDR: WavFileHandler (wav_files/wavfiles.cpp:61-97: 1.536..3.0 MS/s, two channels, PCM 8/16/24/32 or float);
+ *   anything else: RawReader (raw_files/raw_reader.cpp:66-70): unsigned 8-bit IQ at 2.048 MS/s, no header.
+ * head: the first head_bytes of the file (64 KiB is plenty); file_bytes: its total size. */
+enum { DABSTAR_FILE_RAW = 0, DABSTAR_FILE_XML = 1, DABSTAR_FILE_WAV = 2 };
+enum { DABSTAR_READER_XML = 0, DABSTAR_READER_WAV = 1 };
+typedef struct
+{
+  int32_t kind;            /* DABSTAR_FILE_* */
+  int32_t reader;          /* DABSTAR_READER_*: whose sample-rate conversion applies */
+  int32_t sample_rate;     /* Hz */
+  int32_t n_channels;
+  dabstar_sample_format fmt;
+  int64_t data_offset;     /* first byte of the sample data */
+  int64_t n_samples;       /* complex samples (single values for the *_ONLY orders) the reader would play */
+  int32_t frequency_hz;    /* centre frequency of the first data block (XML), else 0 */
+  int32_t reserved;
+} dabstar_file_info;
+int dabstar_file_probe(const uint8_t * head, int64_t head_bytes, int64_t file_bytes, dabstar_file_info * out);
+
+/* Sample-rate conversion to 2.048 MS/s as the readers do it when the reference is built without liquid-dsp (the
+ * default): per 1 ms block of rate/1000 input samples, 2048 output samples by linear interpolation between neighbours
+ * (XmlReader: xml_reader.cpp:70-76,212-231; WavReader: wav_reader.cpp:66-83,196-211; the two differ in table precision
+ * and by one sample of delay). in: n_in complex floats; returns the number of complex samples written (whole blocks
+ * only; n_in copied unchanged when sample_rate is 2 048 000) or <0. dabstar_resample_count gives that number up front. */
+int64_t dabstar_resample_count(int64_t n_in, int sample_rate, int reader);
+int64_t dabstar_resample_linear(dabstar_ctx * ctx, const float * in, int64_t n_in, int sample_rate, int reader, float * out, int64_t out_cap, int mem);
 
 /* ------------------------------------------------------------------------------------------------ stage taps */
 /* fftwf_execute on a 2048-point plan (main/dab_processor.cpp:63,201,276,338): n transforms,

@@ -197,6 +197,23 @@ static float xml_value(const uint8_t * p, int container, int msb, float scaler, 
 int dabo_convert_samples(const uint8_t * in, int container, int bits, int msb_first, int order, int64_t n_samples, float * out)
 {
   static const int width[6] = { 1, 1, 2, 3, 4, 4 };
+  if (container == 6 || container == 7)
+  {
+    /* RIFF/WAVE through libsndfile's sf_readf_float (wav_reader.cpp:164; libsndfile is not part of the reference tree):
+     * 8-bit PCM (v - 128) / 128, 32-bit PCM v / 2^31, little endian, I then Q */
+    if (order != 0) return -1;
+    for (int64_t i = 0; i < 2 * n_samples; i++)
+    {
+      if (container == 6) out[i] = (float)((int)in[i] - 128) / 128.0f;
+      else
+      {
+        const uint8_t * p = in + 4 * i;
+        const uint32_t u = ((uint32_t)p[3] << 24) | (p[2] << 16) | (p[1] << 8) | p[0];
+        out[i] = (float)(int32_t)u / 2147483648.0f;
+      }
+    }
+    return 0;
+  }
   if (container < 0 || container > 5 || order < 0 || order > 3) return -1;
   const int b = width[container];
   const float scaler = xml_scaler(bits > 0 ? bits : 8 * b);
@@ -217,6 +234,82 @@ int dabo_convert_samples(const uint8_t * in, int container, int bits, int msb_fi
     }
   }
   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Sample-rate conversion of the file readers when the reference is built without liquid-dsp (the default): blocks of
+ * rate / 1000 input samples become 2048 output samples by linear interpolation. Restated loop for loop; the readers
+ * themselves need Qt (and libsndfile), so this boundary is pinned by the source text only.
+ * ---------------------------------------------------------------------------------------------- */
+/* XmlReader ctor tables (xml_reader.cpp:70-76) + readSamples (:212-231). Returns the number of output samples. */
+int64_t dabo_resample_xml(const float * in_re_im, int64_t n_in, int sample_rate, float * out_re_im)
+{
+  const cf32 * in = (const cf32 *)in_re_im;
+  cf32 * out = (cf32 *)out_re_im;
+  int16_t map_int[2048];
+  float map_float[2048];
+  for (int i = 0; i < 2048; i++)
+  {
+    const float in_val = (float)(sample_rate / 1000);
+    map_int[i] = (int16_t)(floor(i * (in_val / 2048.0)));
+    map_float[i] = i * (in_val / 2048.0f) - map_int[i];
+  }
+  const int conv_size = sample_rate / 1000;
+  cf32 * conv = (cf32 *)calloc((size_t)conv_size + 1, sizeof(cf32)); /* convBuffer.resize(convBufferSize + 1): zeros */
+  int64_t n_out = 0;
+  for (int64_t pos = 0; pos + conv_size <= n_in; pos += conv_size)
+  {
+    memcpy(&conv[1], &in[pos], sizeof(cf32) * (size_t)conv_size); /* the reader fills &convBuffer[1] */
+    for (int i = 0; i < 2048; i++)
+    {
+      const int16_t base = map_int[i];
+      const float ratio = map_float[i];
+      out[n_out].re = conv[base + 1].re * ratio + conv[base].re * (1.0f - ratio);
+      out[n_out].im = conv[base + 1].im * ratio + conv[base].im * (1.0f - ratio);
+      n_out++;
+    }
+    conv[0] = conv[conv_size];
+  }
+  free(conv);
+  return n_out;
+}
+
+/* WavReader ctor tables (wav_reader.cpp:66-79) + run (:196-211) */
+int64_t dabo_resample_wav(const float * in_re_im, int64_t n_in, int sample_rate, float * out_re_im)
+{
+  const cf32 * in = (const cf32 *)in_re_im;
+  cf32 * out = (cf32 *)out_re_im;
+  int16_t map_int[2048];
+  float map_float[2048];
+  const int16_t conv_size = (int16_t)(sample_rate / 1000);
+  for (int i = 0; i < 2048; i++)
+  {
+    const float in_val = (float)sample_rate / 1000.0f;
+    map_int[i] = (int16_t)(floorf((float)i * (in_val / 2048.0f)));
+    map_float[i] = (float)i * (in_val / 2048.0f) - (float)map_int[i];
+  }
+  cf32 * conv = (cf32 *)calloc((size_t)conv_size + 1, sizeof(cf32));
+  int conv_index = 0;
+  int64_t n_out = 0;
+  for (int64_t i = 0; i < n_in; i++)
+  {
+    conv[conv_index++] = in[i];
+    if (conv_index > conv_size)
+    {
+      for (int j = 0; j < 2048; j++)
+      {
+        const int16_t base = map_int[j];
+        const float ratio = map_float[j];
+        out[n_out].re = conv[base + 1].re * ratio + conv[base].re * (1 - ratio);
+        out[n_out].im = conv[base + 1].im * ratio + conv[base].im * (1 - ratio);
+        n_out++;
+      }
+      conv[0] = conv[conv_size];
+      conv_index = 1;
+    }
+  }
+  free(conv);
+  return n_out;
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -109,6 +109,15 @@ class Oracle:
             f = iq.astype(np.float32) / np.float32(32768.0)
         return np.ascontiguousarray(f).view(np.complex64).reshape(-1)
 
+    def resample(self, x: np.ndarray, sample_rate: int, reader: str) -> np.ndarray:
+        """XmlReader / WavReader linear-interpolation resampling (C restatement only: the readers need Qt)."""
+        x = np.ascontiguousarray(x, np.complex64).reshape(-1)
+        out = np.zeros((x.size // (sample_rate // 1000) + 1) * 2048, np.complex64)
+        fn = self.f("resample_" + reader)
+        fn.restype = ctypes.c_int64
+        n = fn(_ptr(x), ctypes.c_int64(x.size), int(sample_rate), _ptr(out))
+        return out[:n]
+
     def convert_samples(self, raw: np.ndarray, container: int, bits: int, msb_first: int, order: int, n_samples: int) -> np.ndarray:
         """XmlReader::readElements_* (xml_reader.cpp:254-800); only in the C restatement (the reader needs Qt)."""
         raw = np.ascontiguousarray(raw, np.uint8)

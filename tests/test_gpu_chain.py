@@ -214,3 +214,16 @@ def test_cpp_harness_end_to_end(ctx, tmp_path):
     assert np.fromfile(prefix + "0.fic", np.uint8).size == 32 * got.n_good_fibs
     for s in sc:
         assert np.array_equal(np.fromfile(prefix + f"0.sub{s.sub_ch_id}", np.uint8), np.packbits(got.msc[s.sub_ch_id].reshape(-1)))
+    # the same recording as a RIFF/WAVE file (16-bit PCM, 2.048 MS/s) through the container path (-c): header probe on the host,
+    # conversion on the GPU; prints the container and the reference's LCD figures
+    from test_file_containers import wav_bytes
+    wav = str(tmp_path / "rec.wav")
+    with open(wav, "wb") as f:
+        f.write(wav_bytes(np.ascontiguousarray(rec.iq), 2048000, 1, 16))
+    prefix2 = str(tmp_path / "wav_")
+    r = subprocess.run([exe, "-c", "-a", "-o", prefix2, wav], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "wav container, 2048000 S/s" in r.stdout and "MER" in r.stdout and "SNR" in r.stdout
+    assert np.array_equal(np.fromfile(prefix2 + "0.fic", np.uint8), np.fromfile(prefix + "0.fic", np.uint8))
+    for s in sc:
+        assert np.array_equal(np.fromfile(prefix2 + f"0.sub{s.sub_ch_id}", np.uint8), np.fromfile(prefix + f"0.sub{s.sub_ch_id}", np.uint8))

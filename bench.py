@@ -154,6 +154,48 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- native arm
+# (short_form, prot_level, bit_rate, size_cu)
+SWEEP_PROFILES = [("EEP 1-A 72k", 0, 0, 72, 108), ("EEP 2-A 72k", 0, 1, 72, 72), ("EEP 3-A 72k", 0, 2, 72, 54), ("EEP 4-A 72k", 0, 3, 72, 36),
+                  ("EEP 1-B 64k", 0, 4, 64, 54), ("EEP 2-B 64k", 0, 5, 64, 42), ("EEP 3-B 64k", 0, 6, 64, 36), ("EEP 4-B 64k", 0, 7, 64, 30),
+                  ("UEP 1 128k", 1, 1, 128, 140), ("UEP 2 128k", 1, 2, 128, 116), ("UEP 3 128k", 1, 3, 128, 96), ("UEP 4 128k", 1, 4, 128, 84),
+                  ("UEP 5 128k", 1, 5, 128, 64)]
+
+
+def viterbi_sweep(ctx, stream, n_frames):
+    """Protection::deconvolve over n_frames logical frames per protection level; times 3 launches after 1 warm-up with CUDA events."""
+    import ctypes
+    import torch
+    from dabstar_b200 import api
+    out = {"logical_frames_per_level": n_frames, "levels": {}, "input": "noisy soft bits (+-60 with sigma 40), resident in HBM"}
+    g = torch.Generator(device="cuda").manual_seed(4)
+    tot_bits, tot_ms = 0.0, 0.0
+    for name, sf, lvl, br, cu in SWEEP_PROFILES:
+        n_soft = cu * 64
+        soft = ((torch.randint(0, 2, (n_frames, n_soft), generator=g, device="cuda", dtype=torch.int16) * 2 - 1) * 60
+                + (torch.randn((n_frames, n_soft), generator=g, device="cuda") * 40).to(torch.int16)).contiguous()
+        bits = torch.empty((n_frames, 24 * br), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+
+        def run():
+            ctx.check(ctx.lib.dabstar_protection_deconvolve(ctx.h, sf, br, lvl, cu, ctypes.c_void_p(soft.data_ptr()), n_frames,
+                                                            ctypes.c_void_p(bits.data_ptr()), api.MEM_DEVICE), "dabstar_protection_deconvolve")
+        run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(3):
+            run()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        info_bits = n_frames * 24 * br
+        acs = n_frames * 64 * (24 * br + 6)
+        out["levels"][name] = {"ms": ms, "mbit_s": info_bits / ms / 1e3, "gacs": acs / ms / 1e6}
+        tot_bits += info_bits
+        tot_ms += ms
+    out["mbit_s_overall"] = tot_bits / tot_ms / 1e3
+    return out
+
+
 def native_arm(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -230,6 +272,12 @@ def native_arm(args, rank, local_rank, world):
         barrier()
         ms_e2e = e0.elapsed_time(e1)
 
+        # ---- configs[3]: Viterbi-only throughput per protection level (depuncture + K=7 decode of MSC logical frames, soft bits
+        #      resident in HBM), the "Viterbi Mbit/s" half of the metric; bounded batch, rank 0's GPU only
+        vit_sweep = None
+        if rank == 0 and not args.no_viterbi_sweep:
+            vit_sweep = viterbi_sweep(ctx, stream, args.viterbi_frames)
+
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
     fr = torch.tensor([frames_per_step], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -303,7 +351,7 @@ def native_arm(args, rank, local_rank, world):
                    "windows_per_recording": float(cnt[4]) / R, "frames_through_heavy_pass": int(cnt[7]), "x_real_time": value / world / (2048000 / T_F)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(R * n_samples * 2), "d2h_bytes_per_step": int(frames_per_step * 3072),
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
+        "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "stages": stages, "viterbi_sweep": vit_sweep, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
     if world > 1:
@@ -323,6 +371,8 @@ def main():
     ap.add_argument("--snr", type=float, default=15.0)
     ap.add_argument("--synth-budget", type=float, default=45.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-viterbi-sweep", action="store_true")
+    ap.add_argument("--viterbi-frames", type=int, default=32768, help="logical frames per protection level in the Viterbi-only sweep")
     ap.add_argument("--cpu-worker", action="store_true")
     ap.add_argument("--cpu-lib", default="dabo")
     args = ap.parse_args()

@@ -35,6 +35,10 @@ class SampleFormatC(ctypes.Structure):
     _fields_ = [("container", ctypes.c_int32), ("bits_per_channel", ctypes.c_int32), ("msb_first", ctypes.c_int32), ("iq_order", ctypes.c_int32)]
 
 
+class DcIqStateC(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_float) for n in ("mean_i", "mean_q", "mean_ii", "mean_qq", "mean_iq")]
+
+
 class FileInfoC(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("reader", ctypes.c_int32), ("sample_rate", ctypes.c_int32), ("n_channels", ctypes.c_int32),
                 ("fmt", SampleFormatC), ("data_offset", ctypes.c_int64), ("n_samples", ctypes.c_int64), ("frequency_hz", ctypes.c_int32),
@@ -60,7 +64,7 @@ EXPORTS = [
     ("dabstar_abi_version", ctypes.c_int), ("dabstar_kernel_launches", ctypes.c_uint64),
     ("dabstar_freq_interleaver", ctypes.c_int), ("dabstar_phase_table", ctypes.c_int), ("dabstar_protection_addresses", ctypes.c_int),
     ("dabstar_ingest_convert", ctypes.c_int), ("dabstar_sample_format_bytes", ctypes.c_int),
-    ("dabstar_file_probe", ctypes.c_int), ("dabstar_resample_count", ctypes.c_int64), ("dabstar_resample_linear", ctypes.c_int64),
+    ("dabstar_dc_iq_correct", ctypes.c_int), ("dabstar_file_probe", ctypes.c_int), ("dabstar_resample_count", ctypes.c_int64), ("dabstar_resample_linear", ctypes.c_int64),
     ("dabstar_dabplus_decode", ctypes.c_int),
     ("dabstar_fib_parser_create", ctypes.c_int), ("dabstar_fib_parser_destroy", None), ("dabstar_fib_parser_push", ctypes.c_int),
     ("dabstar_fib_parser_ensemble", ctypes.c_int), ("dabstar_fib_parser_subchannels", ctypes.c_int), ("dabstar_fib_parser_components", ctypes.c_int),

@@ -188,6 +188,15 @@ class Context:
         self.check(self.lib.dabstar_ingest_convert(self.h, _ptr(raw), ctypes.byref(c), ctypes.c_int64(n), _ptr(out), MEM_HOST), "dabstar_ingest_convert")
         return out
 
+    def dc_iq_correct(self, x: np.ndarray, do_iq: bool = False, state: "_lib.DcIqStateC | None" = None) -> np.ndarray:
+        """SampleReader::set_dc_and_iq_correction(True, do_iq) over a whole recording (sample_reader.cpp:216-243). state: filter
+        values carried from an earlier call (updated in place); None = a fresh reader."""
+        x = _np(x, np.complex64).reshape(-1)
+        out = np.empty_like(x)
+        self.check(self.lib.dabstar_dc_iq_correct(self.h, _ptr(x), ctypes.c_int64(x.size), 1 if do_iq else 0, ctypes.byref(state) if state is not None else None,
+                                                  _ptr(out), MEM_HOST), "dabstar_dc_iq_correct")
+        return out
+
     def resample_linear(self, x: np.ndarray, sample_rate: int, reader: int = READER_XML) -> np.ndarray:
         """The file readers' conversion to 2.048 MS/s (linear interpolation per 1 ms block; xml_reader.cpp:212-231,
         wav_reader.cpp:196-211). x: complex64 at sample_rate."""

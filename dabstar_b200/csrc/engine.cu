@@ -382,6 +382,27 @@ extern "C" int dabstar_ingest_convert(dabstar_ctx * ctx, const void * src, const
   return 0;
 }
 
+// ---- SampleReader's DC / IQ-imbalance correction (sample_reader.cpp:216-243; set_dc_and_iq_correction, sample_reader.h:66)
+extern "C" int dabstar_dc_iq_correct(dabstar_ctx * ctx, const float * in, int64_t n_samples, int do_iq, dabstar_dciq_state * state, float * out, int mem)
+{
+  if (!ctx || !in || !out || n_samples < 0) return DABSTAR_E_INVALID;
+  if (n_samples == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  dabstar_dciq_state fresh{ 0.0f, 0.0f, 1.0f, 1.0f, 0.0f }; // sample_reader.h:102-106
+  dabstar_dciq_state * st = state ? state : &fresh;
+  double sv[5] = { st->mean_i, st->mean_q, st->mean_ii, st->mean_iq, st->mean_qq };
+  const double alpha = (double)(1.0f / (float)FS / 1.00f); // constexpr f32 ALPHA = 1.0f / INPUT_RATE / 1.00f
+  const void * din; void * dout;
+  const size_t bytes = sizeof(float2) * (size_t)n_samples;
+  if (int r = stage_in(ctx, ctx->scratch[0], in, bytes, mem, &din)) return r;
+  if (int r = stage_out_begin(ctx, ctx->scratch[1], out, bytes, mem, &dout)) return r;
+  CK(ctx->scratch[2].reserve(dciq_workspace_bytes(n_samples)));
+  CK(launch_dc_iq_correct(ctx->stream, (const float2 *)din, n_samples, do_iq != 0, alpha, sv, ctx->scratch[2].p, (float2 *)dout, &ctx->launches));
+  if (int r = stage_out_end(ctx, dout, out, bytes, mem)) return r;
+  st->mean_i = (float)sv[0]; st->mean_q = (float)sv[1]; st->mean_ii = (float)sv[2]; st->mean_iq = (float)sv[3]; st->mean_qq = (float)sv[4];
+  return 0;
+}
+
 // ---- sample-rate conversion of the file readers (xml_reader.cpp:70-76,212-231; wav_reader.cpp:66-83,196-211)
 static void resample_tables(int sample_rate, int reader, short base[2048], float frac[2048], int * block_in, int * shift)
 {

@@ -102,6 +102,11 @@ cudaError_t launch_coarse_afc(cudaStream_t s, const DeviceTables & t, const Fram
                               int * offset_hz, unsigned long long * lc);
 cudaError_t launch_coarse_afc_raw(cudaStream_t s, const DeviceTables & t, const float2 * fft_nat, int n, int * offset_hz, unsigned long long * lc);
 // src: packed file samples (see dabstar_sample_format in the C header); lut: 256 floats for the 8-bit containers (device), else nullptr
+// dciq_kernels.cu: SampleReader's DC / IQ-imbalance correction over a whole recording (sample_reader.cpp:216-243).
+// state: { meanI, meanQ, meanII, meanIQ, meanQQ }, in and out; workspace: dciq_workspace_bytes(n) device bytes.
+size_t dciq_workspace_bytes(long long n);
+cudaError_t launch_dc_iq_correct(cudaStream_t s, const float2 * in, long long n, bool do_iq, double alpha, double state[5], void * workspace, float2 * out,
+                                 unsigned long long * lc);
 // File readers' sample-rate conversion (linear interpolation per 1 ms block); base / frac: 2048-entry device tables.
 cudaError_t launch_resample_linear(cudaStream_t s, const float2 * in, long long n_in, int block_in, int shift, const short * base, const float * frac,
                                    long long n_out, float2 * out, unsigned long long * lc);

@@ -130,6 +130,22 @@ int dabstar_file_probe(const uint8_t * head, int64_t head_bytes, int64_t file_by
 int64_t dabstar_resample_count(int64_t n_in, int sample_rate, int reader);
 int64_t dabstar_resample_linear(dabstar_ctx * ctx, const float * in, int64_t n_in, int sample_rate, int reader, float * out, int64_t out_cap, int mem);
 
+/* ------------------------------------------------------------------------------------------------ DC / IQ correction (row I2, optional) */
+/* SampleReader::set_dc_and_iq_correction(true, do_iq) (ofdm/sample_reader.h:66, sample_reader.cpp:216-243; off by default in
+ * the reference): DC removal by two IIRs (alpha = 1 / 2 048 000) and, with do_iq, the IQ-imbalance correction by three
+ * more. A pre-pass over a whole recording of complex floats (in == out allowed); the result is decoded as
+ * DABSTAR_FMT_CF32. state: the filter values before the first sample, updated to those after the last (NULL: a fresh
+ * SampleReader: 0, 0, 1, 1, 0). The filters are evaluated as scans in double precision, i.e. the recurrences in exact
+ * arithmetic. DC removal agrees with the reference's float loop to about 1e-6 of the sample amplitude. With do_iq the
+ * reference's meanII / meanQQ start at 1 and move by only ~8 float ulps per sample while they are large, so its round-off
+ * is a systematic ~1 % of their decay rate: during the first seconds gainQ (the Q branch) differs by up to a few 1e-3
+ * relative from this implementation; the I branch and the settled state agree as for DC removal. */
+typedef struct
+{
+  float mean_i, mean_q, mean_ii, mean_qq, mean_iq; /* sample_reader.h:102-106 */
+} dabstar_dciq_state;
+int dabstar_dc_iq_correct(dabstar_ctx * ctx, const float * in, int64_t n_samples, int do_iq, dabstar_dciq_state * state, float * out, int mem);
+
 /* ------------------------------------------------------------------------------------------------ stage taps */
 /* fftwf_execute on a 2048-point plan (main/dab_processor.cpp:63,201,276,338): n transforms,
  * unnormalised, sign -1 forward / +1 backward, natural order, complex float interleaved. */

@@ -237,6 +237,42 @@ int dabo_convert_samples(const uint8_t * in, int container, int bits, int msb_fi
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * SampleReader's optional DC removal and IQ-imbalance correction, scalar build (ofdm/sample_reader.cpp:216-243;
+ * members sample_reader.h:102-106; mean_filter glob_defs.h:217-220), sample by sample in float as the reference runs it.
+ * state: { meanI, meanQ, meanII, meanQQ, meanIQ }, in and out.
+ * ---------------------------------------------------------------------------------------------- */
+void dabo_dc_iq_correct(const float * in_re_im, int64_t n, int do_iq, float state[5], float * out_re_im)
+{
+  float mean_i = state[0], mean_q = state[1], mean_ii = state[2], mean_qq = state[3], mean_iq = state[4];
+  const float alpha = 1.0f / (float)FS / 1.00f;
+  for (int64_t i = 0; i < n; i++)
+  {
+    const float v_i = in_re_im[2 * i], v_q = in_re_im[2 * i + 1];
+    mean_i += alpha * (v_i - mean_i);
+    mean_q += alpha * (v_q - mean_q);
+    if (do_iq)
+    {
+      const float x_i = v_i - mean_i;
+      const float x_q = v_q - mean_q;
+      mean_ii += alpha * (x_i * x_i - mean_ii);
+      mean_iq += alpha * (x_i * x_q - mean_iq);
+      const float phi = mean_iq / mean_ii;
+      const float x_q_corr = x_q - phi * x_i;
+      mean_qq += alpha * (x_q_corr * x_q_corr - mean_qq);
+      const float gain_q = sqrtf(mean_ii / mean_qq);
+      out_re_im[2 * i] = x_i;
+      out_re_im[2 * i + 1] = x_q_corr * gain_q;
+    }
+    else
+    {
+      out_re_im[2 * i] = v_i - mean_i;
+      out_re_im[2 * i + 1] = v_q - mean_q;
+    }
+  }
+  state[0] = mean_i; state[1] = mean_q; state[2] = mean_ii; state[3] = mean_qq; state[4] = mean_iq;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * Sample-rate conversion of the file readers when the reference is built without liquid-dsp (the default): blocks of
  * rate / 1000 input samples become 2048 output samples by linear interpolation. Restated loop for loop; the readers
  * themselves need Qt (and libsndfile), so this boundary is pinned by the source text only.

@@ -34,6 +34,9 @@ void dabo_convert_i16(const int16_t * in, float * out_re_im, int64_t n_samples);
  * -1 for an unknown format. */
 int dabo_convert_samples(const uint8_t * in, int container, int bits, int msb_first, int order, int64_t n_samples, float * out_re_im);
 /* (containers 6 / 7: 8-bit and 32-bit PCM of a RIFF/WAVE file as libsndfile's float read scales them, IQ order only) */
+/* SampleReader's DC / IQ-imbalance correction (sample_reader.cpp:216-243), serial float as the reference's scalar build runs it.
+ * state: { meanI, meanQ, meanII, meanQQ, meanIQ } (a fresh reader: 0, 0, 1, 1, 0), in and out. */
+void dabo_dc_iq_correct(const float * in_re_im, int64_t n, int do_iq, float state[5], float * out_re_im);
 /* Linear-interpolation resampling to 2.048 MS/s of XmlReader (xml_reader.cpp:70-76,212-231) and WavReader
  * (wav_reader.cpp:66-83,196-211); out must hold 2048 samples per 1 ms of input. Returns the samples written. */
 int64_t dabo_resample_xml(const float * in_re_im, int64_t n_in, int sample_rate, float * out_re_im);

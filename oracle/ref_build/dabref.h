@@ -82,6 +82,8 @@ typedef struct
   uint8_t fic_valid[4];
 } dabref_frame_info;
 
+/* SampleReader (ofdm/sample_reader.h:60-70) with DC (+ IQ) correction switched on, 0 Hz mixing, over n samples */
+void    dabref_dc_iq_correct(const float * in_re_im, int64_t n, int do_iq, float * out_re_im, float dc_offset[2]);
 void *  dabref_chain_run(const float * iq_re_im, int64_t n_samples, const dabref_chain_cfg * cfg);
 void    dabref_chain_free(void * h);
 int     dabref_chain_n_frames(void * h);

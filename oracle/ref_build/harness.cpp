@@ -281,6 +281,32 @@ public:
   std::function<void()> mOnFirstRead;
 };
 
+} // namespace
+
+// SampleReader with set_dc_and_iq_correction(true, do_iq) over a whole stream, no mixing (0 Hz): the reader's own
+// per-sample loop (sample_reader.cpp:212-281) on an in-memory device.
+extern "C" void dabref_dc_iq_correct(const float * in_re_im, int64_t n, int do_iq, float * out_re_im, float dc_offset[2])
+{
+  MemoryDevice dev(reinterpret_cast<const cf32 *>(in_re_im), n);
+  auto rdp = std::make_unique<SampleReader>(nullptr, &dev, nullptr); // (the reader holds a 16 MB oscillator table)
+  SampleReader & rd = *rdp;
+  rd.set_dc_and_iq_correction(true, do_iq != 0);
+  auto buf = std::make_unique<TArrayTn>();
+  int64_t pos = 0;
+  while (pos < n)
+  {
+    const i32 cnt = (i32)std::min<int64_t>(2048, n - pos);
+    rd.get_samples(*buf, 0, cnt, 0.0f, false);
+    memcpy(out_re_im + 2 * pos, buf->data(), sizeof(cf32) * (size_t)cnt);
+    pos += cnt;
+  }
+  const cf32 dc = rd.get_dc_offset();
+  dc_offset[0] = real(dc);
+  dc_offset[1] = imag(dc);
+}
+
+namespace
+{
 struct FrameRec
 {
   dabref_frame_info info{};

@@ -109,6 +109,21 @@ class Oracle:
             f = iq.astype(np.float32) / np.float32(32768.0)
         return np.ascontiguousarray(f).view(np.complex64).reshape(-1)
 
+    def dc_iq_correct(self, x: np.ndarray, do_iq: bool, state: np.ndarray | None = None) -> np.ndarray:
+        """SampleReader's DC / IQ correction. dabo: serial restatement (state = meanI, meanQ, meanII, meanQQ, meanIQ, updated in
+        place); dabref: the reference's own SampleReader (fresh state; self.last_dc = its get_dc_offset())."""
+        x = np.ascontiguousarray(x, np.complex64).reshape(-1)
+        out = np.zeros_like(x)
+        if self.prefix == "dabo":
+            st = state if state is not None else np.array([0, 0, 1, 1, 0], np.float32)
+            self.f("dc_iq_correct")(_ptr(x), ctypes.c_int64(x.size), int(do_iq), _ptr(st), _ptr(out))
+            self.last_dc = (float(st[0]), float(st[1]))
+        else:
+            dc = np.zeros(2, np.float32)
+            self.f("dc_iq_correct")(_ptr(x), ctypes.c_int64(x.size), int(do_iq), _ptr(out), _ptr(dc))
+            self.last_dc = (float(dc[0]), float(dc[1]))
+        return out
+
     def resample(self, x: np.ndarray, sample_rate: int, reader: str) -> np.ndarray:
         """XmlReader / WavReader linear-interpolation resampling (C restatement only: the readers need Qt)."""
         x = np.ascontiguousarray(x, np.complex64).reshape(-1)

@@ -67,7 +67,7 @@ def build_synth(force: bool = False) -> str:
 
 def build_oracle(force: bool = False) -> str:
     odir = os.path.join(REPO, "oracle")
-    if force or not _newer(LIB_ORACLE, [os.path.join(odir, "dab_oracle.c"), os.path.join(odir, "dab_outer.c"), os.path.join(odir, "dab_oracle.h")]):
+    if force or not _newer(LIB_ORACLE, [os.path.join(odir, f) for f in ("dab_oracle.c", "dab_outer.c", "dab_tii.c", "dab_oracle.h")]):
         _run(["make", "-C", odir, "-B" if force else "-s", "libdab_oracle.so"])
     return LIB_ORACLE
 

@@ -146,6 +146,17 @@ void    dabo_chain_quality(void * h, float out[6]); /* dabo_ofdm_quality of the 
 int     dabo_chain_lcd(void * h, float out[6]);     /* dabo_ofdm_lcd of the chain's decoder */
 double  dabo_chain_seconds(void * h);
 
+/* TII detector (ofdm/tii_detector.cpp; restatement in dab_tii.c) */
+typedef struct { int32_t main_id, sub_id; float strength, phase_deg; int32_t non_etsi; } dabo_tii_result;
+void * dabo_tii_new(void);
+void   dabo_tii_free(void * h);
+void   dabo_tii_reset(void * h);
+void   dabo_tii_set_collisions(void * h, int on, int sub_id);
+void   dabo_tii_add(void * h, const float * fft2048);                                  /* add_to_tii_buffer */
+int    dabo_tii_process(void * h, int threshold_db, dabo_tii_result * out, int cap);  /* process_tii_data; returns the count */
+void   dabo_tii_decoded(void * h, float * out_re_im);                                  /* mDecodedBufferArr, 768 complex */
+void   dabo_tii_tables(void * h, uint8_t pattern[70], uint8_t phase_corr[768]);        /* the two derived constant tables */
+
 #ifdef __cplusplus
 }
 #endif

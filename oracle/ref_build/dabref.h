@@ -82,6 +82,15 @@ typedef struct
   uint8_t fic_valid[4];
 } dabref_frame_info;
 
+/* TiiDetector (ofdm/tii_detector.h:30-45): null-symbol spectra in, transmitter identifications out */
+typedef struct { int32_t main_id, sub_id; float strength, phase_deg; int32_t non_etsi; } dabref_tii_result;
+void * dabref_tii_new(void);
+void   dabref_tii_free(void * h);
+void   dabref_tii_reset(void * h);
+void   dabref_tii_set_collisions(void * h, int on, int sub_id);
+void   dabref_tii_add(void * h, const float * fft2048);                                      /* add_to_tii_buffer */
+int    dabref_tii_process(void * h, int threshold_db, dabref_tii_result * out, int cap);    /* process_tii_data; returns the count */
+
 /* SampleReader (ofdm/sample_reader.h:60-70) with DC (+ IQ) correction switched on, 0 Hz mixing, over n samples */
 void    dabref_dc_iq_correct(const float * in_re_im, int64_t n, int do_iq, float * out_re_im, float dc_offset[2]);
 void *  dabref_chain_run(const float * iq_re_im, int64_t n_samples, const dabref_chain_cfg * cfg);

@@ -239,6 +239,24 @@ extern "C" int dabref_phaseref_estimate_offset(void * h, const float * fft2048)
   return static_cast<PhaseRefBox *>(h)->ref.estimate_carrier_offset_from_sync_symbol_0(as_tu(fft2048));
 }
 
+// ------------------------------------------------------------------------------------------------ TII detector
+extern "C" void * dabref_tii_new(void) { return new TiiDetector(); }
+extern "C" void dabref_tii_free(void * h) { delete static_cast<TiiDetector *>(h); }
+extern "C" void dabref_tii_reset(void * h) { static_cast<TiiDetector *>(h)->reset(); }
+extern "C" void dabref_tii_set_collisions(void * h, int on, int sub_id)
+{
+  static_cast<TiiDetector *>(h)->set_detect_collisions(on != 0);
+  static_cast<TiiDetector *>(h)->set_subid_for_collision_search((u8)sub_id);
+}
+extern "C" void dabref_tii_add(void * h, const float * fft2048) { static_cast<TiiDetector *>(h)->add_to_tii_buffer(as_tu(fft2048)); }
+extern "C" int dabref_tii_process(void * h, int threshold_db, dabref_tii_result * out, int cap)
+{
+  const std::vector<STiiResult> r = static_cast<TiiDetector *>(h)->process_tii_data((i16)threshold_db);
+  for (int i = 0; i < (int)r.size() && i < cap; i++)
+    out[i] = dabref_tii_result{ r[i].mainId, r[i].subId, r[i].strength, r[i].phaseDeg, r[i].isNonEtsiPhase ? 1 : 0 };
+  return (int)r.size();
+}
+
 // ------------------------------------------------------------------------------------------------ whole chain
 namespace
 {

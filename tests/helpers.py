@@ -102,3 +102,37 @@ def dabplus_superframe(bit_rate: int, rng: np.random.Generator, rs_encode, dac_r
     for j in range(rs_dims):
         block[j::rs_dims] = rs_encode(data[j::rs_dims])
     return np.unpackbits(block).reshape(5, 24 * bit_rate), aus
+
+
+# ---- TII (EN 300 401 clause 14.8): null-symbol spectra for the detector tests
+TII_PATTERNS = [b for b in range(256) if bin(b).count("1") == 4]   # main id -> group pattern (MSB = group 0)
+
+
+def tii_pair_fft_index(i: int) -> int:
+    """fft index of the first carrier of pair i (carriers k = -768 + 2 i and k + 1, DC skipped)."""
+    k = -768 + 2 * i
+    return k + 2048 if k < 0 else k + 1
+
+
+def tii_spectrum(ids, rng, amp=30.0, noise=1.0, non_etsi=False, prs=None, single_carriers=()):
+    """One null-symbol spectrum (complex64[2048], fft order) carrying the transmitters `ids` = [(main, sub, phase_rad), ...]:
+    every active carrier pair has both carriers at the same phase (ETSI) or at the PRS phases (the 'non-ETSI' transmitters the
+    reference also looks for); plus white noise and optional lone carriers (which the detector must not take for TII)."""
+    x = (rng.normal(size=2048) + 1j * rng.normal(size=2048)) * (noise / np.sqrt(2.0))
+    for main, sub, ph in ids:
+        pat = TII_PATTERNS[main]
+        for blk in range(4):
+            for grp in range(8):
+                if not pat & (0x80 >> grp):
+                    continue
+                f = tii_pair_fft_index(blk * 192 + grp * 24 + sub)
+                a = amp * np.exp(1j * ph)
+                if non_etsi:
+                    x[f] += a * prs[f]
+                    x[f + 1] += a * prs[f + 1]
+                else:
+                    x[f] += a
+                    x[f + 1] += a
+    for i, a in single_carriers:
+        x[tii_pair_fft_index(i)] += a
+    return x.astype(np.complex64)

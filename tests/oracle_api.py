@@ -308,6 +308,46 @@ class Oracle:
         return res
 
 
+class TiiResultC(ctypes.Structure):
+    _fields_ = [("main_id", ctypes.c_int32), ("sub_id", ctypes.c_int32), ("strength", ctypes.c_float), ("phase_deg", ctypes.c_float), ("non_etsi", ctypes.c_int32)]
+
+
+class TiiDetector:
+    """ofdm/tii_detector.h:30-45 through the oracle restatement (dabo) or the reference's own object (dabref)."""
+
+    def __init__(self, o: "Oracle"):
+        self.o = o
+        o.f("tii_new").restype = c_p
+        self.h = c_p(o.f("tii_new")())
+
+    def __del__(self):
+        try:
+            self.o.f("tii_free")(self.h)
+        except Exception:
+            pass
+
+    def reset(self):
+        self.o.f("tii_reset")(self.h)
+
+    def set_collisions(self, on: bool, sub_id: int = 0):
+        self.o.f("tii_set_collisions")(self.h, int(on), int(sub_id))
+
+    def add(self, fft: np.ndarray):
+        fft = np.ascontiguousarray(fft, np.complex64).reshape(-1, 2048)
+        for row in fft:
+            self.o.f("tii_add")(self.h, _ptr(row))
+
+    def process(self, threshold_db: int) -> list[tuple]:
+        out = (TiiResultC * 2048)()
+        n = int(self.o.f("tii_process")(self.h, int(threshold_db), out, 2048))
+        return [(r.main_id, r.sub_id, r.strength, r.phase_deg, r.non_etsi) for r in out[:n]]
+
+    def decoded(self) -> np.ndarray:
+        out = np.zeros(768, np.complex64)
+        self.o.f("tii_decoded")(self.h, _ptr(out))
+        return out
+
+
 class ChainResult:
     def __init__(self, o: Oracle, h, tab: np.ndarray):
         self.o, self.h = o, h

@@ -1,5 +1,7 @@
 """Direct comparison of the C restatement with the reference's own objects (oracle/_ref), where /root/reference was
 available to build them. Skipped on the GPU box."""
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -84,3 +86,52 @@ def test_eti_generator(oracle, refo):
     assert a.n_frames == b.n_frames
     assert b.eti.size > 0 and b.eti.size % 6144 == 0
     assert np.array_equal(a.eti, b.eti)
+
+
+def _tii_close(a, b):
+    assert len(a) == len(b), (a, b)
+    for x, y in zip(a, b):
+        assert x[:2] == y[:2] and x[4] == y[4], (x, y)
+        assert abs(x[2] - y[2]) <= 1e-5 * max(1.0, abs(y[2])) and abs(((x[3] - y[3] + 180.0) % 360.0) - 180.0) < 1e-2, (x, y)
+
+
+@pytest.mark.parametrize("case", ["one", "three", "non_etsi", "collision", "noise_only", "lone_carriers"])
+def test_tii_detector(oracle, refo, case):
+    """TiiDetector restatement against the reference's own object: same identifications, strengths and phases over several
+    processing rounds (the pair-product IIR carries over), incl. non-ETSI phases, collisions and rejected lone carriers."""
+    from oracle_api import TiiDetector
+    rng = np.random.default_rng(len(case))
+    prs = oracle.phase_table()
+    ids = {"one": [(12, 5, 0.3)], "three": [(3, 0, 0.0), (44, 17, 1.0), (69, 23, -2.0)], "non_etsi": [(20, 9, 0.5)],
+           "collision": [(10, 4, 0.2), (33, 4, 0.9)], "noise_only": [], "lone_carriers": [(7, 2, 0.1)]}[case]
+    a, b = TiiDetector(oracle), TiiDetector(refo)
+    if case == "collision":
+        a.set_collisions(True, 4)
+        b.set_collisions(True, 4)
+    for rnd in range(4):
+        amps = [40.0, 25.0, 60.0, 5.0][rnd]
+        for _ in range(3):
+            x = helpers.tii_spectrum(ids, rng, amp=amps, non_etsi=case == "non_etsi", prs=prs,
+                                     single_carriers=[(100, 300.0), (555, 200.0j)] if case == "lone_carriers" else ())
+            a.add(x)
+            b.add(x)
+        ra, rb = a.process(6 + rnd), b.process(6 + rnd)
+        _tii_close(ra, rb)
+        if rnd == 0 and ids:
+            assert {(r[0], r[1]) for r in ra if r[0] != 99} >= {(m, s) for m, s, _ in ids} or case == "collision"
+    a.reset()
+    b.reset()
+    _tii_close(a.process(8), b.process(8))
+
+
+def test_tii_tables_are_derived_correctly(oracle):
+    """The two constant tables of tii_detector.cpp (:19-125) are derived in the restatement, not copied: check them against the
+    values extracted from the reference source (tests/golden/tii_tables.npz, tools/make_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "tii_tables.npz"))
+    from oracle_api import TiiDetector
+    t = TiiDetector(oracle)
+    pat, pc = np.zeros(70, np.uint8), np.zeros(768, np.uint8)
+    oracle.f("tii_tables")(t.h, pat.ctypes.data_as(ctypes.c_void_p), pc.ctypes.data_as(ctypes.c_void_p))
+    assert np.array_equal(pat, g["main_id_pattern"]) and np.array_equal(pc, g["phase_corr"])
+    assert list(pat) == helpers.TII_PATTERNS

@@ -20,6 +20,7 @@ from dabstar_b200 import synth  # noqa: E402
 from oracle_api import Oracle  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
+REF_ROOT = "/root/reference"
 
 
 def sha(a: np.ndarray) -> str:
@@ -106,6 +107,25 @@ def main():
     r = ref.chain_run(iq_f, synth.subch_table(kw["subch"]), len(kw["subch"]), eti=True)
     np.savez_compressed(os.path.join(OUT, "eti.npz"), iq_sha256=np.array(sha(rec.iq)), n_frames=np.int32(r.n_frames), eti=r.eti.reshape(-1, 6144))
     r.close()
+    # ---- TII detector: its two constant tables, extracted from the reference source text (tii_detector.cpp:19-125), and the
+    #      identifications of the reference's own TiiDetector on seeded spectra
+    import re
+    from oracle_api import TiiDetector
+    src = open(os.path.join(REF_ROOT, "src", "base", "ofdm", "tii_detector.cpp")).read()
+    pc = np.array([int(x) for x in re.findall(r"\d+", re.search(r"cPhaseCorrTable = \{(.*?)\};", src, re.S).group(1))], np.uint8)
+    pat = np.array([int(x, 16) for x in re.findall(r"0x([0-9a-f]{2})", re.search(r"cMainIdPatternTable = \{(.*?)\};", src, re.S).group(1))], np.uint8)
+    np.savez_compressed(os.path.join(OUT, "tii_tables.npz"), main_id_pattern=pat, phase_corr=pc)
+    rng = np.random.default_rng(99)
+    ids = [(3, 0, 0.0), (44, 17, 1.0), (69, 23, -2.0)]
+    det = TiiDetector(ref)
+    spectra, results = [], []
+    for rnd in range(3):
+        for _ in range(2):
+            x = helpers.tii_spectrum(ids, rng, amp=[40.0, 25.0, 60.0][rnd])
+            spectra.append(x)
+            det.add(x)
+        results.append(np.array(det.process(8), np.float64).reshape(-1, 5))
+    np.savez_compressed(os.path.join(OUT, "tii_known_answers.npz"), spectra=np.stack(spectra), r0=results[0], r1=results[1], r2=results[2])
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

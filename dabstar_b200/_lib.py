@@ -35,6 +35,10 @@ class SampleFormatC(ctypes.Structure):
     _fields_ = [("container", ctypes.c_int32), ("bits_per_channel", ctypes.c_int32), ("msb_first", ctypes.c_int32), ("iq_order", ctypes.c_int32)]
 
 
+class TiiResultC(ctypes.Structure):
+    _fields_ = [("main_id", ctypes.c_int32), ("sub_id", ctypes.c_int32), ("strength", ctypes.c_float), ("phase_deg", ctypes.c_float), ("non_etsi", ctypes.c_int32)]
+
+
 class DcIqStateC(ctypes.Structure):
     _fields_ = [(n, ctypes.c_float) for n in ("mean_i", "mean_q", "mean_ii", "mean_qq", "mean_iq")]
 
@@ -64,6 +68,8 @@ EXPORTS = [
     ("dabstar_abi_version", ctypes.c_int), ("dabstar_kernel_launches", ctypes.c_uint64),
     ("dabstar_freq_interleaver", ctypes.c_int), ("dabstar_phase_table", ctypes.c_int), ("dabstar_protection_addresses", ctypes.c_int),
     ("dabstar_ingest_convert", ctypes.c_int), ("dabstar_sample_format_bytes", ctypes.c_int),
+    ("dabstar_tii_create", ctypes.c_int), ("dabstar_tii_destroy", None), ("dabstar_tii_reset", ctypes.c_int), ("dabstar_tii_set_collisions", ctypes.c_int),
+    ("dabstar_tii_add", ctypes.c_int), ("dabstar_tii_process", ctypes.c_int), ("dabstar_tii_decoded", ctypes.c_int),
     ("dabstar_dc_iq_correct", ctypes.c_int), ("dabstar_file_probe", ctypes.c_int), ("dabstar_resample_count", ctypes.c_int64), ("dabstar_resample_linear", ctypes.c_int64),
     ("dabstar_dabplus_decode", ctypes.c_int),
     ("dabstar_fib_parser_create", ctypes.c_int), ("dabstar_fib_parser_destroy", None), ("dabstar_fib_parser_push", ctypes.c_int),

@@ -360,6 +360,46 @@ class Protection:
         return out
 
 
+class TiiDetector:
+    """ofdm/tii_detector.h:30-45 for n recordings at once (one detector each)."""
+
+    def __init__(self, n_detectors: int = 1, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.n = int(n_detectors)
+        self.h = c_p()
+        self.ctx.check(self.ctx.lib.dabstar_tii_create(self.ctx.h, self.n, ctypes.byref(self.h)), "dabstar_tii_create")
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.ctx.lib.dabstar_tii_destroy(self.h)
+        except Exception:
+            pass
+
+    def reset(self):
+        self.ctx.check(self.ctx.lib.dabstar_tii_reset(self.h), "dabstar_tii_reset")
+
+    def set_detect_collisions(self, on: bool, sub_id: int = 0):
+        self.ctx.check(self.ctx.lib.dabstar_tii_set_collisions(self.h, int(on), int(sub_id)), "dabstar_tii_set_collisions")
+
+    def add_to_tii_buffer(self, fft: np.ndarray):
+        """fft: complex64[n_detectors, n_symbols, 2048] (or [n_symbols, 2048] for a single detector): null-symbol spectra, fft order."""
+        fft = _np(fft, np.complex64).reshape(self.n, -1, 2048)
+        self.ctx.check(self.ctx.lib.dabstar_tii_add(self.h, _ptr(fft), fft.shape[1], MEM_HOST), "dabstar_tii_add")
+
+    def process_tii_data(self, threshold_db: int, cap: int = 128) -> list[list[tuple]]:
+        """Per detector: [(main_id, sub_id, strength, phase_deg, non_etsi), ...], strongest first."""
+        out = (_lib.TiiResultC * (self.n * cap))()
+        cnt = np.zeros(self.n, np.int32)
+        self.ctx.check(self.ctx.lib.dabstar_tii_process(self.h, int(threshold_db), out, cap, _ptr(cnt)), "dabstar_tii_process")
+        return [[(r.main_id, r.sub_id, r.strength, r.phase_deg, r.non_etsi) for r in out[d * cap:d * cap + min(int(cnt[d]), cap)]] for d in range(self.n)]
+
+    def decoded(self, detector: int = 0) -> np.ndarray:
+        out = np.zeros(768, np.complex64)
+        self.ctx.check(self.ctx.lib.dabstar_tii_decoded(self.h, detector, _ptr(out)), "dabstar_tii_decoded")
+        return out
+
+
 class FicDecoder:
     """decoder/fic_decoder.h:49-58 (the member DabProcessor calls mFicHandler)."""
 

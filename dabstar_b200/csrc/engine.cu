@@ -382,6 +382,115 @@ extern "C" int dabstar_ingest_convert(dabstar_ctx * ctx, const void * src, const
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ TII detector (next row f4)
+struct dabstar_tii
+{
+  dabstar_ctx * ctx = nullptr;
+  int n = 0;
+  int collisions = 0, sub_id_coll = 0;
+  DevBuf null_sum, decoded, tables, results;
+  DevBuf staging;
+};
+
+extern "C" int dabstar_tii_create(dabstar_ctx * ctx, int n_detectors, dabstar_tii ** out)
+{
+  if (!ctx || !out || n_detectors <= 0) return DABSTAR_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  std::unique_ptr<dabstar_tii> t(new dabstar_tii);
+  t->ctx = ctx;
+  t->n = n_detectors;
+  CK(t->null_sum.reserve(sizeof(float2) * (size_t)n_detectors * T_U));
+  CK(t->decoded.reserve(sizeof(float2) * (size_t)n_detectors * 768));
+  CK(t->tables.reserve(70 + 768 + 16));
+  // cMainIdPatternTable (tii_detector.cpp:19-90): the 70 bytes with four bits set, ascending (EN 300 401 table 42);
+  // cPhaseCorrTable (:92-125): quadrant(PRS[k]) - quadrant(PRS[k + 1]) mod 4 for the carrier pair k, k + 1
+  uint8_t tab[70 + 768];
+  int np = 0;
+  for (int b = 0; b < 256; b++) if (__builtin_popcount((unsigned)b) == 4) tab[np++] = (uint8_t)b;
+  auto quadrant = [&](int f) { const float2 v = ctx->h_prs[f]; return fabsf(v.x) > fabsf(v.y) ? (v.x > 0 ? 0 : 2) : (v.y > 0 ? 1 : 3); };
+  for (int i = 0; i < 768; i++)
+  {
+    const int k = -K_CARR / 2 + 2 * i, f = k < 0 ? k + T_U : k + 1;
+    tab[70 + i] = (uint8_t)((quadrant(f) - quadrant(f + 1)) & 3);
+  }
+  CK(cudaMemcpyAsync(t->tables.p, tab, sizeof(tab), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(t->null_sum.p, 0, sizeof(float2) * (size_t)n_detectors * T_U, ctx->stream));
+  CK(cudaMemsetAsync(t->decoded.p, 0, sizeof(float2) * (size_t)n_detectors * 768, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *out = t.release();
+  return 0;
+}
+extern "C" void dabstar_tii_destroy(dabstar_tii * t)
+{
+  if (!t) return;
+  if (t->ctx) cudaSetDevice(t->ctx->device);
+  delete t;
+}
+extern "C" int dabstar_tii_reset(dabstar_tii * t)
+{
+  if (!t) return DABSTAR_E_INVALID;
+  dabstar_ctx * ctx = t->ctx;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemsetAsync(t->null_sum.p, 0, sizeof(float2) * (size_t)t->n * T_U, ctx->stream));
+  CK(cudaMemsetAsync(t->decoded.p, 0, sizeof(float2) * (size_t)t->n * 768, ctx->stream));
+  return 0;
+}
+extern "C" int dabstar_tii_set_collisions(dabstar_tii * t, int on, int sub_id)
+{
+  if (!t || sub_id < 0 || sub_id > 23) return DABSTAR_E_INVALID;
+  t->collisions = on ? 1 : 0;
+  t->sub_id_coll = sub_id;
+  return 0;
+}
+extern "C" int dabstar_tii_add(dabstar_tii * t, const float * fft, int n_symbols, int mem)
+{
+  if (!t || !fft || n_symbols < 0) return DABSTAR_E_INVALID;
+  if (n_symbols == 0) return 0;
+  dabstar_ctx * ctx = t->ctx;
+  CK(cudaSetDevice(ctx->device));
+  const void * dfft;
+  if (int r = stage_in(ctx, t->staging, fft, sizeof(float2) * (size_t)t->n * n_symbols * T_U, mem, &dfft)) return r;
+  CK(launch_tii_add(ctx->stream, (const float2 *)dfft, t->n, n_symbols, t->null_sum.as<float2>(), &ctx->launches));
+  if (mem == DABSTAR_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream)); // the caller may reuse its buffer
+  return 0;
+}
+extern "C" int dabstar_tii_process(dabstar_tii * t, int threshold_db, dabstar_tii_result * out, int cap, int32_t * counts)
+{
+  if (!t || !out || !counts || cap <= 0) return DABSTAR_E_INVALID;
+  dabstar_ctx * ctx = t->ctx;
+  CK(cudaSetDevice(ctx->device));
+  static_assert(sizeof(TiiResultDev) == sizeof(dabstar_tii_result), "result layout");
+  CK(t->results.reserve(sizeof(TiiResultDev) * (size_t)t->n * cap + sizeof(int) * (size_t)t->n));
+  TiiResultDev * d_res = t->results.as<TiiResultDev>();
+  int * d_cnt = reinterpret_cast<int *>(d_res + (size_t)t->n * cap);
+  const float factor = powf(10.0f, (float)(int16_t)threshold_db / 10.0f); // std::pow(10.0f, (f32)iThreshold_db / 10.0f), tii_detector.cpp:193
+  const uint8_t * tab = t->tables.as<uint8_t>();
+  CK(launch_tii_process(ctx->stream, t->n, t->null_sum.as<float2>(), t->decoded.as<float2>(), tab, tab + 70, factor, t->collisions, t->sub_id_coll, d_res, cap, d_cnt,
+                        &ctx->launches));
+  CK(cudaMemcpyAsync(out, d_res, sizeof(TiiResultDev) * (size_t)t->n * cap, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(counts, d_cnt, sizeof(int) * (size_t)t->n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  // std::sort by strength, descending (tii_detector.cpp:236); the comb threads append in no particular order
+  for (int d = 0; d < t->n; d++)
+  {
+    dabstar_tii_result * r = out + (size_t)d * cap;
+    const int n = std::min(counts[d], cap);
+    std::sort(r, r + n, [](const dabstar_tii_result & a, const dabstar_tii_result & b) {
+      return a.strength != b.strength ? a.strength > b.strength : (a.sub_id != b.sub_id ? a.sub_id < b.sub_id : a.main_id < b.main_id);
+    });
+  }
+  return 0;
+}
+extern "C" int dabstar_tii_decoded(dabstar_tii * t, int detector, float * out)
+{
+  if (!t || !out || detector < 0 || detector >= t->n) return DABSTAR_E_INVALID;
+  dabstar_ctx * ctx = t->ctx;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out, t->decoded.as<float2>() + (size_t)detector * 768, sizeof(float2) * 768, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 // ---- SampleReader's DC / IQ-imbalance correction (sample_reader.cpp:216-243; set_dc_and_iq_correction, sample_reader.h:66)
 extern "C" int dabstar_dc_iq_correct(dabstar_ctx * ctx, const float * in, int64_t n_samples, int do_iq, dabstar_dciq_state * state, float * out, int mem)
 {

@@ -102,6 +102,16 @@ cudaError_t launch_coarse_afc(cudaStream_t s, const DeviceTables & t, const Fram
                               int * offset_hz, unsigned long long * lc);
 cudaError_t launch_coarse_afc_raw(cudaStream_t s, const DeviceTables & t, const float2 * fft_nat, int n, int * offset_hz, unsigned long long * lc);
 // src: packed file samples (see dabstar_sample_format in the C header); lut: 256 floats for the 8-bit containers (device), else nullptr
+// tii_kernels.cu: TiiDetector (ofdm/tii_detector.cpp) for a batch of detectors
+struct TiiResultDev
+{
+  int main_id, sub_id;
+  float strength, phase_deg;
+  int non_etsi;
+};
+cudaError_t launch_tii_add(cudaStream_t s, const float2 * fft, int n_detectors, int n_symbols, float2 * null_sum, unsigned long long * lc);
+cudaError_t launch_tii_process(cudaStream_t s, int n_detectors, float2 * null_sum, float2 * decoded, const uint8_t * pattern, const uint8_t * phase_corr,
+                               float threshold_factor, int collisions, int sub_id_coll, TiiResultDev * out, int cap, int * counts, unsigned long long * lc);
 // dciq_kernels.cu: SampleReader's DC / IQ-imbalance correction over a whole recording (sample_reader.cpp:216-243).
 // state: { meanI, meanQ, meanII, meanIQ, meanQQ }, in and out; workspace: dciq_workspace_bytes(n) device bytes.
 size_t dciq_workspace_bytes(long long n);

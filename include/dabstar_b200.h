@@ -122,6 +122,31 @@ typedef struct
 } dabstar_file_info;
 int dabstar_file_probe(const uint8_t * head, int64_t head_bytes, int64_t file_bytes, dabstar_file_info * out);
 
+/* ------------------------------------------------------------------------------------------------ TII detection (next row f4) */
+/* TiiDetector (ofdm/tii_detector.h:30-45, tii_detector.cpp) for n_detectors recordings at once, one CTA each. The reference
+ * feeds it the FFT of every null symbol whose CIF counter has (count & 7) >= 4 (dab_processor.cpp:273-300), and asks for
+ * the transmitter list after tiiFramesToCount of them. Results are sorted by strength, strongest first (equal strengths:
+ * by sub id, then main id; the reference leaves that order to std::sort). main_id 99 marks a collision on a comb other
+ * than the one set for the detailed search (tii_detector.cpp:462-471). */
+typedef struct dabstar_tii dabstar_tii;
+typedef struct
+{
+  int32_t main_id, sub_id;  /* STiiResult (tii_detector.h:14-21) */
+  float   strength, phase_deg;
+  int32_t non_etsi;
+} dabstar_tii_result;
+int  dabstar_tii_create(dabstar_ctx * ctx, int n_detectors, dabstar_tii ** out);
+void dabstar_tii_destroy(dabstar_tii * t);
+int  dabstar_tii_reset(dabstar_tii * t);                                /* TiiDetector::reset on every detector */
+int  dabstar_tii_set_collisions(dabstar_tii * t, int on, int sub_id);    /* set_detect_collisions + set_subid_for_collision_search */
+/* add_to_tii_buffer: fft = n_detectors x n_symbols x 2048 complex floats (fft order); detector d accumulates its n_symbols spectra */
+int  dabstar_tii_add(dabstar_tii * t, const float * fft, int n_symbols, int mem);
+/* process_tii_data(threshold_db) on every detector: out = n_detectors x cap results, counts[d] = results of detector d
+ * (a count above cap means the list was cut). Host memory. */
+int  dabstar_tii_process(dabstar_tii * t, int threshold_db, dabstar_tii_result * out, int cap, int32_t * counts);
+/* mDecodedBufferArr of one detector: 768 complex floats (the filtered carrier-pair products) */
+int  dabstar_tii_decoded(dabstar_tii * t, int detector, float * out);
+
 /* Sample-rate conversion to 2.048 MS/s as the readers do it when the reference is built without liquid-dsp (the
  * default): per 1 ms block of rate/1000 input samples, 2048 output samples by linear interpolation between neighbours
  * (XmlReader: xml_reader.cpp:70-76,212-231; WavReader: wav_reader.cpp:66-83,196-211; the two differ in table precision

@@ -1,0 +1,85 @@
+"""Next row f4: TII detection. The CUDA detector (one CTA per recording) against the oracle restatement of
+ofdm/tii_detector.cpp, which is pinned against the reference's own TiiDetector object (tests/test_oracle_vs_ref.py,
+tests/golden/tii_known_answers.npz): identifications and flags identical, strengths / phases within float tolerance."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from dabstar_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+CASES = {"one": [(12, 5, 0.3)], "three": [(3, 0, 0.0), (44, 17, 1.0), (69, 23, -2.0)], "non_etsi": [(20, 9, 0.5)],
+         "collision": [(10, 4, 0.2), (33, 4, 0.9)], "noise_only": [], "lone_carriers": [(7, 2, 0.1)]}
+
+
+def _close(a, b):
+    assert len(a) == len(b), (a, b)
+    for x, y in zip(a, b):
+        assert (x[0], x[1], x[4]) == (y[0], y[1], y[4]), (x, y)
+        assert abs(x[2] - y[2]) <= 1e-5 * max(1.0, abs(y[2])) and abs(((x[3] - y[3] + 180.0) % 360.0) - 180.0) < 1e-2, (x, y)
+
+
+@pytest.mark.parametrize("collisions", [False, True])
+def test_tii_batch_against_oracle(ctx, oracle, collisions):
+    """Six recordings with different transmitter constellations in one batch, four processing rounds (the filtered pair products
+    carry over), then reset."""
+    from oracle_api import TiiDetector
+    rng = np.random.default_rng(11)
+    prs = oracle.phase_table()
+    names = list(CASES)
+    dets = [TiiDetector(oracle) for _ in names]
+    gpu = api.TiiDetector(len(names), ctx)
+    if collisions:
+        gpu.set_detect_collisions(True, 4)
+        for d in dets:
+            d.set_collisions(True, 4)
+    for rnd in range(4):
+        amp = [40.0, 25.0, 60.0, 5.0][rnd]
+        n_sym = 1 + rnd % 3
+        x = np.stack([np.stack([helpers.tii_spectrum(CASES[n], rng, amp=amp, non_etsi=n == "non_etsi", prs=prs,
+                                                     single_carriers=[(100, 300.0), (555, 200.0j)] if n == "lone_carriers" else ())
+                                for _ in range(n_sym)]) for n in names])
+        gpu.add_to_tii_buffer(x)
+        for d, xs in zip(dets, x):
+            d.add(xs)
+        got = gpu.process_tii_data(6 + rnd)
+        for i, (d, n) in enumerate(zip(dets, names)):
+            want = d.process(6 + rnd)
+            _close(got[i], want)
+            assert np.allclose(gpu.decoded(i), d.decoded(), rtol=1e-6, atol=1e-6 * np.abs(d.decoded()).max())
+            if rnd == 0 and n not in ("collision", "noise_only"):
+                assert {(r[0], r[1]) for r in got[i]} == {(m, s) for m, s, _ in CASES[n]}, n
+        if rnd == 0:
+            assert got[names.index("noise_only")] == []
+            assert got[names.index("non_etsi")][0][4] == 1
+    gpu.reset()
+    for d in dets:
+        d.reset()
+    for i, d in enumerate(dets):
+        _close(gpu.process_tii_data(8)[i], d.process(8))
+
+
+def test_tii_against_reference_known_answers(ctx):
+    """What the reference's own TiiDetector reported for these spectra (tools/make_golden.py)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "tii_known_answers.npz"))
+    det = api.TiiDetector(1, ctx)
+    for rnd in range(3):
+        det.add_to_tii_buffer(g["spectra"][2 * rnd:2 * rnd + 2])
+        got, want = det.process_tii_data(8)[0], g[f"r{rnd}"]
+        _close(got, [(int(r[0]), int(r[1]), r[2], r[3], int(r[4])) for r in want])
+
+
+def test_tii_result_cap_and_arguments(ctx):
+    det = api.TiiDetector(2, ctx)
+    rng = np.random.default_rng(2)
+    ids = [(m, s, 0.0) for m, s in ((1, 1), (2, 2), (3, 3), (4, 4), (5, 5))]
+    det.add_to_tii_buffer(np.stack([np.stack([helpers.tii_spectrum(ids, rng)]), np.stack([helpers.tii_spectrum([], rng)])]))
+    out = (api._lib.TiiResultC * (2 * 3))()
+    cnt = np.zeros(2, np.int32)
+    ctx.check(ctx.lib.dabstar_tii_process(det.h, 8, out, 3, cnt.ctypes.data_as(api.c_p)), "dabstar_tii_process")
+    assert list(cnt) == [5, 0]  # five found, room for three: the count tells
+    with pytest.raises(api.DabstarError):
+        det.set_detect_collisions(True, 24)

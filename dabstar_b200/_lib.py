@@ -85,6 +85,7 @@ EXPORTS = [
     ("dabstar_decoder_msc_size", ctypes.c_int64), ("dabstar_decoder_msc_copy", ctypes.c_int64),
     ("dabstar_decoder_set_auto_config", ctypes.c_int), ("dabstar_decoder_subchannels", ctypes.c_int), ("dabstar_decoder_ensemble", ctypes.c_int),
     ("dabstar_decoder_enable_eti", ctypes.c_int), ("dabstar_decoder_eti_size", ctypes.c_int64), ("dabstar_decoder_eti_copy", ctypes.c_int64),
+    ("dabstar_decoder_enable_tii", ctypes.c_int), ("dabstar_decoder_tii_events", ctypes.c_int), ("dabstar_decoder_tii_results", ctypes.c_int),
     ("dabstar_decoder_counters", ctypes.c_int), ("dabstar_decoder_quality", ctypes.c_int), ("dabstar_decoder_last_ms", ctypes.c_double),
     ("dabstar_decoder_stage_ms", ctypes.c_int),
 ]

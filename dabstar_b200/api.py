@@ -612,6 +612,23 @@ class DabProcessor:
         lib.dabstar_decoder_counters(self.h, recording, _ptr(cnt))
         return RecordingResult(nf, list(info)[:nf], bits, valid, msc, cnt)
 
+    def set_tii_processing(self, recording: int, on: bool = True, frames_to_count: int = 5, threshold_db: int = 8, collisions: bool = False, sub_id: int = 0):
+        """DabProcessor::set_tii_processing / set_tii_threshold / set_tii_collisions / set_tii_sub_id (+ ProcessParams::tiiFramesToCount);
+        needs set_auto_config (the CIF counter decides which null symbols carry TII)."""
+        self.ctx.check(self.ctx.lib.dabstar_decoder_enable_tii(self.h, recording, int(on), int(frames_to_count), int(threshold_db), int(collisions), int(sub_id)),
+                       "dabstar_decoder_enable_tii")
+
+    def tii_events(self, recording: int, cap: int = 128) -> list[tuple[int, list[tuple]]]:
+        """[(frame, [(main_id, sub_id, strength, phase_deg, non_etsi), ...]), ...]: what signal_show_tii would have carried, per search."""
+        n = self.ctx.check(self.ctx.lib.dabstar_decoder_tii_events(self.h, recording), "dabstar_decoder_tii_events")
+        out = []
+        for e in range(n):
+            buf = (_lib.TiiResultC * cap)()
+            fr = ctypes.c_int32(0)
+            k = self.ctx.check(self.ctx.lib.dabstar_decoder_tii_results(self.h, recording, e, buf, cap, ctypes.byref(fr)), "dabstar_decoder_tii_results")
+            out.append((fr.value, [(r.main_id, r.sub_id, r.strength, r.phase_deg, r.non_etsi) for r in buf[:min(k, cap)]]))
+        return out
+
     def quality(self, recording: int) -> dict:
         """SLcdData figures (MER, SNR, ...) of a recording's OFDM decoder at the end of the last run()."""
         out = np.zeros(6, np.float32)

@@ -1026,6 +1026,12 @@ struct Recording
   bool eti_on = false;       // EtiGenerator running from the first frame of the run (DabProcessor::start_eti_generator)
   int eti_cif_hi = 0, eti_cif_lo = 0; // IFibDecoder::get_cif_count(hi, lo) as the generator samples it at symbol 4
   std::vector<uint8_t> eti;  // ETI-NI frames of the last run, 6144 bytes each
+  // TII (dab_processor.cpp:273-300): needs auto_cfg, because which null symbols carry TII follows from the CIF counter
+  struct TiiCfg { bool on = false; int frames_to_count = 5, threshold_db = 8, collisions = 0, sub_id = 0; } tii;
+  struct TiiEvent { int frame; std::vector<dabstar_tii_result> res; int total; };
+  std::vector<TiiEvent> tii_events;  // one per process_tii_data call of the last run
+  std::vector<FrameDesc> descs;      // descriptors of the accepted frames (the TII pass transforms their null symbols again)
+  std::vector<int> sync_frames;      // n_slots at every successful time sync (mTiiDetector.reset(), dab_processor.cpp:150-152)
   bool auto_cfg = false;     // sub-channels and CIF counter from the recording's own FIG 0/0 and 0/1
   std::vector<int> cif_hi_f, cif_lo_f; // auto_cfg: CIF counter as the FIB decoder holds it after each frame's FIC (-1: none yet)
   dabstar_ensemble_info ens{};
@@ -1051,6 +1057,7 @@ struct dabstar_decoder
   DevBuf d_states;      // OfdmStateDev[n_rec]
   DevBuf d_snap;        // snapshot of d_states
   DevBuf d_desc, d_work, d_cp, d_start, d_coarse, d_dipw, d_dipr, d_jobs, d_mscbits, d_etibits, d_etipacked;
+  DevBuf d_tii_fft;   // null-symbol spectra of one TII event, fft order
   HostBuf h_fib;
   std::vector<int16_t> h_soft_one;
   long long total_slots = 0;
@@ -1417,7 +1424,9 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
     std::vector<MscOut> keep = std::move(R.msc);
     const bool eti_on = R.eti_on, auto_cfg = R.auto_cfg;
     const int eti_hi = R.eti_cif_hi, eti_lo = R.eti_cif_lo;
+    const Recording::TiiCfg tii_cfg = R.tii;
     R = Recording();
+    R.tii = tii_cfg;
     R.auto_cfg = auto_cfg;
     if (auto_cfg) keep.clear(); // rediscovered from this run's FIC
     R.msc = std::move(keep);
@@ -1493,7 +1502,7 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
           Recording & R = dec->recs[who[i]];
           R.pos = dr[i].pos;
           R.clock_err = 0.0f; // dab_processor.cpp:158
-          if (dr[i].status == 0) { R.state = RecState::EVAL; R.cnt_sync_ok++; }
+          if (dr[i].status == 0) { R.state = RecState::EVAL; R.cnt_sync_ok++; R.sync_frames.push_back(R.n_slots); }
           else if (dr[i].status == 3) R.state = RecState::DONE;
           else R.cnt_sync_fail++;
         }
@@ -1903,6 +1912,7 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
           if (complete)
           {
             R.frames.push_back(ctl[i].info);
+            R.descs.push_back(ctl[i].desc);
             R.crc_ok.insert(R.crc_ok.end(), crc.begin() + (size_t)i * 12, crc.begin() + (size_t)i * 12 + 12);
             R.n_slots++;
           }
@@ -2005,6 +2015,88 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
         dabstar_fib_parser_destroy(fp);
       }
       if (int e = sync_profiles(ctx)) return e;
+    }
+  }
+
+  // ================= TII (dab_processor.cpp:273-300) for self-configured recordings: the null symbol after frame f carries TII
+  // when the CIF counter the FIB decoder holds after that frame's FIC has (count & 7) >= 4. Those null symbols are
+  // transformed again (the demapper's spectrum buffer is per window), accumulated tiiFramesToCount at a time and searched;
+  // a time re-synchronisation resets the detector and the counter (dab_processor.cpp:150-152).
+  {
+    struct Seg { int rec; std::vector<int> frames; bool reset_before; };
+    std::map<int, std::vector<Seg>> per_rec;
+    for (int r = 0; r < n_rec; r++)
+    {
+      Recording & R = dec->recs[r];
+      R.tii_events.clear();
+      if (!R.tii.on || !R.auto_cfg || R.n_slots == 0) continue;
+      const int need = std::max(1, R.tii.frames_to_count);
+      std::vector<int> acc;
+      bool reset_pending = false;
+      size_t si = 0;
+      for (int f = 0; f < R.n_slots; f++)
+      {
+        while (si < R.sync_frames.size() && R.sync_frames[si] <= f) { acc.clear(); reset_pending = true; si++; }
+        if (f >= (int)R.cif_hi_f.size() || R.cif_hi_f[f] < 0) continue; // get_cif_count() is still 0: not a TII null symbol
+        if ((((R.cif_hi_f[f] * 250 + R.cif_lo_f[f]) & 7) >= 4))
+        {
+          acc.push_back(f);
+          if ((int)acc.size() >= need) { per_rec[r].push_back({ r, acc, reset_pending }); acc.clear(); reset_pending = false; }
+        }
+      }
+    }
+    if (!per_rec.empty())
+    {
+      // recordings with more events first: event e then concerns the first n_e detectors
+      std::vector<int> order;
+      for (auto & kv : per_rec) order.push_back(kv.first);
+      std::sort(order.begin(), order.end(), [&](int a, int b) { return per_rec[a].size() != per_rec[b].size() ? per_rec[a].size() > per_rec[b].size() : a < b; });
+      dabstar_tii * det = nullptr;
+      if (int e = dabstar_tii_create(ctx, (int)order.size(), &det)) return e;
+      std::unique_ptr<dabstar_tii, void (*)(dabstar_tii *)> guard(det, dabstar_tii_destroy);
+      const int need = std::max(1, dec->recs[order[0]].tii.frames_to_count), cap = 128;
+      for (int r : order)
+        if (std::max(1, dec->recs[r].tii.frames_to_count) != need || dec->recs[r].tii.threshold_db != dec->recs[order[0]].tii.threshold_db ||
+            dec->recs[r].tii.collisions != dec->recs[order[0]].tii.collisions || dec->recs[r].tii.sub_id != dec->recs[order[0]].tii.sub_id)
+          return ctx->fail(DABSTAR_E_INVALID, "TII settings must be the same for every recording of a decoder");
+      dabstar_tii_set_collisions(det, dec->recs[order[0]].tii.collisions, dec->recs[order[0]].tii.sub_id);
+      std::vector<dabstar_tii_result> res((size_t)order.size() * cap);
+      std::vector<int32_t> cnt(order.size());
+      for (size_t ev = 0; ev < per_rec[order[0]].size(); ev++)
+      {
+        int n_act = 0;
+        while (n_act < (int)order.size() && per_rec[order[n_act]].size() > ev) n_act++;
+        std::vector<FrameDesc> fd;
+        for (int a = 0; a < n_act; a++)
+        {
+          const Seg & sg = per_rec[order[a]][ev];
+          if (sg.reset_before)
+          {
+            CK(cudaMemsetAsync(det->null_sum.as<float2>() + (size_t)a * T_U, 0, sizeof(float2) * T_U, st));
+            CK(cudaMemsetAsync(det->decoded.as<float2>() + (size_t)a * 768, 0, sizeof(float2) * 768, st));
+          }
+          for (int f : sg.frames) fd.push_back(dec->recs[order[a]].descs[f]);
+        }
+        CK(dec->d_desc.reserve(sizeof(FrameDesc) * fd.size()));
+        UP(dec->d_desc.p, fd.data(), sizeof(FrameDesc) * fd.size());
+        CK(dec->d_tii_fft.reserve(sizeof(float2) * fd.size() * T_U));
+        CK(launch_fft_null(st, ctx->tab, dec->d_desc.as<FrameDesc>(), (int)fd.size(), d_rin, fmt, dec->d_tii_fft.as<float2>(), &ctx->launches));
+        const int n_keep = det->n;
+        det->n = n_act; // the first n_act detectors take part in this event
+        int e = dabstar_tii_add(det, dec->d_tii_fft.as<float>(), need, DABSTAR_MEM_DEVICE);
+        if (e == 0) e = dabstar_tii_process(det, dec->recs[order[0]].tii.threshold_db, res.data(), cap, cnt.data());
+        det->n = n_keep;
+        if (e) return e;
+        for (int a = 0; a < n_act; a++)
+        {
+          Recording & R = dec->recs[order[a]];
+          Recording::TiiEvent te;
+          te.frame = per_rec[order[a]][ev].frames.back();
+          te.total = cnt[a];
+          te.res.assign(res.begin() + (size_t)a * cap, res.begin() + (size_t)a * cap + std::min(cnt[a], cap));
+          R.tii_events.push_back(std::move(te));
+        }
+      }
     }
   }
 
@@ -2246,6 +2338,31 @@ extern "C" int dabstar_decoder_quality(const dabstar_decoder * dec, int recordin
     phase = fi.phase_cp;
   }
   return quality_from_state(ctx, dec->d_states.as<OfdmStateDev>() + recording, sigma, out);
+}
+extern "C" int dabstar_decoder_enable_tii(dabstar_decoder * dec, int recording, int enable, int frames_to_count, int threshold_db, int collisions, int sub_id)
+{
+  if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  if (enable && (frames_to_count < 1 || sub_id < 0 || sub_id > 23)) return dec->ctx->fail(DABSTAR_E_INVALID, "TII: frames_to_count %d, sub id %d", frames_to_count, sub_id);
+  Recording & R = dec->recs[recording];
+  R.tii.on = enable != 0;
+  if (enable) { R.tii.frames_to_count = frames_to_count; R.tii.threshold_db = threshold_db; R.tii.collisions = collisions ? 1 : 0; R.tii.sub_id = sub_id; }
+  return 0;
+}
+extern "C" int dabstar_decoder_tii_events(const dabstar_decoder * dec, int recording)
+{
+  if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  return (int)dec->recs[recording].tii_events.size();
+}
+extern "C" int dabstar_decoder_tii_results(const dabstar_decoder * dec, int recording, int event, dabstar_tii_result * out, int cap, int32_t * frame)
+{
+  if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  const Recording & R = dec->recs[recording];
+  if (event < 0 || event >= (int)R.tii_events.size() || cap < 0 || (cap > 0 && !out)) return DABSTAR_E_INVALID;
+  const Recording::TiiEvent & te = R.tii_events[event];
+  if (frame) *frame = te.frame;
+  const int n = std::min<int>(cap, (int)te.res.size());
+  for (int i = 0; i < n; i++) out[i] = te.res[i];
+  return (int)te.res.size();
 }
 extern "C" double dabstar_decoder_last_ms(const dabstar_decoder * dec) { return dec ? dec->last_ms : 0.0; }
 extern "C" int dabstar_decoder_stage_ms(const dabstar_decoder * dec, double ms[8], int64_t launches[8])

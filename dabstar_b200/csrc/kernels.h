@@ -102,6 +102,9 @@ cudaError_t launch_coarse_afc(cudaStream_t s, const DeviceTables & t, const Fram
                               int * offset_hz, unsigned long long * lc);
 cudaError_t launch_coarse_afc_raw(cudaStream_t s, const DeviceTables & t, const float2 * fft_nat, int n, int * offset_hz, unsigned long long * lc);
 // src: packed file samples (see dabstar_sample_format in the C header); lut: 256 floats for the 8-bit containers (device), else nullptr
+// FFT (fft order) of the null symbol of each listed frame: out = n_frames x 2048
+cudaError_t launch_fft_null(cudaStream_t s, const DeviceTables & t, const FrameDesc * frames, int n_frames, const RecInput * recs, int fmt, float2 * out,
+                            unsigned long long * lc);
 // tii_kernels.cu: TiiDetector (ofdm/tii_detector.cpp) for a batch of detectors
 struct TiiResultDev
 {

@@ -295,6 +295,32 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) k_fft_batch(const float2 * __r
   }
 }
 
+// FFT of the null symbol of every listed frame in fft order (the TII detector's input, dab_processor.cpp:275-276): the same
+// samples, derotation and transform as row 76 of k_fft_frames, without the carrier selection.
+template <int FMT>
+__global__ void __launch_bounds__(FFT_THREADS, 4) k_fft_null(const FrameDesc * __restrict__ frames, int n_frames, const RecInput * __restrict__ recs,
+                                                             const float2 * __restrict__ w2048, float2 * __restrict__ out)
+{
+  __shared__ float2 smem[FFT_SMEM_F2];
+  __shared__ float2 step[16];
+  __shared__ float2 tw2s[FFT_TW2_F2];
+  const int tid = threadIdx.x;
+  FftTwiddles tw;
+  fft_load_twiddles(tw, w2048, tw2s, tid);
+  __syncthreads();
+  for (int fi = blockIdx.x; fi < n_frames; fi += gridDim.x)
+  {
+    const FrameDesc fd = frames[fi];
+    const RecInput rin = recs[fd.rec];
+    const SymbolItem it = symbol_item(fd, rin, X_ROWS - 1);
+    float2 v[16];
+    load_symbol<FMT>(v, it.iq, it.n_total, it.start, it.f, it.ph, step, tid);
+    fft2048_to_smem(v, tw, smem, tid);
+    for (int i = tid; i < T_U; i += FFT_THREADS) out[(size_t)fi * T_U + i] = smem[fft_nat(i)];
+    __syncthreads();
+  }
+}
+
 // Natural-order spectra [frame][77][2048] -> nominal-carrier order [frame][77][1536] (stage tap for the demapper).
 __global__ void k_reorder_frames(const float2 * __restrict__ fft_nat, int n_rows, const int16_t * __restrict__ bin_of_k, float2 * __restrict__ X)
 {
@@ -1920,6 +1946,14 @@ cudaError_t launch_ingest_convert(cudaStream_t s, const void * src, int containe
                                                                                     n_samples, dst);
   if (lc) (*lc)++;
   return cudaGetLastError();
+}
+
+cudaError_t launch_fft_null(cudaStream_t s, const DeviceTables & t, const FrameDesc * frames, int n_frames, const RecInput * recs, int fmt, float2 * out,
+                            unsigned long long * lc)
+{
+  if (n_frames <= 0) return cudaSuccess;
+  if (lc) (*lc)++;
+  return dispatch_fmt(fmt, [&](auto F) { k_fft_null<decltype(F)::value><<<fft_grid(n_frames), FFT_THREADS, 0, s>>>(frames, n_frames, recs, t.w2048, out); });
 }
 
 cudaError_t launch_resample_linear(cudaStream_t s, const float2 * in, long long n_in, int block_in, int shift, const short * base, const float * frac,

@@ -38,7 +38,7 @@ class _Cfg(ctypes.Structure):
     _fields_ = [("n_frames", ctypes.c_int32), ("format", ctypes.c_int32), ("seed", ctypes.c_uint64),
                 ("snr_db", ctypes.c_float), ("cfo_hz", ctypes.c_float), ("rms", ctypes.c_float),
                 ("lead_samples", ctypes.c_int32), ("tail_samples", ctypes.c_int32), ("n_subch", ctypes.c_int32),
-                ("subch", ctypes.c_void_p), ("fig_mode", ctypes.c_int32), ("eid", ctypes.c_int32)]
+                ("subch", ctypes.c_void_p), ("fig_mode", ctypes.c_int32), ("eid", ctypes.c_int32), ("tii_main", ctypes.c_int32), ("tii_sub", ctypes.c_int32)]
 
 
 @dataclass
@@ -66,15 +66,16 @@ def _load():
 
 def generate(n_frames: int, seed: int = 1, snr_db: float = 20.0, cfo_hz: float = 0.0, subch: list[SubChannel] | None = None,
              fmt: int = FMT_U8, rms: float = 0.25, lead_samples: int = 60000, tail_samples: int = 4096, out: np.ndarray | None = None,
-             fig_mode: int = 0, eid: int = 0x1234) -> Recording:
+             fig_mode: int = 0, eid: int = 0x1234, tii: tuple[int, int] | None = None) -> Recording:
     """Synthesise `n_frames` Mode-I transmission frames. `lead_samples` of noise-like filler precede the first
     null symbol (the reference spends 40 960 samples on its level estimate before it searches the null).
     fig_mode 1: the FIC carries the ensemble's multiplex configuration (FIG 0/0 with a running CIF counter, FIG 0/1, FIG 0/2)
-    instead of random FIB payloads."""
+    instead of random FIB payloads. tii = (main id, sub id): with fig_mode 1 the null symbol after every frame whose CIF counter has
+    (count & 7) >= 4 carries that transmitter identification."""
     lib = _load()
     subch = subch or []
     tab = subch_table(subch)
-    cfg = _Cfg(n_frames, fmt, seed, snr_db, cfo_hz, rms, lead_samples, tail_samples, len(subch), tab.ctypes.data, fig_mode, eid)
+    cfg = _Cfg(n_frames, fmt, seed, snr_db, cfo_hz, rms, lead_samples, tail_samples, len(subch), tab.ctypes.data, fig_mode, eid, tii[0] if tii else -1, tii[1] if tii else -1)
     n = lib.dabsynth_num_samples(ctypes.byref(cfg))
     if out is None:
         out = np.empty(n, np.complex64) if fmt == FMT_CF32 else np.empty((n, 2), np.uint8 if fmt == FMT_U8 else np.int16)

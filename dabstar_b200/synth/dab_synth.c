@@ -37,6 +37,8 @@ typedef struct
   int32_t  fig_mode;      /* 0: random FIB payloads; 1: MCI of the configured ensemble (FIG 0/0 with a running CIF counter,
                              FIG 0/1 per sub-channel, FIG 0/2 one audio service per sub-channel), EN 300 401 clauses 6.2-6.4 */
   int32_t  eid;           /* ensemble identifier for fig_mode 1 */
+  int32_t  tii_main;      /* fig_mode 1: transmitter identification sent in the null symbol after every frame whose CIF counter has */
+  int32_t  tii_sub;       /*   (count & 7) >= 4 (EN 300 401 clause 14.8): main id 0..69 (pattern), sub id 0..23 (comb); -1: no TII */
 } dabsynth_cfg;
 
 /* ---------------------------------------------------------------------------------------------- rng */
@@ -488,6 +490,22 @@ int dabsynth_generate(const dabsynth_cfg * c, void * out_iq, uint8_t * fib_truth
         }
         /* OFDM: null, PRS, 75 differentially modulated symbols */
         memset(frame, 0, sizeof(cf) * TNULL);
+        if (c->fig_mode == 1 && c->tii_main >= 0 && c->tii_main < 70 && c->tii_sub >= 0 && c->tii_sub < 24 && f >= 1 && ((((4 * (f - 1)) % 5000) & 7) >= 4))
+        {
+          /* TII: in each of the 4 blocks of 384 carriers, the groups of the main id's pattern carry the comb's carrier pair */
+          int pat = 0, np = 0;
+          for (int b = 0; b < 256 && np <= c->tii_main; b++) if (__builtin_popcount((unsigned)b) == 4) { pat = b; np++; }
+          memset(sym, 0, sizeof(cf) * TU);
+          for (int blk = 0; blk < 4; blk++)
+            for (int grp = 0; grp < 8; grp++)
+            {
+              if (!(pat & (0x80 >> grp))) continue;
+              const int k = -KC / 2 + 2 * (blk * 192 + grp * 24 + c->tii_sub), bin = k < 0 ? k + TU : k + 1;
+              sym[bin].re = amp; sym[bin + 1].re = amp;
+            }
+          ifft2048(sym);
+          for (int i = 0; i < TNULL; i++) frame[i] = sym[(i - TG + 4 * TU) % TU]; /* the receiver transforms samples TG .. TG + TU - 1 */
+        }
         for (int i = 0; i < TU; i++)
         {
           static const float qre[4] = { 1, 0, -1, 0 }, qim[4] = { 0, 1, 0, -1 };

@@ -358,6 +358,15 @@ int64_t dabstar_decoder_eti_copy(const dabstar_decoder * dec, int recording, uin
 /* out[0] good FIBs, [1] time-sync established count, [2] time-sync failures, [3] samples consumed,
  * [4] speculation windows run, [5] windows cut short by verification, [6] frames decoded,
  * [7] frames sent through the FFT/demap/FIC pass (exceeds [6] by replayed and partial frames) */
+/* TII (DabProcessor::set_tii_processing / set_tii_threshold / set_tii_collisions / set_tii_sub_id, main/dab_processor.h; the
+ * null-symbol handling of dab_processor.cpp:273-300) for a SELF-CONFIGURED recording (dabstar_decoder_set_auto_config): the
+ * null symbol after a frame is a TII symbol when the CIF counter taken from the recording's own FIG 0/0 has (count & 7) >= 4;
+ * frames_to_count of them (ProcessParams::tiiFramesToCount, 5 in the reference's GUI) are accumulated per search. Settings
+ * must be equal for all recordings of a decoder. One event = one process_tii_data call; frame = the frame whose null symbol
+ * completed it. dabstar_decoder_tii_results returns the number of identifications of the event (out receives up to cap). */
+int     dabstar_decoder_enable_tii(dabstar_decoder * dec, int recording, int enable, int frames_to_count, int threshold_db, int collisions, int sub_id);
+int     dabstar_decoder_tii_events(const dabstar_decoder * dec, int recording);
+int     dabstar_decoder_tii_results(const dabstar_decoder * dec, int recording, int event, dabstar_tii_result * out, int cap, int32_t * frame);
 /* dabstar_ofdm_state_quality for a recording's decoder at the end of the last run (the reference shows these figures
  * every 5 frames; mMeanSigmaSqFreqCorr is replayed from the per-frame cyclic-prefix phases). */
 int     dabstar_decoder_quality(const dabstar_decoder * dec, int recording, float out[6]);

@@ -83,3 +83,43 @@ def test_tii_result_cap_and_arguments(ctx):
     assert list(cnt) == [5, 0]  # five found, room for three: the count tells
     with pytest.raises(api.DabstarError):
         det.set_detect_collisions(True, 24)
+
+
+def test_decoder_tii_from_own_cif_counter(ctx, oracle):
+    """Self-configured recordings whose transmitter sends TII in the null symbols the CIF counter selects: the decoder finds the
+    identification, at the frames the reference's counting predicts, and its result equals the oracle detector fed with the
+    null-symbol spectra of the CPU chain for the same frames."""
+    from dabstar_b200 import synth
+    from oracle_api import TiiDetector
+    sc = [synth.SubChannel(3, 100, 54, 0, 2, 72)]
+    recs = [synth.generate(12, seed=50 + i, snr_db=20.0, subch=sc, fmt=synth.FMT_U8, fig_mode=1, tii=t) for i, t in enumerate([(12, 5), (40, 23)])]
+    recs.append(synth.generate(8, seed=60, snr_db=20.0, subch=sc, fmt=synth.FMT_U8, fig_mode=1))  # shorter, no TII sent
+    dp = api.DabProcessor(3, input_format=api.FMT_U8, ctx=ctx)
+    for r in range(3):
+        dp.set_auto_config(r)
+        dp.set_tii_processing(r, True, frames_to_count=2, threshold_db=8)
+    dp.run([r.iq for r in recs])
+    for r, want_id in ((0, (12, 5)), (1, (40, 23))):
+        ev = dp.tii_events(r)
+        nf = dp.result(r).n_frames
+        # CIF counter of frame f is 4 f: TII null symbols follow the odd frames; two per search
+        assert [e[0] for e in ev] == [f for f in range(3, nf, 4)], (ev, nf)
+        for fr, res in ev:
+            assert [(x[0], x[1], x[4]) for x in res] == [(want_id[0], want_id[1], 0)], (fr, res)
+        # the same searches on the CPU: null-symbol FFTs of the oracle chain (row 76), oracle detector
+        chain = oracle.chain_run(oracle.to_cf32(recs[r].iq), synth.subch_table(sc), 1, tap_fft=True)
+        det = TiiDetector(oracle)
+        for (fr, res) in ev:
+            det.add(np.stack([chain.fft(fr - 2)[76], chain.fft(fr)[76]]))
+            want = det.process(8)
+            assert [(x[0], x[1], x[4]) for x in res] == [(y[0], y[1], y[4]) for y in want]
+            assert abs(res[0][2] - want[0][2]) < 1e-3 and abs(((res[0][3] - want[0][3] + 180.0) % 360.0) - 180.0) < 0.5
+        chain.close()
+    ev2 = dp.tii_events(2)
+    assert [e[0] for e in ev2] == [3, 7] and all(res == [] for _, res in ev2)  # searched, nothing above the noise
+    # switched off, or without self-configuration: no searches
+    dp.set_tii_processing(0, False)
+    dp.set_tii_processing(1, False)
+    dp.set_tii_processing(2, False)
+    dp.run([r.iq for r in recs])
+    assert dp.tii_events(0) == []

@@ -227,3 +227,51 @@ def test_cpp_harness_end_to_end(ctx, tmp_path):
     assert np.array_equal(np.fromfile(prefix2 + "0.fic", np.uint8), np.fromfile(prefix + "0.fic", np.uint8))
     for s in sc:
         assert np.array_equal(np.fromfile(prefix2 + f"0.sub{s.sub_ch_id}", np.uint8), np.fromfile(prefix + f"0.sub{s.sub_ch_id}", np.uint8))
+
+
+def test_config3_full_ensemble_18_subchannels(ctx, oracle):
+    """BASELINE configs[2] in small: 18 sub-channels filling 864 CU (EEP-A, EEP-B and UEP, DAB+ and MP2 bit rates), all decoded
+    from one recording in one MSC batch: every sub-channel's logical frames equal the CPU chain's."""
+    spec = [(0, 0, 72, 108), (0, 1, 72, 72), (0, 2, 72, 54), (0, 3, 72, 36), (0, 4, 64, 54), (0, 5, 64, 42), (0, 6, 64, 36), (0, 7, 64, 30),
+            (1, 3, 128, 96), (1, 4, 128, 84), (1, 5, 128, 64), (0, 2, 48, 36), (0, 2, 32, 24), (0, 6, 32, 18), (1, 5, 32, 16), (0, 3, 32, 16),
+            (0, 2, 8, 6), (1, 4, 64, 42)]
+    subch, cu = [], 0
+    for i, (sf, lvl, br, size) in enumerate(spec):
+        subch.append(synth.SubChannel(i + 1, cu, size, sf, lvl, br))
+        cu += size
+    assert len(subch) == 18 and cu <= 864
+    rec = synth.generate(20, seed=3, snr_db=16.0, subch=subch, fmt=synth.FMT_U8)
+    want, dp, got = _run_both(oracle, ctx, rec, subch, synth.FMT_U8)
+    assert want.n_frames == 20
+    _compare(want, dp, got, subch, soft_frames=1)
+    for j, s in enumerate(subch):
+        assert got.msc[s.sub_ch_id].shape == (4 * 20 - 16, 24 * s.bit_rate)
+        assert np.array_equal(got.msc[s.sub_ch_id], rec.msc_truth[j][:got.msc[s.sub_ch_id].shape[0]]), s  # and they are what was sent
+
+
+def test_config5_batch_snr_cfo_timing_sweep(ctx, oracle):
+    """BASELINE configs[4] in small: a batch of independent recordings over SNR 3..30 dB, carrier offsets within +-5 kHz plus the
+    +-30 kHz corner, and arbitrary start offsets: positions and frequencies identical, payload identical from 10 dB up, CRC pass
+    counts close below."""
+    rng = np.random.default_rng(5)
+    snrs = [3.0, 6.0, 9.0, 12.0, 15.0, 18.0, 21.0, 24.0, 27.0, 30.0, 14.0, 20.0]
+    cfos = list(rng.uniform(-5000.0, 5000.0, 10)) + [30000.0, -30000.0]
+    recs = [synth.generate(9, seed=500 + i, snr_db=snrs[i], cfo_hz=float(cfos[i]), subch=[SC_3A], fmt=synth.FMT_U8,
+                           lead_samples=int(rng.integers(45000, 45000 + 196608))) for i in range(12)]
+    dp = api.DabProcessor(len(recs), input_format=synth.FMT_U8, ctx=ctx)
+    for i in range(len(recs)):
+        dp.set_audio_channel(i, [SC_3A])
+    dp.run([r.iq for r in recs])
+    for i, rec in enumerate(recs):
+        want = oracle.chain_run(oracle.to_cf32(rec.iq), synth.subch_table([SC_3A]), 1)
+        got = dp.result(i)
+        if snrs[i] >= 10.0:
+            assert got.n_frames == want.n_frames, (i, snrs[i], cfos[i])
+            assert [(a.sym0_pos, round(a.fbb_null)) for a in got.info] == [(b.sym0_pos, round(b.fbb_null)) for b in want.info], i
+            assert np.array_equal(got.fic_valid, want.fic_valid), i
+            assert np.array_equal(got.msc[3], want.msc[3]), i
+            assert got.n_good_fibs == want.n_good_fibs
+        else:
+            assert abs(got.n_frames - want.n_frames) <= 1, (i, snrs[i])
+            assert abs(got.n_good_fibs - want.n_good_fibs) <= max(3, want.n_good_fibs // 20), (i, got.n_good_fibs, want.n_good_fibs)
+        want.close()

@@ -1058,7 +1058,7 @@ struct dabstar_decoder
   DevBuf d_snap;        // snapshot of d_states
   DevBuf d_desc, d_work, d_cp, d_start, d_coarse, d_dipw, d_dipr, d_jobs, d_mscbits, d_etibits, d_etipacked;
   DevBuf d_tii_fft;   // null-symbol spectra of one TII event, fft order
-  HostBuf h_fib;
+  HostBuf h_fib, h_crc;
   std::vector<int16_t> h_soft_one;
   long long total_slots = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1655,6 +1655,8 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
       }
       const int n_tail = (int)ctl.size();
       if (n_tail == 0) break;
+      if (trace) fprintf(stderr, "[dabstar]     pass: %d tail frames\n", n_tail);
+      tr("  tail laid out");
       CK(need_upto(window_end));
       std::vector<FrameDesc> fdv((size_t)n_tail);
       for (int i = 0; i < n_tail; i++) fdv[i] = ctl[i].desc;
@@ -1700,6 +1702,7 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
         }
       }
       SYNC();
+      tr("  cp synced");
 
       // scalar recurrences (dab_processor.cpp:205-251), with the control state after every frame
       std::vector<CtlSnapshot> after((size_t)n_tail), before_tail(plans.size());
@@ -1730,6 +1733,7 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
       }
       for (int i = 0; i < n_tail; i++) fdv[i] = ctl[i].desc;
       UP(dec->d_desc.p, fdv.data(), sizeof(FrameDesc) * (size_t)n_tail);
+      tr("  recurrences done");
 
       // PRS peak of every tail frame
       uint8_t * d_first = dec->d_desc.as<uint8_t>() + sizeof(FrameDesc) * (size_t)n_tail;
@@ -1741,6 +1745,7 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
       std::vector<int> start((size_t)n_tail);
       CK(cudaMemcpyAsync(start.data(), dec->d_start.p, sizeof(int) * (size_t)n_tail, cudaMemcpyDeviceToHost, st));
       SYNC();
+      tr("  prs synced");
 
       bool any_open = false;
       for (size_t pi = 0; pi < plans.size(); pi++)
@@ -1855,14 +1860,25 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
 
     tr("heavy pass enqueued");
     // ---- read back the FIB CRC flags
+    // (one copy of the slot range this round touched: a copy per recording costs more in launch overhead than the bytes saved)
     std::vector<uint8_t> crc((size_t)n_desc * 12);
-    for (auto & pl : plans)
     {
-      Recording & R = dec->recs[pl.rec];
-      CK(cudaMemcpyAsync(crc.data() + (size_t)R.w_first_desc * 12, dec->d_crc.as<uint8_t>() + (size_t)ctl[R.w_first_desc].desc.slot * 12,
-                         (size_t)(int)pl.fr.size() * 12, cudaMemcpyDeviceToHost, st));
+      long long s_lo = (long long)1 << 62, s_hi = -1;
+      for (auto & pl : plans)
+      {
+        const long long s0 = ctl[dec->recs[pl.rec].w_first_desc].desc.slot;
+        s_lo = std::min(s_lo, s0);
+        s_hi = std::max(s_hi, s0 + (long long)pl.fr.size());
+      }
+      CK(dec->h_crc.reserve((size_t)(s_hi - s_lo) * 12));
+      CK(cudaMemcpyAsync(dec->h_crc.p, dec->d_crc.as<uint8_t>() + (size_t)s_lo * 12, (size_t)(s_hi - s_lo) * 12, cudaMemcpyDeviceToHost, st));
+      SYNC();
+      for (auto & pl : plans)
+      {
+        Recording & R = dec->recs[pl.rec];
+        memcpy(crc.data() + (size_t)R.w_first_desc * 12, dec->h_crc.as<uint8_t>() + (size_t)(ctl[R.w_first_desc].desc.slot - s_lo) * 12, pl.fr.size() * 12);
+      }
     }
-    SYNC();
 
     tr("heavy pass done");
     // ---- accept: the FIC success ratio must not have fallen below 30 % at a frame start (that frame needs the coarse AFC)
@@ -2196,12 +2212,28 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
   tr("rounds done");
   // FIB bits of all accepted frames
   CK(dec->h_fib.reserve((size_t)dec->total_slots * 3072));
-  for (int r = 0; r < n_rec; r++)
   {
-    Recording & R = dec->recs[r];
-    const int fib_slots = std::min(R.slot_cap, R.n_slots + ((R.eti_on && R.partial_syms > 3) ? 1 : 0)); // the generator also frames the CIFs of a cut last frame
-    if (fib_slots > 0)
-      CK(cudaMemcpyAsync(dec->h_fib.as<uint8_t>() + (size_t)R.slot_base * 3072, dec->d_fib.as<uint8_t>() + (size_t)R.slot_base * 3072, (size_t)fib_slots * 3072, cudaMemcpyDeviceToHost, st));
+    // the used slots of consecutive recordings go as one copy when the unused slots between them are few (a copy per
+    // recording costs about as much in launch overhead as 0.3 MB of transfer)
+    long long run_lo = -1, run_hi = -1;
+    auto flush = [&]() -> cudaError_t {
+      if (run_hi <= run_lo) return cudaSuccess;
+      return cudaMemcpyAsync(dec->h_fib.as<uint8_t>() + (size_t)run_lo * 3072, dec->d_fib.as<uint8_t>() + (size_t)run_lo * 3072, (size_t)(run_hi - run_lo) * 3072, cudaMemcpyDeviceToHost, st);
+    };
+    for (int r = 0; r < n_rec; r++)
+    {
+      Recording & R = dec->recs[r];
+      const int fib_slots = std::min(R.slot_cap, R.n_slots + ((R.eti_on && R.partial_syms > 3) ? 1 : 0)); // the generator also frames the CIFs of a cut last frame
+      if (fib_slots <= 0) continue;
+      if (run_hi >= 0 && R.slot_base - run_hi <= 96) run_hi = R.slot_base + fib_slots;
+      else
+      {
+        CK(flush());
+        run_lo = R.slot_base;
+        run_hi = R.slot_base + fib_slots;
+      }
+    }
+    CK(flush());
   }
   std::vector<uint8_t> eti_packed;
   if (!eti_refs.empty())

@@ -1287,8 +1287,16 @@ void ctl_finish_frame(Recording & r, float2 cp_raw, bool ran_coarse, int correct
   r.pos += (long long)n_syms * T_S;
   if (n_syms < 75) return; // recording ends inside this frame
   // the reference sums the derotated samples: raw sum times e^{-j 2 pi f / 1000}
-  const double ang = -2.0 * M_PI * (double)fc.desc.f_data / 1000.0;
-  const double cr = cos(ang), sr = sin(ang);
+  // (the integer frequency changes rarely: a small direct-mapped cache of the two trigonometric values, same expressions)
+  struct Rot { int f; bool set; double c, s; };
+  static thread_local Rot rot_cache[64] = {};
+  Rot & rc = rot_cache[(unsigned)fc.desc.f_data & 63u];
+  if (!rc.set || rc.f != fc.desc.f_data)
+  {
+    const double ang = -2.0 * M_PI * (double)fc.desc.f_data / 1000.0;
+    rc = Rot{ fc.desc.f_data, true, cos(ang), sin(ang) };
+  }
+  const double cr = rc.c, sr = rc.s;
   const float re = (float)((double)cp_raw.x * cr - (double)cp_raw.y * sr), im = (float)((double)cp_raw.x * sr + (double)cp_raw.y * cr);
   float ph = atan2f(im, re);
   const float lim = 20.0f * RAD_PER_DEG_F;
@@ -1707,10 +1715,9 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
       // scalar recurrences (dab_processor.cpp:205-251), with the control state after every frame
       std::vector<CtlSnapshot> after((size_t)n_tail), before_tail(plans.size());
       std::vector<uint8_t> first_flags((size_t)n_tail, 0);
-      for (size_t pi = 0; pi < plans.size(); pi++)
-      {
+      auto recur_plan = [&](size_t pi) {
         Plan & pl = plans[pi];
-        if (!pl.open) continue;
+        if (!pl.open) return;
         Recording & R = dec->recs[pl.rec];
         before_tail[pi] = take(R);
         const int s0 = pl.next_start >= 0 ? pl.next_start : T_G;
@@ -1730,7 +1737,8 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
           ctl[i] = fc;
           after[i] = take(R);
         }
-      }
+      };
+      for (size_t pi = 0; pi < plans.size(); pi++) recur_plan(pi);
       for (int i = 0; i < n_tail; i++) fdv[i] = ctl[i].desc;
       UP(dec->d_desc.p, fdv.data(), sizeof(FrameDesc) * (size_t)n_tail);
       tr("  recurrences done");

@@ -534,9 +534,11 @@ class DabProcessor:
         self.ctx.check(self.ctx.lib.dabstar_decoder_set_subchannels(self.h, recording, arr, len(subch)), "dabstar_decoder_set_subchannels")
         self.subch[recording] = list(subch)
 
-    def set_auto_config(self, recording: int, enable: bool = True):
-        """Take the recording's sub-channels and CIF counter from its own FIC (FIG 0/0, 0/1) instead of set_audio_channel."""
-        self.ctx.check(self.ctx.lib.dabstar_decoder_set_auto_config(self.h, recording, 1 if enable else 0), "dabstar_decoder_set_auto_config")
+    def set_auto_config(self, recording: int, enable: bool = True, tii_null_symbols: bool = False):
+        """Take the recording's sub-channels and CIF counter from its own FIC (FIG 0/0, 0/1) instead of set_audio_channel.
+        tii_null_symbols: also what DabProcessor does with a real FIB decoder behind get_cif_count(): null symbols whose CIF counter
+        has (count & 7) >= 4 are TII symbols and leave the null power alone (costs a second pass over the recording)."""
+        self.ctx.check(self.ctx.lib.dabstar_decoder_set_auto_config(self.h, recording, (2 if tii_null_symbols else 1) if enable else 0), "dabstar_decoder_set_auto_config")
         self.auto[recording] = bool(enable)
 
     def sub_channels(self, recording: int) -> list[SubChannel]:

@@ -1033,6 +1033,8 @@ struct Recording
   std::vector<FrameDesc> descs;      // descriptors of the accepted frames (the TII pass transforms their null symbols again)
   std::vector<int> sync_frames;      // n_slots at every successful time sync (mTiiDetector.reset(), dab_processor.cpp:150-152)
   bool auto_cfg = false;     // sub-channels and CIF counter from the recording's own FIG 0/0 and 0/1
+  bool tii_nulls = false;    // auto_cfg level 2: null symbols whose CIF counter has (count & 7) >= 4 do not update the null power
+  std::vector<uint8_t> tii_flags; // ... per frame, as known from the previous pass over this recording (see dabstar_decoder_run)
   std::vector<int> cif_hi_f, cif_lo_f; // auto_cfg: CIF counter as the FIB decoder holds it after each frame's FIC (-1: none yet)
   dabstar_ensemble_info ens{};
   long long cnt_good_fibs = 0, cnt_sync_ok = 0, cnt_sync_fail = 0, cnt_windows = 0, cnt_cut = 0, cnt_heavy = 0;
@@ -1058,6 +1060,7 @@ struct dabstar_decoder
   DevBuf d_snap;        // snapshot of d_states
   DevBuf d_desc, d_work, d_cp, d_start, d_coarse, d_dipw, d_dipr, d_jobs, d_mscbits, d_etibits, d_etipacked;
   DevBuf d_tii_fft;   // null-symbol spectra of one TII event, fft order
+  DevBuf d_tii_flags; // per descriptor: the frame's null symbol is a TII symbol
   HostBuf h_fib, h_crc;
   std::vector<int16_t> h_soft_one;
   long long total_slots = 0;
@@ -1148,6 +1151,7 @@ extern "C" int dabstar_decoder_set_auto_config(dabstar_decoder * dec, int record
 {
   if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
   dec->recs[recording].auto_cfg = enable != 0;
+  dec->recs[recording].tii_nulls = enable == 2;
   return 0;
 }
 extern "C" int dabstar_decoder_subchannels(const dabstar_decoder * dec, int recording, dabstar_subch * out, int cap)
@@ -1331,7 +1335,7 @@ void restore(Recording & r, const CtlSnapshot & s)
 }
 } // namespace
 
-extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * iq, const int64_t * n_samples, int mem)
+static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, const int64_t * n_samples, int mem)
 {
   if (!dec || !iq || !n_samples) return DABSTAR_E_INVALID;
   dabstar_ctx * ctx = dec->ctx;
@@ -1433,8 +1437,12 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
     const bool eti_on = R.eti_on, auto_cfg = R.auto_cfg;
     const int eti_hi = R.eti_cif_hi, eti_lo = R.eti_cif_lo;
     const Recording::TiiCfg tii_cfg = R.tii;
+    const bool tii_nulls = R.tii_nulls;
+    std::vector<uint8_t> tii_flags = std::move(R.tii_flags);
     R = Recording();
     R.tii = tii_cfg;
+    R.tii_nulls = tii_nulls;
+    R.tii_flags = std::move(tii_flags);
     R.auto_cfg = auto_cfg;
     if (auto_cfg) keep.clear(); // rediscovered from this run's FIC
     R.msc = std::move(keep);
@@ -1852,7 +1860,29 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
       UP(d_wk, wk.data(), sizeof(DemapWork) * wk.size());
       dec->span_begin(ST_DEMAP);
       CK(ctx->demap_ring.reserve(demap_ring_bytes((int)wk.size())));
-      CK(launch_demap(st, ctx->tab, d_wk, (int)wk.size(), d_fd, nullptr, dec->d_X.as<float2>(), dec->d_states.as<OfdmStateDev>(), dec->cfg.soft_bit_type,
+      // TII null symbols (self-configuration level 2): flags per descriptor, from the previous pass's CIF counters
+      const uint8_t * d_tii = nullptr;
+      {
+        std::vector<uint8_t> tii;
+        for (auto & pl : plans)
+        {
+          Recording & R = dec->recs[pl.rec];
+          if (R.tii_flags.empty()) continue;
+          if (tii.empty()) tii.assign((size_t)n_desc, 0);
+          for (int j = 0; j < (int)pl.fr.size(); j++)
+          {
+            const size_t f = (size_t)R.n_slots + (size_t)j;
+            if (f < R.tii_flags.size()) tii[(size_t)R.w_first_desc + (size_t)j] = R.tii_flags[f];
+          }
+        }
+        if (!tii.empty())
+        {
+          CK(dec->d_tii_flags.reserve(tii.size()));
+          UP(dec->d_tii_flags.p, tii.data(), tii.size());
+          d_tii = dec->d_tii_flags.as<uint8_t>();
+        }
+      }
+      CK(launch_demap(st, ctx->tab, d_wk, (int)wk.size(), d_fd, d_tii, dec->d_X.as<float2>(), dec->d_states.as<OfdmStateDev>(), dec->cfg.soft_bit_type,
                       dec->d_soft.as<int16_t>(), ctx->demap_ring.as<unsigned long long>(), &ctx->launches));
       dec->span_end();
     }
@@ -2303,6 +2333,44 @@ extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * i
 }
 
 // ------------------------------------------------------------------------------------------------ results
+// DabProcessor::run() for every recording. With self-configuration level 2 the demapper has to know, at the null symbol of
+// frame f, the CIF counter that frame's own FIC carried (dab_processor.cpp:273-285), which the batched path only learns after
+// the window has been demapped. The run therefore speculates at the granularity of a pass: the first pass treats every null
+// symbol as a plain one, the CIF counters it decodes give the flags, and the recordings are decoded again with them until the
+// flags a pass used equal the flags it produced (one extra pass unless a FIG 0/0 is lost exactly where it matters).
+extern "C" int dabstar_decoder_run(dabstar_decoder * dec, const void * const * iq, const int64_t * n_samples, int mem)
+{
+  if (!dec || !iq || !n_samples) return DABSTAR_E_INVALID;
+  for (auto & R : dec->recs) R.tii_flags.clear();
+  int rc = decoder_run_pass(dec, iq, n_samples, mem);
+  double total_ms = dec->last_ms;
+  for (int pass = 1; rc == 0 && pass <= 3; pass++)
+  {
+    bool again = false;
+    for (auto & R : dec->recs)
+    {
+      if (!R.auto_cfg || !R.tii_nulls || R.n_slots == 0) continue;
+      std::vector<uint8_t> flags((size_t)R.n_slots, 0);
+      for (int f = 0; f < R.n_slots; f++)
+        if (f < (int)R.cif_hi_f.size() && R.cif_hi_f[f] >= 0) flags[f] = (((R.cif_hi_f[f] * 250 + R.cif_lo_f[f]) & 7) >= 4) ? 1 : 0;
+      bool any = false;
+      for (uint8_t v : flags) any = any || v;
+      std::vector<uint8_t> used = R.tii_flags;
+      used.resize(flags.size(), 0);
+      if (any && used != flags) again = true;
+      R.tii_flags = std::move(flags);
+    }
+    if (!again) break;
+    // the recordings are resident on the device after the first pass
+    std::vector<const void *> dptr(dec->recs.size());
+    for (size_t r = 0; r < dec->recs.size(); r++) dptr[r] = dec->recs[r].d_iq;
+    rc = decoder_run_pass(dec, dptr.data(), n_samples, DABSTAR_MEM_DEVICE);
+    total_ms += dec->last_ms;
+  }
+  dec->last_ms = total_ms;
+  return rc;
+}
+
 extern "C" int dabstar_decoder_n_frames(const dabstar_decoder * dec, int recording)
 {
   if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;

@@ -340,7 +340,11 @@ public:
     run(ptrs, nSamples);
   }
   // Sub-channels and CIF counter from the recording's own FIG 0/0 and 0/1 instead of set_audio_channel.
-  void set_auto_config(int recording, bool on = true) { mC.check(dabstar_decoder_set_auto_config(mDec, recording, on ? 1 : 0), "dabstar_decoder_set_auto_config"); }
+  // tiiNullSymbols: null symbols whose CIF counter has (count & 7) >= 4 leave the null power alone, as with a real FIB decoder (second pass)
+  void set_auto_config(int recording, bool on = true, bool tiiNullSymbols = false)
+  {
+    mC.check(dabstar_decoder_set_auto_config(mDec, recording, on ? (tiiNullSymbols ? 2 : 1) : 0), "dabstar_decoder_set_auto_config");
+  }
   std::vector<dabstar_subch> sub_channels(int recording) const
   {
     std::vector<dabstar_subch> v((size_t)std::max(0, dabstar_decoder_subchannels(mDec, recording, nullptr, 0)));

@@ -342,7 +342,12 @@ int64_t dabstar_decoder_msc_copy(const dabstar_decoder * dec, int recording, int
 /* Self-configuration: the recording's sub-channels and CIF counter are taken from its own FIC (dabstar_fib_parser on the
  * CRC-good FIBs in stream order) instead of dabstar_decoder_set_subchannels. Every sub-channel FIG 0/1 describes gets a
  * Backend from the frame after its first description (in the reference that moment is a GUI action); with ETI enabled the
- * generator frames the sub-channel list and FIG 0/0's CIF counter as it would sample them at symbol 4 of each frame. */
+ * generator frames the sub-channel list and FIG 0/0's CIF counter as it would sample them at symbol 4 of each frame.
+ * enable = 2 adds what DabProcessor does with a real FIB decoder behind get_cif_count() (main/dab_processor.cpp:273-285): the
+ * null symbol after a frame whose CIF counter has (count & 7) >= 4 is a TII symbol and does not update the null power
+ * (OfdmDecoder::store_null_symbol_with_tii). The counter of frame f comes from that frame's own FIC, which the batched path
+ * only knows after the window has been demapped, so the run speculates per pass: first with plain null symbols, then again
+ * with the flags its own CIF counters give, until the flags used equal the flags produced (normally one extra pass). */
 int     dabstar_decoder_set_auto_config(dabstar_decoder * dec, int recording, int enable);
 /* sub-channels of the last run (as set, or as discovered); returns the count */
 int     dabstar_decoder_subchannels(const dabstar_decoder * dec, int recording, dabstar_subch * out, int cap);
@@ -355,9 +360,6 @@ int     dabstar_decoder_ensemble(const dabstar_decoder * dec, int recording, dab
 int     dabstar_decoder_enable_eti(dabstar_decoder * dec, int recording, int enable, int cif_count_hi, int cif_count_lo);
 int64_t dabstar_decoder_eti_size(const dabstar_decoder * dec, int recording);
 int64_t dabstar_decoder_eti_copy(const dabstar_decoder * dec, int recording, uint8_t * out, int64_t cap);
-/* out[0] good FIBs, [1] time-sync established count, [2] time-sync failures, [3] samples consumed,
- * [4] speculation windows run, [5] windows cut short by verification, [6] frames decoded,
- * [7] frames sent through the FFT/demap/FIC pass (exceeds [6] by replayed and partial frames) */
 /* TII (DabProcessor::set_tii_processing / set_tii_threshold / set_tii_collisions / set_tii_sub_id, main/dab_processor.h; the
  * null-symbol handling of dab_processor.cpp:273-300) for a SELF-CONFIGURED recording (dabstar_decoder_set_auto_config): the
  * null symbol after a frame is a TII symbol when the CIF counter taken from the recording's own FIG 0/0 has (count & 7) >= 4;
@@ -370,6 +372,9 @@ int     dabstar_decoder_tii_results(const dabstar_decoder * dec, int recording, 
 /* dabstar_ofdm_state_quality for a recording's decoder at the end of the last run (the reference shows these figures
  * every 5 frames; mMeanSigmaSqFreqCorr is replayed from the per-frame cyclic-prefix phases). */
 int     dabstar_decoder_quality(const dabstar_decoder * dec, int recording, float out[6]);
+/* out[0] good FIBs, [1] time-sync established count, [2] time-sync failures, [3] samples consumed,
+ * [4] speculation windows run, [5] windows cut short by verification, [6] frames decoded,
+ * [7] frames sent through the FFT/demap/FIC pass (exceeds [6] by replayed and partial frames) */
 int     dabstar_decoder_counters(const dabstar_decoder * dec, int recording, int64_t out[8]);
 /* Device time of the last dabstar_decoder_run in milliseconds (CUDA events on the context's stream). */
 double  dabstar_decoder_last_ms(const dabstar_decoder * dec);

@@ -997,6 +997,34 @@ int dabo_phaseref_estimate_offset(void * h, const float * fft)
  * Whole chain: SampleReader (ofdm/sample_reader.cpp:44-50,102-297), TimeSyncer (ofdm/timesyncer.cpp:40-90),
  * DabProcessor (main/dab_processor.cpp:110-442), MscHandler (backend/msc_handler.cpp:148-168).
  * ---------------------------------------------------------------------------------------------- */
+/* The part of FibDecoder::process_FIB that get_cif_count() depends on (fib_decoder.cpp:59-106 FIG walk,
+ * fib_decoder_fig0.cpp:89-113): the CIF counter of the last FIG 0/0 among the CRC-good FIBs of one frame's FIC. */
+static void scan_cif_count(const uint8_t * fib_bits, int * cif_hi, int * cif_lo)
+{
+  for (int k = 0; k < 12; k++)
+  {
+    const uint8_t * fib = fib_bits + (k / 3) * 768 + (k % 3) * 256;
+    if (!dabo_check_crc_bits(fib, 256)) continue;
+    int done = 0;
+    while (done < 30)
+    {
+      const uint8_t * d = fib + 8 * done;
+      unsigned type = 0, len = 0, ext = 0, hi = 0, lo = 0;
+      for (int b = 0; b < 3; b++) type = (type << 1) | d[b];
+      for (int b = 3; b < 8; b++) len = (len << 1) | d[b];
+      if ((type == 7 && len == 31) || done + (int)len + 1 > 30) break;
+      for (int b = 11; b < 16; b++) ext = (ext << 1) | d[b];
+      if (type == 0 && ext == 0 && len >= 5)
+      {
+        for (int b = 35; b < 40; b++) hi = (hi << 1) | d[b];
+        for (int b = 40; b < 48; b++) lo = (lo << 1) | d[b];
+        *cif_hi = (int)hi; *cif_lo = (int)lo;
+      }
+      done += (int)len + 1;
+    }
+  }
+}
+
 typedef struct
 {
   dabo_frame_info info;
@@ -1034,6 +1062,7 @@ typedef struct
   frame_rec * frames;
   int n_frames, cap_frames;
   int dip_found, no_dip;
+  int cif_hi, cif_lo;         /* cfg.track_cif: what a real FIB decoder would hold (0, 0 until the first FIG 0/0) */
   double seconds;
 } chain_t;
 
@@ -1400,7 +1429,11 @@ void * dabo_chain_run(const float * iq, int64_t n_samples, const dabo_chain_cfg 
       memcpy(fft_in, &buf[T_G], sizeof(cf32) * T_U);
       fft2048(fft_in, fft_out, -1);
       if (f->fft) memcpy(&f->fft[(size_t)76 * T_U * 2], fft_out, sizeof(cf32) * T_U);
-      dabo_ofdm_store_null_symbol_without_tii(c->ofdm, (const float *)fft_out); /* cif_count == 0: never a TII null */
+      /* dab_processor.cpp:273-300: TII null symbols ((cif count & 7) >= 4) do not update the null power; without a FIB decoder
+       * behind get_cif_count() (the harness' default stub) the count is 0 and every null symbol is a plain one */
+      if (cfg->track_cif) scan_cif_count(c->fic->bits, &c->cif_hi, &c->cif_lo);
+      if (!(cfg->track_cif && (((c->cif_hi * 250 + c->cif_lo) & 7) >= 4)))
+        dabo_ofdm_store_null_symbol_without_tii(c->ofdm, (const float *)fft_out);
       if (correction == 0)
       {
         const float ce = clampf_sym((float)FS * ((float)sample_count / (float)T_FRAME - 1.0f), 307.2f);

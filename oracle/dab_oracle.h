@@ -111,6 +111,8 @@ typedef struct
   const char * eti_path;     /* NULL = ETI generator off; else the ETI-NI stream is also written to this file (as dabref does) */
   int   eti_cif_hi, eti_cif_lo; /* IFibDecoder::get_cif_count(hi, lo) as sampled at symbol 4 of every frame (the dabref stub: 0, 0);
                                    eti_cif_hi < 0: the counter of the last FIG 0/0 received, as a real FIB decoder reports it */
+  int   track_cif;           /* 1: get_cif_count() follows the recording's own FIG 0/0 (a real FIB decoder), so the null symbols with
+                                (count & 7) >= 4 are TII symbols and do not update the null power (dab_processor.cpp:273-285); 0: the count stays 0 */
 } dabo_chain_cfg;
 
 typedef struct

@@ -65,6 +65,8 @@ typedef struct
   int   n_subch;
   const int32_t * subch;     /* n_subch x 7: subChId,startCU,sizeCU,shortForm,protLevel,bitRate,startFrame */
   const char * eti_path;     /* NULL = ETI generator off */
+  int   eti_cif_hi, eti_cif_lo; /* (layout shared with the restatement's configuration; not used here: get_cif_count(hi, lo) gives 0, 0) */
+  int   track_cif;           /* 1: the stub FIB decoder's get_cif_count() follows the FIG 0/0 of the FIBs FicDecoder hands it; 0: always 0 */
 } dabref_chain_cfg;
 
 typedef struct

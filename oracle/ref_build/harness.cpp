@@ -347,6 +347,7 @@ struct ChainRun : Hooks
   int fftInFrame = 0;      // 0 = next mFftPlan execution is symbol 0
   int framesStarted = 0;
   float lastSnr = 0, lastMer = 0;
+  int cifCount = 0;
   double seconds = 0;
 
   void start_backends_for_frame(int frame)
@@ -423,10 +424,33 @@ struct ChainRun : Hooks
     for (int i = 0; i < 4; i++) f.info.fic_valid[i] = v[i] ? 1 : 0;
     framesStarted++;
     start_backends_for_frame(framesStarted); // Backends that shall see their first CIF in the next frame
-    return 0; // every null symbol is treated as non-TII
+    return cfg.track_cif ? cifCount : 0; // default: every null symbol is treated as non-TII
   }
 
-  void on_good_fib(const u8 *, int) override { goodFibs++; }
+  // process_FIB of the stub FIB decoder: count, and (track_cif) follow FIG 0/0's CIF counter the way FibDecoder does
+  // (fib_decoder.cpp:59-106 FIG walk, fib_decoder_fig0.cpp:89-113), so that DabProcessor's own TII null-symbol handling runs
+  void on_good_fib(const u8 * fib, int) override
+  {
+    goodFibs++;
+    if (!cfg.track_cif) return;
+    int done = 0;
+    while (done < 30)
+    {
+      const u8 * d = fib + 8 * done;
+      unsigned type = 0, len = 0, ext = 0, hi = 0, lo = 0;
+      for (int b = 0; b < 3; b++) type = (type << 1) | (d[b] & 1u);
+      for (int b = 3; b < 8; b++) len = (len << 1) | (d[b] & 1u);
+      if ((type == 7 && len == 31) || done + (int)len + 1 > 30) break;
+      for (int b = 11; b < 16; b++) ext = (ext << 1) | (d[b] & 1u);
+      if (type == 0 && ext == 0 && len >= 5)
+      {
+        for (int b = 35; b < 40; b++) hi = (hi << 1) | (d[b] & 1u);
+        for (int b = 40; b < 48; b++) lo = (lo << 1) | (d[b] & 1u);
+        cifCount = (int)(hi * 250 + lo);
+      }
+      done += (int)len + 1;
+    }
+  }
   void on_msc_frame(int id, const u8 * d, int n) override { auto & v = msc[id]; v.insert(v.end(), d, d + n); }
   void on_lcd(float snr, float mer) override { lastSnr = snr; lastMer = mer; }
 };

@@ -22,7 +22,8 @@ class ChainCfg(ctypes.Structure):
     _fields_ = [("soft_bit_type", ctypes.c_int), ("threshold", ctypes.c_float), ("strongest_peak", ctypes.c_int),
                 ("scan_mode", ctypes.c_int), ("tap_soft_bits", ctypes.c_int), ("tap_fft", ctypes.c_int),
                 ("n_subch", ctypes.c_int), ("subch", c_p), ("eti_path", ctypes.c_char_p),
-                ("eti_cif_hi", ctypes.c_int), ("eti_cif_lo", ctypes.c_int)]  # the last two: restatement only (the dabref stub returns 0, 0)
+                ("eti_cif_hi", ctypes.c_int), ("eti_cif_lo", ctypes.c_int),  # these two: restatement only (the dabref stub returns 0, 0)
+                ("track_cif", ctypes.c_int)]
 
 
 class FrameInfo(ctypes.Structure):
@@ -290,8 +291,9 @@ class Oracle:
     # ---- whole chain
     def chain_run(self, iq: np.ndarray, subch_table: np.ndarray | None = None, n_subch: int = 0, soft_bit_type: int = 0,
                   threshold: float = 3.0, strongest_peak: int = 0, scan_mode: int = 0, tap_soft: bool = False, tap_fft: bool = False,
-                  eti: bool = False, eti_cif: tuple[int, int] = (0, 0)):
-        """eti: also run the reference's EtiGenerator (start_eti_generator before run); the ETI-NI stream is in result.eti."""
+                  eti: bool = False, eti_cif: tuple[int, int] = (0, 0), track_cif: bool = False):
+        """eti: also run the reference's EtiGenerator (start_eti_generator before run); the ETI-NI stream is in result.eti.
+        track_cif: get_cif_count() follows the recording's FIG 0/0, so DabProcessor treats every second null symbol as a TII symbol."""
         iq = np.ascontiguousarray(iq, np.complex64)
         tab = np.ascontiguousarray(subch_table if subch_table is not None else np.zeros((1, 7)), np.int32)
         eti_path = None
@@ -299,7 +301,7 @@ class Oracle:
             fd, eti_path = tempfile.mkstemp(suffix=".eti")
             os.close(fd)
         cfg = ChainCfg(soft_bit_type, threshold, strongest_peak, scan_mode, int(tap_soft), int(tap_fft), n_subch, tab.ctypes.data,
-                       eti_path.encode() if eti_path else None, int(eti_cif[0]), int(eti_cif[1]))
+                       eti_path.encode() if eti_path else None, int(eti_cif[0]), int(eti_cif[1]), int(track_cif))
         h = c_p(self.f("chain_run")(_ptr(iq), ctypes.c_int64(iq.size), ctypes.byref(cfg)))
         res = ChainResult(self, h, tab[:n_subch].copy())
         if eti_path:

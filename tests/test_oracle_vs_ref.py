@@ -135,3 +135,21 @@ def test_tii_tables_are_derived_correctly(oracle):
     oracle.f("tii_tables")(t.h, pat.ctypes.data_as(ctypes.c_void_p), pc.ctypes.data_as(ctypes.c_void_p))
     assert np.array_equal(pat, g["main_id_pattern"]) and np.array_equal(pc, g["phase_corr"])
     assert list(pat) == helpers.TII_PATTERNS
+
+
+def test_whole_chain_with_tii_null_symbols(oracle, refo):
+    """get_cif_count() following the recording's own FIG 0/0 (track_cif): the reference's DabProcessor then treats the null symbol
+    after every second frame as a TII symbol and leaves the null power alone (dab_processor.cpp:273-285). Restatement = reference,
+    and the result differs from the run whose FIB decoder holds no counter."""
+    sc = [synth.SubChannel(3, 100, 54, 0, 2, 72)]
+    rec = synth.generate(10, seed=21, snr_db=14.0, subch=sc, fmt=synth.FMT_CF32, fig_mode=1, tii=(12, 5))
+    a = oracle.chain_run(rec.iq, synth.subch_table(sc), 1, tap_soft=True, track_cif=True)
+    b = refo.chain_run(rec.iq, synth.subch_table(sc), 1, tap_soft=True, track_cif=True)
+    plain = oracle.chain_run(rec.iq, synth.subch_table(sc), 1, tap_soft=True)
+    assert a.n_frames == b.n_frames == 10 and np.array_equal(a.fic_valid, b.fic_valid) and np.array_equal(a.msc[3], b.msc[3])
+    differs = 0
+    for f in range(a.n_frames):
+        d = np.abs(a.soft_bits(f).astype(np.int32) - b.soft_bits(f).astype(np.int32))
+        assert (d > 1).mean() <= 1e-4
+        differs += int((a.soft_bits(f) != plain.soft_bits(f)).sum())
+    assert differs > 1000  # the TII energy in every second null symbol does change the soft-bit weights

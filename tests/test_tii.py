@@ -123,3 +123,30 @@ def test_decoder_tii_from_own_cif_counter(ctx, oracle):
     dp.set_tii_processing(2, False)
     dp.run([r.iq for r in recs])
     assert dp.tii_events(0) == []
+
+
+def test_tii_null_symbols_leave_the_null_power_alone(ctx, oracle):
+    """Self-configuration level 2: the demapper skips the null-power update on the null symbols the recording's own CIF counter
+    marks as TII symbols, like DabProcessor with a real FIB decoder (dab_processor.cpp:273-285). Equal to the CPU chain whose
+    get_cif_count() follows FIG 0/0 (itself pinned against the reference's DabProcessor), different from level 1."""
+    from dabstar_b200 import synth
+    sc = [synth.SubChannel(3, 100, 54, 0, 2, 72)]
+    recs = [synth.generate(10, seed=21 + i, snr_db=14.0, subch=sc, fmt=synth.FMT_U8, fig_mode=1, tii=(12, 5)) for i in range(2)]
+    dp = api.DabProcessor(2, input_format=api.FMT_U8, ctx=ctx)
+    dp.set_auto_config(0, True, tii_null_symbols=True)
+    dp.set_auto_config(1, True)                       # level 1 beside it: plain null symbols
+    dp.run([r.iq for r in recs])
+    for r, track in ((0, True), (1, False)):
+        want = oracle.chain_run(oracle.to_cf32(recs[r].iq), synth.subch_table(sc), 1, tap_soft=True, track_cif=track)
+        got = dp.result(r)
+        assert got.n_frames == want.n_frames == 10 and np.array_equal(got.fic_valid, want.fic_valid)
+        for f in range(got.n_frames):
+            d = np.abs(dp.soft_bits(r, f).astype(np.int32) - want.soft_bits(f).astype(np.int32))
+            assert (d > 1).mean() <= 1e-4, (r, f, d.max(), (d > 1).mean())
+        n = min(got.msc[3].shape[0], want.msc[3].shape[0])  # the self-configured Backend starts a frame later than the configured one
+        assert n >= 16 and np.array_equal(got.msc[3][-n:], want.msc[3][-n:])
+        want.close()
+    # and the two levels do differ on the same recording
+    plain = oracle.chain_run(oracle.to_cf32(recs[0].iq), synth.subch_table(sc), 1, tap_soft=True)
+    assert sum(int((dp.soft_bits(0, f) != plain.soft_bits(f)).sum()) for f in range(3, 10)) > 1000
+    plain.close()

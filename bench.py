@@ -349,7 +349,7 @@ def native_arm(args, rank, local_rank, world):
                    "l2": "inputs (3.9 GB) and intermediates far exceed the 126 MB L2", "window": args.window,
                    "fib_crc_pass": good_fibs / max(1.0, 12.0 * frames_per_step),
                    "windows_per_recording": float(cnt[4]) / R, "frames_through_heavy_pass": int(cnt[7]), "x_real_time": value / world / (2048000 / T_F)},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(R * n_samples * 2), "d2h_bytes_per_step": int(frames_per_step * 3072),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(R * n_samples * 2), "d2h_bytes_per_step": int(frames_per_step * 384),
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "stages": stages, "viterbi_sweep": vit_sweep, "cpu_baseline": cpu,
     }

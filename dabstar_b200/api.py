@@ -631,6 +631,13 @@ class DabProcessor:
             out.append((fr.value, [(r.main_id, r.sub_id, r.strength, r.phase_deg, r.non_etsi) for r in buf[:min(k, cap)]]))
         return out
 
+    def fib_packed(self, recording: int) -> np.ndarray:
+        """The recording's FIBs packed 8 bits per byte (uint8[n_frames, 12, 32]), as they come back from the device."""
+        nf = self.ctx.check(self.ctx.lib.dabstar_decoder_n_frames(self.h, recording), "dabstar_decoder_n_frames")
+        out = np.zeros((nf, 12, 32), np.uint8)
+        self.ctx.check(self.ctx.lib.dabstar_decoder_fib_packed(self.h, recording, _ptr(out)), "dabstar_decoder_fib_packed")
+        return out
+
     def quality(self, recording: int) -> dict:
         """SLcdData figures (MER, SNR, ...) of a recording's OFDM decoder at the end of the last run()."""
         out = np.zeros(6, np.float32)

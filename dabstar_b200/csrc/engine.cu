@@ -1060,8 +1060,9 @@ struct dabstar_decoder
   DevBuf d_snap;        // snapshot of d_states
   DevBuf d_desc, d_work, d_cp, d_start, d_coarse, d_dipw, d_dipr, d_jobs, d_mscbits, d_etibits, d_etipacked;
   DevBuf d_tii_fft;   // null-symbol spectra of one TII event, fft order
+  DevBuf d_fibp;      // FIB bits packed 8 per byte for the read-back (384 bytes per frame)
   DevBuf d_tii_flags; // per descriptor: the frame's null symbol is a TII symbol
-  HostBuf h_fib, h_crc;
+  HostBuf h_fib, h_crc, h_fibp; // h_fib: FIB bits of the self-configuration pass (one per byte); h_fibp: all FIBs of the run, packed 8 bits per byte
   std::vector<int16_t> h_soft_one;
   long long total_slots = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -2249,29 +2250,15 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
   }
   tr("rounds done");
   // FIB bits of all accepted frames
-  CK(dec->h_fib.reserve((size_t)dec->total_slots * 3072));
+  // The decoded FIBs leave the device packed 8 bits per byte (32 bytes per FIB, the reference's FIC dump format,
+  // fic_decoder.cpp:291-308): 3.8 MB instead of 30.6 MB per 10 000 frames; dabstar_decoder_fib_bits unpacks on request.
+  if (dec->total_slots > 0)
   {
-    // the used slots of consecutive recordings go as one copy when the unused slots between them are few (a copy per
-    // recording costs about as much in launch overhead as 0.3 MB of transfer)
-    long long run_lo = -1, run_hi = -1;
-    auto flush = [&]() -> cudaError_t {
-      if (run_hi <= run_lo) return cudaSuccess;
-      return cudaMemcpyAsync(dec->h_fib.as<uint8_t>() + (size_t)run_lo * 3072, dec->d_fib.as<uint8_t>() + (size_t)run_lo * 3072, (size_t)(run_hi - run_lo) * 3072, cudaMemcpyDeviceToHost, st);
-    };
-    for (int r = 0; r < n_rec; r++)
-    {
-      Recording & R = dec->recs[r];
-      const int fib_slots = std::min(R.slot_cap, R.n_slots + ((R.eti_on && R.partial_syms > 3) ? 1 : 0)); // the generator also frames the CIFs of a cut last frame
-      if (fib_slots <= 0) continue;
-      if (run_hi >= 0 && R.slot_base - run_hi <= 96) run_hi = R.slot_base + fib_slots;
-      else
-      {
-        CK(flush());
-        run_lo = R.slot_base;
-        run_hi = R.slot_base + fib_slots;
-      }
-    }
-    CK(flush());
+    const long long n_bytes = (long long)dec->total_slots * 384;
+    CK(dec->d_fibp.reserve((size_t)n_bytes));
+    CK(dec->h_fibp.reserve((size_t)n_bytes));
+    CK(launch_pack_bits(st, dec->d_fib.as<uint8_t>(), dec->d_fibp.as<uint8_t>(), n_bytes, &ctx->launches));
+    CK(cudaMemcpyAsync(dec->h_fibp.p, dec->d_fibp.p, (size_t)n_bytes, cudaMemcpyDeviceToHost, st));
   }
   std::vector<uint8_t> eti_packed;
   if (!eti_refs.empty())
@@ -2302,13 +2289,8 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       int o = eti_header(f, own ? R.cif_hi_f[fr] : R.eti_cif_hi, own ? R.cif_lo_f[fr] : R.eti_cif_lo, n & 3, streams);
       const int base = o;
       // fibVector: the four FICs of the frame as the FIC decoder left them at symbol 4, whether their CRCs passed or not
-      const uint8_t * fib = dec->h_fib.as<uint8_t>() + ((size_t)R.slot_base + 4 + (size_t)(n >> 2)) * 3072 + (size_t)(n & 3) * 768;
-      for (int j = 0; j < 96; j++)
-      {
-        unsigned v = 0;
-        for (int k = 0; k < 8; k++) v = (v << 1) | (fib[8 * j + k] & 1u);
-        f[o++] = (uint8_t)v;
-      }
+      memcpy(f + o, dec->h_fibp.as<uint8_t>() + ((size_t)R.slot_base + 4 + (size_t)(n >> 2)) * 384 + (size_t)(n & 3) * 96, 96);
+      o += 96;
       for (const MscOut & m : streams)
       {
         const int nb = 3 * m.sc.bit_rate;
@@ -2388,8 +2370,25 @@ extern "C" int dabstar_decoder_fib_bits(const dabstar_decoder * dec, int recordi
 {
   if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
   const Recording & R = dec->recs[recording];
-  if (bits && R.n_slots > 0) memcpy(bits, dec->h_fib.as<uint8_t>() + (size_t)R.slot_base * 3072, (size_t)R.n_slots * 3072);
+  if (bits && R.n_slots > 0)
+  {
+    const uint8_t * p = dec->h_fibp.as<uint8_t>() + (size_t)R.slot_base * 384;
+    const size_t n = (size_t)R.n_slots * 384;
+    for (size_t i = 0; i < n; i++)
+    {
+      const unsigned v = p[i];
+      uint8_t * o = bits + 8 * i;
+      o[0] = (uint8_t)(v >> 7); o[1] = (v >> 6) & 1; o[2] = (v >> 5) & 1; o[3] = (v >> 4) & 1; o[4] = (v >> 3) & 1; o[5] = (v >> 2) & 1; o[6] = (v >> 1) & 1; o[7] = v & 1;
+    }
+  }
   if (valid) for (int i = 0; i < R.n_slots; i++) memcpy(valid + 4 * i, R.frames[i].fic_valid, 4);
+  return R.n_slots;
+}
+extern "C" int dabstar_decoder_fib_packed(const dabstar_decoder * dec, int recording, uint8_t * packed)
+{
+  if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  const Recording & R = dec->recs[recording];
+  if (packed && R.n_slots > 0) memcpy(packed, dec->h_fibp.as<uint8_t>() + (size_t)R.slot_base * 384, (size_t)R.n_slots * 384);
   return R.n_slots;
 }
 extern "C" int dabstar_decoder_soft_bits(const dabstar_decoder * dec, int recording, int frame, int16_t * out)

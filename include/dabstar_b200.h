@@ -335,6 +335,9 @@ int     dabstar_decoder_n_frames(const dabstar_decoder * dec, int recording);
 int     dabstar_decoder_frame_info(const dabstar_decoder * dec, int recording, dabstar_frame_info * out, int cap);
 /* FicDecoder::get_fib_bits per frame: n_frames x 3072 bytes, valid: n_frames x 4 */
 int     dabstar_decoder_fib_bits(const dabstar_decoder * dec, int recording, uint8_t * bits, uint8_t * valid);
+/* The same FIBs packed 8 bits per byte, first bit most significant: n_frames x 12 x 32 bytes, the reference's FIC dump
+ * format (fic_decoder.cpp:291-308). This is how they are read back from the device; dabstar_decoder_fib_bits unpacks. */
+int     dabstar_decoder_fib_packed(const dabstar_decoder * dec, int recording, uint8_t * packed);
 int     dabstar_decoder_soft_bits(const dabstar_decoder * dec, int recording, int frame, int16_t * out);
 int64_t dabstar_decoder_msc_size(const dabstar_decoder * dec, int recording, int sub_ch_id);
 /* FrameProcessor::add_to_frame payloads (backend/frame_processor.h:43), concatenated, one bit per byte */

@@ -51,6 +51,7 @@ def test_config1_one_dabplus_subchannel(ctx, oracle, fmt, viterbi_path):
     _compare(want, dp, got, [SC_3A])
     # payload is what was transmitted
     assert np.array_equal(got.fib_bits, rec.fib_truth[:got.n_frames])
+    assert np.array_equal(dp.fib_packed(0).reshape(got.n_frames, 384), np.packbits(got.fib_bits, axis=1))  # the read-back format
     assert np.array_equal(got.msc[3], rec.msc_truth[0][:got.msc[3].shape[0]])
 
 

@@ -249,12 +249,14 @@ __global__ void __launch_bounds__(FFT_THREADS, 5) k_fft_frames(const FrameDesc *
       }
       else load_symbol<FMT>(v, cur.iq, cur.n_total, cur.start, cur.f, cur.ph, step, tid);
       fft2048_to_smem(v, tw, smem, tid);
-      float2 * out = X + cur.out;
+      // frequency de-interleave + the demapper's layout: carriers 2p, 2p + 1 as (re, re, im, im), one 16-byte store per pair
+      float4 * out = reinterpret_cast<float4 *>(X + cur.out);
 #pragma unroll
-      for (int i = 0; i < K_CARR / FFT_THREADS; i++)
+      for (int i = 0; i < K_CARR / 2 / FFT_THREADS; i++)
       {
-        const int k = tid + FFT_THREADS * i;
-        out[k] = smem[bins[k]];
+        const int p = tid + FFT_THREADS * i;
+        const float2 a = smem[bins[2 * p]], b = smem[bins[2 * p + 1]];
+        out[p] = make_float4(a.x, b.x, a.y, b.y);
       }
     }
     __syncthreads(); // smem and the stage buffer of this symbol are free again
@@ -321,12 +323,17 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) k_fft_null(const FrameDesc * _
   }
 }
 
-// Natural-order spectra [frame][77][2048] -> nominal-carrier order [frame][77][1536] (stage tap for the demapper).
+// Natural-order spectra [frame][77][2048] -> nominal-carrier order [frame][77][1536] in the demapper's pair layout
+// (re 2p, re 2p+1, im 2p, im 2p+1) (stage tap for the demapper).
 __global__ void k_reorder_frames(const float2 * __restrict__ fft_nat, int n_rows, const int16_t * __restrict__ bin_of_k, float2 * __restrict__ X)
 {
   const int row = blockIdx.x;
   if (row >= n_rows) return;
-  for (int k = threadIdx.x; k < K_CARR; k += blockDim.x) X[(size_t)row * K_CARR + k] = fft_nat[(size_t)row * T_U + bin_of_k[k]];
+  for (int p = threadIdx.x; p < K_CARR / 2; p += blockDim.x)
+  {
+    const float2 a = fft_nat[(size_t)row * T_U + bin_of_k[2 * p]], b = fft_nat[(size_t)row * T_U + bin_of_k[2 * p + 1]];
+    reinterpret_cast<float4 *>(X + (size_t)row * K_CARR)[p] = make_float4(a.x, b.x, a.y, b.y); // the demapper's pair layout
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ block reductions
@@ -629,455 +636,29 @@ __global__ void __launch_bounds__(256) k_cp_corr(const FrameDesc * __restrict__ 
   }
 }
 
-// ------------------------------------------------------------------------------------------------ DQPSK demapper (D1-D3)
-// One CTA per recording walks its frames and symbols in order (the per-carrier IIR chains are sequential in time but
-// independent across carriers). Thread t owns nominal carriers 2t and 2t+1 and keeps their state in registers.
-constexpr int DEMAP_THREADS = K_CARR / 2;
-
-__device__ __forceinline__ float first_quadrant(float ph)
-{
-  if (ph < 0.0f) ph += PI_F;            // common/glob_defs.h:173-182; fmod(x, pi/2) on [0, pi] is exact subtraction
-  if (ph >= PI_2_F) ph -= PI_2_F;
-  if (ph >= PI_2_F) ph -= PI_2_F;
-  return ph;
-}
-
-// (i16)(float) as the reference's x86-64 build evaluates it (ofdm_decoder.cpp:254-255): cvttss2si to 32 bits
-// (0x80000000 when out of range or NaN), then the low 16 bits. Out-of-range values only occur in the start-up
-// transient of the SOFTDEC2 weighting; the Viterbi clamps to +-127 afterwards anyway.
-__device__ __forceinline__ short to_i16(float v)
-{
-  const int r = (fabsf(v) < 2147483648.0f) ? __float2int_rz(v) : (int)0x80000000;
-  return (short)(r & 0xffff);
-}
-
-struct CarrierState
-{
-  float integ, stddev, mean_pow, mean_sigma, null_pow;
-};
-
-// decode_symbol for one carrier (ofdm_decoder.cpp:166-294). Returns r1 (soft value before the symbol-wide scale).
-template <int SOFT>
-__device__ __forceinline__ float2 demap_carrier(CarrierState & st, float2 x, float2 ref, float clock_term)
-{
-  constexpr float ALPHA = 0.005f;
-  const float ref_abs = sqrtf(ref.x * ref.x + ref.y * ref.y);
-  float2 raw = cmul_conj(x, ref);
-  raw.x /= ref_abs;
-  raw.y /= ref_abs;
-  const float perr = clock_term + st.integ;
-  const float a = -perr, a2 = a * a;
-  const float2 rot = make_float2(0.9994032382965087890625f + a2 * (a2 * 3.679168224334716796875e-2f + -0.495580852031707763671875f),
-                                 a * (a2 * -0.16034401953220367431640625f + 0.99903142452239990234375f));
-  const float2 z = cmul(raw, rot);
-  const float ph = first_quadrant(atan2f(z.y, z.x));
-  st.integ += 0.2f * ALPHA * (ph - PI_4_F);
-  st.integ = fminf(fmaxf(st.integ, -20.0f * RAD_PER_DEG_F), 20.0f * RAD_PER_DEG_F);
-  const float dv = ph - PI_4_F;
-  st.stddev += ALPHA * (dv * dv - st.stddev);
-  const float pw = z.x * z.x + z.y * z.y;
-  st.mean_pow += ALPHA * (pw - st.mean_pow);
-  const float lvl = sqrtf(st.mean_pow);
-  const float axis = lvl * 0.70710678118654752440f;
-  const float dr = fabsf(z.x) - axis, di = fabsf(z.y) - axis;
-  st.mean_sigma += ALPHA * (dr * dr + di * di - st.mean_sigma);
-  float sig = st.mean_pow - st.null_pow;
-  if (sig <= 0.0f) sig = 0.1f;
-  float w1;
-  if (SOFT == 2) w1 = ref_abs;
-  else if (SOFT == 1)
-  {
-    w1 = ref_abs / st.mean_sigma;
-    w1 /= st.null_pow / sig + 0.7f;
-  }
-  else
-  {
-    const float zabs = sqrtf(pw);
-    w1 = sqrtf(zabs * ref_abs) * lvl;
-    w1 /= st.null_pow / sig + 0.7f;
-    w1 /= st.mean_sigma * zabs;
-  }
-  return make_float2(z.x * w1, z.y * w1);
-}
-
-template <int SOFT>
-__global__ void __launch_bounds__(DEMAP_THREADS, 1) k_demap(const DemapWork * __restrict__ work, const FrameDesc * __restrict__ frames,
-                                                            const uint8_t * __restrict__ null_is_tii, const float2 * __restrict__ X,
-                                                            const int16_t * __restrict__ rel_of_k, OfdmStateDev * __restrict__ states,
-                                                            int16_t * __restrict__ soft)
-{
-  __shared__ float red[2][DEMAP_THREADS / 32];
-  const DemapWork wk = work[blockIdx.x];
-  const int tid = threadIdx.x, k0 = 2 * tid;
-  OfdmStateDev & sd = states[wk.state];
-  CarrierState s0, s1;
-  if (wk.reset)
-  {
-    s0 = CarrierState{ 0.0f, 0.0f, 0.0f, 0.0f, 0.0f };
-    s1 = s0;
-  }
-  else
-  {
-    s0 = CarrierState{ sd.integ[k0], sd.stddev[k0], sd.mean_pow[k0], sd.mean_sigma[k0], sd.null_pow[k0] };
-    s1 = CarrierState{ sd.integ[k0 + 1], sd.stddev[k0 + 1], sd.mean_pow[k0 + 1], sd.mean_sigma[k0 + 1], sd.null_pow[k0 + 1] };
-  }
-  float mean_value = sd.mean_value; // not touched by reset() (ofdm_decoder.cpp:90-101)
-  const float g0 = (float)(K_CARR / 2 - rel_of_k[k0]) / (float)(K_CARR / 2);
-  const float g1 = (float)(K_CARR / 2 - rel_of_k[k0 + 1]) / (float)(K_CARR / 2);
-  constexpr float W2 = SOFT == 0 ? -100.0f : -140.0f;
-  int buf = 0;
-
-  for (int fi = 0; fi < wk.n_frames; fi++)
-  {
-    const FrameDesc fd = frames[wk.desc_first + fi];
-    const float4 * row = reinterpret_cast<const float4 *>(X + (size_t)fd.xslot * X_ROWS * K_CARR) + tid;
-    int16_t * out = soft + (size_t)fd.slot * FRAME_SOFT;
-    const float ce = fd.clock_err / 1024.0f * PI_F;
-    const float c0 = ce * g0, c1 = ce * g1;
-    float4 ref = row[0];                                   // store_reference_symbol_0
-    float4 cur = row[K_CARR / 2];                          // symbol 1 (row stride = 1536 float2 = 768 float4)
-    for (int sym = 1; sym <= fd.n_syms; sym++)
-    {
-      float4 nxt = cur;
-      if (sym < 76) nxt = row[(size_t)(sym + 1) * (K_CARR / 2)]; // prefetch symbol sym+1 (row 76 = null symbol)
-      const float2 r0 = demap_carrier<SOFT>(s0, make_float2(cur.x, cur.y), make_float2(ref.x, ref.y), c0);
-      const float2 r1 = demap_carrier<SOFT>(s1, make_float2(cur.z, cur.w), make_float2(ref.z, ref.w), c1);
-      const float w2 = W2 / mean_value;
-      short2 re = make_short2(to_i16(r0.x * w2), to_i16(r1.x * w2));
-      short2 im = make_short2(to_i16(r0.y * w2), to_i16(r1.y * w2));
-      int16_t * o = out + (size_t)(sym - 1) * SYM_BITS;
-      reinterpret_cast<short2 *>(o)[tid] = re;
-      reinterpret_cast<short2 *>(o + K_CARR)[tid] = im;
-      // mMeanValue = sum |r1| / K for the NEXT symbol (ofdm_decoder.cpp:256,294)
-      float part = sqrtf(r0.x * r0.x + r0.y * r0.y) + sqrtf(r1.x * r1.x + r1.y * r1.y);
-      part = warp_sum(part);
-      if ((tid & 31) == 0) red[buf][tid >> 5] = part;
-      __syncthreads();
-      float tot = 0.0f;
-#pragma unroll
-      for (int w = 0; w < DEMAP_THREADS / 32; w++) tot += red[buf][w];
-      mean_value = tot / (float)K_CARR;
-      buf ^= 1;
-      ref = cur;
-      cur = nxt;
-    }
-    // null symbol: store_null_symbol_without_tii (ofdm_decoder.cpp:114-130); `cur` holds row 76 when the frame is complete
-    if (fd.n_syms == 75 && !(null_is_tii != nullptr && null_is_tii[wk.desc_first + fi]))
-    {
-      constexpr float MIN_POW = (1.0f / 32767.0f) * (1.0f / 32767.0f);
-      const float p0 = cur.x * cur.x + cur.y * cur.y + MIN_POW, p1 = cur.z * cur.z + cur.w * cur.w + MIN_POW;
-      s0.null_pow += 0.05f * (p0 - s0.null_pow);
-      s1.null_pow += 0.05f * (p1 - s1.null_pow);
-    }
-  }
-  sd.integ[k0] = s0.integ; sd.integ[k0 + 1] = s1.integ;
-  sd.stddev[k0] = s0.stddev; sd.stddev[k0 + 1] = s1.stddev;
-  sd.mean_pow[k0] = s0.mean_pow; sd.mean_pow[k0 + 1] = s1.mean_pow;
-  sd.mean_sigma[k0] = s0.mean_sigma; sd.mean_sigma[k0 + 1] = s1.mean_sigma;
-  sd.null_pow[k0] = s0.null_pow; sd.null_pow[k0 + 1] = s1.null_pow;
-  if (tid == 0) sd.mean_value = mean_value;
-}
-
-// ------------------------------------------------------------------------------------------------ DQPSK demapper, cluster version
-// The same arithmetic as k_demap, laid out for throughput: a cluster of 4 CTAs x 384 threads decodes one recording, one
-// nominal carrier per thread, so 96 recordings fill the 148 SMs with ~36 resident warps each. The only coupling between
-// carriers is mMeanValue (the sum of |r| over the 1536 carriers of the PREVIOUS symbol, ofdm_decoder.cpp:256,294).
-// It is exchanged through distributed shared memory without any block or cluster barrier in the loop:
-//   * every warp reduces its 32 |r| values (fixed shuffle tree) and stores {sum, tag} as ONE 64-bit word into slot
-//     [symbol mod 4][warp] of the ring in each of the 4 CTAs (st.shared::cluster.b64, single-copy atomic);
-//   * warp 0 of each CTA polls the 48 words of that symbol, adds them in a fixed order and publishes {total, tag};
-//   * a warp polls {total, tag} of symbol g-1 only when it needs the scale for symbol g's output, i.e. one symbol of
-//     work later, so the poll normally falls through.
-// The ring depth of 4 is safe because a warp can run at most one symbol ahead of the slowest warp of the cluster.
-// Division, square root and atan2 use the SFU approximations (<= 2 ulp each); the +-1 LSB soft-bit bar is unaffected
-// (tests/test_gpu_stages.py::test_ofdm_decoder_soft_bits).
-constexpr int DM2_CLUSTER = 4;
-constexpr int DM2_THREADS = K_CARR / DM2_CLUSTER;      // 384
-constexpr int DM2_WARPS = DM2_THREADS / 32;            // 12
-constexpr int DM2_ALL_WARPS = DM2_WARPS * DM2_CLUSTER; // 48
-constexpr int DM2_RING = 4;
-
-__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
-__device__ __forceinline__ float fast_sqrt(float a)
-{
-  float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
-  return r;
-}
-
-// turn_phase_to_first_quadrant(arg(z)) (glob_defs.h:173-182) without atan2/fmod: rotate z by a multiple of 90 degrees
-// into the first quadrant, then atan of a ratio <= 1 (Cephes-style reduction, |error| < 2e-7 rad).
-__device__ __forceinline__ float first_quadrant_phase(float x, float y)
-{
-  float u, v;
-  if (y >= 0.0f) { if (x > 0.0f) { u = x; v = y; } else { u = y; v = -x; } }
-  else { if (x < 0.0f) { u = -x; v = -y; } else { u = -y; v = x; } }
-  const bool swap = v > u;
-  const float num = swap ? u : v, den = swap ? v : u;
-  float t = den > 0.0f ? fast_div(num, den) : 0.0f;       // t in [0, 1]
-  const bool hi = t > 0.4142135623730950f;                // tan(pi/8)
-  if (hi) t = fast_div(t - 1.0f, t + 1.0f);
-  const float z = t * t;
-  float p = ((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f;
-  float a = p * z * t + t;
-  if (hi) a += PI_4_F;
-  return swap ? PI_2_F - a : a;
-}
-
-template <int SOFT>
-__device__ __forceinline__ float2 demap_carrier_fast(CarrierState & st, float2 x, float2 ref, float clock_term)
-{
-  constexpr float ALPHA = 0.005f;
-  const float ref_abs = fast_sqrt(ref.x * ref.x + ref.y * ref.y);
-  const float inv_ref = fast_div(1.0f, ref_abs);
-  float2 raw = cmul_conj(x, ref);
-  raw.x *= inv_ref;
-  raw.y *= inv_ref;
-  const float a = -(clock_term + st.integ), a2 = a * a;
-  const float2 rot = make_float2(0.9994032382965087890625f + a2 * (a2 * 3.679168224334716796875e-2f + -0.495580852031707763671875f),
-                                 a * (a2 * -0.16034401953220367431640625f + 0.99903142452239990234375f));
-  const float2 z = cmul(raw, rot);
-  const float ph = first_quadrant_phase(z.x, z.y);
-  st.integ += 0.2f * ALPHA * (ph - PI_4_F);
-  st.integ = fminf(fmaxf(st.integ, -20.0f * RAD_PER_DEG_F), 20.0f * RAD_PER_DEG_F);
-  const float dv = ph - PI_4_F;
-  st.stddev += ALPHA * (dv * dv - st.stddev);
-  const float pw = z.x * z.x + z.y * z.y;
-  st.mean_pow += ALPHA * (pw - st.mean_pow);
-  const float lvl = fast_sqrt(st.mean_pow);
-  const float axis = lvl * 0.70710678118654752440f;
-  const float dr = fabsf(z.x) - axis, di = fabsf(z.y) - axis;
-  st.mean_sigma += ALPHA * (dr * dr + di * di - st.mean_sigma);
-  float sig = st.mean_pow - st.null_pow;
-  if (sig <= 0.0f) sig = 0.1f;
-  float w1;
-  if (SOFT == 2) w1 = ref_abs;
-  else if (SOFT == 1) w1 = fast_div(ref_abs, st.mean_sigma * (fast_div(st.null_pow, sig) + 0.7f));
-  else
-  {
-    const float zabs = fast_sqrt(pw);
-    // sqrt(zabs*ref_abs) * lvl / (nullPow/sig + 0.7) / (meanSigma * zabs)
-    w1 = fast_div(fast_sqrt(zabs * ref_abs) * lvl, (fast_div(st.null_pow, sig) + 0.7f) * (st.mean_sigma * zabs));
-  }
-  return make_float2(z.x * w1, z.y * w1);
-}
-
-__device__ __forceinline__ unsigned smem_u32(const void * p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void st_cluster_b64(unsigned local_addr, unsigned rank, unsigned long long v)
-{
-  unsigned remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
-  asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(remote), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_volatile_b64(unsigned addr)
-{
-  unsigned long long v;
-  asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ unsigned cluster_rank()
-{
-  unsigned r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-
-template <int SOFT>
-__global__ void __cluster_dims__(DM2_CLUSTER, 1, 1) __launch_bounds__(DM2_THREADS, 3)
-k_demap2(const DemapWork * __restrict__ work, const FrameDesc * __restrict__ frames, const uint8_t * __restrict__ null_is_tii,
-         const float2 * __restrict__ X, const int16_t * __restrict__ rel_of_k, OfdmStateDev * __restrict__ states, int16_t * __restrict__ soft)
-{
-  __shared__ __align__(8) unsigned long long ring[DM2_RING][DM2_ALL_WARPS]; // {tag << 32 | float bits} per warp of the cluster
-  __shared__ __align__(8) unsigned long long total[DM2_RING];
-  const DemapWork wk = work[blockIdx.x / DM2_CLUSTER];
-  const unsigned rank = cluster_rank();
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int k = (int)rank * DM2_THREADS + tid;
-  const int cwarp = (int)rank * DM2_WARPS + warp;
-  for (int i = tid; i < DM2_RING * DM2_ALL_WARPS; i += DM2_THREADS) (&ring[0][0])[i] = 0ull;
-  if (tid < DM2_RING) total[tid] = 0ull;
-  cluster_sync_all(); // rings are zero before any remote store can arrive
-
-  OfdmStateDev & sd = states[wk.state];
-  CarrierState s = wk.reset ? CarrierState{ 0.0f, 0.0f, 0.0f, 0.0f, 0.0f }
-                            : CarrierState{ sd.integ[k], sd.stddev[k], sd.mean_pow[k], sd.mean_sigma[k], sd.null_pow[k] };
-  float mean_value = sd.mean_value;
-  const float gk = (float)(K_CARR / 2 - rel_of_k[k]) / (float)(K_CARR / 2);
-  constexpr float W2 = SOFT == 0 ? -100.0f : -140.0f;
-  const unsigned ring_base = smem_u32(&ring[0][0]), total_base = smem_u32(&total[0]);
-  int g = 0; // symbols decoded so far in this launch; tag of symbol g is g + 1
-
-  for (int fi = 0; fi < wk.n_frames; fi++)
-  {
-    const FrameDesc fd = frames[wk.desc_first + fi];
-    const float2 * row = X + (size_t)fd.xslot * X_ROWS * K_CARR + k;
-    int16_t * out = soft + (size_t)fd.slot * FRAME_SOFT + k;
-    const float cterm = fd.clock_err / 1024.0f * PI_F * gk;
-    float2 ref = row[0];
-    float2 cur = fd.n_syms >= 1 ? row[K_CARR] : ref;
-    float2 nxt = fd.n_syms >= 1 ? row[2 * K_CARR] : ref;
-    for (int sym = 1; sym <= fd.n_syms; sym++, g++)
-    {
-      const float2 nn = sym + 2 <= 76 ? row[(size_t)(sym + 2) * K_CARR] : nxt; // prefetch two rows ahead (row 76 = null symbol)
-      const float2 r = demap_carrier_fast<SOFT>(s, cur, ref, cterm);
-      // publish this warp's share of sum |r| for symbol g
-      float part = fast_sqrt(r.x * r.x + r.y * r.y);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      const unsigned long long word = ((unsigned long long)(unsigned)(g + 1) << 32) | (unsigned long long)__float_as_uint(part);
-      if (lane < DM2_CLUSTER) st_cluster_b64(ring_base + 8u * (unsigned)((g & (DM2_RING - 1)) * DM2_ALL_WARPS + cwarp), (unsigned)lane, word);
-      // scale of symbol g = mean |r| of symbol g-1
-      if (g > 0)
-      {
-        const unsigned addr = total_base + 8u * (unsigned)((g - 1) & (DM2_RING - 1));
-        unsigned long long t = ld_volatile_b64(addr);
-        while ((unsigned)(t >> 32) != (unsigned)g) t = ld_volatile_b64(addr);
-        mean_value = __uint_as_float((unsigned)t) / (float)K_CARR;
-      }
-      const float w2 = fast_div(W2, mean_value);
-      out[(size_t)(sym - 1) * SYM_BITS] = to_i16(r.x * w2);
-      out[(size_t)(sym - 1) * SYM_BITS + K_CARR] = to_i16(r.y * w2);
-      // warp 0 gathers the 48 partial sums of symbol g and publishes the total
-      if (warp == 0)
-      {
-        const unsigned slot = ring_base + 8u * (unsigned)((g & (DM2_RING - 1)) * DM2_ALL_WARPS);
-        float acc = 0.0f;
-        if (lane < DM2_ALL_WARPS - 32)
-        {
-          unsigned long long e = ld_volatile_b64(slot + 8u * (unsigned)(lane + 32));
-          while ((unsigned)(e >> 32) != (unsigned)(g + 1)) e = ld_volatile_b64(slot + 8u * (unsigned)(lane + 32));
-          acc = __uint_as_float((unsigned)e);
-        }
-        unsigned long long e = ld_volatile_b64(slot + 8u * (unsigned)lane);
-        while ((unsigned)(e >> 32) != (unsigned)(g + 1)) e = ld_volatile_b64(slot + 8u * (unsigned)lane);
-        acc += __uint_as_float((unsigned)e);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0)
-        {
-          const unsigned long long tw = ((unsigned long long)(unsigned)(g + 1) << 32) | (unsigned long long)__float_as_uint(acc);
-          asm volatile("st.volatile.shared.b64 [%0], %1;" ::"r"(total_base + 8u * (unsigned)(g & (DM2_RING - 1))), "l"(tw) : "memory");
-        }
-      }
-      ref = cur;
-      cur = nxt;
-      nxt = nn;
-    }
-    if (fd.n_syms == 75 && !(null_is_tii != nullptr && null_is_tii[wk.desc_first + fi]))
-    {
-      constexpr float MIN_POW = (1.0f / 32767.0f) * (1.0f / 32767.0f);
-      s.null_pow += 0.05f * (cur.x * cur.x + cur.y * cur.y + MIN_POW - s.null_pow); // `cur` is row 76 here
-    }
-  }
-  // mMeanValue after the last symbol
-  if (g > 0)
-  {
-    const unsigned addr = total_base + 8u * (unsigned)((g - 1) & (DM2_RING - 1));
-    unsigned long long t = ld_volatile_b64(addr);
-    while ((unsigned)(t >> 32) != (unsigned)g) t = ld_volatile_b64(addr);
-    mean_value = __uint_as_float((unsigned)t) / (float)K_CARR;
-  }
-  sd.integ[k] = s.integ;
-  sd.stddev[k] = s.stddev;
-  sd.mean_pow[k] = s.mean_pow;
-  sd.mean_sigma[k] = s.mean_sigma;
-  sd.null_pow[k] = s.null_pow;
-  cluster_sync_all(); // nobody leaves while a peer may still store into its ring; all reads of sd.mean_value are done
-  if (rank == 0 && tid == 0) sd.mean_value = mean_value;
-}
-
-// ------------------------------------------------------------------------------------------------ DQPSK demapper, sliced version
-// Same arithmetic again, laid out so that nothing in the symbol loop waits:
+// ------------------------------------------------------------------------------------------------ DQPSK demapper (D1-D4)
+// OfdmDecoder::decode_symbol (ofdm_decoder.cpp:147-355) for whole recordings. The per-carrier IIR chains are sequential
+// in time but independent across carriers, so the parallelism is recordings x carriers:
 //   * a recording's 1536 carriers are split into `slices` CTAs (2 adjacent carriers per thread: one 16-byte load per
 //     spectrum row, one 4-byte store per soft-bit plane), the slice count chosen by the launcher so that the CTAs of
 //     all recordings fill the 148 SMs evenly; the launch is cooperative, so every CTA is resident;
 //   * the only coupling between carriers, mMeanValue (sum of |r| over the PREVIOUS symbol, ofdm_decoder.cpp:256,294),
 //     scales the OUTPUT only. Each warp publishes its partial sum of symbol g as one 64-bit word {g+1, sum} in a ring
-//     in global memory (L2), keeps its unscaled r in a small shared-memory stash, and writes the soft bits of symbol
-//     g - DM3_LAG, whose scale (24 partial sums of symbol g - DM3_LAG - 1, added in a fixed order by every warp for
-//     itself) was published several symbols ago and has been prefetched one iteration earlier: the tag check almost
-//     never spins, and there is no barrier, cluster or designated reducer;
-//   * spectrum rows are prefetched three rows ahead across frame boundaries (a recording's frames occupy consecutive
-//     row blocks of X);
-//   * 6 MUFU per carrier and symbol: rsqrt|X|^2 (shared by two symbols), rcp for the arctangent, sqrt(meanPow),
+//     in global memory (L2), keeps its unscaled r in a shared-memory stash, and writes the soft bits of symbol
+//     g - LAG, whose scale (24 partial sums of symbol g - LAG - 1, added in a fixed order by every warp for itself)
+//     was published several symbols ago: the tag check rarely fails (then the warp polls), and there is no barrier,
+//     cluster or designated reducer;
+//   * 6.5 MUFU per carrier and symbol: rsqrt|X|^2 (shared by two symbols), rcp for the arctangent, sqrt(meanPow),
 //     rsqrt|z|^2, sqrt(|P|/|z|) and one reciprocal of the combined denominator.
-constexpr int DM3_LAG = 3;
-constexpr int DM3_STASH = DM3_LAG + 1;   // stash depth (power of two)
-static_assert((DM3_STASH & (DM3_STASH - 1)) == 0, "stash depth must be a power of two");
-constexpr int DM3_RING = 64;           // > 2 * lag + 2 (k_demap3: DM3_LAG, k_demap4: its LAG): a slot is never overwritten while a slower warp may still read it
+// (Earlier versions - one CTA per recording with IEEE division / atan2, a cluster of 4 CTAs exchanging through DSMEM, and a
+// scalar-FP32 form of the present scheme - were measured at 12.5 / 9.7 / 8.1 ms per 9984 frames and have been removed.)
+constexpr int DM3_RING = 64;           // > 2 * LAG + 2: a slot is never overwritten while a slower warp may still read it
 constexpr int DM3_WARPS = K_CARR / 64; // warps per recording
 constexpr int DM3_ROW4 = K_CARR / 2;   // float4 per spectrum row
 
 __device__ __forceinline__ float rcp_ftz(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 __device__ __forceinline__ float rsqrt_ftz(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 __device__ __forceinline__ float sqrt_ftz(float a) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
-
-// turn_phase_to_first_quadrant(arg(z)) (glob_defs.h:173-182) = arg(z) mod pi/2: the angle of (|x|, |y|), mirrored when
-// x and y have different signs. One reciprocal and an odd minimax polynomial of degree 13 on [0, 1] (|error| < 3.1e-7 rad).
-__device__ __forceinline__ float folded_phase(float x, float y)
-{
-  const float ax = fabsf(x), ay = fabsf(y);
-  const float mn = fminf(ax, ay), mx = fmaxf(ax, ay);
-  const float t = mn * rcp_ftz(mx);
-  const float z = t * t;
-  float p = 0.00681177107617259f;
-  p = p * z + -0.033604156225919724f;
-  p = p * z + 0.07962360233068466f;
-  p = p * z + -0.13233338296413422f;
-  p = p * z + 0.19807815551757812f;
-  p = p * z + -0.3331736922264099f;
-  p = p * z + 0.9999961256980896f;
-  const float a = p * t;
-  const bool mirror = (ay > ax) != ((__float_as_int(x) ^ __float_as_int(y)) < 0);
-  return mirror ? PI_2_F - a : a;
-}
-
-template <int SOFT>
-__device__ __forceinline__ float2 dm3_carrier(CarrierState & st, float2 x, float2 ref, float ref_abs, float ref_inv, float clock_term, float & r_abs)
-{
-  constexpr float ALPHA = 0.005f;
-  float2 raw = cmul_conj(x, ref);
-  raw.x *= ref_inv;
-  raw.y *= ref_inv;
-  const float a = -(clock_term + st.integ), a2 = a * a;
-  const float2 rot = make_float2(0.9994032382965087890625f + a2 * (a2 * 3.679168224334716796875e-2f + -0.495580852031707763671875f),
-                                 a * (a2 * -0.16034401953220367431640625f + 0.99903142452239990234375f));
-  const float2 z = cmul(raw, rot);
-  const float dv = folded_phase(z.x, z.y) - PI_4_F;
-  st.integ = fminf(fmaxf(st.integ + 0.2f * ALPHA * dv, -20.0f * RAD_PER_DEG_F), 20.0f * RAD_PER_DEG_F);
-  st.stddev += ALPHA * (dv * dv - st.stddev);
-  const float pw = z.x * z.x + z.y * z.y;
-  st.mean_pow += ALPHA * (pw - st.mean_pow);
-  const float lvl = sqrt_ftz(st.mean_pow);
-  const float axis = lvl * 0.70710678118654752440f;
-  const float dr = fabsf(z.x) - axis, di = fabsf(z.y) - axis;
-  st.mean_sigma += ALPHA * (dr * dr + di * di - st.mean_sigma);
-  float sig = st.mean_pow - st.null_pow;
-  if (sig <= 0.0f) sig = 0.1f;
-  const float inv_z = rsqrt_ftz(pw);
-  float w1;
-  if (SOFT == 2) w1 = ref_abs;
-  else
-  {
-    // 1 / ((nullPow / sig + 0.7) * meanSigma) = sig / ((nullPow + 0.7 sig) * meanSigma)
-    const float g = sig * rcp_ftz((st.null_pow + 0.7f * sig) * st.mean_sigma);
-    if (SOFT == 1) w1 = ref_abs * g;
-    else w1 = sqrt_ftz(ref_abs * inv_z) * lvl * g; // sqrt(|z| |P|) / |z| = sqrt(|P| / |z|)
-  }
-  r_abs = pw * inv_z * w1; // |z| w1, w1 >= 0
-  return make_float2(z.x * w1, z.y * w1);
-}
-
-// low 16 bits of the x86 cvttss2si result (see to_i16): the saturated positive case must read 0, not 0xffff
-__device__ __forceinline__ unsigned i16_bits(float v)
-{
-  const int r = __float2int_rz(v);
-  return r == 0x7fffffff ? 0u : (unsigned)r & 0xffffu;
-}
 
 __device__ __forceinline__ unsigned long long ld_volatile_global_b64(const unsigned long long * p)
 {
@@ -1100,156 +681,16 @@ __device__ __forceinline__ float dm3_total(const unsigned long long * slot, unsi
   return v;
 }
 
-template <int SOFT>
-__global__ void __launch_bounds__(DM3_ROW4) k_demap3(const DemapWork * __restrict__ work, const FrameDesc * __restrict__ frames,
-                                                     const uint8_t * __restrict__ null_is_tii, const float2 * __restrict__ X,
-                                                     const int16_t * __restrict__ rel_of_k, OfdmStateDev * __restrict__ states,
-                                                     int16_t * __restrict__ soft, unsigned long long * __restrict__ ring, int slices)
-{
-  extern __shared__ float4 dm3_stash[]; // [DM3_STASH][blockDim.x]: unscaled (r0.x, r0.y, r1.x, r1.y) of the last symbols
-  const int w = blockIdx.x / slices, slice = blockIdx.x - w * slices;
-  const DemapWork wk = work[w];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int t_rec = slice * (int)blockDim.x + tid; // thread index within the recording: carriers 2 t_rec, 2 t_rec + 1
-  const int gw = t_rec >> 5;                       // warp index within the recording
-  const int k0 = 2 * t_rec;
-  unsigned long long * my_ring = ring + (size_t)w * DM3_RING * DM3_WARPS;
-
-  OfdmStateDev & sd = states[wk.state];
-  CarrierState s0, s1;
-  if (wk.reset) { s0 = CarrierState{ 0.0f, 0.0f, 0.0f, 0.0f, 0.0f }; s1 = s0; }
-  else
-  {
-    s0 = CarrierState{ sd.integ[k0], sd.stddev[k0], sd.mean_pow[k0], sd.mean_sigma[k0], sd.null_pow[k0] };
-    s1 = CarrierState{ sd.integ[k0 + 1], sd.stddev[k0 + 1], sd.mean_pow[k0 + 1], sd.mean_sigma[k0 + 1], sd.null_pow[k0 + 1] };
-  }
-  const float mean_value0 = sd.mean_value; // not touched by reset() (ofdm_decoder.cpp:90-101)
-  const float g0 = (float)(K_CARR / 2 - rel_of_k[k0]) / (float)(K_CARR / 2);
-  const float g1 = (float)(K_CARR / 2 - rel_of_k[k0 + 1]) / (float)(K_CARR / 2);
-  constexpr float W2 = SOFT == 0 ? -100.0f : -140.0f;
-
-  const int total_rows = wk.n_frames * X_ROWS;
-  const float4 * rows = reinterpret_cast<const float4 *>(X + (size_t)(total_rows > 0 ? frames[wk.desc_first].xslot : 0) * X_ROWS * K_CARR) + t_rec;
-  float4 cur = total_rows > 0 ? rows[0] : make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 n1 = total_rows > 1 ? rows[(size_t)DM3_ROW4] : cur;
-  float4 n2 = total_rows > 2 ? rows[(size_t)2 * DM3_ROW4] : cur;
-
-  float4 ref = cur;
-  float ref_abs0 = 0.f, ref_inv0 = 0.f, ref_abs1 = 0.f, ref_inv1 = 0.f;
-  float c0 = 0.f, c1 = 0.f;
-  int n_syms = 0, row = 0, fi = 0;
-  int out_row0 = 0;
-  bool tii = false;
-  int g = 0;               // symbols decoded so far; tag of symbol g is g + 1
-  int orow[DM3_LAG];       // output rows (slot * 75 + symbol - 1) of the last DM3_LAG symbols, newest first
-#pragma unroll
-  for (int i = 0; i < DM3_LAG; i++) orow[i] = 0;
-  unsigned long long pre = 0; // prefetched ring word of the symbol whose total is needed next
-
-  // soft bits of symbol d (its unscaled values are in the stash, its scale is the total of symbol d - 1)
-  auto emit = [&](int d, int o_row, unsigned long long word) {
-    float w2;
-    if (d == 0) w2 = rcp_ftz(mean_value0) * W2;
-    else w2 = rcp_ftz(dm3_total(my_ring + (size_t)((d - 1) & (DM3_RING - 1)) * DM3_WARPS, word, (unsigned)d, lane)) * (W2 * (float)K_CARR);
-    const float4 r = dm3_stash[(d & (DM3_STASH - 1)) * blockDim.x + tid];
-    unsigned * o = reinterpret_cast<unsigned *>(soft + (size_t)o_row * SYM_BITS);
-    o[t_rec] = i16_bits(r.x * w2) | (i16_bits(r.z * w2) << 16);
-    o[K_CARR / 2 + t_rec] = i16_bits(r.y * w2) | (i16_bits(r.w * w2) << 16);
-  };
-
-  for (int q = 0; q < total_rows; q++)
-  {
-    const float4 nn = q + 3 < total_rows ? rows[(size_t)(q + 3) * DM3_ROW4] : n2;
-    if (row == 0)
-    {
-      const FrameDesc fd = frames[wk.desc_first + fi];
-      const float ce = fd.clock_err / 1024.0f * PI_F;
-      c0 = ce * g0;
-      c1 = ce * g1;
-      n_syms = fd.n_syms;
-      out_row0 = fd.slot * 75;
-      tii = null_is_tii != nullptr && null_is_tii[wk.desc_first + fi];
-    }
-    if (row == 0 || row <= n_syms)
-    {
-      if (row > 0)
-      {
-        const int d = g - DM3_LAG; // symbol whose soft bits are written in this iteration
-        float a0, a1;
-        const float2 r0 = dm3_carrier<SOFT>(s0, make_float2(cur.x, cur.y), make_float2(ref.x, ref.y), ref_abs0, ref_inv0, c0, a0);
-        const float2 r1 = dm3_carrier<SOFT>(s1, make_float2(cur.z, cur.w), make_float2(ref.z, ref.w), ref_abs1, ref_inv1, c1, a1);
-        float part = a0 + a1;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0)
-          st_volatile_global_b64(my_ring + (size_t)(g & (DM3_RING - 1)) * DM3_WARPS + gw,
-                                 ((unsigned long long)(unsigned)(g + 1) << 32) | (unsigned long long)__float_as_uint(part));
-        dm3_stash[(g & (DM3_STASH - 1)) * blockDim.x + tid] = make_float4(r0.x, r0.y, r1.x, r1.y);
-        if (d >= 0) emit(d, orow[DM3_LAG - 1], pre);
-        // ring word for the next iteration's output (symbol d + 1 is scaled by the total of symbol d): a whole iteration to land
-        if (d >= 0 && lane < DM3_WARPS) pre = ld_volatile_global_b64(my_ring + (size_t)(d & (DM3_RING - 1)) * DM3_WARPS + lane);
-#pragma unroll
-        for (int i = DM3_LAG - 1; i > 0; i--) orow[i] = orow[i - 1];
-        orow[0] = out_row0 + (row - 1);
-        g++;
-      }
-      // this row is the phase reference of the next symbol
-      ref = cur;
-      const float p0 = cur.x * cur.x + cur.y * cur.y, p1 = cur.z * cur.z + cur.w * cur.w;
-      ref_inv0 = rsqrt_ftz(p0);
-      ref_inv1 = rsqrt_ftz(p1);
-      ref_abs0 = p0 * ref_inv0;
-      ref_abs1 = p1 * ref_inv1;
-    }
-    else if (row == X_ROWS - 1 && n_syms == 75 && !tii)
-    {
-      // store_null_symbol_without_tii (ofdm_decoder.cpp:114-130)
-      constexpr float MIN_POW = (1.0f / 32767.0f) * (1.0f / 32767.0f);
-      s0.null_pow += 0.05f * (cur.x * cur.x + cur.y * cur.y + MIN_POW - s0.null_pow);
-      s1.null_pow += 0.05f * (cur.z * cur.z + cur.w * cur.w + MIN_POW - s1.null_pow);
-    }
-    cur = n1;
-    n1 = n2;
-    n2 = nn;
-    if (++row == X_ROWS) { row = 0; fi++; }
-  }
-  // drain: the last DM3_LAG symbols
-#pragma unroll
-  for (int i = DM3_LAG - 1; i >= 0; i--)
-  {
-    const int d = g - 1 - i;
-    if (d < 0) continue;
-    unsigned long long word = 0;
-    if (d >= 1 && lane < DM3_WARPS) word = ld_volatile_global_b64(my_ring + (size_t)((d - 1) & (DM3_RING - 1)) * DM3_WARPS + lane);
-    emit(d, orow[i], word);
-  }
-  sd.integ[k0] = s0.integ; sd.integ[k0 + 1] = s1.integ;
-  sd.stddev[k0] = s0.stddev; sd.stddev[k0 + 1] = s1.stddev;
-  sd.mean_pow[k0] = s0.mean_pow; sd.mean_pow[k0 + 1] = s1.mean_pow;
-  sd.mean_sigma[k0] = s0.mean_sigma; sd.mean_sigma[k0 + 1] = s1.mean_sigma;
-  sd.null_pow[k0] = s0.null_pow; sd.null_pow[k0 + 1] = s1.null_pow;
-  // mMeanValue after the last symbol (every other thread has read sd.mean_value before it published anything)
-  if (gw == 0 && g > 0)
-  {
-    unsigned long long word = 0;
-    const unsigned long long * slot = my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM3_WARPS;
-    if (lane < DM3_WARPS) word = ld_volatile_global_b64(slot + lane);
-    const float tot = dm3_total(slot, word, (unsigned)g, lane);
-    if (lane == 0) sd.mean_value = tot / (float)K_CARR;
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ DQPSK demapper, packed version
-// k_demap3's scheme (sliced cooperative launch, lagged scale exchange through L2) with the arithmetic and the data path
-// redone for sm_100:
+// The scheme above with the arithmetic and the data path done for sm_100:
 //   * the two carriers of a thread run in the two halves of the packed FP32 instructions (FADD2 / FMUL2 / FFMA2): every
 //     multiply-add of the per-carrier recurrences is issued once for both carriers; only MUFU, min/max and the selects
 //     stay scalar;
 //   * spectrum rows arrive through a per-thread cp.async ring in shared memory, DM4_PF rows deep: the load of row q + 8
-//     is issued when row q is consumed and nothing reads a destination register in between. k_demap3 rotates its
-//     prefetch registers with MOVs, and the first MOV waits for the load (an effective distance of ONE row); a register
-//     ring rotated by unrolling the row loop was measured too and is worse (9.7 ms against 7.6 ms: the loads in flight
-//     share the six scoreboards, and a wait on a shared scoreboard waits for the newest load);
+//     is issued when row q is consumed and nothing reads a destination register in between (prefetch registers rotated
+//     with MOVs wait for the load at the first MOV, an effective distance of ONE row; a register ring rotated by unrolling
+//     the row loop was measured too and is worse, 9.7 ms against 7.6 ms: the loads in flight share the six scoreboards,
+//     and a wait on a shared scoreboard waits for the newest load);
 //   * x86 (i16)(float) semantics of the output conversion are checked once per thread and row (rare path) instead of
 //     once per value.
 constexpr int DM4_PF = 8; // rows in flight per thread (power of two)
@@ -1422,7 +863,7 @@ __global__ void __launch_bounds__(DM4_MAX_THREADS) k_demap4(const DemapWork * __
     const float4 cur = rowbuf[slot + tid];
     if (q + DM4_PF < total_rows) cp_async16(rowbuf_addr + slot * 16u, rows + (size_t)(q + DM4_PF) * DM3_ROW4);
     cp_async_commit();
-    const float2 xr = make_float2(cur.x, cur.z), xi = make_float2(cur.y, cur.w);
+    const float2 xr = make_float2(cur.x, cur.y), xi = make_float2(cur.z, cur.w); // X rows hold (re 2t, re 2t+1, im 2t, im 2t+1): register pairs as loaded
     if (row == 0)
     {
       const FrameDesc fd = frames[wk.desc_first + fi];
@@ -1796,7 +1237,6 @@ cudaError_t launch_reorder_frames(cudaStream_t s, const DeviceTables & t, const 
 }
 
 size_t demap_ring_bytes(int n_work) { return sizeof(unsigned long long) * (size_t)std::max(n_work, 1) * DM3_RING * DM3_WARPS; }
-static size_t demap3_smem_bytes(int threads) { return sizeof(float4) * (size_t)DM3_STASH * (size_t)threads; }
 static size_t demap4_smem_bytes(int threads, int lag) { return sizeof(float4) * (size_t)(lag + 1 + DM4_PF) * (size_t)threads + sizeof(int) * (size_t)(lag + 1) * (size_t)(threads / 32); }
 template <int LAG> static const void * demap4_fn(int soft_bit_type)
 {
@@ -1810,36 +1250,11 @@ cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork
   if (n_work <= 0) return cudaSuccess;
   if (soft_bit_type < 0 || soft_bit_type > 2) return cudaErrorInvalidValue;
   if (lc) (*lc)++;
-  static const bool use_v1 = getenv("DABSTAR_DEMAP_V1") != nullptr; // one CTA per recording, IEEE div/sqrt/atan2 (debug aid)
-  if (use_v1)
-  {
-    switch (soft_bit_type)
-    {
-    case 0: k_demap<0><<<n_work, DEMAP_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
-    case 1: k_demap<1><<<n_work, DEMAP_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
-    default: k_demap<2><<<n_work, DEMAP_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
-    }
-    return cudaGetLastError();
-  }
-  static const bool use_v2 = getenv("DABSTAR_DEMAP_V2") != nullptr; // cluster of 4 CTAs per recording, DSMEM exchange (kept for comparison)
-  if (use_v2)
-  {
-    const int grid = n_work * DM2_CLUSTER;
-    switch (soft_bit_type)
-    {
-    case 0: k_demap2<0><<<grid, DM2_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
-    case 1: k_demap2<1><<<grid, DM2_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
-    default: k_demap2<2><<<grid, DM2_THREADS, 0, s>>>(work, frames, null_is_tii, X, t.rel_of_k, states, soft); break;
-    }
-    return cudaGetLastError();
-  }
   if (ring == nullptr) return cudaErrorInvalidValue;
-  static const bool use_v3 = getenv("DABSTAR_DEMAP_V3") != nullptr; // scalar arithmetic, register prefetch (kept for comparison)
-  static const int lag = getenv("DABSTAR_DEMAP_LAG") ? atoi(getenv("DABSTAR_DEMAP_LAG")) : 7; // 3 or 7 symbols between arithmetic and output
-  const void * fn = use_v3 ? (soft_bit_type == 0 ? (const void *)k_demap3<0> : (soft_bit_type == 1 ? (const void *)k_demap3<1> : (const void *)k_demap3<2>))
-                           : (lag == 3 ? demap4_fn<3>(soft_bit_type) : (lag == 15 ? demap4_fn<15>(soft_bit_type) : demap4_fn<7>(soft_bit_type)));
-  auto smem_bytes = [&](int threads) { return use_v3 ? demap3_smem_bytes(threads) : demap4_smem_bytes(threads, lag == 3 ? 3 : (lag == 15 ? 15 : 7)); };
-  if (!use_v3)
+  static const int lag_env = getenv("DABSTAR_DEMAP_LAG") ? atoi(getenv("DABSTAR_DEMAP_LAG")) : 7; // symbols between arithmetic and output (3, 7 or 15)
+  static const int lag = lag_env == 3 ? 3 : (lag_env == 15 ? 15 : 7);
+  const void * fn = lag == 3 ? demap4_fn<3>(soft_bit_type) : (lag == 15 ? demap4_fn<15>(soft_bit_type) : demap4_fn<7>(soft_bit_type));
+  auto smem_bytes = [&](int threads) { return demap4_smem_bytes(threads, lag); };
   {
     static bool attr_set[3] = { false, false, false }; // (per soft-bit type; the lag is fixed for the process)
     if (!attr_set[soft_bit_type])
@@ -1863,7 +1278,7 @@ cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork
   for (int ci = 0; ci < 7; ci++)
   {
     const int sl = cand[ci], threads = DM3_ROW4 / sl;
-    if (!use_v3 && threads > DM4_MAX_THREADS) continue;
+    if (threads > DM4_MAX_THREADS) continue;
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem_bytes(threads)) != cudaSuccess || occ <= 0) continue;
     const int cap = occ * n_sm;                       // CTAs that can be resident at once

@@ -1456,6 +1456,9 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
     R.slot_base = dec->total_slots;
     R.slot_cap = (int)(R.n / T_F) + 2;
     dec->total_slots += R.slot_cap;
+    R.frames.reserve((size_t)R.slot_cap);
+    R.descs.reserve((size_t)R.slot_cap);
+    R.crc_ok.reserve((size_t)R.slot_cap * 12);
     R.pos = 20LL * T_U; // 20 reads of T_u samples for the level estimate, no mixing (f = 0)
     R.state = R.pos <= R.n ? RecState::WAIT_SYNC : RecState::DONE;
     R.ofdm_reset = true;
@@ -1619,6 +1622,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       want = (int)std::min<long long>(want, std::max<long long>(1, budget / std::max<size_t>(1, win_recs.size())));
       want = std::min(want, R.slot_cap - R.n_slots);
       plans.push_back({ r, want, {}, true, R.known_start, 0, 0, 0 });
+      plans.back().fr.reserve((size_t)std::max(want, 1));
     }
     const long long resident = resident_upto();
     bool first_pass = true;

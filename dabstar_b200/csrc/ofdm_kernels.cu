@@ -781,8 +781,18 @@ constexpr int DM4_MAX_THREADS = 384; // at least two slices per recording: leave
 // LAG: symbols between the arithmetic of a symbol and the write of its soft bits (the scale of symbol d is the total of
 // symbol d - 1, which the other warps of the recording publish at their own pace). A longer lag averages the pace of
 // the 24 warps over more symbols before anybody has to wait.
-template <int SOFT, int LAG>
-__global__ void __launch_bounds__(DM4_MAX_THREADS) k_demap4(const DemapWork * __restrict__ work, const FrameDesc * __restrict__ frames,
+// x86 cvttss2si returns 0x80000000 out of range (to_i16): a value the GPU conversion saturated to 0x7fffffff must read 0 in
+// its low half, not 0xffff (start-up transient of SOFTDEC2). Checked once per thread and row; an out-of-line version of
+// the fix-up (so that the loop only tests and branches) was measured and is slower (5.87 against 5.48 ms).
+__device__ __forceinline__ void dm4_fix_saturated(int & a, int & b, int & c, int & e)
+{
+  a = a == 0x7fffffff ? 0 : a; b = b == 0x7fffffff ? 0 : b; c = c == 0x7fffffff ? 0 : c; e = e == 0x7fffffff ? 0 : e;
+}
+
+// TT: threads per CTA when known at compile time (the index arithmetic of the three shared-memory rings folds into shifts
+// and masks), 0 = take blockDim.x.
+template <int SOFT, int LAG, int TT>
+__global__ void __launch_bounds__(TT > 0 ? TT : DM4_MAX_THREADS) k_demap4(const DemapWork * __restrict__ work, const FrameDesc * __restrict__ frames,
                                                      const uint8_t * __restrict__ null_is_tii, const float2 * __restrict__ X,
                                                      const int16_t * __restrict__ rel_of_k, OfdmStateDev * __restrict__ states,
                                                      int16_t * __restrict__ soft, unsigned long long * __restrict__ ring, int slices)
@@ -791,7 +801,7 @@ __global__ void __launch_bounds__(DM4_MAX_THREADS) k_demap4(const DemapWork * __
   static_assert((STASH & (STASH - 1)) == 0, "stash depth must be a power of two");
   static_assert(DM3_RING > 2 * LAG + 2, "a ring slot must not be overwritten while a slower warp may still read it");
   extern __shared__ float4 dm4_smem[]; // [STASH][T] unscaled soft values of the last symbols | [DM4_PF][T] spectrum rows in flight | [STASH][T / 32] output rows
-  const int T = (int)blockDim.x;
+  const int T = TT > 0 ? TT : (int)blockDim.x;
   float4 * stash = dm4_smem;
   float4 * rowbuf = dm4_smem + STASH * T;
   int * orow_ring = reinterpret_cast<int *>(rowbuf + DM4_PF * T) + (threadIdx.x >> 5); // this warp's column: output row (slot * 75 + symbol - 1) of the last STASH symbols
@@ -825,11 +835,9 @@ __global__ void __launch_bounds__(DM4_MAX_THREADS) k_demap4(const DemapWork * __
     cp_async_commit();
   }
 
-  float2 rr = f2(0.f), ri = f2(0.f), ref_abs = f2(0.f), ref_inv = f2(0.f), cterm = f2(0.f);
-  int n_syms = 0, row = 0, fi = 0;
-  int out_row0 = 0;
-  bool tii = false;
+  float2 rr = f2(0.f), ri = f2(0.f), ref_abs = f2(0.f), ref_inv = f2(0.f);
   int g = 0;               // symbols decoded so far; tag of symbol g is g + 1
+  int q = 0;               // spectrum rows consumed so far
   unsigned long long pre = 0; // ring words (lane l < 24: warp l) of the symbol whose total scales this iteration's output
 
   // soft bits of symbol d (its unscaled values are in the stash); total = sum |r| of symbol d - 1 (unused for d = 0)
@@ -838,11 +846,7 @@ __global__ void __launch_bounds__(DM4_MAX_THREADS) k_demap4(const DemapWork * __
     const float4 r = stash[(d & (STASH - 1)) * T + tid]; // (re0, re1, im0, im1)
     const float2 vre = mul2(make_float2(r.x, r.y), f2(w2)), vim = mul2(make_float2(r.z, r.w), f2(w2));
     int a = __float2int_rz(vre.x), b = __float2int_rz(vre.y), c = __float2int_rz(vim.x), e = __float2int_rz(vim.y);
-    if (max(max(a, b), max(c, e)) == 0x7fffffff)
-    {
-      // x86 cvttss2si returns 0x80000000 out of range (to_i16): the saturated positive case must read 0, not 0xffff
-      a = a == 0x7fffffff ? 0 : a; b = b == 0x7fffffff ? 0 : b; c = c == 0x7fffffff ? 0 : c; e = e == 0x7fffffff ? 0 : e;
-    }
+    if (max(max(a, b), max(c, e)) == 0x7fffffff) dm4_fix_saturated(a, b, c, e);
     unsigned * o = reinterpret_cast<unsigned *>(soft + (size_t)o_row * SYM_BITS);
     o[t_rec] = __byte_perm((unsigned)a, (unsigned)b, 0x5410);
     o[K_CARR / 2 + t_rec] = __byte_perm((unsigned)c, (unsigned)e, 0x5410);
@@ -853,78 +857,89 @@ __global__ void __launch_bounds__(DM4_MAX_THREADS) k_demap4(const DemapWork * __
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
   };
-  float part_prev = 0.0f; // this thread's |r| sum of symbol g - 1, published (reduced over the warp) one symbol late
-  const bool upper = (lane & 16) != 0;
-
-  for (int q = 0; q < total_rows; q++)
-  {
+  // the next spectrum row of this thread (its load was requested DM4_PF rows ago); requests row q + DM4_PF
+  auto next_row = [&]() {
     cp_async_wait<DM4_PF - 1>();
     const unsigned slot = (unsigned)((q & (DM4_PF - 1)) * T);
     const float4 cur = rowbuf[slot + tid];
     if (q + DM4_PF < total_rows) cp_async16(rowbuf_addr + slot * 16u, rows + (size_t)(q + DM4_PF) * DM3_ROW4);
     cp_async_commit();
-    const float2 xr = make_float2(cur.x, cur.y), xi = make_float2(cur.z, cur.w); // X rows hold (re 2t, re 2t+1, im 2t, im 2t+1): register pairs as loaded
-    if (row == 0)
+    q++;
+    return cur;
+  };
+  // this row is the phase reference of the next symbol
+  auto set_reference = [&](float2 xr, float2 xi) {
+    rr = xr;
+    ri = xi;
+    const float2 p = fma2(xr, xr, mul2(xi, xi));
+    ref_inv = make_float2(rsqrt_ftz(p.x), rsqrt_ftz(p.y));
+    ref_abs = mul2(p, ref_inv);
+  };
+  float part_prev = 0.0f; // this thread's |r| sum of symbol g - 1, published (reduced over the warp) one symbol late
+  const bool upper = (lane & 16) != 0;
+
+  for (int fi = 0; fi < wk.n_frames; fi++)
+  {
+    const FrameDesc fd = frames[wk.desc_first + fi];
+    const float2 cterm = mul2(f2(fd.clock_err / 1024.0f * PI_F), gk);
+    const int n_syms = fd.n_syms;
+    const int out_row0 = fd.slot * 75;
+    const bool tii = null_is_tii != nullptr && null_is_tii[wk.desc_first + fi];
     {
-      const FrameDesc fd = frames[wk.desc_first + fi];
-      cterm = mul2(f2(fd.clock_err / 1024.0f * PI_F), gk);
-      n_syms = fd.n_syms;
-      out_row0 = fd.slot * 75;
-      tii = null_is_tii != nullptr && null_is_tii[wk.desc_first + fi];
+      const float4 cur = next_row(); // X rows hold (re 2t, re 2t+1, im 2t, im 2t+1): register pairs as loaded
+      set_reference(make_float2(cur.x, cur.y), make_float2(cur.z, cur.w)); // store_reference_symbol_0
     }
-    if (row == 0 || row <= n_syms)
+    for (int sym = 1; sym <= 75; sym++)
     {
-      if (row > 0)
-      {
-        const int d = g - LAG; // symbol whose soft bits are written in this iteration
-        // ONE shuffle chain, independent of this symbol's arithmetic (the scheduler overlaps the two), reduces two values:
-        // a: this warp's share of sum |r| of the PREVIOUS symbol, published under tag g (lower half warp);
-        // b: the total of symbol d - 1 from the ring words fetched one iteration ago (upper half warp; valid if every tag reads d).
-        // After the first exchange the lower lanes hold a[l] + a[l + 16], the upper ones b[l] + b[l - 16]; the remaining
-        // four steps stay inside a half, so both sums come out exactly as two separate butterflies would give them.
-        const float b_in = lane < DM3_WARPS ? __uint_as_float((unsigned)pre) : 0.0f;
-        const bool tags_ok = __all_sync(0xffffffffu, lane >= DM3_WARPS || (unsigned)(pre >> 32) == (unsigned)d);
-        const unsigned long long pre_used = pre;
-        // ring words for the NEXT iteration's output (symbol d + 1 is scaled by the total of symbol d, published at
-        // iteration d + 1 of every warp): requested now, a whole iteration before they are looked at
-        if (d >= 0 && lane < DM3_WARPS) pre = ld_volatile_global_b64(my_ring + (size_t)(d & (DM3_RING - 1)) * DM3_WARPS + lane);
-        float v = (upper ? b_in : part_prev) + __shfl_xor_sync(0xffffffffu, upper ? part_prev : b_in, 16);
+      const float4 cur = next_row();
+      if (sym > n_syms) continue; // the recording ends inside this frame
+      const float2 xr = make_float2(cur.x, cur.y), xi = make_float2(cur.z, cur.w);
+      const int d = g - LAG; // symbol whose soft bits are written in this iteration
+      // ONE shuffle chain, independent of this symbol's arithmetic (the scheduler overlaps the two), reduces two values:
+      // a: this warp's share of sum |r| of the PREVIOUS symbol, published under tag g (lower half warp);
+      // b: the total of symbol d - 1 from the ring words fetched one iteration ago (upper half warp; valid if every tag reads d).
+      // After the first exchange the lower lanes hold a[l] + a[l + 16], the upper ones b[l] + b[l - 16]; the remaining
+      // four steps stay inside a half, so both sums come out exactly as two separate butterflies would give them.
+      const float b_in = lane < DM3_WARPS ? __uint_as_float((unsigned)pre) : 0.0f;
+      const bool tags_ok = __all_sync(0xffffffffu, lane >= DM3_WARPS || (unsigned)(pre >> 32) == (unsigned)d);
+      const unsigned long long pre_used = pre;
+      // ring words for the NEXT iteration's output (symbol d + 1 is scaled by the total of symbol d, published at
+      // iteration d + 1 of every warp): requested now, a whole iteration before they are looked at
+      if (d >= 0 && lane < DM3_WARPS) pre = ld_volatile_global_b64(my_ring + (size_t)(d & (DM3_RING - 1)) * DM3_WARPS + lane);
+      float v = (upper ? b_in : part_prev) + __shfl_xor_sync(0xffffffffu, upper ? part_prev : b_in, 16);
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        const float tot_fast = __shfl_sync(0xffffffffu, v, 16);
-        float2 o_re, o_im, r_abs;
-        dm4_pair<SOFT>(st, xr, xi, rr, ri, ref_abs, ref_inv, cterm, o_re, o_im, r_abs, pow_acc);
-        part_prev = r_abs.x + r_abs.y;
-        stash[(g & (STASH - 1)) * T + tid] = make_float4(o_re.x, o_re.y, o_im.x, o_im.y);
-        if (lane == 0) orow_ring[(g & (STASH - 1)) * (T >> 5)] = out_row0 + (row - 1);
-        __syncwarp();
-        // (the store sits behind the arithmetic so that the chain above shares a basic block with it)
-        if (lane == 0 && g > 0)
-          st_volatile_global_b64(my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM3_WARPS + gw,
-                                 ((unsigned long long)(unsigned)g << 32) | (unsigned long long)__float_as_uint(v));
-        if (d >= 0)
-        {
-          float tot = tot_fast;
-          if (d > 0 && !tags_ok) tot = dm3_total(my_ring + (size_t)((d - 1) & (DM3_RING - 1)) * DM3_WARPS, pre_used, (unsigned)d, lane);
-          emit(d, orow_ring[(d & (STASH - 1)) * (T >> 5)], tot);
-        }
-        g++;
+      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      const float tot_fast = __shfl_sync(0xffffffffu, v, 16);
+      float2 o_re, o_im, r_abs;
+      dm4_pair<SOFT>(st, xr, xi, rr, ri, ref_abs, ref_inv, cterm, o_re, o_im, r_abs, pow_acc);
+      part_prev = r_abs.x + r_abs.y;
+      stash[(g & (STASH - 1)) * T + tid] = make_float4(o_re.x, o_re.y, o_im.x, o_im.y);
+      if (lane == 0) orow_ring[(g & (STASH - 1)) * (T >> 5)] = out_row0 + (sym - 1);
+      __syncwarp();
+      // (the store sits behind the arithmetic so that the chain above shares a basic block with it)
+      if (lane == 0 && g > 0)
+        st_volatile_global_b64(my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM3_WARPS + gw,
+                               ((unsigned long long)(unsigned)g << 32) | (unsigned long long)__float_as_uint(v));
+      if (d >= 0)
+      {
+        float tot = tot_fast;
+        if (d > 0 && !tags_ok) tot = dm3_total(my_ring + (size_t)((d - 1) & (DM3_RING - 1)) * DM3_WARPS, pre_used, (unsigned)d, lane);
+        emit(d, orow_ring[(d & (STASH - 1)) * (T >> 5)], tot);
       }
-      // this row is the phase reference of the next symbol
-      rr = xr;
-      ri = xi;
-      const float2 p = fma2(xr, xr, mul2(xi, xi));
-      ref_inv = make_float2(rsqrt_ftz(p.x), rsqrt_ftz(p.y));
-      ref_abs = mul2(p, ref_inv);
+      g++;
+      set_reference(xr, xi);
     }
-    else if (row == X_ROWS - 1 && n_syms == 75 && !tii)
     {
-      // store_null_symbol_without_tii (ofdm_decoder.cpp:114-130)
-      constexpr float MIN_POW = (1.0f / 32767.0f) * (1.0f / 32767.0f);
-      const float2 p = add2(fma2(xr, xr, mul2(xi, xi)), f2(MIN_POW));
-      st.null_pow = fma2(add2(p, neg2(st.null_pow)), f2(0.05f), st.null_pow);
+      const float4 cur = next_row(); // null symbol
+      if (n_syms == 75 && !tii)
+      {
+        // store_null_symbol_without_tii (ofdm_decoder.cpp:114-130)
+        constexpr float MIN_POW = (1.0f / 32767.0f) * (1.0f / 32767.0f);
+        const float2 xr = make_float2(cur.x, cur.y), xi = make_float2(cur.z, cur.w);
+        const float2 p = add2(fma2(xr, xr, mul2(xi, xi)), f2(MIN_POW));
+        st.null_pow = fma2(add2(p, neg2(st.null_pow)), f2(0.05f), st.null_pow);
+      }
     }
-    if (++row == X_ROWS) { row = 0; fi++; }
   }
   cp_async_wait<0>();
   // the last symbol's share has not been published yet
@@ -1238,9 +1253,18 @@ cudaError_t launch_reorder_frames(cudaStream_t s, const DeviceTables & t, const 
 
 size_t demap_ring_bytes(int n_work) { return sizeof(unsigned long long) * (size_t)std::max(n_work, 1) * DM3_RING * DM3_WARPS; }
 static size_t demap4_smem_bytes(int threads, int lag) { return sizeof(float4) * (size_t)(lag + 1 + DM4_PF) * (size_t)threads + sizeof(int) * (size_t)(lag + 1) * (size_t)(threads / 32); }
-template <int LAG> static const void * demap4_fn(int soft_bit_type)
+template <int LAG, int TT> static const void * demap4_fn(int soft_bit_type)
 {
-  return soft_bit_type == 0 ? (const void *)k_demap4<0, LAG> : (soft_bit_type == 1 ? (const void *)k_demap4<1, LAG> : (const void *)k_demap4<2, LAG>);
+  return soft_bit_type == 0 ? (const void *)k_demap4<0, LAG, TT> : (soft_bit_type == 1 ? (const void *)k_demap4<1, LAG, TT> : (const void *)k_demap4<2, LAG, TT>);
+}
+// the instantiation for a lag and a CTA size (compile-time sizes for the default lag's common slicings, else blockDim.x)
+static const void * demap4_fn_for(int lag, int threads, int soft_bit_type)
+{
+  if (lag == 3) return demap4_fn<3, 0>(soft_bit_type);
+  if (lag == 7) return demap4_fn<7, 0>(soft_bit_type);
+  if (threads == 256) return demap4_fn<15, 256>(soft_bit_type);
+  if (threads == 384) return demap4_fn<15, 384>(soft_bit_type);
+  return demap4_fn<15, 0>(soft_bit_type);
 }
 
 cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork * work, int n_work, const FrameDesc * frames,
@@ -1255,17 +1279,15 @@ cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork
   // words to the warp through cp.async as well (requested 8 symbols ahead) was measured at 5.67 ms and dropped.
   static const int lag_env = getenv("DABSTAR_DEMAP_LAG") ? atoi(getenv("DABSTAR_DEMAP_LAG")) : 15;
   static const int lag = lag_env == 3 ? 3 : (lag_env == 7 ? 7 : 15);
-  const void * fn = lag == 3 ? demap4_fn<3>(soft_bit_type) : (lag == 15 ? demap4_fn<15>(soft_bit_type) : demap4_fn<7>(soft_bit_type));
   auto smem_bytes = [&](int threads) { return demap4_smem_bytes(threads, lag); };
-  {
-    static bool attr_set[3] = { false, false, false }; // (per soft-bit type; the lag is fixed for the process)
-    if (!attr_set[soft_bit_type])
-    {
-      cudaError_t ea = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(DM4_MAX_THREADS));
-      if (ea != cudaSuccess) return ea;
-      attr_set[soft_bit_type] = true;
-    }
-  }
+  // every instantiation needs the opt-in for its dynamic shared memory once
+  auto prepared = [&](const void * fn) -> cudaError_t {
+    static std::vector<const void *> done;
+    if (std::find(done.begin(), done.end(), fn) != done.end()) return cudaSuccess;
+    cudaError_t ea = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(DM4_MAX_THREADS));
+    if (ea == cudaSuccess) done.push_back(fn);
+    return ea;
+  };
   // slices per recording: fill the SMs as evenly as the co-residency limit allows
   static int n_sm = 0;
   if (n_sm == 0)
@@ -1282,7 +1304,9 @@ cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork
     const int sl = cand[ci], threads = DM3_ROW4 / sl;
     if (threads > DM4_MAX_THREADS) continue;
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem_bytes(threads)) != cudaSuccess || occ <= 0) continue;
+    const void * fn_c = demap4_fn_for(lag, threads, soft_bit_type);
+    if (cudaError_t ea = prepared(fn_c)) return ea;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn_c, threads, smem_bytes(threads)) != cudaSuccess || occ <= 0) continue;
     const int cap = occ * n_sm;                       // CTAs that can be resident at once
     const int per_launch = cap / sl;                  // recordings per launch
     if (per_launch <= 0) continue;
@@ -1294,6 +1318,7 @@ cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork
   }
   if (best_s == 0) return cudaErrorLaunchOutOfResources;
   const int threads = DM3_ROW4 / best_s, per_launch = std::max(1, best_cap / best_s);
+  const void * fn = demap4_fn_for(lag, threads, soft_bit_type);
   cudaError_t e = cudaMemsetAsync(ring, 0, demap_ring_bytes(n_work), s);
   for (int first = 0; first < n_work && e == cudaSuccess; first += per_launch)
   {

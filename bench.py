@@ -196,6 +196,27 @@ def viterbi_sweep(ctx, stream, n_frames):
     return out
 
 
+def pin_to_gpu_cpus(local_rank, world):
+    """One host control loop per GPU: keep each rank on the CPUs NVML reports as local to its GPU (its NUMA node), and inside
+    that set on its own share, so that the ranks do not migrate across sockets or onto each other."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        local = [c for c in range(n_cpu) if (words[c // 64] >> (c % 64)) & 1]
+        allowed = sorted(set(local) & set(os.sched_getaffinity(0))) or sorted(os.sched_getaffinity(0))
+        # ranks whose GPUs share this CPU set split it evenly
+        same = [r for r in range(world) if list(pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(r), (n_cpu + 63) // 64)) == list(words)]
+        k, i = max(1, len(allowed) // max(1, len(same))), same.index(local_rank) if local_rank in same else 0
+        mine = allowed[i * k:(i + 1) * k] or allowed
+        os.sched_setaffinity(0, mine)
+        return len(mine)
+    except Exception:
+        return None
+
+
 def native_arm(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -206,6 +227,7 @@ def native_arm(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pinned_cpus = pin_to_gpu_cpus(local_rank, world) if world > 1 and not args.no_cpu_affinity else None
     R, F = args.recordings, args.frames
     n_samples = 60000 + F * T_F + 4096
 
@@ -346,7 +368,7 @@ def native_arm(args, rank, local_rank, world):
         "data": f"synthetic ({unique} unique recordings per GPU of {R}, random FIB payloads, AWGN {args.snr} dB)",
         "config": {"workload": "configs[1] FIC-only decode of a 10k-frame batch", "recordings_per_gpu": R, "frames_per_recording": F,
                    "frames_per_step_all_gpus": total_frames, "input": "u8 IQ 2.048 MS/s", "input_bytes_per_gpu": int(R * n_samples * 2),
-                   "l2": "inputs (3.9 GB) and intermediates far exceed the 126 MB L2", "window": args.window,
+                   "l2": "inputs (3.9 GB) and intermediates far exceed the 126 MB L2", "window": args.window, "cpus_per_rank": pinned_cpus,
                    "fib_crc_pass": good_fibs / max(1.0, 12.0 * frames_per_step),
                    "windows_per_recording": float(cnt[4]) / R, "frames_through_heavy_pass": int(cnt[7]), "x_real_time": value / world / (2048000 / T_F)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(R * n_samples * 2), "d2h_bytes_per_step": int(frames_per_step * 384),
@@ -372,6 +394,7 @@ def main():
     ap.add_argument("--synth-budget", type=float, default=45.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-viterbi-sweep", action="store_true")
+    ap.add_argument("--no-cpu-affinity", action="store_true", help="N > 1: do not pin each rank to the CPUs local to its GPU")
     ap.add_argument("--viterbi-frames", type=int, default=32768, help="logical frames per protection level in the Viterbi-only sweep")
     ap.add_argument("--cpu-worker", action="store_true")
     ap.add_argument("--cpu-lib", default="dabo")

@@ -6,6 +6,8 @@
 //     -c  containers: every file's header is inspected (RIFF/WAVE .wav / .sdr, XML .uff, else raw u8); samples are converted and
 //         resampled to 2.048 MS/s as the reference's file readers do
 //     -a  self-configuration: sub-channels from the recording's FIG 0/1 (no -s needed)
+//     -t  with -a: TII detection on the null symbols the recording's CIF counter selects (5 per search, threshold 8 dB), and those
+//         null symbols leave the demapper's null power alone, as in the reference with its FIB decoder running
 //     -e  also write the ETI(NI) stream, <prefix><n>.eti (what DABstar's ETI generator writes)
 //
 // The reference can only play files through its GUI, paced to real time (raw_reader.cpp:153-165); this harness feeds
@@ -35,7 +37,7 @@ static std::vector<unsigned char> read_file(const char * path)
 int main(int argc, char ** argv)
 {
   int fmt = DABSTAR_FMT_U8;
-  bool autoCfg = false, eti = false, xml = false, containers = false;
+  bool autoCfg = false, eti = false, xml = false, containers = false, tii = false;
   dabstar_sample_format sf{};
   std::string prefix = "dab_out_";
   std::vector<dabstar_subch> subch;
@@ -46,6 +48,7 @@ int main(int argc, char ** argv)
     if (a == "-f" && i + 1 < argc) { const std::string v = argv[++i]; fmt = v == "i16" ? DABSTAR_FMT_I16 : (v == "cf32" ? DABSTAR_FMT_CF32 : DABSTAR_FMT_U8); }
     else if (a == "-o" && i + 1 < argc) prefix = argv[++i];
     else if (a == "-a") autoCfg = true;
+    else if (a == "-t") tii = true;
     else if (a == "-c") { containers = true; fmt = DABSTAR_FMT_CF32; }
     else if (a == "-e") eti = true;
     else if (a == "-x" && i + 1 < argc)
@@ -99,7 +102,8 @@ int main(int argc, char ** argv)
     dabstar::DabProcessor proc(ctx, (int)files.size(), fmt, subch.empty() && !autoCfg);
     for (size_t r = 0; r < files.size(); r++)
     {
-      if (autoCfg) proc.set_auto_config((int)r);
+      if (autoCfg) proc.set_auto_config((int)r, true, tii);
+      if (autoCfg && tii) proc.set_tii_processing((int)r, true);
       else proc.set_audio_channel((int)r, subch);
       if (eti) proc.start_eti_generator((int)r);
     }
@@ -140,6 +144,11 @@ int main(int argc, char ** argv)
       if (fic) fclose(fic);
       for (FILE * o : outs) if (o) fclose(o);
       printf("%s: %d frames, %ld good FIBs, %.2f ms device time\n", files[r], proc.n_frames((int)r), fibs, proc.last_ms());
+      if (autoCfg && tii)
+        for (const auto & ev : proc.tii_events((int)r))
+          for (const auto & id : ev.transmitterIds)
+            printf("%s: frame %d: TII main id %d sub id %d strength %.2f phase %.0f deg%s\n", files[r], ev.frame, id.main_id, id.sub_id, id.strength, id.phase_deg,
+                   id.non_etsi ? " (non-ETSI phases)" : "");
       if (proc.n_frames((int)r) > 0)
       {
         const dabstar::SLcdData q = proc.lcd_data((int)r);

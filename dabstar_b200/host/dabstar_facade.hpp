@@ -274,6 +274,39 @@ struct SLcdData
   f32 MER, SNR, MeanValue, MeanPowerOvrAll, NoisePower, MeanSigmaSqFreqCorr;
 };
 
+// ofdm/tii_detector.h:30-45 for nDetectors recordings at once (STiiResult = dabstar_tii_result).
+class TiiDetector
+{
+public:
+  explicit TiiDetector(Context & c, int nDetectors = 1) : mC(c), mN(nDetectors) { c.check(dabstar_tii_create(c.get(), nDetectors, &mT), "dabstar_tii_create"); }
+  ~TiiDetector() { dabstar_tii_destroy(mT); }
+  TiiDetector(const TiiDetector &) = delete;
+  TiiDetector & operator=(const TiiDetector &) = delete;
+  void reset() { mC.check(dabstar_tii_reset(mT), "dabstar_tii_reset"); }
+  void set_detect_collisions(bool b) { mColl = b; mC.check(dabstar_tii_set_collisions(mT, mColl ? 1 : 0, mSubId), "dabstar_tii_set_collisions"); }
+  void set_subid_for_collision_search(u8 subId) { mSubId = subId; mC.check(dabstar_tii_set_collisions(mT, mColl ? 1 : 0, mSubId), "dabstar_tii_set_collisions"); }
+  // iV: nDetectors x nSymbols x 2048 null-symbol spectra in fft order (the reference adds one spectrum per call)
+  void add_to_tii_buffer(const cf32 * iV, int nSymbols = 1) { mC.check(dabstar_tii_add(mT, reinterpret_cast<const float *>(iV), nSymbols, DABSTAR_MEM_HOST), "dabstar_tii_add"); }
+  // per detector: the transmitters found, strongest first
+  std::vector<std::vector<dabstar_tii_result>> process_tii_data(i16 iThreshold_db)
+  {
+    constexpr int cap = 128;
+    std::vector<dabstar_tii_result> buf((size_t)mN * cap);
+    std::vector<int32_t> cnt((size_t)mN);
+    mC.check(dabstar_tii_process(mT, iThreshold_db, buf.data(), cap, cnt.data()), "dabstar_tii_process");
+    std::vector<std::vector<dabstar_tii_result>> out((size_t)mN);
+    for (int d = 0; d < mN; d++) out[d].assign(buf.begin() + (size_t)d * cap, buf.begin() + (size_t)d * cap + std::min(cnt[d], cap));
+    return out;
+  }
+
+private:
+  Context & mC;
+  int mN;
+  dabstar_tii * mT = nullptr;
+  bool mColl = false;
+  u8 mSubId = 0;
+};
+
 // Frame granular: one call = store_reference_symbol_0 + 75 x decode_symbol + store_null_symbol_without_tii.
 class OfdmDecoder
 {
@@ -364,6 +397,26 @@ public:
     return v;
   }
   int n_frames(int recording) const { return dabstar_decoder_n_frames(mDec, recording); }
+  // DabProcessor::set_tii_processing / set_tii_threshold / set_tii_collisions / set_tii_sub_id (+ ProcessParams::tiiFramesToCount);
+  // needs set_auto_config: the recording's own CIF counter decides which null symbols carry TII
+  void set_tii_processing(int recording, bool on, int framesToCount = 5, int thresholdDb = 8, bool collisions = false, int subId = 0)
+  {
+    mC.check(dabstar_decoder_enable_tii(mDec, recording, on ? 1 : 0, framesToCount, thresholdDb, collisions ? 1 : 0, subId), "dabstar_decoder_enable_tii");
+  }
+  struct TiiEvent { int frame; std::vector<dabstar_tii_result> transmitterIds; };
+  std::vector<TiiEvent> tii_events(int recording) const // what signal_show_tii would have carried, one entry per search
+  {
+    std::vector<TiiEvent> ev((size_t)std::max(0, dabstar_decoder_tii_events(mDec, recording)));
+    for (size_t e = 0; e < ev.size(); e++)
+    {
+      int32_t frame = 0;
+      ev[e].transmitterIds.resize(128);
+      const int n = dabstar_decoder_tii_results(mDec, recording, (int)e, ev[e].transmitterIds.data(), 128, &frame);
+      ev[e].transmitterIds.resize((size_t)std::max(0, std::min(n, 128)));
+      ev[e].frame = frame;
+    }
+    return ev;
+  }
   SLcdData lcd_data(int recording) const // the recording's OfdmDecoder figures at the end of the run
   {
     float q[6];

@@ -150,3 +150,25 @@ def test_tii_null_symbols_leave_the_null_power_alone(ctx, oracle):
     plain = oracle.chain_run(oracle.to_cf32(recs[0].iq), synth.subch_table(sc), 1, tap_soft=True)
     assert sum(int((dp.soft_bits(0, f) != plain.soft_bits(f)).sum()) for f in range(3, 10)) > 1000
     plain.close()
+
+
+def test_cpp_harness_reports_tii(ctx, tmp_path):
+    """The C++ facade (DabProcessor::set_tii_processing / tii_events) through the headless harness: -a -t on a recording whose
+    transmitter sends TII prints the identification found in the null symbols its CIF counter selects."""
+    import shutil, subprocess
+    from dabstar_b200 import synth
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "dab_file_decode")
+    subprocess.run(["g++", "-std=c++17", "-O2", os.path.join(root, "dabstar_b200", "host", "dab_file_decode.cpp"), "-I", os.path.join(root, "include"),
+                    "-L", os.path.join(root, "dabstar_b200"), "-ldabstar_b200", "-Wl,-rpath," + os.path.join(root, "dabstar_b200"), "-o", exe], check=True)
+    sc = [synth.SubChannel(3, 100, 54, 0, 2, 72)]
+    rec = synth.generate(22, seed=71, snr_db=18.0, subch=sc, fmt=synth.FMT_U8, fig_mode=1, tii=(12, 5))
+    path = str(tmp_path / "rec.iq")
+    rec.iq.tofile(path)
+    r = subprocess.run([exe, "-f", "u8", "-a", "-t", "-o", str(tmp_path / "o_"), path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if "TII main id" in l]
+    assert len(lines) == 2 and all("TII main id 12 sub id 5" in l for l in lines), r.stdout  # five TII null symbols per search: frames 9 and 19
+    assert "frame 9:" in lines[0] and "frame 19:" in lines[1]

@@ -161,7 +161,7 @@ SWEEP_PROFILES = [("EEP 1-A 72k", 0, 0, 72, 108), ("EEP 2-A 72k", 0, 1, 72, 72),
                   ("UEP 5 128k", 1, 5, 128, 64)]
 
 
-def viterbi_sweep(ctx, stream, n_frames):
+def viterbi_sweep(ctx, stream, n_frames, sm_mhz=1965.0):
     """Protection::deconvolve over n_frames logical frames per protection level; times 3 launches after 1 warm-up with CUDA events."""
     import ctypes
     import torch
@@ -189,7 +189,9 @@ def viterbi_sweep(ctx, stream, n_frames):
         ms = e0.elapsed_time(e1) / 3
         info_bits = n_frames * 24 * br
         acs = n_frames * 64 * (24 * br + 6)
-        out["levels"][name] = {"ms": ms, "mbit_s": info_bits / ms / 1e3, "gacs": acs / ms / 1e6}
+        # integer-ALU issue roofline: 148 SMs x 128 lanes x f_clk / 4 lane-ops per add-compare-select
+        out["levels"][name] = {"ms": ms, "mbit_s": info_bits / ms / 1e3, "gacs": acs / ms / 1e6,
+                               "frac_int_alu": (acs / ms / 1e6) / (148 * 128 * sm_mhz * 1e6 / 4.0 / 1e9)}
         tot_bits += info_bits
         tot_ms += ms
     out["mbit_s_overall"] = tot_bits / tot_ms / 1e3
@@ -298,7 +300,7 @@ def native_arm(args, rank, local_rank, world):
         #      resident in HBM), the "Viterbi Mbit/s" half of the metric; bounded batch, rank 0's GPU only
         vit_sweep = None
         if rank == 0 and not args.no_viterbi_sweep:
-            vit_sweep = viterbi_sweep(ctx, stream, args.viterbi_frames)
+            vit_sweep = viterbi_sweep(ctx, stream, args.viterbi_frames, clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0)
 
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
     fr = torch.tensor([frames_per_step], dtype=torch.float64, device="cuda")

@@ -397,7 +397,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-viterbi-sweep", action="store_true")
     ap.add_argument("--no-cpu-affinity", action="store_true", help="N > 1: do not pin each rank to the CPUs local to its GPU")
-    ap.add_argument("--viterbi-frames", type=int, default=32768, help="logical frames per protection level in the Viterbi-only sweep")
+    ap.add_argument("--viterbi-frames", type=int, default=131072, help="logical frames per protection level in the Viterbi-only sweep")
     ap.add_argument("--cpu-worker", action="store_true")
     ap.add_argument("--cpu-lib", default="dabo")
     args = ap.parse_args()

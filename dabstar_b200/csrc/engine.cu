@@ -666,7 +666,9 @@ extern "C" int dabstar_fft2048(dabstar_ctx * ctx, const float * in, float * out,
 // Workspace of the thread-per-code-word Viterbi: what one launch needs, capped (the launcher then works in chunks).
 static int reserve_viterbi_ws(dabstar_ctx * ctx, int n_jobs, int max_steps)
 {
-  const size_t cap = (size_t)3 << 29; // 1.5 GiB
+  // 6 GiB of the 180 GB: about 125 000 of the longest MSC code words (3078 steps x 16 B) per launch, i.e. four warps per scheduler
+  // (the kernel's register limit); a 1.5 GiB cap left a launch at 1.7 warps per scheduler (ncu: 33 % of the stall samples on loads)
+  const size_t cap = (size_t)6 << 30;
   CK(ctx->vit_ws.reserve(std::min(viterbi_ws_bytes(n_jobs, max_steps), cap)));
   return 0;
 }

@@ -996,7 +996,7 @@ struct MscOut
   dabstar_subch sc;
   int profile = -1;
   int first_seen = 0;   // frame whose FIC first described the sub-channel (self-configuration; 0 when set by the caller)
-  std::vector<uint8_t> bits;
+  long long out_off = 0, out_len = 0; // this sub-channel's decoded bits of the last run: bit range in the packed read-back buffer
 };
 
 struct Recording
@@ -1062,8 +1062,10 @@ struct dabstar_decoder
   DevBuf d_snap;        // snapshot of d_states
   DevBuf d_desc, d_work, d_cp, d_start, d_coarse, d_dipw, d_dipr, d_jobs, d_mscbits, d_etibits, d_etipacked;
   DevBuf d_tii_fft;   // null-symbol spectra of one TII event, fft order
+  DevBuf d_mscpacked; // MSC payload packed 8 bits per byte for the read-back
   DevBuf d_fibp;      // FIB bits packed 8 per byte for the read-back (384 bytes per frame)
   DevBuf d_tii_flags; // per descriptor: the frame's null symbol is a TII symbol
+  HostBuf h_mscp; // MSC payload of the last run, packed 8 bits per byte
   HostBuf h_fib, h_crc, h_fibp; // h_fib: FIB bits of the self-configuration pass (one per byte); h_fibp: all FIBs of the run, packed 8 bits per byte
   std::vector<int16_t> h_soft_one;
   long long total_slots = 0;
@@ -1452,7 +1454,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
     R.eti_on = eti_on;
     R.eti_cif_hi = eti_hi;
     R.eti_cif_lo = eti_lo;
-    for (auto & m : R.msc) m.bits.clear();
+    for (auto & m : R.msc) { m.out_off = 0; m.out_len = 0; }
     R.d_iq = rin[r].iq;
     R.n = rin[r].n;
     R.slot_base = dec->total_slots;
@@ -2166,8 +2168,6 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
   {
     std::map<int, std::vector<VitJob>> by_steps; // group launches by code-word length (shared-memory footprint)
     long long out_total = 0;
-    struct OutRef { int rec, ch; long long off, len; };
-    std::vector<OutRef> outs;
     for (int r = 0; r < n_rec; r++)
     {
       Recording & R = dec->recs[r];
@@ -2178,10 +2178,10 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
         const VitProfile & p = ctx->profiles[m.profile];
         const int g_start = 4 * m.sc.start_frame;
         const int n_out = std::max(0, n_cifs - (g_start + 16));
-        m.bits.assign((size_t)n_out * p.n_bits, 0);
+        m.out_off = out_total;
+        m.out_len = (long long)n_out * p.n_bits;
         if (n_out == 0) continue;
         make_backend_jobs(by_steps[p.n_bits + 6], m.profile, p, R.slot_base * FRAME_SOFT, g_start, 0, n_cifs, m.sc.start_cu, out_total);
-        outs.push_back({ r, (int)c, out_total, (long long)n_out * p.n_bits });
         out_total += (long long)n_out * p.n_bits;
       }
     }
@@ -2195,8 +2195,13 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
         dec->span_end();
         SYNC(); // d_jobs is reused by the next group
       }
-      for (auto & o : outs)
-        CK(cudaMemcpyAsync(dec->recs[o.rec].msc[o.ch].bits.data(), dec->d_mscbits.as<uint8_t>() + o.off, (size_t)o.len, cudaMemcpyDeviceToHost, st));
+      // the payload leaves the device packed 8 bits per byte in ONE copy into pinned memory (every logical frame is a whole
+      // number of bytes: 24 x bit rate bits); dabstar_decoder_msc_copy unpacks a sub-channel on request. One pageable copy
+      // per sub-channel and recording of the bits as bytes cost 220 ms per 10 000 full-ensemble frames, 7 x the kernels.
+      CK(dec->d_mscpacked.reserve((size_t)(out_total / 8)));
+      CK(dec->h_mscp.reserve((size_t)(out_total / 8)));
+      CK(launch_pack_bits(st, dec->d_mscbits.as<uint8_t>(), dec->d_mscpacked.as<uint8_t>(), out_total / 8, &ctx->launches));
+      CK(cudaMemcpyAsync(dec->h_mscp.p, dec->d_mscpacked.p, (size_t)(out_total / 8), cudaMemcpyDeviceToHost, st));
     }
   }
   // ================= ETI: every sub-channel of every CIF through EtiGenerator's own de-interleaver (eti_generator.cpp:90-204)
@@ -2416,14 +2421,30 @@ static const MscOut * find_msc(const dabstar_decoder * dec, int recording, int s
 extern "C" int64_t dabstar_decoder_msc_size(const dabstar_decoder * dec, int recording, int sub_ch_id)
 {
   const MscOut * m = find_msc(dec, recording, sub_ch_id);
-  return m ? (int64_t)m->bits.size() : 0;
+  return m ? (int64_t)m->out_len : 0;
 }
 extern "C" int64_t dabstar_decoder_msc_copy(const dabstar_decoder * dec, int recording, int sub_ch_id, uint8_t * out, int64_t cap)
 {
   const MscOut * m = find_msc(dec, recording, sub_ch_id);
   if (!m || !out) return 0;
-  const int64_t n = std::min<int64_t>(cap, (int64_t)m->bits.size());
-  memcpy(out, m->bits.data(), (size_t)n);
+  const int64_t n = std::min<int64_t>(cap, (int64_t)m->out_len);
+  const uint8_t * p = dec->h_mscp.as<uint8_t>() + m->out_off / 8; // (out_off is a multiple of 8: whole logical frames precede it)
+  const int64_t whole = n >> 3;
+  for (int64_t b = 0; b < whole; b++)
+  {
+    const unsigned v = p[b];
+    uint8_t * o = out + 8 * b;
+    o[0] = (uint8_t)(v >> 7); o[1] = (v >> 6) & 1; o[2] = (v >> 5) & 1; o[3] = (v >> 4) & 1; o[4] = (v >> 3) & 1; o[5] = (v >> 2) & 1; o[6] = (v >> 1) & 1; o[7] = v & 1;
+  }
+  for (int64_t i = 8 * whole; i < n; i++) out[i] = (uint8_t)((p[i >> 3] >> (7 - (i & 7))) & 1u);
+  return n;
+}
+extern "C" int64_t dabstar_decoder_msc_packed(const dabstar_decoder * dec, int recording, int sub_ch_id, uint8_t * out, int64_t cap)
+{
+  const MscOut * m = find_msc(dec, recording, sub_ch_id);
+  if (!m || !out) return 0;
+  const int64_t n = std::min<int64_t>(cap, (int64_t)(m->out_len / 8));
+  memcpy(out, dec->h_mscp.as<uint8_t>() + m->out_off / 8, (size_t)n);
   return n;
 }
 extern "C" int dabstar_decoder_counters(const dabstar_decoder * dec, int recording, int64_t out[8])

@@ -342,6 +342,10 @@ int     dabstar_decoder_soft_bits(const dabstar_decoder * dec, int recording, in
 int64_t dabstar_decoder_msc_size(const dabstar_decoder * dec, int recording, int sub_ch_id);
 /* FrameProcessor::add_to_frame payloads (backend/frame_processor.h:43), concatenated, one bit per byte */
 int64_t dabstar_decoder_msc_copy(const dabstar_decoder * dec, int recording, int sub_ch_id, uint8_t * out, int64_t cap);
+/* The same payload packed 8 bits per byte, first bit most significant (3 x bit rate bytes per logical frame, as
+ * eti_generator.cpp:403-411 packs a sub-channel): how it is read back from the device; dabstar_decoder_msc_copy unpacks.
+ * Returns the bytes written (dabstar_decoder_msc_size / 8 in total). */
+int64_t dabstar_decoder_msc_packed(const dabstar_decoder * dec, int recording, int sub_ch_id, uint8_t * out, int64_t cap);
 /* Self-configuration: the recording's sub-channels and CIF counter are taken from its own FIC (dabstar_fib_parser on the
  * CRC-good FIBs in stream order) instead of dabstar_decoder_set_subchannels. Every sub-channel FIG 0/1 describes gets a
  * Backend from the frame after its first description (in the reference that moment is a GUI action); with ETI enabled the

@@ -70,6 +70,12 @@ def test_mixed_eep_uep_ensemble(ctx, oracle, viterbi_path):
     want, dp, got = _run_both(oracle, ctx, rec, subch, synth.FMT_U8)
     _compare(want, dp, got, subch, soft_frames=1)
     assert got.msc[9].shape[0] == got.msc[1].shape[0] - 8  # Backend created two frames later emits 8 logical frames fewer
+    # the payload's read-back format: packed 8 bits per byte
+    import ctypes
+    for s_ in subch:
+        buf = np.zeros(got.msc[s_.sub_ch_id].size // 8, np.uint8)
+        n = ctx.lib.dabstar_decoder_msc_packed(dp.h, 0, s_.sub_ch_id, buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(buf.size))
+        assert n == buf.size and np.array_equal(buf, np.packbits(got.msc[s_.sub_ch_id].reshape(-1)))
 
 
 def test_low_snr_same_crc_counts(ctx, oracle):

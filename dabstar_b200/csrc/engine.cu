@@ -799,9 +799,8 @@ static void make_backend_jobs(std::vector<VitJob> & jobs, int prof, const VitPro
     j.src_mode = VIT_SRC_TIME_DEINTERLEAVE;
     j.flags = VIT_FLAG_PRBS;
     j.cif_first = g - 16;
-    int mask = 0;
-    for (int m = 0; m < 16; m++) if (g - 16 + m >= g_start) mask |= 1 << m;
-    j.row_mask = mask;
+    const int lo = std::max(0, g_start - (g - 16)); // rows m with g - 16 + m >= g_start hold CIFs the Backend has seen
+    j.row_mask = lo >= 16 ? 0 : ((0xFFFF << lo) & 0xFFFF);
     j.frag_off = start_cu * 64;
     jobs.push_back(j);
     out += p.n_bits;
@@ -1066,6 +1065,7 @@ struct dabstar_decoder
   DevBuf d_fibp;      // FIB bits packed 8 per byte for the read-back (384 bytes per frame)
   DevBuf d_tii_flags; // per descriptor: the frame's null symbol is a TII symbol
   HostBuf h_mscp; // MSC payload of the last run, packed 8 bits per byte
+  std::map<int, std::vector<VitJob>> msc_jobs; // MSC job lists by code-word length, reused between runs
   HostBuf h_fib, h_crc, h_fibp; // h_fib: FIB bits of the self-configuration pass (one per byte); h_fibp: all FIBs of the run, packed 8 bits per byte
   std::vector<int16_t> h_soft_one;
   long long total_slots = 0;
@@ -2166,8 +2166,21 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
   // ================= MSC: all logical frames of all sub-channels in one batch per profile size
   if (!dec->cfg.scan_mode)
   {
-    std::map<int, std::vector<VitJob>> by_steps; // group launches by code-word length (shared-memory footprint)
+    std::map<int, std::vector<VitJob>> & by_steps = dec->msc_jobs; // group launches by code-word length (shared-memory footprint)
+    for (auto & kv : by_steps) kv.second.clear();                  // (kept between runs: tens of megabytes of page faults otherwise)
     long long out_total = 0;
+    {
+      // one job per sub-channel and CIF (several hundred thousand for a full ensemble): size the lists first
+      std::map<int, size_t> count;
+      for (int r = 0; r < n_rec; r++)
+      {
+        const Recording & R = dec->recs[r];
+        const int n_cifs = 4 * R.n_slots + std::max(0, (R.partial_syms - 3) / 18);
+        for (const MscOut & m : R.msc) count[ctx->profiles[m.profile].n_bits + 6] += (size_t)std::max(0, n_cifs - (4 * m.sc.start_frame + 16));
+      }
+      for (auto & kv : count) by_steps[kv.first].reserve(kv.second);
+    }
+    tr("msc jobs sized");
     for (int r = 0; r < n_rec; r++)
     {
       Recording & R = dec->recs[r];
@@ -2185,6 +2198,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
         out_total += (long long)n_out * p.n_bits;
       }
     }
+    tr("msc jobs built");
     if (out_total > 0)
     {
       CK(dec->d_mscbits.reserve((size_t)out_total));
@@ -2202,6 +2216,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       CK(dec->h_mscp.reserve((size_t)(out_total / 8)));
       CK(launch_pack_bits(st, dec->d_mscbits.as<uint8_t>(), dec->d_mscpacked.as<uint8_t>(), out_total / 8, &ctx->launches));
       CK(cudaMemcpyAsync(dec->h_mscp.p, dec->d_mscpacked.p, (size_t)(out_total / 8), cudaMemcpyDeviceToHost, st));
+      tr("msc enqueued");
     }
   }
   // ================= ETI: every sub-channel of every CIF through EtiGenerator's own de-interleaver (eti_generator.cpp:90-204)

@@ -1065,7 +1065,6 @@ struct dabstar_decoder
   DevBuf d_fibp;      // FIB bits packed 8 per byte for the read-back (384 bytes per frame)
   DevBuf d_tii_flags; // per descriptor: the frame's null symbol is a TII symbol
   HostBuf h_mscp; // MSC payload of the last run, packed 8 bits per byte
-  std::map<int, std::vector<VitJob>> msc_jobs; // MSC job lists by code-word length, reused between runs
   HostBuf h_fib, h_crc, h_fibp; // h_fib: FIB bits of the self-configuration pass (one per byte); h_fibp: all FIBs of the run, packed 8 bits per byte
   std::vector<int16_t> h_soft_one;
   long long total_slots = 0;
@@ -2166,21 +2165,11 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
   // ================= MSC: all logical frames of all sub-channels in one batch per profile size
   if (!dec->cfg.scan_mode)
   {
-    std::map<int, std::vector<VitJob>> & by_steps = dec->msc_jobs; // group launches by code-word length (shared-memory footprint)
-    for (auto & kv : by_steps) kv.second.clear();                  // (kept between runs: tens of megabytes of page faults otherwise)
+    // One job per sub-channel and CIF (several hundred thousand for a full ensemble), grouped by code-word length (one launch
+    // per length: shared-memory footprint). The host only lists one range per Backend; the jobs are written on the device.
+    std::map<int, std::vector<BackendJobRange>> by_steps;
+    std::map<int, int> n_jobs_of;
     long long out_total = 0;
-    {
-      // one job per sub-channel and CIF (several hundred thousand for a full ensemble): size the lists first
-      std::map<int, size_t> count;
-      for (int r = 0; r < n_rec; r++)
-      {
-        const Recording & R = dec->recs[r];
-        const int n_cifs = 4 * R.n_slots + std::max(0, (R.partial_syms - 3) / 18);
-        for (const MscOut & m : R.msc) count[ctx->profiles[m.profile].n_bits + 6] += (size_t)std::max(0, n_cifs - (4 * m.sc.start_frame + 16));
-      }
-      for (auto & kv : count) by_steps[kv.first].reserve(kv.second);
-    }
-    tr("msc jobs sized");
     for (int r = 0; r < n_rec; r++)
     {
       Recording & R = dec->recs[r];
@@ -2194,18 +2183,29 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
         m.out_off = out_total;
         m.out_len = (long long)n_out * p.n_bits;
         if (n_out == 0) continue;
-        make_backend_jobs(by_steps[p.n_bits + 6], m.profile, p, R.slot_base * FRAME_SOFT, g_start, 0, n_cifs, m.sc.start_cu, out_total);
+        int & nj = n_jobs_of[p.n_bits + 6];
+        by_steps[p.n_bits + 6].push_back(BackendJobRange{ R.slot_base * FRAME_SOFT, out_total, m.profile, p.n_bits, g_start, g_start + 16, n_out, m.sc.start_cu * 64, nj, 0 });
+        nj += n_out;
         out_total += (long long)n_out * p.n_bits;
       }
     }
-    tr("msc jobs built");
+    tr("msc ranges built");
     if (out_total > 0)
     {
       CK(dec->d_mscbits.reserve((size_t)out_total));
+      if (int e = sync_profiles(ctx)) return e;
       for (auto & kv : by_steps)
       {
+        const int n_jobs = n_jobs_of[kv.first];
+        CK(dec->d_jobs.reserve(sizeof(VitJob) * (size_t)n_jobs + sizeof(BackendJobRange) * kv.second.size() + 256));
+        VitJob * d_jobs = dec->d_jobs.as<VitJob>();
+        BackendJobRange * d_ranges = reinterpret_cast<BackendJobRange *>(reinterpret_cast<unsigned char *>(d_jobs) + ((sizeof(VitJob) * (size_t)n_jobs + 255) & ~(size_t)255));
+        UP(d_ranges, kv.second.data(), sizeof(BackendJobRange) * kv.second.size());
+        CK(launch_expand_backend_jobs(st, d_ranges, (int)kv.second.size(), d_jobs, &ctx->launches));
+        if (int e = reserve_viterbi_ws(ctx, n_jobs, kv.first)) return e;
         dec->span_begin(ST_MSC);
-        if (int e = run_viterbi_jobs(ctx, kv.second, kv.first, dec->d_soft.as<int16_t>(), dec->d_mscbits.as<uint8_t>(), nullptr, nullptr, dec->d_jobs)) return e;
+        CK(launch_viterbi(st, d_jobs, nullptr, n_jobs, ctx->d_profiles.as<VitProfile>(), kv.first, dec->d_soft.as<int16_t>(), dec->d_mscbits.as<uint8_t>(), ctx->tab.prbs,
+                          nullptr, nullptr, ctx->d_step_tab.as<unsigned>(), ctx->vit_ws.p, ctx->vit_ws.cap, &ctx->launches));
         dec->span_end();
         SYNC(); // d_jobs is reused by the next group
       }

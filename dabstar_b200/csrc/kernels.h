@@ -67,6 +67,7 @@ cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, const Frame
                            const unsigned * step_tab, void * ws, size_t ws_bytes, unsigned long long * launch_counter);
 
 // bits: one decoded bit per byte (8-byte aligned, n_bytes * 8 of them) -> out: n_bytes bytes, first bit most significant
+cudaError_t launch_expand_backend_jobs(cudaStream_t stream, const BackendJobRange * ranges, int n_ranges, VitJob * jobs, unsigned long long * launch_counter);
 cudaError_t launch_pack_bits(cudaStream_t stream, const uint8_t * bits, uint8_t * out, long long n_bytes, unsigned long long * launch_counter);
 
 // dabplus_kernels.cu: one record per five-frame window of a DAB+ sub-channel

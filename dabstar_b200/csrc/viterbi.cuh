@@ -58,6 +58,18 @@ struct VitJob
                        // (rows at or after it read one CIF later, row index -1 reads the dropped CIF itself); 0 = Backend
 };
 
+// A Backend's jobs in compact form (expanded on the device, k_expand_backend_jobs): logical frames g_first .. g_first + n_jobs - 1
+// of a sub-channel whose Backend exists from CIF g_start on.
+struct BackendJobRange
+{
+  long long src, out;  // as VitJob::src; byte index of the first decoded bit of the range
+  int profile, n_bits; // n_bits = 24 * bit rate
+  int g_start, g_first, n_jobs;
+  int frag_off;
+  int job_first;       // index of the range's first job in the launch's job array
+  int pad;
+};
+
 // CIF read by de-interleaver row m of a job (see VitJob::skip_plus1 and engine.cu, ETI section)
 __host__ __device__ inline int vit_row_cif(int cif_first, int skip_plus1, int m)
 {

@@ -424,6 +424,30 @@ __global__ void __launch_bounds__(POST_WARPS * 32) k_fic_post(const VitJob * __r
     crc_ok[3 * job.aux + lane] = reg == 0;
   }
 }
+// One Backend (sub-channel of a recording) = one range of per-CIF jobs; the job list of a full ensemble has several hundred
+// thousand entries, so it is written here instead of on the host (Backend::_process_segment start-up: logical frame g needs
+// CIFs g-16 .. g-1 ... g; rows whose CIF precedes the Backend's creation read zeros, backend.cpp:129-161).
+__global__ void __launch_bounds__(128) k_expand_backend_jobs(const BackendJobRange * __restrict__ ranges, VitJob * __restrict__ jobs)
+{
+  const BackendJobRange r = ranges[blockIdx.x];
+  for (int i = threadIdx.x; i < r.n_jobs; i += blockDim.x)
+  {
+    const int g = r.g_first + i;
+    VitJob j;
+    j.src = r.src;
+    j.out = r.out + (long long)i * r.n_bits;
+    j.profile = r.profile;
+    j.src_mode = VIT_SRC_TIME_DEINTERLEAVE;
+    j.flags = VIT_FLAG_PRBS;
+    j.cif_first = g - 16;
+    const int lo = max(0, r.g_start - (g - 16));
+    j.row_mask = lo >= 16 ? 0 : ((0xFFFF << lo) & 0xFFFF);
+    j.frag_off = r.frag_off;
+    j.aux = 0;
+    j.skip_plus1 = 0;
+    jobs[r.job_first + i] = j;
+  }
+}
 // EtiGenerator::_process_sub_channel storage loop (eti_generator.cpp:403-411): 8 decoded bits (one per byte) -> one byte, first bit most significant
 __global__ void __launch_bounds__(256) k_pack_bits(const uint8_t * __restrict__ bits, uint8_t * __restrict__ out, long long n_bytes)
 {
@@ -435,6 +459,14 @@ __global__ void __launch_bounds__(256) k_pack_bits(const uint8_t * __restrict__ 
   }
 }
 } // namespace
+
+cudaError_t launch_expand_backend_jobs(cudaStream_t stream, const BackendJobRange * ranges, int n_ranges, VitJob * jobs, unsigned long long * launch_counter)
+{
+  if (n_ranges <= 0) return cudaSuccess;
+  k_expand_backend_jobs<<<(unsigned)n_ranges, 128, 0, stream>>>(ranges, jobs);
+  if (launch_counter) (*launch_counter)++;
+  return cudaGetLastError();
+}
 
 cudaError_t launch_pack_bits(cudaStream_t stream, const uint8_t * bits, uint8_t * out, long long n_bytes, unsigned long long * launch_counter)
 {

@@ -204,43 +204,106 @@ __global__ void __launch_bounds__(256) k_viterbi(const VitJob * __restrict__ job
 //                  packed byte store
 //   k_fic_post   : FIB CRC and BER re-encode of FIC blocks (warp per block)
 constexpr int GATHER_STEPS = 64; // trellis steps per CTA tile
+// Every CTA first files, per code word and de-interleave delay row, where kept bit 0 of that row lives (shared memory):
+// the per-bit work is then one 4-bit reversal, one pointer fetch and one load. ncu on the previous form (address
+// arithmetic per bit: CIF offset, row mask, source mode) showed the kernel issue bound, 155 warp instructions per lane
+// and trellis step (profiles/r1_g2_ncu_gather_summary.txt). Staging the 47 CIF rows of a CTA in shared memory was
+// measured twice (bit exact, 19.5 instead of 16.9 ms for the MSC pass of the full ensemble) and dropped.
+// Soft bit at p if take, else 0: a predicated load instead of a branch around it, so that the loads of a batch overlap
+__device__ __forceinline__ int ld_soft_if(const int16_t * p, bool take)
+{
+  int v;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.s32 %0, 0;\n\t@q ld.global.nc.s16 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"((int)take));
+  return v;
+}
 
+template <int BATCH>
 __global__ void __launch_bounds__(256) k_vit_gather(const VitJob * __restrict__ jobs, const FrameDesc * __restrict__ fic_frames, int job_first, int n_jobs,
                                                     const VitProfile * __restrict__ profiles, const unsigned * __restrict__ step_tab,
                                                     const int16_t * __restrict__ soft, unsigned * __restrict__ sym, int stride, int rows)
 {
   __shared__ unsigned tile[32][GATHER_STEPS + 1];
+  // per code word: int16 index of kept bit 0 of de-interleave delay row m (negative: that CIF precedes the Backend, the
+  // de-interleaver memory is still zero; a linear source has the same index in all 16 rows), trellis steps, step table
+  __shared__ long long rowoff[32][16];
+  __shared__ int sh_steps[32], sh_tab[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int jb = blockIdx.x * 32, t0 = blockIdx.y * GATHER_STEPS;
-#pragma unroll 1
-  for (int c = 0; c < 4; c++)
+
+  for (int i = threadIdx.x; i < 32 * 16; i += 256)
   {
-    const int jl = jb + 4 * warp + c;
+    const int jr = i >> 4, m = i & 15;
+    long long p = -1;
     VitJob job;
-    const bool valid = jl < n_jobs && load_job(jobs, fic_frames, job_first + jl, job);
-    int steps = 0;
-    const unsigned * tab = nullptr;
-    if (valid) { const VitProfile * pr = profiles + job.profile; steps = pr->n_bits + 6; tab = step_tab + pr->tab_off; }
-#pragma unroll
-    for (int h = 0; h < GATHER_STEPS / 32; h++)
+    const bool valid = jb + jr < n_jobs && load_job(jobs, fic_frames, job_first + jb + jr, job);
+    if (valid)
     {
-      const int t = t0 + lane + 32 * h;
-      unsigned word = 0x7f7f7f7fu; // erasures
-      if (t < steps)
+      if (job.src_mode == VIT_SRC_LINEAR) p = job.src;
+      else if ((job.row_mask >> m) & 1) p = job.src + cif_offset(vit_row_cif(job.cif_first, job.skip_plus1, m)) + job.frag_off;
+    }
+    rowoff[jr][m] = p;
+    if (m == 0)
+    {
+      const VitProfile * pr = profiles + (valid ? job.profile : 0);
+      sh_steps[jr] = valid ? pr->n_bits + 6 : 0;
+      sh_tab[jr] = valid ? pr->tab_off : 0;
+    }
+  }
+  __syncthreads();
+
+  // BATCH code words of the warp at a time as straight-line code: their step-table words first, then all row pointers,
+  // then all soft-bit loads (predicated, no branches), so that 8 * BATCH loads are in flight per lane
+#pragma unroll 1
+  for (int c0 = 0; c0 < 4; c0 += BATCH)
+  {
+    unsigned e[BATCH][GATHER_STEPS / 32];
+#pragma unroll
+    for (int c = 0; c < BATCH; c++)
+    {
+      const int jr = 4 * warp + c0 + c;
+      const int steps = sh_steps[jr];
+      const unsigned * tab = step_tab + sh_tab[jr];
+#pragma unroll
+      for (int h = 0; h < GATHER_STEPS / 32; h++)
       {
-        const unsigned e = tab[t];
-        int k = (int)(e & 0x0fffffffu), v[4];
+        const int t = t0 + lane + 32 * h;
+        const unsigned w = tab[max(min(t, steps - 1), 0)];
+        e[c][h] = t < steps ? w : 0u; // no step: nothing kept, the word below comes out as four erasures (127)
+      }
+    }
+    asm volatile("" ::: "memory"); // all step-table words requested before the first one is needed
+    int a[BATCH][GATHER_STEPS / 32][4];
+#pragma unroll
+    for (int c = 0; c < BATCH; c++)
+    {
+      const int jr = 4 * warp + c0 + c;
+#pragma unroll
+      for (int h = 0; h < GATHER_STEPS / 32; h++)
+      {
+        int k = (int)(e[c][h] & 0x0fffffffu);
 #pragma unroll
         for (int g = 0; g < 4; g++)
         {
-          const bool keep = (e >> (28 + g)) & 1u;
-          v[g] = keep ? job_soft(job, soft, k) : 0;
+          const bool keep = (e[c][h] >> (28 + g)) & 1u;
+          const long long off = rowoff[jr][__brev((unsigned)k) >> 28]; // time_map: 4-bit reversal of k & 15
+          a[c][h][g] = ld_soft_if(soft + off + k, keep && off >= 0);
           k += keep;
         }
-        word = tpc_pack_syms(v);
       }
-      tile[4 * warp + c][lane + 32 * h] = word;
     }
+    asm volatile("" ::: "memory"); // the stores below wait for their loads: keep them behind the whole batch of loads
+#pragma unroll
+    for (int c = 0; c < BATCH; c++)
+#pragma unroll
+      for (int h = 0; h < GATHER_STEPS / 32; h++)
+      {
+        // viterbi_scalar.h:34-40: in + 127 wraps in 16 bits before the clamp to 0..255 (the 16-bit halves taken by the PRMT)
+        unsigned lo = __byte_perm((unsigned)(a[c][h][0] + 127), (unsigned)(a[c][h][1] + 127), 0x5410);
+        unsigned hi = __byte_perm((unsigned)(a[c][h][2] + 127), (unsigned)(a[c][h][3] + 127), 0x5410);
+        lo = __vmins2(__vmaxs2(lo, 0u), 0x00ff00ffu);
+        hi = __vmins2(__vmaxs2(hi, 0u), 0x00ff00ffu);
+        tile[4 * warp + c0 + c][lane + 32 * h] = __byte_perm(lo, hi, 0x6420);
+      }
   }
   __syncthreads();
   for (int r = warp; r < GATHER_STEPS; r += 8)
@@ -538,13 +601,19 @@ cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, const Frame
   if (n_jobs < min_jobs || fit < 32 || step_tab == nullptr)
     return launch_viterbi_warp(stream, jobs, fic_frames, n_jobs, profiles, max_steps, soft, out_bits, prbs, crc_ok, ber, launch_counter);
   const int chunk = (int)min((size_t)((n_jobs + 31) & ~31), fit);
+  // DABSTAR_GATHER_BATCH = 1, 2 or 4 code words per warp in flight at a time (A/B measurements)
+  int gather_batch = 2;
+  if (const char * ev = getenv("DABSTAR_GATHER_BATCH")) gather_batch = atoi(ev);
   unsigned * sym = static_cast<unsigned *>(ws);
   unsigned long long * surv = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(ws) + (((size_t)rows * chunk * 4 + 255) & ~(size_t)255));
   for (int first = 0; first < n_jobs; first += chunk)
   {
     const int n = min(chunk, n_jobs - first);
     const int groups = (n + 31) / 32;
-    k_vit_gather<<<dim3((unsigned)groups, (unsigned)((rows + GATHER_STEPS - 1) / GATHER_STEPS)), 256, 0, stream>>>(jobs, fic_frames, first, n, profiles, step_tab, soft, sym, chunk, rows);
+    const dim3 ggrid((unsigned)groups, (unsigned)((rows + GATHER_STEPS - 1) / GATHER_STEPS));
+    if (gather_batch >= 4) k_vit_gather<4><<<ggrid, 256, 0, stream>>>(jobs, fic_frames, first, n, profiles, step_tab, soft, sym, chunk, rows);
+    else if (gather_batch >= 2) k_vit_gather<2><<<ggrid, 256, 0, stream>>>(jobs, fic_frames, first, n, profiles, step_tab, soft, sym, chunk, rows);
+    else k_vit_gather<1><<<ggrid, 256, 0, stream>>>(jobs, fic_frames, first, n, profiles, step_tab, soft, sym, chunk, rows);
     k_vit_tpc<<<groups, 32, 0, stream>>>(jobs, fic_frames, first, n, profiles, sym, surv, chunk, out_bits, prbs);
     if (launch_counter) (*launch_counter) += 2;
     if (crc_ok != nullptr || ber != nullptr)

@@ -203,17 +203,19 @@ __global__ void __launch_bounds__(256) k_viterbi(const VitJob * __restrict__ job
 //   k_vit_tpc    : forward pass (decision words to [step][code word]) and chain back, energy dispersal fused into the
 //                  packed byte store
 //   k_fic_post   : FIB CRC and BER re-encode of FIC blocks (warp per block)
-constexpr int GATHER_STEPS = 64; // trellis steps per CTA tile
+constexpr int GATHER_STEPS = 128; // trellis steps per CTA tile
 // Every CTA first files, per code word and de-interleave delay row, where kept bit 0 of that row lives (shared memory):
-// the per-bit work is then one 4-bit reversal, one pointer fetch and one load. ncu on the previous form (address
-// arithmetic per bit: CIF offset, row mask, source mode) showed the kernel issue bound, 155 warp instructions per lane
+// the per-bit work is then one 4-bit reversal, one pointer fetch and one predicated load. ncu on the first form (address
+// arithmetic per bit: CIF offset, row mask, source mode) showed the kernel issue bound at 155 warp instructions per lane
 // and trellis step (profiles/r1_g2_ncu_gather_summary.txt). Staging the 47 CIF rows of a CTA in shared memory was
 // measured twice (bit exact, 19.5 instead of 16.9 ms for the MSC pass of the full ensemble) and dropped.
-// Soft bit at p if take, else 0: a predicated load instead of a branch around it, so that the loads of a batch overlap
-__device__ __forceinline__ int ld_soft_if(const int16_t * p, bool take)
+__device__ int16_t g_zero_row[CIF_BITS]; // what a delay row reads while its CIF precedes the Backend (backend.cpp:129-161: the memory starts as zeros)
+
+// Soft bit at p if take != 0, else 0: a predicated load instead of a branch around it, so that the loads of a batch overlap
+__device__ __forceinline__ int ld_soft_if(const int16_t * p, unsigned take)
 {
   int v;
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.s32 %0, 0;\n\t@q ld.global.nc.s16 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"((int)take));
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.s32 %0, 0;\n\t@q ld.global.nc.s16 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"(take));
   return v;
 }
 
@@ -222,41 +224,45 @@ __global__ void __launch_bounds__(256) k_vit_gather(const VitJob * __restrict__ 
                                                     const VitProfile * __restrict__ profiles, const unsigned * __restrict__ step_tab,
                                                     const int16_t * __restrict__ soft, unsigned * __restrict__ sym, int stride, int rows)
 {
+  constexpr int H = GATHER_STEPS / 32;
   __shared__ unsigned tile[32][GATHER_STEPS + 1];
-  // per code word: int16 index of kept bit 0 of de-interleave delay row m (negative: that CIF precedes the Backend, the
-  // de-interleaver memory is still zero; a linear source has the same index in all 16 rows), trellis steps, step table
-  __shared__ long long rowoff[32][16];
+  // per code word: kept bit 0 of de-interleave delay row m (a linear source has the same pointer in all 16 rows; one
+  // pad entry per code word keeps the lane-per-code-word stores off a single bank), trellis steps, step table
+  __shared__ const int16_t * rowptr[32][17];
   __shared__ int sh_steps[32], sh_tab[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int jb = blockIdx.x * 32, t0 = blockIdx.y * GATHER_STEPS;
 
-  for (int i = threadIdx.x; i < 32 * 16; i += 256)
   {
-    const int jr = i >> 4, m = i & 15;
-    long long p = -1;
+    // lane = code word, warp = two of the 16 delay rows
     VitJob job;
-    const bool valid = jb + jr < n_jobs && load_job(jobs, fic_frames, job_first + jb + jr, job);
-    if (valid)
+    const bool valid = jb + lane < n_jobs && load_job(jobs, fic_frames, job_first + jb + lane, job);
+#pragma unroll
+    for (int q = 0; q < 2; q++)
     {
-      if (job.src_mode == VIT_SRC_LINEAR) p = job.src;
-      else if ((job.row_mask >> m) & 1) p = job.src + cif_offset(vit_row_cif(job.cif_first, job.skip_plus1, m)) + job.frag_off;
+      const int m = 2 * warp + q;
+      const int16_t * p = g_zero_row;
+      if (valid)
+      {
+        if (job.src_mode == VIT_SRC_LINEAR) p = soft + job.src;
+        else if ((job.row_mask >> m) & 1) p = soft + job.src + cif_offset(vit_row_cif(job.cif_first, job.skip_plus1, m)) + job.frag_off;
+      }
+      rowptr[lane][m] = p;
     }
-    rowoff[jr][m] = p;
-    if (m == 0)
+    if (warp == 0)
     {
       const VitProfile * pr = profiles + (valid ? job.profile : 0);
-      sh_steps[jr] = valid ? pr->n_bits + 6 : 0;
-      sh_tab[jr] = valid ? pr->tab_off : 0;
+      sh_steps[lane] = valid ? pr->n_bits + 6 : 0;
+      sh_tab[lane] = valid ? pr->tab_off : 0;
     }
   }
   __syncthreads();
 
-  // BATCH code words of the warp at a time as straight-line code: their step-table words first, then all row pointers,
-  // then all soft-bit loads (predicated, no branches), so that 8 * BATCH loads are in flight per lane
+  // BATCH code words of the warp at a time as straight-line code: 4 * H * BATCH predicated soft-bit loads in flight per lane
 #pragma unroll 1
   for (int c0 = 0; c0 < 4; c0 += BATCH)
   {
-    unsigned e[BATCH][GATHER_STEPS / 32];
+    unsigned e[BATCH][H];
 #pragma unroll
     for (int c = 0; c < BATCH; c++)
     {
@@ -264,30 +270,28 @@ __global__ void __launch_bounds__(256) k_vit_gather(const VitJob * __restrict__ 
       const int steps = sh_steps[jr];
       const unsigned * tab = step_tab + sh_tab[jr];
 #pragma unroll
-      for (int h = 0; h < GATHER_STEPS / 32; h++)
+      for (int h = 0; h < H; h++)
       {
         const int t = t0 + lane + 32 * h;
         const unsigned w = tab[max(min(t, steps - 1), 0)];
         e[c][h] = t < steps ? w : 0u; // no step: nothing kept, the word below comes out as four erasures (127)
       }
     }
-    asm volatile("" ::: "memory"); // all step-table words requested before the first one is needed
-    int a[BATCH][GATHER_STEPS / 32][4];
+    int a[BATCH][H][4];
 #pragma unroll
     for (int c = 0; c < BATCH; c++)
     {
-      const int jr = 4 * warp + c0 + c;
+      const int16_t * const * rp = rowptr[4 * warp + c0 + c];
 #pragma unroll
-      for (int h = 0; h < GATHER_STEPS / 32; h++)
+      for (int h = 0; h < H; h++)
       {
         int k = (int)(e[c][h] & 0x0fffffffu);
 #pragma unroll
         for (int g = 0; g < 4; g++)
         {
-          const bool keep = (e[c][h] >> (28 + g)) & 1u;
-          const long long off = rowoff[jr][__brev((unsigned)k) >> 28]; // time_map: 4-bit reversal of k & 15
-          a[c][h][g] = ld_soft_if(soft + off + k, keep && off >= 0);
-          k += keep;
+          const unsigned keep = e[c][h] & (1u << (28 + g));
+          a[c][h][g] = ld_soft_if(rp[__brev((unsigned)k) >> 28] + k, keep); // time_map: 4-bit reversal of k & 15
+          k += keep != 0;
         }
       }
     }
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(256) k_vit_gather(const VitJob * __restrict__ 
 #pragma unroll
     for (int c = 0; c < BATCH; c++)
 #pragma unroll
-      for (int h = 0; h < GATHER_STEPS / 32; h++)
+      for (int h = 0; h < H; h++)
       {
         // viterbi_scalar.h:34-40: in + 127 wraps in 16 bits before the clamp to 0..255 (the 16-bit halves taken by the PRMT)
         unsigned lo = __byte_perm((unsigned)(a[c][h][0] + 127), (unsigned)(a[c][h][1] + 127), 0x5410);
@@ -601,7 +605,7 @@ cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, const Frame
   if (n_jobs < min_jobs || fit < 32 || step_tab == nullptr)
     return launch_viterbi_warp(stream, jobs, fic_frames, n_jobs, profiles, max_steps, soft, out_bits, prbs, crc_ok, ber, launch_counter);
   const int chunk = (int)min((size_t)((n_jobs + 31) & ~31), fit);
-  // DABSTAR_GATHER_BATCH = 1, 2 or 4 code words per warp in flight at a time (A/B measurements)
+  // DABSTAR_GATHER_BATCH = 1 or 2 code words per warp in flight at a time (A/B measurements)
   int gather_batch = 2;
   if (const char * ev = getenv("DABSTAR_GATHER_BATCH")) gather_batch = atoi(ev);
   unsigned * sym = static_cast<unsigned *>(ws);
@@ -611,8 +615,7 @@ cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, const Frame
     const int n = min(chunk, n_jobs - first);
     const int groups = (n + 31) / 32;
     const dim3 ggrid((unsigned)groups, (unsigned)((rows + GATHER_STEPS - 1) / GATHER_STEPS));
-    if (gather_batch >= 4) k_vit_gather<4><<<ggrid, 256, 0, stream>>>(jobs, fic_frames, first, n, profiles, step_tab, soft, sym, chunk, rows);
-    else if (gather_batch >= 2) k_vit_gather<2><<<ggrid, 256, 0, stream>>>(jobs, fic_frames, first, n, profiles, step_tab, soft, sym, chunk, rows);
+    if (gather_batch >= 2) k_vit_gather<2><<<ggrid, 256, 0, stream>>>(jobs, fic_frames, first, n, profiles, step_tab, soft, sym, chunk, rows);
     else k_vit_gather<1><<<ggrid, 256, 0, stream>>>(jobs, fic_frames, first, n, profiles, step_tab, soft, sym, chunk, rows);
     k_vit_tpc<<<groups, 32, 0, stream>>>(jobs, fic_frames, first, n, profiles, sym, surv, chunk, out_bits, prbs);
     if (launch_counter) (*launch_counter) += 2;

@@ -22,9 +22,10 @@ REFERENCE_ROOT = "/root/reference"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--use_fast_math" if False else "-DDABSTAR_NO_FAST_MATH",  # IEEE division/sqrt: parity with the float reference matters
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-shared", "-cudart", "shared",
+    "-DDABSTAR_NO_FAST_MATH",  # IEEE division/sqrt: parity with the float reference matters (no --use_fast_math)
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-cudart", "shared",
 ]
+OBJ_DIR = os.path.join(CSRC, "_obj")  # per-source objects (git-ignored): only what changed is recompiled, in parallel
 
 
 def _newer(target: str, sources: list[str]) -> bool:
@@ -46,14 +47,24 @@ def cuda_sources() -> list[str]:
 
 
 def build_cuda(force: bool = False, verbose_ptxas: bool = False) -> str:
+    from concurrent.futures import ThreadPoolExecutor
     srcs = cuda_sources()
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    deps.append(os.path.join(REPO, "include", "dabstar_b200.h"))
-    if not force and _newer(LIB_CUDA, deps):
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(REPO, "include", "dabstar_b200.h"))
+    if not force and _newer(LIB_CUDA, srcs + headers):
         return LIB_CUDA
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose_ptxas else []) + ["-I", os.path.join(REPO, "include"), "-I", CSRC, "-o", LIB_CUDA] + srcs
-    _run(cmd)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    base = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose_ptxas else []) + ["-I", os.path.join(REPO, "include"), "-I", CSRC]
+    objs, todo = [], []
+    for src in srcs:
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or verbose_ptxas or not _newer(obj, [src] + headers):
+            todo.append(base + ["-c", "-o", obj, src])
+    with ThreadPoolExecutor(max_workers=max(1, min(8, len(todo)))) as pool:
+        list(pool.map(_run, todo))
+    _run([nvcc, "-shared", "-cudart", "shared", "-o", LIB_CUDA] + objs)
     return LIB_CUDA
 
 

@@ -273,20 +273,22 @@ extern "C" int dabstar_create(dabstar_ctx ** out, int device, void * stream)
     bin_idx[k] = (int16_t)(b < 0 ? b + T_U : b);
     rel[k] = (int16_t)(b < 0 ? b + K_CARR / 2 : b + K_CARR / 2 - 1); // ofdm_decoder.cpp:169-180
   }
-  std::vector<uint8_t> prbs(9216);
-  host_prbs(prbs.data(), 9216);
+  // energy dispersal: as long as the longest logical frame make_msc_profile accepts (24 x 1024 bits; the reference builds
+  // 24 x bitRate entries per Backend, backend.cpp:72-83) plus slack for the kernels' 8-byte loads
+  std::vector<uint8_t> prbs(PRBS_LEN);
+  host_prbs(prbs.data(), PRBS_LEN);
   bool ok = true;
   ok = ok && cudaMalloc(&ctx->tab.w2048, sizeof(float2) * T_U) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->tab.prs, sizeof(float2) * T_U) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->tab.ref_arg_conj, sizeof(float2) * T_U) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->tab.bin_of_k, sizeof(int16_t) * K_CARR) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->tab.rel_of_k, sizeof(int16_t) * K_CARR) == cudaSuccess;
-  ok = ok && cudaMalloc(&ctx->tab.prbs, 9216) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->tab.prbs, PRBS_LEN) == cudaSuccess;
   ok = ok && cudaMemcpy(ctx->tab.w2048, w.data(), sizeof(float2) * T_U, cudaMemcpyHostToDevice) == cudaSuccess;
   ok = ok && cudaMemcpy(ctx->tab.prs, ctx->h_prs.data(), sizeof(float2) * T_U, cudaMemcpyHostToDevice) == cudaSuccess;
   ok = ok && cudaMemcpy(ctx->tab.bin_of_k, bin_idx.data(), sizeof(int16_t) * K_CARR, cudaMemcpyHostToDevice) == cudaSuccess;
   ok = ok && cudaMemcpy(ctx->tab.rel_of_k, rel.data(), sizeof(int16_t) * K_CARR, cudaMemcpyHostToDevice) == cudaSuccess;
-  ok = ok && cudaMemcpy(ctx->tab.prbs, prbs.data(), 9216, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok = ok && cudaMemcpy(ctx->tab.prbs, prbs.data(), PRBS_LEN, cudaMemcpyHostToDevice) == cudaSuccess;
   ok = ok && launch_init_ref_arg(ctx->stream, ctx->tab, &ctx->launches) == cudaSuccess;
   ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
   if (!ok) { dabstar_destroy(ctx.release()); return DABSTAR_E_CUDA; }
@@ -698,6 +700,7 @@ extern "C" int dabstar_viterbi(dabstar_ctx * ctx, const int16_t * soft, const in
   for (int i = 0; i < n; i++)
   {
     if (frame_bits[i] <= 0 || frame_bits[i] > 16384) return ctx->fail(DABSTAR_E_INVALID, "frame_bits[%d] = %d", i, frame_bits[i]);
+    if (soft_off[i] < 0 || bits_off[i] < 0) return ctx->fail(DABSTAR_E_INVALID, "negative offset for code word %d", i);
     VitJob & j = jobs[i];
     memset(&j, 0, sizeof(j));
     j.src = soft_off[i];
@@ -1136,6 +1139,16 @@ extern "C" int dabstar_decoder_set_subchannels(dabstar_decoder * dec, int record
   if (!dec || recording < 0 || recording >= (int)dec->recs.size() || n < 0 || (n > 0 && !sc)) return DABSTAR_E_INVALID;
   dabstar_ctx * ctx = dec->ctx;
   Recording & r = dec->recs[recording];
+  // an ETI frame has room for 64 streams (NST is a 7-bit field next to FICF) and the sub-channels of a CIF do not overlap;
+  // a list that breaks either rule would also overrun the 6144-byte ETI frame (8 + 4 NST + 4 + 96 + 3 x sum of bit rates + 8)
+  if (n > 64) return ctx->fail(DABSTAR_E_INVALID, "%d sub-channels (an ensemble has at most 64)", n);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < i; j++)
+    {
+      if (sc[i].sub_ch_id == sc[j].sub_ch_id) return ctx->fail(DABSTAR_E_INVALID, "sub-channel %d listed twice", sc[i].sub_ch_id);
+      if (sc[i].start_cu < sc[j].start_cu + sc[j].size_cu && sc[j].start_cu < sc[i].start_cu + sc[i].size_cu)
+        return ctx->fail(DABSTAR_E_INVALID, "sub-channels %d and %d overlap", sc[j].sub_ch_id, sc[i].sub_ch_id);
+    }
   r.msc.clear();
   for (int i = 0; i < n; i++)
   {
@@ -1457,7 +1470,9 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
     R.d_iq = rin[r].iq;
     R.n = rin[r].n;
     R.slot_base = dec->total_slots;
-    R.slot_cap = (int)(R.n / T_F) + 2;
+    // a frame consumes T_u + start_index + 75 T_s + T_n samples with start_index >= T_g - 250 (phasereference.cpp:136-139):
+    // fewer than T_F when the sample clock runs fast or after a re-sync
+    R.slot_cap = (int)(R.n / (T_U + (T_G - 250) + 75LL * T_S + T_N)) + 2;
     dec->total_slots += R.slot_cap;
     R.frames.reserve((size_t)R.slot_cap);
     R.descs.reserve((size_t)R.slot_cap);
@@ -2310,7 +2325,9 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       uint8_t * f = R.eti.data() + (size_t)n * 6144;
       const int fr = 4 + (n >> 2);
       std::vector<MscOut> streams; // the sub-channel list as sampled at symbol 4 of the CIF's frame
-      for (const MscOut & m : R.msc) if (m.first_seen <= fr) { streams.push_back(MscOut()); streams.back().sc = m.sc; }
+      size_t need = 8 + 4 + 96 + 8;
+      for (const MscOut & m : R.msc) if (m.first_seen <= fr) { streams.push_back(MscOut()); streams.back().sc = m.sc; need += 4 + 3 * (size_t)m.sc.bit_rate; }
+      if (streams.size() > 64 || need > 6144) return ctx->fail(DABSTAR_E_INVALID, "ETI frame overflow: %zu streams, %zu bytes", streams.size(), need);
       const bool own = R.auto_cfg && fr < (int)R.cif_hi_f.size() && R.cif_hi_f[fr] >= 0;
       int o = eti_header(f, own ? R.cif_hi_f[fr] : R.eti_cif_hi, own ? R.cif_lo_f[fr] : R.eti_cif_lo, n & 3, streams);
       const int base = o;

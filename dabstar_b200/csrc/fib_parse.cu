@@ -60,10 +60,12 @@ struct dabstar_fib_parser
 
   void restart() { subch.clear(); comps.clear(); restarts++; }   // FibDecoder::_restart_fib_decoding: collected content is untrustworthy
 
-  // returns bytes used, or -1 to abandon the FIB
-  int fig0s1(const uint8_t * d, int off_bytes)
+  // returns bytes used, -1 to abandon the FIB, or -2 to abandon this FIG: an entry that would cross the end of the FIG
+  // (fig_bits = its length in bits) is not read - a CRC-good but malformed FIG must not make the parser read past the FIB
+  int fig0s1(const uint8_t * d, int off_bytes, int fig_bits)
   {
     int o = off_bytes * 8;
+    if (o + 24 > fig_bits) return -2;
     dabstar_subch s{};
     s.sub_ch_id = (int)bits(d, o, 6);
     bool known = false;
@@ -72,6 +74,7 @@ struct dabstar_fib_parser
     if (known) return (o + (known_short ? 24 : 32)) / 8; // the stored form decides the length, as the reference does
     s.start_cu = (int)bits(d, o + 6, 10);
     s.short_form = bits(d, o + 16, 1) == 0 ? 1 : 0;
+    if (!s.short_form && o + 32 > fig_bits) return -2;
     if (s.short_form)
     {
       const Table8Row & row = table8()[bits(d, o + 18, 6)];
@@ -99,13 +102,15 @@ struct dabstar_fib_parser
     return o / 8;
   }
 
-  int fig0s2(const uint8_t * d, int off_bytes, int pd)
+  int fig0s2(const uint8_t * d, int off_bytes, int pd, int fig_bits)
   {
     int o = off_bytes * 8;
+    if (o + (pd ? 40 : 24) > fig_bits) return -2;
     const uint32_t sid = pd ? bits(d, o, 32) : bits(d, o, 16);
     o += pd ? 32 : 16;
     const int n = (int)bits(d, o + 4, 4);
     o += 8;
+    if (o + 16 * n > fig_bits) return -2;
     for (int c = 0; c < n; c++, o += 16)
     {
       bool known = false;
@@ -153,7 +158,8 @@ struct dabstar_fib_parser
           bool abandon = false;
           while (used < len + 1)
           {
-            used = ext == 1 ? fig0s1(d, used) : fig0s2(d, used, pd);
+            used = ext == 1 ? fig0s1(d, used, 8 * (len + 1)) : fig0s2(d, used, pd, 8 * (len + 1));
+            if (used == -2) break;                       // truncated entry: the rest of this FIG is not evaluated
             if (used < 0) { abandon = true; break; }
           }
           if (abandon) break; // the rest of this FIB is not evaluated

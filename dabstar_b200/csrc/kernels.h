@@ -15,8 +15,10 @@ struct DeviceTables
   float2 * ref_arg_conj; // coarse-AFC reference (phasereference.cpp:58-66), filled by init_ref_arg
   int16_t * bin_of_k;    // frequency interleaver: nominal carrier k -> fft index 0..2047
   int16_t * rel_of_k;    // realCarrRelIdx of carrier k (ofdm_decoder.cpp:169-180)
-  uint8_t * prbs;        // energy dispersal sequence, 9216 bits
+  uint8_t * prbs;        // energy dispersal sequence, PRBS_LEN bits (one per byte)
 };
+
+constexpr int PRBS_LEN = 24 * 1024 + 64; // the longest logical frame make_msc_profile accepts, plus slack for 8-byte loads
 
 // Per-recording OFDM decoder state in HBM (ofdm_decoder.h:89-103), nominal carrier order.
 struct OfdmStateDev

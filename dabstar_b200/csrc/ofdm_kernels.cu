@@ -7,6 +7,7 @@
 // FreqInterleaver + OfdmDecoder (ofdm/ofdm_decoder.cpp:114-355).
 #include "fft2048.cuh"
 #include "kernels.h"
+#include "devcache.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -1235,11 +1236,9 @@ cudaError_t launch_fft_frames(cudaStream_t s, const DeviceTables & t, const Fram
   return dispatch_fmt(fmt, [&](auto F) {
     constexpr int FMT = decltype(F)::value;
     constexpr int stage = 2 * fft_stage_bytes<FMT>();
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_fft_frames<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage); attr_set = true; }
-    static int per_sm = 0; // resident CTAs per SM (registers and shared memory of this instantiation)
-    if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fft_frames<FMT>, FFT_THREADS, stage) != cudaSuccess || per_sm <= 0)) per_sm = 4;
-    k_fft_frames<FMT><<<std::min(n_items, N_SM * per_sm), FFT_THREADS, stage, s>>>(frames, n_items, recs, t.w2048, t.bin_of_k, X);
+    const LaunchProps lp = launch_props((const void *)k_fft_frames<FMT>, FFT_THREADS, stage, stage); // per device: resident CTAs per SM of this instantiation
+    const int per_sm = lp.err == cudaSuccess && lp.ctas_per_sm > 0 ? lp.ctas_per_sm : 4;
+    k_fft_frames<FMT><<<std::min(n_items, lp.n_sm * per_sm), FFT_THREADS, stage, s>>>(frames, n_items, recs, t.w2048, t.bin_of_k, X);
   });
 }
 
@@ -1280,22 +1279,8 @@ cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork
   static const int lag_env = getenv("DABSTAR_DEMAP_LAG") ? atoi(getenv("DABSTAR_DEMAP_LAG")) : 15;
   static const int lag = lag_env == 3 ? 3 : (lag_env == 7 ? 7 : 15);
   auto smem_bytes = [&](int threads) { return demap4_smem_bytes(threads, lag); };
-  // every instantiation needs the opt-in for its dynamic shared memory once
-  auto prepared = [&](const void * fn) -> cudaError_t {
-    static std::vector<const void *> done;
-    if (std::find(done.begin(), done.end(), fn) != done.end()) return cudaSuccess;
-    cudaError_t ea = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(DM4_MAX_THREADS));
-    if (ea == cudaSuccess) done.push_back(fn);
-    return ea;
-  };
-  // slices per recording: fill the SMs as evenly as the co-residency limit allows
-  static int n_sm = 0;
-  if (n_sm == 0)
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = N_SM;
-  }
+  // slices per recording: fill the SMs as evenly as the co-residency limit allows (opt-in and occupancy cached per device)
+  int n_sm = N_SM;
   const int cand[7] = { 1, 2, 3, 4, 6, 8, 12 };
   int best_s = 0, best_cap = 0;
   long long best_cost = -1;
@@ -1303,10 +1288,12 @@ cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork
   {
     const int sl = cand[ci], threads = DM3_ROW4 / sl;
     if (threads > DM4_MAX_THREADS) continue;
-    int occ = 0;
     const void * fn_c = demap4_fn_for(lag, threads, soft_bit_type);
-    if (cudaError_t ea = prepared(fn_c)) return ea;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn_c, threads, smem_bytes(threads)) != cudaSuccess || occ <= 0) continue;
+    const LaunchProps lp = launch_props(fn_c, threads, smem_bytes(threads), smem_bytes(DM4_MAX_THREADS));
+    if (lp.err != cudaSuccess) return lp.err;
+    const int occ = lp.ctas_per_sm;
+    n_sm = lp.n_sm;
+    if (occ <= 0) continue;
     const int cap = occ * n_sm;                       // CTAs that can be resident at once
     const int per_launch = cap / sl;                  // recordings per launch
     if (per_launch <= 0) continue;

@@ -3,6 +3,7 @@
 #include "viterbi.cuh"
 #include "viterbi_tpc.cuh"
 #include "kernels.h"
+#include "devcache.h"
 
 #include <cstdlib>
 
@@ -569,13 +570,8 @@ static cudaError_t launch_viterbi_warp(cudaStream_t stream, const VitJob * jobs,
   while (warps > 1 && per_warp * warps > 56 * 1024) warps >>= 1; // <= 56 KB per CTA -> 4 CTAs/SM when possible
   const int smem = per_warp * warps;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  static bool attr_set = false;
-  if (!attr_set)
-  {
-    cudaError_t e = cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  const LaunchProps lp = launch_props((const void *)k_viterbi, warps * 32, (size_t)smem, 227 * 1024); // opt-in once per device
+  if (lp.err != cudaSuccess) return lp.err;
   const int ctas_needed = (n_jobs + warps - 1) / warps;
   const int per_sm = max(1, min(16, (227 * 1024) / max(smem, 1)));
   const int grid = min(ctas_needed, N_SM * per_sm);

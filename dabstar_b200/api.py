@@ -568,6 +568,37 @@ class DabProcessor:
             self.ctx.lib.dabstar_decoder_eti_copy(self.h, recording, _ptr(buf), ctypes.c_int64(n))
         return buf.reshape(-1, 6144)
 
+    # ---- long recordings: segments inside a run, chunks of a stream across runs (include/dabstar_b200.h, "long recordings")
+    def set_segmentation(self, segment_frames: int, warmup_frames: int = 18):
+        """A verified window of >= 2 x segment_frames frames of one recording is demapped as parallel segments, each warm-started
+        warmup_frames early (OfdmDecoder's per-carrier IIRs, ofdm_decoder.cpp:182-251, are the only state approximated)."""
+        self.ctx.check(self.ctx.lib.dabstar_decoder_set_segmentation(self.h, int(segment_frames), int(warmup_frames)), "dabstar_decoder_set_segmentation")
+
+    def set_streaming(self, enable: bool = True):
+        """Runs decode chunks of a longer stream: an incomplete trailing frame is left for the next chunk (see consumed())."""
+        self.ctx.check(self.ctx.lib.dabstar_decoder_set_streaming(self.h, int(enable)), "dabstar_decoder_set_streaming")
+
+    def consumed(self, recording: int) -> int:
+        """Stream index of the first sample the decoder has not consumed."""
+        return int(self.ctx.check(self.ctx.lib.dabstar_decoder_consumed(self.h, recording), "dabstar_decoder_consumed"))
+
+    def warmup_frames(self, recording: int) -> int:
+        return int(self.ctx.check(self.ctx.lib.dabstar_decoder_warmup_frames(self.h, recording), "dabstar_decoder_warmup_frames"))
+
+    def export_state(self, recording: int) -> np.ndarray:
+        """Everything the stream's next chunk depends on (DabProcessor's loops, OfdmDecoder state, 16 CIFs of soft bits) as bytes."""
+        n = int(self.ctx.check(self.ctx.lib.dabstar_decoder_state_size(self.h, recording), "dabstar_decoder_state_size"))
+        blob = np.zeros(n, np.uint8)
+        self.ctx.check(self.ctx.lib.dabstar_decoder_export_state(self.h, recording, _ptr(blob), ctypes.c_int64(n)), "dabstar_decoder_export_state")
+        return blob
+
+    def import_state(self, recording: int, blob: np.ndarray, lead_samples: int = 0):
+        """The recording's next run continues the stream `blob` was exported from; its input must start lead_samples before
+        the exported consumed() position."""
+        blob = np.ascontiguousarray(blob, np.uint8)
+        self.ctx.check(self.ctx.lib.dabstar_decoder_import_state(self.h, recording, _ptr(blob), ctypes.c_int64(blob.size), ctypes.c_int64(lead_samples)),
+                       "dabstar_decoder_import_state")
+
     def run_ptrs(self, ptrs: list[int], n_samples: list[int], mem: int) -> float:
         """Decode complete recordings given raw pointers. Returns the device time in ms (CUDA events)."""
         p = (c_p * self.n)(*[c_p(x) for x in ptrs])

@@ -948,7 +948,7 @@ extern "C" int dabstar_ofdm_decode_frames(dabstar_ctx * ctx, dabstar_ofdm_state 
     fd[f].n_syms = 75;
     if (null_is_tii) tii[f] = null_is_tii[f];
   }
-  DemapWork wk{ 0, n_frames, 0, 0 };
+  DemapWork wk{ 0, n_frames, 0, 0, 0, 0 };
   CK(ctx->scratch[3].reserve(sizeof(FrameDesc) * fd.size() + sizeof(DemapWork) + tii.size() + 64));
   char * aux = ctx->scratch[3].as<char>();
   FrameDesc * dfd = reinterpret_cast<FrameDesc *>(aux);
@@ -1019,6 +1019,14 @@ struct Recording
   bool careful_spec = true;// a window that starts with a coarse-AFC frame may speculate that its FIC decodes (reset when that failed)
   int last_start = -1;     // PRS peak index of the last verified frame (-1: none since the time sync)
   bool ofdm_reset = true;  // OfdmDecoder::reset() pending
+  int state_cur = 0;       // which of the recording's two OfdmStateDev buffers holds its state (a window writes the other one
+                           // and the buffers swap when it is committed: a window that fails verification needs no restore)
+  // stream continuation (dabstar_decoder_import_state): the next run continues a stream instead of starting one
+  long long abs_pos0 = 0;  // stream index of sample 0 of this run's input
+  long long abs_frames = 0;// frames of the stream decoded before this run
+  int hist = 0;            // frame slots of soft-bit history in front of slot_base (the 16-CIF time de-interleaver reaches 4 frames back)
+  int held_state = 0;      // ... 0: in front of a frame (EVAL), 1: in front of a time-sync search, 2: before the stream's first sample
+  bool held = false;       // streaming: the run stopped in front of a frame (or a time-sync search) the chunk does not hold completely
   // bookkeeping
   long long slot_base = 0; // first frame slot of this recording in the soft-bit / FIB buffers
   int slot_cap = 0;
@@ -1041,7 +1049,7 @@ struct Recording
   std::vector<uint8_t> tii_flags; // ... per frame, as known from the previous pass over this recording (see dabstar_decoder_run)
   std::vector<int> cif_hi_f, cif_lo_f; // auto_cfg: CIF counter as the FIB decoder holds it after each frame's FIC (-1: none yet)
   dabstar_ensemble_info ens{};
-  long long cnt_good_fibs = 0, cnt_sync_ok = 0, cnt_sync_fail = 0, cnt_windows = 0, cnt_cut = 0, cnt_heavy = 0;
+  long long cnt_good_fibs = 0, cnt_sync_ok = 0, cnt_sync_fail = 0, cnt_windows = 0, cnt_cut = 0, cnt_heavy = 0, cnt_warmup = 0;
   // window scratch
   int w_first_desc = 0, w_frames = 0;
   bool w_careful = false;
@@ -1060,8 +1068,20 @@ struct dabstar_decoder
   DevBuf d_crc;         // [total_slots][12]
   DevBuf d_ber;         // [total_slots][8] int
   DevBuf d_X;           // window: [frames][77][1536] float2
-  DevBuf d_states;      // OfdmStateDev[n_rec]
-  DevBuf d_snap;        // snapshot of d_states
+  DevBuf d_states;      // OfdmStateDev[2][n_rec]: current / next state of every recording (Recording::state_cur)
+  int seg_frames = 0, seg_warmup = 0; // dabstar_decoder_set_segmentation
+  bool streaming = false;             // dabstar_decoder_set_streaming
+  struct Resume                       // dabstar_decoder_import_state: what the next run of a recording starts from
+  {
+    bool on = false;
+    long long stream_pos = 0, abs_frames = 0, lead = 0;
+    int rec_state = 0, osc_phase = 0, fic_ratio = 0, first_after_sync = 1, known_start = -2, spec_ok = 0, careful_spec = 1, last_start = -1, ofdm_reset = 1;
+    float f_sync = 0, f_bb = 0, clock_err = 0, phase_cp = 0;
+    int hist = 0;
+    std::vector<unsigned char> ofdm;  // OfdmStateDev
+    std::vector<int16_t> soft;        // hist x FRAME_SOFT
+  };
+  std::vector<Resume> resume;
   DevBuf d_desc, d_work, d_cp, d_start, d_coarse, d_dipw, d_dipr, d_jobs, d_mscbits, d_etibits, d_etipacked;
   DevBuf d_tii_fft;   // null-symbol spectra of one TII event, fft order
   DevBuf d_mscpacked; // MSC payload packed 8 bits per byte for the read-back
@@ -1115,6 +1135,7 @@ extern "C" int dabstar_decoder_create(dabstar_ctx * ctx, const dabstar_decoder_c
   if (d->cfg.max_window <= 0) d->cfg.max_window = 256;
   if (d->cfg.sync_threshold <= 0.0f) d->cfg.sync_threshold = 3.0f;
   d->recs.resize((size_t)n_recordings);
+  d->resume.resize((size_t)n_recordings);
   CK(cudaEventCreate(&d->ev0));
   CK(cudaEventCreate(&d->ev1));
   CK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
@@ -1273,7 +1294,7 @@ void ctl_begin_frame(Recording & r, int start_index, int n_syms, FrameCtl & fc)
   fc.desc.ph_eval = r.osc_phase;
   fc.desc.sym0 = r.pos + start_index;
   fc.desc.n_syms = n_syms;
-  fc.info.sym0_pos = fc.desc.sym0;
+  fc.info.sym0_pos = r.abs_pos0 + fc.desc.sym0;
   fc.info.start_index = start_index;
   fc.info.fbb_sym0 = r.f_bb;
   fc.info.fic_ratio_before = r.fic_ratio * 10;
@@ -1445,7 +1466,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
   UP(dec->d_recs.p, rin.data(), sizeof(RecInput) * (size_t)n_rec);
   const RecInput * d_rin = dec->d_recs.as<RecInput>();
 
-  // ---- per-recording reset (DabProcessor::run prologue, dab_processor.cpp:110-142)
+  // ---- per-recording reset (DabProcessor::run prologue, dab_processor.cpp:110-142), or continuation of a stream
   dec->total_slots = 0;
   for (int r = 0; r < n_rec; r++)
   {
@@ -1469,25 +1490,55 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
     for (auto & m : R.msc) { m.out_off = 0; m.out_len = 0; }
     R.d_iq = rin[r].iq;
     R.n = rin[r].n;
-    R.slot_base = dec->total_slots;
+    const dabstar_decoder::Resume & rs = dec->resume[r];
+    if (rs.on)
+    {
+      if (eti_on || auto_cfg || tii_cfg.on) return ctx->fail(DABSTAR_E_UNSUPPORTED, "stream continuation with ETI / self-configuration / TII is not supported");
+      if (rs.lead > R.n) return ctx->fail(DABSTAR_E_INVALID, "recording %d: %lld lead samples, %lld samples given", r, rs.lead, R.n);
+      R.hist = rs.hist;
+      R.abs_frames = rs.abs_frames;
+      R.abs_pos0 = rs.stream_pos - rs.lead;
+      R.pos = rs.lead;
+      R.osc_phase = rs.osc_phase; R.f_sync = rs.f_sync; R.f_bb = rs.f_bb; R.clock_err = rs.clock_err; R.phase_cp = rs.phase_cp; R.fic_ratio = rs.fic_ratio;
+      R.first_after_sync = rs.first_after_sync != 0; R.known_start = rs.known_start; R.spec_ok = rs.spec_ok != 0; R.careful_spec = rs.careful_spec != 0;
+      R.last_start = rs.last_start; R.ofdm_reset = rs.ofdm_reset != 0;
+      R.state = rs.rec_state == 1 ? RecState::WAIT_SYNC : RecState::EVAL;
+    }
+    R.slot_base = dec->total_slots + R.hist;
     // a frame consumes T_u + start_index + 75 T_s + T_n samples with start_index >= T_g - 250 (phasereference.cpp:136-139):
     // fewer than T_F when the sample clock runs fast or after a re-sync
     R.slot_cap = (int)(R.n / (T_U + (T_G - 250) + 75LL * T_S + T_N)) + 2;
-    dec->total_slots += R.slot_cap;
+    dec->total_slots += R.hist + R.slot_cap;
     R.frames.reserve((size_t)R.slot_cap);
     R.descs.reserve((size_t)R.slot_cap);
     R.crc_ok.reserve((size_t)R.slot_cap * 12);
-    R.pos = 20LL * T_U; // 20 reads of T_u samples for the level estimate, no mixing (f = 0)
-    R.state = R.pos <= R.n ? RecState::WAIT_SYNC : RecState::DONE;
-    R.ofdm_reset = true;
+    if (!rs.on)
+    {
+      R.pos = 20LL * T_U; // 20 reads of T_u samples for the level estimate, no mixing (f = 0)
+      R.state = R.pos <= R.n ? RecState::WAIT_SYNC : RecState::DONE;
+      if (R.state == RecState::DONE && dec->streaming) { R.pos = 0; R.held = true; R.held_state = 2; } // the chunk is shorter than the level estimate's 20 reads
+      R.ofdm_reset = true;
+    }
   }
   CK(dec->d_soft.reserve(sizeof(int16_t) * (size_t)dec->total_slots * FRAME_SOFT));
   CK(dec->d_fib.reserve((size_t)dec->total_slots * 3072));
   CK(dec->d_crc.reserve((size_t)dec->total_slots * 12));
   CK(dec->d_ber.reserve(sizeof(int) * (size_t)dec->total_slots * 8));
-  CK(dec->d_states.reserve(sizeof(OfdmStateDev) * (size_t)n_rec));
-  CK(dec->d_snap.reserve(sizeof(OfdmStateDev) * (size_t)n_rec));
-  if (int e = ofdm_state_init(ctx, dec->d_states.as<OfdmStateDev>(), true, n_rec)) return e;
+  CK(dec->d_states.reserve(sizeof(OfdmStateDev) * 2 * (size_t)n_rec));
+  if (int e = ofdm_state_init(ctx, dec->d_states.as<OfdmStateDev>(), true, 2 * n_rec)) return e;
+  for (int r = 0; r < n_rec; r++)
+  {
+    dabstar_decoder::Resume & rs = dec->resume[r];
+    if (!rs.on) continue;
+    // the stream's OFDM decoder state and the soft bits of its last frames (history of the time de-interleaver)
+    Recording & R = dec->recs[r];
+    CK(cudaMemcpyAsync(dec->d_states.as<OfdmStateDev>() + r, rs.ofdm.data(), sizeof(OfdmStateDev), cudaMemcpyHostToDevice, st));
+    if (R.hist > 0)
+      CK(cudaMemcpyAsync(dec->d_soft.as<int16_t>() + (size_t)(R.slot_base - R.hist) * FRAME_SOFT, rs.soft.data(), sizeof(int16_t) * (size_t)R.hist * FRAME_SOFT,
+                         cudaMemcpyHostToDevice, st));
+    SYNC(); // (pageable source)
+    rs.on = false; // consumed: a further run without a new import starts a new stream
+  }
   CK(cudaMemsetAsync(dec->d_crc.p, 0, (size_t)dec->total_slots * 12, st));
 
   tr("setup done");
@@ -1515,7 +1566,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
         R.known_start = -2;
         R.spec_ok = false;
         R.last_start = -1;
-        dw.push_back({ r, R.pos });
+        dw.push_back({ r, R.pos, R.abs_pos0 });
         who.push_back(r);
       }
       if (!dw.empty())
@@ -1538,6 +1589,14 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
         for (size_t i = 0; i < who.size(); i++)
         {
           Recording & R = dec->recs[who[i]];
+          if (dr[i].status == 3 && dec->streaming)
+          {
+            // the chunk ends inside the search: the next chunk repeats it from where it started
+            R.state = RecState::DONE;
+            R.held = true;
+            R.held_state = 1;
+            continue;
+          }
           R.pos = dr[i].pos;
           R.clock_err = 0.0f; // dab_processor.cpp:158
           if (dr[i].status == 0) { R.state = RecState::EVAL; R.cnt_sync_ok++; R.sync_frames.push_back(R.n_slots); }
@@ -1557,7 +1616,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       Recording & R = dec->recs[r];
       if (R.state == RecState::WAIT_SYNC) { any_wait = true; continue; }
       if (R.state != RecState::EVAL) continue;
-      if (R.pos + T_U > R.n) { R.state = RecState::DONE; continue; } // the eval read hits the end of the data
+      if (R.pos + T_U > R.n) { R.state = RecState::DONE; R.held = dec->streaming; R.held_state = 0; continue; } // the eval read hits the end of the data
       R.w_careful = (R.fic_ratio * 10 < 30) || (R.known_start == -2 && !R.spec_ok);
       R.w_first_desc = (int)ctl.size();
       R.w_frames = 0;
@@ -1683,6 +1742,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
           fc.desc.xslot = (int)ctl.size();
           pl.t_frames++;
           if (avail >= 75LL * T_S + T_N) { ctl.push_back(fc); p = after_sym0 + 75LL * T_S + T_N; continue; }
+          if (dec->streaming) { pl.t_frames--; break; } // a chunk of a longer stream: the frame is left for the next chunk
           // the recording ends inside this frame: the reference still decodes the symbols it could read
           fc.desc.n_syms = (int)std::min<long long>(75, avail / T_S);
           ctl.push_back(fc);
@@ -1836,7 +1896,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
             R.pos += T_U;
             R.state = RecState::WAIT_SYNC;
           }
-          else R.state = RecState::DONE; // nothing left to read
+          else { R.state = RecState::DONE; R.held = dec->streaming; R.held_state = 0; } // nothing left to read
           continue;
         }
         R.w_first_desc = (int)ctl.size();
@@ -1863,22 +1923,33 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
     FrameDesc * d_fd = dec->d_desc.as<FrameDesc>();
 
     // ---- heavy pass: FFT (+ingest, derotation, de-interleave) -> demap -> FIC
-    CK(dec->d_work.reserve(sizeof(DemapWork) * plans.size() + 64));
     CK(dec->d_X.reserve((size_t)x_frame_bytes * (size_t)n_desc));
     dec->span_begin(ST_FFT);
     CK(launch_fft_frames(st, ctx->tab, d_fd, n_desc, d_rin, fmt, dec->d_X.as<float2>(), &ctx->launches));
     dec->span_end();
-    // snapshot of the decoder states (copy kernel: a D2D cudaMemcpyAsync may queue behind the recording upload on a copy engine)
-    k_upload<<<64, 256, 0, st>>>(dec->d_snap.as<unsigned char>(), dec->d_states.as<unsigned char>(), sizeof(OfdmStateDev) * (size_t)n_rec);
-    ctx->launches++;
-    CK(cudaGetLastError());
     {
+      // One demapper run per recording, or several SEGMENTS when a long window of one recording would otherwise be one serial
+      // chain: segment s > 0 starts from reset() state `seg_warmup` frames early (their spectra are in the window's buffer
+      // anyway) and discards those frames' soft bits. The window's result goes to the recording's OTHER state buffer; the
+      // buffers swap when the window is committed, so a window that fails verification leaves the state untouched.
       std::vector<DemapWork> wk;
       for (auto & pl : plans)
       {
         Recording & R = dec->recs[pl.rec];
-        wk.push_back({ R.w_first_desc, (int)pl.fr.size(), pl.rec, R.ofdm_reset ? 1 : 0 });
+        const int n = (int)pl.fr.size();
+        const int s_in = pl.rec + R.state_cur * n_rec, s_out = pl.rec + (R.state_cur ^ 1) * n_rec;
+        int n_seg = 1;
+        if (dec->seg_frames > 0 && n >= 2 * dec->seg_frames) n_seg = n / dec->seg_frames;
+        for (int sg = 0; sg < n_seg; sg++)
+        {
+          const int b = (int)((long long)n * sg / n_seg), e = (int)((long long)n * (sg + 1) / n_seg);
+          const int w = sg == 0 ? 0 : std::min(dec->seg_warmup, b);
+          const bool from_state = b - w == 0; // reaches back to the window's first frame: continue from the recording's state (exact)
+          wk.push_back({ R.w_first_desc + b - w, e - b + w, s_in, sg == n_seg - 1 ? s_out : -1, from_state ? (R.ofdm_reset ? 1 : 0) : 1, w });
+          if (sg > 0) R.cnt_warmup += w;
+        }
       }
+      CK(dec->d_work.reserve(sizeof(DemapWork) * wk.size() + 64));
       DemapWork * d_wk = dec->d_work.as<DemapWork>();
       UP(d_wk, wk.data(), sizeof(DemapWork) * wk.size());
       dec->span_begin(ST_DEMAP);
@@ -1996,6 +2067,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
           else { R.partial_syms = ctl[i].desc.n_syms; R.state = RecState::DONE; }
         }
         R.fic_ratio = ratio;
+        R.state_cur ^= 1; // the demapper wrote the state after this window into the other buffer
         R.last_start = pl.fr.back().info.start_index;
         if (ratio * 10 >= 30) R.careful_spec = true;
         R.ofdm_reset = false;
@@ -2024,16 +2096,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
         else { R.force_window = 0; R.spec_ok = false; } // careful mode follows from the ratio
       }
     }
-    if (need_restore)
-    {
-      for (int r : restore_recs)
-      {
-        k_upload<<<8, 256, 0, st>>>(reinterpret_cast<unsigned char *>(dec->d_states.as<OfdmStateDev>() + r), reinterpret_cast<unsigned char *>(dec->d_snap.as<OfdmStateDev>() + r),
-                                    sizeof(OfdmStateDev));
-        ctx->launches++;
-        CK(cudaGetLastError());
-      }
-    }
+    (void)need_restore; // (the OFDM state of a rolled-back recording is still in its current buffer)
   }
 
   // ================= self-configuration: sub-channels and CIF counter from the recording's own FIC (FIG 0/0, 0/1)
@@ -2193,13 +2256,17 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       {
         MscOut & m = R.msc[c];
         const VitProfile & p = ctx->profiles[m.profile];
-        const int g_start = 4 * m.sc.start_frame;
-        const int n_out = std::max(0, n_cifs - (g_start + 16));
+        // start_frame counts the frames of the STREAM; CIF indices here are relative to this run's first frame, and a run
+        // that continues a stream finds the CIFs of the last R.hist frames in front of its own (negative indices)
+        const long long g_abs = 4LL * ((long long)m.sc.start_frame - R.abs_frames);
+        const int g_start = (int)std::max<long long>(g_abs, -4LL * R.hist);
+        const int g_first = std::max(g_start + 16, 0);
+        const int n_out = std::max(0, n_cifs - g_first);
         m.out_off = out_total;
         m.out_len = (long long)n_out * p.n_bits;
         if (n_out == 0) continue;
         int & nj = n_jobs_of[p.n_bits + 6];
-        by_steps[p.n_bits + 6].push_back(BackendJobRange{ R.slot_base * FRAME_SOFT, out_total, m.profile, p.n_bits, g_start, g_start + 16, n_out, m.sc.start_cu * 64, nj, 0 });
+        by_steps[p.n_bits + 6].push_back(BackendJobRange{ R.slot_base * FRAME_SOFT, out_total, m.profile, p.n_bits, g_start, g_first, n_out, m.sc.start_cu * 64, nj, 0 });
         nj += n_out;
         out_total += (long long)n_out * p.n_bits;
       }
@@ -2490,7 +2557,7 @@ extern "C" int dabstar_decoder_counters(const dabstar_decoder * dec, int recordi
 extern "C" int dabstar_decoder_quality(const dabstar_decoder * dec, int recording, float out[6])
 {
   if (!dec || !out || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
-  if (dec->d_states.cap < sizeof(OfdmStateDev) * dec->recs.size()) return DABSTAR_E_INVALID; // no run yet
+  if (dec->d_states.cap < sizeof(OfdmStateDev) * 2 * dec->recs.size()) return DABSTAR_E_INVALID; // no run yet
   dabstar_ctx * ctx = dec->ctx;
   CK(cudaSetDevice(ctx->device));
   // mMeanSigmaSqFreqCorr (ofdm_decoder.cpp:296-300): at symbol 1 of every frame, from the cyclic-prefix phase the
@@ -2503,7 +2570,7 @@ extern "C" int dabstar_decoder_quality(const dabstar_decoder * dec, int recordin
     sigma += 0.2f * (fc * fc - sigma);
     phase = fi.phase_cp;
   }
-  return quality_from_state(ctx, dec->d_states.as<OfdmStateDev>() + recording, sigma, out);
+  return quality_from_state(ctx, dec->d_states.as<OfdmStateDev>() + recording + (size_t)R.state_cur * dec->recs.size(), sigma, out);
 }
 extern "C" int dabstar_decoder_enable_tii(dabstar_decoder * dec, int recording, int enable, int frames_to_count, int threshold_db, int collisions, int sub_id)
 {
@@ -2535,5 +2602,115 @@ extern "C" int dabstar_decoder_stage_ms(const dabstar_decoder * dec, double ms[8
 {
   if (!dec || !ms || !launches) return DABSTAR_E_INVALID;
   for (int i = 0; i < 8; i++) { ms[i] = dec->stage_ms[i]; launches[i] = dec->stage_launches[i]; }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ long recordings: segments, stream continuation
+extern "C" int dabstar_decoder_set_segmentation(dabstar_decoder * dec, int segment_frames, int warmup_frames)
+{
+  if (!dec || segment_frames < 0 || warmup_frames < 0) return DABSTAR_E_INVALID;
+  dec->seg_frames = segment_frames;
+  dec->seg_warmup = warmup_frames;
+  return 0;
+}
+extern "C" int dabstar_decoder_set_streaming(dabstar_decoder * dec, int enable)
+{
+  if (!dec) return DABSTAR_E_INVALID;
+  dec->streaming = enable != 0;
+  return 0;
+}
+extern "C" int64_t dabstar_decoder_warmup_frames(const dabstar_decoder * dec, int recording)
+{
+  if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  return (int64_t)dec->recs[recording].cnt_warmup;
+}
+extern "C" int64_t dabstar_decoder_consumed(const dabstar_decoder * dec, int recording)
+{
+  if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  const Recording & R = dec->recs[recording];
+  return (int64_t)(R.abs_pos0 + R.pos);
+}
+
+namespace
+{
+// What a DabProcessor, its OfdmDecoder and its Backends' de-interleavers carry from one frame to the next
+// (dab_processor.cpp:110-265, ofdm_decoder.h:89-103, backend.cpp:129-161), as one relocatable block of bytes.
+struct StateBlobHdr
+{
+  uint32_t magic, version;
+  int64_t bytes;
+  int64_t stream_pos;   // stream index of the first sample the decoder has not consumed
+  int64_t abs_frames;   // frames of the stream decoded so far
+  int32_t rec_state;    // 0: in front of a frame, 1: in front of a time-sync search, 2: nothing decoded yet (start of a stream)
+  int32_t osc_phase, fic_ratio, first_after_sync, known_start, spec_ok, careful_spec, last_start, ofdm_reset;
+  float f_sync, f_bb, clock_err, phase_cp;
+  int32_t hist;         // frames of soft bits that follow the OFDM state (0..4)
+  int32_t reserved[7];
+};
+constexpr uint32_t STATE_MAGIC = 0x31534244u; // "DBS1"
+int hist_frames_after(const Recording & R) { return (int)std::min<long long>(4, (long long)R.hist + R.n_slots); }
+} // namespace
+
+extern "C" int64_t dabstar_decoder_state_size(const dabstar_decoder * dec, int recording)
+{
+  if (!dec || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  return (int64_t)(sizeof(StateBlobHdr) + sizeof(OfdmStateDev) + sizeof(int16_t) * (size_t)hist_frames_after(dec->recs[recording]) * FRAME_SOFT);
+}
+
+extern "C" int64_t dabstar_decoder_export_state(dabstar_decoder * dec, int recording, void * blob, int64_t cap)
+{
+  if (!dec || !blob || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
+  dabstar_ctx * ctx = dec->ctx;
+  const Recording & R = dec->recs[recording];
+  if (dec->d_states.cap < sizeof(OfdmStateDev) * 2 * dec->recs.size()) return ctx->fail(DABSTAR_E_INVALID, "export_state: no run yet");
+  if (R.partial_syms > 0 || (R.state == RecState::DONE && !R.held && R.pos > 0))
+    return ctx->fail(DABSTAR_E_INVALID, "export_state: the run decoded into the end of its input; enable dabstar_decoder_set_streaming for chunked input");
+  const int64_t need = dabstar_decoder_state_size(dec, recording);
+  if (cap < need) return ctx->fail(DABSTAR_E_INVALID, "export_state: %lld bytes needed, %lld given", (long long)need, (long long)cap);
+  CK(cudaSetDevice(ctx->device));
+  StateBlobHdr h;
+  memset(&h, 0, sizeof(h));
+  h.magic = STATE_MAGIC; h.version = 1; h.bytes = need;
+  h.stream_pos = R.abs_pos0 + R.pos;
+  h.abs_frames = R.abs_frames + R.n_slots;
+  h.rec_state = R.held_state;
+  h.osc_phase = R.osc_phase; h.fic_ratio = R.fic_ratio; h.first_after_sync = R.first_after_sync ? 1 : 0; h.known_start = R.known_start;
+  h.spec_ok = R.spec_ok ? 1 : 0; h.careful_spec = R.careful_spec ? 1 : 0; h.last_start = R.last_start; h.ofdm_reset = R.ofdm_reset ? 1 : 0;
+  h.f_sync = R.f_sync; h.f_bb = R.f_bb; h.clock_err = R.clock_err; h.phase_cp = R.phase_cp;
+  h.hist = hist_frames_after(R);
+  unsigned char * o = static_cast<unsigned char *>(blob);
+  memcpy(o, &h, sizeof(h));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(o + sizeof(h), dec->d_states.as<OfdmStateDev>() + recording + (size_t)R.state_cur * dec->recs.size(), sizeof(OfdmStateDev), cudaMemcpyDeviceToHost));
+  if (h.hist > 0)
+    CK(cudaMemcpy(o + sizeof(h) + sizeof(OfdmStateDev), dec->d_soft.as<int16_t>() + (size_t)(R.slot_base + R.n_slots - h.hist) * FRAME_SOFT,
+                  sizeof(int16_t) * (size_t)h.hist * FRAME_SOFT, cudaMemcpyDeviceToHost));
+  return need;
+}
+
+extern "C" int dabstar_decoder_import_state(dabstar_decoder * dec, int recording, const void * blob, int64_t size, int64_t lead_samples)
+{
+  if (!dec || !blob || recording < 0 || recording >= (int)dec->recs.size() || lead_samples < 0) return DABSTAR_E_INVALID;
+  dabstar_ctx * ctx = dec->ctx;
+  StateBlobHdr h;
+  if (size < (int64_t)sizeof(h)) return ctx->fail(DABSTAR_E_INVALID, "import_state: truncated blob");
+  memcpy(&h, blob, sizeof(h));
+  if (h.magic != STATE_MAGIC || h.version != 1 || h.bytes > size || h.hist < 0 || h.hist > 4 ||
+      h.bytes != (int64_t)(sizeof(h) + sizeof(OfdmStateDev) + sizeof(int16_t) * (size_t)h.hist * FRAME_SOFT) || h.rec_state < 0 || h.rec_state > 2)
+    return ctx->fail(DABSTAR_E_INVALID, "import_state: not a state blob of this library version");
+  if (lead_samples > h.stream_pos) return ctx->fail(DABSTAR_E_INVALID, "import_state: %lld lead samples in front of stream position %lld", (long long)lead_samples, (long long)h.stream_pos);
+  dabstar_decoder::Resume & rs = dec->resume[recording];
+  rs = dabstar_decoder::Resume();
+  if (h.rec_state == 2) return 0; // nothing had been decoded: the next run starts the stream
+  rs.on = true;
+  rs.stream_pos = h.stream_pos; rs.abs_frames = h.abs_frames; rs.lead = lead_samples;
+  rs.rec_state = h.rec_state; rs.osc_phase = h.osc_phase; rs.fic_ratio = h.fic_ratio; rs.first_after_sync = h.first_after_sync; rs.known_start = h.known_start;
+  rs.spec_ok = h.spec_ok; rs.careful_spec = h.careful_spec; rs.last_start = h.last_start; rs.ofdm_reset = h.ofdm_reset;
+  rs.f_sync = h.f_sync; rs.f_bb = h.f_bb; rs.clock_err = h.clock_err; rs.phase_cp = h.phase_cp;
+  rs.hist = h.hist;
+  const unsigned char * in = static_cast<const unsigned char *>(blob) + sizeof(h);
+  rs.ofdm.assign(in, in + sizeof(OfdmStateDev));
+  rs.soft.resize((size_t)h.hist * FRAME_SOFT);
+  if (h.hist > 0) memcpy(rs.soft.data(), in + sizeof(OfdmStateDev), sizeof(int16_t) * rs.soft.size());
   return 0;
 }

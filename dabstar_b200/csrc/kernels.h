@@ -38,18 +38,25 @@ struct OfdmStateDev
 constexpr double POW_ALL_BETA = 3.255208184782532e-06;   // (float)(0.005f / 1536.0f)
 constexpr float POW_ALL_DECAY = 0.9950124713222692f;     // (1 - beta)^1536
 
+// One serial run of the demapper: consecutive frames of one recording (a whole window, or one SEGMENT of it).
+// Segments ("frame batches with a warm-up prefix"): the per-carrier IIRs of OfdmDecoder run across all frames
+// of a stream, so a segment that does not start where the recording's state was left starts from reset() state `warmup`
+// frames early and throws those frames' soft bits away; only the segment that ends the window stores the state.
 struct DemapWork
 {
-  int desc_first;  // first FrameDesc of this recording in the window
-  int n_frames;
-  int state;       // index into the OfdmStateDev array
-  int reset;       // OfdmDecoder::reset() before the first frame (after a time-sync loss)
+  int desc_first;  // first FrameDesc of this run (warm-up frames included)
+  int n_frames;    // frames incl. warm-up
+  int state_in;    // OfdmStateDev the run starts from (index into the state array)
+  int state_out;   // where the state after the last frame is stored, -1: nowhere (in == out is allowed)
+  int reset;       // start from OfdmDecoder::reset() state instead of state_in's vectors (after a time-sync loss; warm-started segments)
+  int warmup;      // leading frames whose soft bits are not written
 };
 
 struct DipWork
 {
   int rec;
-  long long pos;   // stream position where TimeSyncer::read_samples_until_end_of_level_drop starts
+  long long pos;   // position (in this run's input) where TimeSyncer::read_samples_until_end_of_level_drop starts
+  long long abs0;  // stream index of the input's sample 0 (0 unless the run continues a stream): the level IIR's age
 };
 struct DipResult
 {

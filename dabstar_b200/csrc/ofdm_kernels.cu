@@ -814,7 +814,7 @@ __global__ void __launch_bounds__(TT > 0 ? TT : DM4_MAX_THREADS) k_demap4(const 
   const int k0 = 2 * t_rec;
   unsigned long long * my_ring = ring + (size_t)w * DM3_RING * DM3_WARPS;
 
-  OfdmStateDev & sd = states[wk.state];
+  const OfdmStateDev & sd = states[wk.state_in];
   CarrierPair st;
   if (wk.reset) st = CarrierPair{ f2(0.f), f2(0.f), f2(0.f), f2(0.f), f2(0.f) };
   else
@@ -843,6 +843,7 @@ __global__ void __launch_bounds__(TT > 0 ? TT : DM4_MAX_THREADS) k_demap4(const 
 
   // soft bits of symbol d (its unscaled values are in the stash); total = sum |r| of symbol d - 1 (unused for d = 0)
   auto emit = [&](int d, int o_row, float total) {
+    if (o_row < 0) return; // warm-up frame of a segment: the state advances, nothing is written
     const float w2 = d == 0 ? rcp_ftz(mean_value0) * W2 : rcp_ftz(total) * (W2 * (float)K_CARR);
     const float4 r = stash[(d & (STASH - 1)) * T + tid]; // (re0, re1, im0, im1)
     const float2 vre = mul2(make_float2(r.x, r.y), f2(w2)), vim = mul2(make_float2(r.z, r.w), f2(w2));
@@ -884,7 +885,7 @@ __global__ void __launch_bounds__(TT > 0 ? TT : DM4_MAX_THREADS) k_demap4(const 
     const FrameDesc fd = frames[wk.desc_first + fi];
     const float2 cterm = mul2(f2(fd.clock_err / 1024.0f * PI_F), gk);
     const int n_syms = fd.n_syms;
-    const int out_row0 = fd.slot * 75;
+    const int out_row0 = fi < wk.warmup ? -(1 << 30) : fd.slot * 75;
     const bool tii = null_is_tii != nullptr && null_is_tii[wk.desc_first + fi];
     {
       const float4 cur = next_row(); // X rows hold (re 2t, re 2t+1, im 2t, im 2t+1): register pairs as loaded
@@ -967,22 +968,28 @@ __global__ void __launch_bounds__(TT > 0 ? TT : DM4_MAX_THREADS) k_demap4(const 
     }
     emit(d, orow_ring[(d & (STASH - 1)) * (T >> 5)], tot);
   }
-  sd.integ[k0] = st.integ.x; sd.integ[k0 + 1] = st.integ.y;
-  sd.stddev[k0] = st.stddev.x; sd.stddev[k0 + 1] = st.stddev.y;
-  sd.mean_pow[k0] = st.mean_pow.x; sd.mean_pow[k0 + 1] = st.mean_pow.y;
-  sd.mean_sigma[k0] = st.mean_sigma.x; sd.mean_sigma[k0 + 1] = st.mean_sigma.y;
-  sd.null_pow[k0] = st.null_pow.x; sd.null_pow[k0 + 1] = st.null_pow.y;
-  sd.pow_acc[k0] = pow_acc.x; sd.pow_acc[k0 + 1] = pow_acc.y;
-  // mMeanValue after the last symbol (every other thread has read sd.mean_value before it published anything)
-  if (gw == 0 && g > 0)
+  if (wk.state_out < 0) return; // a segment that does not end the window: its state is not the recording's
+  OfdmStateDev & so = states[wk.state_out];
+  so.integ[k0] = st.integ.x; so.integ[k0 + 1] = st.integ.y;
+  so.stddev[k0] = st.stddev.x; so.stddev[k0 + 1] = st.stddev.y;
+  so.mean_pow[k0] = st.mean_pow.x; so.mean_pow[k0 + 1] = st.mean_pow.y;
+  so.mean_sigma[k0] = st.mean_sigma.x; so.mean_sigma[k0 + 1] = st.mean_sigma.y;
+  so.null_pow[k0] = st.null_pow.x; so.null_pow[k0 + 1] = st.null_pow.y;
+  so.pow_acc[k0] = pow_acc.x; so.pow_acc[k0 + 1] = pow_acc.y;
+  // mMeanValue after the last symbol (with state_out == state_in: every other thread has read mean_value before it published anything)
+  if (gw == 0)
   {
-    unsigned long long word = 0;
-    const unsigned long long * slot = my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM3_WARPS;
-    if (lane < DM3_WARPS) word = ld_volatile_global_b64(slot + lane);
-    const float tot = dm3_total(slot, word, (unsigned)g, lane);
-    if (lane == 0) sd.mean_value = tot / (float)K_CARR;
+    float tot = mean_value0 * (float)K_CARR;
+    if (g > 0)
+    {
+      unsigned long long word = 0;
+      const unsigned long long * slot = my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM3_WARPS;
+      if (lane < DM3_WARPS) word = ld_volatile_global_b64(slot + lane);
+      tot = dm3_total(slot, word, (unsigned)g, lane);
+    }
+    if (lane == 0) so.mean_value = g > 0 ? tot / (float)K_CARR : mean_value0;
   }
-  if (t_rec == 0) sd.pow_carry = pow_carry0 * powf(POW_ALL_DECAY, (float)g); // (only this thread reads or writes pow_carry)
+  if (t_rec == 0) so.pow_carry = pow_carry0 * powf(POW_ALL_DECAY, (float)g); // (only this thread reads or writes pow_carry)
 }
 
 // ------------------------------------------------------------------------------------------------ time sync (S1)
@@ -1021,7 +1028,7 @@ __global__ void __launch_bounds__(DIP_THREADS) k_dip_search(const DipWork * __re
   __syncthreads();
   float s_level = 0.0f;
   for (int w = 0; w < DIP_THREADS / 32; w++) s_level += redf[w];
-  s_level = LEVEL_ALPHA * s_level + (hist == p0 ? 0.1f * expf((float)p0 * loga) : 0.0f);
+  s_level = LEVEL_ALPHA * s_level + (hist == p0 ? 0.1f * expf((float)(p0 + wk.abs0) * loga) : 0.0f);
   __syncthreads();
 
   // phase 0: searching the dip (first check after 50 samples), phase 1: searching its end

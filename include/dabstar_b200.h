@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DABSTAR_ABI_VERSION 1
+#define DABSTAR_ABI_VERSION 2
 
 enum { DABSTAR_MEM_HOST = 0, DABSTAR_MEM_DEVICE = 1 };
 enum { DABSTAR_FMT_CF32 = 0, DABSTAR_FMT_U8 = 1, DABSTAR_FMT_I16 = 2 };
@@ -383,6 +383,38 @@ int     dabstar_decoder_quality(const dabstar_decoder * dec, int recording, floa
  * [4] speculation windows run, [5] windows cut short by verification, [6] frames decoded,
  * [7] frames sent through the FFT/demap/FIC pass (exceeds [6] by replayed and partial frames) */
 int     dabstar_decoder_counters(const dabstar_decoder * dec, int recording, int64_t out[8]);
+/* Frames demapped a second time as the warm-up of a segment (dabstar_decoder_set_segmentation) in the last run. */
+int64_t dabstar_decoder_warmup_frames(const dabstar_decoder * dec, int recording);
+/* ---- long recordings ("one long stream as frame batches with a warm-up prefix")
+ * The reference is a stream receiver: OfdmDecoder's per-carrier IIRs (ofdm/ofdm_decoder.cpp:182-251), DabProcessor's AFC / clock
+ * loops (main/dab_processor.cpp:191-265) and Backend's 16-CIF de-interleaver (backend/backend.cpp:129-161) run across all
+ * frames. Three controls map that onto batches:
+ *
+ * dabstar_decoder_set_segmentation: inside a run, a verified window of one recording that holds at least 2 x segment_frames
+ *   frames is demapped as floor(n / segment_frames) SEGMENTS in parallel instead of one serial chain. Frame positions, AFC, FFT,
+ *   FIC / MSC decoding and the time de-interleaver are not affected (they see the whole window: exact); only OfdmDecoder's
+ *   per-carrier state is approximated: a segment other than the first starts from reset() state warmup_frames early and
+ *   discards the soft bits of those frames. The IIR constants are 0.005 per symbol (mean power, sigma, std deviation: 1e-3
+ *   left after 18 frames) and 0.001 (phase integrator). segment_frames = 0 switches segments off (default).
+ *
+ * dabstar_decoder_set_streaming + export_state / import_state: the input of a run is a CHUNK of a longer stream. With streaming
+ *   enabled a frame (or a time-sync search) the chunk does not hold completely is left for the next chunk instead of being decoded
+ *   as far as the samples reach (what the reference does at the end of a file); dabstar_decoder_consumed() is the stream index
+ *   of the first sample not consumed. export_state writes everything the next chunk depends on (control loops, oscillator
+ *   phase, FIC success counter, OfdmDecoder state, the soft bits of the last 4 frames = 16 CIFs) into a relocatable blob;
+ *   import_state on any decoder (another context, GPU or process) makes that recording's next run continue the stream: its
+ *   input must begin lead_samples before the consumed position (lead > 0 gives the level estimate of a time re-synchronisation
+ *   its history, sample_reader.cpp:236; 2^21 samples make it exact). Decoding a recording in chunks gives bit for bit the
+ *   results of one run. dabstar_subch::start_frame counts frames of the stream; frame positions are reported as stream indices.
+ *   Not available together with self-configuration, ETI or TII. */
+int     dabstar_decoder_set_segmentation(dabstar_decoder * dec, int segment_frames, int warmup_frames);
+int     dabstar_decoder_set_streaming(dabstar_decoder * dec, int enable);
+int64_t dabstar_decoder_consumed(const dabstar_decoder * dec, int recording);
+int64_t dabstar_decoder_state_size(const dabstar_decoder * dec, int recording);
+/* returns the bytes written (= dabstar_decoder_state_size) or < 0 */
+int64_t dabstar_decoder_export_state(dabstar_decoder * dec, int recording, void * blob, int64_t cap);
+int     dabstar_decoder_import_state(dabstar_decoder * dec, int recording, const void * blob, int64_t size, int64_t lead_samples);
+
 /* Device time of the last dabstar_decoder_run in milliseconds (CUDA events on the context's stream). */
 double  dabstar_decoder_last_ms(const dabstar_decoder * dec);
 /* Device time and launch count per kernel family of the last run (CUDA events around every launch):

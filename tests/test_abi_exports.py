@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_symbols():
         assert hasattr(lib, name), name
     lib.dabstar_abi_version.restype = ctypes.c_int
-    assert lib.dabstar_abi_version() == 1
+    assert lib.dabstar_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():

@@ -248,6 +248,8 @@ def native_arm(args, rank, local_rank, world):
     stream = torch.cuda.Stream()
     ctx = api.Context(local_rank, stream=stream)
     dp = api.DabProcessor(R, input_format=api.FMT_U8, scan_mode=True, max_window=args.window, ctx=ctx)
+    if args.segment_frames > 0:
+        dp.set_segmentation(args.segment_frames, args.segment_warmup)
     d_ptrs = [dev[r].data_ptr() for r in range(R)]
     h_ptrs = [host[r].data_ptr() for r in range(R)]
     ns = [n_samples] * R
@@ -273,9 +275,12 @@ def native_arm(args, rank, local_rank, world):
         clocks.start()
         launches0 = ctx.kernel_launches
         stage_acc = {}
+        heavy_acc = [0.0, 0.0]
         e0.record(stream)
         for _ in range(args.steps):
             dp.run_ptrs(d_ptrs, ns, api.MEM_DEVICE)
+            heavy_acc[0] += dp.heavy_ms(False)
+            heavy_acc[1] += dp.heavy_ms(True)
             for k, (ms, ln) in dp.stage_ms().items():
                 a = stage_acc.setdefault(k, [0.0, 0])
                 a[0] += ms
@@ -337,6 +342,13 @@ def native_arm(args, rank, local_rank, world):
             peak_acs = 148 * 128 * sm_mhz * 1e6 / 4.0   # 4 lane-ops per add-compare-select
             d.update({"achieved_gacs": acs / 1e9, "frac_int_alu": acs / peak_acs, "mbit_s": 3072 * frames_per_step * args.steps / (ms / 1e3) / 1e6})
         stages[k] = d
+    # the FFT + demap STAGE as one span (its chunks overlap on two streams), against SURVEY.md 8(d)'s stage bytes: 76 symbols +
+    # null symbol of spectra in, soft bits out = 1 722 368 B per frame
+    stage_bytes = 77 * 2048 * 8 + 75 * 3072 * 2
+    gbs = stage_bytes * frames_per_step * args.steps / (max(heavy_acc[0], 1e-9) / 1e3) / 1e9
+    stages["fft_demap_stage"] = {"ms_per_step": heavy_acc[0] / args.steps, "with_fic_ms_per_step": heavy_acc[1] / args.steps, "algorithmic_bytes_per_frame": stage_bytes,
+                                 "achieved_gbs_stage": gbs, "frac_hbm_stage": gbs / hbm_peak,
+                                 "note": "first FFT launch to last demap launch of every window, CUDA events; the per-kernel times above overlap"}
     hbm_stages = {k: v for k, v in stages.items() if "achieved_gbs" in v}
     dom = max(hbm_stages, key=lambda k: hbm_stages[k]["ms_per_step"])
     roofline = {"kernel": {"ingest_fft": "k_fft_frames", "demap": "k_demap", "cp_corr": "k_cp_corr", "prs_corr": "k_prs_corr"}[dom], "bound": "hbm",
@@ -398,6 +410,8 @@ def main():
     ap.add_argument("--no-viterbi-sweep", action="store_true")
     ap.add_argument("--no-cpu-affinity", action="store_true", help="N > 1: do not pin each rank to the CPUs local to its GPU")
     ap.add_argument("--viterbi-frames", type=int, default=131072, help="logical frames per protection level in the Viterbi-only sweep")
+    ap.add_argument("--segment-frames", type=int, default=0, help="demap a recording's window as parallel segments of this many frames (0 = off)")
+    ap.add_argument("--segment-warmup", type=int, default=18)
     ap.add_argument("--cpu-worker", action="store_true")
     ap.add_argument("--cpu-lib", default="dabo")
     args = ap.parse_args()

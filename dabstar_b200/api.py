@@ -684,6 +684,10 @@ class DabProcessor:
         self.ctx.check(self.ctx.lib.dabstar_decoder_stage_ms(self.h, ms, ln), "dabstar_decoder_stage_ms")
         return {n: (ms[i], int(ln[i])) for i, n in enumerate(self.STAGES)}
 
+    def heavy_ms(self, with_fic: bool = True) -> float:
+        """Device milliseconds of the FFT + demap (+ FIC) passes of the last run(), one span per window (the chunks overlap)."""
+        return float(self.ctx.lib.dabstar_decoder_heavy_ms(self.h, int(with_fic)))
+
     def soft_bits(self, recording: int, frame: int) -> np.ndarray:
         out = np.zeros((75, 3072), np.int16)
         self.ctx.check(self.ctx.lib.dabstar_decoder_soft_bits(self.h, recording, frame, _ptr(out)), "dabstar_decoder_soft_bits")

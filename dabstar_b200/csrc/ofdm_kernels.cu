@@ -639,22 +639,30 @@ __global__ void __launch_bounds__(256) k_cp_corr(const FrameDesc * __restrict__ 
 
 // ------------------------------------------------------------------------------------------------ DQPSK demapper (D1-D4)
 // OfdmDecoder::decode_symbol (ofdm_decoder.cpp:147-355) for whole recordings. The per-carrier IIR chains are sequential
-// in time but independent across carriers, so the parallelism is recordings x carriers:
-//   * a recording's 1536 carriers are split into `slices` CTAs (2 adjacent carriers per thread: one 16-byte load per
-//     spectrum row, one 4-byte store per soft-bit plane), the slice count chosen by the launcher so that the CTAs of
-//     all recordings fill the 148 SMs evenly; the launch is cooperative, so every CTA is resident;
+// in time but independent across carriers, so the parallelism is (recordings or segments) x carriers:
+//   * a run (DemapWork: consecutive frames of one recording) is 3 CTAs of 128 threads; a thread owns 4 adjacent carriers
+//     = two pairs: one 32-byte piece of a spectrum row, one 8-byte store per soft-bit plane. The two carriers of a pair run
+//     in the two halves of the packed FP32 instructions (FADD2 / FMUL2 / FFMA2); the two pairs are independent dependency
+//     chains the scheduler interleaves;
 //   * the only coupling between carriers, mMeanValue (sum of |r| over the PREVIOUS symbol, ofdm_decoder.cpp:256,294),
 //     scales the OUTPUT only. Each warp publishes its partial sum of symbol g as one 64-bit word {g+1, sum} in a ring
 //     in global memory (L2), keeps its unscaled r in a shared-memory stash, and writes the soft bits of symbol
-//     g - LAG, whose scale (24 partial sums of symbol g - LAG - 1, added in a fixed order by every warp for itself)
+//     g - LAG, whose scale (12 partial sums of symbol g - LAG - 1, added in a fixed order by every warp for itself)
 //     was published several symbols ago: the tag check rarely fails (then the warp polls), and there is no barrier,
 //     cluster or designated reducer;
+//   * the launch is NOT cooperative: a CTA takes its work item from a ticket counter when it starts, so the CTAs a running
+//     CTA may wait for (the other slices of its run) either run already or are the next to start as soon as any CTA
+//     finishes: there is always a run with all slices resident, hence no deadlock, for any number of runs per launch;
+//   * spectrum rows arrive through a per-thread cp.async ring in shared memory, 8 rows deep: the load of row q + 8 is issued
+//     when row q is consumed and nothing reads a destination register in between;
 //   * 6.5 MUFU per carrier and symbol: rsqrt|X|^2 (shared by two symbols), rcp for the arctangent, sqrt(meanPow),
-//     rsqrt|z|^2, sqrt(|P|/|z|) and one reciprocal of the combined denominator.
-// (Earlier versions - one CTA per recording with IEEE division / atan2, a cluster of 4 CTAs exchanging through DSMEM, and a
-// scalar-FP32 form of the present scheme - were measured at 12.5 / 9.7 / 8.1 ms per 9984 frames and have been removed.)
+//     rsqrt|z|^2, sqrt(|P|/|z|) and one reciprocal of the combined denominator; the arctangent is a degree-13 odd minimax
+//     polynomial; x86 (i16)(float) semantics of the output conversion are checked once per thread and row.
+// History (ms per 9984 frames): one CTA per recording with IEEE division / atan2 12.5; cluster of 4 CTAs over DSMEM 9.7;
+// scalar FP32 with the ring 8.1; packed FP32, 2 carriers per thread, cooperative launch (k_demap4, round 1) 5.49 at 235 warp
+// instructions per thread and symbol of which ~87 are the recurrences; this kernel 5.58 at 366 per FOUR carriers (-28 %
+// instructions, same time: two warps per scheduler leave it bound by dependent-issue latency, profiles/r2_a_*).
 constexpr int DM3_RING = 64;           // > 2 * LAG + 2: a slot is never overwritten while a slower warp may still read it
-constexpr int DM3_WARPS = K_CARR / 64; // warps per recording
 constexpr int DM3_ROW4 = K_CARR / 2;   // float4 per spectrum row
 
 __device__ __forceinline__ float rcp_ftz(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
@@ -671,30 +679,6 @@ __device__ __forceinline__ void st_volatile_global_b64(unsigned long long * p, u
 {
   asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-
-// Sum of |r| over the 1536 carriers of the symbol with tag `tag`: lane l < 24 holds the word of warp l (possibly stale).
-__device__ __forceinline__ float dm3_total(const unsigned long long * slot, unsigned long long w, unsigned tag, int lane)
-{
-  while (__any_sync(0xffffffffu, lane < DM3_WARPS && (unsigned)(w >> 32) != tag)) w = ld_volatile_global_b64(slot + (lane < DM3_WARPS ? lane : 0));
-  float v = lane < DM3_WARPS ? __uint_as_float((unsigned)w) : 0.0f;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// ------------------------------------------------------------------------------------------------ DQPSK demapper, packed version
-// The scheme above with the arithmetic and the data path done for sm_100:
-//   * the two carriers of a thread run in the two halves of the packed FP32 instructions (FADD2 / FMUL2 / FFMA2): every
-//     multiply-add of the per-carrier recurrences is issued once for both carriers; only MUFU, min/max and the selects
-//     stay scalar;
-//   * spectrum rows arrive through a per-thread cp.async ring in shared memory, DM4_PF rows deep: the load of row q + 8
-//     is issued when row q is consumed and nothing reads a destination register in between (prefetch registers rotated
-//     with MOVs wait for the load at the first MOV, an effective distance of ONE row; a register ring rotated by unrolling
-//     the row loop was measured too and is worse, 9.7 ms against 7.6 ms: the loads in flight share the six scoreboards,
-//     and a wait on a shared scoreboard waits for the newest load);
-//   * x86 (i16)(float) semantics of the output conversion are checked once per thread and row (rare path) instead of
-//     once per value.
-constexpr int DM4_PF = 8; // rows in flight per thread (power of two)
 
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
@@ -777,105 +761,136 @@ __device__ __forceinline__ void dm4_pair(CarrierPair & st, float2 xr, float2 xi,
   o_im = mul2(zi, w1);
 }
 
-constexpr int DM4_MAX_THREADS = 384; // at least two slices per recording: leaves 170 registers per thread
-
-// LAG: symbols between the arithmetic of a symbol and the write of its soft bits (the scale of symbol d is the total of
-// symbol d - 1, which the other warps of the recording publish at their own pace). A longer lag averages the pace of
-// the 24 warps over more symbols before anybody has to wait.
 // x86 cvttss2si returns 0x80000000 out of range (to_i16): a value the GPU conversion saturated to 0x7fffffff must read 0 in
-// its low half, not 0xffff (start-up transient of SOFTDEC2). Checked once per thread and row; an out-of-line version of
-// the fix-up (so that the loop only tests and branches) was measured and is slower (5.87 against 5.48 ms).
+// its low half, not 0xffff (start-up transient of SOFTDEC2). Checked once per thread and row.
 __device__ __forceinline__ void dm4_fix_saturated(int & a, int & b, int & c, int & e)
 {
   a = a == 0x7fffffff ? 0 : a; b = b == 0x7fffffff ? 0 : b; c = c == 0x7fffffff ? 0 : c; e = e == 0x7fffffff ? 0 : e;
 }
 
-// TT: threads per CTA when known at compile time (the index arithmetic of the three shared-memory rings folds into shifts
-// and masks), 0 = take blockDim.x.
-template <int SOFT, int LAG, int TT>
-__global__ void __launch_bounds__(TT > 0 ? TT : DM4_MAX_THREADS) k_demap4(const DemapWork * __restrict__ work, const FrameDesc * __restrict__ frames,
-                                                     const uint8_t * __restrict__ null_is_tii, const float2 * __restrict__ X,
-                                                     const int16_t * __restrict__ rel_of_k, OfdmStateDev * __restrict__ states,
-                                                     int16_t * __restrict__ soft, unsigned long long * __restrict__ ring, int slices)
+// ------------------------------------------------------------------------------------------------ the demapper kernel
+constexpr int DM5_T = 128;                 // threads per CTA
+constexpr int DM5_SLICES = K_CARR / 4 / DM5_T; // 3 CTAs per recording
+constexpr int DM5_WARPS = K_CARR / 128;    // 12 warps per recording
+constexpr int DM5_PF = 8;                  // spectrum rows in flight per thread
+
+__device__ __forceinline__ float dm5_total(const unsigned long long * slot, unsigned long long w, unsigned tag, int lane)
+{
+  while (__any_sync(0xffffffffu, lane < DM5_WARPS && (unsigned)(w >> 32) != tag)) w = ld_volatile_global_b64(slot + (lane < DM5_WARPS ? lane : 0));
+  float v = lane < DM5_WARPS ? __uint_as_float((unsigned)w) : 0.0f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int SOFT, int LAG>
+__global__ void __launch_bounds__(DM5_T, 4) k_demap5(const DemapWork * __restrict__ work, const FrameDesc * __restrict__ frames,
+                                                      const uint8_t * __restrict__ null_is_tii, const float2 * __restrict__ X,
+                                                      const int16_t * __restrict__ rel_of_k, OfdmStateDev * __restrict__ states,
+                                                      int16_t * __restrict__ soft, unsigned long long * __restrict__ ring, unsigned * __restrict__ ticket)
 {
   constexpr int STASH = LAG + 1; // stash depth (power of two)
+  constexpr int T = DM5_T;
   static_assert((STASH & (STASH - 1)) == 0, "stash depth must be a power of two");
   static_assert(DM3_RING > 2 * LAG + 2, "a ring slot must not be overwritten while a slower warp may still read it");
-  extern __shared__ float4 dm4_smem[]; // [STASH][T] unscaled soft values of the last symbols | [DM4_PF][T] spectrum rows in flight | [STASH][T / 32] output rows
-  const int T = TT > 0 ? TT : (int)blockDim.x;
-  float4 * stash = dm4_smem;
-  float4 * rowbuf = dm4_smem + STASH * T;
-  int * orow_ring = reinterpret_cast<int *>(rowbuf + DM4_PF * T) + (threadIdx.x >> 5); // this warp's column: output row (slot * 75 + symbol - 1) of the last STASH symbols
-  const int w = blockIdx.x / slices, slice = blockIdx.x - w * slices;
+  extern __shared__ float4 dm5_smem[]; // [STASH][T][2] unscaled soft values of the last symbols | [DM5_PF][T][2] spectrum rows in flight | [STASH][T / 32] output rows
+  __shared__ unsigned s_ticket;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  float4 * stash = dm5_smem;
+  float4 * rowbuf = dm5_smem + STASH * T * 2;
+  int * orow_ring = reinterpret_cast<int *>(rowbuf + DM5_PF * T * 2) + (threadIdx.x >> 5);
+  const int w = (int)s_ticket / DM5_SLICES, slice = (int)s_ticket - w * DM5_SLICES;
   const DemapWork wk = work[w];
   const int tid = threadIdx.x, lane = tid & 31;
-  const int t_rec = slice * T + tid; // thread index within the recording: carriers 2 t_rec, 2 t_rec + 1
+  const int t_rec = slice * T + tid; // thread index within the recording: carriers 4 t_rec .. 4 t_rec + 3
   const int gw = t_rec >> 5;         // warp index within the recording
-  const int k0 = 2 * t_rec;
-  unsigned long long * my_ring = ring + (size_t)w * DM3_RING * DM3_WARPS;
+  const int k0 = 4 * t_rec;
+  unsigned long long * my_ring = ring + (size_t)w * DM3_RING * DM5_WARPS;
 
   const OfdmStateDev & sd = states[wk.state_in];
-  CarrierPair st;
-  if (wk.reset) st = CarrierPair{ f2(0.f), f2(0.f), f2(0.f), f2(0.f), f2(0.f) };
+  CarrierPair sa, sb;
+  float2 pow_a = f2(0.f), pow_b = f2(0.f);
+  if (wk.reset) sa = sb = CarrierPair{ f2(0.f), f2(0.f), f2(0.f), f2(0.f), f2(0.f) };
   else
-    st = CarrierPair{ make_float2(sd.integ[k0], sd.integ[k0 + 1]), make_float2(sd.stddev[k0], sd.stddev[k0 + 1]), make_float2(sd.mean_pow[k0], sd.mean_pow[k0 + 1]),
-                      make_float2(sd.mean_sigma[k0], sd.mean_sigma[k0 + 1]), make_float2(sd.null_pow[k0], sd.null_pow[k0 + 1]) };
+  {
+    const float4 v0 = *reinterpret_cast<const float4 *>(sd.integ + k0), v1 = *reinterpret_cast<const float4 *>(sd.stddev + k0),
+                 v2 = *reinterpret_cast<const float4 *>(sd.mean_pow + k0), v3 = *reinterpret_cast<const float4 *>(sd.mean_sigma + k0),
+                 v4 = *reinterpret_cast<const float4 *>(sd.null_pow + k0), v5 = *reinterpret_cast<const float4 *>(sd.pow_acc + k0);
+    sa = CarrierPair{ make_float2(v0.x, v0.y), make_float2(v1.x, v1.y), make_float2(v2.x, v2.y), make_float2(v3.x, v3.y), make_float2(v4.x, v4.y) };
+    sb = CarrierPair{ make_float2(v0.z, v0.w), make_float2(v1.z, v1.w), make_float2(v2.z, v2.w), make_float2(v3.z, v3.w), make_float2(v4.z, v4.w) };
+    pow_a = make_float2(v5.x, v5.y);
+    pow_b = make_float2(v5.z, v5.w);
+  }
   const float mean_value0 = sd.mean_value; // not touched by reset() (ofdm_decoder.cpp:90-101)
-  float2 pow_acc = wk.reset ? f2(0.f) : make_float2(sd.pow_acc[k0], sd.pow_acc[k0 + 1]);
   const float pow_carry0 = wk.reset ? 1.0f : sd.pow_carry; // mMeanPowerOvrAll = 1 at reset() (ofdm_decoder.cpp:98)
-  const float2 gk = make_float2((float)(K_CARR / 2 - rel_of_k[k0]) / (float)(K_CARR / 2), (float)(K_CARR / 2 - rel_of_k[k0 + 1]) / (float)(K_CARR / 2));
+  const float2 gka = make_float2((float)(K_CARR / 2 - rel_of_k[k0]) / (float)(K_CARR / 2), (float)(K_CARR / 2 - rel_of_k[k0 + 1]) / (float)(K_CARR / 2));
+  const float2 gkb = make_float2((float)(K_CARR / 2 - rel_of_k[k0 + 2]) / (float)(K_CARR / 2), (float)(K_CARR / 2 - rel_of_k[k0 + 3]) / (float)(K_CARR / 2));
   constexpr float W2 = SOFT == 0 ? -100.0f : -140.0f;
 
   const int total_rows = wk.n_frames * X_ROWS;
-  const float4 * rows = reinterpret_cast<const float4 *>(X + (size_t)(total_rows > 0 ? frames[wk.desc_first].xslot : 0) * X_ROWS * K_CARR) + t_rec;
-  const unsigned rowbuf_addr = smem_addr_u32(rowbuf + tid);
+  const float4 * rows = reinterpret_cast<const float4 *>(X + (size_t)(total_rows > 0 ? frames[wk.desc_first].xslot : 0) * X_ROWS * K_CARR) + 2 * t_rec;
+  const unsigned rowbuf_addr = smem_addr_u32(rowbuf + 2 * tid);
 #pragma unroll
-  for (int i = 0; i < DM4_PF; i++)
+  for (int i = 0; i < DM5_PF; i++)
   {
-    if (i < total_rows) cp_async16(rowbuf_addr + (unsigned)(i * T) * 16u, rows + (size_t)i * DM3_ROW4);
+    if (i < total_rows)
+    {
+      cp_async16(rowbuf_addr + (unsigned)(i * T) * 32u, rows + (size_t)i * DM3_ROW4);
+      cp_async16(rowbuf_addr + (unsigned)(i * T) * 32u + 16u, rows + (size_t)i * DM3_ROW4 + 1);
+    }
     cp_async_commit();
   }
 
-  float2 rr = f2(0.f), ri = f2(0.f), ref_abs = f2(0.f), ref_inv = f2(0.f);
+  float2 rra = f2(0.f), ria = f2(0.f), ref_abs_a = f2(0.f), ref_inv_a = f2(0.f);
+  float2 rrb = f2(0.f), rib = f2(0.f), ref_abs_b = f2(0.f), ref_inv_b = f2(0.f);
   int g = 0;               // symbols decoded so far; tag of symbol g is g + 1
   int q = 0;               // spectrum rows consumed so far
-  unsigned long long pre = 0; // ring words (lane l < 24: warp l) of the symbol whose total scales this iteration's output
+  unsigned long long pre = 0; // ring words (lane l < 12: warp l) of the symbol whose total scales this iteration's output
 
   // soft bits of symbol d (its unscaled values are in the stash); total = sum |r| of symbol d - 1 (unused for d = 0)
   auto emit = [&](int d, int o_row, float total) {
     if (o_row < 0) return; // warm-up frame of a segment: the state advances, nothing is written
     const float w2 = d == 0 ? rcp_ftz(mean_value0) * W2 : rcp_ftz(total) * (W2 * (float)K_CARR);
-    const float4 r = stash[(d & (STASH - 1)) * T + tid]; // (re0, re1, im0, im1)
-    const float2 vre = mul2(make_float2(r.x, r.y), f2(w2)), vim = mul2(make_float2(r.z, r.w), f2(w2));
-    int a = __float2int_rz(vre.x), b = __float2int_rz(vre.y), c = __float2int_rz(vim.x), e = __float2int_rz(vim.y);
-    if (max(max(a, b), max(c, e)) == 0x7fffffff) dm4_fix_saturated(a, b, c, e);
-    unsigned * o = reinterpret_cast<unsigned *>(soft + (size_t)o_row * SYM_BITS);
-    o[t_rec] = __byte_perm((unsigned)a, (unsigned)b, 0x5410);
-    o[K_CARR / 2 + t_rec] = __byte_perm((unsigned)c, (unsigned)e, 0x5410);
+    const float4 ra = stash[((d & (STASH - 1)) * T + tid) * 2], rb = stash[((d & (STASH - 1)) * T + tid) * 2 + 1]; // (re0, re1, im0, im1) of each pair
+    const float2 are = mul2(make_float2(ra.x, ra.y), f2(w2)), aim = mul2(make_float2(ra.z, ra.w), f2(w2));
+    const float2 bre = mul2(make_float2(rb.x, rb.y), f2(w2)), bim = mul2(make_float2(rb.z, rb.w), f2(w2));
+    int a0 = __float2int_rz(are.x), a1 = __float2int_rz(are.y), a2 = __float2int_rz(aim.x), a3 = __float2int_rz(aim.y);
+    int b0 = __float2int_rz(bre.x), b1 = __float2int_rz(bre.y), b2 = __float2int_rz(bim.x), b3 = __float2int_rz(bim.y);
+    if (max(max(max(a0, a1), max(a2, a3)), max(max(b0, b1), max(b2, b3))) == 0x7fffffff) { dm4_fix_saturated(a0, a1, a2, a3); dm4_fix_saturated(b0, b1, b2, b3); }
+    int16_t * o = soft + (size_t)o_row * SYM_BITS;
+    reinterpret_cast<uint2 *>(o)[t_rec] = make_uint2(__byte_perm((unsigned)a0, (unsigned)a1, 0x5410), __byte_perm((unsigned)b0, (unsigned)b1, 0x5410));
+    reinterpret_cast<uint2 *>(o + K_CARR)[t_rec] = make_uint2(__byte_perm((unsigned)a2, (unsigned)a3, 0x5410), __byte_perm((unsigned)b2, (unsigned)b3, 0x5410));
   };
-  // warp sum in a fixed order
   auto wsum = [](float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
   };
-  // the next spectrum row of this thread (its load was requested DM4_PF rows ago); requests row q + DM4_PF
+  // the next spectrum row of this thread (its load was requested DM5_PF rows ago); requests row q + DM5_PF
+  float4 cur_a, cur_b;
   auto next_row = [&]() {
-    cp_async_wait<DM4_PF - 1>();
-    const unsigned slot = (unsigned)((q & (DM4_PF - 1)) * T);
-    const float4 cur = rowbuf[slot + tid];
-    if (q + DM4_PF < total_rows) cp_async16(rowbuf_addr + slot * 16u, rows + (size_t)(q + DM4_PF) * DM3_ROW4);
+    cp_async_wait<DM5_PF - 1>();
+    const unsigned slot = (unsigned)((q & (DM5_PF - 1)) * T);
+    cur_a = rowbuf[(slot + tid) * 2];
+    cur_b = rowbuf[(slot + tid) * 2 + 1];
+    if (q + DM5_PF < total_rows)
+    {
+      cp_async16(rowbuf_addr + slot * 32u, rows + (size_t)(q + DM5_PF) * DM3_ROW4);
+      cp_async16(rowbuf_addr + slot * 32u + 16u, rows + (size_t)(q + DM5_PF) * DM3_ROW4 + 1);
+    }
     cp_async_commit();
     q++;
-    return cur;
   };
   // this row is the phase reference of the next symbol
-  auto set_reference = [&](float2 xr, float2 xi) {
-    rr = xr;
-    ri = xi;
-    const float2 p = fma2(xr, xr, mul2(xi, xi));
-    ref_inv = make_float2(rsqrt_ftz(p.x), rsqrt_ftz(p.y));
-    ref_abs = mul2(p, ref_inv);
+  auto set_reference = [&]() {
+    rra = make_float2(cur_a.x, cur_a.y); ria = make_float2(cur_a.z, cur_a.w);
+    rrb = make_float2(cur_b.x, cur_b.y); rib = make_float2(cur_b.z, cur_b.w);
+    const float2 pa = fma2(rra, rra, mul2(ria, ria)), pb = fma2(rrb, rrb, mul2(rib, rib));
+    ref_inv_a = make_float2(rsqrt_ftz(pa.x), rsqrt_ftz(pa.y));
+    ref_inv_b = make_float2(rsqrt_ftz(pb.x), rsqrt_ftz(pb.y));
+    ref_abs_a = mul2(pa, ref_inv_a);
+    ref_abs_b = mul2(pb, ref_inv_b);
   };
   float part_prev = 0.0f; // this thread's |r| sum of symbol g - 1, published (reduced over the warp) one symbol late
   const bool upper = (lane & 16) != 0;
@@ -883,64 +898,57 @@ __global__ void __launch_bounds__(TT > 0 ? TT : DM4_MAX_THREADS) k_demap4(const 
   for (int fi = 0; fi < wk.n_frames; fi++)
   {
     const FrameDesc fd = frames[wk.desc_first + fi];
-    const float2 cterm = mul2(f2(fd.clock_err / 1024.0f * PI_F), gk);
+    const float cfac = fd.clock_err / 1024.0f * PI_F;
+    const float2 cterm_a = mul2(f2(cfac), gka), cterm_b = mul2(f2(cfac), gkb);
     const int n_syms = fd.n_syms;
     const int out_row0 = fi < wk.warmup ? -(1 << 30) : fd.slot * 75;
     const bool tii = null_is_tii != nullptr && null_is_tii[wk.desc_first + fi];
-    {
-      const float4 cur = next_row(); // X rows hold (re 2t, re 2t+1, im 2t, im 2t+1): register pairs as loaded
-      set_reference(make_float2(cur.x, cur.y), make_float2(cur.z, cur.w)); // store_reference_symbol_0
-    }
+    next_row();
+    set_reference(); // store_reference_symbol_0
     for (int sym = 1; sym <= 75; sym++)
     {
-      const float4 cur = next_row();
+      next_row();
       if (sym > n_syms) continue; // the recording ends inside this frame
-      const float2 xr = make_float2(cur.x, cur.y), xi = make_float2(cur.z, cur.w);
       const int d = g - LAG; // symbol whose soft bits are written in this iteration
-      // ONE shuffle chain, independent of this symbol's arithmetic (the scheduler overlaps the two), reduces two values:
-      // a: this warp's share of sum |r| of the PREVIOUS symbol, published under tag g (lower half warp);
-      // b: the total of symbol d - 1 from the ring words fetched one iteration ago (upper half warp; valid if every tag reads d).
-      // After the first exchange the lower lanes hold a[l] + a[l + 16], the upper ones b[l] + b[l - 16]; the remaining
-      // four steps stay inside a half, so both sums come out exactly as two separate butterflies would give them.
-      const float b_in = lane < DM3_WARPS ? __uint_as_float((unsigned)pre) : 0.0f;
-      const bool tags_ok = __all_sync(0xffffffffu, lane >= DM3_WARPS || (unsigned)(pre >> 32) == (unsigned)d);
+      // ONE shuffle chain, independent of this symbol's arithmetic, reduces two values: this warp's share of sum |r| of the PREVIOUS symbol (lower half warp) and
+      // the total of symbol d - 1 from the ring words fetched one iteration ago (upper half warp)
+      const float b_in = lane < DM5_WARPS ? __uint_as_float((unsigned)pre) : 0.0f;
+      const bool tags_ok = __all_sync(0xffffffffu, lane >= DM5_WARPS || (unsigned)(pre >> 32) == (unsigned)d);
       const unsigned long long pre_used = pre;
-      // ring words for the NEXT iteration's output (symbol d + 1 is scaled by the total of symbol d, published at
-      // iteration d + 1 of every warp): requested now, a whole iteration before they are looked at
-      if (d >= 0 && lane < DM3_WARPS) pre = ld_volatile_global_b64(my_ring + (size_t)(d & (DM3_RING - 1)) * DM3_WARPS + lane);
+      if (d >= 0 && lane < DM5_WARPS) pre = ld_volatile_global_b64(my_ring + (size_t)(d & (DM3_RING - 1)) * DM5_WARPS + lane);
       float v = (upper ? b_in : part_prev) + __shfl_xor_sync(0xffffffffu, upper ? part_prev : b_in, 16);
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       const float tot_fast = __shfl_sync(0xffffffffu, v, 16);
-      float2 o_re, o_im, r_abs;
-      dm4_pair<SOFT>(st, xr, xi, rr, ri, ref_abs, ref_inv, cterm, o_re, o_im, r_abs, pow_acc);
-      part_prev = r_abs.x + r_abs.y;
-      stash[(g & (STASH - 1)) * T + tid] = make_float4(o_re.x, o_re.y, o_im.x, o_im.y);
+      float2 a_re, a_im, a_abs, b_re, b_im, b_abs;
+      dm4_pair<SOFT>(sa, make_float2(cur_a.x, cur_a.y), make_float2(cur_a.z, cur_a.w), rra, ria, ref_abs_a, ref_inv_a, cterm_a, a_re, a_im, a_abs, pow_a);
+      dm4_pair<SOFT>(sb, make_float2(cur_b.x, cur_b.y), make_float2(cur_b.z, cur_b.w), rrb, rib, ref_abs_b, ref_inv_b, cterm_b, b_re, b_im, b_abs, pow_b);
+      part_prev = (a_abs.x + a_abs.y) + (b_abs.x + b_abs.y);
+      stash[((g & (STASH - 1)) * T + tid) * 2] = make_float4(a_re.x, a_re.y, a_im.x, a_im.y);
+      stash[((g & (STASH - 1)) * T + tid) * 2 + 1] = make_float4(b_re.x, b_re.y, b_im.x, b_im.y);
       if (lane == 0) orow_ring[(g & (STASH - 1)) * (T >> 5)] = out_row0 + (sym - 1);
       __syncwarp();
-      // (the store sits behind the arithmetic so that the chain above shares a basic block with it)
       if (lane == 0 && g > 0)
-        st_volatile_global_b64(my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM3_WARPS + gw,
+        st_volatile_global_b64(my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM5_WARPS + gw,
                                ((unsigned long long)(unsigned)g << 32) | (unsigned long long)__float_as_uint(v));
       if (d >= 0)
       {
         float tot = tot_fast;
-        if (d > 0 && !tags_ok) tot = dm3_total(my_ring + (size_t)((d - 1) & (DM3_RING - 1)) * DM3_WARPS, pre_used, (unsigned)d, lane);
+        if (d > 0 && !tags_ok) tot = dm5_total(my_ring + (size_t)((d - 1) & (DM3_RING - 1)) * DM5_WARPS, pre_used, (unsigned)d, lane);
         emit(d, orow_ring[(d & (STASH - 1)) * (T >> 5)], tot);
       }
       g++;
-      set_reference(xr, xi);
+      set_reference();
     }
+    next_row(); // null symbol
+    if (n_syms == 75 && !tii)
     {
-      const float4 cur = next_row(); // null symbol
-      if (n_syms == 75 && !tii)
-      {
-        // store_null_symbol_without_tii (ofdm_decoder.cpp:114-130)
-        constexpr float MIN_POW = (1.0f / 32767.0f) * (1.0f / 32767.0f);
-        const float2 xr = make_float2(cur.x, cur.y), xi = make_float2(cur.z, cur.w);
-        const float2 p = add2(fma2(xr, xr, mul2(xi, xi)), f2(MIN_POW));
-        st.null_pow = fma2(add2(p, neg2(st.null_pow)), f2(0.05f), st.null_pow);
-      }
+      // store_null_symbol_without_tii (ofdm_decoder.cpp:114-130)
+      constexpr float MIN_POW = (1.0f / 32767.0f) * (1.0f / 32767.0f);
+      const float2 xra = make_float2(cur_a.x, cur_a.y), xia = make_float2(cur_a.z, cur_a.w), xrb = make_float2(cur_b.x, cur_b.y), xib = make_float2(cur_b.z, cur_b.w);
+      const float2 pa = add2(fma2(xra, xra, mul2(xia, xia)), f2(MIN_POW)), pb = add2(fma2(xrb, xrb, mul2(xib, xib)), f2(MIN_POW));
+      sa.null_pow = fma2(add2(pa, neg2(sa.null_pow)), f2(0.05f), sa.null_pow);
+      sb.null_pow = fma2(add2(pb, neg2(sb.null_pow)), f2(0.05f), sb.null_pow);
     }
   }
   cp_async_wait<0>();
@@ -949,7 +957,7 @@ __global__ void __launch_bounds__(TT > 0 ? TT : DM4_MAX_THREADS) k_demap4(const 
   {
     const float part = wsum(part_prev);
     if (lane == 0)
-      st_volatile_global_b64(my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM3_WARPS + gw,
+      st_volatile_global_b64(my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM5_WARPS + gw,
                              ((unsigned long long)(unsigned)g << 32) | (unsigned long long)__float_as_uint(part));
   }
   // drain: the last LAG symbols
@@ -961,34 +969,33 @@ __global__ void __launch_bounds__(TT > 0 ? TT : DM4_MAX_THREADS) k_demap4(const 
     float tot = 0.0f;
     if (d >= 1)
     {
-      const unsigned long long * slot = my_ring + (size_t)((d - 1) & (DM3_RING - 1)) * DM3_WARPS;
+      const unsigned long long * slot = my_ring + (size_t)((d - 1) & (DM3_RING - 1)) * DM5_WARPS;
       unsigned long long word = 0;
-      if (lane < DM3_WARPS) word = ld_volatile_global_b64(slot + lane);
-      tot = dm3_total(slot, word, (unsigned)d, lane);
+      if (lane < DM5_WARPS) word = ld_volatile_global_b64(slot + lane);
+      tot = dm5_total(slot, word, (unsigned)d, lane);
     }
     emit(d, orow_ring[(d & (STASH - 1)) * (T >> 5)], tot);
   }
   if (wk.state_out < 0) return; // a segment that does not end the window: its state is not the recording's
-  OfdmStateDev & so = states[wk.state_out];
-  so.integ[k0] = st.integ.x; so.integ[k0 + 1] = st.integ.y;
-  so.stddev[k0] = st.stddev.x; so.stddev[k0 + 1] = st.stddev.y;
-  so.mean_pow[k0] = st.mean_pow.x; so.mean_pow[k0 + 1] = st.mean_pow.y;
-  so.mean_sigma[k0] = st.mean_sigma.x; so.mean_sigma[k0 + 1] = st.mean_sigma.y;
-  so.null_pow[k0] = st.null_pow.x; so.null_pow[k0 + 1] = st.null_pow.y;
-  so.pow_acc[k0] = pow_acc.x; so.pow_acc[k0 + 1] = pow_acc.y;
-  // mMeanValue after the last symbol (with state_out == state_in: every other thread has read mean_value before it published anything)
-  if (gw == 0)
+  // mMeanValue after the last symbol, fetched BEFORE anything is stored: with state_out == state_in the other slices of the
+  // recording read mean_value when they start, which may be later than this (the launch is not cooperative); whoever can
+  // see the last symbol's total has been waited for by it, i.e. all slices have started and read their input state
+  float tot_last = mean_value0 * (float)K_CARR;
+  if (gw == 0 && g > 0)
   {
-    float tot = mean_value0 * (float)K_CARR;
-    if (g > 0)
-    {
-      unsigned long long word = 0;
-      const unsigned long long * slot = my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM3_WARPS;
-      if (lane < DM3_WARPS) word = ld_volatile_global_b64(slot + lane);
-      tot = dm3_total(slot, word, (unsigned)g, lane);
-    }
-    if (lane == 0) so.mean_value = g > 0 ? tot / (float)K_CARR : mean_value0;
+    unsigned long long word = 0;
+    const unsigned long long * slot = my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM5_WARPS;
+    if (lane < DM5_WARPS) word = ld_volatile_global_b64(slot + lane);
+    tot_last = dm5_total(slot, word, (unsigned)g, lane);
   }
+  OfdmStateDev & so = states[wk.state_out];
+  *reinterpret_cast<float4 *>(so.integ + k0) = make_float4(sa.integ.x, sa.integ.y, sb.integ.x, sb.integ.y);
+  *reinterpret_cast<float4 *>(so.stddev + k0) = make_float4(sa.stddev.x, sa.stddev.y, sb.stddev.x, sb.stddev.y);
+  *reinterpret_cast<float4 *>(so.mean_pow + k0) = make_float4(sa.mean_pow.x, sa.mean_pow.y, sb.mean_pow.x, sb.mean_pow.y);
+  *reinterpret_cast<float4 *>(so.mean_sigma + k0) = make_float4(sa.mean_sigma.x, sa.mean_sigma.y, sb.mean_sigma.x, sb.mean_sigma.y);
+  *reinterpret_cast<float4 *>(so.null_pow + k0) = make_float4(sa.null_pow.x, sa.null_pow.y, sb.null_pow.x, sb.null_pow.y);
+  *reinterpret_cast<float4 *>(so.pow_acc + k0) = make_float4(pow_a.x, pow_a.y, pow_b.x, pow_b.y);
+  if (gw == 0 && lane == 0) so.mean_value = g > 0 ? tot_last / (float)K_CARR : mean_value0;
   if (t_rec == 0) so.pow_carry = pow_carry0 * powf(POW_ALL_DECAY, (float)g); // (only this thread reads or writes pow_carry)
 }
 
@@ -1235,7 +1242,7 @@ cudaError_t launch_fft_batch(cudaStream_t s, const DeviceTables & t, const float
 }
 
 cudaError_t launch_fft_frames(cudaStream_t s, const DeviceTables & t, const FrameDesc * frames, int n_frames, const RecInput * recs, int fmt,
-                              float2 * X, unsigned long long * lc)
+                              float2 * X, int max_ctas_per_sm, unsigned long long * lc)
 {
   if (n_frames <= 0) return cudaSuccess;
   const int n_items = n_frames * X_ROWS;
@@ -1244,7 +1251,9 @@ cudaError_t launch_fft_frames(cudaStream_t s, const DeviceTables & t, const Fram
     constexpr int FMT = decltype(F)::value;
     constexpr int stage = 2 * fft_stage_bytes<FMT>();
     const LaunchProps lp = launch_props((const void *)k_fft_frames<FMT>, FFT_THREADS, stage, stage); // per device: resident CTAs per SM of this instantiation
-    const int per_sm = lp.err == cudaSuccess && lp.ctas_per_sm > 0 ? lp.ctas_per_sm : 4;
+    int per_sm = lp.err == cudaSuccess && lp.ctas_per_sm > 0 ? lp.ctas_per_sm : 4;
+    if (max_ctas_per_sm > 0) per_sm = std::min(per_sm, max_ctas_per_sm);
+    if (const char * ev = getenv("DABSTAR_FFT_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(ev))); // A/B switch: resident CTAs per SM
     k_fft_frames<FMT><<<std::min(n_items, lp.n_sm * per_sm), FFT_THREADS, stage, s>>>(frames, n_items, recs, t.w2048, t.bin_of_k, X);
   });
 }
@@ -1257,20 +1266,12 @@ cudaError_t launch_reorder_frames(cudaStream_t s, const DeviceTables & t, const 
   return cudaGetLastError();
 }
 
-size_t demap_ring_bytes(int n_work) { return sizeof(unsigned long long) * (size_t)std::max(n_work, 1) * DM3_RING * DM3_WARPS; }
-static size_t demap4_smem_bytes(int threads, int lag) { return sizeof(float4) * (size_t)(lag + 1 + DM4_PF) * (size_t)threads + sizeof(int) * (size_t)(lag + 1) * (size_t)(threads / 32); }
-template <int LAG, int TT> static const void * demap4_fn(int soft_bit_type)
+// exchange ring of the per-symbol sums (one word per warp of a recording and ring slot) + the ticket counter of k_demap5
+size_t demap_ring_bytes(int n_work) { return sizeof(unsigned long long) * (size_t)std::max(n_work, 1) * DM3_RING * DM5_WARPS + 256; }
+static size_t demap5_smem_bytes(int lag) { return sizeof(float4) * 2 * (size_t)(lag + 1 + DM5_PF) * DM5_T + sizeof(int) * (size_t)(lag + 1) * (DM5_T / 32); }
+template <int LAG> static const void * demap5_fn(int soft_bit_type)
 {
-  return soft_bit_type == 0 ? (const void *)k_demap4<0, LAG, TT> : (soft_bit_type == 1 ? (const void *)k_demap4<1, LAG, TT> : (const void *)k_demap4<2, LAG, TT>);
-}
-// the instantiation for a lag and a CTA size (compile-time sizes for the default lag's common slicings, else blockDim.x)
-static const void * demap4_fn_for(int lag, int threads, int soft_bit_type)
-{
-  if (lag == 3) return demap4_fn<3, 0>(soft_bit_type);
-  if (lag == 7) return demap4_fn<7, 0>(soft_bit_type);
-  if (threads == 256) return demap4_fn<15, 256>(soft_bit_type);
-  if (threads == 384) return demap4_fn<15, 384>(soft_bit_type);
-  return demap4_fn<15, 0>(soft_bit_type);
+  return soft_bit_type == 0 ? (const void *)k_demap5<0, LAG> : (soft_bit_type == 1 ? (const void *)k_demap5<1, LAG> : (const void *)k_demap5<2, LAG>);
 }
 
 cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork * work, int n_work, const FrameDesc * frames,
@@ -1281,51 +1282,23 @@ cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork
   if (soft_bit_type < 0 || soft_bit_type > 2) return cudaErrorInvalidValue;
   if (lc) (*lc)++;
   if (ring == nullptr) return cudaErrorInvalidValue;
-  // symbols between arithmetic and output: 15 by default (measured 5.57 ms per 9984 frames; 7: 5.62 ms, 3: 6.3 ms). Handing the ring
-  // words to the warp through cp.async as well (requested 8 symbols ahead) was measured at 5.67 ms and dropped.
-  static const int lag_env = getenv("DABSTAR_DEMAP_LAG") ? atoi(getenv("DABSTAR_DEMAP_LAG")) : 15;
-  static const int lag = lag_env == 3 ? 3 : (lag_env == 7 ? 7 : 15);
-  auto smem_bytes = [&](int threads) { return demap4_smem_bytes(threads, lag); };
-  // slices per recording: fill the SMs as evenly as the co-residency limit allows (opt-in and occupancy cached per device)
-  int n_sm = N_SM;
-  const int cand[7] = { 1, 2, 3, 4, 6, 8, 12 };
-  int best_s = 0, best_cap = 0;
-  long long best_cost = -1;
-  for (int ci = 0; ci < 7; ci++)
-  {
-    const int sl = cand[ci], threads = DM3_ROW4 / sl;
-    if (threads > DM4_MAX_THREADS) continue;
-    const void * fn_c = demap4_fn_for(lag, threads, soft_bit_type);
-    const LaunchProps lp = launch_props(fn_c, threads, smem_bytes(threads), smem_bytes(DM4_MAX_THREADS));
-    if (lp.err != cudaSuccess) return lp.err;
-    const int occ = lp.ctas_per_sm;
-    n_sm = lp.n_sm;
-    if (occ <= 0) continue;
-    const int cap = occ * n_sm;                       // CTAs that can be resident at once
-    const int per_launch = cap / sl;                  // recordings per launch
-    if (per_launch <= 0) continue;
-    // cost: every launch lasts as long as its busiest SM has threads to run (threads per SM summed over the launches)
-    long long cost = 0;
-    for (int first = 0; first < n_work; first += per_launch)
-      cost += (long long)((std::min(per_launch, n_work - first) * sl + n_sm - 1) / n_sm) * threads;
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = sl; best_cap = cap; }
-  }
-  if (best_s == 0) return cudaErrorLaunchOutOfResources;
-  const int threads = DM3_ROW4 / best_s, per_launch = std::max(1, best_cap / best_s);
-  const void * fn = demap4_fn_for(lag, threads, soft_bit_type);
-  cudaError_t e = cudaMemsetAsync(ring, 0, demap_ring_bytes(n_work), s);
-  for (int first = 0; first < n_work && e == cudaSuccess; first += per_launch)
-  {
-    const int n = std::min(per_launch, n_work - first);
-    const DemapWork * wk = work + first;
-    unsigned long long * rg = ring + (size_t)first * DM3_RING * DM3_WARPS;
-    const int16_t * rel = t.rel_of_k;
-    int sl = best_s;
-    void * args[] = { (void *)&wk, (void *)&frames, (void *)&null_is_tii, (void *)&X, (void *)&rel, (void *)&states, (void *)&soft, (void *)&rg, (void *)&sl };
-    e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)(n * best_s)), dim3((unsigned)threads), args, smem_bytes(threads), s);
-    if (lc && first > 0) (*lc)++;
-  }
-  return e;
+  // symbols between a symbol's arithmetic and the write of its soft bits: the stash is (lag + 1) x 4 KB of shared memory per
+  // CTA, so a shorter lag trades waiting on the slowest warp of a run against resident CTAs per SM (2 / 3 / 4 at lag 15 / 7 /
+  // 3). Measured (profiles/README.md): 288 CTAs (96 recordings) 5.57 / 5.61 / 7.07 ms, 576 CTAs (192 segments) - / 7.83 / 6.08 ms:
+  // the longest lag whose residency still holds the whole grid. DABSTAR_DEMAP_LAG = 3 | 7 | 15 overrides (A/B switch).
+  static const int lag_env = getenv("DABSTAR_DEMAP_LAG") ? atoi(getenv("DABSTAR_DEMAP_LAG")) : 0;
+  const int grid_ctas = n_work * DM5_SLICES;
+  const int lag = lag_env == 3 || lag_env == 7 || lag_env == 15 ? lag_env : (grid_ctas <= 2 * N_SM ? 15 : (grid_ctas <= 3 * N_SM ? 7 : 3));
+  const void * fn = lag == 3 ? demap5_fn<3>(soft_bit_type) : (lag == 15 ? demap5_fn<15>(soft_bit_type) : demap5_fn<7>(soft_bit_type));
+  const size_t smem = demap5_smem_bytes(lag);
+  const LaunchProps lp = launch_props(fn, DM5_T, smem, smem); // opt-in for the dynamic shared memory, once per device
+  if (lp.err != cudaSuccess) return lp.err;
+  cudaError_t e = cudaMemsetAsync(ring, 0, demap_ring_bytes(n_work), s); // ring tags and the ticket counter
+  if (e != cudaSuccess) return e;
+  unsigned * ticket = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(ring) + demap_ring_bytes(n_work) - 256);
+  const int16_t * rel = t.rel_of_k;
+  void * args[] = { (void *)&work, (void *)&frames, (void *)&null_is_tii, (void *)&X, (void *)&rel, (void *)&states, (void *)&soft, (void *)&ring, (void *)&ticket };
+  return cudaLaunchKernel(fn, dim3((unsigned)(n_work * DM5_SLICES)), dim3(DM5_T), args, smem, s);
 }
 
 cudaError_t launch_cp_corr(cudaStream_t s, const FrameDesc * frames, int n_frames, const RecInput * recs, int fmt, float2 * cp, unsigned long long * lc)

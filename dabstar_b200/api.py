@@ -308,6 +308,16 @@ class PhaseReference:
         return out
 
 
+def cp_correlate(frames: np.ndarray, ctx: Context | None = None) -> np.ndarray:
+    """Cyclic-prefix correlation of DabProcessor::_process_ofdm_symbols_1_to_L (dab_processor.cpp:317-333): frames = complex64[n, 75 * 2552]
+    (symbols 1..75 with prefixes) -> complex64[n]."""
+    ctx = ctx or default_context()
+    x = _np(frames, np.complex64).reshape(-1, 75 * 2552)
+    out = np.zeros(x.shape[0], np.complex64)
+    ctx.check(ctx.lib.dabstar_cp_correlate(ctx.h, _ptr(x), x.shape[0], _ptr(out), MEM_HOST), "dabstar_cp_correlate")
+    return out
+
+
 class ViterbiSpiral:
     """support/viterbi_spiral/viterbi_spiral.h:20 — deconvolve() over a batch of equally long code words."""
 

@@ -988,6 +988,35 @@ extern "C" int dabstar_estimate_carrier_offset(dabstar_ctx * ctx, const float * 
   return stage_out_end(ctx, dout, offset_hz, sizeof(int32_t) * (size_t)n, mem);
 }
 
+// Stage tap of the cyclic-prefix correlation (main/dab_processor.cpp:317-333,366): samples = n frames x (75 x T_s) complex floats, the
+// data symbols 1..75 of each frame WITH their cyclic prefixes, as DabProcessor reads them; out[f] = sum over the 75 symbols and
+// the 504 prefix samples of x[i + T_u] conj(x[i]) (re, im): the value whose argument becomes the fine frequency correction.
+extern "C" int dabstar_cp_correlate(dabstar_ctx * ctx, const float * samples, int n, float * out, int mem)
+{
+  if (!ctx || !samples || !out || n < 0) return DABSTAR_E_INVALID;
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  const long long per = 75LL * T_S;
+  const void * din; void * dout;
+  if (int r = stage_in(ctx, ctx->scratch[0], samples, sizeof(float2) * (size_t)per * n, mem, &din)) return r;
+  if (int r = stage_out_begin(ctx, ctx->scratch[1], out, sizeof(float2) * (size_t)n, mem, &dout)) return r;
+  std::vector<FrameDesc> fd((size_t)n);
+  for (int f = 0; f < n; f++)
+  {
+    memset(&fd[f], 0, sizeof(FrameDesc));
+    fd[f].sym0 = (long long)f * per - T_U; // the kernel's symbol 1 starts T_u after sym0
+    fd[f].n_syms = 75;
+  }
+  const RecInput rin{ din, per * n };
+  CK(ctx->scratch[3].reserve(sizeof(FrameDesc) * fd.size() + sizeof(RecInput) + 64));
+  FrameDesc * dfd = ctx->scratch[3].as<FrameDesc>();
+  RecInput * drin = reinterpret_cast<RecInput *>(dfd + fd.size());
+  UP(dfd, fd.data(), sizeof(FrameDesc) * fd.size());
+  UP(drin, &rin, sizeof(rin));
+  CK(launch_cp_corr(ctx->stream, dfd, n, drin, FMT_CF32, (float2 *)dout, &ctx->launches));
+  return stage_out_end(ctx, dout, out, sizeof(float2) * (size_t)n, mem);
+}
+
 // ------------------------------------------------------------------------------------------------ whole path
 namespace
 {

@@ -299,6 +299,11 @@ int  dabstar_fib_parser_ensemble(const dabstar_fib_parser * p, dabstar_ensemble_
 int  dabstar_fib_parser_subchannels(const dabstar_fib_parser * p, dabstar_subch * out, int cap);
 int  dabstar_fib_parser_components(const dabstar_fib_parser * p, dabstar_service_comp * out, int cap);
 
+/* Cyclic-prefix correlation of DabProcessor::_process_ofdm_symbols_1_to_L (main/dab_processor.cpp:317-333): samples = n frames x
+ * 75 x 2552 complex floats (data symbols 1..75 of a frame with their prefixes); out = n x (re, im) of
+ * sum_sym sum_{i < 504} x[i + 2048] conj(x[i]); its argument, limited to +-20 degrees, is the fine AFC step (:236-251,366). */
+int dabstar_cp_correlate(dabstar_ctx * ctx, const float * samples, int n, float * out_re_im, int mem);
+
 /* ------------------------------------------------------------------------------------------------ whole path */
 typedef struct
 {

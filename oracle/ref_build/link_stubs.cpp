@@ -38,7 +38,11 @@ void IFibDecoder::signal_fib_time_info(const SUtcTimeSet &) {}
 void IFibDecoder::signal_fib_loaded_state(EFibLoadingState) {}
 
 // ---------------------------------------------------------------------------------------------------
-// FFTW3f shim: unnormalised DFT, sign as planned, double precision internally.
+// FFTW3f shim: unnormalised DFT, sign as planned.
+// Parity build (default): radix-2 in double precision, rounded to float (the golden vectors were made with it).
+// Timing build (-DDABREF_FAST_FFT, libdabref_fast.so): single-precision Stockham autosort radix-4 (+ one radix-2 pass for
+// n = 2^odd) with precomputed twiddles, the inner loops written so that gcc vectorises them: what stands in for FFTW's
+// speed when the reference's CPU chain is TIMED (bench.py); FFTW itself is third party and not installed.
 // ---------------------------------------------------------------------------------------------------
 struct fftwf_plan_s
 {
@@ -49,6 +53,10 @@ struct fftwf_plan_s
   std::vector<std::complex<double>> tw;   // e^{sign*j*2*pi*k/n}, k < n/2
   std::vector<int> rev;
   std::vector<std::complex<double>> work;
+#ifdef DABREF_FAST_FFT
+  std::vector<float> twr, twi;            // e^{sign*j*2*pi*k/n}, k < n (split re / im)
+  std::vector<float> ar, ai, br, bi;      // ping-pong work arrays (split re / im)
+#endif
 };
 
 extern "C" fftwf_plan fftwf_plan_dft_1d(int n, fftwf_complex * in, fftwf_complex * out, int sign, unsigned)
@@ -58,6 +66,16 @@ extern "C" fftwf_plan fftwf_plan_dft_1d(int n, fftwf_complex * in, fftwf_complex
   p->sign = sign;
   p->in = in;
   p->out = out;
+#ifdef DABREF_FAST_FFT
+  p->twr.resize(n); p->twi.resize(n);
+  for (int k = 0; k < n; k++)
+  {
+    const double a = (double)sign * 2.0 * M_PI * (double)k / (double)n;
+    p->twr[k] = (float)std::cos(a);
+    p->twi[k] = (float)std::sin(a);
+  }
+  p->ar.resize(n); p->ai.resize(n); p->br.resize(n); p->bi.resize(n);
+#else
   p->tw.resize(n / 2);
   for (int k = 0; k < n / 2; k++)
   {
@@ -74,13 +92,81 @@ extern "C" fftwf_plan fftwf_plan_dft_1d(int n, fftwf_complex * in, fftwf_complex
     p->rev[i] = r;
   }
   p->work.resize(n);
+#endif
   return p;
 }
+
+#ifdef DABREF_FAST_FFT
+// One Stockham pass of radix R over x (length n = R * l * m): y[(R j + q) m + k] = sum_r w^{j l_stride ...}; standard autosort form:
+// for j < l, k < m:  a_r = x[(j + r l) m + k];  y[(R j + q) m + k] = (sum_r a_r W_R^{r q}) * W_n^{q j m ... } (twiddle applied to inputs).
+static void stockham_radix4(int n, int l, int m, int sign, const float * xr, const float * xi, float * yr, float * yi, const float * twr, const float * twi)
+{
+  // x viewed as [4][l][m], y as [l][4][m]; twiddle w = W_n^{j m}
+  for (int j = 0; j < l; j++)
+  {
+    const int t1 = (j * m) % n, t2 = (2 * j * m) % n, t3 = (3 * j * m) % n;
+    const float w1r = twr[t1], w1i = twi[t1], w2r = twr[t2], w2i = twi[t2], w3r = twr[t3], w3i = twi[t3];
+    const float * x0r = xr + (size_t)j * m, * x0i = xi + (size_t)j * m;
+    const float * x1r = x0r + (size_t)l * m, * x1i = x0i + (size_t)l * m;
+    const float * x2r = x1r + (size_t)l * m, * x2i = x1i + (size_t)l * m;
+    const float * x3r = x2r + (size_t)l * m, * x3i = x2i + (size_t)l * m;
+    float * y0r = yr + (size_t)4 * j * m, * y0i = yi + (size_t)4 * j * m;
+    float * y1r = y0r + m, * y1i = y0i + m, * y2r = y1r + m, * y2i = y1i + m, * y3r = y2r + m, * y3i = y2i + m;
+    const float sg = (float)sign; // -j for the forward transform (sign = -1): multiply by sign * j
+    for (int k = 0; k < m; k++)
+    {
+      const float ar = x0r[k], ai = x0i[k], br_ = x1r[k], bi_ = x1i[k], cr = x2r[k], ci = x2i[k], dr = x3r[k], di = x3i[k];
+      const float s0r = ar + cr, s0i = ai + ci, s1r = ar - cr, s1i = ai - ci;
+      const float s2r = br_ + dr, s2i = bi_ + di, s3r = br_ - dr, s3i = bi_ - di;
+      // sign * j * s3
+      const float j3r = -sg * s3i, j3i = sg * s3r;
+      const float u0r = s0r + s2r, u0i = s0i + s2i;
+      const float u1r = s1r + j3r, u1i = s1i + j3i;
+      const float u2r = s0r - s2r, u2i = s0i - s2i;
+      const float u3r = s1r - j3r, u3i = s1i - j3i;
+      y0r[k] = u0r; y0i[k] = u0i;
+      y1r[k] = u1r * w1r - u1i * w1i; y1i[k] = u1r * w1i + u1i * w1r;
+      y2r[k] = u2r * w2r - u2i * w2i; y2i[k] = u2r * w2i + u2i * w2r;
+      y3r[k] = u3r * w3r - u3i * w3i; y3i[k] = u3r * w3i + u3i * w3r;
+    }
+  }
+}
+static void stockham_radix2(int n, int l, int m, const float * xr, const float * xi, float * yr, float * yi, const float * twr, const float * twi)
+{
+  for (int j = 0; j < l; j++)
+  {
+    const int t = (j * m) % n;
+    const float wr = twr[t], wi = twi[t];
+    const float * x0r = xr + (size_t)j * m, * x0i = xi + (size_t)j * m, * x1r = x0r + (size_t)l * m, * x1i = x0i + (size_t)l * m;
+    float * y0r = yr + (size_t)2 * j * m, * y0i = yi + (size_t)2 * j * m, * y1r = y0r + m, * y1i = y0i + m;
+    for (int k = 0; k < m; k++)
+    {
+      const float ar = x0r[k], ai = x0i[k], br_ = x1r[k], bi_ = x1i[k];
+      y0r[k] = ar + br_; y0i[k] = ai + bi_;
+      const float dr = ar - br_, di = ai - bi_;
+      y1r[k] = dr * wr - di * wi; y1i[k] = dr * wi + di * wr;
+    }
+  }
+}
+#endif
 
 extern "C" void fftwf_execute(const fftwf_plan p)
 {
   if (gHooks) gHooks->before_fft(p);
   const int n = p->n;
+#ifdef DABREF_FAST_FFT
+  float * xr = p->ar.data(), * xi = p->ai.data(), * yr = p->br.data(), * yi = p->bi.data();
+  for (int i = 0; i < n; i++) { xr[i] = p->in[i][0]; xi[i] = p->in[i][1]; }
+  // decimation in frequency, Stockham autosort: x is [R][l][m] with l * m * R = n; m grows by R every pass
+  int l = n, m = 1;
+  while (l > 1)
+  {
+    if (l % 4 == 0) { l /= 4; stockham_radix4(n, l, m, p->sign, xr, xi, yr, yi, p->twr.data(), p->twi.data()); m *= 4; }
+    else { l /= 2; stockham_radix2(n, l, m, xr, xi, yr, yi, p->twr.data(), p->twi.data()); m *= 2; }
+    std::swap(xr, yr); std::swap(xi, yi);
+  }
+  for (int i = 0; i < n; i++) { p->out[i][0] = xr[i]; p->out[i][1] = xi[i]; }
+#else
   auto & w = p->work;
   for (int i = 0; i < n; i++) w[p->rev[i]] = { (double)p->in[i][0], (double)p->in[i][1] };
   for (int len = 2; len <= n; len <<= 1)
@@ -102,6 +188,7 @@ extern "C" void fftwf_execute(const fftwf_plan p)
     p->out[i][0] = (float)w[i].real();
     p->out[i][1] = (float)w[i].imag();
   }
+#endif
   if (gHooks) gHooks->after_fft(p, (const float *)p->out);
 }
 

@@ -56,10 +56,12 @@ class Oracle:
         self.prefix = prefix
         if prefix == "dabo":
             path = build.build_oracle()
-        elif prefix == "dabref":
-            path = build.LIB_REF
+        elif prefix in ("dabref", "dabref_fast"):
+            # dabref_fast: the TIMING build of the same sources (AVX2 Viterbi, x86-64-v3, float FFT shim): bench.py only
+            path = build.LIB_REF if prefix == "dabref" else build.LIB_REF_FAST
             if not os.path.exists(path):
-                raise FileNotFoundError("oracle/_ref/libdabref.so is not built (needs /root/reference)")
+                raise FileNotFoundError(f"{path} is not built (needs /root/reference)")
+            self.prefix = prefix = "dabref"
         else:
             raise ValueError(prefix)
         self.lib = ctypes.CDLL(path)

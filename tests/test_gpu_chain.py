@@ -282,3 +282,59 @@ def test_config5_batch_snr_cfo_timing_sweep(ctx, oracle):
             assert abs(got.n_frames - want.n_frames) <= 1, (i, snrs[i])
             assert abs(got.n_good_fibs - want.n_good_fibs) <= max(3, want.n_good_fibs // 20), (i, got.n_good_fibs, want.n_good_fibs)
         want.close()
+
+
+# ---- parity in the shape the bench runs: 104-frame recordings (10 s), a batch in lock step, max_window = 128, scan mode
+@pytest.mark.parametrize("fmt,n_rec", [(synth.FMT_U8, 16), (synth.FMT_I16, 6)])
+def test_bench_shape_batch_of_10s_recordings(ctx, oracle, fmt, n_rec):
+    recs = [synth.generate(104, seed=300 + i, snr_db=15.0, fmt=fmt) for i in range(n_rec)]
+    dp = api.DabProcessor(n_rec, input_format=fmt, scan_mode=True, max_window=128, ctx=ctx)
+    dp.run([r.iq for r in recs])
+    for i, rec in enumerate(recs):
+        want = oracle.chain_run(oracle.to_cf32(rec.iq), scan_mode=1, tap_soft=(i % 4 == 0))
+        got = dp.result(i)
+        assert got.n_frames == want.n_frames == 104, i
+        assert [(a.sym0_pos, a.start_index, round(a.fbb_data)) for a in got.info] == [(b.sym0_pos, b.start_index, round(b.fbb_data)) for b in want.info]
+        assert np.array_equal(got.fic_valid, want.fic_valid) and want.fic_valid.all()
+        assert np.array_equal(got.fib_bits, want.fib_bits) and np.array_equal(got.fib_bits, rec.fib_truth)
+        assert got.n_good_fibs == want.n_good_fibs == 12 * 104
+        if i % 4 == 0:  # soft bits of the LAST frames: 103 frames of IIR history behind them
+            for f in (102, 103):
+                d = np.abs(dp.soft_bits(i, f).astype(np.int32) - want.soft_bits(f).astype(np.int32))
+                assert (d > 1).mean() <= 1e-4, (i, f, d.max())
+        want.close()
+
+
+def test_config0_ten_seconds_one_dabplus_subchannel(ctx, oracle):
+    """BASELINE configs[0] at its full size: 10 s = 104 frames, one DAB+ EEP 3-A 72 kbit/s sub-channel + FIC."""
+    rec = synth.generate(104, seed=1, snr_db=20.0, subch=[SC_3A], fmt=synth.FMT_U8)
+    want, dp, got = _run_both(oracle, ctx, rec, [SC_3A], synth.FMT_U8, max_window=128)
+    assert want.n_frames == 104
+    _compare(want, dp, got, [SC_3A], soft_frames=1)
+    for f in (52, 103):
+        d = np.abs(dp.soft_bits(0, f).astype(np.int32) - want.soft_bits(f).astype(np.int32))
+        assert (d > 1).mean() <= 1e-4, (f, d.max())
+    assert got.msc[3].shape[0] == 4 * 104 - 16 and np.array_equal(got.msc[3], rec.msc_truth[0][:got.msc[3].shape[0]])
+
+
+def test_snr_cfo_batch_config4_small(ctx, oracle):
+    """BASELINE configs[4] in small: recordings across the SNR sweep with kHz carrier offsets and random timing, in one batch.
+    At >= 10 dB everything is identical to the oracle; below, positions and CRC counts are compared."""
+    snrs = [3.0, 6.0, 9.0, 12.0, 15.0, 18.0, 21.0, 24.0, 27.0, 30.0]
+    rng = np.random.default_rng(9)
+    recs = [synth.generate(10, seed=500 + i, snr_db=s, cfo_hz=float(rng.uniform(-5000, 5000)), fmt=synth.FMT_U8, lead_samples=int(rng.integers(45000, 45000 + 196608)))
+            for i, s in enumerate(snrs)]
+    dp = api.DabProcessor(len(recs), input_format=synth.FMT_U8, scan_mode=True, ctx=ctx)
+    dp.run([r.iq for r in recs])
+    for i, (rec, snr) in enumerate(zip(recs, snrs)):
+        want = oracle.chain_run(oracle.to_cf32(rec.iq), scan_mode=1)
+        got = dp.result(i)
+        assert got.n_frames == want.n_frames, (snr, got.n_frames, want.n_frames)
+        assert [a.sym0_pos for a in got.info] == [b.sym0_pos for b in want.info], snr
+        if snr >= 10.0:
+            assert np.array_equal(got.fic_valid, want.fic_valid) and [round(a.fbb_data) for a in got.info] == [round(b.fbb_data) for b in want.info]
+            ok = want.fic_valid.astype(bool).repeat(768, axis=1)
+            assert np.array_equal(got.fib_bits[ok], want.fib_bits[ok])
+        else:
+            assert abs(got.n_good_fibs - want.n_good_fibs) <= max(3, want.n_good_fibs // 20), (snr, got.n_good_fibs, want.n_good_fibs)
+        want.close()

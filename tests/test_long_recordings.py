@@ -169,3 +169,28 @@ def test_export_state_needs_streaming(ctx):
         dp.export_state(0)
     with pytest.raises(api.DabstarError):
         dp.import_state(0, np.zeros(100, np.uint8))
+
+
+def test_stream_sharded_over_ranks_identical_bytes(ctx):
+    """parallel.stream_shard: one recording as three sample ranges, each decoded from a cold start a few frames early (what three
+    ranks do, here one after the other on one GPU): FIB bits, flags, positions and MSC bytes of the stitched result equal one run."""
+    from dabstar_b200 import parallel
+    rec = synth.generate(150, seed=47, snr_db=15.0, subch=SC, fmt=synth.FMT_U8)
+    one = api.DabProcessor(1, input_format=synth.FMT_U8, max_window=256, ctx=ctx)
+    one.set_audio_channel(0, SC)
+    one.run([rec.iq])
+    want = one.result(0)
+    parts = []
+    for rank in range(3):
+        sh = parallel.stream_shard(rec.iq.shape[0], rank, 3, warmup_frames=18)
+        dp = api.DabProcessor(1, input_format=synth.FMT_U8, max_window=256, ctx=ctx)
+        dp.set_audio_channel(0, SC)
+        dp.set_streaming(rank < 2)  # the last range ends the stream
+        parts.append(parallel.decode_stream_shard(dp, rec.iq[sh.in_lo:sh.in_hi], sh, SC))
+        assert parts[-1]["decoded_frames"] >= parts[-1]["frames"] + (25 if rank else 0) - 2
+    got = parallel.stitch(parts)
+    assert got["frames"] == want.n_frames == 150
+    assert got["pos"] == [i.sym0_pos for i in want.info]
+    assert np.array_equal(got["valid"], want.fic_valid) and np.array_equal(got["fib"], want.fib_bits)
+    for s in SC:
+        assert np.array_equal(got["msc"][s.sub_ch_id], want.msc[s.sub_ch_id]), s

@@ -694,6 +694,12 @@ class DabProcessor:
         self.ctx.check(self.ctx.lib.dabstar_decoder_stage_ms(self.h, ms, ln), "dabstar_decoder_stage_ms")
         return {n: (ms[i], int(ln[i])) for i, n in enumerate(self.STAGES)}
 
+    def msc_kernel_ms(self) -> tuple[float, float]:
+        """(gather, trellis) device milliseconds of the MSC pass of the last run()."""
+        a, b = ctypes.c_double(0), ctypes.c_double(0)
+        self.ctx.check(self.ctx.lib.dabstar_decoder_msc_kernel_ms(self.h, ctypes.byref(a), ctypes.byref(b)), "dabstar_decoder_msc_kernel_ms")
+        return a.value, b.value
+
     def heavy_ms(self, with_fic: bool = True) -> float:
         """Device milliseconds of the FFT + demap (+ FIC) passes of the last run(), one span per window (the chunks overlap)."""
         return float(self.ctx.lib.dabstar_decoder_heavy_ms(self.h, int(with_fic)))

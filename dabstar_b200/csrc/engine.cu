@@ -1134,8 +1134,8 @@ struct dabstar_decoder
   std::vector<Span> spans;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
-  double stage_ms[8] = { 0 };
-  long long stage_launches[8] = { 0 };
+  double stage_ms[10] = { 0 };   // [8], [9]: the MSC pass split into its gather and trellis kernels (VitSpanHook)
+  long long stage_launches[10] = { 0 };
   cudaEvent_t ev_get()
   {
     if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
@@ -1151,7 +1151,16 @@ struct dabstar_decoder
   int state_slots = 0;  // OfdmStateDev slots in d_states: 2 per recording + scratch for the segments of a window
   DevBuf d_descc;       // chunk-major copy of the window's descriptors
 };
-enum { ST_DIP = 0, ST_PRS = 1, ST_CP = 2, ST_COARSE = 3, ST_FFT = 4, ST_DEMAP = 5, ST_FIC = 6, ST_MSC = 7 };
+enum { ST_DIP = 0, ST_PRS = 1, ST_CP = 2, ST_COARSE = 3, ST_FFT = 4, ST_DEMAP = 5, ST_FIC = 6, ST_MSC = 7, ST_MSC_GATHER = 8, ST_MSC_TRELLIS = 9 };
+
+// VitSpanHook of the MSC pass: a span per kernel of every chunk
+static void msc_span_mark(void * user, int which, cudaStream_t stream)
+{
+  dabstar_decoder * dec = static_cast<dabstar_decoder *>(user);
+  // 0: gather kernel begins; 1: gather ends, trellis kernel begins; 2: trellis ends; 3: the warp-per-code-word kernel (gather fused) begins
+  if (which == 1 || which == 2) dec->span_end(stream);
+  if (which != 2) dec->span_begin(which == 0 ? ST_MSC_GATHER : ST_MSC_TRELLIS, stream);
+}
 
 static inline int mod_fs_host(long long x)
 {
@@ -1429,7 +1438,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
   dec->fft_demap_spans.clear();
   dec->heavy_ms = dec->fft_demap_ms = 0;
   dec->ev_used = 0;
-  for (int i = 0; i < 8; i++) { dec->stage_ms[i] = 0; dec->stage_launches[i] = 0; }
+  for (int i = 0; i < 10; i++) { dec->stage_ms[i] = 0; dec->stage_launches[i] = 0; }
   CK(cudaEventRecord(dec->ev0, st));
 
   static const bool trace = getenv("DABSTAR_TRACE") != nullptr; // per-round progress on stderr (debug aid)
@@ -2408,10 +2417,11 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
         UP(d_ranges, kv.second.data(), sizeof(BackendJobRange) * kv.second.size());
         CK(launch_expand_backend_jobs(st, d_ranges, (int)kv.second.size(), d_jobs, &ctx->launches));
         if (int e = reserve_viterbi_ws(ctx, n_jobs, kv.first)) return e;
-        dec->span_begin(ST_MSC);
-        CK(launch_viterbi(st, d_jobs, nullptr, n_jobs, ctx->d_profiles.as<VitProfile>(), kv.first, dec->d_soft.as<int16_t>(), dec->d_mscbits.as<uint8_t>(), ctx->tab.prbs,
-                          nullptr, nullptr, ctx->d_step_tab.as<unsigned>(), ctx->vit_ws.p, ctx->vit_ws.cap, &ctx->launches));
-        dec->span_end();
+        {
+          const VitSpanHook hook{ msc_span_mark, dec }; // one span per kernel (gather / trellis) instead of one around the launch
+          CK(launch_viterbi(st, d_jobs, nullptr, n_jobs, ctx->d_profiles.as<VitProfile>(), kv.first, dec->d_soft.as<int16_t>(), dec->d_mscbits.as<uint8_t>(), ctx->tab.prbs,
+                            nullptr, nullptr, ctx->d_step_tab.as<unsigned>(), ctx->vit_ws.p, ctx->vit_ws.cap, &ctx->launches, &hook));
+        }
         SYNC(); // d_jobs is reused by the next group
       }
       // the payload leaves the device packed 8 bits per byte in ONE copy into pinned memory (every logical frame is a whole
@@ -2736,6 +2746,14 @@ extern "C" int dabstar_decoder_stage_ms(const dabstar_decoder * dec, double ms[8
 {
   if (!dec || !ms || !launches) return DABSTAR_E_INVALID;
   for (int i = 0; i < 8; i++) { ms[i] = dec->stage_ms[i]; launches[i] = dec->stage_launches[i]; }
+  ms[ST_MSC] += dec->stage_ms[ST_MSC_GATHER] + dec->stage_ms[ST_MSC_TRELLIS]; // the MSC pass as a whole, as before
+  return 0;
+}
+extern "C" int dabstar_decoder_msc_kernel_ms(const dabstar_decoder * dec, double * gather_ms, double * trellis_ms)
+{
+  if (!dec || !gather_ms || !trellis_ms) return DABSTAR_E_INVALID;
+  *gather_ms = dec->stage_ms[ST_MSC_GATHER];
+  *trellis_ms = dec->stage_ms[ST_MSC_TRELLIS];
   return 0;
 }
 

@@ -71,9 +71,17 @@ int viterbi_smem_bytes(int max_steps, int warps);
 // step_tab: device copy of the profiles' step tables (VitProfile::tab_off). ws / ws_bytes: device workspace of the thread-per-code-word path (viterbi_ws_bytes() for one launch; a smaller
 // workspace makes the launcher work in chunks, none selects the warp-per-code-word kernel).
 size_t viterbi_ws_bytes(int n_jobs, int max_steps);
+// hook (optional): called on the launch stream before the gather kernel (0), between gather and trellis kernel (1) and after the
+// trellis kernel (2) of every chunk of the thread-per-code-word path, or before (3) and after (2) the warp-per-code-word kernel:
+// lets the caller time the kernels separately.
+struct VitSpanHook
+{
+  void (*mark)(void * user, int which, cudaStream_t stream);
+  void * user;
+};
 cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, const FrameDesc * fic_frames, int n_jobs, const VitProfile * profiles, int max_steps,
                            const int16_t * soft, uint8_t * out_bits, const uint8_t * prbs, uint8_t * crc_ok, int * ber,
-                           const unsigned * step_tab, void * ws, size_t ws_bytes, unsigned long long * launch_counter);
+                           const unsigned * step_tab, void * ws, size_t ws_bytes, unsigned long long * launch_counter, const VitSpanHook * hook = nullptr);
 
 // bits: one decoded bit per byte (8-byte aligned, n_bytes * 8 of them) -> out: n_bytes bytes, first bit most significant
 cudaError_t launch_expand_backend_jobs(cudaStream_t stream, const BackendJobRange * ranges, int n_ranges, VitJob * jobs, unsigned long long * launch_counter);

@@ -587,7 +587,7 @@ constexpr int VIT_TPC_MIN_JOBS = 2048;
 
 cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, const FrameDesc * fic_frames, int n_jobs, const VitProfile * profiles, int max_steps,
                            const int16_t * soft, uint8_t * out_bits, const uint8_t * prbs, uint8_t * crc_ok, int * ber,
-                           const unsigned * step_tab, void * ws, size_t ws_bytes, unsigned long long * launch_counter)
+                           const unsigned * step_tab, void * ws, size_t ws_bytes, unsigned long long * launch_counter, const VitSpanHook * hook)
 {
   if (n_jobs <= 0) return cudaSuccess;
   const int rows = tpc_rows(max_steps);
@@ -599,7 +599,12 @@ cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, const Frame
   int min_jobs = VIT_TPC_MIN_JOBS;
   if (const char * ev = getenv("DABSTAR_VITERBI_TPC_MIN")) min_jobs = atoi(ev);
   if (n_jobs < min_jobs || fit < 32 || step_tab == nullptr)
-    return launch_viterbi_warp(stream, jobs, fic_frames, n_jobs, profiles, max_steps, soft, out_bits, prbs, crc_ok, ber, launch_counter);
+  {
+    if (hook) hook->mark(hook->user, 3, stream);
+    const cudaError_t e = launch_viterbi_warp(stream, jobs, fic_frames, n_jobs, profiles, max_steps, soft, out_bits, prbs, crc_ok, ber, launch_counter);
+    if (hook) hook->mark(hook->user, 2, stream);
+    return e;
+  }
   const int chunk = (int)min((size_t)((n_jobs + 31) & ~31), fit);
   // DABSTAR_GATHER_BATCH = 1 or 2 code words per warp in flight at a time (A/B measurements)
   int gather_batch = 2;
@@ -611,9 +616,12 @@ cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, const Frame
     const int n = min(chunk, n_jobs - first);
     const int groups = (n + 31) / 32;
     const dim3 ggrid((unsigned)groups, (unsigned)((rows + GATHER_STEPS - 1) / GATHER_STEPS));
+    if (hook) hook->mark(hook->user, 0, stream);
     if (gather_batch >= 2) k_vit_gather<2><<<ggrid, 256, 0, stream>>>(jobs, fic_frames, first, n, profiles, step_tab, soft, sym, chunk, rows);
     else k_vit_gather<1><<<ggrid, 256, 0, stream>>>(jobs, fic_frames, first, n, profiles, step_tab, soft, sym, chunk, rows);
+    if (hook) hook->mark(hook->user, 1, stream);
     k_vit_tpc<<<groups, 32, 0, stream>>>(jobs, fic_frames, first, n, profiles, sym, surv, chunk, out_bits, prbs);
+    if (hook) hook->mark(hook->user, 2, stream);
     if (launch_counter) (*launch_counter) += 2;
     if (crc_ok != nullptr || ber != nullptr)
     {

@@ -428,6 +428,8 @@ double  dabstar_decoder_heavy_ms(const dabstar_decoder * dec, int with_fic /* 0:
 /* Device time and launch count per kernel family of the last run (CUDA events around every launch):
  * [0] time sync [1] PRS correlation [2] CP correlation [3] coarse AFC [4] ingest+FFT [5] demap [6] FIC Viterbi [7] MSC Viterbi */
 int     dabstar_decoder_stage_ms(const dabstar_decoder * dec, double ms[8], int64_t launches[8]);
+/* The MSC Viterbi time of [7] split into its two kernels: time de-interleave / depuncture gather, and trellis + chain back. */
+int     dabstar_decoder_msc_kernel_ms(const dabstar_decoder * dec, double * gather_ms, double * trellis_ms);
 
 #ifdef __cplusplus
 }

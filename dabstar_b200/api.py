@@ -655,6 +655,23 @@ class DabProcessor:
         lib.dabstar_decoder_counters(self.h, recording, _ptr(cnt))
         return RecordingResult(nf, list(info)[:nf], bits, valid, msc, cnt)
 
+    def n_frames(self, recording: int) -> int:
+        return int(self.ctx.check(self.ctx.lib.dabstar_decoder_n_frames(self.h, recording), "dabstar_decoder_n_frames"))
+
+    def counters(self, recording: int) -> np.ndarray:
+        """dabstar_decoder_counters: [good FIBs, time syncs, time-sync failures, samples consumed, windows run, windows cut, frames
+        decoded, frames through the heavy pass] of the last run(), without copying the decoded bits."""
+        cnt = np.zeros(8, np.int64)
+        self.ctx.check(self.ctx.lib.dabstar_decoder_counters(self.h, recording, _ptr(cnt)), "dabstar_decoder_counters")
+        return cnt
+
+    def frame_positions(self, recording: int) -> np.ndarray:
+        """Stream index of symbol 0 of every decoded frame."""
+        nf = self.n_frames(recording)
+        info = (FrameInfo * max(nf, 1))()
+        self.ctx.lib.dabstar_decoder_frame_info(self.h, recording, info, nf)
+        return np.array([info[i].sym0_pos for i in range(nf)], np.int64)
+
     def set_tii_processing(self, recording: int, on: bool = True, frames_to_count: int = 5, threshold_db: int = 8, collisions: bool = False, sub_id: int = 0):
         """DabProcessor::set_tii_processing / set_tii_threshold / set_tii_collisions / set_tii_sub_id (+ ProcessParams::tiiFramesToCount);
         needs set_auto_config (the CIF counter decides which null symbols carry TII)."""

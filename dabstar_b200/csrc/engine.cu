@@ -10,8 +10,10 @@
 #include "../../include/dabstar_b200.h"
 #include "kernels.h"
 #include "tables.h"
+#include "hostpool.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -113,6 +115,16 @@ struct dabstar_ctx
   DevBuf d_gf, d_fc_syn; // DAB+ outer code: GF(2^8) / Fire code tables (built on first use)
   HostBuf arena;        // pinned staging of small uploads; reused after every stream synchronisation
   size_t arena_off = 0;
+  std::unique_ptr<dab::HostPool> pool; // host threads of the per-recording control loops (created by the first decoder run)
+  dab::HostPool & host_pool()
+  {
+    if (!pool)
+    {
+      const char * ev = getenv("DABSTAR_HOST_THREADS"); // total threads incl. the caller (1 = serial)
+      pool.reset(new dab::HostPool(ev ? std::max(0, atoi(ev) - 1) : dab::HostPool::default_workers()));
+    }
+    return *pool;
+  }
 
   int fail(int code, const char * fmt, ...)
   {
@@ -1750,6 +1762,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       int next_start;           // measured PRS peak of the frame after fr (-2: not measured)
       int event;                // 1: the frame after the window has no PRS peak (time sync lost)
       int t_first, t_frames;    // this pass: descriptors of the tail being laid out
+      int t_last_syms;          // symbols of the last of them (< 75: the recording ends inside it)
     };
     std::vector<Plan> plans;
     for (int r : win_recs)
@@ -1758,16 +1771,18 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       int want = R.force_window > 0 ? R.force_window : ((R.w_careful && !R.careful_spec) ? 1 : dec->cfg.max_window);
       want = (int)std::min<long long>(want, std::max<long long>(1, budget / std::max<size_t>(1, win_recs.size())));
       want = std::min(want, R.slot_cap - R.n_slots);
-      plans.push_back({ r, want, {}, true, R.known_start, 0, 0, 0 });
+      plans.push_back({ r, want, {}, true, R.known_start, 0, 0, 0, 75 });
       plans.back().fr.reserve((size_t)std::max(want, 1));
     }
     const long long resident = resident_upto();
     bool first_pass = true;
+    dab::HostPool & pool = ctx->host_pool();
     while (true)
     {
-      // tail layout of the open plans
-      ctl.clear();
+      // tail layout of the open plans: positions first (a few integer operations per frame), then the descriptors of all
+      // plans filled in by the pool
       long long window_end = 0;
+      int n_laid = 0;
       for (auto & pl : plans)
       {
         if (!pl.open) continue;
@@ -1776,14 +1791,16 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
         long long p = R.pos;
         // host input still in flight: stay within what has arrived, but always reach into the chunk being copied
         const long long lim = host_in ? std::max(resident, (snaps[pl.rec].pos / dec->chunk_samples + 1) * dec->chunk_samples) : ((long long)1 << 62);
-        pl.t_first = (int)ctl.size();
+        pl.t_first = n_laid;
         pl.t_frames = 0;
+        pl.t_last_syms = 75;
         int room = pl.want - (int)pl.fr.size();
         {
-          // while the frame timing is still settling (the last peak was not at T_g) only one frame is probed per pass
+          // the peak of the frame after one whose peak was off T_g is not speculated (a detection that was a sample early is
+          // followed by one a sample late): probe that frame alone. A MEASURED peak (next_start) is a known start: the frames
+          // behind it are laid out at T_g straight away.
           const int prev = pl.fr.empty() ? R.last_start : pl.fr.back().info.start_index;
-          const int cur0 = pl.next_start >= 0 ? pl.next_start : (prev == T_G ? T_G : -1);
-          if (cur0 != T_G) room = std::min(room, 1);
+          if (pl.next_start < 0 && prev != T_G) room = std::min(room, 1);
         }
         for (int j = 0; j < room; j++)
         {
@@ -1792,26 +1809,39 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
           const long long after_sym0 = p + T_U + s;
           const long long avail = R.n - after_sym0;
           if (!(pl.fr.empty() && j == 0) && std::min<long long>(R.n, after_sym0 + 75LL * T_S + T_N) > lim) break;
-          FrameCtl fc;
-          memset(&fc, 0, sizeof(fc));
-          fc.desc.rec = pl.rec;
-          fc.desc.eval = p;
-          fc.desc.sym0 = p + s;
-          fc.desc.n_syms = 75;
-          fc.desc.slot = (int)(R.slot_base + R.n_slots + (int)pl.fr.size() + j);
-          fc.desc.xslot = (int)ctl.size();
           pl.t_frames++;
-          if (avail >= 75LL * T_S + T_N) { ctl.push_back(fc); p = after_sym0 + 75LL * T_S + T_N; continue; }
+          if (avail >= 75LL * T_S + T_N) { p = after_sym0 + 75LL * T_S + T_N; continue; }
           if (dec->streaming) { pl.t_frames--; break; } // a chunk of a longer stream: the frame is left for the next chunk
           // the recording ends inside this frame: the reference still decodes the symbols it could read
-          fc.desc.n_syms = (int)std::min<long long>(75, avail / T_S);
-          ctl.push_back(fc);
-          p = after_sym0 + (long long)fc.desc.n_syms * T_S;
+          pl.t_last_syms = (int)std::min<long long>(75, avail / T_S);
+          p = after_sym0 + (long long)pl.t_last_syms * T_S;
           break;
         }
         if (pl.t_frames == 0) { pl.open = false; continue; }
+        n_laid += pl.t_frames;
         window_end = std::max(window_end, p);
       }
+      ctl.resize((size_t)n_laid);
+      pool.parallel_for((int)plans.size(), [&](int pi) {
+        Plan & pl = plans[(size_t)pi];
+        if (!pl.open) return;
+        const Recording & R = dec->recs[pl.rec];
+        const int s0 = pl.next_start >= 0 ? pl.next_start : T_G;
+        long long p = R.pos;
+        for (int j = 0; j < pl.t_frames; j++)
+        {
+          const int s = j == 0 ? s0 : T_G;
+          FrameCtl & fc = ctl[(size_t)(pl.t_first + j)];
+          memset(&fc.desc, 0, sizeof(fc.desc));
+          fc.desc.rec = pl.rec;
+          fc.desc.eval = p;
+          fc.desc.sym0 = p + s;
+          fc.desc.n_syms = j == pl.t_frames - 1 ? pl.t_last_syms : 75;
+          fc.desc.slot = (int)(R.slot_base + R.n_slots + (int)pl.fr.size() + j);
+          fc.desc.xslot = pl.t_first + j;
+          p += T_U + s + 75LL * T_S + T_N;
+        }
+      });
       const int n_tail = (int)ctl.size();
       if (n_tail == 0) break;
       if (trace) fprintf(stderr, "[dabstar]     pass: %d tail frames\n", n_tail);
@@ -1889,7 +1919,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
           after[i] = take(R);
         }
       };
-      for (size_t pi = 0; pi < plans.size(); pi++) recur_plan(pi);
+      pool.parallel_for((int)plans.size(), [&](int pi) { recur_plan((size_t)pi); });
       for (int i = 0; i < n_tail; i++) fdv[i] = ctl[i].desc;
       UP(dec->d_desc.p, fdv.data(), sizeof(FrameDesc) * (size_t)n_tail);
       tr("  recurrences done");
@@ -1906,11 +1936,11 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       SYNC();
       tr("  prs synced");
 
-      bool any_open = false;
-      for (size_t pi = 0; pi < plans.size(); pi++)
-      {
+      std::atomic<int> n_open{ 0 };
+      pool.parallel_for((int)plans.size(), [&](int pi_) {
+        const size_t pi = (size_t)pi_;
         Plan & pl = plans[pi];
-        if (!pl.open) continue;
+        if (!pl.open) return;
         Recording & R = dec->recs[pl.rec];
         int valid = 0;
         for (int j = 0; j < pl.t_frames; j++)
@@ -1926,21 +1956,22 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
           // everything laid out in this pass verified; the next pass closes the plan when there is no room or no data left
           // (a pass may have been limited to one probe frame)
           if ((int)pl.fr.size() >= pl.want || pl.fr.back().desc.n_syms < 75) pl.open = false;
-          else any_open = true;
-          continue;
+          else n_open.fetch_add(1, std::memory_order_relaxed);
+          return;
         }
         restore(R, valid > 0 ? after[pl.t_first + valid - 1] : before_tail[pi]);
         const int sj = start[pl.t_first + valid];
         if (sj < 0) { pl.event = 1; pl.open = false; }
-        else { pl.next_start = sj; any_open = true; R.cnt_cut++; }
-      }
+        else { pl.next_start = sj; n_open.fetch_add(1, std::memory_order_relaxed); R.cnt_cut++; }
+      });
+      const bool any_open = n_open.load() > 0;
       first_pass = false;
       tr("layout pass done");
       if (!any_open) break;
     }
 
     // ---- this round's verified frames
-    ctl.clear();
+    int n_round = 0;
     {
       std::vector<Plan> kept;
       for (auto & pl : plans)
@@ -1959,9 +1990,9 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
           else { R.state = RecState::DONE; R.held = dec->streaming; R.held_state = 0; } // nothing left to read
           continue;
         }
-        R.w_first_desc = (int)ctl.size();
+        R.w_first_desc = n_round;
         R.w_frames = (int)pl.fr.size();
-        for (auto & fc : pl.fr) { fc.desc.xslot = (int)ctl.size(); ctl.push_back(fc); }
+        n_round += (int)pl.fr.size();
         budget -= (long long)pl.fr.size();
         kept.push_back(std::move(pl));
       }
@@ -1969,17 +2000,25 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
     }
     if (plans.empty()) continue;
     dec->cnt_rounds++;
-    const int n_desc = (int)ctl.size();
+    const int n_desc = n_round;
+    ctl.resize((size_t)n_desc);
+    std::vector<FrameDesc> fdv((size_t)n_desc);
+    pool.parallel_for((int)plans.size(), [&](int pi) {
+      Plan & pl = plans[(size_t)pi];
+      const int base = dec->recs[pl.rec].w_first_desc;
+      for (int j = 0; j < (int)pl.fr.size(); j++)
+      {
+        pl.fr[(size_t)j].desc.xslot = base + j;
+        ctl[(size_t)(base + j)] = pl.fr[(size_t)j];
+        fdv[(size_t)(base + j)] = pl.fr[(size_t)j].desc;
+      }
+    });
     if (trace)
       fprintf(stderr, "[dabstar] round %lld t=%.3f ms: %zu recordings, %d frames, chunks resident %d/%d waited %d\n", dec->cnt_rounds,
               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_run0).count(), plans.size(), n_desc, dec->chunks_done, dec->n_chunks,
               dec->chunks_waited);
-    {
-      std::vector<FrameDesc> fdv((size_t)n_desc);
-      for (int i = 0; i < n_desc; i++) fdv[i] = ctl[i].desc;
-      CK(dec->d_desc.reserve(sizeof(FrameDesc) * (size_t)n_desc + 64));
-      UP(dec->d_desc.p, fdv.data(), sizeof(FrameDesc) * (size_t)n_desc);
-    }
+    CK(dec->d_desc.reserve(sizeof(FrameDesc) * (size_t)n_desc + 64));
+    UP(dec->d_desc.p, fdv.data(), sizeof(FrameDesc) * (size_t)n_desc);
     FrameDesc * d_fd = dec->d_desc.as<FrameDesc>();
 
     // ---- heavy pass: FFT (+ingest, derotation, de-interleave) -> demap -> FIC
@@ -1997,22 +2036,26 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       const int nch = n_desc >= 1024 ? std::max(1, std::min(chunks_env, 16)) : 1; // small windows (acquisition): one chunk
       // chunk-major copy of the descriptors: what the FFT and the FIC decoder of a chunk walk (the demapper indexes the
       // recording-major array, where the frames of a recording and their spectra are consecutive)
-      std::vector<FrameDesc> fdc;
       std::vector<int> chunk_off((size_t)nch + 1, 0);
-      fdc.reserve((size_t)n_desc);
-      for (int c = 0; c < nch; c++)
+      const FrameDesc * d_fdc = d_fd; // one chunk: the recording-major array is the chunk
+      chunk_off[nch] = n_desc;
+      if (nch > 1)
       {
-        chunk_off[c] = (int)fdc.size();
-        for (auto & pl : plans)
+        std::vector<FrameDesc> fdc;
+        fdc.reserve((size_t)n_desc);
+        for (int c = 0; c < nch; c++)
         {
-          const int n = (int)pl.fr.size(), base = dec->recs[pl.rec].w_first_desc;
-          for (int j = (int)((long long)n * c / nch); j < (int)((long long)n * (c + 1) / nch); j++) fdc.push_back(ctl[base + j].desc);
+          chunk_off[c] = (int)fdc.size();
+          for (auto & pl : plans)
+          {
+            const int n = (int)pl.fr.size(), base = dec->recs[pl.rec].w_first_desc;
+            for (int j = (int)((long long)n * c / nch); j < (int)((long long)n * (c + 1) / nch); j++) fdc.push_back(ctl[base + j].desc);
+          }
         }
+        CK(dec->d_descc.reserve(sizeof(FrameDesc) * (size_t)n_desc + 64));
+        UP(dec->d_descc.p, fdc.data(), sizeof(FrameDesc) * (size_t)n_desc);
+        d_fdc = dec->d_descc.as<FrameDesc>();
       }
-      chunk_off[nch] = (int)fdc.size();
-      CK(dec->d_descc.reserve(sizeof(FrameDesc) * (size_t)n_desc + 64));
-      UP(dec->d_descc.p, fdc.data(), sizeof(FrameDesc) * (size_t)n_desc);
-      const FrameDesc * d_fdc = dec->d_descc.as<FrameDesc>();
 
       // demapper runs: (segment of a recording's window) x (chunk). Segment s > 0 starts from reset() state `seg_warmup`
       // frames early (their spectra are in the window's buffer anyway) and discards those frames' soft bits; a run hands
@@ -2146,10 +2189,9 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
 
     tr("heavy pass done");
     // ---- accept: the FIC success ratio must not have fallen below 30 % at a frame start (that frame needs the coarse AFC)
-    bool need_restore = false;
-    std::vector<int> restore_recs;
-    for (auto & pl : plans)
-    {
+    // (the OFDM state of a rolled-back recording is still in its current buffer: nothing to restore on the device)
+    pool.parallel_for((int)plans.size(), [&](int pi) {
+      Plan & pl = plans[(size_t)pi];
       Recording & R = dec->recs[pl.rec];
       R.cnt_windows++;
       R.cnt_heavy += (int)pl.fr.size();
@@ -2221,14 +2263,11 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
         // the FIC ratio fell below 30 % inside the window: roll back and replay the prefix that needs no coarse AFC
         R.cnt_cut++;
         restore(R, snaps[pl.rec]);
-        restore_recs.push_back(pl.rec);
-        need_restore = true;
         R.careful_spec = false;
         if (valid > 0) R.force_window = valid;
         else { R.force_window = 0; R.spec_ok = false; } // careful mode follows from the ratio
       }
-    }
-    (void)need_restore; // (the OFDM state of a rolled-back recording is still in its current buffer)
+    });
   }
 
   // ================= self-configuration: sub-channels and CIF counter from the recording's own FIC (FIG 0/0, 0/1)

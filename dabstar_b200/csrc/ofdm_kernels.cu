@@ -159,24 +159,60 @@ __device__ __forceinline__ SymbolItem symbol_item(const FrameDesc & fd, const Re
   return it;
 }
 
-// Raw samples reach the CTA through a double-buffered cp.async stage in shared memory: the 16-byte chunks that cover
-// the next symbol are requested before the current symbol is transformed, no register holds them meanwhile and no
-// instruction waits for them until the next iteration (register prefetch made the compiler sink the loads and the
-// first use stalled on HBM latency). Symbols within 8 samples of either end of a recording (where the 16-byte aligned
-// superset could leave the buffer) take the bounds-checked path.
+// Raw samples reach the CTA through a double-buffered stage in shared memory filled by the TMA engine: ONE thread issues one
+// bulk copy (cp.async.bulk, UBLKCP in SASS) of the 16-byte aligned superset of the next symbol's samples before the current
+// symbol is transformed, completion is signalled on an mbarrier the consumers wait on (no per-thread LDGSTS, whose 16-byte
+// shared-memory writes ran at 2.8x their ideal wavefronts, and no CTA barrier for the hand-over). Symbols within 8 samples of
+// either end of a recording (where the aligned superset could leave the buffer) take the bounds-checked path.
 template <int FMT> __host__ __device__ constexpr int fft_stage_bytes() { return T_U * (int)sizeof(typename Raw<FMT>::type) + 16; }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void * src, unsigned bytes, unsigned bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+  unsigned ok;
+  do
+  {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
 
 template <int FMT>
 __device__ __forceinline__ bool item_async(const SymbolItem & it) { return it.out >= 0 && it.start >= 8 && it.start + T_U + 8 <= it.n_total; }
 
-template <int FMT>
-__device__ __forceinline__ void stage_symbol(const SymbolItem & it, unsigned stage_addr, int tid)
+// 32-bit (x mod FS) for |x| < 2^31
+__device__ __forceinline__ int mod_fs32(int x)
 {
-  typedef typename Raw<FMT>::type T;
-  const unsigned long long a = (unsigned long long)(reinterpret_cast<const T *>(it.iq) + it.start);
-  const unsigned long long a0 = a & ~15ull;
-  const int chunks = (int)((a - a0) + T_U * sizeof(T) + 15) >> 4;
-  for (int c = tid; c < chunks; c += FFT_THREADS) cp_async16(stage_addr + 16u * (unsigned)c, reinterpret_cast<const void *>(a0 + 16ull * (unsigned)c));
+  const int r = x % FS;
+  return r < 0 ? r + FS : r;
+}
+
+// The 16 converted samples of a thread times the integer-Hz oscillator (sample_reader.cpp:276-281). f == 0 leaves ONE phasor
+// for the whole symbol (the oscillator stands at `ph`); otherwise sample 128 n1 + tid takes osc[ph - f (128 n1 + tid + 1)] =
+// s0(tid) * step[n1], step = phasors of -128 f n1 (shared, recomputed by the caller only when f changes).
+template <int FMT>
+__device__ __forceinline__ void convert_mix(float2 (&v)[16], const typename Raw<FMT>::reg (&r)[16], int f, int ph, const float2 * step, int tid)
+{
+#pragma unroll
+  for (int n1 = 0; n1 < 16; n1++) v[n1] = to_cf(r[n1]);
+  if (f == 0)
+  {
+    if (ph == 0) return; // osc[0] = 1: the reference multiplies by exactly (1, 0)
+    const float2 c = osc(ph);
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) v[n1] = cmul(v[n1], c);
+    return;
+  }
+  const float2 s0 = osc(mod_fs32(ph - f * (tid + 1)));
+#pragma unroll
+  for (int n1 = 0; n1 < 16; n1++) v[n1] = cmul(v[n1], n1 == 0 ? s0 : cmul(s0, step[n1]));
 }
 
 template <int FMT>
@@ -186,36 +222,74 @@ __global__ void __launch_bounds__(FFT_THREADS, 5) k_fft_frames(const FrameDesc *
 {
   typedef typename Raw<FMT>::type T;
   extern __shared__ __align__(16) unsigned char fft_stage[]; // 2 x fft_stage_bytes<FMT>()
-  __shared__ float2 smem[FFT_SMEM_F2];
+  __shared__ __align__(16) float2 smem[FFT_SMEM_F2];
   __shared__ float2 tw2s[FFT_TW2_F2];
   __shared__ float2 step[16];
-  __shared__ int16_t bins[K_CARR]; // padded natural-order slot of nominal carrier k
+  __shared__ unsigned short pos[16 * FFT_THREADS]; // byte offset in `smem` of the nominal-carrier slot of output (h, j2) of every thread
+  __shared__ __align__(8) unsigned long long mbar[2];
   const int tid = threadIdx.x;
   FftTwiddles tw;
   fft_load_twiddles(tw, w2048, tw2s, tid);
-  for (int k = tid; k < K_CARR; k += FFT_THREADS) bins[k] = (int16_t)fft_nat(bin_of_k[k]);
+  // Epilogue layout: after stage 3 a thread holds the bins fft_out_index(tid, h, j2); each is scattered straight to the slot of
+  // its nominal carrier k (frequency de-interleaving, freq_interleaver.cpp) in a [K_CARR] float2 array, so that the demapper's
+  // rows (carriers 2p, 2p + 1 as re, re, im, im) are one conflict-free 16-byte read per pair. Bins that carry no carrier (DC,
+  // guard band) go to a per-thread dump slot behind the array.
+  {
+    short * inv = reinterpret_cast<short *>(smem); // nominal carrier of every bin, -1: none (scratch, before the first transform)
+    for (int b = tid; b < T_U; b += FFT_THREADS) inv[b] = -1;
+    __syncthreads();
+    for (int k = tid; k < K_CARR; k += FFT_THREADS) inv[bin_of_k[k]] = (short)k;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+    {
+      const int k = inv[fft_out_index(tid, i >> 3, i & 7)];
+      pos[i * FFT_THREADS + tid] = (unsigned short)((k >= 0 ? k : K_CARR + tid) * (int)sizeof(float2));
+    }
+  }
+  static_assert((K_CARR + FFT_THREADS) <= FFT_SMEM_F2, "nominal-order staging + dump slots must fit the transform buffer");
   const unsigned stage0 = smem_addr_u32(fft_stage);
+  const unsigned bar0 = smem_addr_u32(mbar);
   constexpr int SB = fft_stage_bytes<FMT>();
+  if (tid == 0)
+  {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
 
-  // A CTA walks a contiguous range of (frame, row) items, so the frame descriptor is fetched once per 77 symbols
-  // instead of in front of every symbol (where its latency sat on the critical path of the cp.async issue).
+  // A CTA walks a contiguous range of (frame, row) items: the frame descriptor is fetched once per 77 symbols and the items of
+  // the data symbols follow from their predecessor (start + T_s, oscillator phase - f T_s) instead of 64-bit products and
+  // remainders per symbol.
   const int per = n_items / (int)gridDim.x, rem = n_items - per * (int)gridDim.x;
   int item = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
   const int item_end = item + per + ((int)blockIdx.x < rem ? 1 : 0);
   int buf = 0, fi = item / X_ROWS, row = item - fi * X_ROWS;
+  unsigned phase_bits = 0; // bit b: parity the next wait on mbar[b] expects
   FrameDesc fd;
   RecInput rin;
   SymbolItem cur;
   cur.out = -1;
+  int dph = 0;        // oscillator phase step of one data symbol: -f_data T_s mod FS
+  int step_f = 0;     // integer Hz the shared step table holds (0: none needed)
+  auto issue = [&](const SymbolItem & it, int b) {
+    if (tid == 0)
+    {
+      const unsigned long long a = (unsigned long long)(reinterpret_cast<const T *>(it.iq) + it.start);
+      mbar_expect_tx(bar0 + 8u * (unsigned)b, (unsigned)SB);
+      bulk_g2s(stage0 + (unsigned)(b * SB), reinterpret_cast<const void *>(a & ~15ull), (unsigned)SB, bar0 + 8u * (unsigned)b);
+    }
+  };
   if (item < item_end)
   {
     fd = frames[fi];
     rin = recs[fd.rec];
     cur = symbol_item(fd, rin, row);
-    if (item_async<FMT>(cur)) stage_symbol<FMT>(cur, stage0, tid);
+    dph = mod_fs32(-(int)(((long long)fd.f_data * T_S) % FS));
+    if (item_async<FMT>(cur)) issue(cur, 0);
   }
-  cp_async_commit();
-  __syncthreads();
   while (item < item_end)
   {
     const int next = item + 1;
@@ -229,35 +303,79 @@ __global__ void __launch_bounds__(FFT_THREADS, 5) k_fft_frames(const FrameDesc *
         fi++;
         fd = frames[fi];
         rin = recs[fd.rec];
+        dph = mod_fs32(-(int)(((long long)fd.f_data * T_S) % FS));
       }
-      nxt = symbol_item(fd, rin, row);
-      if (item_async<FMT>(nxt)) stage_symbol<FMT>(nxt, stage0 + (unsigned)((buf ^ 1) * SB), tid);
+      if (row >= 2 && row <= 75)
+      {
+        // data symbol after a data symbol of the same frame
+        nxt.iq = cur.iq;
+        nxt.n_total = cur.n_total;
+        nxt.start = cur.start + T_S;
+        nxt.f = cur.f;
+        nxt.ph = cur.ph + dph;
+        if (nxt.ph >= FS) nxt.ph -= FS;
+        nxt.out = row > fd.n_syms ? -1 : ((long long)fd.xslot * X_ROWS + row) * K_CARR;
+      }
+      else nxt = symbol_item(fd, rin, row);
+      if (item_async<FMT>(nxt)) issue(nxt, buf ^ 1);
     }
-    cp_async_commit();
     if (cur.out >= 0)
     {
       float2 v[16];
+      if (cur.f != 0 && cur.f != step_f)
+      {
+        // (all threads agree on cur.f: no divergence around the barriers)
+        __syncthreads(); // nobody reads the previous table any more
+        if (tid < 16) step[tid] = osc(mod_fs32(-(int)(((long long)cur.f * 128 * tid) % FS)));
+        step_f = cur.f;
+        __syncthreads();
+      }
       if (item_async<FMT>(cur))
       {
-        cp_async_wait<1>();  // this thread's chunks of the current symbol have landed ...
-        __syncthreads();     // ... and so have everybody else's
+        mbar_wait(bar0 + 8u * (unsigned)buf, (phase_bits >> buf) & 1u); // the bulk copy of this symbol has landed (visible to every waiter)
+        phase_bits ^= 1u << buf;
         const unsigned off = (unsigned)((unsigned long long)(reinterpret_cast<const T *>(cur.iq) + cur.start) & 15ull);
         const T * sp = reinterpret_cast<const T *>(fft_stage + buf * SB + off) + tid;
         typename Raw<FMT>::reg r[16];
 #pragma unroll
         for (int n1 = 0; n1 < 16; n1++) r[n1] = sp[128 * n1];
-        mix_symbol<FMT>(v, r, cur.n_total, cur.start, cur.f, cur.ph, step, tid);
+        convert_mix<FMT>(v, r, cur.f, cur.ph, step, tid);
       }
-      else load_symbol<FMT>(v, cur.iq, cur.n_total, cur.start, cur.f, cur.ph, step, tid);
-      fft2048_to_smem(v, tw, smem, tid);
-      // frequency de-interleave + the demapper's layout: carriers 2p, 2p + 1 as (re, re, im, im), one 16-byte store per pair
+      else
+      {
+        typename Raw<FMT>::reg r[16];
+        fetch_symbol<FMT>(r, cur.iq, cur.n_total, cur.start, tid);
+        convert_mix<FMT>(v, r, cur.f, cur.ph, step, tid);
+        if (!(cur.start >= 0 && cur.start + T_U <= cur.n_total))
+        {
+#pragma unroll
+          for (int n1 = 0; n1 < 16; n1++)
+          {
+            const long long i = cur.start + 128 * n1 + tid;
+            if (i < 0 || i >= cur.n_total) v[n1] = make_float2(0.0f, 0.0f); // outside the recording: zero amplitude
+          }
+        }
+      }
+      fft_stage1(v, tw, smem, tid);
+      __syncthreads();
+      fft_stage2_read(v, smem, tid);
+      __syncthreads();
+      fft_stage2(v, tw, smem, tid);
+      __syncthreads();
+      fft_stage3(v, smem, tid);
+      __syncthreads();
+      unsigned char * sbase = reinterpret_cast<unsigned char *>(smem);
+#pragma unroll
+      for (int i = 0; i < 16; i++) *reinterpret_cast<float2 *>(sbase + pos[i * FFT_THREADS + tid]) = v[i];
+      __syncthreads();
       float4 * out = reinterpret_cast<float4 *>(X + cur.out);
+      const float4 * prs = reinterpret_cast<const float4 *>(smem);
 #pragma unroll
       for (int i = 0; i < K_CARR / 2 / FFT_THREADS; i++)
       {
         const int p = tid + FFT_THREADS * i;
-        const float2 a = smem[bins[2 * p]], b = smem[bins[2 * p + 1]];
-        out[p] = make_float4(a.x, b.x, a.y, b.y);
+        const float4 ab = prs[p]; // (re 2p, im 2p, re 2p+1, im 2p+1)
+        out[p] = make_float4(ab.x, ab.z, ab.y, ab.w);
       }
     }
     __syncthreads(); // smem and the stage buffer of this symbol are free again
@@ -265,7 +383,6 @@ __global__ void __launch_bounds__(FFT_THREADS, 5) k_fft_frames(const FrameDesc *
     item = next;
     buf ^= 1;
   }
-  cp_async_wait<0>();
 }
 
 // Natural-order batch transform (stage tap dabstar_fft2048). sign > 0: conj in, conj out.

@@ -16,8 +16,9 @@ stream = torch.cuda.Stream()
 ctx = api.Context(0, stream=stream)
 dp = api.DabProcessor(R, input_format=api.FMT_U8, scan_mode=True, max_window=128, ctx=ctx)
 ptrs = [host[r].data_ptr() for r in range(R)]
+DEV_ONLY = len(sys.argv) > 2 and sys.argv[2] == "dev"
 with torch.cuda.stream(stream):
-    for i in range(3):
+    for i in range(0 if DEV_ONLY else 3):
         t0 = time.time()
         dp.run_ptrs(ptrs, [n] * R, api.MEM_HOST)
         torch.cuda.synchronize()
@@ -31,6 +32,8 @@ with torch.cuda.stream(stream):
         torch.cuda.synchronize()
         print(f"device-resident run {i}: {1e3 * (time.time() - t0):.2f} ms wall", file=sys.stderr)
     del dev_in
+    if DEV_ONLY:
+        sys.exit(0)
     # plain copy speed for comparison
     dev = torch.empty_like(host, device="cuda")
     torch.cuda.synchronize()

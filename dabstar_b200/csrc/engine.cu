@@ -740,21 +740,17 @@ extern "C" int dabstar_protection_deconvolve(dabstar_ctx * ctx, int short_form, 
   if (prof < 0) return ctx->fail(DABSTAR_E_INVALID, "unknown protection profile %d/%d/%d", short_form, bit_rate, prot_level);
   const VitProfile & p = ctx->profiles[prof];
   if (p.n_kept > size_cu * 64) return ctx->fail(DABSTAR_E_INVALID, "size_cu %d too small for profile (%d soft bits)", size_cu, p.n_kept);
-  std::vector<VitJob> jobs((size_t)n);
-  for (int i = 0; i < n; i++)
-  {
-    VitJob & j = jobs[i];
-    memset(&j, 0, sizeof(j));
-    j.src = (long long)i * size_cu * 64;
-    j.out = (long long)i * p.n_bits;
-    j.profile = prof;
-    j.src_mode = VIT_SRC_LINEAR;
-  }
   const void * dsoft; void * dbits;
   const size_t in_bytes = sizeof(int16_t) * (size_t)n * size_cu * 64, out_bytes = (size_t)n * p.n_bits;
   if (int r = stage_in(ctx, ctx->scratch[0], soft, in_bytes, mem, &dsoft)) return r;
   if (int r = stage_out_begin(ctx, ctx->scratch[1], bits, out_bytes, mem, &dbits)) return r;
-  if (int r = run_viterbi_jobs(ctx, jobs, p.n_bits + 6, (const int16_t *)dsoft, (uint8_t *)dbits, nullptr, nullptr, ctx->scratch[2])) return r;
+  // the job list is written on the device (one job per logical frame at a constant stride)
+  if (int r = sync_profiles(ctx)) return r;
+  CK(ctx->scratch[2].reserve(sizeof(VitJob) * (size_t)n));
+  CK(launch_linear_jobs(ctx->stream, ctx->scratch[2].as<VitJob>(), n, (long long)size_cu * 64, p.n_bits, prof, &ctx->launches));
+  if (int r = reserve_viterbi_ws(ctx, n, p.n_bits + 6)) return r;
+  CK(launch_viterbi(ctx->stream, ctx->scratch[2].as<VitJob>(), nullptr, n, ctx->d_profiles.as<VitProfile>(), p.n_bits + 6, (const int16_t *)dsoft, (uint8_t *)dbits,
+                    ctx->tab.prbs, nullptr, nullptr, ctx->d_step_tab.as<unsigned>(), ctx->vit_ws.p, ctx->vit_ws.cap, &ctx->launches));
   return stage_out_end(ctx, dbits, bits, out_bytes, mem);
 }
 
@@ -2416,9 +2412,10 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
   {
     // One job per sub-channel and CIF (several hundred thousand for a full ensemble), grouped by code-word length (one launch
     // per length: shared-memory footprint). The host only lists one range per Backend; the jobs are written on the device.
-    std::map<int, std::vector<BackendJobRange>> by_steps;
-    std::map<int, int> n_jobs_of;
-    long long out_total = 0;
+    // The decoded bits are laid out group by group (code-word length), so that a group's payload can be packed and copied
+    // to the host while the next group is decoded; nothing on the host waits between the groups.
+    struct Group { std::vector<BackendJobRange> ranges; std::vector<MscOut *> outs; int n_jobs = 0; long long bits = 0, bit_base = 0; int job_base = 0; };
+    std::map<int, Group> groups;
     for (int r = 0; r < n_rec; r++)
     {
       Recording & R = dec->recs[r];
@@ -2433,43 +2430,79 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
         const int g_start = (int)std::max<long long>(g_abs, -4LL * R.hist);
         const int g_first = std::max(g_start + 16, 0);
         const int n_out = std::max(0, n_cifs - g_first);
-        m.out_off = out_total;
+        m.out_off = 0;
         m.out_len = (long long)n_out * p.n_bits;
         if (n_out == 0) continue;
-        int & nj = n_jobs_of[p.n_bits + 6];
-        by_steps[p.n_bits + 6].push_back(BackendJobRange{ R.slot_base * FRAME_SOFT, out_total, m.profile, p.n_bits, g_start, g_first, n_out, m.sc.start_cu * 64, nj, 0 });
-        nj += n_out;
-        out_total += (long long)n_out * p.n_bits;
+        Group & g = groups[p.n_bits + 6];
+        // out / job_first are relative to the group here; the group's bases are added below
+        g.ranges.push_back(BackendJobRange{ R.slot_base * FRAME_SOFT, g.bits, m.profile, p.n_bits, g_start, g_first, n_out, m.sc.start_cu * 64, g.n_jobs, 0 });
+        g.outs.push_back(&m);
+        g.n_jobs += n_out;
+        g.bits += (long long)n_out * p.n_bits;
       }
+    }
+    long long out_total = 0;
+    int jobs_total = 0;
+    std::vector<BackendJobRange> all_ranges;
+    for (auto & kv : groups)
+    {
+      Group & g = kv.second;
+      g.bit_base = out_total;
+      g.job_base = jobs_total;
+      for (size_t i = 0; i < g.ranges.size(); i++)
+      {
+        g.ranges[i].out += g.bit_base;
+        g.ranges[i].job_first += g.job_base;
+        g.outs[i]->out_off = g.ranges[i].out;
+      }
+      all_ranges.insert(all_ranges.end(), g.ranges.begin(), g.ranges.end());
+      out_total += g.bits;
+      jobs_total += g.n_jobs;
     }
     tr("msc ranges built");
     if (out_total > 0)
     {
       CK(dec->d_mscbits.reserve((size_t)out_total));
-      if (int e = sync_profiles(ctx)) return e;
-      for (auto & kv : by_steps)
-      {
-        const int n_jobs = n_jobs_of[kv.first];
-        CK(dec->d_jobs.reserve(sizeof(VitJob) * (size_t)n_jobs + sizeof(BackendJobRange) * kv.second.size() + 256));
-        VitJob * d_jobs = dec->d_jobs.as<VitJob>();
-        BackendJobRange * d_ranges = reinterpret_cast<BackendJobRange *>(reinterpret_cast<unsigned char *>(d_jobs) + ((sizeof(VitJob) * (size_t)n_jobs + 255) & ~(size_t)255));
-        UP(d_ranges, kv.second.data(), sizeof(BackendJobRange) * kv.second.size());
-        CK(launch_expand_backend_jobs(st, d_ranges, (int)kv.second.size(), d_jobs, &ctx->launches));
-        if (int e = reserve_viterbi_ws(ctx, n_jobs, kv.first)) return e;
-        {
-          const VitSpanHook hook{ msc_span_mark, dec }; // one span per kernel (gather / trellis) instead of one around the launch
-          CK(launch_viterbi(st, d_jobs, nullptr, n_jobs, ctx->d_profiles.as<VitProfile>(), kv.first, dec->d_soft.as<int16_t>(), dec->d_mscbits.as<uint8_t>(), ctx->tab.prbs,
-                            nullptr, nullptr, ctx->d_step_tab.as<unsigned>(), ctx->vit_ws.p, ctx->vit_ws.cap, &ctx->launches, &hook));
-        }
-        SYNC(); // d_jobs is reused by the next group
-      }
-      // the payload leaves the device packed 8 bits per byte in ONE copy into pinned memory (every logical frame is a whole
-      // number of bytes: 24 x bit rate bits); dabstar_decoder_msc_copy unpacks a sub-channel on request. One pageable copy
-      // per sub-channel and recording of the bits as bytes cost 220 ms per 10 000 full-ensemble frames, 7 x the kernels.
       CK(dec->d_mscpacked.reserve((size_t)(out_total / 8)));
       CK(dec->h_mscp.reserve((size_t)(out_total / 8)));
-      CK(launch_pack_bits(st, dec->d_mscbits.as<uint8_t>(), dec->d_mscpacked.as<uint8_t>(), out_total / 8, &ctx->launches));
-      CK(cudaMemcpyAsync(dec->h_mscp.p, dec->d_mscpacked.p, (size_t)(out_total / 8), cudaMemcpyDeviceToHost, st));
+      if (int e = sync_profiles(ctx)) return e;
+      // every Backend's jobs of every group in one array, written by one launch
+      CK(dec->d_jobs.reserve(sizeof(VitJob) * (size_t)jobs_total + sizeof(BackendJobRange) * all_ranges.size() + 256));
+      VitJob * d_jobs = dec->d_jobs.as<VitJob>();
+      BackendJobRange * d_ranges = reinterpret_cast<BackendJobRange *>(reinterpret_cast<unsigned char *>(d_jobs) + ((sizeof(VitJob) * (size_t)jobs_total + 255) & ~(size_t)255));
+      UP(d_ranges, all_ranges.data(), sizeof(BackendJobRange) * all_ranges.size());
+      CK(launch_expand_backend_jobs(st, d_ranges, (int)all_ranges.size(), d_jobs, &ctx->launches));
+      {
+        // one workspace for all groups (they run one after the other on the stream), sized for the largest product
+        size_t need_jobs = 0;
+        int need_steps = 0;
+        for (auto & kv : groups)
+          if (viterbi_ws_bytes(kv.second.n_jobs, kv.first) > viterbi_ws_bytes((int)need_jobs, need_steps)) { need_jobs = (size_t)kv.second.n_jobs; need_steps = kv.first; }
+        if (int e = reserve_viterbi_ws(ctx, (int)need_jobs, need_steps)) return e;
+      }
+      // the payload leaves the device packed 8 bits per byte (every logical frame is a whole number of bytes: 24 x bit rate
+      // bits), one copy per group into pinned memory on the copy stream; dabstar_decoder_msc_copy unpacks a sub-channel on
+      // request. One pageable copy per sub-channel and recording of the bits as bytes cost 220 ms per 10 000 full-ensemble
+      // frames, 7 x the kernels.
+      for (auto & kv : groups)
+      {
+        Group & g = kv.second;
+        {
+          const VitSpanHook hook{ msc_span_mark, dec }; // one span per kernel (gather / trellis) instead of one around the launch
+          CK(launch_viterbi(st, d_jobs + g.job_base, nullptr, g.n_jobs, ctx->d_profiles.as<VitProfile>(), kv.first, dec->d_soft.as<int16_t>(), dec->d_mscbits.as<uint8_t>(), ctx->tab.prbs,
+                            nullptr, nullptr, ctx->d_step_tab.as<unsigned>(), ctx->vit_ws.p, ctx->vit_ws.cap, &ctx->launches, &hook));
+        }
+        CK(launch_pack_bits(st, dec->d_mscbits.as<uint8_t>() + g.bit_base, dec->d_mscpacked.as<uint8_t>() + g.bit_base / 8, g.bits / 8, &ctx->launches));
+        cudaEvent_t ev = dec->ev_get();
+        CK(cudaEventRecord(ev, st));
+        CK(cudaStreamWaitEvent(dec->copy_stream, ev, 0));
+        CK(cudaMemcpyAsync(dec->h_mscp.as<uint8_t>() + g.bit_base / 8, dec->d_mscpacked.as<uint8_t>() + g.bit_base / 8, (size_t)(g.bits / 8), cudaMemcpyDeviceToHost, dec->copy_stream));
+      }
+      {
+        cudaEvent_t ev = dec->ev_get();
+        CK(cudaEventRecord(ev, dec->copy_stream));
+        CK(cudaStreamWaitEvent(st, ev, 0)); // the run's final synchronisation of `st` covers the copies
+      }
       tr("msc enqueued");
     }
   }

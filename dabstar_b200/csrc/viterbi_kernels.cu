@@ -516,6 +516,26 @@ __global__ void __launch_bounds__(128) k_expand_backend_jobs(const BackendJobRan
     jobs[r.job_first + i] = j;
   }
 }
+// Protection::deconvolve over n logical frames at a constant stride (stage tap): job i reads its fragment at i * src_stride and
+// writes at i * n_bits; written on the device because a million 48-byte jobs built and staged by the host cost more than decoding them.
+__global__ void __launch_bounds__(256) k_linear_jobs(VitJob * __restrict__ jobs, int n, long long src_stride, int n_bits, int profile)
+{
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+  {
+    VitJob j;
+    j.src = (long long)i * src_stride;
+    j.out = (long long)i * n_bits;
+    j.profile = profile;
+    j.src_mode = VIT_SRC_LINEAR;
+    j.flags = 0;
+    j.cif_first = 0;
+    j.row_mask = 0;
+    j.frag_off = 0;
+    j.aux = 0;
+    j.skip_plus1 = 0;
+    jobs[i] = j;
+  }
+}
 // EtiGenerator::_process_sub_channel storage loop (eti_generator.cpp:403-411): 8 decoded bits (one per byte) -> one byte, first bit most significant
 __global__ void __launch_bounds__(256) k_pack_bits(const uint8_t * __restrict__ bits, uint8_t * __restrict__ out, long long n_bytes)
 {
@@ -532,6 +552,14 @@ cudaError_t launch_expand_backend_jobs(cudaStream_t stream, const BackendJobRang
 {
   if (n_ranges <= 0) return cudaSuccess;
   k_expand_backend_jobs<<<(unsigned)n_ranges, 128, 0, stream>>>(ranges, jobs);
+  if (launch_counter) (*launch_counter)++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_linear_jobs(cudaStream_t stream, VitJob * jobs, int n, long long src_stride, int n_bits, int profile, unsigned long long * launch_counter)
+{
+  if (n <= 0) return cudaSuccess;
+  k_linear_jobs<<<(unsigned)std::min((n + 255) / 256, N_SM * 8), 256, 0, stream>>>(jobs, n, src_stride, n_bits, profile);
   if (launch_counter) (*launch_counter)++;
   return cudaGetLastError();
 }

@@ -616,6 +616,17 @@ class DabProcessor:
         self.ctx.check(self.ctx.lib.dabstar_decoder_run(self.h, p, ns, mem), "dabstar_decoder_run")
         return float(self.ctx.lib.dabstar_decoder_last_ms(self.h))
 
+    def prepared(self, ptrs: list[int], n_samples: list[int], mem: int):
+        """run_ptrs with the argument arrays built once: returns a callable that decodes the same buffers again (a caller that
+        decodes in a loop, e.g. bench.py, keeps the ctypes marshalling out of its timed region)."""
+        p = (c_p * self.n)(*[c_p(x) for x in ptrs])
+        ns = (ctypes.c_int64 * self.n)(*n_samples)
+        run, check, h = self.ctx.lib.dabstar_decoder_run, self.ctx.check, self.h
+
+        def call():
+            check(run(h, p, ns, mem), "dabstar_decoder_run")
+        return call
+
     def run(self, recordings: list[np.ndarray]) -> float:
         """recordings: host arrays (uint8[n,2] / int16[n,2] / complex64[n]) in the configured input format."""
         dt = {FMT_U8: np.uint8, FMT_I16: np.int16, FMT_CF32: np.complex64}[self.cfg.input_format]

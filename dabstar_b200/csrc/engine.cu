@@ -1157,6 +1157,7 @@ struct dabstar_decoder
   double heavy_ms = 0, fft_demap_ms = 0;
   cudaStream_t heavy_stream = nullptr;
   int state_slots = 0;  // OfdmStateDev slots in d_states: 2 per recording + scratch for the segments of a window
+  HostBuf h_dip, h_start, h_cp, h_coarse; // pinned read-back of the control kernels' results (a pageable target makes the copy a blocking, staged one)
   DevBuf d_descc;       // chunk-major copy of the window's descriptors
 };
 enum { ST_DIP = 0, ST_PRS = 1, ST_CP = 2, ST_COARSE = 3, ST_FFT = 4, ST_DEMAP = 5, ST_FIC = 6, ST_MSC = 7, ST_MSC_GATHER = 8, ST_MSC_TRELLIS = 9 };
@@ -1650,8 +1651,9 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
         dec->span_begin(ST_DIP);
         CK(launch_dip_search(st, dec->d_dipw.as<DipWork>(), (int)dw.size(), d_rin, fmt, dec->d_dipr.as<DipResult>(), &ctx->launches));
         dec->span_end();
-        std::vector<DipResult> dr(dw.size());
-        CK(cudaMemcpyAsync(dr.data(), dec->d_dipr.p, sizeof(DipResult) * dw.size(), cudaMemcpyDeviceToHost, st));
+        CK(dec->h_dip.reserve(sizeof(DipResult) * dw.size()));
+        const DipResult * dr = dec->h_dip.as<DipResult>();
+        CK(cudaMemcpyAsync(dec->h_dip.p, dec->d_dipr.p, sizeof(DipResult) * dw.size(), cudaMemcpyDeviceToHost, st));
         SYNC();
         tr("time sync done");
         for (size_t i = 0; i < who.size(); i++)
@@ -1725,8 +1727,9 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
         CK(launch_prs_corr(st, ctx->tab, dec->d_desc.as<FrameDesc>(), (int)fd.size(), d_rin, fmt, thr0, 2.0f * thr0, dfirst,
                            dec->cfg.strongest_peak, dec->d_start.as<int>(), &ctx->launches));
         dec->span_end();
-        std::vector<int> si(fd.size());
-        CK(cudaMemcpyAsync(si.data(), dec->d_start.p, sizeof(int) * fd.size(), cudaMemcpyDeviceToHost, st));
+        CK(dec->h_start.reserve(sizeof(int) * fd.size()));
+        const int * si = dec->h_start.as<int>();
+        CK(cudaMemcpyAsync(dec->h_start.p, dec->d_start.p, sizeof(int) * fd.size(), cudaMemcpyDeviceToHost, st));
         SYNC();
         for (size_t i = 0; i < who.size(); i++)
         {
@@ -1854,8 +1857,9 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       dec->span_begin(ST_CP);
       CK(launch_cp_corr(st, d_fd, n_tail, d_rin, fmt, dec->d_cp.as<float2>(), &ctx->launches));
       dec->span_end();
-      std::vector<float2> cp((size_t)n_tail);
-      CK(cudaMemcpyAsync(cp.data(), dec->d_cp.p, sizeof(float2) * (size_t)n_tail, cudaMemcpyDeviceToHost, st));
+      CK(dec->h_cp.reserve(sizeof(float2) * (size_t)n_tail));
+      const float2 * cp = dec->h_cp.as<float2>();
+      CK(cudaMemcpyAsync(dec->h_cp.p, dec->d_cp.p, sizeof(float2) * (size_t)n_tail, cudaMemcpyDeviceToHost, st));
       std::vector<int> coarse((size_t)n_tail, 0);
       if (first_pass)
       {
@@ -1880,8 +1884,9 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
           dec->span_begin(ST_COARSE);
           CK(launch_coarse_afc(st, ctx->tab, dec->d_work.as<FrameDesc>(), (int)cf.size(), d_rin, fmt, dec->d_coarse.as<int>(), &ctx->launches));
           dec->span_end();
-          std::vector<int> res(cf.size());
-          CK(cudaMemcpyAsync(res.data(), dec->d_coarse.p, sizeof(int) * cf.size(), cudaMemcpyDeviceToHost, st));
+          CK(dec->h_coarse.reserve(sizeof(int) * cf.size()));
+          const int * res = dec->h_coarse.as<int>();
+          CK(cudaMemcpyAsync(dec->h_coarse.p, dec->d_coarse.p, sizeof(int) * cf.size(), cudaMemcpyDeviceToHost, st));
           SYNC();
           for (size_t i = 0; i < idx.size(); i++) coarse[idx[i]] = res[i];
         }
@@ -1927,8 +1932,9 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       dec->span_begin(ST_PRS);
       CK(launch_prs_corr(st, ctx->tab, d_fd, n_tail, d_rin, fmt, thr0, 2.0f * thr0, d_first, dec->cfg.strongest_peak, dec->d_start.as<int>(), &ctx->launches));
       dec->span_end();
-      std::vector<int> start((size_t)n_tail);
-      CK(cudaMemcpyAsync(start.data(), dec->d_start.p, sizeof(int) * (size_t)n_tail, cudaMemcpyDeviceToHost, st));
+      CK(dec->h_start.reserve(sizeof(int) * (size_t)n_tail));
+      const int * start = dec->h_start.as<int>();
+      CK(cudaMemcpyAsync(dec->h_start.p, dec->d_start.p, sizeof(int) * (size_t)n_tail, cudaMemcpyDeviceToHost, st));
       SYNC();
       tr("  prs synced");
 

@@ -731,14 +731,30 @@ __global__ void __launch_bounds__(256) k_cp_corr(const FrameDesc * __restrict__ 
     const RecInput rin = recs[fd.rec];
     const long long base = fd.sym0 + T_U;
     float2 acc = make_float2(0.0f, 0.0f);
-    const int total = fd.n_syms * T_G;
-    for (int q = threadIdx.x; q < total; q += 256)
+    // a warp takes every eighth symbol; the 2 x 16 loads of a lane are issued before the first product (a strided loop with one
+    // pair of 2-byte loads in flight per thread ran at a third of the HBM rate)
+    typedef typename Raw<FMT>::type T;
+    const int lane = threadIdx.x & 31;
+    for (int sym = threadIdx.x >> 5; sym < fd.n_syms; sym += 8)
     {
-      const int sym = q / T_G, i = q - sym * T_G;
-      const long long p = base + (long long)sym * T_S + i;
-      const float2 a = load_sample<FMT>(rin.iq, p + T_U), b = load_sample<FMT>(rin.iq, p);
-      acc.x += a.x * b.x + a.y * b.y;
-      acc.y += a.y * b.x - a.x * b.y;
+      const T * pp = reinterpret_cast<const T *>(rin.iq) + base + (long long)sym * T_S + lane;
+      typename Raw<FMT>::reg ra[16], rb[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++)
+      {
+        if (lane + 32 * k < T_G) { ra[k] = pp[32 * k + T_U]; rb[k] = pp[32 * k]; }
+        else { ra[k] = typename Raw<FMT>::reg(); rb[k] = typename Raw<FMT>::reg(); }
+      }
+#pragma unroll
+      for (int k = 0; k < 16; k++)
+      {
+        if (lane + 32 * k < T_G)
+        {
+          const float2 a = to_cf(ra[k]), b = to_cf(rb[k]);
+          acc.x += a.x * b.x + a.y * b.y;
+          acc.y += a.y * b.x - a.x * b.y;
+        }
+      }
     }
     acc.x = warp_sum(acc.x);
     acc.y = warp_sum(acc.y);
@@ -1145,8 +1161,26 @@ __global__ void __launch_bounds__(DIP_THREADS) k_dip_search(const DipWork * __re
 
   // sLevel at p0: IIR over everything read so far (initial value 0.1, sample_reader.h:91); older than 2^21 samples is < 1e-9.
   const long long hist = p0 < (1LL << 21) ? p0 : (1LL << 21);
+  // weight of sample p0 - 1 - i is (1 - alpha)^i. Eight samples of a thread are in flight at a time (a re-synchronisation deep
+  // in a stream sums 2^21 samples, one CTA per recording: with one 2-byte load per iteration the kernel was a chain of
+  // memory latencies); their weights are one expf times the constants (1 - alpha)^(256 u).
   float acc = 0.0f;
-  for (long long i = tid; i < hist; i += DIP_THREADS) acc += sample_abs<FMT>(rin.iq, p0 - 1 - i) * expf((float)i * loga);
+  {
+    float ru[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) ru[u] = expf((float)(DIP_THREADS * u) * loga);
+    long long i = tid;
+    for (; i + 7LL * DIP_THREADS < hist; i += 8LL * DIP_THREADS)
+    {
+      float m[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) m[u] = sample_abs<FMT>(rin.iq, p0 - 1 - (i + (long long)u * DIP_THREADS));
+      const float w = expf((float)i * loga);
+#pragma unroll
+      for (int u = 0; u < 8; u++) acc = fmaf(m[u], w * ru[u], acc);
+    }
+    for (; i < hist; i += DIP_THREADS) acc = fmaf(sample_abs<FMT>(rin.iq, p0 - 1 - i), expf((float)i * loga), acc);
+  }
   acc = warp_sum(acc);
   if ((tid & 31) == 0) redf[tid >> 5] = acc;
   __syncthreads();
@@ -1175,39 +1209,54 @@ __global__ void __launch_bounds__(DIP_THREADS) k_dip_search(const DipWork * __re
     float A = 1.0f, B = 0.0f;
 #pragma unroll
     for (int q = 0; q < 4; q++) { const float m = mag[49 + 4 * tid + q]; B = a1 * B + LEVEL_ALPHA * m; A *= a1; }
-    scan_ab[tid] = make_float2(A, B);
-    __syncthreads();
-    if (tid == 0)
+    // inclusive scan of the maps (composition: first this thread's predecessors, then its own): shuffles inside a warp, the eight
+    // warp totals through shared memory
     {
+      const int lane = tid & 31, wp = tid >> 5;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const float pa = __shfl_up_sync(0xffffffffu, A, o), pb = __shfl_up_sync(0xffffffffu, B, o);
+        if (lane >= o) { B = fmaf(A, pb, B); A *= pa; }
+      }
+      if (lane == 31) scan_ab[wp] = make_float2(A, B);
+      __syncthreads();
+      // level in front of this warp: the block's start level through the totals of the warps before it
       float s = s_level;
-      for (int t = 0; t < DIP_THREADS; t++) { const float2 ab = scan_ab[t]; scan_ab[t].x = s; s = ab.x * s + ab.y; }
-      scan_ab[0].y = s; // level after the block
-    }
-    __syncthreads();
-    {
-      float s = scan_ab[tid].x;
+      for (int w = 0; w < wp; w++) { const float2 ab = scan_ab[w]; s = fmaf(ab.x, s, ab.y); }
+      // level in front of this thread: through the inclusive map of the lane before it
+      const float ea = __shfl_up_sync(0xffffffffu, A, 1), eb = __shfl_up_sync(0xffffffffu, B, 1);
+      if (lane > 0) s = fmaf(ea, s, eb);
 #pragma unroll
       for (int q = 0; q < 4; q++) { s = a1 * s + LEVEL_ALPHA * mag[49 + 4 * tid + q]; lvl[4 * tid + q] = s; }
+      if (tid == DIP_THREADS - 1) scan_ab[DIP_THREADS / 32].x = s; // level after the block
     }
     if (tid == 0) found = 0x7fffffff;
     __syncthreads();
-    const float s_after = scan_ab[0].y;
+    const float s_after = scan_ab[DIP_THREADS / 32].x;
     // evaluate both phases inside this block (the dip end may follow in the same block)
     int from = 0;
     while (true)
     {
       int best = 0x7fffffff;
-      for (int q = 0; q < 4; q++)
       {
-        const int i = 4 * tid + q;
-        const long long gi = b0 + i;
-        if (i < from) continue;
-        if (phase == 0 && gi < 49) continue;
-        float c = 0.0f;
-        for (int j = 0; j < 50; j++) c += mag[i + j]; // mag[i..i+49] = samples gi-49..gi
-        const float mean = c / 50.0f;
-        const bool hit = phase == 0 ? !(mean > 0.55f * lvl[i]) : !(mean < 0.75f * lvl[i]);
-        if (hit) { best = i; break; }
+        // window sums of the thread's four samples: the first directly (two chains), the others by sliding, as the reference's
+        // running sum does (timesyncer.cpp:57-62); mag[i..i+49] = samples gi-49..gi
+        float c0 = 0.0f, c1 = 0.0f;
+#pragma unroll 5
+        for (int j = 0; j < 50; j += 2) { c0 += mag[4 * tid + j]; c1 += mag[4 * tid + j + 1]; }
+        float c = c0 + c1;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+          const int i = 4 * tid + q;
+          const long long gi = b0 + i;
+          if (q > 0) c += mag[i + 49] - mag[i - 1];
+          if (i < from || (phase == 0 && gi < 49) || best != 0x7fffffff) continue;
+          const float mean = c / 50.0f;
+          const bool hit = phase == 0 ? !(mean > 0.55f * lvl[i]) : !(mean < 0.75f * lvl[i]);
+          if (hit) best = i;
+        }
       }
       if (best != 0x7fffffff) atomicMin(&found, best);
       __syncthreads();

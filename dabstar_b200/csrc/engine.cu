@@ -174,6 +174,28 @@ int upload(dabstar_ctx * ctx, void * dst, const void * src, size_t bytes)
   CK(cudaGetLastError());
   return 0;
 }
+// The same in two halves: upload_begin hands out the staging area (the caller fills it, e.g. from several threads),
+// upload_commit queues the copy kernel.
+int upload_begin(dabstar_ctx * ctx, size_t bytes, unsigned char ** stage)
+{
+  const size_t need = (bytes + 255) & ~(size_t)255;
+  if (ctx->arena.cap < need || ctx->arena_off + need > ctx->arena.cap)
+  {
+    if (int r = sync_stream(ctx)) return r;
+    if (ctx->arena.cap < need) CK(ctx->arena.reserve(std::max<size_t>(need, (size_t)8 << 20)));
+  }
+  *stage = ctx->arena.as<unsigned char>() + ctx->arena_off;
+  ctx->arena_off += need;
+  return 0;
+}
+int upload_commit(dabstar_ctx * ctx, void * dst, const unsigned char * stage, size_t bytes)
+{
+  const int grid = (int)std::min<size_t>(64, (bytes / 16 + 255) / 256 + 1);
+  k_upload<<<grid, 256, 0, ctx->stream>>>(static_cast<unsigned char *>(dst), stage, bytes);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
 #define UP(dst, src, bytes) do { if (int r_ = upload(ctx, (dst), (src), (bytes))) return r_; } while (0)
 #define SYNC() do { if (int r_ = sync_stream(ctx)) return r_; } while (0)
 
@@ -1846,10 +1868,19 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       if (trace) fprintf(stderr, "[dabstar]     pass: %d tail frames\n", n_tail);
       tr("  tail laid out");
       CK(need_upto(window_end));
-      std::vector<FrameDesc> fdv((size_t)n_tail);
-      for (int i = 0; i < n_tail; i++) fdv[i] = ctl[i].desc;
+      // descriptors go from the control records straight into the pinned staging area, a share per pool thread
+      auto upload_descs = [&](int n) -> int {
+        unsigned char * stage = nullptr;
+        if (int r_ = upload_begin(ctx, sizeof(FrameDesc) * (size_t)n, &stage)) return r_;
+        FrameDesc * o = reinterpret_cast<FrameDesc *>(stage);
+        const int parts = std::max(1, std::min(n / 512, 16));
+        pool.parallel_for(parts, [&](int k) {
+          for (int i = (int)((long long)n * k / parts); i < (int)((long long)n * (k + 1) / parts); i++) o[i] = ctl[(size_t)i].desc;
+        });
+        return upload_commit(ctx, dec->d_desc.p, stage, sizeof(FrameDesc) * (size_t)n);
+      };
       CK(dec->d_desc.reserve(sizeof(FrameDesc) * (size_t)n_tail + (size_t)n_tail + 64));
-      UP(dec->d_desc.p, fdv.data(), sizeof(FrameDesc) * (size_t)n_tail);
+      if (int r_ = upload_descs(n_tail)) return r_;
       FrameDesc * d_fd = dec->d_desc.as<FrameDesc>();
 
       // CP correlation on raw samples (all tail frames) and coarse AFC (first frame of a careful window)
@@ -1921,8 +1952,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
         }
       };
       pool.parallel_for((int)plans.size(), [&](int pi) { recur_plan((size_t)pi); });
-      for (int i = 0; i < n_tail; i++) fdv[i] = ctl[i].desc;
-      UP(dec->d_desc.p, fdv.data(), sizeof(FrameDesc) * (size_t)n_tail);
+      if (int r_ = upload_descs(n_tail)) return r_;
       tr("  recurrences done");
 
       // PRS peak of every tail frame
@@ -2004,23 +2034,25 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
     dec->cnt_rounds++;
     const int n_desc = n_round;
     ctl.resize((size_t)n_desc);
-    std::vector<FrameDesc> fdv((size_t)n_desc);
+    CK(dec->d_desc.reserve(sizeof(FrameDesc) * (size_t)n_desc + 64));
+    unsigned char * desc_stage = nullptr;
+    if (int r_ = upload_begin(ctx, sizeof(FrameDesc) * (size_t)n_desc, &desc_stage)) return r_;
     pool.parallel_for((int)plans.size(), [&](int pi) {
       Plan & pl = plans[(size_t)pi];
       const int base = dec->recs[pl.rec].w_first_desc;
+      FrameDesc * o = reinterpret_cast<FrameDesc *>(desc_stage);
       for (int j = 0; j < (int)pl.fr.size(); j++)
       {
         pl.fr[(size_t)j].desc.xslot = base + j;
         ctl[(size_t)(base + j)] = pl.fr[(size_t)j];
-        fdv[(size_t)(base + j)] = pl.fr[(size_t)j].desc;
+        o[base + j] = pl.fr[(size_t)j].desc;
       }
     });
     if (trace)
       fprintf(stderr, "[dabstar] round %lld t=%.3f ms: %zu recordings, %d frames, chunks resident %d/%d waited %d\n", dec->cnt_rounds,
               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_run0).count(), plans.size(), n_desc, dec->chunks_done, dec->n_chunks,
               dec->chunks_waited);
-    CK(dec->d_desc.reserve(sizeof(FrameDesc) * (size_t)n_desc + 64));
-    UP(dec->d_desc.p, fdv.data(), sizeof(FrameDesc) * (size_t)n_desc);
+    if (int r_ = upload_commit(ctx, dec->d_desc.p, desc_stage, sizeof(FrameDesc) * (size_t)n_desc)) return r_;
     FrameDesc * d_fd = dec->d_desc.as<FrameDesc>();
 
     // ---- heavy pass: FFT (+ingest, derotation, de-interleave) -> demap -> FIC

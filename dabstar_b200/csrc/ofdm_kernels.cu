@@ -916,6 +916,16 @@ __device__ __forceinline__ float dm5_total(const unsigned long long * slot, unsi
   return v;
 }
 
+// Measurement builds only (-DDABSTAR_ABLATE, never shipped: the results are wrong): parts of the demapper switched off through
+// DABSTAR_DEMAP_ABLATE to see what each costs. 1: no waiting on the ring, 2: no soft-bit output, 4: no spectrum row loads,
+// 8: no publishing of the partial sums.
+#ifdef DABSTAR_ABLATE
+__device__ int g_demap_ablate;
+#define ABL(bit) ((abl & (bit)) != 0)
+#else
+#define ABL(bit) false
+#endif
+
 template <int SOFT, int LAG>
 __global__ void __launch_bounds__(DM5_T, 4) k_demap5(const DemapWork * __restrict__ work, const FrameDesc * __restrict__ frames,
                                                       const uint8_t * __restrict__ null_is_tii, const float2 * __restrict__ X,
@@ -930,6 +940,9 @@ __global__ void __launch_bounds__(DM5_T, 4) k_demap5(const DemapWork * __restric
   __shared__ unsigned s_ticket;
   if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
   __syncthreads();
+#ifdef DABSTAR_ABLATE
+  const int abl = g_demap_ablate;
+#endif
   float4 * stash = dm5_smem;
   float4 * rowbuf = dm5_smem + STASH * T * 2;
   int * orow_ring = reinterpret_cast<int *>(rowbuf + DM5_PF * T * 2) + (threadIdx.x >> 5);
@@ -1007,7 +1020,7 @@ __global__ void __launch_bounds__(DM5_T, 4) k_demap5(const DemapWork * __restric
     const unsigned slot = (unsigned)((q & (DM5_PF - 1)) * T);
     cur_a = rowbuf[(slot + tid) * 2];
     cur_b = rowbuf[(slot + tid) * 2 + 1];
-    if (q + DM5_PF < total_rows)
+    if (q + DM5_PF < total_rows && !ABL(4))
     {
       cp_async16(rowbuf_addr + slot * 32u, rows + (size_t)(q + DM5_PF) * DM3_ROW4);
       cp_async16(rowbuf_addr + slot * 32u + 16u, rows + (size_t)(q + DM5_PF) * DM3_ROW4 + 1);
@@ -1048,7 +1061,7 @@ __global__ void __launch_bounds__(DM5_T, 4) k_demap5(const DemapWork * __restric
       const float b_in = lane < DM5_WARPS ? __uint_as_float((unsigned)pre) : 0.0f;
       const bool tags_ok = __all_sync(0xffffffffu, lane >= DM5_WARPS || (unsigned)(pre >> 32) == (unsigned)d);
       const unsigned long long pre_used = pre;
-      if (d >= 0 && lane < DM5_WARPS) pre = ld_volatile_global_b64(my_ring + (size_t)(d & (DM3_RING - 1)) * DM5_WARPS + lane);
+      if (d >= 0 && lane < DM5_WARPS && !ABL(1)) pre = ld_volatile_global_b64(my_ring + (size_t)(d & (DM3_RING - 1)) * DM5_WARPS + lane);
       float v = (upper ? b_in : part_prev) + __shfl_xor_sync(0xffffffffu, upper ? part_prev : b_in, 16);
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -1061,14 +1074,14 @@ __global__ void __launch_bounds__(DM5_T, 4) k_demap5(const DemapWork * __restric
       stash[((g & (STASH - 1)) * T + tid) * 2 + 1] = make_float4(b_re.x, b_re.y, b_im.x, b_im.y);
       if (lane == 0) orow_ring[(g & (STASH - 1)) * (T >> 5)] = out_row0 + (sym - 1);
       __syncwarp();
-      if (lane == 0 && g > 0)
+      if (lane == 0 && g > 0 && !ABL(8))
         st_volatile_global_b64(my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM5_WARPS + gw,
                                ((unsigned long long)(unsigned)g << 32) | (unsigned long long)__float_as_uint(v));
       if (d >= 0)
       {
         float tot = tot_fast;
-        if (d > 0 && !tags_ok) tot = dm5_total(my_ring + (size_t)((d - 1) & (DM3_RING - 1)) * DM5_WARPS, pre_used, (unsigned)d, lane);
-        emit(d, orow_ring[(d & (STASH - 1)) * (T >> 5)], tot);
+        if (d > 0 && !tags_ok && !ABL(1)) tot = dm5_total(my_ring + (size_t)((d - 1) & (DM3_RING - 1)) * DM5_WARPS, pre_used, (unsigned)d, lane);
+        if (!ABL(2)) emit(d, orow_ring[(d & (STASH - 1)) * (T >> 5)], tot);
       }
       g++;
       set_reference();
@@ -1105,7 +1118,7 @@ __global__ void __launch_bounds__(DM5_T, 4) k_demap5(const DemapWork * __restric
       const unsigned long long * slot = my_ring + (size_t)((d - 1) & (DM3_RING - 1)) * DM5_WARPS;
       unsigned long long word = 0;
       if (lane < DM5_WARPS) word = ld_volatile_global_b64(slot + lane);
-      tot = dm5_total(slot, word, (unsigned)d, lane);
+      if (!ABL(1)) tot = dm5_total(slot, word, (unsigned)d, lane);
     }
     emit(d, orow_ring[(d & (STASH - 1)) * (T >> 5)], tot);
   }
@@ -1119,7 +1132,7 @@ __global__ void __launch_bounds__(DM5_T, 4) k_demap5(const DemapWork * __restric
     unsigned long long word = 0;
     const unsigned long long * slot = my_ring + (size_t)((g - 1) & (DM3_RING - 1)) * DM5_WARPS;
     if (lane < DM5_WARPS) word = ld_volatile_global_b64(slot + lane);
-    tot_last = dm5_total(slot, word, (unsigned)g, lane);
+    if (!ABL(1)) tot_last = dm5_total(slot, word, (unsigned)g, lane);
   }
   OfdmStateDev & so = states[wk.state_out];
   *reinterpret_cast<float4 *>(so.integ + k0) = make_float4(sa.integ.x, sa.integ.y, sb.integ.x, sb.integ.y);
@@ -1195,16 +1208,30 @@ __global__ void __launch_bounds__(DIP_THREADS) k_dip_search(const DipWork * __re
   int status = -1;
   long long end_pos = p0;
   const float a1 = 1.0f - LEVEL_ALPHA;
+  // |x| of a block's own 1024 samples, fetched one block ahead (the loads of block b + 1 are in flight while block b is
+  // evaluated); the 49 samples of window history in front of a block are the tail of the previous block's array
+  float nx[DIP_BLOCK / DIP_THREADS];
+  auto fetch = [&](long long b0) {
+    const bool inside = p0 + b0 + DIP_BLOCK <= rin.n;
+#pragma unroll
+    for (int u = 0; u < DIP_BLOCK / DIP_THREADS; u++) nx[u] = inside ? sample_abs<FMT>(rin.iq, p0 + b0 + tid + u * DIP_THREADS) : 0.0f;
+  };
+  fetch(0);
+  if (tid < 49) mag[tid] = 0.0f; // nothing in front of the search
   for (long long b0 = 0; status < 0; b0 += DIP_BLOCK)
   {
     if (p0 + b0 + DIP_BLOCK > rin.n) { status = 3; end_pos = rin.n; break; }
-    // |x| for this block plus the 49 preceding samples (window history)
-    for (int i = tid; i < DIP_BLOCK + 49; i += DIP_THREADS)
+    if (b0 > 0)
     {
-      const long long g = b0 + i - 49;
-      mag[i] = g >= 0 ? sample_abs<FMT>(rin.iq, p0 + g) : 0.0f;
+      float keep = 0.0f;
+      if (tid < 49) keep = mag[DIP_BLOCK + tid];
+      __syncthreads();
+      if (tid < 49) mag[tid] = keep;
     }
+#pragma unroll
+    for (int u = 0; u < DIP_BLOCK / DIP_THREADS; u++) mag[49 + tid + u * DIP_THREADS] = nx[u];
     __syncthreads();
+    fetch(b0 + DIP_BLOCK);
     // level IIR s_i = a s_{i-1} + alpha |x_i| as a scan of affine maps, 4 samples per thread
     float A = 1.0f, B = 0.0f;
 #pragma unroll
@@ -1461,6 +1488,17 @@ cudaError_t launch_demap(cudaStream_t s, const DeviceTables & t, const DemapWork
   if (lp.err != cudaSuccess) return lp.err;
   cudaError_t e = cudaMemsetAsync(ring, 0, demap_ring_bytes(n_work), s); // ring tags and the ticket counter
   if (e != cudaSuccess) return e;
+#ifdef DABSTAR_ABLATE
+  {
+    // the first DABSTAR_DEMAP_ABLATE_AFTER launches run complete (their soft bits stay in the buffers: the control flow of the
+    // later, ablated runs over the same input does not change)
+    static int n_launch = 0;
+    const int after = getenv("DABSTAR_DEMAP_ABLATE_AFTER") ? atoi(getenv("DABSTAR_DEMAP_ABLATE_AFTER")) : 0;
+    const int abl = (getenv("DABSTAR_DEMAP_ABLATE") && n_launch++ >= after) ? atoi(getenv("DABSTAR_DEMAP_ABLATE")) : 0;
+    e = cudaMemcpyToSymbolAsync(g_demap_ablate, &abl, sizeof(int), 0, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+  }
+#endif
   unsigned * ticket = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(ring) + demap_ring_bytes(n_work) - 256);
   const int16_t * rel = t.rel_of_k;
   void * args[] = { (void *)&work, (void *)&frames, (void *)&null_is_tii, (void *)&X, (void *)&rel, (void *)&states, (void *)&soft, (void *)&ring, (void *)&ticket };

@@ -1157,6 +1157,18 @@ template <int FMT> __device__ __forceinline__ float sample_abs(const void * iq, 
   const float2 v = load_sample<FMT>(iq, i);
   return sqrtf(v.x * v.x + v.y * v.y);
 }
+// The same in two halves, so that a batch of loads is issued before the first conversion: the IEEE square root carries a
+// branch (its slow path), and a load is not moved across it (ncu: 63 % of this kernel's stall samples sat on the instruction
+// after each load, one memory latency per sample).
+template <int FMT> __device__ __forceinline__ typename Raw<FMT>::reg sample_raw(const void * iq, long long i)
+{
+  return (typename Raw<FMT>::reg)reinterpret_cast<const typename Raw<FMT>::type *>(iq)[i];
+}
+template <int FMT> __device__ __forceinline__ float raw_abs(typename Raw<FMT>::reg r)
+{
+  const float2 v = to_cf(r);
+  return sqrtf(v.x * v.x + v.y * v.y);
+}
 
 template <int FMT>
 __global__ void __launch_bounds__(DIP_THREADS) k_dip_search(const DipWork * __restrict__ work, const RecInput * __restrict__ recs, DipResult * __restrict__ out)
@@ -1185,9 +1197,12 @@ __global__ void __launch_bounds__(DIP_THREADS) k_dip_search(const DipWork * __re
     long long i = tid;
     for (; i + 7LL * DIP_THREADS < hist; i += 8LL * DIP_THREADS)
     {
+      typename Raw<FMT>::reg rw[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) rw[u] = sample_raw<FMT>(rin.iq, p0 - 1 - (i + (long long)u * DIP_THREADS));
       float m[8];
 #pragma unroll
-      for (int u = 0; u < 8; u++) m[u] = sample_abs<FMT>(rin.iq, p0 - 1 - (i + (long long)u * DIP_THREADS));
+      for (int u = 0; u < 8; u++) m[u] = raw_abs<FMT>(rw[u]);
       const float w = expf((float)i * loga);
 #pragma unroll
       for (int u = 0; u < 8; u++) acc = fmaf(m[u], w * ru[u], acc);
@@ -1210,11 +1225,11 @@ __global__ void __launch_bounds__(DIP_THREADS) k_dip_search(const DipWork * __re
   const float a1 = 1.0f - LEVEL_ALPHA;
   // |x| of a block's own 1024 samples, fetched one block ahead (the loads of block b + 1 are in flight while block b is
   // evaluated); the 49 samples of window history in front of a block are the tail of the previous block's array
-  float nx[DIP_BLOCK / DIP_THREADS];
+  typename Raw<FMT>::reg nx[DIP_BLOCK / DIP_THREADS]; // raw: converted when the block is filed, a block later
   auto fetch = [&](long long b0) {
     const bool inside = p0 + b0 + DIP_BLOCK <= rin.n;
 #pragma unroll
-    for (int u = 0; u < DIP_BLOCK / DIP_THREADS; u++) nx[u] = inside ? sample_abs<FMT>(rin.iq, p0 + b0 + tid + u * DIP_THREADS) : 0.0f;
+    for (int u = 0; u < DIP_BLOCK / DIP_THREADS; u++) nx[u] = inside ? sample_raw<FMT>(rin.iq, p0 + b0 + tid + u * DIP_THREADS) : typename Raw<FMT>::reg();
   };
   fetch(0);
   if (tid < 49) mag[tid] = 0.0f; // nothing in front of the search
@@ -1229,7 +1244,7 @@ __global__ void __launch_bounds__(DIP_THREADS) k_dip_search(const DipWork * __re
       if (tid < 49) mag[tid] = keep;
     }
 #pragma unroll
-    for (int u = 0; u < DIP_BLOCK / DIP_THREADS; u++) mag[49 + tid + u * DIP_THREADS] = nx[u];
+    for (int u = 0; u < DIP_BLOCK / DIP_THREADS; u++) mag[49 + tid + u * DIP_THREADS] = raw_abs<FMT>(nx[u]);
     __syncthreads();
     fetch(b0 + DIP_BLOCK);
     // level IIR s_i = a s_{i-1} + alpha |x_i| as a scan of affine maps, 4 samples per thread

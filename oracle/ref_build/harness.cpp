@@ -74,6 +74,111 @@ extern "C" int dabref_firecode_check_and_correct(uint8_t * x11)
 }
 extern "C" int dabref_check_crc_bytes(const uint8_t * msg, int len) { return check_crc_bytes(msg, len) ? 1 : 0; }
 
+// The reference's own FibDecoder (decoder/fib_decoder*.cpp, fib_config_fig0/1.cpp) fed with CRC-good FIBs: the multiplex
+// configuration it extracts (FIG 0/0 CIF counter and EId, FIG 0/1 sub-channel organisation, FIG 0/2 service components).
+extern "C" void * dabref_fibdec_new(void)
+{
+  auto * d = new FibDecoder(nullptr);
+  d->connect_channel();
+  return d;
+}
+extern "C" void dabref_fibdec_free(void * h) { delete static_cast<FibDecoder *>(h); }
+// bits: 256 bytes, one bit each (30 bytes of FIGs + CRC), as FicDecoder hands them over (fic_decoder.cpp:239-247)
+extern "C" void dabref_fibdec_process(void * h, const uint8_t * bits, int fic_no)
+{
+  std::array<std::byte, cFibSizeVitOut> a;
+  for (int i = 0; i < cFibSizeVitOut; i++) a[i] = (std::byte)bits[i];
+  static_cast<FibDecoder *>(h)->process_FIB(a, (u16)fic_no);
+}
+extern "C" void dabref_fibdec_cif_count(void * h, int * hi, int * lo)
+{
+  i16 a = 0, b = 0;
+  static_cast<FibDecoder *>(h)->get_cif_count(&a, &b);
+  *hi = a;
+  *lo = b;
+}
+extern "C" int dabref_fibdec_eid(void * h) { return static_cast<FibDecoder *>(h)->get_EId(); }
+// out: in_use, id, start_cu, short form (uepFlag), protection level, size in CU, bit rate
+extern "C" void dabref_fibdec_subch(void * h, int sub_ch_id, int out[7])
+{
+  SChannelData d{};
+  static_cast<FibDecoder *>(h)->get_sub_channel_info(&d, sub_ch_id);
+  out[0] = d.in_use ? 1 : 0; out[1] = d.id; out[2] = d.start_cu; out[3] = d.uepFlag; out[4] = d.protlev; out[5] = d.size; out[6] = d.bitrate;
+}
+extern "C" int dabref_fibdec_subch_list(void * h, int8_t * out, int cap)
+{
+  const std::vector<i8> v = static_cast<FibDecoder *>(h)->get_sub_channel_id_list();
+  for (size_t i = 0; i < v.size() && (int)i < cap; i++) out[i] = v[i];
+  return (int)v.size();
+}
+// Service components as FIG 0/2 filed them in the CURRENT configuration: per component SId, TMId, sub-channel id (or SCId for
+// packet mode), ASCTy/DSCTy, primary flag. Returns the number of components (out receives up to cap rows of 6 ints).
+extern "C" int dabref_fibdec_components(void * h, int * out, int cap)
+{
+  auto * d = static_cast<FibDecoder *>(h);
+  int n = 0;
+  for (const auto & e : d->mpFibConfigFig0Curr->Fig0s2_BasicService_ServiceCompDefVec)
+  {
+    if (n < cap)
+    {
+      int * o = out + 6 * n;
+      const auto & c = e.ServiceComp_C;
+      o[0] = (int)e.get_SId(); o[1] = c.TMId; o[2] = c.TMId == 3 ? (int)c.TMId11.SCId : (int)c.TMId00.SubChId;
+      o[3] = c.TMId == 3 ? 0 : (int)c.TMId00.ASCTy; o[4] = c.PS_Flag; o[5] = e.ServiceComp_C_index;
+    }
+    n++;
+  }
+  return n;
+}
+
+// The reference's own Mp4Processor (backend/audio/mp4processor.cpp: super-frame synchronisation, RS repair, Fire code, AU borders
+// and CRCs) fed with logical frames; its AAC decoder is a stand-in that records the calls (stubs/faad_decoder.h).
+std::vector<DabrefAacEvent> * gDabrefAacSink = nullptr;
+struct Mp4Box
+{
+  std::vector<DabrefAacEvent> events;
+  RingBuffer<i16> audio{ 64 * 32768 };
+  RingBuffer<u8> frames{ 2 * 32768 };
+  std::unique_ptr<Mp4Processor> proc;
+  int bitRate = 0;
+};
+extern "C" void * dabref_mp4_new(int bit_rate)
+{
+  auto * b = new Mp4Box;
+  b->bitRate = bit_rate;
+  b->proc.reset(new Mp4Processor(nullptr, (i16)bit_rate, &b->audio, &b->frames));
+  return b;
+}
+extern "C" void dabref_mp4_free(void * h) { delete static_cast<Mp4Box *>(h); }
+// frame_bits: n_frames x 24 * bit_rate bytes (one bit per byte). Returns the number of decoder events so far.
+extern "C" int dabref_mp4_add_frames(void * h, const uint8_t * frame_bits, int n_frames)
+{
+  auto * b = static_cast<Mp4Box *>(h);
+  gDabrefAacSink = &b->events;
+  const size_t len = 24 * (size_t)b->bitRate;
+  for (int i = 0; i < n_frames; i++)
+  {
+    std::vector<u8> v(frame_bits + (size_t)i * len, frame_bits + (size_t)(i + 1) * len);
+    b->proc->add_to_frame(v);
+    // the "AAC dump" ring buffer is never drained here: keep it from filling up
+    b->frames.flush_ring_buffer();
+  }
+  gDabrefAacSink = nullptr;
+  return (int)b->events.size();
+}
+// Event i: kind (1 access unit / 0 concealment), value (stream parameters / samples), bytes written to `out` (up to cap).
+extern "C" int dabref_mp4_event(void * h, int i, int * kind, int * value, uint8_t * out, int cap)
+{
+  auto * b = static_cast<Mp4Box *>(h);
+  if (i < 0 || i >= (int)b->events.size()) return -1;
+  const DabrefAacEvent & e = b->events[(size_t)i];
+  *kind = e.kind;
+  *value = e.value;
+  const int n = (int)std::min<size_t>(e.bytes.size(), (size_t)std::max(cap, 0));
+  if (n > 0) memcpy(out, e.bytes.data(), (size_t)n);
+  return (int)e.bytes.size();
+}
+
 // ------------------------------------------------------------------------------------------------ channel decoding
 extern "C" void dabref_viterbi(const int16_t * in, int frame_bits, uint8_t * out)
 {

@@ -37,6 +37,9 @@
 #include "crc.h"
 #include "dabradio.h"
 #include "process_params.h"
+#include "mp4processor.h"
+#include "fib_decoder.h"
+#include "charsets.h"
 #undef private
 #undef protected
 #include <vector>

@@ -36,6 +36,16 @@ void IFibDecoder::signal_start_announcement(const QString &, i32) {}
 void IFibDecoder::signal_stop_announcement(const QString &, i32) {}
 void IFibDecoder::signal_fib_time_info(const SUtcTimeSet &) {}
 void IFibDecoder::signal_fib_loaded_state(EFibLoadingState) {}
+// backend/charsets.cpp needs QChar tables; labels are not part of what is pinned: bytes pass through
+QString to_QString_using_charset(const QByteArray & b, ECharacterSet) { return QString(std::string(b)); }
+QString to_QString_using_charset(const char * p, ECharacterSet, i32 size) { return QString::fromUtf8(p, size); }
+// Mp4Processor's signals (moc would generate them): GUI counters only
+void Mp4Processor::signal_show_frame_errors(i32) {}
+void Mp4Processor::signal_show_rs_errors(i32) {}
+void Mp4Processor::signal_show_aac_errors(i32) {}
+void Mp4Processor::signal_is_stereo(bool) {}
+void Mp4Processor::signal_new_aac_frame() {}
+void Mp4Processor::signal_show_rs_corrections(i32, i32) {}
 
 // ---------------------------------------------------------------------------------------------------
 // FFTW3f shim: unnormalised DFT, sign as planned.

@@ -175,6 +175,31 @@ class Oracle:
         n = int(self.f("dabplus_run")(_ptr(b), int(bit_rate), int(b.shape[0]), rec, cap, _ptr(pay)))
         return list(rec[:n]), pay[:n]
 
+    def mp4_events(self, frame_bits: np.ndarray, bit_rate: int) -> list[tuple]:
+        """oracle/_ref only: the reference's own Mp4Processor (mp4processor.cpp) over a run of logical frames, with a recording
+        stand-in for its AAC decoder. Returns what the processor handed to the decoder, in order:
+        ("au", stream parameter bits, access-unit bytes) or ("conceal", samples)."""
+        assert self.prefix == "dabref"
+        b = np.ascontiguousarray(frame_bits, np.uint8).reshape(-1, 24 * bit_rate)
+        self.f("mp4_new").restype = c_p
+        h = c_p(self.f("mp4_new")(int(bit_rate)))
+        try:
+            n = int(self.f("mp4_add_frames")(h, _ptr(b), int(b.shape[0])))
+            out = []
+            buf = np.zeros(1024, np.uint8)
+            for i in range(n):
+                kind, value = ctypes.c_int(0), ctypes.c_int(0)
+                ln = int(self.f("mp4_event")(h, i, ctypes.byref(kind), ctypes.byref(value), _ptr(buf), buf.size))
+                out.append(("au", value.value, buf[:ln].tobytes()) if kind.value == 1 else ("conceal", value.value))
+            return out
+        finally:
+            self.f("mp4_free")(h)
+
+    def fib_decoder(self) -> "RefFibDecoder":
+        """oracle/_ref only: the reference's own FibDecoder object (decoder/fib_decoder*.cpp)."""
+        assert self.prefix == "dabref"
+        return RefFibDecoder(self)
+
     # ---- channel decoding
     def viterbi(self, soft: np.ndarray, frame_bits: int) -> np.ndarray:
         soft = np.ascontiguousarray(soft, np.int16)
@@ -350,6 +375,52 @@ class TiiDetector:
         out = np.zeros(768, np.complex64)
         self.o.f("tii_decoded")(self.h, _ptr(out))
         return out
+
+
+class RefFibDecoder:
+    """FibDecoder of the reference behind the harness: process_FIB, then the multiplex configuration it filed."""
+
+    def __init__(self, o: "Oracle"):
+        self.o = o
+        o.f("fibdec_new").restype = c_p
+        self.h = c_p(o.f("fibdec_new")())
+
+    def __del__(self):
+        try:
+            self.o.f("fibdec_free")(self.h)
+        except Exception:
+            pass
+
+    def process_FIB(self, fib_bits: np.ndarray):
+        b = np.ascontiguousarray(fib_bits, np.uint8).reshape(-1, 256)
+        for i, row in enumerate(b):
+            self.o.f("fibdec_process")(self.h, _ptr(row), ctypes.c_int(i % 12))
+
+    def get_cif_count(self) -> tuple[int, int]:
+        hi, lo = ctypes.c_int(0), ctypes.c_int(0)
+        self.o.f("fibdec_cif_count")(self.h, ctypes.byref(hi), ctypes.byref(lo))
+        return hi.value, lo.value
+
+    def eid(self) -> int:
+        return int(self.o.f("fibdec_eid")(self.h))
+
+    def sub_channels(self) -> list[tuple]:
+        """[(sub_ch_id, start_cu, size_cu, short_form, prot_level, bit_rate)] in the order FIG 0/1 filed them."""
+        ids = np.zeros(64, np.int8)
+        n = int(self.o.f("fibdec_subch_list")(self.h, _ptr(ids), 64))
+        out = []
+        for i in ids[:n]:
+            v = (ctypes.c_int * 7)()
+            self.o.f("fibdec_subch")(self.h, int(i), v)
+            assert v[0] == 1 and v[1] == int(i)
+            out.append((v[1], v[2], v[5], v[3], v[4], v[6]))
+        return out
+
+    def components(self) -> list[tuple]:
+        """[(SId, TMId, SubChId or SCId, ASCTy / DSCTy, primary, index within the service)]"""
+        buf = (ctypes.c_int * (6 * 256))()
+        n = int(self.o.f("fibdec_components")(self.h, buf, 256))
+        return [(buf[6 * i] & 0xffffffff,) + tuple(buf[6 * i + k] for k in range(1, 6)) for i in range(min(n, 256))]
 
 
 class ChainResult:

@@ -50,6 +50,59 @@ def test_rs_and_firecode_against_the_reference_objects(oracle, refo):
         assert oa == ob and np.array_equal(ya, yb)
 
 
+def expected_decoder_events(rec, pay):
+    """What Mp4Processor hands to its AAC decoder for the super-frames the restatement reports (mp4processor.cpp:317-397):
+    every CRC-good access unit of an accepted super-frame, a concealment call for every other one (concealment is on by
+    default), nothing for a super-frame whose RS / Fire-code repair failed."""
+    ev = []
+    for r, p in zip(rec, pay):
+        if not r.ok:
+            continue
+        params = r.dac_rate | (r.sbr_flag << 1) | (r.aac_channel_mode << 2) | (r.ps_flag << 3) | (r.mpeg_surround << 4)
+        for u in range(r.num_aus):
+            if r.au_state[u] == 1:
+                ev.append(("au", params, p[r.au_start[u]:r.au_start[u + 1] - 2].tobytes()))
+            else:
+                ev.append(("conceal", 960 * (2 if r.sbr_flag else 1) * 2))
+    return ev
+
+
+@pytest.mark.parametrize("bit_rate,scenario", [(72, "clean"), (72, "byte_errors"), (32, "heavy"), (128, "resync"), (48, "too_short"), (8, "junk"), (96, "lost_sync")])
+def test_superframe_state_machine_against_the_reference_mp4processor(oracle, refo, bit_rate, scenario):
+    """Pins the restated super-frame processor (oracle/dab_outer.c) to the reference's own Mp4Processor object: synchronisation
+    on the Fire code, the 4-super-frame grace counter, the one-frame slide after a miss, RS repair, AU borders and CRCs."""
+    def byte_errors(stream, rng, rate):
+        by = np.packbits(stream.reshape(-1))
+        pos = rng.choice(by.size, max(1, int(by.size * rate)), replace=False)
+        by[pos] ^= rng.integers(1, 256, pos.size, dtype=np.uint8)
+        stream[:] = np.unpackbits(by).reshape(stream.shape)
+
+    def resync(stream, rng):
+        stream[12:22] = rng.integers(0, 2, stream[12:22].shape, dtype=np.uint8)
+        byte_errors(stream[30:], rng, 0.01)
+
+    def lost_sync(stream, rng):  # five super-frames of noise: the grace counter runs out and the processor searches again
+        stream[10:36] = rng.integers(0, 2, stream[10:36].shape, dtype=np.uint8)
+
+    damage = {"clean": None, "byte_errors": lambda s, r: byte_errors(s, r, 0.02), "heavy": lambda s, r: byte_errors(s, r, 0.06), "resync": resync,
+              "too_short": None, "junk": None, "lost_sync": lost_sync}[scenario]
+    n_sf = 1 if scenario == "too_short" else 12
+    stream, _ = make_stream(oracle, bit_rate, n_sf, seed=len(scenario) + bit_rate, lead=0 if scenario == "too_short" else 2, damage=damage)
+    if scenario == "too_short":
+        stream = stream[:4]
+    if scenario == "junk":
+        stream = np.random.default_rng(5).integers(0, 2, stream.shape, dtype=np.uint8)
+    if scenario == "resync":
+        stream = np.concatenate([stream[:40], np.random.default_rng(1).integers(0, 2, (1, 24 * bit_rate), dtype=np.uint8), stream[40:]])
+    rec, pay = oracle.dabplus_run(stream, bit_rate)
+    got = refo.mp4_events(stream, bit_rate)
+    want = expected_decoder_events(rec, pay)
+    assert len(got) == len(want), (len(got), len(want))
+    assert got == want
+    if scenario in ("clean", "byte_errors", "resync", "lost_sync"):
+        assert sum(1 for e in got if e[0] == "au") > 10
+
+
 @pytest.mark.parametrize("bit_rate", [32, 72, 128])
 def test_superframe_processor_recovers_the_access_units(oracle, bit_rate):
     def damage(stream, rng):  # up to 5 byte errors in every code word: all corrected

@@ -1,6 +1,7 @@
 """Row f1: multiplex configuration out of the FIC (FIG 0/0, 0/1, 0/2). The parser is host code in the product library, so
-most of this runs without a GPU. The reference's FibDecoder needs Qt (QTimer, signals) and is not buildable here: this
-boundary is pinned by EN 300 401 bit layouts as the reference's source states them (fib_decoder_fig0.cpp:89-290,
+most of this runs without a GPU. The parser is pinned against the reference's OWN FibDecoder object (decoder/fib_decoder*.cpp,
+fib_config_fig0.cpp compiled into oracle/_ref against stand-ins for QString / QTimer, oracle/ref_build/stubs) on transmitter-made
+and on randomly assembled FIBs, by EN 300 401 bit layouts as the reference's source states them (fib_decoder_fig0.cpp:89-290,
 fib_table.h:51) and by round trips through the bundled transmitter's MCI generator."""
 import numpy as np
 import pytest
@@ -34,6 +35,121 @@ def test_round_trip_through_the_transmitter():
     p.process_FIB(rec.fib_truth[2].reshape(12, 256))
     assert len(p.sub_channels()) == len(ENSEMBLE) and len(p.components()) == len(ENSEMBLE)
     assert p.get_cif_count() == (0, 8) and p.ensemble().restarts == 0
+
+
+def _subch_key(s):
+    return (s.sub_ch_id, s.start_cu, s.size_cu, s.short_form, s.prot_level, s.bit_rate)
+
+
+def _compare_with_reference(p, d):
+    assert [_subch_key(s) for s in p.sub_channels()] == d.sub_channels()
+    # (a packet-mode component carries its 12-bit SCId in `type` and no sub-channel; the harness reports it in the sub-channel column)
+    assert [(c.sid, c.tmid, c.type if c.tmid == 3 else c.sub_ch_id, 0 if c.tmid == 3 else c.type, c.primary, c.comp_index) for c in p.components()] == d.components()
+    if p.ensemble() is not None:
+        assert p.get_cif_count() == d.get_cif_count()
+
+
+def test_against_the_reference_fibdecoder_on_transmitter_fibs(refo):
+    rec = synth.generate(70, seed=5, subch=ENSEMBLE, fig_mode=1, eid=0x4FFF, snr_db=100.0, lead_samples=0, tail_samples=0)
+    p, d = api.FibParser(), refo.fib_decoder()
+    for f in range(70):   # incl. the CIF counter's wrap at 250
+        fibs = rec.fib_truth[f].reshape(12, 256)
+        p.process_FIB(fibs)
+        d.process_FIB(fibs)
+        _compare_with_reference(p, d)
+    assert len(p.sub_channels()) == len(ENSEMBLE) and p.get_cif_count() == divmod(4 * 69, 250)
+
+
+def _random_mci(rng, n_sub):
+    """Non-overlapping sub-channels (short and long form, both EEP options) and one service per sub-channel with 1..3 components."""
+    t8 = [(16, 32), (21, 32), (24, 32), (29, 32), (35, 32), (24, 48), (29, 48), (35, 48), (42, 48), (52, 48), (29, 56), (35, 56), (42, 56), (52, 56),
+          (32, 64), (42, 64), (48, 64), (58, 64), (70, 64), (40, 80), (52, 80), (58, 80), (70, 80), (84, 80), (48, 96), (58, 96), (70, 96), (84, 96),
+          (104, 96), (58, 112), (70, 112), (84, 112), (104, 112), (64, 128), (84, 128), (96, 128), (116, 128), (140, 128)]
+    figs01, figs02, cu = [], [], 0
+    ids = rng.choice(64, n_sub, replace=False)
+    for i, sid in enumerate(ids):
+        if rng.integers(0, 2):
+            idx = int(rng.integers(0, len(t8)))
+            size = t8[idx][0]
+            entry = bytes([(int(sid) << 2) | (cu >> 8), cu & 0xff, idx])
+        else:
+            opt, lvl = int(rng.integers(0, 2)), int(rng.integers(0, 4))
+            n = int(rng.integers(1, 5))
+            size = ([12, 8, 6, 4][lvl] * n) if opt == 0 else ([27, 21, 18, 15][lvl] * n)
+            entry = bytes([(int(sid) << 2) | (cu >> 8), cu & 0xff, 0x80 | (opt << 4) | (lvl << 2) | (size >> 8), size & 0xff])
+        if cu + size > 864:
+            break
+        figs01.append(entry)
+        cu += size + int(rng.integers(0, 6))
+        # FIG 0/2: one service, primary component on this sub-channel, sometimes a secondary data / packet component
+        comps = [bytes([(0 << 6) | int(rng.integers(0, 64)), (int(sid) << 2) | 2])]
+        if rng.integers(0, 3) == 0:
+            comps.append(bytes([(1 << 6) | int(rng.integers(0, 64)), (int(sid) << 2) | 0]))
+        if rng.integers(0, 4) == 0:
+            scid = int(rng.integers(0, 4096))
+            comps.append(bytes([(3 << 6) | (scid >> 6), ((scid & 63) << 2) | 0]))
+        if rng.integers(0, 4) == 0:   # data service: 32-bit SId
+            figs02.append((1, bytes([0xE1, 0x00 | int(rng.integers(0, 16)), int(rng.integers(0, 256)), i, len(comps)]) + b"".join(comps)))
+        else:
+            figs02.append((0, bytes([0xD0 | int(rng.integers(0, 16)), i, len(comps)]) + b"".join(comps)))
+    return figs01, figs02
+
+
+def _pack_fibs(rng, figs01, figs02, cif):
+    """FIG 0/0 + the entries spread over FIBs of at most 30 bytes, in random order."""
+    groups = [("00", bytes([0x00, 0x4F, 0xFF, (cif // 250) & 0x1f, cif % 250]))]
+    groups += [("01", e) for e in figs01] + [("02%d" % pd, e) for pd, e in figs02]
+    order = rng.permutation(len(groups))
+    fibs, cur, open_fig = [], b"", None
+    for k in order:
+        kind, body = groups[k]
+        head = {"00": 0x00, "01": 0x01, "020": 0x02, "021": 0x22}[kind]
+        # a FIG of its own per entry (header 1 + extension byte 1 + body): simple and legal
+        fig = bytes([len(body) + 1, head]) + body
+        if len(cur) + len(fig) > 30:
+            fibs.append(fib_bytes_to_bits(cur))
+            cur = b""
+        cur += fig
+    if cur:
+        fibs.append(fib_bytes_to_bits(cur))
+    return np.stack(fibs)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_against_the_reference_fibdecoder_on_random_mci(refo, seed):
+    rng = np.random.default_rng(100 + seed)
+    figs01, figs02 = _random_mci(rng, int(rng.integers(1, 20)))
+    p, d = api.FibParser(), refo.fib_decoder()
+    for rep in range(3):   # the MCI repeats: nothing is filed twice, the counter advances
+        fibs = _pack_fibs(rng, figs01, figs02, cif=4 * rep + 240)
+        for fib in fibs:
+            p.process_FIB(fib)
+            d.process_FIB(fib)
+            _compare_with_reference(p, d)
+    assert len(p.sub_channels()) == len(figs01) and len(p.components()) == sum(e[4 if pd else 2] & 15 for pd, e in figs02)
+
+
+def test_against_the_reference_fibdecoder_on_impossible_content(refo):
+    """Overlapping sub-channels or a sub-channel beyond CU 864 make the reference drop everything it has collected
+    (_restart_fib_decoding, fib_decoder.cpp:131-150): same database afterwards on both sides."""
+    ok = bytes([4, 0x01, (1 << 2), 10, 35])
+    clash = bytes([4, 0x01, (2 << 2), 100, 35])
+    beyond = bytes([5, 0x01, (3 << 2) | 3, 0x20, 0x80 | (3 << 2), 100])
+    svc = bytes([6, 0x02, 0xD1, 0x23, 1, 0x3F, (1 << 2) | 2])
+    p, d = api.FibParser(), refo.fib_decoder()
+    for fib in (ok + svc, ok + clash, ok, svc, beyond, ok + svc):
+        b = fib_bytes_to_bits(fib)
+        p.process_FIB(b)
+        d.process_FIB(b)
+        _compare_with_reference(p, d)
+    assert len(p.sub_channels()) == 1 and len(p.components()) == 1
+    # One deliberate difference: an entry that crosses the end of its FIG (here a FIG 0/2 whose length byte is one short) is
+    # abandoned by the parser; the reference has no such bound and files what it reads beyond the FIG (fib_decoder_fig0.cpp:
+    # 251-290; found by the round-1 review as an over-read of the caller's buffer, include/dabstar_b200.h).
+    short = bytes([5, 0x02, 0xD9, 0x99, 1, 0x3F, (1 << 2) | 2])
+    p.process_FIB(fib_bytes_to_bits(short))
+    d.process_FIB(fib_bytes_to_bits(short))
+    assert len(p.components()) == 1 and len(d.components()) == 2
 
 
 def test_cif_counter_wraps_at_250():

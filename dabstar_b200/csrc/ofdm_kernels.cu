@@ -205,7 +205,7 @@ __device__ __forceinline__ void convert_mix(float2 (&v)[16], const typename Raw<
   if (f == 0)
   {
     if (ph == 0) return; // osc[0] = 1: the reference multiplies by exactly (1, 0)
-    const float2 c = osc(ph);
+    const float2 c = step[0]; // osc(ph), filed by the caller when the phase changed (it stands still while f = 0)
 #pragma unroll
     for (int n1 = 0; n1 < 16; n1++) v[n1] = cmul(v[n1], c);
     return;
@@ -273,7 +273,8 @@ __global__ void __launch_bounds__(FFT_THREADS, 5) k_fft_frames(const FrameDesc *
   SymbolItem cur;
   cur.out = -1;
   int dph = 0;        // oscillator phase step of one data symbol: -f_data T_s mod FS
-  int step_f = 0;     // integer Hz the shared step table holds (0: none needed)
+  int step_f = 0;     // integer Hz the shared step table holds (0: none)
+  int step_ph = -1;   // f = 0: oscillator phase whose phasor step[0] holds (-1: none)
   auto issue = [&](const SymbolItem & it, int b) {
     if (tid == 0)
     {
@@ -322,12 +323,22 @@ __global__ void __launch_bounds__(FFT_THREADS, 5) k_fft_frames(const FrameDesc *
     if (cur.out >= 0)
     {
       float2 v[16];
-      if (cur.f != 0 && cur.f != step_f)
+      if (cur.f != 0 ? cur.f != step_f : (cur.ph != 0 && cur.ph != step_ph))
       {
-        // (all threads agree on cur.f: no divergence around the barriers)
+        // (all threads agree on cur.f / cur.ph: no divergence around the barriers)
         __syncthreads(); // nobody reads the previous table any more
-        if (tid < 16) step[tid] = osc(mod_fs32(-(int)(((long long)cur.f * 128 * tid) % FS)));
-        step_f = cur.f;
+        if (cur.f != 0)
+        {
+          if (tid < 16) step[tid] = osc(mod_fs32(-(int)(((long long)cur.f * 128 * tid) % FS)));
+          step_f = cur.f;
+          step_ph = -1;
+        }
+        else
+        {
+          if (tid == 0) step[0] = osc(cur.ph);
+          step_ph = cur.ph;
+          step_f = 0;
+        }
         __syncthreads();
       }
       if (item_async<FMT>(cur))

@@ -39,6 +39,24 @@ def test_protection_and_backend_cuda(ctx, viterbi_path):
     assert np.array_equal(out, np.unpackbits(g["backend_out"], axis=1)[:, :1728])
 
 
+def test_sweep_soft_bits_of_the_reference_cuda(ctx, viterbi_path):
+    """configs[3]'s input: the reference's own soft bits per protection level (tests/golden/sweep_softbits.npz: OfdmDecoder output
+    of oracle/_ref at 12 dB, time de-interleaved; tools/make_sweep_softbits.py). Protection::deconvolve on the GPU gives the
+    reference's Backend output once the energy dispersal is put back; a tiled batch of 2 400 frames takes the
+    thread-per-code-word path with its device-written job list, the 16 frames alone the warp-per-code-word kernel."""
+    import bench
+    g = load("sweep_softbits.npz")
+    assert [tuple(int(x) for x in row) for row in g["profiles"]] == [p[1:] for p in bench.SWEEP_PROFILES]
+    for li, (name, sf, lvl, br, cu) in enumerate(bench.SWEEP_PROFILES):
+        soft = g[f"soft_{li}"]
+        want = np.unpackbits(g[f"bits_{li}"], axis=1)[:, :24 * br] ^ bench.prbs_bits(24 * br)[None, :]
+        assert soft.shape == (16, cu * 64) and want.shape == (16, 24 * br)
+        prot = api.Protection(sf, br, lvl, ctx)
+        assert np.array_equal(prot.deconvolve(soft, cu).reshape(want.shape), want), name
+        big = prot.deconvolve(np.tile(soft, (150, 1)), cu).reshape(150, 16, 24 * br)
+        assert np.array_equal(big, np.broadcast_to(want, big.shape)), name
+
+
 def test_tables_cuda(ctx):
     g = load("tables.npz")
     fi = api.FreqInterleaver(ctx)

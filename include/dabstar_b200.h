@@ -78,9 +78,11 @@ int dabstar_protection_addresses(dabstar_ctx * ctx, int short_form, int bit_rate
  *   reference does, so 32 bits per channel divide by -2^31; float32: as is.
  * The decoder's native input formats (DABSTAR_FMT_U8 / I16 / CF32) are converted inside the FFT kernel; every
  * other combination goes through this call first and is then decoded as DABSTAR_FMT_CF32.
- * Reference reader bugs that are NOT reproduced (they read the wrong byte or a constant): uint8 with QI order
- * indexes the table with the loop counter (xml_reader.cpp:421), int8 with Q_Only sets the real part to 127
- * (:690), MSB int24 takes one byte from offset 4*i+4 (:309). */
+ * Reference reader defects that are NOT reproduced (they read the wrong byte, a constant, or leave the channels unswapped; each
+ * is pinned against the reference's own XmlReader thread in tests/test_ingest_formats.py): uint8 with QI order indexes the table
+ * with the loop counter (xml_reader.cpp:421), int8 with Q_Only sets the real part to 127 (:690), MSB int24 takes one byte from
+ * offset 4*i+4 (:309, and :456 in the QI branch, which also sign-extends with 0x7F000000), float32 with QI order does not swap I
+ * and Q (:525-543). int8 divides by 127 in IEEE arithmetic; the reference's -ffast-math build multiplies by the reciprocal (1 ulp). */
 enum { DABSTAR_CONTAINER_INT8 = 0, DABSTAR_CONTAINER_UINT8 = 1, DABSTAR_CONTAINER_INT16 = 2, DABSTAR_CONTAINER_INT24 = 3,
        DABSTAR_CONTAINER_INT32 = 4, DABSTAR_CONTAINER_FLOAT32 = 5,
        /* RIFF/WAVE files go through libsndfile's float read in the reference (wav_reader.cpp:164): 16 / 24-bit PCM and

@@ -74,6 +74,49 @@ extern "C" int dabref_firecode_check_and_correct(uint8_t * x11)
 }
 extern "C" int dabref_check_crc_bytes(const uint8_t * msg, int len) { return check_crc_bytes(msg, len) ? 1 : 0; }
 
+// The reference's own file-reader threads: XmlReader (sample format conversion of every container / byte order / channel order,
+// 1 ms linear-interpolation resampling) and WavReader (resampling of libsndfile's float frames). The threads pace themselves in
+// real time (1 ms of sleep per millisecond of recording): keep the inputs to a fraction of a second.
+static u32 pow2_at_least(long long n) { u32 p = 1024; while ((long long)p < n) p <<= 1; return p; }
+extern "C" int64_t dabref_xml_reader_run(const uint8_t * bytes, int64_t n_bytes, int sample_rate, int bits, const char * container, const char * byte_order,
+                                         const char * iq_order, int64_t n_samples, float * out, int64_t cap)
+{
+  FILE * f = fmemopen(const_cast<uint8_t *>(bytes), (size_t)n_bytes, "rb");
+  if (!f) return -1;
+  bool ok = false;
+  XmlDescriptor fd(nullptr, &ok);
+  fd.sampleRate = sample_rate;
+  fd.nrChannels = 2;
+  fd.bitsperChannel = bits;
+  fd.container = container;
+  fd.byteOrder = byte_order;
+  fd.iqOrder = iq_order;
+  XmlFileReader parent;
+  parent.samplesToRead = n_samples;
+  parent.mFileLength = n_bytes;
+  RingBuffer<cf32> rb(pow2_at_least((n_samples / std::max(1, sample_rate / 1000) + 4) * 2048));
+  {
+    XmlReader reader(&parent, f, &fd, 0, &rb); // the constructor starts the thread; the QThread stand-in runs it to its end here
+  }
+  fclose(f);
+  const int64_t n = std::min<int64_t>(rb.get_ring_buffer_read_available(), cap);
+  rb.get_data_from_ring_buffer(reinterpret_cast<cf32 *>(out), (i32)n);
+  return n;
+}
+extern "C" int64_t dabref_wav_reader_run(const float * frames, int64_t n_frames, int sample_rate, float * out, int64_t cap)
+{
+  SNDFILE snd{ frames, (sf_count_t)n_frames, 0 };
+  WavFileHandler parent;
+  RingBuffer<cf32> rb(pow2_at_least((n_frames / std::max(1, sample_rate / 1000) + 4) * 2048 + 4 * 32768));
+  {
+    WavReader reader(&parent, &snd, &rb, sample_rate);
+    reader.start_reader();
+  }
+  const int64_t n = std::min<int64_t>(rb.get_ring_buffer_read_available(), cap);
+  rb.get_data_from_ring_buffer(reinterpret_cast<cf32 *>(out), (i32)n);
+  return n;
+}
+
 // The reference's own FibDecoder (decoder/fib_decoder*.cpp, fib_config_fig0/1.cpp) fed with CRC-good FIBs: the multiplex
 // configuration it extracts (FIG 0/0 CIF counter and EId, FIG 0/1 sub-channel organisation, FIG 0/2 service components).
 extern "C" void * dabref_fibdec_new(void)

@@ -40,6 +40,11 @@
 #include "mp4processor.h"
 #include "fib_decoder.h"
 #include "charsets.h"
+#include "xml_reader.h"
+#include "xml_descriptor.h"
+#include "xml_filereader.h"
+#include "wav_reader.h"
+#include "wavfiles.h"
 #undef private
 #undef protected
 #include <vector>

@@ -147,6 +147,33 @@ class Oracle:
         assert r == 0
         return out
 
+    def xml_reader_run(self, raw: np.ndarray, sample_rate: int, container: str, bits: int, byte_order: str, iq_order: str, n_samples: int) -> np.ndarray:
+        """oracle/_ref only: the reference's own XmlReader thread over a file image `raw` (sample data only, as after the
+        descriptor): format conversion + (sample_rate != 2 048 000) resampling, what it put into its ring buffer. Paces itself in
+        real time: 1 ms per millisecond of recording."""
+        assert self.prefix == "dabref"
+        raw = np.ascontiguousarray(raw, np.uint8)
+        cap = (n_samples // max(1, sample_rate // 1000) + 4) * 2048
+        out = np.zeros(cap, np.complex64)
+        fn = self.f("xml_reader_run")
+        fn.restype = ctypes.c_int64
+        n = fn(_ptr(raw), ctypes.c_int64(raw.size), int(sample_rate), int(bits), container.encode(), byte_order.encode(), iq_order.encode(),
+               ctypes.c_int64(n_samples), _ptr(out), ctypes.c_int64(cap))
+        assert n >= 0
+        return out[:n]
+
+    def wav_reader_run(self, frames: np.ndarray, sample_rate: int) -> np.ndarray:
+        """oracle/_ref only: the reference's own WavReader thread over the float frames libsndfile would deliver."""
+        assert self.prefix == "dabref"
+        x = np.ascontiguousarray(frames, np.complex64).reshape(-1)
+        cap = (x.size // max(1, sample_rate // 1000) + 4) * 2048 + 4 * 32768
+        out = np.zeros(cap, np.complex64)
+        fn = self.f("wav_reader_run")
+        fn.restype = ctypes.c_int64
+        n = fn(_ptr(x), ctypes.c_int64(x.size), int(sample_rate), _ptr(out), ctypes.c_int64(cap))
+        assert n >= 0
+        return out[:n]
+
     # ---- DAB+ outer code
     def rs_decode(self, cw: np.ndarray):
         cw = np.ascontiguousarray(cw, np.uint8)

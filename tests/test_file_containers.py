@@ -129,6 +129,40 @@ def test_oracle_resample_matches_formula(oracle, rate, reader):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("rate", RATES)
+def test_xml_reader_resampling_against_the_reference(oracle, refo, rate):
+    """The reference's own XmlReader thread (oracle/_ref) at a non-native sample rate: 1 ms blocks, linear interpolation
+    (xml_reader.cpp:70-76, 212-231). Bit exact."""
+    rng = np.random.default_rng(rate % 977)
+    ms = 30
+    n = ms * (rate // 1000)
+    x16 = rng.integers(-20000, 20000, (n + 4 * (rate // 1000), 2)).astype(np.int16)
+    got = refo.xml_reader_run(x16.view(np.uint8).reshape(-1), rate, "int16", 16, "LSB", "IQ", n)
+    x = (x16.astype(np.float32) / np.float32(32768)).view(np.complex64).reshape(-1)
+    want = oracle.resample(x, rate, "xml")
+    m = ms * 2048
+    assert got.size >= m and want.size >= m
+    assert np.array_equal(got[:m].view(np.uint32), want[:m].view(np.uint32))
+
+
+@pytest.mark.parametrize("rate", RATES)
+def test_wav_reader_resampling_against_the_reference(oracle, refo, rate):
+    """The reference's own WavReader thread over the float frames libsndfile would deliver (wav_reader.cpp:66-83, 196-211).
+    Its interpolation table is computed in single precision under -ffast-math: gcc turns sampleRate / 1000.0f into a product
+    with 0.001f, which moves the interpolation positions by up to 2e-4 of a sample unless the rate is exact in both forms; the
+    restatement keeps the IEEE division. Same blocks, values within that; bit exact at 2.5 MS/s. The reader drops the last,
+    incomplete 32768-frame read."""
+    rng = np.random.default_rng(rate % 971)
+    n_frames = 4 * 32768 + 1000
+    x = ((rng.normal(size=n_frames) + 1j * rng.normal(size=n_frames)) * 0.3).astype(np.complex64)
+    got = refo.wav_reader_run(x, rate)
+    want = oracle.resample(x[:4 * 32768], rate, "wav")
+    assert got.size == want.size == ((4 * 32768 - 1) // (rate // 1000)) * 2048
+    assert np.abs(got - want).max() < 2e-3
+    if rate == 2500000:
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
 def test_oracle_pcm_conversions(oracle):
     rng = np.random.default_rng(5)
     u8 = rng.integers(0, 256, 2 * 500, dtype=np.uint8)

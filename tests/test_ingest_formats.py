@@ -1,6 +1,7 @@
 """Row I1: file sample formats. CPU part: the oracle's restatement of XmlReader::readElements_* against independent numpy
-formulas (the reader itself needs Qt, so this boundary is pinned by the formulas the reference source states,
-xml_reader.cpp:254-800). GPU part: dabstar_ingest_convert bit exact against the oracle, and a recording stored as
+formulas (xml_reader.cpp:254-800) and against the reference's OWN XmlReader thread (compiled into oracle/_ref with stand-ins for
+its Qt parent widget and the XML descriptor parser): bit exact for every container / byte order / channel order except the
+reader defects listed in test_xml_reader_against_the_reference, which are asserted as such. GPU part: dabstar_ingest_convert bit exact against the oracle, and a recording stored as
 big-endian QI int16 decodes to the same bits as its native little-endian IQ form."""
 import itertools
 
@@ -50,6 +51,45 @@ def numpy_reference(raw, container, bits, byte_order, order, n):
     else:
         out[:, 1] = v
     return out.view(np.complex64).reshape(-1)
+
+
+# What the reference's reader does differently from its own other branches (all in xml_reader.cpp); the product follows the
+# formulas of the other branches (include/dabstar_b200.h documents the list).
+REFERENCE_DEFECTS = {
+    ("uint8", "LSB", "QI"): "table indexed with the loop counter instead of the sample byte (:421)",
+    ("int8", "LSB", "Q_Only"): "real part set to 127 (:690)",
+    ("int24", "MSB", "IQ"): "one byte taken from offset 4 i + 4 instead of 6 i + 4 (:309)",
+    ("int24", "MSB", "QI"): "the same offset, and the sign extension ORs 0x7F000000 instead of 0xFF000000 (:456-463)",
+    ("float32", "LSB", "QI"): "I and Q are not swapped (:536-543)",
+    ("float32", "MSB", "QI"): "I and Q are not swapped (:525-533)",
+}
+
+
+@pytest.mark.parametrize("container,byte_order,order", CASES)
+def test_xml_reader_against_the_reference(oracle, refo, container, byte_order, order):
+    n = 2048 * 4   # the reader delivers 2048 samples per millisecond at the native rate
+    per = 2 if order in ("IQ", "QI") else 1
+    for bits in {"int16": (16, 12), "int24": (24, 20), "int32": (32, 24)}.get(container, (0,)):
+        raw = raw_bytes(container, per * (n + 4096), seed=3 + bits)
+        if container == "float32":   # finite floats only (bit patterns of NaNs do not survive a swap in numpy)
+            raw = np.random.default_rng(bits).normal(size=per * (n + 4096)).astype(np.float32).view(np.uint8)
+        got = refo.xml_reader_run(raw, 2048000, container, bits or 8 * WIDTH[container], byte_order, order, n)[:n]
+        want = oracle.convert_samples(raw, api.CONTAINERS[container], bits, byte_order == "MSB", api.IQ_ORDERS[order], n)
+        assert got.size == n
+        key = (container, byte_order, order)
+        if key in REFERENCE_DEFECTS:
+            assert not np.array_equal(got.view(np.uint32), want.view(np.uint32)), REFERENCE_DEFECTS[key]
+            if container == "float32":   # exactly: the reference treats QI like IQ
+                as_iq = oracle.convert_samples(raw, api.CONTAINERS[container], bits, byte_order == "MSB", api.IQ_ORDERS["IQ"], n)
+                assert np.array_equal(got.view(np.uint32), as_iq.view(np.uint32))
+            if key == ("int8", "LSB", "Q_Only"):
+                assert np.all(got.real == 127.0) and np.allclose(got.imag, want.imag, rtol=2e-7)
+        elif container == "int8":
+            # v / 127: the reference is built with -ffast-math (CMakeLists.txt:76), gcc multiplies by the reciprocal: one ulp
+            d = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
+            assert d.max() <= 1
+        else:
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (key, bits)
 
 
 @pytest.mark.parametrize("container,byte_order,order", CASES)

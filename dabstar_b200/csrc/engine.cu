@@ -11,6 +11,7 @@
 #include "kernels.h"
 #include "tables.h"
 #include "hostpool.h"
+#include "fft2048.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -318,6 +319,12 @@ extern "C" int dabstar_create(dabstar_ctx ** out, int device, void * stream)
   ok = ok && cudaMalloc(&ctx->tab.bin_of_k, sizeof(int16_t) * K_CARR) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->tab.rel_of_k, sizeof(int16_t) * K_CARR) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->tab.prbs, PRBS_LEN) == cudaSuccess;
+  std::vector<uint16_t> slot_w(16 * FFT_THREADS), slot_r(K_CARR);
+  host_fft_epilogue_layout(bin_idx.data(), slot_w.data(), slot_r.data());
+  ok = ok && cudaMalloc(&ctx->tab.fft_slot_w, sizeof(uint16_t) * slot_w.size()) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->tab.fft_slot_r, sizeof(uint16_t) * slot_r.size()) == cudaSuccess;
+  ok = ok && cudaMemcpy(ctx->tab.fft_slot_w, slot_w.data(), sizeof(uint16_t) * slot_w.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+  ok = ok && cudaMemcpy(ctx->tab.fft_slot_r, slot_r.data(), sizeof(uint16_t) * slot_r.size(), cudaMemcpyHostToDevice) == cudaSuccess;
   ok = ok && cudaMemcpy(ctx->tab.w2048, w.data(), sizeof(float2) * T_U, cudaMemcpyHostToDevice) == cudaSuccess;
   ok = ok && cudaMemcpy(ctx->tab.prs, ctx->h_prs.data(), sizeof(float2) * T_U, cudaMemcpyHostToDevice) == cudaSuccess;
   ok = ok && cudaMemcpy(ctx->tab.bin_of_k, bin_idx.data(), sizeof(int16_t) * K_CARR, cudaMemcpyHostToDevice) == cudaSuccess;
@@ -336,7 +343,7 @@ extern "C" void dabstar_destroy(dabstar_ctx * ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaFree(ctx->tab.w2048); cudaFree(ctx->tab.prs); cudaFree(ctx->tab.ref_arg_conj);
-  cudaFree(ctx->tab.bin_of_k); cudaFree(ctx->tab.rel_of_k); cudaFree(ctx->tab.prbs);
+  cudaFree(ctx->tab.bin_of_k); cudaFree(ctx->tab.rel_of_k); cudaFree(ctx->tab.prbs); cudaFree(ctx->tab.fft_slot_w); cudaFree(ctx->tab.fft_slot_r);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

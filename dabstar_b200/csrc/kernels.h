@@ -15,6 +15,8 @@ struct DeviceTables
   float2 * ref_arg_conj; // coarse-AFC reference (phasereference.cpp:58-66), filled by init_ref_arg
   int16_t * bin_of_k;    // frequency interleaver: nominal carrier k -> fft index 0..2047
   int16_t * rel_of_k;    // realCarrRelIdx of carrier k (ofdm_decoder.cpp:169-180)
+  uint16_t * fft_slot_w; // k_fft_frames epilogue: staging slot of output i of thread tid, [16][128] (tables.cu: host_fft_epilogue_layout)
+  uint16_t * fft_slot_r; // ... and of nominal carrier k, [1536]
   uint8_t * prbs;        // energy dispersal sequence, PRBS_LEN bits (one per byte)
 };
 

@@ -217,37 +217,30 @@ __device__ __forceinline__ void convert_mix(float2 (&v)[16], const typename Raw<
 
 template <int FMT>
 __global__ void __launch_bounds__(FFT_THREADS, 5) k_fft_frames(const FrameDesc * __restrict__ frames, int n_items, const RecInput * __restrict__ recs,
-                                                               const float2 * __restrict__ w2048, const int16_t * __restrict__ bin_of_k,
-                                                               float2 * __restrict__ X)
+                                                               const float2 * __restrict__ w2048, const uint16_t * __restrict__ slot_w,
+                                                               const uint16_t * __restrict__ slot_r, float2 * __restrict__ X)
 {
   typedef typename Raw<FMT>::type T;
   extern __shared__ __align__(16) unsigned char fft_stage[]; // 2 x fft_stage_bytes<FMT>()
   __shared__ __align__(16) float2 smem[FFT_SMEM_F2];
   __shared__ float2 tw2s[FFT_TW2_F2];
   __shared__ float2 step[16];
-  __shared__ unsigned short pos[16 * FFT_THREADS]; // byte offset in `smem` of the nominal-carrier slot of output (h, j2) of every thread
+  __shared__ unsigned short pos[16 * FFT_THREADS]; // byte offset in `smem` of the staging slot of output i = 8 h + j2 of every thread
+  __shared__ unsigned rpos[K_CARR / 2];            // byte offsets of the slots of carriers 2p (low half) and 2p + 1 (high half)
   __shared__ __align__(8) unsigned long long mbar[2];
   const int tid = threadIdx.x;
   FftTwiddles tw;
   fft_load_twiddles(tw, w2048, tw2s, tid);
-  // Epilogue layout: after stage 3 a thread holds the bins fft_out_index(tid, h, j2); each is scattered straight to the slot of
-  // its nominal carrier k (frequency de-interleaving, freq_interleaver.cpp) in a [K_CARR] float2 array, so that the demapper's
-  // rows (carriers 2p, 2p + 1 as re, re, im, im) are one conflict-free 16-byte read per pair. Bins that carry no carrier (DC,
-  // guard band) go to a per-thread dump slot behind the array.
-  {
-    short * inv = reinterpret_cast<short *>(smem); // nominal carrier of every bin, -1: none (scratch, before the first transform)
-    for (int b = tid; b < T_U; b += FFT_THREADS) inv[b] = -1;
-    __syncthreads();
-    for (int k = tid; k < K_CARR; k += FFT_THREADS) inv[bin_of_k[k]] = (short)k;
-    __syncthreads();
+  // Epilogue layout (tables.cu, host_fft_epilogue_layout): after stage 3 a thread holds the bins fft_out_index(tid, h, j2); each
+  // goes straight to the staging slot of its nominal carrier (frequency de-interleaving, freq_interleaver.cpp), and a row of the
+  // demapper's layout (carriers 2p, 2p + 1 as re, re, im, im) is two 8-byte reads per pair. The slots are chosen so that the
+  // scatter stores AND the gather loads are free of bank conflicts; bins that carry no carrier (DC, guard band) go to slots
+  // nobody reads.
 #pragma unroll
-    for (int i = 0; i < 16; i++)
-    {
-      const int k = inv[fft_out_index(tid, i >> 3, i & 7)];
-      pos[i * FFT_THREADS + tid] = (unsigned short)((k >= 0 ? k : K_CARR + tid) * (int)sizeof(float2));
-    }
-  }
-  static_assert((K_CARR + FFT_THREADS) <= FFT_SMEM_F2, "nominal-order staging + dump slots must fit the transform buffer");
+  for (int i = 0; i < 16; i++) pos[i * FFT_THREADS + tid] = (unsigned short)(slot_w[i * FFT_THREADS + tid] * (int)sizeof(float2));
+  for (int p = tid; p < K_CARR / 2; p += FFT_THREADS)
+    rpos[p] = (unsigned)slot_r[2 * p] * (unsigned)sizeof(float2) | ((unsigned)slot_r[2 * p + 1] * (unsigned)sizeof(float2)) << 16;
+  static_assert(2048 <= FFT_SMEM_F2, "the staging slots (16 per write group) must fit the transform buffer");
   const unsigned stage0 = smem_addr_u32(fft_stage);
   const unsigned bar0 = smem_addr_u32(mbar);
   constexpr int SB = fft_stage_bytes<FMT>();
@@ -380,13 +373,13 @@ __global__ void __launch_bounds__(FFT_THREADS, 5) k_fft_frames(const FrameDesc *
       for (int i = 0; i < 16; i++) *reinterpret_cast<float2 *>(sbase + pos[i * FFT_THREADS + tid]) = v[i];
       __syncthreads();
       float4 * out = reinterpret_cast<float4 *>(X + cur.out);
-      const float4 * prs = reinterpret_cast<const float4 *>(smem);
 #pragma unroll
       for (int i = 0; i < K_CARR / 2 / FFT_THREADS; i++)
       {
         const int p = tid + FFT_THREADS * i;
-        const float4 ab = prs[p]; // (re 2p, im 2p, re 2p+1, im 2p+1)
-        out[p] = make_float4(ab.x, ab.z, ab.y, ab.w);
+        const unsigned rp = rpos[p];
+        const float2 a = *reinterpret_cast<const float2 *>(sbase + (rp & 0xffffu)), b = *reinterpret_cast<const float2 *>(sbase + (rp >> 16));
+        out[p] = make_float4(a.x, b.x, a.y, b.y);
       }
     }
     __syncthreads(); // smem and the stage buffer of this symbol are free again
@@ -987,6 +980,8 @@ __global__ void __launch_bounds__(DM5_T, 4) k_demap5(const DemapWork * __restric
 
   const int total_rows = wk.n_frames * X_ROWS;
   const float4 * rows = reinterpret_cast<const float4 *>(X + (size_t)(total_rows > 0 ? frames[wk.desc_first].xslot : 0) * X_ROWS * K_CARR) + 2 * t_rec;
+  // (the two 16-byte halves of a thread's row / stash entry are interleaved at a 32-byte stride: twice the ideal wavefronts; separate
+  // planes of contiguous 16-byte accesses were measured, 5.76 instead of 5.56 ms)
   const unsigned rowbuf_addr = smem_addr_u32(rowbuf + 2 * tid);
 #pragma unroll
   for (int i = 0; i < DM5_PF; i++)
@@ -1473,7 +1468,7 @@ cudaError_t launch_fft_frames(cudaStream_t s, const DeviceTables & t, const Fram
     int per_sm = lp.err == cudaSuccess && lp.ctas_per_sm > 0 ? lp.ctas_per_sm : 4;
     if (max_ctas_per_sm > 0) per_sm = std::min(per_sm, max_ctas_per_sm);
     if (const char * ev = getenv("DABSTAR_FFT_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(ev))); // A/B switch: resident CTAs per SM
-    k_fft_frames<FMT><<<std::min(n_items, lp.n_sm * per_sm), FFT_THREADS, stage, s>>>(frames, n_items, recs, t.w2048, t.bin_of_k, X);
+    k_fft_frames<FMT><<<std::min(n_items, lp.n_sm * per_sm), FFT_THREADS, stage, s>>>(frames, n_items, recs, t.w2048, t.fft_slot_w, t.fft_slot_r, X);
   });
 }
 

@@ -4,6 +4,8 @@
 // (protection/protTables.cpp:36-62), UEP profiles (protection/uep_protection.cpp:52-132), energy-dispersal PRBS
 // (decoder/fic_decoder.cpp:59-73).
 #include "tables.h"
+#include "fft2048.cuh"
+#include <vector>
 
 #include <cmath>
 #include <cstring>
@@ -60,6 +62,80 @@ void host_freq_interleaver(int16_t * bin_signed)
     if (v == T_U / 2 || v < 256 || v > 256 + K_CARR) continue;
     bin_signed[n++] = (int16_t)(v - T_U / 2);
   }
+}
+
+// Staging layout of the FFT kernel's epilogue. After the last stage thread tid holds the bins fft_out_index(tid, h, j2) as its
+// values i = 8 h + j2; the frequency de-interleaver (a pseudo-random permutation, freq_interleaver.cpp:37-60) sends them to
+// nominal carriers; the demapper's rows want carriers 2p, 2p + 1 next to each other. The values pass through shared memory once:
+// written with STS.64 (16 per thread: value i of the 32 lanes of a warp at a time), read with LDS.64 (carrier 2p + b of 32
+// consecutive p at a time). A 64-bit access is served per HALF warp, 16 lanes on 16 pairs of banks, so an instruction is
+// conflict free when the 16 slots of each half warp differ modulo 16. Every carrier sits in exactly one write group (warp,
+// half, i) and one read group (iteration, b, warp, half), groups hold at most 16 carriers: the carriers are the edges of a
+// bipartite multigraph of maximum degree 16, which has a proper edge colouring with 16 colours (Koenig); colour = slot modulo
+// 16, slot = 16 * write group + colour. Written with the pseudo-random slots of the straightforward layout (slot = carrier) a
+// scatter store took 6.5 wavefronts instead of 2 (ncu, profiles/r2_m_*), a third of the kernel's shared-memory traffic.
+void host_fft_epilogue_layout(const int16_t * bin_of_k, uint16_t * slot_w, uint16_t * slot_r)
+{
+  constexpr int NW = 128, NR = 96, D = 16;
+  std::vector<int> carrier_of_bin(T_U, -1);
+  for (int k = 0; k < K_CARR; k++) carrier_of_bin[bin_of_k[k]] = k;
+  // edges
+  std::vector<int> wg(K_CARR, -1), rg(K_CARR, -1);
+  for (int i = 0; i < 16; i++)
+    for (int tid = 0; tid < FFT_THREADS; tid++)
+    {
+      const int c = carrier_of_bin[fft_out_index(tid, i >> 3, i & 7)];
+      if (c >= 0) wg[c] = (i * 4 + (tid >> 5)) * 2 + ((tid >> 4) & 1);
+    }
+  for (int c = 0; c < K_CARR; c++)
+  {
+    const int p = c >> 1, b = c & 1, it = p / FFT_THREADS, tid = p % FFT_THREADS;
+    rg[c] = ((it * 2 + b) * 4 + (tid >> 5)) * 2 + ((tid >> 4) & 1);
+  }
+  // bipartite edge colouring with D colours: at[side][vertex][colour] = edge using that colour at the vertex, or -1
+  std::vector<int> at_w(NW * D, -1), at_r(NR * D, -1), colour(K_CARR, -1);
+  for (int e = 0; e < K_CARR; e++)
+  {
+    const int u = wg[e], v = rg[e];
+    int a = 0, b = 0;
+    while (at_w[u * D + a] >= 0) a++; // free at u
+    while (at_r[v * D + b] >= 0) b++; // free at v
+    if (a != b)
+    {
+      // colour a is taken at v: flip the a / b alternating path that starts there (it cannot reach u, where a is free and the
+      // path would have to arrive through an a edge)
+      std::vector<int> path;
+      int x = v, side = 1, want = a; // at a right vertex looking for its `a` edge
+      while (true)
+      {
+        const int f = side ? at_r[x * D + want] : at_w[x * D + want];
+        if (f < 0) break;
+        path.push_back(f);
+        x = side ? wg[f] : rg[f];
+        side ^= 1;
+        want = want == a ? b : a;
+      }
+      for (int f : path) { at_w[wg[f] * D + colour[f]] = -1; at_r[rg[f] * D + colour[f]] = -1; }
+      for (int f : path) { colour[f] = colour[f] == a ? b : a; }
+      for (int f : path) { at_w[wg[f] * D + colour[f]] = f; at_r[rg[f] * D + colour[f]] = f; }
+    }
+    colour[e] = a;
+    at_w[u * D + a] = e;
+    at_r[v * D + a] = e;
+  }
+  for (int c = 0; c < K_CARR; c++) slot_r[c] = (uint16_t)(wg[c] * D + colour[c]);
+  // the writers: carriers go to their slots, values of bins without a carrier to the colours their write group has left
+  for (int i = 0; i < 16; i++)
+    for (int tid = 0; tid < FFT_THREADS; tid++)
+    {
+      const int g = (i * 4 + (tid >> 5)) * 2 + ((tid >> 4) & 1);
+      const int c = carrier_of_bin[fft_out_index(tid, i >> 3, i & 7)];
+      if (c >= 0) { slot_w[i * FFT_THREADS + tid] = slot_r[c]; continue; }
+      int a = 0;
+      while (at_w[g * D + a] >= 0) a++;
+      at_w[g * D + a] = K_CARR; // taken by a value nobody reads
+      slot_w[i * FFT_THREADS + tid] = (uint16_t)(g * D + a);
+    }
 }
 
 void host_phase_table(float2 * prs)

@@ -14,9 +14,12 @@
 #include "fft2048.cuh"
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <chrono>
+#include <climits>
 #include <cmath>
+#include <cstdint>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -1411,25 +1414,34 @@ void ctl_after_coarse(Recording & r, bool ran_coarse, int correction, FrameCtl &
   fc.info.clock_err = r.clock_err;
 }
 
-void ctl_finish_frame(Recording & r, float2 cp_raw, bool ran_coarse, int correction, FrameCtl & fc)
+// Phase of the cyclic-prefix sum after the derotation by the integer frequency f (dab_processor.cpp:326-333; the kernel sums the
+// RAW samples, the derotated sum differs by the constant factor e^{-j 2 pi f / 1000}): the one expensive, state-independent part
+// of the per-frame recurrence once f is known.
+float cp_phase(float2 cp_raw, int f)
+{
+  // (the integer frequency changes rarely: a small direct-mapped cache of the two trigonometric values, same expressions)
+  struct Rot { int f; bool set; double c, s; };
+  static thread_local Rot rot_cache[64] = {};
+  Rot & rc = rot_cache[(unsigned)f & 63u];
+  if (!rc.set || rc.f != f)
+  {
+    const double ang = -2.0 * M_PI * (double)f / 1000.0;
+    rc = Rot{ f, true, cos(ang), sin(ang) };
+  }
+  const double cr = rc.c, sr = rc.s;
+  const float re = (float)((double)cp_raw.x * cr - (double)cp_raw.y * sr), im = (float)((double)cp_raw.x * sr + (double)cp_raw.y * cr);
+  return atan2f(im, re);
+}
+
+// spec_f / spec_ph: cp_phase(cp_raw, spec_f) computed ahead (by the pool, for the integer frequency the window started with);
+// used when the frame's frequency turns out to be that one
+void ctl_finish_frame(Recording & r, float2 cp_raw, bool ran_coarse, int correction, FrameCtl & fc, int spec_f = INT32_MIN, float spec_ph = 0.0f)
 {
   const int n_syms = fc.desc.n_syms;
   r.osc_phase = mod_fs_host((long long)r.osc_phase - (long long)fc.desc.f_data * ((long long)n_syms * T_S));
   r.pos += (long long)n_syms * T_S;
   if (n_syms < 75) return; // recording ends inside this frame
-  // the reference sums the derotated samples: raw sum times e^{-j 2 pi f / 1000}
-  // (the integer frequency changes rarely: a small direct-mapped cache of the two trigonometric values, same expressions)
-  struct Rot { int f; bool set; double c, s; };
-  static thread_local Rot rot_cache[64] = {};
-  Rot & rc = rot_cache[(unsigned)fc.desc.f_data & 63u];
-  if (!rc.set || rc.f != fc.desc.f_data)
-  {
-    const double ang = -2.0 * M_PI * (double)fc.desc.f_data / 1000.0;
-    rc = Rot{ fc.desc.f_data, true, cos(ang), sin(ang) };
-  }
-  const double cr = rc.c, sr = rc.s;
-  const float re = (float)((double)cp_raw.x * cr - (double)cp_raw.y * sr), im = (float)((double)cp_raw.x * sr + (double)cp_raw.y * cr);
-  float ph = atan2f(im, re);
+  float ph = fc.desc.f_data == spec_f ? spec_ph : cp_phase(cp_raw, fc.desc.f_data);
   const float lim = 20.0f * RAD_PER_DEG_F;
   ph = ph > lim ? lim : (ph < -lim ? -lim : ph);
   r.phase_cp = ph;
@@ -1850,15 +1862,20 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
         window_end = std::max(window_end, p);
       }
       ctl.resize((size_t)n_laid);
-      pool.parallel_for((int)plans.size(), [&](int pi) {
-        Plan & pl = plans[(size_t)pi];
-        if (!pl.open) return;
+      // (plan, first frame, end frame) pieces of at most 1024 frames: one long recording is a single plan, the pool works on pieces
+      std::vector<std::array<int, 3>> pieces;
+      for (size_t pi = 0; pi < plans.size(); pi++)
+        if (plans[pi].open)
+          for (int j0 = 0; j0 < plans[pi].t_frames; j0 += 1024) pieces.push_back({ (int)pi, j0, std::min(plans[pi].t_frames, j0 + 1024) });
+      pool.parallel_for((int)pieces.size(), [&](int k) {
+        Plan & pl = plans[(size_t)pieces[(size_t)k][0]];
         const Recording & R = dec->recs[pl.rec];
         const int s0 = pl.next_start >= 0 ? pl.next_start : T_G;
-        long long p = R.pos;
-        for (int j = 0; j < pl.t_frames; j++)
+        for (int j = pieces[(size_t)k][1]; j < pieces[(size_t)k][2]; j++)
         {
           const int s = j == 0 ? s0 : T_G;
+          // frame 0 starts at R.pos; frame j > 0 behind frame 0 (peak s0) and j - 1 frames with the peak at T_g
+          const long long p = j == 0 ? R.pos : R.pos + (T_U + s0 + 75LL * T_S + T_N) + (long long)(j - 1) * (T_U + T_G + 75LL * T_S + T_N);
           FrameCtl & fc = ctl[(size_t)(pl.t_first + j)];
           memset(&fc.desc, 0, sizeof(fc.desc));
           fc.desc.rec = pl.rec;
@@ -1867,7 +1884,6 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
           fc.desc.n_syms = j == pl.t_frames - 1 ? pl.t_last_syms : 75;
           fc.desc.slot = (int)(R.slot_base + R.n_slots + (int)pl.fr.size() + j);
           fc.desc.xslot = pl.t_first + j;
-          p += T_U + s + 75LL * T_S + T_N;
         }
       });
       const int n_tail = (int)ctl.size();
@@ -1935,6 +1951,26 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       // scalar recurrences (dab_processor.cpp:205-251), with the control state after every frame
       std::vector<CtlSnapshot> after((size_t)n_tail), before_tail(plans.size());
       std::vector<uint8_t> first_flags((size_t)n_tail, 0);
+      // The recurrence of a recording is serial over its frames, but its one expensive step (atan2f of the rotated CP sum) depends
+      // on the state only through the INTEGER frequency, which moves rarely: the pool computes the phases of all tail frames for
+      // the frequency each plan starts with, the serial pass takes them where the frequency still is that one. (One long
+      // recording has a single plan: without this the pass ran 1.0 ms per 9984 frames on one thread.)
+      std::vector<float> spec_ph((size_t)n_tail);
+      std::vector<int> spec_f(plans.size(), INT32_MIN);
+      std::vector<int> plan_of((size_t)n_tail, -1);
+      for (size_t pi = 0; pi < plans.size(); pi++)
+      {
+        if (!plans[pi].open) continue;
+        spec_f[pi] = (int)roundf(dec->recs[plans[pi].rec].f_bb);
+        for (int j = 0; j < plans[pi].t_frames; j++) plan_of[(size_t)(plans[pi].t_first + j)] = (int)pi;
+      }
+      {
+        const int parts = std::max(1, std::min(n_tail / 256, 4 * (pool.workers() + 1)));
+        pool.parallel_for(parts, [&](int k) {
+          for (int i = (int)((long long)n_tail * k / parts); i < (int)((long long)n_tail * (k + 1) / parts); i++)
+            if (plan_of[(size_t)i] >= 0) spec_ph[(size_t)i] = cp_phase(cp[i], spec_f[(size_t)plan_of[(size_t)i]]);
+        });
+      }
       auto recur_plan = [&](size_t pi) {
         Plan & pl = plans[pi];
         if (!pl.open) return;
@@ -1950,7 +1986,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
           ctl_begin_frame(R, j == 0 ? s0 : T_G, n_syms, fc);
           const bool ran_coarse = pl.fr.empty() && (j == 0) && (R.fic_ratio * 10 < 30);
           ctl_after_coarse(R, ran_coarse, coarse[i], fc);
-          ctl_finish_frame(R, cp[i], ran_coarse, coarse[i], fc);
+          ctl_finish_frame(R, cp[i], ran_coarse, coarse[i], fc, spec_f[pi], spec_ph[(size_t)i]);
           fc.desc.rec = pl.rec;
           fc.desc.slot = slot;
           fc.desc.xslot = i;
@@ -2044,17 +2080,22 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
     CK(dec->d_desc.reserve(sizeof(FrameDesc) * (size_t)n_desc + 64));
     unsigned char * desc_stage = nullptr;
     if (int r_ = upload_begin(ctx, sizeof(FrameDesc) * (size_t)n_desc, &desc_stage)) return r_;
-    pool.parallel_for((int)plans.size(), [&](int pi) {
-      Plan & pl = plans[(size_t)pi];
-      const int base = dec->recs[pl.rec].w_first_desc;
-      FrameDesc * o = reinterpret_cast<FrameDesc *>(desc_stage);
-      for (int j = 0; j < (int)pl.fr.size(); j++)
-      {
-        pl.fr[(size_t)j].desc.xslot = base + j;
-        ctl[(size_t)(base + j)] = pl.fr[(size_t)j];
-        o[base + j] = pl.fr[(size_t)j].desc;
-      }
-    });
+    {
+      std::vector<std::array<int, 3>> pieces;
+      for (size_t pi = 0; pi < plans.size(); pi++)
+        for (int j0 = 0; j0 < (int)plans[pi].fr.size(); j0 += 1024) pieces.push_back({ (int)pi, j0, std::min((int)plans[pi].fr.size(), j0 + 1024) });
+      pool.parallel_for((int)pieces.size(), [&](int k) {
+        Plan & pl = plans[(size_t)pieces[(size_t)k][0]];
+        const int base = dec->recs[pl.rec].w_first_desc;
+        FrameDesc * o = reinterpret_cast<FrameDesc *>(desc_stage);
+        for (int j = pieces[(size_t)k][1]; j < pieces[(size_t)k][2]; j++)
+        {
+          pl.fr[(size_t)j].desc.xslot = base + j;
+          ctl[(size_t)(base + j)] = pl.fr[(size_t)j];
+          o[base + j] = pl.fr[(size_t)j].desc;
+        }
+      });
+    }
     if (trace)
       fprintf(stderr, "[dabstar] round %lld t=%.3f ms: %zu recordings, %d frames, chunks resident %d/%d waited %d\n", dec->cnt_rounds,
               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_run0).count(), plans.size(), n_desc, dec->chunks_done, dec->n_chunks,

@@ -430,7 +430,13 @@ def single_stream_workload(T, ctx, args, rank, world, uniq_dev):
 
     dev = piece(sh.in_lo, sh.in_hi)
     dp = api.DabProcessor(1, input_format=api.FMT_U8, scan_mode=True, max_window=args.stream_window, ctx=ctx)
-    dp.set_segmentation(args.stream_segment_frames, args.segment_warmup)
+    # segments per window: about 96 (288 demapper CTAs fill the 148 SMs twice); a rank whose share is shorter than a full
+    # window takes shorter segments (more warm-up frames per decoded frame, reported as redundant) instead of leaving SMs empty
+    seg_frames = args.stream_segment_frames
+    if seg_frames <= 0:
+        share = min(args.stream_window, (tiles * F + world - 1) // world)
+        seg_frames = max(32, min(104, (share + 95) // 96))
+    dp.set_segmentation(seg_frames, args.segment_warmup)
     ptrs, ns = [dev.data_ptr()], [dev.shape[0]]
     ms, stages, _ = T.run(dp, ptrs, ns, args.extra_steps)
     first, last = parallel.owned_frames(dp.frame_positions(0), sh)
@@ -443,7 +449,7 @@ def single_stream_workload(T, ctx, args, rank, world, uniq_dev):
     out = {"workload": f"one {tiles * F}-frame recording ({tiles * F * 0.096 / 60:.0f} min), FIC only, decoded as frame batches with a warm-up prefix",
            "scaling": "strong", "frames": owned, "frames_expected": tiles * F, "steps": args.extra_steps, "ms_per_step": ms, "frames_per_s": owned / ms * 1e3,
            "x_real_time": owned / ms * 1e3 / (2048000 / T_F),
-           "segment_frames": args.stream_segment_frames, "segment_warmup_frames": args.segment_warmup, "window": args.stream_window,
+           "segment_frames": seg_frames, "segment_warmup_frames": args.segment_warmup, "window": args.stream_window,
            "redundant_frames": redundant, "redundant_fraction": redundant / max(1.0, owned),
            "fib_crc_pass_incl_lead_in": good / max(1.0, 12.0 * dec_all),
            "rank0": {"samples": int(dev.shape[0]), "frames_decoded": int(decoded), "frames_owned": int(last - first), "segment_warmup_frames_demapped": int(warm),
@@ -707,7 +713,7 @@ def main():
     ap.add_argument("--segment-warmup", type=int, default=18)
     ap.add_argument("--stream-frames", type=int, default=37440, help="single_stream: frames of the one long recording (1 h)")
     ap.add_argument("--stream-window", type=int, default=9984)
-    ap.add_argument("--stream-segment-frames", type=int, default=104)
+    ap.add_argument("--stream-segment-frames", type=int, default=0, help="single_stream: frames per demapper segment (0 = about 96 segments per window, 32..104 frames)")
     ap.add_argument("--snr-cfo-frames", type=int, default=13)
     ap.add_argument("--cpu-worker", action="store_true")
     ap.add_argument("--cpu-lib", default="dabo")

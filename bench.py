@@ -451,7 +451,7 @@ def single_stream_workload(T, ctx, args, rank, world, uniq_dev):
            "x_real_time": owned / ms * 1e3 / (2048000 / T_F),
            "segment_frames": seg_frames, "segment_warmup_frames": args.segment_warmup, "window": args.stream_window,
            "redundant_frames": redundant, "redundant_fraction": redundant / max(1.0, owned),
-           "fib_crc_pass_incl_lead_in": good / max(1.0, 12.0 * dec_all),
+           "fib_crc_pass_incl_lead_in": min(1.0, good / max(1.0, 12.0 * dec_all)),   # (FIBs of a trailing incomplete frame count as good, not as a frame)
            "rank0": {"samples": int(dev.shape[0]), "frames_decoded": int(decoded), "frames_owned": int(last - first), "segment_warmup_frames_demapped": int(warm),
                      "windows_run": int(cnt[4]), "windows_cut_by_verification": int(cnt[5])},
            "stages_ms": stages,

@@ -318,6 +318,164 @@ __global__ void __launch_bounds__(256) k_vit_gather(const VitJob * __restrict__ 
   }
 }
 
+// Second form of the gather (the default): the kept soft bits of a code word are consecutive in the source, only the trellis
+// steps they belong to are irregular. So each warp first copies the kept bits of its code word's 128 steps into shared
+// memory as clamped bytes — lane L takes kept bits 4L..4L+3 (mod 128) from the 128-aligned start, which fixes the four
+// de-interleave delay rows of a lane for the whole code word: four pointer fetches per code word instead of one per bit,
+// loads at constant offsets, no work for punctured positions — and then builds each step's word from the four bytes at
+// the step's first kept bit (two shared-memory words and a funnel shift) with one PRMT whose selector puts 127 (erasure)
+// into the punctured positions. Same words as k_vit_gather, bit for bit (tests/test_gpu_viterbi.py runs both).
+constexpr int GK_WORDS = (4 * GATHER_STEPS + 128) / 4 + 1; // kept bytes of a tile from the aligned start, + the funnel shift's second word
+constexpr int GK_ITERS = (4 * GATHER_STEPS + 128) / 128;
+
+// soft bit at p if k < lim; unspecified otherwise (such bytes are never selected)
+__device__ __forceinline__ int ld_soft_lt(const int16_t * p, int k, int lim)
+{
+  int v;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.s32 q, %2, %3;\n\t@q ld.global.nc.s16 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"(k), "r"(lim));
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_vit_gather_kb(const VitJob * __restrict__ jobs, const FrameDesc * __restrict__ fic_frames, int job_first, int n_jobs,
+                                                       const VitProfile * __restrict__ profiles, const unsigned * __restrict__ step_tab,
+                                                       const int16_t * __restrict__ soft, unsigned * __restrict__ sym, int stride, int rows)
+{
+  constexpr int H = GATHER_STEPS / 32;
+  __shared__ unsigned tile[32][GATHER_STEPS + 1];
+  __shared__ const int16_t * rowptr[32][17];
+  __shared__ int sh_steps[32], sh_tab[32], sh_ka[32], sh_k1[32];
+  __shared__ unsigned kb[8][GK_WORDS];
+  __shared__ unsigned sel_lut[16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int jb = blockIdx.x * 32, t0 = blockIdx.y * GATHER_STEPS;
+
+  {
+    VitJob job;
+    const bool valid = jb + lane < n_jobs && load_job(jobs, fic_frames, job_first + jb + lane, job);
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+    {
+      const int m = 2 * warp + q;
+      const int16_t * p = g_zero_row;
+      if (valid)
+      {
+        if (job.src_mode == VIT_SRC_LINEAR) p = soft + job.src;
+        else if ((job.row_mask >> m) & 1) p = soft + job.src + cif_offset(vit_row_cif(job.cif_first, job.skip_plus1, m)) + job.frag_off;
+      }
+      rowptr[lane][m] = p;
+    }
+    if (warp == 0)
+    {
+      const VitProfile * pr = profiles + (valid ? job.profile : 0);
+      const int steps = valid ? pr->n_bits + 6 : 0;
+      const unsigned * tab = step_tab + pr->tab_off;
+      int k0 = 0, k1 = 0; // kept bits [k0, k1) belong to the tile's steps
+      if (t0 < steps)
+      {
+        k0 = (int)(tab[t0] & 0x0fffffffu);
+        k1 = t0 + GATHER_STEPS < steps ? (int)(tab[t0 + GATHER_STEPS] & 0x0fffffffu) : pr->n_kept;
+      }
+      sh_steps[lane] = steps;
+      sh_tab[lane] = pr->tab_off;
+      sh_ka[lane] = k0 & ~127;
+      sh_k1[lane] = k1;
+    }
+    if (threadIdx.x < 16)
+    {
+      // PRMT selector of a keep mask: the n-th kept position takes byte n of the four kept bytes, a punctured one byte 4 (= 127)
+      unsigned s = 0, n = 0;
+#pragma unroll
+      for (int g = 0; g < 4; g++) s |= (((threadIdx.x >> g) & 1) ? n++ : 4u) << (4 * g);
+      sel_lut[threadIdx.x] = s;
+    }
+  }
+  __syncthreads();
+
+  unsigned * kbw = kb[warp];
+  // What depends only on the code word's profile and the tile is kept across the warp's code words (the jobs of a launch are
+  // ordered by sub-channel: a CTA of mixed profiles is the exception): the kept-bit range, and per step the position of
+  // its four bytes in kbw, the funnel-shift count and the PRMT selector.
+  int cur_tab = -1, cur_steps = -1, ka = 0, span = 0, kl = 0, rem = 0;
+  unsigned kpos[H], kshift[H], ksel[H];
+  int ridx[4];
+#pragma unroll
+  for (int g = 0; g < 4; g++) ridx[g] = (int)(__brev((unsigned)(4 * lane + g)) >> 28); // time_map: 4-bit reversal of k & 15
+#pragma unroll 1
+  for (int c = 0; c < 4; c++)
+  {
+    const int jr = 4 * warp + c;
+    if (sh_tab[jr] != cur_tab || sh_steps[jr] != cur_steps)
+    {
+      cur_tab = sh_tab[jr];
+      cur_steps = sh_steps[jr];
+      ka = sh_ka[jr];
+      span = sh_k1[jr] - ka;  // kept bits from the aligned start to the end of the tile
+      kl = ka + 4 * lane;
+      rem = span - 4 * lane;  // the lane's bit 128 i + g exists if 128 i + g < rem
+      const unsigned * tab = step_tab + cur_tab;
+#pragma unroll
+      for (int h = 0; h < H; h++)
+      {
+        const int t = t0 + lane + 32 * h;
+        const unsigned w = tab[max(min(t, cur_steps - 1), 0)];
+        const unsigned e = t < cur_steps ? w : (unsigned)ka; // no step: nothing kept, four erasures
+        const int rel = (int)(e & 0x0fffffffu) - ka;
+        kpos[h] = (unsigned)(rel >> 2);
+        kshift[h] = (unsigned)rel << 3;
+        ksel[h] = sel_lut[e >> 28];
+      }
+    }
+    // ---- kept bits -> clamped bytes; every load of the code word is issued before the first is used
+    {
+      const int16_t * p[4];
+#pragma unroll
+      for (int g = 0; g < 4; g++) p[g] = rowptr[jr][ridx[g]] + kl + g;
+      int a[GK_ITERS][4];
+#pragma unroll
+      for (int i = 0; i < GK_ITERS; i++)
+      {
+        if (128 * i < span)
+        {
+#pragma unroll
+          for (int g = 0; g < 4; g++) a[i][g] = ld_soft_lt(p[g] + 128 * i, 128 * i + g, rem);
+        }
+      }
+      asm volatile("" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < GK_ITERS; i++)
+      {
+        if (128 * i < span)
+        {
+          // viterbi_scalar.h:34-40: in + 127 wraps in 16 bits before the clamp to 0..255 (the 16-bit halves taken by the PRMT)
+          unsigned lo = __byte_perm((unsigned)(a[i][0] + 127), (unsigned)(a[i][1] + 127), 0x5410);
+          unsigned hi = __byte_perm((unsigned)(a[i][2] + 127), (unsigned)(a[i][3] + 127), 0x5410);
+          lo = __vmins2(__vmaxs2(lo, 0u), 0x00ff00ffu);
+          hi = __vmins2(__vmaxs2(hi, 0u), 0x00ff00ffu);
+          kbw[32 * i + lane] = __byte_perm(lo, hi, 0x6420);
+        }
+      }
+    }
+    __syncwarp();
+    // ---- the four symbols of each step
+#pragma unroll
+    for (int h = 0; h < H; h++)
+    {
+      const unsigned v = __funnelshift_r(kbw[kpos[h]], kbw[kpos[h] + 1], kshift[h]);
+      tile[jr][lane + 32 * h] = __byte_perm(v, 0x7f7f7f7fu, ksel[h]);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  unsigned * dst = sym + (size_t)(t0 + warp) * stride + jb + lane;
+  const unsigned * src = &tile[lane][warp];
+#pragma unroll
+  for (int q = 0; q < GATHER_STEPS / 8; q++)
+  {
+    if (t0 + warp + 8 * q < rows) *dst = src[8 * q];
+    dst += (size_t)8 * stride;
+  }
+}
+
 __global__ void __launch_bounds__(32) k_vit_tpc(const VitJob * __restrict__ jobs, const FrameDesc * __restrict__ fic_frames, int job_first, int n_jobs,
                                                 const VitProfile * __restrict__ profiles, const unsigned * __restrict__ sym,
                                                 unsigned long long * __restrict__ surv, int stride, uint8_t * __restrict__ out_bits,
@@ -334,30 +492,37 @@ __global__ void __launch_bounds__(32) k_vit_tpc(const VitJob * __restrict__ jobs
   const unsigned * sp = sym + jl;
   unsigned long long * vp = surv + jl;
 
-  // ---- forward pass, five steps per iteration; the symbols of the next TWO iterations are in flight meanwhile
-  // (rows are padded to a multiple of 5, loads beyond the code word are clamped to its last block of rows)
+  // ---- forward pass, five steps per iteration; the symbols of the next TWO iterations are in flight meanwhile: the
+  // symbol rows are followed by TPC_READ_AHEAD rows that are read and never used, and the decision rows are padded to a
+  // multiple of 5, so neither the loads nor the stores of an iteration need a bound (launch_viterbi lays the workspace out)
   unsigned S[32];
   tpc_init(S);
-  const int last0 = (steps - 1) / 5 * 5;
+  const size_t row = (size_t)(unsigned)stride;
   unsigned cur[5], nx1[5];
 #pragma unroll
-  for (int i = 0; i < 5; i++) { cur[i] = sp[(size_t)i * stride]; nx1[i] = sp[(size_t)(min(5, last0) + i) * stride]; }
+  for (int i = 0; i < 5; i++) { cur[i] = sp[i * row]; nx1[i] = sp[(5 + i) * row]; }
+  const unsigned * pn = sp + 10 * row;
+  unsigned long long * pv = vp;
+  int to_renorm = TPC_RENORM / 5;
 #pragma unroll 1
   for (int t0 = 0; t0 < steps; t0 += 5)
   {
     unsigned nx2[5];
-    const int tn = min(t0 + 10, last0);
 #pragma unroll
-    for (int i = 0; i < 5; i++) nx2[i] = sp[(size_t)(tn + i) * stride];
+    for (int i = 0; i < 5; i++) nx2[i] = pn[i * row];
+    pn += 5 * row;
     unsigned long long dec[5];
-    tpc_five_steps(S, cur, dec, (t0 + 5) % TPC_RENORM == 0);
+    const bool renorm = --to_renorm == 0;
+    if (renorm) to_renorm = TPC_RENORM / 5;
+    tpc_five_steps(S, cur, dec, renorm);
 #pragma unroll
     for (int i = 0; i < 5; i++)
     {
-      if (t0 + i < steps) vp[(size_t)(t0 + i) * stride] = dec[i];
+      pv[i * row] = dec[i];
       cur[i] = nx1[i];
       nx1[i] = nx2[i];
     }
+    pv += 5 * row;
   }
 
   // ---- chain back from state 0; decoded bit i is the decision read at step i + 6 (viterbi_scalar.h:84-93).
@@ -582,10 +747,12 @@ int viterbi_smem_bytes(int max_steps, int warps)
 // Workspace of the thread-per-code-word path for one launch of n_jobs code words of at most max_steps trellis steps:
 // symbols u32[rows][stride] + decision words u64[rows][stride], rows = max_steps rounded up to 5, stride = jobs rounded up to 32.
 static inline int tpc_rows(int max_steps) { return (max_steps + 4) / 5 * 5; }
+constexpr int TPC_READ_AHEAD = 10; // symbol rows k_vit_tpc reads beyond the last block of five
+static inline size_t tpc_bytes_per_job(int rows) { return (size_t)(rows + TPC_READ_AHEAD) * 4 + (size_t)rows * 8; }
 size_t viterbi_ws_bytes(int n_jobs, int max_steps)
 {
   const size_t stride = ((size_t)n_jobs + 31) & ~(size_t)31;
-  return (size_t)tpc_rows(max_steps) * stride * 12 + 256;
+  return tpc_bytes_per_job(tpc_rows(max_steps)) * stride + 256;
 }
 
 static cudaError_t launch_viterbi_warp(cudaStream_t stream, const VitJob * jobs, const FrameDesc * fic_frames, int n_jobs, const VitProfile * profiles, int max_steps,
@@ -619,7 +786,7 @@ cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, const Frame
 {
   if (n_jobs <= 0) return cudaSuccess;
   const int rows = tpc_rows(max_steps);
-  const size_t per_job = (size_t)rows * 12;
+  const size_t per_job = tpc_bytes_per_job(rows);
   size_t fit = ws != nullptr && ws_bytes > 256 ? (ws_bytes - 256) / per_job : 0;
   fit &= ~(size_t)31;
   // DABSTAR_VITERBI_TPC_MIN overrides the batch size from which the thread-per-code-word path is taken (read per launch
@@ -634,18 +801,19 @@ cudaError_t launch_viterbi(cudaStream_t stream, const VitJob * jobs, const Frame
     return e;
   }
   const int chunk = (int)min((size_t)((n_jobs + 31) & ~31), fit);
-  // DABSTAR_GATHER_BATCH = 1 or 2 code words per warp in flight at a time (A/B measurements)
-  int gather_batch = 2;
+  // DABSTAR_GATHER_BATCH = 1 or 2: the first form of the gather with that many code words per warp in flight (A/B measurements)
+  int gather_batch = 0;
   if (const char * ev = getenv("DABSTAR_GATHER_BATCH")) gather_batch = atoi(ev);
   unsigned * sym = static_cast<unsigned *>(ws);
-  unsigned long long * surv = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(ws) + (((size_t)rows * chunk * 4 + 255) & ~(size_t)255));
+  unsigned long long * surv = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(ws) + (((size_t)(rows + TPC_READ_AHEAD) * chunk * 4 + 255) & ~(size_t)255));
   for (int first = 0; first < n_jobs; first += chunk)
   {
     const int n = min(chunk, n_jobs - first);
     const int groups = (n + 31) / 32;
     const dim3 ggrid((unsigned)groups, (unsigned)((rows + GATHER_STEPS - 1) / GATHER_STEPS));
     if (hook) hook->mark(hook->user, 0, stream);
-    if (gather_batch >= 2) k_vit_gather<2><<<ggrid, 256, 0, stream>>>(jobs, fic_frames, first, n, profiles, step_tab, soft, sym, chunk, rows);
+    if (gather_batch <= 0) k_vit_gather_kb<<<ggrid, 256, 0, stream>>>(jobs, fic_frames, first, n, profiles, step_tab, soft, sym, chunk, rows);
+    else if (gather_batch >= 2) k_vit_gather<2><<<ggrid, 256, 0, stream>>>(jobs, fic_frames, first, n, profiles, step_tab, soft, sym, chunk, rows);
     else k_vit_gather<1><<<ggrid, 256, 0, stream>>>(jobs, fic_frames, first, n, profiles, step_tab, soft, sym, chunk, rows);
     if (hook) hook->mark(hook->user, 1, stream);
     k_vit_tpc<<<groups, 32, 0, stream>>>(jobs, fic_frames, first, n, profiles, sym, surv, chunk, out_bits, prbs);

@@ -5,9 +5,11 @@
 // state 0), organised for the integer pipes of sm_100a instead of for one warp:
 //
 //   * the 64 path metrics of a code word live in 32 registers as unsigned 16-bit PAIRS. One VIMNMX.U16x2 (the packed
-//     integer min of sm_90+) selects the survivors of two states, one 32-bit add advances two metrics, and the two
-//     decisions are the sign bits of the packed difference m0 - m1 + 0x7fff: one PRMT in sign-replicate mode gathers
-//     the four decisions of a packed butterfly, one LOP3 files them in the decision word. A warp therefore advances 32
+//     integer add-and-min of sm_100) advances one path and selects the survivors of two states, one 32-bit add advances
+//     the other path, and the two decisions are the sign bits of the packed difference m0 - m1 + 0x7fff: one PRMT in
+//     sign-replicate mode gathers the four decisions of a packed butterfly, one LOP3 files them in the decision word.
+//     The adds are written as two-input adds wherever possible so that ptxas can spread them over the ALU and the FMA
+//     pipe (IADD3 / IMAD.IADD): the ALU pipe alone (min, PRMT, LOP3) bounds the kernel. A warp therefore advances 32
 //     code words with ~200 instructions per trellis step, where the warp-per-code-word kernel needs ~60 instructions
 //     per step for ONE code word.
 //   * Exactness: the reference's 32-bit metrics never differ by more than 6*1020+1000 = 7120 between states. The
@@ -50,6 +52,16 @@ __host__ __device__ __forceinline__ unsigned tpc_minu(unsigned a, unsigned b)
 #endif
 }
 
+// min(a + b, c) per 16-bit half: VIADDMNMX.U16x2, one ALU-pipe instruction for the add and the select
+__host__ __device__ __forceinline__ unsigned tpc_addmin(unsigned a, unsigned b, unsigned c)
+{
+#ifdef __CUDA_ARCH__
+  return __vminu2(__vadd2(a, b), c);
+#else
+  return tpc_minu(a + b, c); // no half of a + b carries (see "Exactness" above)
+#endif
+}
+
 // Bytes [t0.b1, t1.b1, t0.b3, t1.b3] with the most significant bit of each replicated over the byte (0x00 / 0xFF).
 __host__ __device__ __forceinline__ unsigned tpc_signs(unsigned t0, unsigned t1)
 {
@@ -63,8 +75,31 @@ __host__ __device__ __forceinline__ unsigned tpc_signs(unsigned t0, unsigned t1)
 }
 
 // (low half of x, low half of y) and (high half of x, high half of y): PRMT on the device
-__host__ __device__ __forceinline__ unsigned tpc_lo_lo(unsigned x, unsigned y) { return (x & 0xffffu) | (y << 16); }
-__host__ __device__ __forceinline__ unsigned tpc_hi_hi(unsigned x, unsigned y) { return (x >> 16) | (y & 0xffff0000u); }
+__host__ __device__ __forceinline__ unsigned tpc_lo_lo(unsigned x, unsigned y)
+{
+#ifdef __CUDA_ARCH__
+  return __byte_perm(x, y, 0x5410);
+#else
+  return (x & 0xffffu) | (y << 16);
+#endif
+}
+__host__ __device__ __forceinline__ unsigned tpc_hi_hi(unsigned x, unsigned y)
+{
+#ifdef __CUDA_ARCH__
+  return __byte_perm(x, y, 0x7632);
+#else
+  return (x >> 16) | (y & 0xffff0000u);
+#endif
+}
+// byte j of x
+template <int J> __host__ __device__ __forceinline__ unsigned tpc_byte(unsigned x)
+{
+#ifdef __CUDA_ARCH__
+  return __byte_perm(x, 0u, 0x4440 + J);
+#else
+  return (x >> (8 * J)) & 255u;
+#endif
+}
 __host__ __device__ __forceinline__ unsigned tpc_lo_hi(unsigned x, unsigned y) { return (x & 0xffffu) | (y & 0xffff0000u); }
 
 // Bit of the decision word of a type-K step that holds the decision of new state y (see TpcButterfly).
@@ -86,21 +121,40 @@ __host__ __device__ __forceinline__ void tpc_init(unsigned (&S)[32])
 //   S[i] = old[a] | old[a ^ m] << 16,   S[16 + i] = old[a + 32] | old[(a ^ m) + 32] << 16.
 // T receives the new metrics in the layout of type K + 1; for K = 4 in the layout T[x] = new[x] | new[x + 32] << 16.
 // sym: the four clamped symbols of the step, byte j = symbol j. dlo/dhi: decision word (tpc_decision_bit).
+// Butterflies with i < TPC_DFORM take their two decision words from D = L - H (three two-input adds, which ptxas may
+// place on either integer pipe), the others from one three-input add each (ALU pipe only): see tpc_step.
+constexpr int TPC_DFORM = 16;
+
 template <int K, int A>
 struct TpcButterfly
 {
-  static __host__ __device__ __forceinline__ void run(const unsigned (&S)[32], unsigned (&T)[32], const unsigned (&PB)[8], unsigned & lo, unsigned & hi)
+  static __host__ __device__ __forceinline__ void run(const unsigned (&S)[32], unsigned (&T)[32], const unsigned (&PB)[8], const unsigned (&KB)[8], unsigned & lo,
+                                                      unsigned & hi)
   {
     if constexpr (((A >> K) & 1) == 0)
     {
       constexpr int i = tpc_compress(A, K), p = tpc_pat(A);
       const unsigned L = S[i], H = S[16 + i];
-      // low halves: butterfly A (new states 2A, 2A+1); high halves: butterfly A ^ m
-      const unsigned m0 = L + PB[p], m1 = H + PB[p ^ 7], m2 = L + PB[p ^ 7], m3 = H + PB[p];
-      const unsigned n0 = tpc_minu(m0, m1), n1 = tpc_minu(m2, m3);
+      // low halves: butterfly A (new states 2A, 2A+1); high halves: butterfly A ^ m.
+      // m0 = L + PB[p], m1 = H + PB[p ^ 7] -> new state 2A; m2 = L + PB[p ^ 7], m3 = H + PB[p] -> new state 2A + 1
+      const unsigned m1 = H + PB[p ^ 7], m3 = H + PB[p];
+      const unsigned n0 = tpc_addmin(L, PB[p], m1), n1 = tpc_addmin(L, PB[p ^ 7], m3);
       // decision = 1 when the path from old state +32 is strictly better (viterbi_scalar.h: d = (m0 - m1) > 0):
-      // per half m0 - m1 + 0x7fff has bit 15 set exactly then (|m0 - m1| <= 7120 + 1020, so no half borrows or carries)
-      const unsigned t0 = m0 - m1 + 0x7fff7fffu, t1 = m2 - m3 + 0x7fff7fffu;
+      // per half m0 - m1 + 0x7fff has bit 15 set exactly then (|m0 - m1| <= 7120 + 1020, so the halves of the final
+      // value neither borrow nor carry; the 32-bit intermediates may, which cancels). With PB[p] + PB[p ^ 7] = 1020 per
+      // half, m0 - m1 + 0x7fff = (L - H) + KB[p] and m2 - m3 + 0x7fff = (L - H) + KB[p ^ 7], KB[p] = 2 PB[p] + (0x7fff - 1020).
+      unsigned t0, t1;
+      if constexpr (i < TPC_DFORM)
+      {
+        const unsigned D = L - H;
+        t0 = D + KB[p];
+        t1 = D + KB[p ^ 7];
+      }
+      else
+      {
+        t0 = L + (PB[p] + 0x7fff7fffu) - m1;
+        t1 = L + (PB[p ^ 7] + 0x7fff7fffu) - m3;
+      }
       const unsigned x = tpc_signs(t0, t1) & (0x01010101u << (i & 7));
       if constexpr (i < 8) lo |= x; else hi |= x;
       if constexpr (K < 4)
@@ -110,35 +164,41 @@ struct TpcButterfly
       }
       else { T[2 * A] = n0; T[2 * A + 1] = n1; }
     }
-    if constexpr (A + 1 < 32) TpcButterfly<K, A + 1>::run(S, T, PB, lo, hi);
+    if constexpr (A + 1 < 32) TpcButterfly<K, A + 1>::run(S, T, PB, KB, lo, hi);
   }
 };
 
 template <int K>
 __host__ __device__ __forceinline__ void tpc_step(const unsigned (&S)[32], unsigned (&T)[32], unsigned sym, unsigned & dlo, unsigned & dhi)
 {
-  // packed branch metrics: low half = metric of pattern p, high half = metric of pattern p ^ F (the partner butterfly)
+  // packed branch metrics: low half = metric of pattern p, high half = metric of pattern p ^ F (the partner butterfly).
+  // Each packed term is one multiply-add of the symbol value x (maximum M): x * 0x00010001 = (x, x),
+  // x * 0xfffeffff + (M, M) = (M - x, M - x), x * 0xffff0001 + (0, M) = (x, M - x), x * 0x0000ffff + (M, 0) = (M - x, x)
+  // (low half first), which keeps them on the FMA pipe.
   constexpr int F = tpc_pat(1 << K);
-  const unsigned s0 = sym & 255u, s1 = (sym >> 8) & 255u, s2 = (sym >> 16) & 255u, s3 = sym >> 24;
-  const unsigned a = (s0 + s3) * 0x10001u, b = s1 * 0x10001u, c = s2 * 0x10001u;
-  const unsigned an = 0x01fe01feu - a, bn = 0x00ff00ffu - b, cn = 0x00ff00ffu - c;
-  const unsigned Ap[2] = { (F & 1) ? tpc_lo_hi(a, an) : a, (F & 1) ? tpc_lo_hi(an, a) : an };
-  const unsigned Bp[2] = { (F & 2) ? tpc_lo_hi(b, bn) : b, (F & 2) ? tpc_lo_hi(bn, b) : bn };
-  const unsigned Cp[2] = { (F & 4) ? tpc_lo_hi(c, cn) : c, (F & 4) ? tpc_lo_hi(cn, c) : cn };
-  unsigned PB[8];
+  const unsigned s1 = tpc_byte<1>(sym), s2 = tpc_byte<2>(sym), sa = tpc_byte<0>(sym) + tpc_byte<3>(sym);
+  const unsigned Ap[2] = { (F & 1) ? sa * 0xffff0001u + 0x01fe0000u : sa * 0x00010001u, (F & 1) ? sa * 0x0000ffffu + 0x000001feu : sa * 0xfffeffffu + 0x01fe01feu };
+  const unsigned Bp[2] = { (F & 2) ? s1 * 0xffff0001u + 0x00ff0000u : s1 * 0x00010001u, (F & 2) ? s1 * 0x0000ffffu + 0x000000ffu : s1 * 0xfffeffffu + 0x00ff00ffu };
+  const unsigned Cp[2] = { (F & 4) ? s2 * 0xffff0001u + 0x00ff0000u : s2 * 0x00010001u, (F & 4) ? s2 * 0x0000ffffu + 0x000000ffu : s2 * 0xfffeffffu + 0x00ff00ffu };
+  unsigned PB[8], KB[8];
 #pragma unroll
-  for (int p = 0; p < 8; p++) PB[p] = Ap[p & 1] + Bp[(p >> 1) & 1] + Cp[(p >> 2) & 1];
+  for (int p = 0; p < 8; p++)
+  {
+    PB[p] = Ap[p & 1] + Bp[(p >> 1) & 1] + Cp[(p >> 2) & 1];
+    KB[p] = PB[p] * 2u + 0x7c037c03u; // 0x7fff - 1020 per half
+  }
   unsigned lo = 0, hi = 0;
-  TpcButterfly<K, 0>::run(S, T, PB, lo, hi);
+  TpcButterfly<K, 0>::run(S, T, PB, KB, lo, hi);
   dlo = lo;
   dhi = hi;
 }
 
-// (x, x + 32) pairs -> type-0 layout, optionally subtracting the minimum metric from every state.
-__host__ __device__ __forceinline__ void tpc_repair(const unsigned (&R)[32], unsigned (&S)[32], bool renorm)
+// (x, x + 32) pairs -> type-0 layout; RENORM: the minimum metric is subtracted from every state.
+template <bool RENORM>
+__host__ __device__ __forceinline__ void tpc_repair(const unsigned (&R)[32], unsigned (&S)[32])
 {
   unsigned sub = 0;
-  if (renorm)
+  if constexpr (RENORM)
   {
     unsigned m = R[0];
 #pragma unroll
@@ -149,7 +209,7 @@ __host__ __device__ __forceinline__ void tpc_repair(const unsigned (&R)[32], uns
 #pragma unroll
   for (int a = 0; a < 32; a += 2)
   {
-    const unsigned x = R[a] - sub, y = R[a + 1] - sub; // no half borrows: every half >= mn
+    const unsigned x = RENORM ? R[a] - sub : R[a], y = RENORM ? R[a + 1] - sub : R[a + 1]; // no half borrows: every half >= mn
     S[a >> 1] = tpc_lo_lo(x, y);      // (s[a], s[a+1])
     S[16 + (a >> 1)] = tpc_hi_hi(x, y); // (s[a+32], s[a+33])
   }
@@ -164,7 +224,7 @@ __host__ __device__ __forceinline__ void tpc_five_steps(unsigned (&S)[32], const
   tpc_step<2>(S, T, sym[2], lo, hi); dec[2] = (unsigned long long)lo | ((unsigned long long)hi << 32);
   tpc_step<3>(T, S, sym[3], lo, hi); dec[3] = (unsigned long long)lo | ((unsigned long long)hi << 32);
   tpc_step<4>(S, T, sym[4], lo, hi); dec[4] = (unsigned long long)lo | ((unsigned long long)hi << 32);
-  tpc_repair(T, S, renorm);
+  if (renorm) tpc_repair<true>(T, S); else tpc_repair<false>(T, S);
 }
 
 // Chain back one step: y = current state, w = decision word of the step that entered y, pos = tpc_decision_bit of

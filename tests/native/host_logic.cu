@@ -76,7 +76,7 @@ static void viterbi_tpc_emulated(const VitProfile & pr, const int16_t * soft, ui
   {
     const unsigned sy[5] = { syms[t0], syms[t0 + 1], syms[t0 + 2], syms[t0 + 3], syms[t0 + 4] };
     unsigned long long dec[5];
-    tpc_five_steps(S, sy, dec, (t0 + 5) % TPC_RENORM == 0);
+    tpc_five_steps(S, sy, dec, (t0 + 5) % TPC_RENORM == 0); // k_vit_tpc counts the blocks down instead
     for (int i = 0; i < 5; i++) surv[t0 + i] = dec[i];
     for (int i = 0; i < 32; i++) if ((S[i] & 0xffffu) > 60000u || (S[i] >> 16) > 60000u) { fprintf(stderr, "metric overflow\n"); exit(3); }
   }

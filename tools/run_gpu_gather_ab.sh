@@ -1,12 +1,20 @@
 #!/bin/bash
-# usage: bash tools/run_gpu_gather_ab.sh <tag>  -- GPU parity tests, then the full-ensemble decode with 1 and 2 code words per warp in flight in k_vit_gather
+# usage: bash tools/run_gpu_gather_ab.sh <tag>  -- GPU parity tests, then the bench with the first form of the gather (k_vit_gather, two code
+# words per warp in flight) and with the default one (k_vit_gather_kb)
 TAG=${1:-ab}
 cd $GRAFT_REPO_ROOT
 O=gpurun_out/${TAG}
-timeout 600 python -m pytest tests -m gpu -x -q > ${O}_tests.log 2>&1; echo "tests exit $?" >> ${O}_tests.log
+timeout 900 python -m pytest tests -m gpu -x -q > ${O}_tests.log 2>&1; echo "tests exit $?" >> ${O}_tests.log
 tail -4 ${O}_tests.log
-for b in 1 2; do
-  DABSTAR_GATHER_BATCH=$b timeout 300 python tools/bench_full_ensemble.py > ${O}_fe_batch$b.json 2> ${O}_fe_batch$b.err
-  python -c "import json,sys; d=json.load(open('${O}_fe_batch$b.json')); print('batch $b', round(d['ms_per_step'],2), 'ms', round(d['frames_per_s']), 'frames/s', 'msc', round(d['stages_ms']['msc_viterbi'],2), 'fic', round(d['stages_ms']['fic_viterbi'],3), 'ok', d['payload_equals_transmitted'])"
-  tail -2 ${O}_fe_batch$b.err
+for b in 2 0; do
+  DABSTAR_GATHER_BATCH=$b timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > ${O}_bench_gather$b.json 2> ${O}_bench_gather$b.err
+  python - ${O}_bench_gather$b.json $b <<'PY'
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+fe, c0, sw = d["full_ensemble"], d["config0"], d["viterbi_sweep"]
+print("gather", sys.argv[2], "value", round(d["value"]), "fic", round(d["stages"]["fic_viterbi"]["ms_per_step"], 3),
+      "| full ensemble", round(fe["frames_per_s"]), "msc", round(fe["stages_ms"]["msc_viterbi"], 2), "gather", round(fe["msc_gather_ms"], 2), "trellis", round(fe["msc_trellis_ms"], 2), fe["payload_equals_transmitted"],
+      "| config0", round(c0["frames_per_s"]), "| sweep", round(sw["mbit_s_overall"]), sw["bits_equal_reference"], {k: round(v["frac_int_alu"], 3) for k, v in list(sw["levels"].items())[::4]})
+PY
+  tail -2 ${O}_bench_gather$b.err
 done

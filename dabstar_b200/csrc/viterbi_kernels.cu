@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(256) k_vit_gather(const VitJob * __restrict__ 
 // into the punctured positions. Same words as k_vit_gather, bit for bit (tests/test_gpu_viterbi.py runs both).
 constexpr int GK_WORDS = (4 * GATHER_STEPS + 128) / 4 + 1; // kept bytes of a tile from the aligned start, + the funnel shift's second word
 constexpr int GK_ITERS = (4 * GATHER_STEPS + 128) / 128;
+constexpr int GK_BATCH = 3; // 128-bit groups of a code word whose loads are in flight together
 
 // soft bit at p if k < lim; unspecified otherwise (such bytes are never selected)
 __device__ __forceinline__ int ld_soft_lt(const int16_t * p, int k, int lim)
@@ -336,7 +337,7 @@ __device__ __forceinline__ int ld_soft_lt(const int16_t * p, int k, int lim)
   return v;
 }
 
-__global__ void __launch_bounds__(256) k_vit_gather_kb(const VitJob * __restrict__ jobs, const FrameDesc * __restrict__ fic_frames, int job_first, int n_jobs,
+__global__ void __launch_bounds__(256, 4) k_vit_gather_kb(const VitJob * __restrict__ jobs, const FrameDesc * __restrict__ fic_frames, int job_first, int n_jobs,
                                                        const VitProfile * __restrict__ profiles, const unsigned * __restrict__ step_tab,
                                                        const int16_t * __restrict__ soft, unsigned * __restrict__ sym, int stride, int rows)
 {
@@ -344,6 +345,7 @@ __global__ void __launch_bounds__(256) k_vit_gather_kb(const VitJob * __restrict
   __shared__ unsigned tile[32][GATHER_STEPS + 1];
   __shared__ const int16_t * rowptr[32][17];
   __shared__ int sh_steps[32], sh_tab[32], sh_ka[32], sh_k1[32];
+  __shared__ unsigned char sh_lin[32]; // the code word's kept bits are contiguous and 8-byte aligned: four per load
   __shared__ unsigned kb[8][GK_WORDS];
   __shared__ unsigned sel_lut[16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -379,6 +381,7 @@ __global__ void __launch_bounds__(256) k_vit_gather_kb(const VitJob * __restrict
       sh_tab[lane] = pr->tab_off;
       sh_ka[lane] = k0 & ~127;
       sh_k1[lane] = k1;
+      sh_lin[lane] = valid && job.src_mode == VIT_SRC_LINEAR && (pr->n_kept & 3) == 0 && ((uintptr_t)(soft + job.src) & 7) == 0;
     }
     if (threadIdx.x < 16)
     {
@@ -426,32 +429,61 @@ __global__ void __launch_bounds__(256) k_vit_gather_kb(const VitJob * __restrict
       }
     }
     // ---- kept bits -> clamped bytes; every load of the code word is issued before the first is used
+    // (three 128-bit groups of the code word at a time: all of a rate-1/2 tile, and it keeps the kernel at 64 registers)
+    if (sh_lin[jr])
+    {
+      const uint2 * p = reinterpret_cast<const uint2 *>(rowptr[jr][0] + kl);
+#pragma unroll
+      for (int i0 = 0; i0 < GK_ITERS; i0 += GK_BATCH)
+      {
+        uint2 a[GK_BATCH];
+#pragma unroll
+        for (int i = i0; i < i0 + GK_BATCH && i < GK_ITERS; i++)
+          if (128 * i < span && 128 * i < rem) a[i - i0] = __ldg(p + 32 * i); // the code word has a multiple of four kept bits
+        asm volatile("" ::: "memory");
+#pragma unroll
+        for (int i = i0; i < i0 + GK_BATCH && i < GK_ITERS; i++)
+        {
+          if (128 * i < span)
+          {
+            const unsigned lo = __vmins2(__vmaxs2(__vadd2(a[i - i0].x, 0x007f007fu), 0u), 0x00ff00ffu);
+            const unsigned hi = __vmins2(__vmaxs2(__vadd2(a[i - i0].y, 0x007f007fu), 0u), 0x00ff00ffu);
+            kbw[32 * i + lane] = __byte_perm(lo, hi, 0x6420);
+          }
+        }
+      }
+    }
+    else
     {
       const int16_t * p[4];
 #pragma unroll
       for (int g = 0; g < 4; g++) p[g] = rowptr[jr][ridx[g]] + kl + g;
-      int a[GK_ITERS][4];
 #pragma unroll
-      for (int i = 0; i < GK_ITERS; i++)
+      for (int i0 = 0; i0 < GK_ITERS; i0 += GK_BATCH)
       {
-        if (128 * i < span)
-        {
+        int a[GK_BATCH][4];
 #pragma unroll
-          for (int g = 0; g < 4; g++) a[i][g] = ld_soft_lt(p[g] + 128 * i, 128 * i + g, rem);
+        for (int i = i0; i < i0 + GK_BATCH && i < GK_ITERS; i++)
+        {
+          if (128 * i < span)
+          {
+#pragma unroll
+            for (int g = 0; g < 4; g++) a[i - i0][g] = ld_soft_lt(p[g] + 128 * i, 128 * i + g, rem);
+          }
         }
-      }
-      asm volatile("" ::: "memory");
+        asm volatile("" ::: "memory");
 #pragma unroll
-      for (int i = 0; i < GK_ITERS; i++)
-      {
-        if (128 * i < span)
+        for (int i = i0; i < i0 + GK_BATCH && i < GK_ITERS; i++)
         {
-          // viterbi_scalar.h:34-40: in + 127 wraps in 16 bits before the clamp to 0..255 (the 16-bit halves taken by the PRMT)
-          unsigned lo = __byte_perm((unsigned)(a[i][0] + 127), (unsigned)(a[i][1] + 127), 0x5410);
-          unsigned hi = __byte_perm((unsigned)(a[i][2] + 127), (unsigned)(a[i][3] + 127), 0x5410);
-          lo = __vmins2(__vmaxs2(lo, 0u), 0x00ff00ffu);
-          hi = __vmins2(__vmaxs2(hi, 0u), 0x00ff00ffu);
-          kbw[32 * i + lane] = __byte_perm(lo, hi, 0x6420);
+          if (128 * i < span)
+          {
+            // viterbi_scalar.h:34-40: in + 127 wraps in 16 bits before the clamp to 0..255 (the 16-bit halves taken by the PRMT)
+            unsigned lo = __byte_perm((unsigned)(a[i - i0][0] + 127), (unsigned)(a[i - i0][1] + 127), 0x5410);
+            unsigned hi = __byte_perm((unsigned)(a[i - i0][2] + 127), (unsigned)(a[i - i0][3] + 127), 0x5410);
+            lo = __vmins2(__vmaxs2(lo, 0u), 0x00ff00ffu);
+            hi = __vmins2(__vmaxs2(hi, 0u), 0x00ff00ffu);
+            kbw[32 * i + lane] = __byte_perm(lo, hi, 0x6420);
+          }
         }
       }
     }

@@ -774,6 +774,146 @@ __global__ void __launch_bounds__(256) k_cp_corr(const FrameDesc * __restrict__ 
   }
 }
 
+// The same sums for 8-bit input with the samples brought in by the TMA engine: a warp keeps CPB_STAGES symbols in flight, each as
+// two bulk copies (the prefix and the samples 2048 later, 1024 bytes from a 16-byte aligned start; both have the same offset in
+// their copy) into the warp's own ring in shared memory, completion on an mbarrier per stage. Elements, lanes and the order of
+// the additions are those of k_cp_corr, so the sums are the same bit for bit; what changes is that no register waits for a
+// load (k_cp_corr: 67 % of the stall samples on the 32 two-byte loads of a symbol, 3.6 TB/s) and a warp has 8 KB in flight
+// instead of 2. Symbols whose aligned copies could leave the recording take the direct loads.
+constexpr int CPB_STAGES = 4;
+constexpr int CPB_COPY = 1024;
+constexpr int CPB_SMEM = 8 * CPB_STAGES * 2 * CPB_COPY;
+
+__global__ void __launch_bounds__(256) k_cp_corr_bulk(const FrameDesc * __restrict__ frames, int n_frames, const RecInput * __restrict__ recs, float2 * __restrict__ cp)
+{
+  extern __shared__ __align__(128) unsigned char cpb_ring[];
+  __shared__ unsigned long long cpb_bar[8 * CPB_STAGES];
+  __shared__ float2 red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char * ring = cpb_ring + warp * (CPB_STAGES * 2 * CPB_COPY);
+  const unsigned ring_s = smem_addr_u32(ring), bar_s = smem_addr_u32(cpb_bar + warp * CPB_STAGES);
+  if (lane == 0)
+  {
+#pragma unroll
+    for (int b = 0; b < CPB_STAGES; b++) mbar_init(bar_s + 8u * (unsigned)b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  // the warp's symbols in order: frames blockIdx.x, blockIdx.x + gridDim.x, ..., symbols warp, warp + 8, ... of each
+  struct Cursor
+  {
+    int fi, sym, n_syms;
+    long long base, n;
+    const unsigned char * iq;
+  };
+  auto enter = [&](Cursor & c) {
+    // first frame from c.fi on that has a symbol for this warp
+    while (c.fi < n_frames)
+    {
+      const FrameDesc & fd = frames[c.fi];
+      c.n_syms = fd.n_syms;
+      if (warp < c.n_syms)
+      {
+        const RecInput rin = recs[fd.rec];
+        c.base = fd.sym0 + T_U;
+        c.n = rin.n;
+        c.iq = static_cast<const unsigned char *>(rin.iq);
+        c.sym = warp;
+        return;
+      }
+      c.fi += (int)gridDim.x;
+    }
+  };
+  auto advance = [&](Cursor & c) {
+    c.sym += 8;
+    if (c.sym >= c.n_syms) { c.fi += (int)gridDim.x; enter(c); }
+  };
+  auto first_sample = [](const Cursor & c) { return c.base + (long long)c.sym * T_S; };
+  auto by_copy = [&](const Cursor & c) { const long long s0 = first_sample(c); return s0 >= 8 && s0 + T_U + T_G + 8 <= c.n; };
+  auto issue = [&](const Cursor & c, int b) {
+    if (c.fi < n_frames && by_copy(c) && lane == 0)
+    {
+      const unsigned long long a = (unsigned long long)(c.iq + 2 * first_sample(c)) & ~15ull;
+      const unsigned dst = ring_s + (unsigned)(b * 2 * CPB_COPY), bar = bar_s + 8u * (unsigned)b;
+      mbar_expect_tx(bar, 2u * CPB_COPY);
+      bulk_g2s(dst, reinterpret_cast<const void *>(a), CPB_COPY, bar);
+      bulk_g2s(dst + CPB_COPY, reinterpret_cast<const void *>(a + 2ull * T_U), CPB_COPY, bar);
+    }
+  };
+
+  Cursor ahead;
+  ahead.fi = (int)blockIdx.x;
+  ahead.sym = 0; ahead.n_syms = 0; ahead.base = 0; ahead.n = 0; ahead.iq = nullptr;
+  enter(ahead);
+  Cursor cur = ahead;
+#pragma unroll 1
+  for (int b = 0; b < CPB_STAGES && ahead.fi < n_frames; b++) { issue(ahead, b); advance(ahead); }
+  int stage = 0;
+  unsigned phase_bits = 0;
+
+  for (int fi = blockIdx.x; fi < n_frames; fi += gridDim.x)
+  {
+    float2 acc = make_float2(0.0f, 0.0f);
+    while (cur.fi == fi)
+    {
+      unsigned ra[16], rb[16];
+      if (by_copy(cur))
+      {
+        mbar_wait(bar_s + 8u * (unsigned)stage, (phase_bits >> stage) & 1u);
+        phase_bits ^= 1u << stage;
+        const unsigned off = (unsigned)((unsigned long long)(cur.iq + 2 * first_sample(cur)) & 15ull);
+        const unsigned short * sp = reinterpret_cast<const unsigned short *>(ring + stage * 2 * CPB_COPY + off) + lane;
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+        {
+          if (lane + 32 * k < T_G) { ra[k] = sp[32 * k + CPB_COPY / 2]; rb[k] = sp[32 * k]; }
+          else { ra[k] = 0; rb[k] = 0; }
+        }
+      }
+      else
+      {
+        const unsigned short * pp = reinterpret_cast<const unsigned short *>(cur.iq) + first_sample(cur) + lane;
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+        {
+          if (lane + 32 * k < T_G) { ra[k] = pp[32 * k + T_U]; rb[k] = pp[32 * k]; }
+          else { ra[k] = 0; rb[k] = 0; }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 16; k++)
+      {
+        if (lane + 32 * k < T_G)
+        {
+          const float2 a = to_cf(ra[k]), b = to_cf(rb[k]);
+          acc.x += a.x * b.x + a.y * b.y;
+          acc.y += a.y * b.x - a.x * b.y;
+        }
+      }
+      // the stage is free again: every lane has its values in registers
+      __syncwarp();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(ahead, stage);
+      if (ahead.fi < n_frames) advance(ahead);
+      advance(cur);
+      stage = stage + 1 == CPB_STAGES ? 0 : stage + 1;
+    }
+    acc.x = warp_sum(acc.x);
+    acc.y = warp_sum(acc.y);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      float2 s = red[0];
+      for (int w = 1; w < 8; w++) { s.x += red[w].x; s.y += red[w].y; }
+      cp[fi] = s;
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ DQPSK demapper (D1-D4)
 // OfdmDecoder::decode_symbol (ofdm_decoder.cpp:147-355) for whole recordings. The per-carrier IIR chains are sequential
 // in time but independent across carriers, so the parallelism is (recordings or segments) x carriers:
@@ -1530,6 +1670,17 @@ cudaError_t launch_cp_corr(cudaStream_t s, const FrameDesc * frames, int n_frame
 {
   if (n_frames <= 0) return cudaSuccess;
   if (lc) (*lc)++;
+  // DABSTAR_CP_BULK=0: the direct-load kernel for 8-bit input too (read per launch: A/B measurements, and the parity test of the two)
+  const char * ev = getenv("DABSTAR_CP_BULK");
+  const bool bulk = ev == nullptr || atoi(ev) != 0;
+  if (fmt == FMT_U8 && bulk)
+  {
+    const LaunchProps lp = launch_props((const void *)k_cp_corr_bulk, 256, CPB_SMEM, CPB_SMEM);
+    if (lp.err != cudaSuccess) return lp.err;
+    const int slots = lp.n_sm * (lp.ctas_per_sm > 0 ? lp.ctas_per_sm : 1);
+    k_cp_corr_bulk<<<n_frames < slots ? n_frames : slots, 256, CPB_SMEM, s>>>(frames, n_frames, recs, cp);
+    return cudaGetLastError();
+  }
   const int grid = n_frames < N_SM * 8 ? n_frames : N_SM * 8;
   return dispatch_fmt(fmt, [&](auto F) { k_cp_corr<decltype(F)::value><<<grid, 256, 0, s>>>(frames, n_frames, recs, cp); });
 }

@@ -143,6 +143,30 @@ def test_cp_correlation_stage_tap(ctx):
     assert api.cp_correlate(np.zeros((0, per), np.complex64), ctx).shape == (0,)
 
 
+def test_cp_correlation_by_bulk_copy_equals_direct_loads(ctx, monkeypatch):
+    """8-bit input: k_cp_corr_bulk (TMA copies into a ring in shared memory) and k_cp_corr (direct loads) add the same products
+    in the same order, so the whole decode (frame positions, every soft bit, FIBs) is identical; the recordings start at odd
+    sample offsets so that the 16-byte aligned copies see every alignment, and one ends inside a frame."""
+    recs = []
+    for i in range(6):
+        r = synth.generate(5, seed=300 + i, snr_db=11.0 + i, cfo_hz=-2300.0 + 900.0 * i, fmt=synth.FMT_U8)
+        iq = r.iq[3 + i:]  # (n, 2) samples: a different 16-byte alignment of the frame start in every recording
+        recs.append(np.ascontiguousarray(iq[:len(iq) - (50000 if i == 5 else 0)]))
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DABSTAR_CP_BULK", mode)
+        dp = api.DabProcessor(len(recs), input_format=synth.FMT_U8, ctx=ctx)
+        dp.run(recs)
+        out[mode] = [(dp.n_frames(r), dp.frame_positions(r).copy(), dp.fib_packed(r).copy(),
+                      np.stack([dp.soft_bits(r, f) for f in range(dp.n_frames(r))]) if dp.n_frames(r) else None) for r in range(len(recs))]
+    assert sum(o[0] for o in out["1"]) >= 20
+    for a, b in zip(out["0"], out["1"]):
+        assert a[0] == b[0]
+        assert np.array_equal(a[1], b[1])
+        assert np.array_equal(a[2], b[2])
+        assert (a[3] is None and b[3] is None) or np.array_equal(a[3], b[3])
+
+
 # ---- the reference's own objects on the GPU box (oracle/_ref/libdabref.so ships with the snapshot when it was built)
 def test_chain_against_the_reference_itself(ctx, refo):
     sc = [synth.SubChannel(3, 100, 54, 0, 2, 72)]

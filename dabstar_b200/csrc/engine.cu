@@ -125,7 +125,8 @@ struct dabstar_ctx
     if (!pool)
     {
       const char * ev = getenv("DABSTAR_HOST_THREADS"); // total threads incl. the caller (1 = serial)
-      pool.reset(new dab::HostPool(ev ? std::max(0, atoi(ev) - 1) : dab::HostPool::default_workers()));
+      const char * sp = getenv("DABSTAR_HOST_SPIN_US"); // how long an idle worker polls before it sleeps (hostpool.h)
+      pool.reset(new dab::HostPool(ev ? std::max(0, atoi(ev) - 1) : dab::HostPool::default_workers(), sp ? std::max(0, atoi(sp)) : 1000));
     }
     return *pool;
   }
@@ -1490,6 +1491,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
   dec->ev_used = 0;
   for (int i = 0; i < 10; i++) { dec->stage_ms[i] = 0; dec->stage_launches[i] = 0; }
   CK(cudaEventRecord(dec->ev0, st));
+  ctx->host_pool().prewake(); // the first region of the run is less than a wake-up away
 
   static const bool trace = getenv("DABSTAR_TRACE") != nullptr; // per-round progress on stderr (debug aid)
   const auto t_run0 = std::chrono::steady_clock::now();
@@ -1735,6 +1737,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       win_recs.push_back(r);
     }
     if (win_recs.empty()) { if (any_wait) continue; break; }
+    tr("  windows opened");
 
     // ---- step A: measure the PRS peak of the first frame where it is not known and not speculated
     {
@@ -1817,6 +1820,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
     const long long resident = resident_upto();
     bool first_pass = true;
     dab::HostPool & pool = ctx->host_pool();
+    tr("  plans made");
     while (true)
     {
       // tail layout of the open plans: positions first (a few integer operations per frame), then the descriptors of all
@@ -1862,6 +1866,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
         window_end = std::max(window_end, p);
       }
       ctl.resize((size_t)n_laid);
+      tr("  positions walked");
       // (plan, first frame, end frame) pieces of at most 1024 frames: one long recording is a single plan, the pool works on pieces
       std::vector<std::array<int, 3>> pieces;
       for (size_t pi = 0; pi < plans.size(); pi++)
@@ -2103,6 +2108,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
     if (int r_ = upload_commit(ctx, dec->d_desc.p, desc_stage, sizeof(FrameDesc) * (size_t)n_desc)) return r_;
     FrameDesc * d_fd = dec->d_desc.as<FrameDesc>();
 
+    cudaEvent_t wake_ev = nullptr; // end of the round's last demapper launch
     // ---- heavy pass: FFT (+ingest, derotation, de-interleave) -> demap -> FIC
     // The window is cut into `nch` chunks in TIME (the same share of every recording's frames); the FFT of chunk c + 1 runs
     // on the context's stream while the demapper and the FIC Viterbi of chunk c run on a second stream. The two kernels
@@ -2245,6 +2251,7 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       CK(cudaEventRecord(h1, st));
       dec->heavy_spans.push_back({ h0, h1 });
       dec->fft_demap_spans.push_back({ h0, hd });
+      wake_ev = hd;
     }
 
     tr("heavy pass enqueued");
@@ -2261,6 +2268,8 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       }
       CK(dec->h_crc.reserve((size_t)(s_hi - s_lo) * 12));
       CK(cudaMemcpyAsync(dec->h_crc.p, dec->d_crc.as<uint8_t>() + (size_t)s_lo * 12, (size_t)(s_hi - s_lo) * 12, cudaMemcpyDeviceToHost, st));
+      // the pool's workers went to sleep during the FFT and the demapper: have them polling again when the FIC decode ends
+      if (wake_ev) { CK(cudaEventSynchronize(wake_ev)); pool.prewake(); }
       SYNC();
       for (auto & pl : plans)
       {

@@ -6,6 +6,7 @@
 // plain loop.
 #pragma once
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -19,7 +20,11 @@ namespace dab
 class HostPool
 {
 public:
-  explicit HostPool(int workers)
+  // spin_us: how long an idle worker polls the generation counter before it goes to sleep. The regions of a decode step are
+  // less than that apart, so the workers stay awake through a step's control phases and sleep through its long kernels;
+  // prewake() gets them polling again shortly before the next region is due (waking a sleeping worker costs ~50 us, which a
+  // step paid several times over: 0.4 of 12.9 ms).
+  explicit HostPool(int workers, int spin_us = 1000) : spin_us_(spin_us)
   {
     for (int i = 0; i < workers; i++) threads_.emplace_back([this] { loop(); });
   }
@@ -34,6 +39,17 @@ public:
     for (auto & t : threads_) t.join();
   }
   int workers() const { return (int)threads_.size(); }
+
+  // sleeping workers start polling again (for spin_us): call when a parallel_for is coming up
+  void prewake()
+  {
+    if (threads_.empty()) return;
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      wake_++;
+    }
+    cv_.notify_all();
+  }
 
   // CPUs this process may run on, minus the caller's, capped
   static int default_workers(int cap = 7)
@@ -83,21 +99,30 @@ private:
   }
   void loop()
   {
-    unsigned long long seen = 0;
+    unsigned long long seen = 0, seen_wake = 0;
     while (true)
     {
       std::function<void(int)> * f = nullptr;
       int n = 0;
-      // the regions of a decode step come in bursts: spin on the generation counter (no lock) before sleeping
-      for (int spin = 0; spin < 20000 && gen_.load(std::memory_order_acquire) == seen; spin++)
+      // poll the generation counter (no lock) before sleeping
       {
-        if ((spin & 63) == 63) std::this_thread::yield();
-        else __builtin_ia32_pause();
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int spin = 0; gen_.load(std::memory_order_acquire) == seen; spin++)
+        {
+          if ((spin & 63) == 63)
+          {
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(spin_us_)) break;
+            std::this_thread::yield();
+          }
+          else __builtin_ia32_pause();
+        }
       }
       {
         std::unique_lock<std::mutex> lk(m_);
-        cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen || stop_; });
+        cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen || stop_ || wake_ != seen_wake; });
         if (stop_) return;
+        seen_wake = wake_;
+        if (gen_.load(std::memory_order_acquire) == seen) continue; // woken ahead of a region: poll for it
         seen = gen_.load(std::memory_order_acquire);
         f = job_;
         n = n_;
@@ -111,6 +136,8 @@ private:
     }
   }
 
+  const int spin_us_;
+  unsigned long long wake_ = 0; // under m_
   std::vector<std::thread> threads_;
   std::mutex m_;
   std::condition_variable cv_;

@@ -1,5 +1,6 @@
 """The engine's host thread pool (dabstar_b200/csrc/hostpool.h): compiled into a small test program with g++ (no CUDA needed)
-and hammered with parallel_for calls of every size, nested data dependencies between regions and pools of 0..7 workers."""
+and hammered with parallel_for calls of every size, nested data dependencies between regions, pools of 0..7 workers, polling and
+sleeping workers and wake-ups ahead of a region (prewake)."""
 import os
 import subprocess
 import sys
@@ -16,12 +17,15 @@ int main()
 {
   for (int workers = 0; workers <= 7; workers++)
   {
-    dab::HostPool pool(workers);
+    dab::HostPool pool(workers, workers % 2 ? 1000 : 0); // workers that poll for 1 ms, and workers that sleep at once
     std::vector<long long> v(5000);
     long long want = 0;
     for (int round = 0; round < 400; round++)
     {
       const int n = round % 97 == 0 ? 5000 : (round * 37) % 131;   // incl. 0 and 1
+      if (round % 50 == 49) std::this_thread::sleep_for(std::chrono::milliseconds(3)); // let the workers fall asleep
+      if (round % 3 == 0) pool.prewake();                                              // with and without a region behind it
+      if (round % 100 == 99) { pool.prewake(); std::this_thread::sleep_for(std::chrono::milliseconds(3)); } // a wake-up nothing follows
       // region A writes, region B reads what A wrote (a region is complete when parallel_for returns)
       pool.parallel_for(n, [&](int i) { v[(size_t)i] = (long long)i * round; });
       std::atomic<long long> sum{ 0 };

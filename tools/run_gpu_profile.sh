@@ -11,6 +11,6 @@ tail -4 ${O}_tests.log
 timeout 900 python bench.py --steps 10 --warmup 3 > ${O}_bench.json 2> ${O}_bench.err; tail -c 400 ${O}_bench.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > ${O}_bench_ref.json 2> ${O}_bench_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file ${O}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-viterbi-sweep --no-extras > ${O}_ncu_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_fft_frames|k_demap5|k_vit_tpc|k_vit_gather|k_fic_post|k_cp_corr|k_dip_search|k_prs_corr' -c 12 -o ${O}_prof python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-viterbi-sweep --no-extras > ${O}_ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_fft_frames|k_demap5|k_vit_tpc|k_vit_gather|k_fic_post|k_cp_corr|k_dip_search|k_prs_corr' -c 14 -o ${O}_prof python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-viterbi-sweep --no-extras > ${O}_ncu_full.log 2>&1
 tail -2 ${O}_ncu_full.log
 python -c "import __graft_entry__ as g; g.smoke()" > ${O}_smoke.log 2>&1; tail -2 ${O}_smoke.log

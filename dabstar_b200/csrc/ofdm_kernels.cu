@@ -725,16 +725,69 @@ __global__ void __launch_bounds__(FFT_THREADS) k_init_ref_arg(const float2 * __r
 // cp[frame] = sum over symbols 1..75 and the 504 prefix samples of x[i+2048] conj(x[i]) on the RAW samples. The
 // derotated sum the reference forms differs by the constant factor e^{-j 2 pi f / 1000} (f = integer Hz), which the
 // host control loop applies.
+//
+// 8-bit input is summed in INTEGERS: a sample is ((I - c) / 128, (Q - c) / 128) with c = 127.38 (to_cf), so with a = x[i+2048],
+// b = x[i] as bytes
+//   16384 Re = P1 - c S1 + 2 N c^2,  P1 = sum(aI bI + aQ bQ),  S1 = sum(aI + aQ + bI + bQ),  N = number of products
+//   16384 Im = P2 - c S2,            P2 = sum(aQ bI - aI bQ),  S2 = sum(aQ - aI + bI - bQ)
+// and the four sums are dot products of byte vectors (IDP.4A): seven of them per TWO samples instead of ~20 instructions per
+// sample for the conversion to float and the complex multiply-add, no rounding until the one conversion per frame, and a
+// result that does not depend on which lane adds what (the two kernels below and their edge paths agree bit for bit by
+// construction). The reference's float sum of the same 37 800 products carries a rounding error of ~1e-5 relative, as did the
+// float form of this kernel; the integer form is the exact value of that sum.
+struct CpInt
+{
+  int p1, p2, s1, s2;
+};
+__device__ __forceinline__ unsigned dp4a_uu(unsigned a, unsigned b, unsigned c)
+{
+  unsigned d;
+  asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp4a_us(unsigned a, unsigned b_signed, int c)
+{
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b_signed), "r"(c));
+  return d;
+}
+// aw: bytes (I, Q, I, Q) of up to two samples of x[i+2048], bw: the same of x[i]; bytes outside the sum must be zero in both
+__device__ __forceinline__ void cp_int_add(CpInt & t, unsigned aw, unsigned bw)
+{
+  t.p1 = (int)dp4a_uu(aw, bw, (unsigned)t.p1);
+  const unsigned bs = __byte_perm(bw, 0u, 0x2301); // (Q, I, Q, I)
+  t.p2 = (int)dp4a_uu(aw & 0xff00ff00u, bs, (unsigned)t.p2);
+  t.p2 -= (int)dp4a_uu(aw & 0x00ff00ffu, bs, 0u);
+  t.s1 = (int)dp4a_uu(aw, 0x01010101u, dp4a_uu(bw, 0x01010101u, (unsigned)t.s1));
+  t.s2 = dp4a_us(aw, 0x01ff01ffu, dp4a_us(bw, 0xff01ff01u, t.s2)); // weights (-1, +1, -1, +1) and (+1, -1, +1, -1)
+}
+__device__ __forceinline__ int warp_sum_int(int v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// the per-warp sums of a frame (at most 10 symbols x 504 products: below 2^31) -> cp; thread 0, after a barrier
+__device__ __forceinline__ float2 cp_int_finish(const CpInt * red, int n_syms)
+{
+  long long p1 = 0, p2 = 0, s1 = 0, s2 = 0;
+  for (int w = 0; w < 8; w++) { p1 += red[w].p1; p2 += red[w].p2; s1 += red[w].s1; s2 += red[w].s2; }
+  const double c = 127.38, n = (double)n_syms * (double)T_G;
+  return make_float2((float)(((double)p1 - c * (double)s1 + 2.0 * n * c * c) * (1.0 / 16384.0)), (float)(((double)p2 - c * (double)s2) * (1.0 / 16384.0)));
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(256) k_cp_corr(const FrameDesc * __restrict__ frames, int n_frames, const RecInput * __restrict__ recs, float2 * __restrict__ cp)
 {
   __shared__ float2 red[8];
+  __shared__ CpInt redi[8];
   for (int fi = blockIdx.x; fi < n_frames; fi += gridDim.x)
   {
     const FrameDesc fd = frames[fi];
     const RecInput rin = recs[fd.rec];
     const long long base = fd.sym0 + T_U;
     float2 acc = make_float2(0.0f, 0.0f);
+    CpInt ti = { 0, 0, 0, 0 };
     // a warp takes every eighth symbol; the 2 x 16 loads of a lane are issued before the first product (a strided loop with one
     // pair of 2-byte loads in flight per thread ran at a third of the HBM rate)
     typedef typename Raw<FMT>::type T;
@@ -754,21 +807,35 @@ __global__ void __launch_bounds__(256) k_cp_corr(const FrameDesc * __restrict__ 
       {
         if (lane + 32 * k < T_G)
         {
-          const float2 a = to_cf(ra[k]), b = to_cf(rb[k]);
-          acc.x += a.x * b.x + a.y * b.y;
-          acc.y += a.y * b.x - a.x * b.y;
+          if constexpr (FMT == FMT_U8) cp_int_add(ti, ra[k], rb[k]);
+          else
+          {
+            const float2 a = to_cf(ra[k]), b = to_cf(rb[k]);
+            acc.x += a.x * b.x + a.y * b.y;
+            acc.y += a.y * b.x - a.x * b.y;
+          }
         }
       }
     }
-    acc.x = warp_sum(acc.x);
-    acc.y = warp_sum(acc.y);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0)
+    if constexpr (FMT == FMT_U8)
     {
-      float2 s = red[0];
-      for (int w = 1; w < 8; w++) { s.x += red[w].x; s.y += red[w].y; }
-      cp[fi] = s;
+      ti.p1 = warp_sum_int(ti.p1); ti.p2 = warp_sum_int(ti.p2); ti.s1 = warp_sum_int(ti.s1); ti.s2 = warp_sum_int(ti.s2);
+      if ((threadIdx.x & 31) == 0) redi[threadIdx.x >> 5] = ti;
+      __syncthreads();
+      if (threadIdx.x == 0) cp[fi] = cp_int_finish(redi, fd.n_syms);
+    }
+    else
+    {
+      acc.x = warp_sum(acc.x);
+      acc.y = warp_sum(acc.y);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+      __syncthreads();
+      if (threadIdx.x == 0)
+      {
+        float2 s = red[0];
+        for (int w = 1; w < 8; w++) { s.x += red[w].x; s.y += red[w].y; }
+        cp[fi] = s;
+      }
     }
     __syncthreads();
   }
@@ -776,10 +843,11 @@ __global__ void __launch_bounds__(256) k_cp_corr(const FrameDesc * __restrict__ 
 
 // The same sums for 8-bit input with the samples brought in by the TMA engine: a warp keeps CPB_STAGES symbols in flight, each as
 // two bulk copies (the prefix and the samples 2048 later, 1024 bytes from a 16-byte aligned start; both have the same offset in
-// their copy) into the warp's own ring in shared memory, completion on an mbarrier per stage. Elements, lanes and the order of
-// the additions are those of k_cp_corr, so the sums are the same bit for bit; what changes is that no register waits for a
-// load (k_cp_corr: 67 % of the stall samples on the 32 two-byte loads of a symbol, 3.6 TB/s) and a warp has 8 KB in flight
-// instead of 2. Symbols whose aligned copies could leave the recording take the direct loads.
+// their copy) into the warp's own ring in shared memory, completion on an mbarrier per stage. A lane then takes 16 bytes (eight
+// samples) of each copy at a time; the bytes of the first and the last 16 that lie outside the prefix are masked. No register
+// waits for a load (k_cp_corr: 67 % of the stall samples on the 32 two-byte loads of a symbol, 3.6 TB/s), a warp has 8 KB in
+// flight instead of 2, and the sums are exact integers, so the result equals k_cp_corr's. Symbols whose aligned copies could
+// leave the recording take the direct loads.
 constexpr int CPB_STAGES = 4;
 constexpr int CPB_COPY = 1024;
 constexpr int CPB_SMEM = 8 * CPB_STAGES * 2 * CPB_COPY;
@@ -788,7 +856,7 @@ __global__ void __launch_bounds__(256) k_cp_corr_bulk(const FrameDesc * __restri
 {
   extern __shared__ __align__(128) unsigned char cpb_ring[];
   __shared__ unsigned long long cpb_bar[8 * CPB_STAGES];
-  __shared__ float2 red[8];
+  __shared__ CpInt red[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char * ring = cpb_ring + warp * (CPB_STAGES * 2 * CPB_COPY);
   const unsigned ring_s = smem_addr_u32(ring), bar_s = smem_addr_u32(cpb_bar + warp * CPB_STAGES);
@@ -855,42 +923,68 @@ __global__ void __launch_bounds__(256) k_cp_corr_bulk(const FrameDesc * __restri
 
   for (int fi = blockIdx.x; fi < n_frames; fi += gridDim.x)
   {
-    float2 acc = make_float2(0.0f, 0.0f);
+    CpInt ti = { 0, 0, 0, 0 };
+    const int n_syms = frames[fi].n_syms;
     while (cur.fi == fi)
     {
-      unsigned ra[16], rb[16];
       if (by_copy(cur))
       {
         mbar_wait(bar_s + 8u * (unsigned)stage, (phase_bits >> stage) & 1u);
         phase_bits ^= 1u << stage;
-        const unsigned off = (unsigned)((unsigned long long)(cur.iq + 2 * first_sample(cur)) & 15ull);
-        const unsigned short * sp = reinterpret_cast<const unsigned short *>(ring + stage * 2 * CPB_COPY + off) + lane;
+        const int off = (int)((unsigned long long)(cur.iq + 2 * first_sample(cur)) & 15ull); // the prefix is bytes [off, off + 1008) of a copy
+        const uint4 * sp = reinterpret_cast<const uint4 *>(ring + stage * 2 * CPB_COPY) + lane;
+        uint4 va[2], vb[2];
 #pragma unroll
-        for (int k = 0; k < 16; k++)
+        for (int it = 0; it < 2; it++) { vb[it] = sp[32 * it]; va[it] = sp[32 * it + CPB_COPY / 16]; }
+        if (lane == 0)
         {
-          if (lane + 32 * k < T_G) { ra[k] = sp[32 * k + CPB_COPY / 2]; rb[k] = sp[32 * k]; }
-          else { ra[k] = 0; rb[k] = 0; }
+          // bytes [0, off) of the first 16 (off is even)
+          unsigned * w = reinterpret_cast<unsigned *>(&va[0]);
+          unsigned * u = reinterpret_cast<unsigned *>(&vb[0]);
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+          {
+            const int drop = min(max(off - 4 * j, 0), 4); // leading bytes of word j that precede the prefix
+            const unsigned m = drop >= 4 ? 0u : 0xffffffffu << (8 * drop);
+            w[j] &= m;
+            u[j] &= m;
+          }
+        }
+        if (lane == 31)
+        {
+          // bytes [off - 16 + 16, 16) of the last 16, i.e. those from 1008 + off on: keep the first `off` bytes
+          unsigned * w = reinterpret_cast<unsigned *>(&va[1]);
+          unsigned * u = reinterpret_cast<unsigned *>(&vb[1]);
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+          {
+            const int keep = min(max(off - 4 * j, 0), 4);
+            const unsigned m = keep >= 4 ? 0xffffffffu : ~(0xffffffffu << (8 * keep));
+            w[j] &= m;
+            u[j] &= m;
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < 2; it++)
+        {
+          cp_int_add(ti, va[it].x, vb[it].x);
+          cp_int_add(ti, va[it].y, vb[it].y);
+          cp_int_add(ti, va[it].z, vb[it].z);
+          cp_int_add(ti, va[it].w, vb[it].w);
         }
       }
       else
       {
         const unsigned short * pp = reinterpret_cast<const unsigned short *>(cur.iq) + first_sample(cur) + lane;
+        unsigned ra[16], rb[16];
 #pragma unroll
         for (int k = 0; k < 16; k++)
         {
           if (lane + 32 * k < T_G) { ra[k] = pp[32 * k + T_U]; rb[k] = pp[32 * k]; }
           else { ra[k] = 0; rb[k] = 0; }
         }
-      }
 #pragma unroll
-      for (int k = 0; k < 16; k++)
-      {
-        if (lane + 32 * k < T_G)
-        {
-          const float2 a = to_cf(ra[k]), b = to_cf(rb[k]);
-          acc.x += a.x * b.x + a.y * b.y;
-          acc.y += a.y * b.x - a.x * b.y;
-        }
+        for (int k = 0; k < 16; k++) cp_int_add(ti, ra[k], rb[k]);
       }
       // the stage is free again: every lane has its values in registers
       __syncwarp();
@@ -900,16 +994,10 @@ __global__ void __launch_bounds__(256) k_cp_corr_bulk(const FrameDesc * __restri
       advance(cur);
       stage = stage + 1 == CPB_STAGES ? 0 : stage + 1;
     }
-    acc.x = warp_sum(acc.x);
-    acc.y = warp_sum(acc.y);
-    if (lane == 0) red[warp] = acc;
+    ti.p1 = warp_sum_int(ti.p1); ti.p2 = warp_sum_int(ti.p2); ti.s1 = warp_sum_int(ti.s1); ti.s2 = warp_sum_int(ti.s2);
+    if (lane == 0) red[warp] = ti;
     __syncthreads();
-    if (threadIdx.x == 0)
-    {
-      float2 s = red[0];
-      for (int w = 1; w < 8; w++) { s.x += red[w].x; s.y += red[w].y; }
-      cp[fi] = s;
-    }
+    if (threadIdx.x == 0) cp[fi] = cp_int_finish(red, n_syms);
     __syncthreads();
   }
 }

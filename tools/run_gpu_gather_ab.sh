@@ -1,13 +1,12 @@
 #!/bin/bash
-# usage: bash tools/run_gpu_gather_ab.sh <tag>  -- GPU parity tests, then the bench with the first form of the gather (k_vit_gather, two code
-# words per warp in flight) and with the default one (k_vit_gather_kb)
+# usage: [AB_VAR=DABSTAR_TPC_PIPE AB_VALUES="0 1"] bash tools/run_gpu_gather_ab.sh <tag>  -- GPU parity tests, then the bench once per value of a switch
 TAG=${1:-ab}
 cd $GRAFT_REPO_ROOT
 O=gpurun_out/${TAG}
 timeout 900 python -m pytest tests -m gpu -x -q > ${O}_tests.log 2>&1; echo "tests exit $?" >> ${O}_tests.log
 tail -4 ${O}_tests.log
-for b in 2 0; do
-  DABSTAR_GATHER_BATCH=$b timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > ${O}_bench_gather$b.json 2> ${O}_bench_gather$b.err
+for b in ${AB_VALUES:-2 0}; do
+  env ${AB_VAR:-DABSTAR_GATHER_BATCH}=$b timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > ${O}_bench_gather$b.json 2> ${O}_bench_gather$b.err
   python - ${O}_bench_gather$b.json $b <<'PY'
 import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])

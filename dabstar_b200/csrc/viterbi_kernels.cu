@@ -558,37 +558,45 @@ __global__ void __launch_bounds__(32) k_vit_tpc(const VitJob * __restrict__ jobs
   }
 
   // ---- chain back from state 0; decoded bit i is the decision read at step i + 6 (viterbi_scalar.h:84-93).
-  // The decision words of the next 8 steps are loaded while the current 8 are walked (the addresses do not depend on
-  // the state, only the walk itself is serial).
+  // The decision words of the next CB steps are loaded while the current CB are walked (the addresses do not depend on
+  // the state, only the walk itself is serial); the forward pass's registers are free here, so CB = 16 words of 8 bytes.
   unsigned y = 0;
   const bool scramble = (job.flags & VIT_FLAG_PRBS) != 0;
   uint8_t * out = out_bits + job.out;
-  if ((((unsigned long long)(uintptr_t)out | (unsigned long long)n_bits) & 7) == 0 && n_bits >= 8)
+  constexpr int CB = 16;
+  if (((unsigned long long)(uintptr_t)out & 7) == 0 && n_bits % CB == 0 && n_bits >= CB)
   {
-    unsigned long long w[8], wn[8];
+    unsigned long long w[CB], wn[CB];
 #pragma unroll
-    for (int q = 0; q < 8; q++) w[q] = vp[(size_t)(n_bits - 8 + 6 + q) * stride];
-    int ty7 = (n_bits + 5) % 5; // type of step i + 13 for i = n_bits - 8
+    for (int q = 0; q < CB; q++) w[q] = vp[(size_t)(n_bits - CB + 6 + q) * stride];
+    int ty7 = (n_bits + 5) % 5; // type of step i + CB + 5 for i = n_bits - CB
 #pragma unroll 1
-    for (int i = n_bits - 8; i >= 0; i -= 8)
+    for (int i = n_bits - CB; i >= 0; i -= CB)
     {
-      const int ip = i >= 8 ? i - 8 : 0;
+      const int ip = i >= CB ? i - CB : 0;
 #pragma unroll
-      for (int q = 0; q < 8; q++) wn[q] = vp[(size_t)(ip + 6 + q) * stride];
-      unsigned lo = 0, hi = 0;
+      for (int q = 0; q < CB; q++) wn[q] = vp[(size_t)(ip + 6 + q) * stride];
+      unsigned b[CB / 4];
+#pragma unroll
+      for (int q = 0; q < CB / 4; q++) b[q] = 0;
       int ty = ty7;
 #pragma unroll
-      for (int q = 7; q >= 0; q--)
+      for (int q = CB - 1; q >= 0; q--)
       {
         const unsigned k = tpc_traceback_step(w[q], pos_lut[ty][y], y);
-        if (q >= 4) hi |= k << (8 * (q - 4)); else lo |= k << (8 * q);
+        b[q >> 2] |= k << (8 * (q & 3));
         ty = ty == 0 ? 4 : ty - 1;
       }
       ty7 = ty;
-      if (scramble) { const uint2 pw = *reinterpret_cast<const uint2 *>(prbs + i); lo ^= pw.x; hi ^= pw.y; }
-      *reinterpret_cast<uint2 *>(out + i) = make_uint2(lo, hi);
 #pragma unroll
-      for (int q = 0; q < 8; q++) w[q] = wn[q];
+      for (int q = 0; q < CB / 8; q++)
+      {
+        unsigned lo = b[2 * q], hi = b[2 * q + 1];
+        if (scramble) { const uint2 pw = *reinterpret_cast<const uint2 *>(prbs + i + 8 * q); lo ^= pw.x; hi ^= pw.y; }
+        *reinterpret_cast<uint2 *>(out + i + 8 * q) = make_uint2(lo, hi);
+      }
+#pragma unroll
+      for (int q = 0; q < CB; q++) w[q] = wn[q];
     }
   }
   else

@@ -2579,8 +2579,11 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       // bits), one copy per group into pinned memory on the copy stream; dabstar_decoder_msc_copy unpacks a sub-channel on
       // request. One pageable copy per sub-channel and recording of the bits as bytes cost 220 ms per 10 000 full-ensemble
       // frames, 7 x the kernels.
-      for (auto & kv : groups)
+      // Longest code words first: a group's copy runs under the next group's kernels, only the last group's copy is exposed, and
+      // the groups of long code words carry most of the payload (full ensemble: 46 of 141 MB per 9984 frames in the 128 kbit/s group).
+      for (auto it = groups.rbegin(); it != groups.rend(); ++it)
       {
+        auto & kv = *it;
         Group & g = kv.second;
         {
           const VitSpanHook hook{ msc_span_mark, dec }; // one span per kernel (gather / trellis) instead of one around the launch

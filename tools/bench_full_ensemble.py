@@ -52,13 +52,14 @@ def main():
             dp.run_ptrs(ptrs, ns, api.MEM_DEVICE)
             for k, (ms, ln) in dp.stage_ms().items():
                 acc[k] = acc.get(k, 0.0) + ms
+            gm, tm = dp.msc_kernel_ms()
         e1.record(stream)
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     frames = sum(dp.result(r).n_frames for r in range(args.recordings))
     info_bits = frames * (3072 + 4 * 24 * sum(s.bit_rate for s in subch))
     print(json.dumps({"workload": "configs[2] full ensemble, 18 sub-channels (864 CU)", "recordings": args.recordings, "frames_per_step": frames,
-                      "ms_per_step": ms, "frames_per_s": frames / ms * 1e3, "decoded_mbit_s": info_bits / ms / 1e3, "payload_equals_transmitted": bool(ok),
+                      "ms_per_step": ms, "frames_per_s": frames / ms * 1e3, "decoded_mbit_s": info_bits / ms / 1e3, "payload_equals_transmitted": bool(ok), "msc_gather_ms": gm, "msc_trellis_ms": tm,
                       "stages_ms": {k: v / args.steps for k, v in acc.items() if v > 0}}))
 
 

@@ -2119,9 +2119,15 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
     if (int e = sync_profiles(ctx)) return e;
     if (int e = reserve_viterbi_ws(ctx, 4 * n_desc, FIC_OUT + 6)) return e;
     {
-      static const int chunks_env = getenv("DABSTAR_CHUNKS") ? atoi(getenv("DABSTAR_CHUNKS")) : 1;
-      static const int fft_ctas_env = getenv("DABSTAR_FFT_OVERLAP_CTAS") ? atoi(getenv("DABSTAR_FFT_OVERLAP_CTAS")) : 2;
-      const int nch = n_desc >= 1024 ? std::max(1, std::min(chunks_env, 16)) : 1; // small windows (acquisition): one chunk
+      // (read per run: the parity tests switch the chunking on for small windows)
+      const int chunks_env = getenv("DABSTAR_CHUNKS") ? atoi(getenv("DABSTAR_CHUNKS")) : 1;
+      const int fft_ctas_env = getenv("DABSTAR_FFT_OVERLAP_CTAS") ? atoi(getenv("DABSTAR_FFT_OVERLAP_CTAS")) : 2;
+      const int chunk_min_env = getenv("DABSTAR_CHUNK_MIN_FRAMES") ? atoi(getenv("DABSTAR_CHUNK_MIN_FRAMES")) : 1024;
+      // DABSTAR_CHUNK_MODE = 1: the FFT of the whole window first, then the demapper chunk by chunk on the same stream with the
+      // FIC decoder of chunk c on the second stream, next to the demapper of chunk c + 1 (0: FFT of chunk c + 1 next to the
+      // demapper of chunk c, as described above)
+      const bool fic_beside_demap = getenv("DABSTAR_CHUNK_MODE") && atoi(getenv("DABSTAR_CHUNK_MODE")) == 1;
+      const int nch = n_desc >= chunk_min_env ? std::max(1, std::min(chunks_env, 16)) : 1; // small windows (acquisition): one chunk
       // chunk-major copy of the descriptors: what the FFT and the FIC decoder of a chunk walk (the demapper indexes the
       // recording-major array, where the frames of a recording and their spectra are consecutive)
       std::vector<int> chunk_off((size_t)nch + 1, 0);
@@ -2219,6 +2225,29 @@ static int decoder_run_pass(dabstar_decoder * dec, const void * const * iq, cons
       cudaStream_t sb = nch > 1 ? dec->heavy_stream : st; // demapper + FIC decoder of a chunk
       cudaEvent_t h0 = dec->ev_get(), h1 = dec->ev_get(), hd = nullptr;
       CK(cudaEventRecord(h0, st));
+      if (nch > 1 && fic_beside_demap)
+      {
+        dec->span_begin(ST_FFT, st);
+        CK(launch_fft_frames(st, ctx->tab, d_fdc, n_desc, d_rin, fmt, dec->d_X.as<float2>(), 0, &ctx->launches));
+        dec->span_end(st);
+        for (int c = 0; c < nch; c++)
+        {
+          const int n_c = chunk_off[c + 1] - chunk_off[c];
+          dec->span_begin(ST_DEMAP, st);
+          CK(launch_demap(st, ctx->tab, d_wk + wk_off[c], wk_off[c + 1] - wk_off[c], d_fd, d_tii, dec->d_X.as<float2>(), dec->d_states.as<OfdmStateDev>(), dec->cfg.soft_bit_type,
+                          dec->d_soft.as<int16_t>(), reinterpret_cast<unsigned long long *>(ctx->demap_ring.as<unsigned char>() + ring_off[c]), &ctx->launches));
+          dec->span_end(st);
+          cudaEvent_t ev = dec->ev_get();
+          CK(cudaEventRecord(ev, st));
+          if (c == nch - 1) hd = ev;
+          CK(cudaStreamWaitEvent(sb, ev, 0));
+          dec->span_begin(ST_FIC, sb);
+          CK(launch_viterbi(sb, nullptr, d_fdc + chunk_off[c], 4 * n_c, ctx->d_profiles.as<VitProfile>(), FIC_OUT + 6, dec->d_soft.as<int16_t>(), dec->d_fib.as<uint8_t>(),
+                            ctx->tab.prbs, dec->d_crc.as<uint8_t>(), dec->d_ber.as<int>(), ctx->d_step_tab.as<unsigned>(), ctx->vit_ws.p, ctx->vit_ws.cap, &ctx->launches));
+          dec->span_end(sb);
+        }
+      }
+      else
       for (int c = 0; c < nch; c++)
       {
         const int n_c = chunk_off[c + 1] - chunk_off[c];
@@ -2785,7 +2814,7 @@ extern "C" int dabstar_decoder_frame_info(const dabstar_decoder * dec, int recor
 {
   if (!dec || !out || recording < 0 || recording >= (int)dec->recs.size()) return DABSTAR_E_INVALID;
   const Recording & R = dec->recs[recording];
-  const int n = std::min<int>(cap, (int)R.frames.size());
+  const int n = std::max(0, std::min<int>(cap, (int)R.frames.size()));
   for (int i = 0; i < n; i++) out[i] = R.frames[i];
   return n;
 }
@@ -2838,7 +2867,7 @@ extern "C" int64_t dabstar_decoder_msc_size(const dabstar_decoder * dec, int rec
 extern "C" int64_t dabstar_decoder_msc_copy(const dabstar_decoder * dec, int recording, int sub_ch_id, uint8_t * out, int64_t cap)
 {
   const MscOut * m = find_msc(dec, recording, sub_ch_id);
-  if (!m || !out) return 0;
+  if (!m || !out || cap <= 0) return 0;
   const int64_t n = std::min<int64_t>(cap, (int64_t)m->out_len);
   const uint8_t * p = dec->h_mscp.as<uint8_t>() + m->out_off / 8; // (out_off is a multiple of 8: whole logical frames precede it)
   const int64_t whole = n >> 3;
@@ -2854,9 +2883,9 @@ extern "C" int64_t dabstar_decoder_msc_copy(const dabstar_decoder * dec, int rec
 extern "C" int64_t dabstar_decoder_msc_packed(const dabstar_decoder * dec, int recording, int sub_ch_id, uint8_t * out, int64_t cap)
 {
   const MscOut * m = find_msc(dec, recording, sub_ch_id);
-  if (!m || !out) return 0;
+  if (!m || !out || cap <= 0) return 0; // (a negative cap would reach memcpy as a huge size)
   const int64_t n = std::min<int64_t>(cap, (int64_t)(m->out_len / 8));
-  memcpy(out, dec->h_mscp.as<uint8_t>() + m->out_off / 8, (size_t)n);
+  if (n > 0) memcpy(out, dec->h_mscp.as<uint8_t>() + m->out_off / 8, (size_t)n);
   return n;
 }
 extern "C" int dabstar_decoder_counters(const dabstar_decoder * dec, int recording, int64_t out[8])

@@ -60,7 +60,8 @@ def env_int(name, default):
 def workload_config(args):
     """The `config` object: what is decoded, identical in both arms (everything measured goes into `run`)."""
     return {"workload": f"configs[1] FIC-only decode of a 10k-frame batch: {args.recordings} independent recordings x {args.frames} frames per GPU",
-            "recordings_per_gpu": args.recordings, "frames_per_recording": args.frames, "input": "u8 IQ 2.048 MS/s", "snr_db": args.snr}
+            "recordings_per_gpu": args.recordings, "frames_per_recording": args.frames, "input": "u8 IQ 2.048 MS/s", "snr_db": args.snr,
+            "l2": f"no flush between steps: the inputs of a step ({args.recordings * args.frames * 196608 * 2 / 1e9:.1f} GB per GPU) and its intermediates exceed the 126 MB L2"}
 
 
 # ---------------------------------------------------------------------------------------------- CPU arms

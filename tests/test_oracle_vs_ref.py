@@ -199,3 +199,35 @@ def test_whole_chain_other_soft_bit_types(oracle, refo, soft_type):
     for f in range(a.n_frames):
         d = np.abs(a.soft_bits(f).astype(np.int32) - b.soft_bits(f).astype(np.int32))
         assert (d > 1).mean() <= 1e-4, (f, (d > 1).mean())
+
+
+def test_phase_reference_stage_functions(oracle, refo):
+    """PhaseReference::correlate_with_phase_ref_and_find_max_peak (phasereference.cpp:87-213) and
+    estimate_carrier_offset_from_sync_symbol_0 (:223-280) called directly on the reference's object and on the restatement:
+    timing offsets across the search range, both thresholds, first / strongest peak, two echoes, noise only, all zeros;
+    carrier offsets up to +-34 kHz incl. fractional ones and a symbol without a PRS."""
+    rng = np.random.default_rng(7)
+    base = 2656  # first sample of the PRS cyclic prefix in frame 0
+    for snr in (20.0, 6.0, 0.0):
+        rec = synth.generate(2, seed=int(60 + snr), snr_db=snr, fmt=synth.FMT_CF32, lead_samples=0, tail_samples=0)
+        echo = rec.iq.copy()
+        echo[37:] += 0.8 * rec.iq[:-37]  # a second path 37 samples later: two candidates
+        for src in (rec.iq, echo):
+            for off in (0, 1, 100, 250, 254, 400, 503):
+                w = src[base + off: base + off + 2048]
+                for thr in (3.0, 6.0):
+                    for strongest in (0, 1):
+                        assert oracle.phaseref_correlate(w, thr, strongest) == refo.phaseref_correlate(w, thr, strongest), (snr, off, thr, strongest)
+        n = np.arange(2048)
+        for cfo in (0.0, 1000.0, -3000.0, 2400.0, 2499.0, 17000.0, -34000.0, 34400.0, 123.0):
+            sym0 = (rec.iq[base + 504: base + 504 + 2048] * np.exp(2j * np.pi * cfo * n / 2048000.0)).astype(np.complex64)
+            X = refo.fft2048(sym0, -1)
+            a, b = oracle.phaseref_estimate_offset(X), refo.phaseref_estimate_offset(X)
+            assert abs(a - b) <= 1, (snr, cfo, a, b)  # (int)(offset * 1000): a last-bit difference may move the truncation by one
+    noise = (rng.normal(size=2048) + 1j * rng.normal(size=2048)).astype(np.complex64)
+    zeros = np.zeros(2048, np.complex64)
+    for thr in (3.0, 6.0):
+        for strongest in (0, 1):
+            assert oracle.phaseref_correlate(noise, thr, strongest) == refo.phaseref_correlate(noise, thr, strongest)  # (3 x the mean is within reach of noise)
+        assert oracle.phaseref_correlate(zeros, thr) == refo.phaseref_correlate(zeros, thr) == -1  # phasereference.cpp:126-129
+    assert oracle.phaseref_estimate_offset(noise) == refo.phaseref_estimate_offset(noise)

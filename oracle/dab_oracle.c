@@ -1061,7 +1061,7 @@ typedef struct
 
   frame_rec * frames;
   int n_frames, cap_frames;
-  int dip_found, no_dip;
+  int dip_found, no_dip, sync_attempts;
   int cif_hi, cif_lo;         /* cfg.track_cif: what a real FIB decoder would hold (0, 0 until the first FIG 0/0) */
   double seconds;
 } chain_t;
@@ -1085,7 +1085,7 @@ static int read_samples(chain_t * c, cf32 * dst, int n, float freq_hz)
   return 1;
 }
 
-/* returns 1 established, 0 no dip / no end of dip, -1 end of data */
+/* returns 1 established, 0 no dip, 2 no end of dip, -1 end of data (timesyncer.cpp:40-90) */
 static int time_sync(chain_t * c)
 {
   float env[4096];
@@ -1113,7 +1113,7 @@ static int time_sync(chain_t * c)
     env[idx] = cabs32(s);
     level += env[idx] - env[(idx - 50) & 4095];
     idx = (idx + 1) & 4095;
-    if (++counter > T_NULL + 50 + 20) return 0;
+    if (++counter > T_NULL + 50 + 20) return 2;
   }
   return 1;
 }
@@ -1354,7 +1354,11 @@ void * dabo_chain_run(const float * iq, int64_t n_samples, const dabo_chain_cfg 
       thr = cfg->threshold;
       const int r = time_sync(c);
       if (r < 0) break;
-      if (r == 1) { c->dip_found++; state = EVAL_SYNC; } else c->no_dip++;
+      /* _state_wait_for_time_sync_marker (dab_processor.cpp:416-442): signal_no_dip_sync_found goes out once per eight
+         NO_DIP_FOUND results in a row; NO_END_OF_DIP_FOUND and a success restart the count */
+      if (r == 1) { c->dip_found++; c->sync_attempts = 0; state = EVAL_SYNC; }
+      else if (r == 2) c->sync_attempts = 0;
+      else if (++c->sync_attempts >= 8) { c->sync_attempts = 0; c->no_dip++; }
       clock_err = 0.0f;
     }
     else if (state == EVAL_SYNC)

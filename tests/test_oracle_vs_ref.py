@@ -231,3 +231,47 @@ def test_phase_reference_stage_functions(oracle, refo):
             assert oracle.phaseref_correlate(noise, thr, strongest) == refo.phaseref_correlate(noise, thr, strongest)  # (3 x the mean is within reach of noise)
         assert oracle.phaseref_correlate(zeros, thr) == refo.phaseref_correlate(zeros, thr) == -1  # phasereference.cpp:126-129
     assert oracle.phaseref_estimate_offset(noise) == refo.phaseref_estimate_offset(noise)
+
+
+T_F = 196608
+
+
+def _damaged_recordings():
+    """A 12-frame recording damaged in the middle in ways that make DabProcessor lose or shift its synchronisation
+    (dab_processor.cpp:144-182: PRS peak below threshold -> back to the time syncer; :205-265: AFC and clock loops)."""
+    rng = np.random.default_rng(5)
+    rec = synth.generate(12, seed=71, snr_db=15.0, cfo_hz=300.0, fmt=synth.FMT_CF32)
+    iq = rec.iq
+    s = 60000 + 4 * T_F + 5000
+    noise = ((rng.normal(size=2 * T_F) + 1j * rng.normal(size=2 * T_F)) * 0.25 / np.sqrt(2)).astype(np.complex64)
+    x = iq.copy(); x[s:s + 2 * T_F] = noise
+    yield "noise burst of two frames", x
+    yield "1000 samples dropped", np.concatenate([iq[:s], iq[s + 1000:]])
+    yield "7 samples dropped", np.concatenate([iq[:s], iq[s + 7:]])
+    x = iq.copy(); n = np.arange(x.size - s); x[s:] *= np.exp(2j * np.pi * 2700.0 * n / 2048000.0).astype(np.complex64)
+    yield "carrier jumps by 2.7 kHz", x
+    x = iq.copy(); x[s:s + 3 * T_F] *= 0.02
+    yield "deep fade of three frames", x
+    x = iq.copy(); x[s:s + T_F // 2] = 0
+    yield "half a frame of zeros", x
+    x = iq.copy(); x[s:] = 0
+    yield "signal ends, zeros follow", x
+
+
+def test_synchronisation_loss_and_recovery(oracle, refo):
+    """The control loops of DabProcessor::run under damage: the restatement follows the reference's own DabProcessor frame for frame
+    (positions, integer-Hz derotation, FIC CRCs, soft bits) and signal for signal (dip found / no dip found, reads, stream position)."""
+    seen_resync = False
+    for name, iq in _damaged_recordings():
+        a = oracle.chain_run(iq, scan_mode=1, tap_soft=True)
+        b = refo.chain_run(iq, scan_mode=1, tap_soft=True)
+        assert a.n_frames == b.n_frames, name
+        assert [i.sym0_pos for i in a.info] == [i.sym0_pos for i in b.info], name
+        assert [round(i.fbb_null) for i in a.info] == [round(i.fbb_null) for i in b.info], name
+        assert np.array_equal(a.fic_valid, b.fic_valid) and np.array_equal(a.fib_bits, b.fib_bits), name
+        assert np.array_equal(a.counters[:4], b.counters[:4]), (name, a.counters[:4], b.counters[:4])
+        for f in range(a.n_frames):
+            d = np.abs(a.soft_bits(f).astype(np.int32) - b.soft_bits(f).astype(np.int32))
+            assert (d > 1).mean() <= 1e-4, (name, f)
+        seen_resync = seen_resync or a.counters[0] > 1
+    assert seen_resync  # at least one of the cases went back through the time syncer

@@ -275,3 +275,20 @@ def test_synchronisation_loss_and_recovery(oracle, refo):
             assert (d > 1).mean() <= 1e-4, (name, f)
         seen_resync = seen_resync or a.counters[0] > 1
     assert seen_resync  # at least one of the cases went back through the time syncer
+
+
+@pytest.mark.parametrize("cfo,snr,seed", [(0.0, 20.0, 20), (12345.0, 12.0, 12), (-800.0, 8.0, 8), (300.0, 15.0, 71)])
+def test_control_loop_values_per_frame(oracle, refo, cfo, snr, seed):
+    """What DabProcessor carries from frame to frame (dab_processor.cpp:191-265), frame by frame: PRS start index, the clock-error
+    IIR and the FIC success ratio identical; the AFC frequencies (fSync, the fBB of each frame segment) within 1e-3 Hz and the
+    cyclic-prefix phase within 1e-5 rad of the reference's -ffast-math floats (measured: 6e-5 Hz, 3.4e-7 rad)."""
+    rec = synth.generate(10, seed=seed, snr_db=snr, cfo_hz=cfo, fmt=synth.FMT_CF32)
+    a, b = oracle.chain_run(rec.iq, scan_mode=1), refo.chain_run(rec.iq, scan_mode=1)
+    assert a.n_frames == b.n_frames >= 8
+    get = lambda res, f: np.array([getattr(i, f) for i in res.info], dtype=np.float64)
+    for f in ("sym0_pos", "start_index", "clock_err", "fic_ratio_before", "fic_ratio_after"):
+        assert np.array_equal(get(a, f), get(b, f)), f
+    for f in ("fbb_sym0", "fbb_data", "fbb_null", "fsync"):
+        assert np.abs(get(a, f) - get(b, f)).max() <= 1e-3, f
+        assert np.array_equal(np.round(get(a, f)), np.round(get(b, f))), f  # what the derotation uses: integer Hz
+    assert np.abs(get(a, "phase_cp") - get(b, "phase_cp")).max() <= 1e-5

@@ -292,3 +292,31 @@ def test_control_loop_values_per_frame(oracle, refo, cfo, snr, seed):
         assert np.abs(get(a, f) - get(b, f)).max() <= 1e-3, f
         assert np.array_equal(np.round(get(a, f)), np.round(get(b, f))), f  # what the derotation uses: integer Hz
     assert np.abs(get(a, "phase_cp") - get(b, "phase_cp")).max() <= 1e-5
+
+
+@pytest.mark.parametrize("strongest,threshold", [(1, 3.0), (0, 4.5), (1, 6.0)])
+def test_whole_chain_with_an_echo_and_sync_options(oracle, refo, strongest, threshold):
+    """set_sync_on_strongest_peak and the correlation threshold through the whole chain, on a two-path channel (an echo 45 samples
+    late and 2 dB stronger than the first path: first-peak and strongest-peak synchronisation settle on different positions)."""
+    sc = [synth.SubChannel(3, 100, 54, 0, 2, 72)]
+    rec = synth.generate(8, seed=91, snr_db=16.0, cfo_hz=-150.0, subch=sc, fmt=synth.FMT_CF32)
+    iq = rec.iq.copy()
+    iq[45:] += 1.26 * rec.iq[:-45]
+    a = oracle.chain_run(iq, synth.subch_table(sc), 1, threshold=threshold, strongest_peak=strongest)
+    b = refo.chain_run(iq, synth.subch_table(sc), 1, threshold=threshold, strongest_peak=strongest)
+    assert a.n_frames == b.n_frames >= 6
+    assert [(i.sym0_pos, i.start_index, round(i.fbb_null)) for i in a.info] == [(i.sym0_pos, i.start_index, round(i.fbb_null)) for i in b.info]
+    assert np.array_equal(a.fic_valid, b.fic_valid) and np.array_equal(a.fib_bits, b.fib_bits)
+    assert np.array_equal(a.msc[3], b.msc[3])
+    assert np.array_equal(a.counters[:4], b.counters[:4])
+
+
+def test_strongest_peak_changes_the_position(oracle):
+    rec = synth.generate(6, seed=91, snr_db=16.0, fmt=synth.FMT_CF32)
+    iq = rec.iq.copy()
+    iq[45:] += 1.26 * rec.iq[:-45]
+    first = oracle.chain_run(iq, scan_mode=1, strongest_peak=0)
+    strong = oracle.chain_run(iq, scan_mode=1, strongest_peak=1)
+    assert first.n_frames == strong.n_frames >= 4
+    d = [s.sym0_pos - f.sym0_pos for f, s in zip(first.info, strong.info)]
+    assert all(x == 45 for x in d[1:]), d  # the option is live: the strongest path is the late one
